@@ -1,0 +1,123 @@
+/* b2p — B200-native (sm_100a) drop-in for Palace's partial-assembly operator path and the
+ * smoother / multigrid / Krylov loop that drives it.  Plain C ABI: opaque handles, raw pointers
+ * and sizes, no C++/torch types.  Every entry point returns 0 on success or a non-zero code with
+ * a message retrievable through b2p_last_error() (mirrors libCEED's CEED_ERROR_SUCCESS +
+ * CeedGetErrorMessage contract that Palace wraps in PalaceCeedCall,
+ * /root/reference/palace/fem/libceed/ceed.hpp:13-33).
+ *
+ * Ownership: the creator owns a handle and destroys it; host arrays passed in *_desc structs are
+ * copied during the call (CEED_COPY_VALUES semantics, /root/reference/palace/fem/libceed/restriction.cpp:192-204);
+ * the caller owns all vectors; device vector pointers are only used in stream order of the call.
+ * Threading: one caller thread per b2p_ctx (the reference uses exactly one Ceed context on GPU,
+ * /root/reference/palace/fem/libceed/ceed.cpp:35-39). All work is enqueued on the stream given.
+ * There is NO CPU fallback: every entry fails with B2P_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef B2P_H
+#define B2P_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2p_ctx b2p_ctx;       /* device + (optional) NCCL communicator; ~ Ceed + MPI_Comm      */
+typedef struct b2p_geom b2p_geom;     /* geometry q-data of one element block; ~ ceed::CeedGeomFactorData (mesh.cpp:146-209) */
+typedef struct b2p_op b2p_op;         /* one local partially-assembled operator; ~ a CeedOperator sub-operator of ceed::Operator */
+typedef struct b2p_interp b2p_interp; /* element-dense interpolator (P_l, G); ~ AssembleCeedInterpolator (libceed/integrator.cpp:515-548) */
+typedef struct b2p_halo b2p_halo;     /* shared-dof exchange plan; ~ the P / P^T of ParOperator (linalg/rap.cpp:212-222) */
+typedef void *b2p_stream;             /* cudaStream_t */
+
+enum
+{
+  B2P_SUCCESS = 0,
+  B2P_ERR_ARG = 1,
+  B2P_ERR_CUDA = 2,
+  B2P_ERR_UNSUPPORTED = 3,
+  B2P_ERR_NCCL = 4
+};
+
+/* Which bilinear form (selects D at the quadrature points), /root/reference/palace/fem/integ/ *.cpp */
+enum
+{
+  B2P_CURLCURL = 0,      /* CurlCurlIntegrator        -> f_apply_hdiv_33      (integ/curlcurl.cpp:47-52)     */
+  B2P_ND_MASS = 1,       /* VectorFEMassIntegrator    -> f_apply_hcurl_33     (integ/vecfemass.cpp:72-105)   */
+  B2P_CURLCURL_MASS = 2, /* CurlCurlMassIntegrator    -> f_apply_hdivmass_33  (integ/curlcurlmass.cpp:37-44) */
+  B2P_H1_DIFFUSION = 3   /* DiffusionIntegrator       -> f_apply_hcurl_33 on grad (integ/diffusion.cpp:37-42) */
+};
+
+/* ---- context -------------------------------------------------------------------------------- */
+int b2p_ctx_create(int cuda_device, b2p_ctx **out);
+/* Multi-GPU: one process per GPU. `nccl_unique_id` = 128 bytes from b2p_nccl_unique_id() on rank 0,
+ * distributed by the caller (MPI_Bcast in Palace, torch.distributed in the harness). */
+int b2p_nccl_unique_id(void *out128);
+int b2p_ctx_create_dist(int cuda_device, const void *nccl_unique_id, int rank, int nranks, b2p_ctx **out);
+void b2p_ctx_destroy(b2p_ctx *ctx);
+const char *b2p_last_error(b2p_ctx *ctx); /* ctx may be NULL: last error of the calling thread */
+int b2p_ctx_rank(b2p_ctx *ctx);
+int b2p_ctx_nranks(b2p_ctx *ctx);
+int b2p_ctx_sync(b2p_ctx *ctx, b2p_stream s);
+
+/* ---- device memory helpers (so a C/C++ host needs no CUDA runtime of its own) ----------------- */
+int b2p_malloc(b2p_ctx *ctx, size_t bytes, void **dptr);
+int b2p_free(b2p_ctx *ctx, void *dptr);
+int b2p_memcpy_h2d(b2p_ctx *ctx, void *dst, const void *src, size_t bytes, b2p_stream s);
+int b2p_memcpy_d2h(b2p_ctx *ctx, void *dst, const void *src, size_t bytes, b2p_stream s);
+
+/* ---- geometry q-data (replaces Mesh::GetCeedGeomFactorData, fem/mesh.cpp:146-209,321-333) ----- */
+/* Hexahedra of nodal order `mesh_order`; xe[ne][3][(mesh_order+1)^3] element node coordinates
+ * (host, lexicographic tensor nodes, component-major); nodeB/nodeG[q1d][mesh_order+1]: the 1-D nodal
+ * basis and its derivative at the q1d quadrature points; qw1d[q1d]; attr[ne]: 1-based local
+ * attribute. Computes on the device {w detJ, adj(J)^T/detJ} per quadrature point
+ * (qfunctions/33/geom_33_qf.h:9-34). */
+int b2p_geom_create_hex(b2p_ctx *ctx, int ne, int mesh_order, int q1d, const double *xe, const double *nodeB,
+                        const double *nodeG, const double *qw1d, const int32_t *attr, b2p_geom **out);
+/* Prebuilt q-data in the reference layout qdata[ne][11][Q] = {attr, w detJ, adjJt/detJ[9]} (host). */
+int b2p_geom_create_qdata(b2p_ctx *ctx, int ne, int q1d, const double *qdata, b2p_geom **out);
+/* Copy the device q-data back in the reference layout [ne][11][Q] (for parity tests). */
+int b2p_geom_get_qdata(b2p_geom *g, double *qdata_host);
+void b2p_geom_destroy(b2p_geom *g);
+
+/* ---- local operator (replaces ceed::Operator sub-operators, fem/libceed/operator.hpp:32-65) ---- */
+typedef struct
+{
+  int kind;                /* B2P_CURLCURL ... */
+  int p;                   /* element order */
+  int ne;                  /* elements in this block (must equal the geometry's) */
+  int64_t lsize;           /* L-vector size (GetVSize()) */
+  const int32_t *idx;      /* [ne][P] native-order element dofs (InitNativeRestr / InitLexicoRestr) */
+  const int8_t *orient;    /* [ne][P] +1/-1 or NULL (restriction.cpp:290-297) */
+  const int32_t *dof_map;  /* [P] lexicographic -> native, -1-n for a sign flip (TensorBasisElement::GetDofMap()); NULL = identity */
+  const double *Bo;        /* [q1d][p]   open basis at quadrature points (ND only) */
+  const double *Bc;        /* [q1d][p+1] closed basis */
+  const double *Gc;        /* [q1d][p+1] closed basis derivative */
+  const void *coeff_ctx;   /* coefficient context blob, layout of qfunctions/coeff/coeff_qf.h:7-43 (pair ctx for CURLCURL_MASS) */
+  size_t coeff_ctx_bytes;
+  int assemble_qdata;      /* 0: geometry + coefficient applied on the fly (reference default);
+                              1: pre-multiplied symmetric D stored per point (BilinearForm::AssembleQuadratureData) */
+} b2p_op_desc;
+
+int b2p_op_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_op_desc *desc, b2p_op **out);
+/* p-coarsening that shares the fine operator's quadrature, geometry and coefficient
+ * (ceed::CeedOperatorCoarsen, fem/libceed/operator.cpp:525-585): only space fields of desc are read
+ * (p, lsize, idx, orient, dof_map, Bo/Bc/Gc evaluated at the FINE q1d points). */
+int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *coarse_space, b2p_op **out);
+/* y = A x  (ceed::Operator::Mult zero-fills first, operator.cpp:182-190) */
+int b2p_op_apply(b2p_op *op, const double *x, double *y, b2p_stream s);
+/* y += A x (ceed::Operator::AddMult, a == 1 only, operator.cpp:192-212) */
+int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s);
+/* diag += diag(A) (ceed::Operator::AssembleDiagonal, operator.cpp:116-143) */
+int b2p_op_diag_add(b2p_op *op, double *diag, b2p_stream s);
+/* Replace the coefficient context without touching geometry/restriction (driven sweeps re-coefficient
+ * per frequency, drivers/drivensolver.cpp:176-198). */
+int b2p_op_set_coeff(b2p_op *op, const void *coeff_ctx, size_t bytes);
+int64_t b2p_op_lsize(b2p_op *op);
+/* Algorithmic HBM bytes one apply moves (x read + y write + indices + q-data), for roofline reports. */
+int64_t b2p_op_algorithmic_bytes(b2p_op *op);
+void b2p_op_destroy(b2p_op *op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2P_H */

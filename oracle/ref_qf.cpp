@@ -1,0 +1,69 @@
+// TEST INFRASTRUCTURE ONLY. Builds oracle/_ref/libpalace_qf_ref.so from the reference's OWN
+// QFunction headers where they lie under /root/reference (never copied into this repo):
+//   palace/fem/qfunctions/33/{geom,hdiv,hcurl,hdivmass,hdiv_build,hcurl_build,hdivmass_build}_33_qf.h
+//   palace/fem/qfunctions/apply/apply_33_qf.h
+// behind the minimal libCEED macro shim below. Used only to pin oracle.cpp's restatement of the
+// pointwise arithmetic (tests/test_oracle_ref.py). The libCEED operator/basis/restriction layer and
+// MFEM are un-vendored, so this is the only part of the reference path that compiles here.
+#define CEED_QFUNCTION(name) static inline int name
+#define CEED_QFUNCTION_HELPER static inline
+#define CeedPragmaSIMD
+typedef double CeedScalar;
+typedef int CeedInt;
+
+#include "fem/qfunctions/33/geom_33_qf.h"
+#include "fem/qfunctions/33/hcurl_33_qf.h"
+#include "fem/qfunctions/33/hdiv_33_qf.h"
+#include "fem/qfunctions/33/hdivmass_33_qf.h"
+#include "fem/qfunctions/33/hcurl_build_33_qf.h"
+#include "fem/qfunctions/33/hdiv_build_33_qf.h"
+#include "fem/qfunctions/33/hdivmass_build_33_qf.h"
+#include "fem/qfunctions/apply/apply_33_qf.h"
+
+extern "C"
+{
+// in0 = {attr[Q], qw[Q], J[9][Q]} split as the reference passes them (geom_33_qf.h:12).
+int ref_build_geom_factor_33(int Q, const double *attr, const double *qw, const double *J, double *qdata)
+{
+  const double *in[3] = {attr, qw, J};
+  double *out[1] = {qdata};
+  return f_build_geom_factor_33(nullptr, Q, in, out);
+}
+int ref_apply_hcurl_33(void *ctx, int Q, const double *qdata, const double *u, double *v)
+{
+  const double *in[2] = {qdata, u};
+  double *out[1] = {v};
+  return f_apply_hcurl_33(ctx, Q, in, out);
+}
+int ref_apply_hdiv_33(void *ctx, int Q, const double *qdata, const double *u, double *v)
+{
+  const double *in[2] = {qdata, u};
+  double *out[1] = {v};
+  return f_apply_hdiv_33(ctx, Q, in, out);
+}
+int ref_apply_hdivmass_33(void *ctx, int Q, const double *qdata, const double *u, const double *curlu, double *v,
+                          double *curlv)
+{
+  const double *in[3] = {qdata, u, curlu};
+  double *out[2] = {v, curlv};
+  return f_apply_hdivmass_33(ctx, Q, in, out);
+}
+int ref_build_hcurl_33(void *ctx, int Q, const double *qdata, double *qd)
+{
+  const double *in[1] = {qdata};
+  double *out[1] = {qd};
+  return f_build_hcurl_33(ctx, Q, in, out);
+}
+int ref_build_hdiv_33(void *ctx, int Q, const double *qdata, double *qd)
+{
+  const double *in[1] = {qdata};
+  double *out[1] = {qd};
+  return f_build_hdiv_33(ctx, Q, in, out);
+}
+int ref_build_hdivmass_33(void *ctx, int Q, const double *qdata, double *qd)
+{
+  const double *in[1] = {qdata};
+  double *out[1] = {qd};
+  return f_build_hdivmass_33(ctx, Q, in, out);
+}
+}

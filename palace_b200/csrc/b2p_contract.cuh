@@ -1,0 +1,69 @@
+// Shared-memory tensor-contraction helpers for the sum-factorised element kernels.
+#pragma once
+
+namespace b2p
+{
+
+// One pencil of a 3-D tensor contraction along axis AX.
+//   in  has dims (D0, D1, D2), x fastest; the contracted axis has NIN entries and becomes NOUT.
+//   out[o] (+)= sgn * sum_i M[o*mso + i*msi] * in[i]
+template <int AX, int D0, int D1, int D2, int NIN, int NOUT, bool ACC>
+__device__ __forceinline__ void pencil(int r, const double *__restrict__ in, double *__restrict__ out,
+                                       const double *__restrict__ M, int mso, int msi, double sgn)
+{
+  static_assert((AX == 0 ? D0 : AX == 1 ? D1 : D2) == NIN, "axis size mismatch");
+  int ibase, obase, istr, ostr;
+  if (AX == 0)
+  {
+    ibase = r * D0;  // r = j + k*D1
+    obase = r * NOUT;
+    istr = ostr = 1;
+  }
+  else if (AX == 1)
+  {
+    const int i = r % D0, k = r / D0;
+    ibase = i + k * D0 * D1;
+    obase = i + k * D0 * NOUT;
+    istr = ostr = D0;
+  }
+  else
+  {
+    ibase = obase = r;  // r = i + j*D0
+    istr = ostr = D0 * D1;
+  }
+  double v[NIN];
+#pragma unroll
+  for (int i = 0; i < NIN; i++) v[i] = in[ibase + i * istr];
+#pragma unroll
+  for (int o = 0; o < NOUT; o++)
+  {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NIN; i++) s += M[o * mso + i * msi] * v[i];
+    if (ACC)
+      out[obase + o * ostr] += sgn * s;
+    else
+      out[obase + o * ostr] = sgn * s;
+  }
+}
+
+template <int AX, int D0, int D1, int D2>
+struct NPencil
+{
+  static constexpr int value = (AX == 0 ? D1 * D2 : AX == 1 ? D0 * D2 : D0 * D1);
+};
+
+// Block-wide contraction over NEB elements; `in`/`out` are per-element arrays with strides.
+template <int AX, int D0, int D1, int D2, int NIN, int NOUT, bool ACC, int NEB, int NT>
+__device__ __forceinline__ void contract(const double *in, int in_estride, double *out, int out_estride,
+                                         const double *M, int mso, int msi, double sgn)
+{
+  constexpr int NP = NPencil<AX, D0, D1, D2>::value;
+  for (int w = threadIdx.x; w < NEB * NP; w += NT)
+  {
+    const int e = w / NP, r = w % NP;
+    pencil<AX, D0, D1, D2, NIN, NOUT, ACC>(r, in + e * in_estride, out + e * out_estride, M, mso, msi, sgn);
+  }
+}
+
+}  // namespace b2p

@@ -1,0 +1,528 @@
+// Context, errors, device memory helpers, geometry q-data and operator construction for the C ABI.
+#include <cstring>
+#include <mutex>
+
+#include "b2p_internal.hpp"
+#include "b2p_qf.cuh"
+
+namespace b2p
+{
+
+static thread_local std::string tls_error;
+
+void set_error(b2p_ctx *ctx, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  tls_error = buf;
+  if (ctx) ctx->last_error = buf;
+}
+
+template <typename T>
+int upload(b2p_ctx *ctx, const T *host, size_t n, T **dptr)
+{
+  *dptr = nullptr;
+  if (n == 0) return B2P_SUCCESS;
+  B2P_CUDA(ctx, cudaMalloc((void **)dptr, n * sizeof(T)));
+  B2P_CUDA(ctx, cudaMemcpy(*dptr, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return B2P_SUCCESS;
+}
+template int upload<double>(b2p_ctx *, const double *, size_t, double **);
+template int upload<int32_t>(b2p_ctx *, const int32_t *, size_t, int32_t **);
+template int upload<int8_t>(b2p_ctx *, const int8_t *, size_t, int8_t **);
+
+namespace
+{
+
+// Geometry factors at quadrature points of order-k hexes (K6 of SURVEY §2d; restates
+// qfunctions/33/geom_33_qf.h:9-34 on the device). One thread per (element, point).
+__global__ void geom_hex_kernel(int ne, int k, int q, const double *__restrict__ xe, const double *__restrict__ B,
+                                const double *__restrict__ G, const double *__restrict__ qw, double *__restrict__ qd)
+{
+  const int n = k + 1, Nn = n * n * n, Q = q * q * q;
+  const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (size_t)ne * Q) return;
+  const int e = (int)(w / Q), iq = (int)(w % Q);
+  const int qx = iq % q, qy = (iq / q) % q, qz = iq / (q * q);
+  double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const double *x = xe + (size_t)e * 3 * Nn;
+  for (int kk = 0; kk < n; kk++)
+    for (int jj = 0; jj < n; jj++)
+      for (int ii = 0; ii < n; ii++)
+      {
+        const int m = ii + n * (jj + n * kk);
+        const double gx = G[qx * n + ii] * B[qy * n + jj] * B[qz * n + kk];
+        const double gy = B[qx * n + ii] * G[qy * n + jj] * B[qz * n + kk];
+        const double gz = B[qx * n + ii] * B[qy * n + jj] * G[qz * n + kk];
+        for (int c = 0; c < 3; c++)
+        {
+          const double xc = x[c * Nn + m];
+          J[c + 0] += xc * gx;
+          J[c + 3] += xc * gy;
+          J[c + 6] += xc * gz;
+        }
+      }
+  double A[9];
+  cofactor33(J, A);
+  const double detJ = J[0] * A[0] + J[1] * A[1] + J[2] * A[2];
+  double *o = qd + (size_t)e * 10 * Q + iq;
+  o[0] = qw[qx] * qw[qy] * qw[qz] * detJ;
+  for (int t = 0; t < 9; t++) o[(1 + t) * Q] = A[t] / detJ;
+}
+
+}  // namespace
+
+int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, const double *d_B, const double *d_G,
+                    const double *d_qw, double *d_qd, cudaStream_t s)
+{
+  const size_t total = (size_t)ne * q1d * q1d * q1d;
+  const int nt = 128;
+  geom_hex_kernel<<<(unsigned)((total + nt - 1) / nt), nt, 0, s>>>(ne, k, q1d, d_xe, d_B, d_G, d_qw, d_qd);
+  B2P_CUDA(ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+
+}  // namespace b2p
+
+using namespace b2p;
+
+extern "C"
+{
+
+int b2p_ctx_create(int cuda_device, b2p_ctx **out)
+{
+  if (!out) return B2P_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+  {
+    set_error(nullptr, "b2p_ctx_create: no CUDA device (%s); there is no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return B2P_ERR_CUDA;
+  }
+  B2P_CHECK(nullptr, cuda_device >= 0 && cuda_device < count, B2P_ERR_ARG, "b2p_ctx_create: bad device %d", cuda_device);
+  B2P_CUDA(nullptr, cudaSetDevice(cuda_device));
+  cudaDeviceProp prop;
+  B2P_CUDA(nullptr, cudaGetDeviceProperties(&prop, cuda_device));
+  B2P_CHECK(nullptr, prop.major >= 10, B2P_ERR_CUDA,
+            "b2p_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", cuda_device, prop.major,
+            prop.minor);
+  b2p_ctx *ctx = new b2p_ctx;
+  ctx->device = cuda_device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->red_cap = 4096;
+  B2P_CUDA(nullptr, cudaMalloc((void **)&ctx->d_red, ctx->red_cap * sizeof(double)));
+  B2P_CUDA(nullptr, cudaMallocHost((void **)&ctx->h_red, ctx->red_cap * sizeof(double)));
+  *out = ctx;
+  return B2P_SUCCESS;
+}
+
+const char *b2p_last_error(b2p_ctx *ctx) { return ctx ? ctx->last_error.c_str() : tls_error.c_str(); }
+int b2p_ctx_rank(b2p_ctx *ctx) { return ctx ? ctx->rank : 0; }
+int b2p_ctx_nranks(b2p_ctx *ctx) { return ctx ? ctx->nranks : 1; }
+
+int b2p_ctx_sync(b2p_ctx *ctx, b2p_stream s)
+{
+  B2P_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)s));
+  return B2P_SUCCESS;
+}
+
+int b2p_malloc(b2p_ctx *ctx, size_t bytes, void **dptr)
+{
+  B2P_CUDA(ctx, cudaMalloc(dptr, bytes));
+  return B2P_SUCCESS;
+}
+int b2p_free(b2p_ctx *ctx, void *dptr)
+{
+  B2P_CUDA(ctx, cudaFree(dptr));
+  return B2P_SUCCESS;
+}
+int b2p_memcpy_h2d(b2p_ctx *ctx, void *dst, const void *src, size_t bytes, b2p_stream s)
+{
+  B2P_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)s));
+  return B2P_SUCCESS;
+}
+int b2p_memcpy_d2h(b2p_ctx *ctx, void *dst, const void *src, size_t bytes, b2p_stream s)
+{
+  B2P_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  B2P_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)s));
+  return B2P_SUCCESS;
+}
+
+// ---- geometry ---------------------------------------------------------------------------------
+
+int b2p_geom_create_hex(b2p_ctx *ctx, int ne, int mesh_order, int q1d, const double *xe, const double *nodeB,
+                        const double *nodeG, const double *qw1d, const int32_t *attr, b2p_geom **out)
+{
+  B2P_CHECK(ctx, ctx && out && xe && nodeB && nodeG && qw1d && attr, B2P_ERR_ARG, "b2p_geom_create_hex: null argument");
+  B2P_CHECK(ctx, ne > 0 && mesh_order >= 1 && q1d >= 1, B2P_ERR_ARG, "b2p_geom_create_hex: bad sizes");
+  const int n = mesh_order + 1, Nn = n * n * n, Q = q1d * q1d * q1d;
+  b2p_geom *g = new b2p_geom;
+  g->ctx = ctx;
+  g->ne = ne;
+  g->q1d = q1d;
+  g->Q = Q;
+  double *d_xe = nullptr, *d_B = nullptr, *d_G = nullptr, *d_qw = nullptr;
+  int rc;
+  if ((rc = upload(ctx, xe, (size_t)ne * 3 * Nn, &d_xe))) return rc;
+  if ((rc = upload(ctx, nodeB, (size_t)q1d * n, &d_B))) return rc;
+  if ((rc = upload(ctx, nodeG, (size_t)q1d * n, &d_G))) return rc;
+  if ((rc = upload(ctx, qw1d, (size_t)q1d, &d_qw))) return rc;
+  if ((rc = upload(ctx, attr, (size_t)ne, &g->attr))) return rc;
+  B2P_CUDA(ctx, cudaMalloc((void **)&g->qd, (size_t)ne * 10 * Q * sizeof(double)));
+  if ((rc = launch_geom_hex(ctx, ne, mesh_order, q1d, d_xe, d_B, d_G, d_qw, g->qd, 0))) return rc;
+  B2P_CUDA(ctx, cudaDeviceSynchronize());
+  cudaFree(d_xe);
+  cudaFree(d_B);
+  cudaFree(d_G);
+  cudaFree(d_qw);
+  *out = g;
+  return B2P_SUCCESS;
+}
+
+int b2p_geom_create_qdata(b2p_ctx *ctx, int ne, int q1d, const double *qdata, b2p_geom **out)
+{
+  B2P_CHECK(ctx, ctx && out && qdata && ne > 0 && q1d > 0, B2P_ERR_ARG, "b2p_geom_create_qdata: bad argument");
+  const int Q = q1d * q1d * q1d;
+  std::vector<double> qd((size_t)ne * 10 * Q);
+  std::vector<int32_t> attr(ne);
+  for (int e = 0; e < ne; e++)
+  {
+    attr[e] = (int32_t)qdata[(size_t)e * 11 * Q];
+    std::memcpy(&qd[(size_t)e * 10 * Q], &qdata[((size_t)e * 11 + 1) * Q], sizeof(double) * 10 * Q);
+  }
+  b2p_geom *g = new b2p_geom;
+  g->ctx = ctx;
+  g->ne = ne;
+  g->q1d = q1d;
+  g->Q = Q;
+  int rc;
+  if ((rc = upload(ctx, qd.data(), qd.size(), &g->qd))) return rc;
+  if ((rc = upload(ctx, attr.data(), attr.size(), &g->attr))) return rc;
+  *out = g;
+  return B2P_SUCCESS;
+}
+
+int b2p_geom_get_qdata(b2p_geom *g, double *qdata_host)
+{
+  if (!g || !qdata_host) return B2P_ERR_ARG;
+  const int Q = g->Q;
+  std::vector<double> qd((size_t)g->ne * 10 * Q);
+  std::vector<int32_t> attr(g->ne);
+  B2P_CUDA(g->ctx, cudaMemcpy(qd.data(), g->qd, qd.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  B2P_CUDA(g->ctx, cudaMemcpy(attr.data(), g->attr, attr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int e = 0; e < g->ne; e++)
+  {
+    for (int i = 0; i < Q; i++) qdata_host[(size_t)e * 11 * Q + i] = (double)attr[e];
+    std::memcpy(&qdata_host[((size_t)e * 11 + 1) * Q], &qd[(size_t)e * 10 * Q], sizeof(double) * 10 * Q);
+  }
+  return B2P_SUCCESS;
+}
+
+void b2p_geom_destroy(b2p_geom *g)
+{
+  if (!g) return;
+  if (--g->refcount > 0) return;
+  cudaFree(g->qd);
+  cudaFree(g->attr);
+  delete g;
+}
+
+// ---- operator ---------------------------------------------------------------------------------
+
+namespace
+{
+
+union IntScalar
+{
+  int first;
+  double second;
+};
+
+// Decode a coefficient context (coeff_qf.h:7-43): returns per-attribute material index and the
+// material matrices; n_attr == 0 means "every attribute -> material 0".
+struct DecodedCtx
+{
+  std::vector<int> attr_mat;
+  std::vector<double> mats;  // [n_mat][9]
+  size_t entries = 0;        // entries consumed
+};
+
+bool decode_ctx(const IntScalar *c, size_t avail, DecodedCtx &d)
+{
+  if (avail < 2) return false;
+  const int na = c[0].first;
+  if (na < 0 || (size_t)(2 + na) > avail) return false;
+  d.attr_mat.resize(na);
+  for (int i = 0; i < na; i++) d.attr_mat[i] = c[1 + i].first;
+  const int nm = c[1 + na].first;
+  if (nm <= 0 || (size_t)(2 + na + 9 * (size_t)nm) > avail) return false;
+  d.mats.resize(9 * (size_t)nm);
+  for (size_t i = 0; i < 9 * (size_t)nm; i++) d.mats[i] = c[2 + na + i].second;
+  d.entries = 2 + na + 9 * (size_t)nm;
+  for (int i = 0; i < na; i++)
+    if (d.attr_mat[i] < 0 || d.attr_mat[i] >= nm) return false;
+  return true;
+}
+
+int set_coeff(b2p_op *op, const void *blob, size_t bytes)
+{
+  b2p_ctx *ctx = op->ctx;
+  B2P_CHECK(ctx, blob && bytes % 8 == 0 && bytes >= 16, B2P_ERR_ARG, "coefficient context: bad size %zu", bytes);
+  const IntScalar *c = (const IntScalar *)blob;
+  const size_t avail = bytes / 8;
+  DecodedCtx first, second;
+  B2P_CHECK(ctx, decode_ctx(c, avail, first), B2P_ERR_ARG, "coefficient context: malformed (first part)");
+  const bool pair = (op->kind == B2P_CURLCURL_MASS);
+  if (pair)
+    B2P_CHECK(ctx, decode_ctx(c + first.entries, avail - first.entries, second), B2P_ERR_ARG,
+              "coefficient context: malformed (second part of pair)");
+  // material table: first part then second part
+  std::vector<double> mats = first.mats;
+  const int off2 = (int)(first.mats.size() / 9);
+  mats.insert(mats.end(), second.mats.begin(), second.mats.end());
+  std::vector<int32_t> attr(op->ne), emat(2 * (size_t)op->ne);
+  B2P_CUDA(ctx, cudaMemcpy(attr.data(), op->geom->attr, sizeof(int32_t) * op->ne, cudaMemcpyDeviceToHost));
+  auto lookup = [&](const DecodedCtx &d, int a, int &m) -> bool
+  {
+    if (d.attr_mat.empty())
+    {
+      m = 0;
+      return true;
+    }
+    if (a < 1 || a > (int)d.attr_mat.size()) return false;
+    m = d.attr_mat[a - 1];
+    return true;
+  };
+  for (int e = 0; e < op->ne; e++)
+  {
+    int m0 = 0, m1 = 0;
+    B2P_CHECK(ctx, lookup(first, attr[e], m0), B2P_ERR_ARG, "element %d attribute %d outside coefficient context", e,
+              attr[e]);
+    if (pair)
+    {
+      B2P_CHECK(ctx, lookup(second, attr[e], m1), B2P_ERR_ARG, "element %d attribute %d outside coefficient context", e,
+                attr[e]);
+      m1 += off2;
+    }
+    else
+      m1 = m0;  // single-part kinds read the same table for whichever part they use
+    emat[2 * (size_t)e] = m0;
+    emat[2 * (size_t)e + 1] = m1;
+  }
+  if (op->owns_coeff)
+  {
+    cudaFree(op->mat);
+    cudaFree(op->emat);
+  }
+  op->owns_coeff = true;
+  op->n_mat = (int)(mats.size() / 9);
+  int rc;
+  if ((rc = upload(ctx, mats.data(), mats.size(), &op->mat))) return rc;
+  if ((rc = upload(ctx, emat.data(), emat.size(), &op->emat))) return rc;
+  return B2P_SUCCESS;
+}
+
+int elem_dofs(int kind, int p) { return kind == B2P_H1_DIFFUSION ? (p + 1) * (p + 1) * (p + 1) : 3 * p * (p + 1) * (p + 1); }
+
+// Compose the native-order restriction + orientation with the lexicographic->native dof map
+// (restriction.cpp:134-188,281-297) into one signed lexicographic index array.
+int build_restriction(b2p_op *op, const b2p_op_desc *d)
+{
+  const int P = op->P, ne = op->ne;
+  std::vector<int32_t> lidx((size_t)ne * P);
+  for (int l = 0; l < P; l++)
+  {
+    int nat = d->dof_map ? d->dof_map[l] : l;
+    int sg = 1;
+    if (nat < 0)
+    {
+      nat = -1 - nat;
+      sg = -1;
+    }
+    B2P_CHECK(op->ctx, nat >= 0 && nat < P, B2P_ERR_ARG, "dof_map[%d] out of range", l);
+    for (int e = 0; e < ne; e++)
+    {
+      const int32_t gi = d->idx[(size_t)e * P + nat];
+      B2P_CHECK(op->ctx, gi >= 0 && gi < op->lsize, B2P_ERR_ARG, "idx[%d][%d]=%d outside L-vector of size %lld", e, nat,
+                gi, (long long)op->lsize);
+      const int s = sg * (d->orient ? (int)d->orient[(size_t)e * P + nat] : 1);
+      lidx[(size_t)e * P + l] = (s >= 0) ? gi : (-1 - gi);
+    }
+  }
+  return upload(op->ctx, lidx.data(), lidx.size(), &op->lidx);
+}
+
+int build_tables(b2p_op *op, const b2p_op_desc *d)
+{
+  const int p = op->p, q = op->q1d, n = p + 1;
+  std::vector<double> tab((size_t)q * p + 2 * (size_t)q * n, 0.0);
+  if (op->kind != B2P_H1_DIFFUSION)
+  {
+    B2P_CHECK(op->ctx, d->Bo, B2P_ERR_ARG, "Bo table required for ND operators");
+    std::memcpy(tab.data(), d->Bo, sizeof(double) * q * p);
+  }
+  B2P_CHECK(op->ctx, d->Bc && d->Gc, B2P_ERR_ARG, "Bc/Gc tables required");
+  std::memcpy(tab.data() + (size_t)q * p, d->Bc, sizeof(double) * q * n);
+  std::memcpy(tab.data() + (size_t)q * p + (size_t)q * n, d->Gc, sizeof(double) * q * n);
+  return upload(op->ctx, tab.data(), tab.size(), &op->tab);
+}
+
+int assemble_qdata(b2p_op *op)
+{
+  const int parts = (op->kind == B2P_CURLCURL_MASS) ? 2 : 1;
+  op->aq_ncomp = 9 * parts;
+  if (!op->aq) B2P_CUDA(op->ctx, cudaMalloc((void **)&op->aq, (size_t)op->ne * op->aq_ncomp * op->geom->Q * sizeof(double)));
+  int rc = launch_assemble_qdata(op, 0);
+  if (rc) return rc;
+  B2P_CUDA(op->ctx, cudaDeviceSynchronize());
+  return B2P_SUCCESS;
+}
+
+}  // namespace
+
+int b2p_op_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_op_desc *d, b2p_op **out)
+{
+  B2P_CHECK(ctx, ctx && geom && d && out, B2P_ERR_ARG, "b2p_op_create: null argument");
+  B2P_CHECK(ctx, d->kind >= B2P_CURLCURL && d->kind <= B2P_H1_DIFFUSION, B2P_ERR_ARG, "b2p_op_create: bad kind %d", d->kind);
+  B2P_CHECK(ctx, d->ne == geom->ne, B2P_ERR_ARG, "b2p_op_create: %d elements vs %d in geometry", d->ne, geom->ne);
+  B2P_CHECK(ctx, d->p >= 1 && d->p <= 6 && d->p < geom->q1d && geom->q1d <= 7, B2P_ERR_UNSUPPORTED,
+            "b2p_op_create: unsupported p=%d q1d=%d (hex kernels cover p<=6, p<q1d<=7)", d->p, geom->q1d);
+  B2P_CHECK(ctx, d->idx && d->lsize > 0, B2P_ERR_ARG, "b2p_op_create: missing restriction");
+  b2p_op *op = new b2p_op;
+  op->ctx = ctx;
+  op->geom = geom;
+  geom->refcount++;
+  op->kind = d->kind;
+  op->p = d->p;
+  op->q1d = geom->q1d;
+  op->ne = d->ne;
+  op->P = elem_dofs(d->kind, d->p);
+  op->lsize = d->lsize;
+  op->assembled = d->assemble_qdata;
+  int rc;
+  if ((rc = build_restriction(op, d)) || (rc = build_tables(op, d)) || (rc = set_coeff(op, d->coeff_ctx, d->coeff_ctx_bytes)))
+  {
+    b2p_op_destroy(op);
+    return rc;
+  }
+  if (op->assembled && (rc = assemble_qdata(op)))
+  {
+    b2p_op_destroy(op);
+    return rc;
+  }
+  *out = op;
+  return B2P_SUCCESS;
+}
+
+int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *d, b2p_op **out)
+{
+  B2P_CHECK(fine ? fine->ctx : nullptr, fine && d && out, B2P_ERR_ARG, "b2p_op_coarsen: null argument");
+  b2p_ctx *ctx = fine->ctx;
+  B2P_CHECK(ctx, d->p >= 1 && d->p <= fine->p, B2P_ERR_ARG, "b2p_op_coarsen: coarse p=%d must be <= fine p=%d", d->p, fine->p);
+  B2P_CHECK(ctx, d->idx && d->lsize > 0, B2P_ERR_ARG, "b2p_op_coarsen: missing restriction");
+  b2p_op *op = new b2p_op;
+  op->ctx = ctx;
+  op->geom = fine->geom;
+  fine->geom->refcount++;
+  op->kind = fine->kind;
+  op->p = d->p;
+  op->q1d = fine->q1d;
+  op->ne = fine->ne;
+  op->P = elem_dofs(fine->kind, d->p);
+  op->lsize = d->lsize;
+  op->assembled = fine->assembled;
+  // share coefficient arrays and assembled q-data with the fine operator (kept alive by refcount)
+  op->mat = fine->mat;
+  op->emat = fine->emat;
+  op->n_mat = fine->n_mat;
+  op->aq = fine->aq;
+  op->aq_ncomp = fine->aq_ncomp;
+  op->owns_coeff = false;
+  op->parent = fine;
+  fine->refcount++;
+  int rc;
+  if ((rc = build_restriction(op, d)) || (rc = build_tables(op, d)))
+  {
+    b2p_op_destroy(op);
+    return rc;
+  }
+  *out = op;
+  return B2P_SUCCESS;
+}
+
+int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s)
+{
+  if (!op || !x || !y) return B2P_ERR_ARG;
+  if (op->kind == B2P_H1_DIFFUSION) return launch_h1_hex_apply(op, x, y, (cudaStream_t)s);
+  return launch_nd_hex_apply(op, x, y, (cudaStream_t)s);
+}
+
+int b2p_op_apply(b2p_op *op, const double *x, double *y, b2p_stream s)
+{
+  if (!op || !x || !y) return B2P_ERR_ARG;
+  B2P_CUDA(op->ctx, cudaMemsetAsync(y, 0, sizeof(double) * op->lsize, (cudaStream_t)s));
+  return b2p_op_apply_add(op, x, y, s);
+}
+
+int b2p_op_diag_add(b2p_op *op, double *diag, b2p_stream s)
+{
+  if (!op || !diag) return B2P_ERR_ARG;
+  if (op->kind == B2P_H1_DIFFUSION) return launch_h1_hex_diag(op, diag, (cudaStream_t)s);
+  return launch_nd_hex_diag(op, diag, (cudaStream_t)s);
+}
+
+int b2p_op_set_coeff(b2p_op *op, const void *blob, size_t bytes)
+{
+  if (!op) return B2P_ERR_ARG;
+  B2P_CHECK(op->ctx, op->parent == nullptr, B2P_ERR_ARG, "b2p_op_set_coeff: set the coefficient on the fine operator");
+  int rc = set_coeff(op, blob, bytes);
+  if (rc) return rc;
+  if (op->assembled) return assemble_qdata(op);
+  return B2P_SUCCESS;
+}
+
+int64_t b2p_op_lsize(b2p_op *op) { return op ? op->lsize : 0; }
+
+int64_t b2p_op_algorithmic_bytes(b2p_op *op)
+{
+  if (!op) return 0;
+  // x read once + y written once per unique dof, 4-byte index per element dof, q-data per point.
+  const int64_t Q = op->geom->Q;
+  const int64_t per_point = op->assembled ? op->aq_ncomp : 10;
+  return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->P + 8 * per_point * Q + (op->assembled ? 0 : 8));
+}
+
+void b2p_op_destroy(b2p_op *op)
+{
+  if (!op) return;
+  if (--op->refcount > 0) return;
+  cudaFree(op->lidx);
+  cudaFree(op->tab);
+  if (op->parent)
+  {
+    b2p_op_destroy(op->parent);
+  }
+  else
+  {
+    cudaFree(op->mat);
+    cudaFree(op->emat);
+    cudaFree(op->aq);
+  }
+  b2p_geom_destroy(op->geom);
+  delete op;
+}
+
+void b2p_ctx_destroy(b2p_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaFree(ctx->d_red);
+  cudaFreeHost(ctx->h_red);
+  delete ctx;
+}
+
+}  // extern "C"

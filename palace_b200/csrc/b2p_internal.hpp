@@ -1,0 +1,106 @@
+// Internal declarations shared by the b2p translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/b2p.h"
+
+struct ncclComm;
+
+namespace b2p
+{
+
+void set_error(b2p_ctx *ctx, const char *fmt, ...);
+
+#define B2P_CUDA(ctx, call)                                                                              \
+  do                                                                                                     \
+  {                                                                                                      \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+    {                                                                                                    \
+      b2p::set_error(ctx, "%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return B2P_ERR_CUDA;                                                                               \
+    }                                                                                                    \
+  } while (0)
+
+#define B2P_CHECK(ctx, cond, code, ...)     \
+  do                                        \
+  {                                         \
+    if (!(cond))                            \
+    {                                       \
+      b2p::set_error(ctx, __VA_ARGS__);     \
+      return code;                          \
+    }                                       \
+  } while (0)
+
+template <typename T>
+int upload(b2p_ctx *ctx, const T *host, size_t n, T **dptr);
+
+}  // namespace b2p
+
+struct b2p_ctx
+{
+  int device = 0;
+  int sm_count = 0;
+  int rank = 0, nranks = 1;
+  ncclComm *comm = nullptr;
+  std::string last_error;
+  // scratch for reductions (dot products): device partials + pinned host result
+  double *d_red = nullptr;
+  double *h_red = nullptr;
+  size_t red_cap = 0;
+};
+
+// Geometry q-data of one element block, device resident.
+//   qd[ne][10][Q]: {w detJ, (adjJ^T/detJ)[9] column-major}; attr[ne] int32 (1-based).
+// (The reference stores attr as an 11th double per point, mesh.cpp:188-195; it is constant per
+// element, so it is kept once per element here.)
+struct b2p_geom
+{
+  b2p_ctx *ctx = nullptr;
+  int ne = 0, q1d = 0, Q = 0;
+  double *qd = nullptr;
+  int32_t *attr = nullptr;
+  int refcount = 1;
+};
+
+struct b2p_op
+{
+  b2p_ctx *ctx = nullptr;
+  b2p_geom *geom = nullptr;  // shared (refcounted)
+  int kind = 0, p = 0, q1d = 0, ne = 0, P = 0;
+  int64_t lsize = 0;
+  int assembled = 0;
+  // restriction in LEXICOGRAPHIC element order with the sign folded in:
+  // lidx[e][l] >= 0 -> +x[lidx], < 0 -> -x[-1-lidx]   (layout [ne][P])
+  int32_t *lidx = nullptr;
+  // 1-D tables (device): Bo[q1d][p], Bc[q1d][p+1], Gc[q1d][p+1]
+  double *tab = nullptr;  // packed Bo | Bc | Gc
+  // coefficients: material tables + per-element material index for the two parts
+  double *mat = nullptr;       // [n_mat_total][9] column-major (mass part first, then curl part)
+  int32_t *emat = nullptr;     // [ne][2] indices into mat (value part, derivative part)
+  int n_mat = 0;
+  // assembled q-data (optional): aq[ne][ncomp][Q], symmetric 6 per part
+  double *aq = nullptr;
+  int aq_ncomp = 0;
+  bool owns_coeff = true;  // coarsened operators share the fine operator's coefficient arrays
+  b2p_op *parent = nullptr;
+  int refcount = 1;
+};
+
+namespace b2p
+{
+// Kernel launchers (defined in the .cu files).
+int launch_nd_hex_apply(b2p_op *op, const double *x, double *y, cudaStream_t s);
+int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
+int launch_h1_hex_apply(b2p_op *op, const double *x, double *y, cudaStream_t s);
+int launch_h1_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
+int launch_assemble_qdata(b2p_op *op, cudaStream_t s);
+int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, const double *d_B, const double *d_G,
+                    const double *d_qw, double *d_qd, cudaStream_t s);
+}  // namespace b2p

@@ -1,0 +1,109 @@
+"""Shared problem builders for the parity tests: caller-side mesh/space data (palace_b200.host), the
+oracle's dense tables (oracle.pyoracle) and the conversion of both into C-ABI operator descriptors."""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+from oracle import pyoracle as O
+from palace_b200.host import coeff as cf
+from palace_b200.host import hexmesh as hm
+from palace_b200.host import hexspace as hs
+
+
+@dataclasses.dataclass
+class Problem:
+    mesh: hm.HexMesh
+    topo: hs.HexTopology
+    p: int
+    q1d: int
+    mesh_order: int
+    xe: np.ndarray
+    nd: hs.HexSpace
+    h1: hs.HexSpace
+    tabs: hs.Tables1D
+    node_tabs: tuple  # (B, G) of the mesh nodal basis at the quadrature points
+    qdata_ref: np.ndarray  # oracle q-data [ne][11][Q]
+
+
+def make_problem(n=(3, 2, 2), p=2, q1d=None, mesh_order=2, warp=0.04, scramble=3, n_attr=3, size=(1.0, 0.7, 0.9)) -> Problem:
+    mesh = hm.box_mesh(n, size, warp_amp=warp, scramble_seed=scramble, n_attr=n_attr)
+    topo = hs.build_topology(mesh)
+    q1d = p + 1 if q1d is None else q1d
+    nodes = hs.gauss_lobatto(mesh_order + 1)
+    xe = mesh.node_coords(mesh_order, nodes)
+    qx, qw = hs.gauss_legendre(q1d)
+    nB, nG = hs.lagrange_table(nodes, qx)
+    nd = hs.build_nd_space(mesh, topo, p)
+    h1 = hs.build_h1_space(mesh, topo, p)
+    qd = O.geom_hex_qdata(xe, mesh.attr, mesh_order, q1d)
+    return Problem(mesh, topo, p, q1d, mesh_order, xe, nd, h1, hs.tables_1d(p, q1d), (nB, nG), qd)
+
+
+def coefficient(kind, n_attr, coeff_type="matrix", a_mass=1.0, a_curl=1.0):
+    """Coefficient context blob for operator ``kind`` in the style of the reference unit tests."""
+    if coeff_type == "const":
+        first = cf.coeff_ctx(a=a_mass)
+        second = cf.coeff_ctx(a=a_curl)
+    else:
+        am, mc = cf.test_suite_coefficient(n_attr, "scalar" if coeff_type == "scalar" else "matrix")
+        first = cf.coeff_ctx(am, mc, a=a_mass)
+        # a different (transposed, rescaled) coefficient for the curl part of pair contexts
+        second = cf.coeff_ctx(am, mc[::-1].copy() if len(mc) > 1 else mc, a=a_curl, transpose=True)
+    if kind == O.CURLCURL_MASS:
+        return cf.coeff_ctx_pair(first, second)
+    if kind == O.CURLCURL:
+        return second
+    return first
+
+
+def oracle_apply(prob: Problem, kind, ctx_blob, x, space=None, q1d=None):
+    """y = A x through the dense reference-style path (oracle)."""
+    q1d = prob.q1d if q1d is None else q1d
+    if kind == O.H1_DIFFUSION:
+        sp = prob.h1 if space is None else space
+        _, grad, _ = O.h1_hex_tables(sp.p, q1d)
+        idx = sp.lex_gid.astype(np.int32)
+        y = np.zeros(sp.ndofs)
+        return O.apply_add(kind, None, grad, idx, None, prob.qdata_ref, ctx_blob, np.ascontiguousarray(x), y)
+    sp = prob.nd if space is None else space
+    interp, curl, _ = O.nd_hex_tables(sp.p, q1d)
+    idx, ori = sp.native_restriction()
+    y = np.zeros(sp.ndofs)
+    return O.apply_add(kind, interp, curl, idx, ori, prob.qdata_ref, ctx_blob, np.ascontiguousarray(x), y)
+
+
+def oracle_diag(prob: Problem, kind, ctx_blob, space=None, q1d=None):
+    q1d = prob.q1d if q1d is None else q1d
+    if kind == O.H1_DIFFUSION:
+        sp = prob.h1 if space is None else space
+        _, grad, _ = O.h1_hex_tables(sp.p, q1d)
+        return O.diag_add(kind, None, grad, sp.lex_gid.astype(np.int32), prob.qdata_ref, ctx_blob, np.zeros(sp.ndofs))
+    sp = prob.nd if space is None else space
+    interp, curl, _ = O.nd_hex_tables(sp.p, q1d)
+    idx, _ = sp.native_restriction()
+    return O.diag_add(kind, interp, curl, idx, prob.qdata_ref, ctx_blob, np.zeros(sp.ndofs))
+
+
+def gpu_geom(ctx, prob: Problem):
+    from palace_b200 import capi
+
+    nB, nG = prob.node_tabs
+    return capi.Geom.hex(ctx, prob.xe, prob.mesh.attr, prob.mesh_order, prob.q1d, nB, nG, prob.tabs.qw)
+
+
+def gpu_op(ctx, geom, prob: Problem, kind, ctx_blob, assemble=False, space=None):
+    """Operator through the C ABI, fed exactly what MFEM/Palace would supply: native-order idx +
+    orientation, GetDofMap(), 1-D tables."""
+    from palace_b200 import capi
+
+    if kind == O.H1_DIFFUSION:
+        sp = prob.h1 if space is None else space
+        t = hs.tables_1d(sp.p, prob.q1d)
+        return capi.Op.create(ctx, geom, kind, sp.p, sp.ndofs, sp.lex_gid.astype(np.int32), None, None, None, t.Bc, t.Gc,
+                              ctx_blob, assemble)
+    sp = prob.nd if space is None else space
+    t = hs.tables_1d(sp.p, prob.q1d)
+    idx, ori = sp.native_restriction()
+    return capi.Op.create(ctx, geom, kind, sp.p, sp.ndofs, idx, ori, sp.dof_map, t.Bo, t.Bc, t.Gc, ctx_blob, assemble)
