@@ -107,6 +107,20 @@ int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *coarse_space, b2p_op **out);
 int b2p_op_apply(b2p_op *op, const double *x, double *y, b2p_stream s);
 /* y += A x (ceed::Operator::AddMult, a == 1 only, operator.cpp:192-212) */
 int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s);
+/* y += alpha * A x with options (ParOperator::AddMult scaling, linalg/rap.cpp:277-318):
+ *   B2P_APPLY_MASKED         use the restriction with essential dofs masked out (b2p_op_set_essential):
+ *                            masked inputs read as 0 and masked outputs are not written, which is what
+ *                            ParOperator::Mult does with SetSubVector(tx, dbc_tdof_list, 0.0) before P and
+ *                            the overwrite of y at those rows after P^T (rap.cpp:207-233)
+ *   B2P_APPLY_SIMPLE_KERNEL  run the simple cross-check kernel instead of the production one */
+enum
+{
+  B2P_APPLY_MASKED = 1,
+  B2P_APPLY_SIMPLE_KERNEL = 2
+};
+int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, int flags, b2p_stream s);
+/* Essential (Dirichlet / PEC) L-vector dofs for the masked apply. */
+int b2p_op_set_essential(b2p_op *op, const int32_t *ess_ldofs, int64_t n);
 /* diag += diag(A) (ceed::Operator::AssembleDiagonal, operator.cpp:116-143) */
 int b2p_op_diag_add(b2p_op *op, double *diag, b2p_stream s);
 /* Replace the coefficient context without touching geometry/restriction (driven sweeps re-coefficient

@@ -189,6 +189,14 @@ class Op:
     def apply_add(self, x, y, stream=None):
         _chk(lib().b2p_op_apply_add(self.h, _vp(x), _vp(y), _stream(stream)), self.ctx.h)
 
+    def apply_add_ex(self, alpha, x, y, masked=False, simple_kernel=False, stream=None):
+        flags = (1 if masked else 0) | (2 if simple_kernel else 0)
+        _chk(lib().b2p_op_apply_add_ex(self.h, C.c_double(alpha), _vp(x), _vp(y), flags, _stream(stream)), self.ctx.h)
+
+    def set_essential(self, ess_ldofs):
+        e = _np(ess_ldofs, np.int32)
+        _chk(lib().b2p_op_set_essential(self.h, _ptr(e), C.c_int64(e.size)), self.ctx.h)
+
     def diag_add(self, d, stream=None):
         _chk(lib().b2p_op_diag_add(self.h, _vp(d), _stream(stream)), self.ctx.h)
 

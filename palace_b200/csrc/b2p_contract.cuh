@@ -4,6 +4,20 @@
 namespace b2p
 {
 
+__device__ __forceinline__ double gather1(const double *__restrict__ x, int32_t gi)
+{
+  if (gi == B2P_SKIP_IDX) return 0.0;
+  return (gi >= 0) ? __ldg(x + gi) : -__ldg(x + (-1 - gi));
+}
+__device__ __forceinline__ void scatter1(double *y, int32_t gi, double v)
+{
+  if (gi == B2P_SKIP_IDX) return;
+  if (gi >= 0)
+    atomicAdd(y + gi, v);
+  else
+    atomicAdd(y + (-1 - gi), -v);
+}
+
 // One pencil of a 3-D tensor contraction along axis AX.
 //   in  has dims (D0, D1, D2), x fastest; the contracted axis has NIN entries and becomes NOUT.
 //   out[o] (+)= sgn * sum_i M[o*mso + i*msi] * in[i]

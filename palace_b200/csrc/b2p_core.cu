@@ -68,7 +68,7 @@ __global__ void geom_hex_kernel(int ne, int k, int q, const double *__restrict__
   double A[9];
   cofactor33(J, A);
   const double detJ = J[0] * A[0] + J[1] * A[1] + J[2] * A[2];
-  double *o = qd + (size_t)e * 10 * Q + iq;
+  double *o = qd + (size_t)e * 10 * Q + qslot(q, qx, qy, qz);
   o[0] = qw[qx] * qw[qy] * qw[qz] * detJ;
   for (int t = 0; t < 9; t++) o[(1 + t) * Q] = A[t] / detJ;
 }
@@ -193,7 +193,9 @@ int b2p_geom_create_qdata(b2p_ctx *ctx, int ne, int q1d, const double *qdata, b2
   for (int e = 0; e < ne; e++)
   {
     attr[e] = (int32_t)qdata[(size_t)e * 11 * Q];
-    std::memcpy(&qd[(size_t)e * 10 * Q], &qdata[((size_t)e * 11 + 1) * Q], sizeof(double) * 10 * Q);
+    for (int c = 0; c < 10; c++)
+      for (int iq = 0; iq < Q; iq++)
+        qd[((size_t)e * 10 + c) * Q + qslot_of(q1d, iq)] = qdata[((size_t)e * 11 + 1 + c) * Q + iq];
   }
   b2p_geom *g = new b2p_geom;
   g->ctx = ctx;
@@ -218,7 +220,9 @@ int b2p_geom_get_qdata(b2p_geom *g, double *qdata_host)
   for (int e = 0; e < g->ne; e++)
   {
     for (int i = 0; i < Q; i++) qdata_host[(size_t)e * 11 * Q + i] = (double)attr[e];
-    std::memcpy(&qdata_host[((size_t)e * 11 + 1) * Q], &qd[(size_t)e * 10 * Q], sizeof(double) * 10 * Q);
+    for (int c = 0; c < 10; c++)
+      for (int iq = 0; iq < Q; iq++)
+        qdata_host[((size_t)e * 11 + 1 + c) * Q + iq] = qd[((size_t)e * 10 + c) * Q + qslot_of(g->q1d, iq)];
   }
   return B2P_SUCCESS;
 }
@@ -334,7 +338,9 @@ int elem_dofs(int kind, int p) { return kind == B2P_H1_DIFFUSION ? (p + 1) * (p 
 int build_restriction(b2p_op *op, const b2p_op_desc *d)
 {
   const int P = op->P, ne = op->ne;
-  std::vector<int32_t> lidx((size_t)ne * P);
+  op->PS = (P + 3) & ~3;
+  const int PS = op->PS;
+  std::vector<int32_t> lidx((size_t)ne * PS, (int32_t)B2P_SKIP_IDX);
   for (int l = 0; l < P; l++)
   {
     int nat = d->dof_map ? d->dof_map[l] : l;
@@ -351,7 +357,7 @@ int build_restriction(b2p_op *op, const b2p_op_desc *d)
       B2P_CHECK(op->ctx, gi >= 0 && gi < op->lsize, B2P_ERR_ARG, "idx[%d][%d]=%d outside L-vector of size %lld", e, nat,
                 gi, (long long)op->lsize);
       const int s = sg * (d->orient ? (int)d->orient[(size_t)e * P + nat] : 1);
-      lidx[(size_t)e * P + l] = (s >= 0) ? gi : (-1 - gi);
+      lidx[(size_t)e * PS + l] = (s >= 0) ? gi : (-1 - gi);
     }
   }
   return upload(op->ctx, lidx.data(), lidx.size(), &op->lidx);
@@ -369,6 +375,7 @@ int build_tables(b2p_op *op, const b2p_op_desc *d)
   B2P_CHECK(op->ctx, d->Bc && d->Gc, B2P_ERR_ARG, "Bc/Gc tables required");
   std::memcpy(tab.data() + (size_t)q * p, d->Bc, sizeof(double) * q * n);
   std::memcpy(tab.data() + (size_t)q * p + (size_t)q * n, d->Gc, sizeof(double) * q * n);
+  op->h_tab = tab;
   return upload(op->ctx, tab.data(), tab.size(), &op->tab);
 }
 
@@ -376,7 +383,12 @@ int assemble_qdata(b2p_op *op)
 {
   const int parts = (op->kind == B2P_CURLCURL_MASS) ? 2 : 1;
   op->aq_ncomp = 9 * parts;
-  if (!op->aq) B2P_CUDA(op->ctx, cudaMalloc((void **)&op->aq, (size_t)op->ne * op->aq_ncomp * op->geom->Q * sizeof(double)));
+  op->aq_estride = ((int64_t)op->aq_ncomp * op->geom->Q + 1) & ~(int64_t)1;
+  if (!op->aq)
+  {
+    B2P_CUDA(op->ctx, cudaMalloc((void **)&op->aq, (size_t)op->ne * op->aq_estride * sizeof(double)));
+    B2P_CUDA(op->ctx, cudaMemset(op->aq, 0, (size_t)op->ne * op->aq_estride * sizeof(double)));
+  }
   int rc = launch_assemble_qdata(op, 0);
   if (rc) return rc;
   B2P_CUDA(op->ctx, cudaDeviceSynchronize());
@@ -442,6 +454,7 @@ int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *d, b2p_op **out)
   op->n_mat = fine->n_mat;
   op->aq = fine->aq;
   op->aq_ncomp = fine->aq_ncomp;
+  op->aq_estride = fine->aq_estride;
   op->owns_coeff = false;
   op->parent = fine;
   fine->refcount++;
@@ -455,18 +468,50 @@ int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *d, b2p_op **out)
   return B2P_SUCCESS;
 }
 
-int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s)
+int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, int flags, b2p_stream s)
 {
   if (!op || !x || !y) return B2P_ERR_ARG;
-  if (op->kind == B2P_H1_DIFFUSION) return launch_h1_hex_apply(op, x, y, (cudaStream_t)s);
-  return launch_nd_hex_apply(op, x, y, (cudaStream_t)s);
+  const int32_t *lidx = op->lidx;
+  if (flags & B2P_APPLY_MASKED)
+  {
+    B2P_CHECK(op->ctx, op->lidx_bc, B2P_ERR_ARG, "b2p_op_apply_add_ex: masked apply without b2p_op_set_essential");
+    lidx = op->lidx_bc;
+  }
+  if (op->kind == B2P_H1_DIFFUSION) return launch_h1_hex_apply(op, lidx, alpha, x, y, (cudaStream_t)s);
+  if (flags & B2P_APPLY_SIMPLE_KERNEL) return launch_nd_hex_apply(op, lidx, alpha, x, y, (cudaStream_t)s);
+  return launch_nd_hex_apply2(op, lidx, alpha, x, y, (cudaStream_t)s);
 }
+
+int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s) { return b2p_op_apply_add_ex(op, 1.0, x, y, 0, s); }
 
 int b2p_op_apply(b2p_op *op, const double *x, double *y, b2p_stream s)
 {
   if (!op || !x || !y) return B2P_ERR_ARG;
   B2P_CUDA(op->ctx, cudaMemsetAsync(y, 0, sizeof(double) * op->lsize, (cudaStream_t)s));
-  return b2p_op_apply_add(op, x, y, s);
+  return b2p_op_apply_add_ex(op, 1.0, x, y, 0, s);
+}
+
+int b2p_op_set_essential(b2p_op *op, const int32_t *ess_ldofs, int64_t n)
+{
+  if (!op || (n > 0 && !ess_ldofs)) return B2P_ERR_ARG;
+  std::vector<char> mark((size_t)op->lsize, 0);
+  for (int64_t i = 0; i < n; i++)
+  {
+    B2P_CHECK(op->ctx, ess_ldofs[i] >= 0 && ess_ldofs[i] < op->lsize, B2P_ERR_ARG, "essential dof %d outside the L-vector",
+              ess_ldofs[i]);
+    mark[ess_ldofs[i]] = 1;
+  }
+  std::vector<int32_t> lidx((size_t)op->ne * op->PS);
+  B2P_CUDA(op->ctx, cudaMemcpy(lidx.data(), op->lidx, lidx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (auto &g : lidx)
+  {
+    if (g == (int32_t)B2P_SKIP_IDX) continue;
+    const int32_t d = g >= 0 ? g : -1 - g;
+    if (mark[d]) g = B2P_SKIP_IDX;
+  }
+  cudaFree(op->lidx_bc);
+  op->lidx_bc = nullptr;
+  return upload(op->ctx, lidx.data(), lidx.size(), &op->lidx_bc);
 }
 
 int b2p_op_diag_add(b2p_op *op, double *diag, b2p_stream s)
@@ -494,7 +539,7 @@ int64_t b2p_op_algorithmic_bytes(b2p_op *op)
   // x read once + y written once per unique dof, 4-byte index per element dof, q-data per point.
   const int64_t Q = op->geom->Q;
   const int64_t per_point = op->assembled ? op->aq_ncomp : 10;
-  return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->P + 8 * per_point * Q + (op->assembled ? 0 : 8));
+  return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->PS + 8 * per_point * Q + (op->assembled ? 0 : 8));  // +8: emat
 }
 
 void b2p_op_destroy(b2p_op *op)
@@ -502,6 +547,7 @@ void b2p_op_destroy(b2p_op *op)
   if (!op) return;
   if (--op->refcount > 0) return;
   cudaFree(op->lidx);
+  cudaFree(op->lidx_bc);
   cudaFree(op->tab);
   if (op->parent)
   {

@@ -24,7 +24,10 @@ struct H1Params
   const double *aq;
   const double *x;
   double *y;
+  double alpha;
+  int64_t aq_estride;
   int ne;
+  int PS;  // padded restriction row stride
 };
 
 template <int P_, int Q_>
@@ -57,8 +60,7 @@ __global__ void __launch_bounds__(NT) h1_hex_diffusion_kernel(H1Params prm)
     double v = 0.0;
     if (e0 + e < prm.ne)
     {
-      const int gi = prm.lidx[(size_t)(e0 + e) * P + l];
-      v = (gi >= 0) ? prm.x[gi] : -prm.x[-1 - gi];
+      v = gather1(prm.x, prm.lidx[(size_t)(e0 + e) * prm.PS + l]);
     }
     U[e * ES + l] = v;
   }
@@ -77,20 +79,20 @@ __global__ void __launch_bounds__(NT) h1_hex_diffusion_kernel(H1Params prm)
   __syncthreads();
   for (int w = threadIdx.x; w < NEB * Q; w += NT)
   {
-    const int e = w / Q, iq = w % Q;
+    const int e = w / Q, iq = w % Q, sq = qslot_of(q, iq);
     if (e0 + e >= prm.ne) continue;
     double *ge = gq + e * ES;
     const double u0 = ge[iq], u1 = ge[Q + iq], u2 = ge[2 * Q + iq];
     if (ASM)
     {
-      const double *a = prm.aq + (size_t)(e0 + e) * 9 * Q + iq;
+      const double *a = prm.aq + (size_t)(e0 + e) * prm.aq_estride + sq;
       ge[iq] = a[0 * Q] * u0 + a[3 * Q] * u1 + a[6 * Q] * u2;
       ge[Q + iq] = a[1 * Q] * u0 + a[4 * Q] * u1 + a[7 * Q] * u2;
       ge[2 * Q + iq] = a[2 * Q] * u0 + a[5 * Q] * u1 + a[8 * Q] * u2;
     }
     else
     {
-      const double *g = prm.qd + (size_t)(e0 + e) * 10 * Q + iq;
+      const double *g = prm.qd + (size_t)(e0 + e) * 10 * Q + sq;
       double A[9], C[9], u[3] = {u0, u1, u2}, v[3];
 #pragma unroll
       for (int i = 0; i < 9; i++) A[i] = g[(1 + i) * Q];
@@ -120,12 +122,7 @@ __global__ void __launch_bounds__(NT) h1_hex_diffusion_kernel(H1Params prm)
   {
     const int e = w / P, l = w % P;
     if (e0 + e >= prm.ne) continue;
-    const int gi = prm.lidx[(size_t)(e0 + e) * P + l];
-    const double v = U[e * ES + l];
-    if (gi >= 0)
-      atomicAdd(prm.y + gi, v);
-    else
-      atomicAdd(prm.y - 1 - gi, -v);
+    scatter1(prm.y, prm.lidx[(size_t)(e0 + e) * prm.PS + l], prm.alpha * U[e * ES + l]);
   }
 }
 
@@ -145,12 +142,12 @@ __global__ void h1_hex_diag_kernel(H1Params prm, int p, int q, bool assembled)
     for (int qy = 0; qy < q; qy++)
       for (int qx = 0; qx < q; qx++)
       {
-        const int iq = qx + q * (qy + q * qz);
+        const int iq = qslot(q, qx, qy, qz);
         double u[3] = {Gc[qx * n + i] * Bc[qy * n + j] * Bc[qz * n + k], Bc[qx * n + i] * Gc[qy * n + j] * Bc[qz * n + k],
                        Bc[qx * n + i] * Bc[qy * n + j] * Gc[qz * n + k]};
         if (assembled)
         {
-          const double *a = prm.aq + (size_t)e * 9 * Q + iq;
+          const double *a = prm.aq + (size_t)e * prm.aq_estride + iq;
           for (int rr = 0; rr < 3; rr++)
             for (int cc = 0; cc < 3; cc++) s += u[rr] * a[(rr + 3 * cc) * Q] * u[cc];
         }
@@ -163,15 +160,19 @@ __global__ void h1_hex_diag_kernel(H1Params prm, int p, int q, bool assembled)
           s += u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
         }
       }
-  int gi = prm.lidx[(size_t)e * P + l];
+  int gi = prm.lidx[(size_t)e * prm.PS + l];
+  if (gi == B2P_SKIP_IDX) return;
   if (gi < 0) gi = -1 - gi;
   atomicAdd(prm.y + gi, s);
 }
 
-H1Params make_params(b2p_op *op, const double *x, double *y)
+H1Params make_params(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y)
 {
   H1Params prm;
-  prm.lidx = op->lidx;
+  prm.lidx = lidx;
+  prm.alpha = alpha;
+  prm.aq_estride = op->aq_estride;
+  prm.PS = op->PS;
   prm.tab = op->tab;
   prm.qd = op->geom->qd;
   prm.mat = op->mat;
@@ -184,7 +185,7 @@ H1Params make_params(b2p_op *op, const double *x, double *y)
 }
 
 template <int P_, int Q_, bool ASM>
-int launch_pq(b2p_op *op, const double *x, double *y, cudaStream_t s)
+int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
 {
   using L = H1Layout<P_, Q_>;
   constexpr int per_elem_bytes = L::PER_ELEM * 8;
@@ -199,18 +200,18 @@ int launch_pq(b2p_op *op, const double *x, double *y, cudaStream_t s)
     B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     configured = true;
   }
-  kern<<<(op->ne + NEB - 1) / NEB, NT, shmem, s>>>(make_params(op, x, y));
+  kern<<<(op->ne + NEB - 1) / NEB, NT, shmem, s>>>(make_params(op, lidx, alpha, x, y));
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
 
 }  // namespace
 
-int launch_h1_hex_apply(b2p_op *op, const double *x, double *y, cudaStream_t s)
+int launch_h1_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
 {
 #define B2P_CASE(PP, QQ)                                                                              \
   if (op->p == PP && op->q1d == QQ)                                                                   \
-    return op->assembled ? launch_pq<PP, QQ, true>(op, x, y, s) : launch_pq<PP, QQ, false>(op, x, y, s);
+    return op->assembled ? launch_pq<PP, QQ, true>(op, lidx, alpha, x, y, s) : launch_pq<PP, QQ, false>(op, lidx, alpha, x, y, s);
   B2P_CASE(1, 2) B2P_CASE(1, 3) B2P_CASE(1, 4) B2P_CASE(1, 5) B2P_CASE(1, 6) B2P_CASE(1, 7)
   B2P_CASE(2, 3) B2P_CASE(2, 4) B2P_CASE(2, 5) B2P_CASE(2, 6) B2P_CASE(2, 7)
   B2P_CASE(3, 4) B2P_CASE(3, 5) B2P_CASE(3, 6) B2P_CASE(3, 7)
@@ -224,7 +225,7 @@ int launch_h1_hex_apply(b2p_op *op, const double *x, double *y, cudaStream_t s)
 
 int launch_h1_hex_diag(b2p_op *op, double *diag, cudaStream_t s)
 {
-  H1Params prm = make_params(op, nullptr, diag);
+  H1Params prm = make_params(op, op->lidx, 1.0, nullptr, diag);
   const size_t total = (size_t)op->ne * op->P;
   const int nt = 128;
   h1_hex_diag_kernel<<<(unsigned)((total + nt - 1) / nt), nt, 0, s>>>(prm, op->p, op->q1d, op->assembled);

@@ -48,7 +48,10 @@ struct NDParams
   const double *aq;    // assembled q-data [ne][ncomp][Q] or null
   const double *x;
   double *y;
+  double alpha;
+  int64_t aq_estride;
   int ne;
+  int PS;  // padded restriction row stride
 };
 
 // KIND: B2P_CURLCURL / B2P_ND_MASS / B2P_CURLCURL_MASS. ASM: assembled q-data.
@@ -81,8 +84,7 @@ __global__ void __launch_bounds__(NT) nd_hex_apply_kernel(NDParams prm)
     double v = 0.0;
     if (e0 + e < prm.ne)
     {
-      const int gi = prm.lidx[(size_t)(e0 + e) * P + l];
-      v = (gi >= 0) ? prm.x[gi] : -prm.x[-1 - gi];
+      v = gather1(prm.x, prm.lidx[(size_t)(e0 + e) * prm.PS + l]);
     }
     U[e * ES + l] = v;
   }
@@ -144,12 +146,12 @@ __global__ void __launch_bounds__(NT) nd_hex_apply_kernel(NDParams prm)
   // ---- D at quadrature points ----
   for (int w = threadIdx.x; w < NEB * Q; w += NT)
   {
-    const int e = w / Q, iq = w % Q;
+    const int e = w / Q, iq = w % Q, sq = qslot_of(q, iq);
     if (e0 + e >= prm.ne) continue;
     double *uqe = uq + e * ES, *cqe = cq + e * ES;
     if (ASM)
     {
-      const double *a = prm.aq + (size_t)(e0 + e) * ((MASS ? 9 : 0) + (CURL ? 9 : 0)) * Q + iq;
+      const double *a = prm.aq + (size_t)(e0 + e) * prm.aq_estride + sq;
       if (MASS)
       {
         const double u0 = uqe[iq], u1 = uqe[Q + iq], u2 = uqe[2 * Q + iq];
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(NT) nd_hex_apply_kernel(NDParams prm)
     }
     else
     {
-      const double *g = prm.qd + (size_t)(e0 + e) * 10 * Q + iq;
+      const double *g = prm.qd + (size_t)(e0 + e) * 10 * Q + sq;
       const double wdetJ = g[0];
       double A[9];
 #pragma unroll
@@ -260,12 +262,7 @@ __global__ void __launch_bounds__(NT) nd_hex_apply_kernel(NDParams prm)
   {
     const int e = w / P, l = w % P;
     if (e0 + e >= prm.ne) continue;
-    const int gi = prm.lidx[(size_t)(e0 + e) * P + l];
-    const double v = U[e * ES + l];
-    if (gi >= 0)
-      atomicAdd(prm.y + gi, v);
-    else
-      atomicAdd(prm.y - 1 - gi, -v);
+    scatter1(prm.y, prm.lidx[(size_t)(e0 + e) * prm.PS + l], prm.alpha * U[e * ES + l]);
   }
 }
 
@@ -300,7 +297,7 @@ __global__ void nd_hex_diag_kernel(NDParams prm, int p, int q, bool assembled)
     for (int qy = 0; qy < q; qy++)
       for (int qx = 0; qx < q; qx++)
       {
-        const int iq = qx + q * (qy + q * qz);
+        const int iq = qslot(q, qx, qy, qz);
         // 1-D factors for this dof at this point: value f and the two non-zero curl entries
         double fx, fy, fz, gx, gy, gz;  // value / derivative of the factor along each axis
         fx = (c == 0) ? Bo[qx * p + i] : Bc[qx * n + i];
@@ -316,7 +313,7 @@ __global__ void nd_hex_diag_kernel(NDParams prm, int p, int q, bool assembled)
         else { cu[0] = fx * gy * fz; cu[1] = -gx * fy * fz; }
         if (assembled)
         {
-          const double *a = prm.aq + (size_t)e * ((MASS ? 9 : 0) + (CURL ? 9 : 0)) * Q + iq;
+          const double *a = prm.aq + (size_t)e * prm.aq_estride + iq;
           if (MASS)
           {
             for (int rr = 0; rr < 3; rr++)
@@ -346,7 +343,8 @@ __global__ void nd_hex_diag_kernel(NDParams prm, int p, int q, bool assembled)
           }
         }
       }
-  int gi = prm.lidx[(size_t)e * P + l];
+  int gi = prm.lidx[(size_t)e * prm.PS + l];
+  if (gi == B2P_SKIP_IDX) return;
   if (gi < 0) gi = -1 - gi;
   atomicAdd(prm.y + gi, s);
 }
@@ -365,7 +363,7 @@ __global__ void nd_assemble_qdata_kernel(NDParams prm, int Q, double *aq)
   const int32_t *em = prm.emat + 2 * (size_t)e;
   double A[9], C[9], S[9];
   for (int t = 0; t < 9; t++) A[t] = g[(1 + t) * Q];
-  double *a = aq + (size_t)e * ((MASS ? 9 : 0) + (CURL ? 9 : 0)) * Q + iq;
+  double *a = aq + (size_t)e * prm.aq_estride + iq;
   if (MASS)
   {
     for (int t = 0; t < 9; t++) C[t] = prm.mat[9 * em[0] + t];
@@ -383,10 +381,13 @@ __global__ void nd_assemble_qdata_kernel(NDParams prm, int Q, double *aq)
   }
 }
 
-NDParams make_params(b2p_op *op, const double *x, double *y)
+NDParams make_params(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y)
 {
   NDParams prm;
-  prm.lidx = op->lidx;
+  prm.lidx = lidx;
+  prm.alpha = alpha;
+  prm.aq_estride = op->aq_estride;
+  prm.PS = op->PS;
   prm.tab = op->tab;
   prm.qd = op->geom->qd;
   prm.mat = op->mat;
@@ -399,7 +400,7 @@ NDParams make_params(b2p_op *op, const double *x, double *y)
 }
 
 template <int P_, int Q_, int KIND, bool ASM>
-int launch_pq(b2p_op *op, const double *x, double *y, cudaStream_t s)
+int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
 {
   using L = NDLayout<P_, Q_>;
   // elements per block: keep shared memory under ~96 KB and at least 128 threads of work
@@ -416,24 +417,24 @@ int launch_pq(b2p_op *op, const double *x, double *y, cudaStream_t s)
     configured = true;
   }
   const int grid = (op->ne + NEB - 1) / NEB;
-  kern<<<grid, NT, shmem, s>>>(make_params(op, x, y));
+  kern<<<grid, NT, shmem, s>>>(make_params(op, lidx, alpha, x, y));
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
 
 template <int P_, int Q_>
-int launch_kind(b2p_op *op, const double *x, double *y, cudaStream_t s)
+int launch_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
 {
   const bool a = op->assembled;
   switch (op->kind)
   {
     case B2P_CURLCURL:
-      return a ? launch_pq<P_, Q_, B2P_CURLCURL, true>(op, x, y, s) : launch_pq<P_, Q_, B2P_CURLCURL, false>(op, x, y, s);
+      return a ? launch_pq<P_, Q_, B2P_CURLCURL, true>(op, lidx, alpha, x, y, s) : launch_pq<P_, Q_, B2P_CURLCURL, false>(op, lidx, alpha, x, y, s);
     case B2P_ND_MASS:
-      return a ? launch_pq<P_, Q_, B2P_ND_MASS, true>(op, x, y, s) : launch_pq<P_, Q_, B2P_ND_MASS, false>(op, x, y, s);
+      return a ? launch_pq<P_, Q_, B2P_ND_MASS, true>(op, lidx, alpha, x, y, s) : launch_pq<P_, Q_, B2P_ND_MASS, false>(op, lidx, alpha, x, y, s);
     case B2P_CURLCURL_MASS:
-      return a ? launch_pq<P_, Q_, B2P_CURLCURL_MASS, true>(op, x, y, s)
-               : launch_pq<P_, Q_, B2P_CURLCURL_MASS, false>(op, x, y, s);
+      return a ? launch_pq<P_, Q_, B2P_CURLCURL_MASS, true>(op, lidx, alpha, x, y, s)
+               : launch_pq<P_, Q_, B2P_CURLCURL_MASS, false>(op, lidx, alpha, x, y, s);
   }
   set_error(op->ctx, "nd_hex_apply: unsupported kind %d", op->kind);
   return B2P_ERR_UNSUPPORTED;
@@ -441,10 +442,10 @@ int launch_kind(b2p_op *op, const double *x, double *y, cudaStream_t s)
 
 }  // namespace
 
-int launch_nd_hex_apply(b2p_op *op, const double *x, double *y, cudaStream_t s)
+int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
 {
 #define B2P_CASE(PP, QQ) \
-  if (op->p == PP && op->q1d == QQ) return launch_kind<PP, QQ>(op, x, y, s);
+  if (op->p == PP && op->q1d == QQ) return launch_kind<PP, QQ>(op, lidx, alpha, x, y, s);
   // (p, q1d): q1d = p+1 for a stand-alone operator; larger q1d for p-coarsened operators that
   // reuse the fine level's quadrature (CeedOperatorCoarsen, libceed/operator.cpp:525-585).
   B2P_CASE(1, 2) B2P_CASE(1, 3) B2P_CASE(1, 4) B2P_CASE(1, 5) B2P_CASE(1, 6) B2P_CASE(1, 7)
@@ -460,7 +461,7 @@ int launch_nd_hex_apply(b2p_op *op, const double *x, double *y, cudaStream_t s)
 
 int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s)
 {
-  NDParams prm = make_params(op, nullptr, diag);
+  NDParams prm = make_params(op, op->lidx, 1.0, nullptr, diag);
   const size_t total = (size_t)op->ne * op->P;
   const int nt = 128;
   const unsigned grid = (unsigned)((total + nt - 1) / nt);
@@ -479,7 +480,7 @@ int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s)
 
 int launch_assemble_qdata(b2p_op *op, cudaStream_t s)
 {
-  NDParams prm = make_params(op, nullptr, nullptr);
+  NDParams prm = make_params(op, op->lidx, 1.0, nullptr, nullptr);
   const int Q = op->geom->Q;
   const size_t total = (size_t)op->ne * Q;
   const int nt = 128;

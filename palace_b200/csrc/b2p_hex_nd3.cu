@@ -1,0 +1,773 @@
+// Production Nedelec hexahedron apply kernel: warp-autonomous persistent pipeline.
+//
+//   y_L += alpha * sum_e E_e^T  B^T  D  B  E_e x_L          (curl-curl, mass, curl-curl + mass)
+//
+// Same operator as b2p_hex_nd.cu (the simple cross-check kernel), organised for the B200:
+//   * persistent grid; every WARP owns a batch of NEW elements through all five phases, so the only
+//     synchronisation is __syncwarp() (no CTA barriers, warps drift apart and fill each other's stalls):
+//       Z   z-contraction of the gathered dofs          (reads the staged x values)
+//       Y   y-contraction
+//       XDX x-contraction INTO REGISTERS -> u, curl u on one (qy,qz) line of q-points, pointwise D,
+//           transposed x-contraction from registers
+//       Yt  transposed y-contraction
+//       Zt  transposed z-contraction, scatter-add (RED.F64) straight from registers
+//   * a three-deep software pipeline per warp hides HBM/L2 latency behind the arithmetic:
+//       - the batch's signed restriction indices arrive by TMA bulk copy (cp.async.bulk, UBLKCP) two
+//         batches ahead, behind an mbarrier
+//       - the x values are gathered one batch ahead with cp.async (LDGSTS) straight into shared memory
+//       - the batch's geometry q-data (one contiguous block in HBM) arrives by TMA bulk copy into a
+//         single buffer that is refilled as soon as the XDX phase of the previous batch has read it
+//   * q-data is stored x-SLOWEST so the XDX phase reads it conflict-free; shared work arrays are laid
+//     out so each phase stores thread-contiguous vectors and the next phase loads conflict-free
+//   * the 1-D basis tables travel in the kernel parameter block: every basis entry is a constant-bank
+//     operand of the DFMA (no shared/global load per multiply).
+//
+// Reference semantics: ceed::Operator::AddMult over CeedOperatorApplyAdd
+// (/root/reference/palace/fem/libceed/operator.cpp:148-178,192-212); D from
+// /root/reference/palace/fem/qfunctions/33/{hdiv,hcurl,hdivmass}_33_qf.h.
+#include "b2p_internal.hpp"
+#include "b2p_qf.cuh"
+#include "b2p_contract.cuh"
+
+namespace b2p
+{
+
+namespace
+{
+
+template <int P_, int Q_>
+struct ND2Params
+{
+  const int32_t *lidx;  // [ne][PS] signed lexicographic restriction, rows padded to 16 bytes (B2P_SKIP_IDX = masked/pad)
+  const double *qd;     // [ne][10][Q] geometry, x-slowest point order
+  const double *aq;     // [ne][ncomp][Q] assembled D, x-slowest (or null)
+  const double *mat;    // [n_mat][9]
+  const int32_t *emat;  // [ne][2]
+  const double *x;
+  double *y;
+  double alpha;
+  int ne;
+  double Bo[Q_ * P_];
+  double Bc[Q_ * (P_ + 1)];
+  double Gc[Q_ * (P_ + 1)];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t ok = 0;
+  while (!ok)
+  {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int P_, int Q_, int KIND, bool ASM>
+struct ND3Layout
+{
+  static constexpr int p = P_, q = Q_, n = P_ + 1, Q = q * q * q, P = 3 * p * n * n, D3 = p * n * n;
+  static constexpr int PS = (P + 3) & ~3;  // padded restriction stride (16-byte rows for TMA)
+  static constexpr bool MASS = (KIND == B2P_ND_MASS || KIND == B2P_CURLCURL_MASS);
+  static constexpr bool CURL = (KIND == B2P_CURLCURL || KIND == B2P_CURLCURL_MASS);
+  // Z region (after the z contraction): index qz + q*(t), t = i + ni*j
+  static constexpr int ZXA = 0, ZXB = ZXA + p * n * q, ZYA = ZXB + p * n * q, ZYB = ZYA + n * p * q, ZZA = ZYB + n * p * q,
+                       ZSZ = ZZA + n * n * q;
+  // Y region (after z and y contractions): index qy + q*(qz + q*i)
+  static constexpr int YX1 = ZSZ, YX2 = YX1 + p * q * q, YX3 = YX2 + p * q * q, YY1 = YX3 + p * q * q, YY2 = YY1 + n * q * q,
+                       YZ1 = YY2 + n * q * q, YZ3 = YZ1 + n * q * q, YEND = YZ3 + n * q * q;
+  static constexpr int ES = (YEND + 1) & ~1;  // doubles of work space per element (even)
+  static constexpr int GCOMP = ASM ? ((MASS ? 9 : 0) + (CURL ? 9 : 0)) : 10;
+  static constexpr int GE = (GCOMP * Q + 1) & ~1;  // doubles of q-data per element (even: 16-byte blocks for TMA)
+  static constexpr int CE = 18;                    // coefficient matrices per element
+  // elements per warp: enough (qy,qz) lines to fill the 32 lanes in the XDX phase
+  static constexpr int NEW = (q * q >= 32) ? 1 : 32 / (q * q);
+  // per-warp shared memory (bytes), every block 16-byte aligned
+  static constexpr int OFF_G = 0;
+  static constexpr int OFF_W = OFF_G + NEW * GE * 8;
+  static constexpr int OFF_U = OFF_W + NEW * ES * 8;             // [2][NEW*PS] doubles
+  static constexpr int OFF_I = OFF_U + 2 * NEW * PS * 8;         // [2][NEW*PS] int32
+  static constexpr int OFF_C = OFF_I + 2 * NEW * PS * 4;         // [NEW*18] doubles
+  static constexpr int OFF_B = OFF_C + ((NEW * CE * 8 + 15) & ~15);  // 3 mbarriers
+  static constexpr int WS = (OFF_B + 3 * 8 + 15) & ~15;
+};
+
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Staged dof value with the restriction's sign; masked / out-of-range entries read as zero.
+__device__ __forceinline__ double staged(const int32_t *cI, const double *cU, int pos, bool valid)
+{
+  const int32_t gi = cI[pos];
+  const double v = cU[pos];
+  if (!valid || gi == B2P_SKIP_IDX) return 0.0;
+  return gi >= 0 ? v : -v;
+}
+
+template <int P_, int Q_, int KIND, bool ASM, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __grid_constant__ ND2Params<P_, Q_> prm)
+{
+  using L = ND3Layout<P_, Q_, KIND, ASM>;
+  constexpr int p = L::p, q = L::q, n = L::n, Q = L::Q, D3 = L::D3, ES = L::ES, GE = L::GE, PS = L::PS, NEW = L::NEW;
+  constexpr bool MASS = L::MASS, CURL = L::CURL;
+  constexpr int QQ = q * q;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *wbase = smem_raw + (size_t)wid * L::WS;
+  double *sG = (double *)(wbase + L::OFF_G);
+  double *sW = (double *)(wbase + L::OFF_W);
+  double *sU = (double *)(wbase + L::OFF_U);
+  int32_t *sI = (int32_t *)(wbase + L::OFF_I);
+  double *sC = (double *)(wbase + L::OFF_C);
+  uint64_t *bar_g = (uint64_t *)(wbase + L::OFF_B);
+  uint64_t *bar_i = bar_g + 1;  // [2]
+
+  const int nb = (prm.ne + NEW - 1) / NEW;  // element batches
+  const int GW = gridDim.x * NW;            // warps in the grid
+  int b = blockIdx.x * NW + wid;
+  if (b >= nb) return;                      // (whole warp)
+
+  if (lane == 0)
+  {
+    mbar_init(bar_g, 1);
+    mbar_init(bar_i + 0, 1);
+    mbar_init(bar_i + 1, 1);
+  }
+  __syncwarp();
+
+  auto issue_idx = [&](int bb, int slot)
+  {
+    const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
+    const uint32_t bytes = (uint32_t)(nel * PS * sizeof(int32_t));
+    mbar_expect_tx(bar_i + slot, bytes);
+    tma_bulk_g2s(sI + slot * NEW * PS, prm.lidx + (size_t)e0 * PS, bytes, bar_i + slot);
+  };
+  auto issue_geom = [&](int bb)
+  {
+    const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
+    const uint32_t bytes = (uint32_t)(nel * GE * sizeof(double));
+    mbar_expect_tx(bar_g, bytes);
+    tma_bulk_g2s(sG, (ASM ? prm.aq : prm.qd) + (size_t)e0 * GE, bytes, bar_g);
+  };
+  auto gather_x = [&](int bb, int slot)
+  {
+    const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
+    const int32_t *cI = sI + slot * NEW * PS;
+    double *cU = sU + slot * NEW * PS;
+    for (int l = lane; l < nel * PS; l += 32)
+    {
+      const int32_t gi = cI[l];
+      if (gi != B2P_SKIP_IDX) cp_async8(cU + l, prm.x + (gi >= 0 ? gi : -1 - gi));
+    }
+  };
+
+  uint32_t par_g = 0, par_i = 0;  // mbarrier phase parities (par_i: bit per index slot)
+  if (lane == 0)
+  {
+    issue_idx(b, 0);
+    if (b + GW < nb) issue_idx(b + GW, 1);
+    issue_geom(b);
+  }
+  mbar_wait(bar_i + 0, par_i & 1u);
+  par_i ^= 1u;
+  gather_x(b, 0);
+  cp_async_commit();
+
+  const double alpha = prm.alpha;
+  for (int it = 0; b < nb; b += GW, it++)
+  {
+    const int slot = it & 1, nslot = slot ^ 1;
+    const int bn = b + GW;
+    const int e0 = b * NEW, nel = min(NEW, prm.ne - e0);
+    const int32_t *cI = sI + slot * NEW * PS;
+    const double *cU = sU + slot * NEW * PS;
+
+    // stage the next batch's x values while this batch computes
+    if (bn < nb)
+    {
+      mbar_wait(bar_i + nslot, (par_i >> nslot) & 1u);
+      par_i ^= (1u << nslot);
+      gather_x(bn, nslot);
+    }
+    cp_async_commit();
+    // coefficient matrices of this batch (tiny, L2 resident): load now, store after phase Z
+    double creg[(NEW * 18 + 31) / 32];
+    if (!ASM)
+    {
+#pragma unroll
+      for (int r = 0; r < (NEW * 18 + 31) / 32; r++)
+      {
+        const int w = lane + 32 * r, e = w / 18, i = w % 18;
+        creg[r] = (w < NEW * 18 && e < nel) ? __ldg(prm.mat + 9 * (size_t)__ldg(prm.emat + 2 * (size_t)(e0 + e) + (i / 9)) + (i % 9)) : 0.0;
+      }
+    }
+    cp_async_wait<1>();
+    __syncwarp();
+
+    // ------------------------------------------------------------------ phase Z (gather + z)
+    // x-directed: t = i + p*j (i<p open, j<n), k<n closed
+    for (int w = lane; w < NEW * (p * n); w += 32)
+    {
+      const int e = w / (p * n), t = w % (p * n);
+      double u[n];
+  #pragma unroll
+      for (int k = 0; k < n; k++) u[k] = staged(cI, cU, e * PS + t + p * n * k, e < nel);
+      double *za = sW + e * ES + L::ZXA + q * t, *zb = sW + e * ES + L::ZXB + q * t;
+  #pragma unroll
+      for (int qz = 0; qz < q; qz++)
+      {
+        double a = 0.0, b = 0.0;
+  #pragma unroll
+        for (int k = 0; k < n; k++)
+        {
+          a += prm.Bc[qz * n + k] * u[k];
+          if (CURL) b += prm.Gc[qz * n + k] * u[k];
+        }
+        za[qz] = a;
+        if (CURL) zb[qz] = b;
+      }
+    }
+    // y-directed: t = i + n*j (i<n, j<p open), k<n closed
+    for (int w = lane; w < NEW * (n * p); w += 32)
+    {
+      const int e = w / (n * p), t = w % (n * p);
+      double u[n];
+  #pragma unroll
+      for (int k = 0; k < n; k++) u[k] = staged(cI, cU, e * PS + D3 + t + n * p * k, e < nel);
+      double *za = sW + e * ES + L::ZYA + q * t, *zb = sW + e * ES + L::ZYB + q * t;
+  #pragma unroll
+      for (int qz = 0; qz < q; qz++)
+      {
+        double a = 0.0, b = 0.0;
+  #pragma unroll
+        for (int k = 0; k < n; k++)
+        {
+          a += prm.Bc[qz * n + k] * u[k];
+          if (CURL) b += prm.Gc[qz * n + k] * u[k];
+        }
+        za[qz] = a;
+        if (CURL) zb[qz] = b;
+      }
+    }
+    // z-directed: t = i + n*j (i,j<n), k<p open
+    for (int w = lane; w < NEW * (n * n); w += 32)
+    {
+      const int e = w / (n * n), t = w % (n * n);
+      double u[p];
+  #pragma unroll
+      for (int k = 0; k < p; k++) u[k] = staged(cI, cU, e * PS + 2 * D3 + t + n * n * k, e < nel);
+      double *za = sW + e * ES + L::ZZA + q * t;
+  #pragma unroll
+      for (int qz = 0; qz < q; qz++)
+      {
+        double a = 0.0;
+  #pragma unroll
+        for (int k = 0; k < p; k++) a += prm.Bo[qz * p + k] * u[k];
+        za[qz] = a;
+      }
+    }
+
+    if (!ASM)
+    {
+#pragma unroll
+      for (int r = 0; r < (NEW * 18 + 31) / 32; r++)
+        if (lane + 32 * r < NEW * 18) sC[lane + 32 * r] = creg[r];
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ phase Y
+    // items t' = qz + q*i ; reads Z[qz + q*(i + ni*j)] over j ; writes V[qy + q*t'] (thread-contiguous)
+    // x-directed (ni = p, j<n closed): V1 = Bc_y a, V3 = Gc_y a, V2 = Bc_y b
+    for (int w = lane; w < NEW * (p * q); w += 32)
+    {
+      const int e = w / (p * q), t = w % (p * q), qz = t % q, i = t / q;
+      const double *za = sW + e * ES + L::ZXA + qz + q * i, *zb = sW + e * ES + L::ZXB + qz + q * i;
+      double a[n], b[n];
+  #pragma unroll
+      for (int j = 0; j < n; j++)
+      {
+        a[j] = za[q * p * j];
+        if (CURL) b[j] = zb[q * p * j];
+      }
+      double *v1 = sW + e * ES + L::YX1 + q * t, *v2 = sW + e * ES + L::YX2 + q * t, *v3 = sW + e * ES + L::YX3 + q * t;
+  #pragma unroll
+      for (int qy = 0; qy < q; qy++)
+      {
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  #pragma unroll
+        for (int j = 0; j < n; j++)
+        {
+          if (MASS) s1 += prm.Bc[qy * n + j] * a[j];
+          if (CURL) s2 += prm.Bc[qy * n + j] * b[j];
+          if (CURL) s3 += prm.Gc[qy * n + j] * a[j];
+        }
+        if (MASS) v1[qy] = s1;
+        if (CURL) v2[qy] = s2;
+        if (CURL) v3[qy] = s3;
+      }
+    }
+    // y-directed (ni = n, j<p open): V1 = Bo_y a, V2 = Bo_y b
+    for (int w = lane; w < NEW * (n * q); w += 32)
+    {
+      const int e = w / (n * q), t = w % (n * q), qz = t % q, i = t / q;
+      const double *za = sW + e * ES + L::ZYA + qz + q * i, *zb = sW + e * ES + L::ZYB + qz + q * i;
+      double a[p], b[p];
+  #pragma unroll
+      for (int j = 0; j < p; j++)
+      {
+        a[j] = za[q * n * j];
+        if (CURL) b[j] = zb[q * n * j];
+      }
+      double *v1 = sW + e * ES + L::YY1 + q * t, *v2 = sW + e * ES + L::YY2 + q * t;
+  #pragma unroll
+      for (int qy = 0; qy < q; qy++)
+      {
+        double s1 = 0.0, s2 = 0.0;
+  #pragma unroll
+        for (int j = 0; j < p; j++)
+        {
+          s1 += prm.Bo[qy * p + j] * a[j];
+          if (CURL) s2 += prm.Bo[qy * p + j] * b[j];
+        }
+        v1[qy] = s1;
+        if (CURL) v2[qy] = s2;
+      }
+    }
+    // z-directed (ni = n, j<n closed): V1 = Bc_y a, V3 = Gc_y a
+    for (int w = lane; w < NEW * (n * q); w += 32)
+    {
+      const int e = w / (n * q), t = w % (n * q), qz = t % q, i = t / q;
+      const double *za = sW + e * ES + L::ZZA + qz + q * i;
+      double a[n];
+  #pragma unroll
+      for (int j = 0; j < n; j++) a[j] = za[q * n * j];
+      double *v1 = sW + e * ES + L::YZ1 + q * t, *v3 = sW + e * ES + L::YZ3 + q * t;
+  #pragma unroll
+      for (int qy = 0; qy < q; qy++)
+      {
+        double s1 = 0.0, s3 = 0.0;
+  #pragma unroll
+        for (int j = 0; j < n; j++)
+        {
+          s1 += prm.Bc[qy * n + j] * a[j];
+          if (CURL) s3 += prm.Gc[qy * n + j] * a[j];
+        }
+        v1[qy] = s1;
+        if (CURL) v3[qy] = s3;
+      }
+    }
+
+    __syncwarp();
+    mbar_wait(bar_g, par_g);  // q-data of this batch has landed
+    par_g ^= 1;
+
+    // ------------------------------------------------------------------ phase XDX
+    // item s = qy + q*qz: reads V[s + q^2 i]; all qx of this line live in registers.
+    for (int w = lane; w < NEW * (QQ); w += 32)
+    {
+      const int e = w / QQ, s = w % QQ;
+      double *W = sW + e * ES + s;
+      double x1[p], x2[p], x3[p], y1[n], y2[n], z1[n], z3[n];
+  #pragma unroll
+      for (int i = 0; i < p; i++)
+      {
+        if (MASS) x1[i] = W[L::YX1 + QQ * i];
+        if (CURL) x2[i] = W[L::YX2 + QQ * i];
+        if (CURL) x3[i] = W[L::YX3 + QQ * i];
+      }
+  #pragma unroll
+      for (int i = 0; i < n; i++)
+      {
+        y1[i] = W[L::YY1 + QQ * i];
+        if (CURL) y2[i] = W[L::YY2 + QQ * i];
+        z1[i] = W[L::YZ1 + QQ * i];
+        if (CURL) z3[i] = W[L::YZ3 + QQ * i];
+      }
+      double ax1[p], ax2[p], ax3[p], ay1[n], ay2[n], az1[n], az3[n];
+  #pragma unroll
+      for (int i = 0; i < p; i++) ax1[i] = ax2[i] = ax3[i] = 0.0;
+  #pragma unroll
+      for (int i = 0; i < n; i++) ay1[i] = ay2[i] = az1[i] = az3[i] = 0.0;
+      const double *g = sG + e * GE + s;
+      const double *C = sC + e * 18;
+  #pragma unroll
+      for (int qx = 0; qx < q; qx++)
+      {
+        double u[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+        {
+          double dzux = 0, dyux = 0, dzuy = 0, dxuy = 0, dyuz = 0, dxuz = 0;
+  #pragma unroll
+          for (int i = 0; i < p; i++)
+          {
+            if (MASS) u[0] += prm.Bo[qx * p + i] * x1[i];
+            if (CURL) dzux += prm.Bo[qx * p + i] * x2[i];
+            if (CURL) dyux += prm.Bo[qx * p + i] * x3[i];
+          }
+  #pragma unroll
+          for (int i = 0; i < n; i++)
+          {
+            if (MASS) u[1] += prm.Bc[qx * n + i] * y1[i];
+            if (CURL) dzuy += prm.Bc[qx * n + i] * y2[i];
+            if (CURL) dxuy += prm.Gc[qx * n + i] * y1[i];
+            if (MASS) u[2] += prm.Bc[qx * n + i] * z1[i];
+            if (CURL) dyuz += prm.Bc[qx * n + i] * z3[i];
+            if (CURL) dxuz += prm.Gc[qx * n + i] * z1[i];
+          }
+          c[0] = dyuz - dzuy;
+          c[1] = dzux - dxuz;
+          c[2] = dxuy - dyux;
+        }
+        double v[3] = {0, 0, 0}, cw[3] = {0, 0, 0};
+        if (e < nel)
+        {
+          const double *gq = g + QQ * qx;
+          if (ASM)
+          {
+            const double *a = gq;
+            if (MASS)
+            {
+  #pragma unroll
+              for (int r = 0; r < 3; r++) v[r] = a[(r)*Q] * u[0] + a[(r + 3) * Q] * u[1] + a[(r + 6) * Q] * u[2];
+              a += 9 * Q;
+            }
+            if (CURL)
+            {
+  #pragma unroll
+              for (int r = 0; r < 3; r++) cw[r] = a[(r)*Q] * c[0] + a[(r + 3) * Q] * c[1] + a[(r + 6) * Q] * c[2];
+            }
+          }
+          else
+          {
+            const double wdetJ = gq[0];
+            double A[9];
+  #pragma unroll
+            for (int i = 0; i < 9; i++) A[i] = gq[(1 + i) * Q];
+            if (MASS) AtCAx(A, C, u, wdetJ, v);
+            if (CURL)
+            {
+              double Jd[9];
+              cofactor33(A, Jd);
+              AtCAx(Jd, C + 9, c, wdetJ, cw);
+            }
+          }
+        }
+        // transpose along x, accumulated in registers
+  #pragma unroll
+        for (int i = 0; i < p; i++)
+        {
+          if (MASS) ax1[i] += prm.Bo[qx * p + i] * v[0];
+          if (CURL) ax2[i] += prm.Bo[qx * p + i] * cw[1];
+          if (CURL) ax3[i] -= prm.Bo[qx * p + i] * cw[2];
+        }
+  #pragma unroll
+        for (int i = 0; i < n; i++)
+        {
+          if (MASS) ay1[i] += prm.Bc[qx * n + i] * v[1];
+          if (CURL) ay1[i] += prm.Gc[qx * n + i] * cw[2];
+          if (CURL) ay2[i] -= prm.Bc[qx * n + i] * cw[0];
+          if (MASS) az1[i] += prm.Bc[qx * n + i] * v[2];
+          if (CURL) az1[i] -= prm.Gc[qx * n + i] * cw[1];
+          if (CURL) az3[i] += prm.Bc[qx * n + i] * cw[0];
+        }
+      }
+  #pragma unroll
+      for (int i = 0; i < p; i++)
+      {
+        if (MASS) W[L::YX1 + QQ * i] = ax1[i];
+        if (CURL) W[L::YX2 + QQ * i] = ax2[i];
+        if (CURL) W[L::YX3 + QQ * i] = ax3[i];
+      }
+  #pragma unroll
+      for (int i = 0; i < n; i++)
+      {
+        W[L::YY1 + QQ * i] = ay1[i];
+        if (CURL) W[L::YY2 + QQ * i] = ay2[i];
+        W[L::YZ1 + QQ * i] = az1[i];
+        if (CURL) W[L::YZ3 + QQ * i] = az3[i];
+      }
+    }
+
+    __syncwarp();
+    if (bn < nb && lane == 0)
+    {
+      fence_proxy_async();
+      issue_geom(bn);  // refill the single q-data buffer for the next batch
+    }
+
+    // ------------------------------------------------------------------ phase Yt
+    // x-directed: Za'[j] = sum_qy Bc[qy][j] W1 + Gc[qy][j] W3 ; Zb'[j] = sum_qy Bc[qy][j] W2
+    for (int w = lane; w < NEW * (p * q); w += 32)
+    {
+      const int e = w / (p * q), t = w % (p * q), qz = t % q, i = t / q;
+      const double *v1 = sW + e * ES + L::YX1 + q * t, *v2 = sW + e * ES + L::YX2 + q * t, *v3 = sW + e * ES + L::YX3 + q * t;
+      double w1[q], w2[q], w3[q];
+  #pragma unroll
+      for (int qy = 0; qy < q; qy++)
+      {
+        if (MASS) w1[qy] = v1[qy];
+        if (CURL) w2[qy] = v2[qy];
+        if (CURL) w3[qy] = v3[qy];
+      }
+      double *za = sW + e * ES + L::ZXA + qz + q * i, *zb = sW + e * ES + L::ZXB + qz + q * i;
+  #pragma unroll
+      for (int j = 0; j < n; j++)
+      {
+        double a = 0.0, b = 0.0;
+  #pragma unroll
+        for (int qy = 0; qy < q; qy++)
+        {
+          if (MASS) a += prm.Bc[qy * n + j] * w1[qy];
+          if (CURL) a += prm.Gc[qy * n + j] * w3[qy];
+          if (CURL) b += prm.Bc[qy * n + j] * w2[qy];
+        }
+        za[q * p * j] = a;
+        if (CURL) zb[q * p * j] = b;
+      }
+    }
+    // y-directed: Za'[j<p] = sum_qy Bo[qy][j] W1 ; Zb' = sum_qy Bo[qy][j] W2
+    for (int w = lane; w < NEW * (n * q); w += 32)
+    {
+      const int e = w / (n * q), t = w % (n * q), qz = t % q, i = t / q;
+      const double *v1 = sW + e * ES + L::YY1 + q * t, *v2 = sW + e * ES + L::YY2 + q * t;
+      double w1[q], w2[q];
+  #pragma unroll
+      for (int qy = 0; qy < q; qy++)
+      {
+        w1[qy] = v1[qy];
+        if (CURL) w2[qy] = v2[qy];
+      }
+      double *za = sW + e * ES + L::ZYA + qz + q * i, *zb = sW + e * ES + L::ZYB + qz + q * i;
+  #pragma unroll
+      for (int j = 0; j < p; j++)
+      {
+        double a = 0.0, b = 0.0;
+  #pragma unroll
+        for (int qy = 0; qy < q; qy++)
+        {
+          a += prm.Bo[qy * p + j] * w1[qy];
+          if (CURL) b += prm.Bo[qy * p + j] * w2[qy];
+        }
+        za[q * n * j] = a;
+        if (CURL) zb[q * n * j] = b;
+      }
+    }
+    // z-directed: Za'[j] = sum_qy Bc[qy][j] W1 + Gc[qy][j] W3
+    for (int w = lane; w < NEW * (n * q); w += 32)
+    {
+      const int e = w / (n * q), t = w % (n * q), qz = t % q, i = t / q;
+      const double *v1 = sW + e * ES + L::YZ1 + q * t, *v3 = sW + e * ES + L::YZ3 + q * t;
+      double w1[q], w3[q];
+  #pragma unroll
+      for (int qy = 0; qy < q; qy++)
+      {
+        w1[qy] = v1[qy];
+        if (CURL) w3[qy] = v3[qy];
+      }
+      double *za = sW + e * ES + L::ZZA + qz + q * i;
+  #pragma unroll
+      for (int j = 0; j < n; j++)
+      {
+        double a = 0.0;
+  #pragma unroll
+        for (int qy = 0; qy < q; qy++)
+        {
+          a += prm.Bc[qy * n + j] * w1[qy];
+          if (CURL) a += prm.Gc[qy * n + j] * w3[qy];
+        }
+        za[q * n * j] = a;
+      }
+    }
+
+    __syncwarp();
+
+    // ------------------------------------------------------------------ phase Zt (+ scatter)
+    for (int w = lane; w < NEW * (p * n); w += 32)
+    {
+      const int e = w / (p * n), t = w % (p * n);
+      if (e >= nel) continue;
+      const double *za = sW + e * ES + L::ZXA + q * t, *zb = sW + e * ES + L::ZXB + q * t;
+      double a[q], b[q];
+  #pragma unroll
+      for (int qz = 0; qz < q; qz++)
+      {
+        a[qz] = za[qz];
+        if (CURL) b[qz] = zb[qz];
+      }
+      const int32_t *li = cI + e * PS + t;
+  #pragma unroll
+      for (int k = 0; k < n; k++)
+      {
+        double o = 0.0;
+  #pragma unroll
+        for (int qz = 0; qz < q; qz++)
+        {
+          o += prm.Bc[qz * n + k] * a[qz];
+          if (CURL) o += prm.Gc[qz * n + k] * b[qz];
+        }
+        scatter1(prm.y, li[p * n * k], alpha * o);
+      }
+    }
+    for (int w = lane; w < NEW * (n * p); w += 32)
+    {
+      const int e = w / (n * p), t = w % (n * p);
+      if (e >= nel) continue;
+      const double *za = sW + e * ES + L::ZYA + q * t, *zb = sW + e * ES + L::ZYB + q * t;
+      double a[q], b[q];
+  #pragma unroll
+      for (int qz = 0; qz < q; qz++)
+      {
+        a[qz] = za[qz];
+        if (CURL) b[qz] = zb[qz];
+      }
+      const int32_t *li = cI + e * PS + D3 + t;
+  #pragma unroll
+      for (int k = 0; k < n; k++)
+      {
+        double o = 0.0;
+  #pragma unroll
+        for (int qz = 0; qz < q; qz++)
+        {
+          o += prm.Bc[qz * n + k] * a[qz];
+          if (CURL) o += prm.Gc[qz * n + k] * b[qz];
+        }
+        scatter1(prm.y, li[n * p * k], alpha * o);
+      }
+    }
+    for (int w = lane; w < NEW * (n * n); w += 32)
+    {
+      const int e = w / (n * n), t = w % (n * n);
+      if (e >= nel) continue;
+      const double *za = sW + e * ES + L::ZZA + q * t;
+      double a[q];
+  #pragma unroll
+      for (int qz = 0; qz < q; qz++) a[qz] = za[qz];
+      const int32_t *li = cI + e * PS + 2 * D3 + t;
+  #pragma unroll
+      for (int k = 0; k < p; k++)
+      {
+        double o = 0.0;
+  #pragma unroll
+        for (int qz = 0; qz < q; qz++) o += prm.Bo[qz * p + k] * a[qz];
+        scatter1(prm.y, li[n * n * k], alpha * o);
+      }
+    }
+
+    __syncwarp();
+    if (bn + GW < nb && lane == 0)
+    {
+      fence_proxy_async();
+      issue_idx(bn + GW, slot);
+    }
+  }
+}
+
+template <int P_, int Q_, int KIND, bool ASM>
+int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+{
+  using L = ND3Layout<P_, Q_, KIND, ASM>;
+  // warps per CTA / CTAs per SM from the per-warp shared-memory footprint
+  constexpr int SMEM_SM = 222 * 1024;
+  constexpr int WPS = (SMEM_SM / L::WS) < 1 ? 1 : (SMEM_SM / L::WS > 10 ? 10 : SMEM_SM / L::WS);  // warps per SM (<= 10: 204 regs)
+  constexpr int MINB = (WPS >= 8) ? 2 : 1;
+  constexpr int NW = (WPS / MINB) < 1 ? 1 : WPS / MINB;
+  const size_t shmem = (size_t)NW * L::WS;
+  auto kern = nd_hex_apply3_kernel<P_, Q_, KIND, ASM, NW, MINB>;
+  static bool configured = false;
+  if (!configured)
+  {
+    B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    configured = true;
+  }
+  ND2Params<P_, Q_> prm;
+  prm.lidx = lidx;
+  prm.qd = op->geom->qd;
+  prm.aq = op->aq;
+  prm.mat = op->mat;
+  prm.emat = op->emat;
+  prm.x = x;
+  prm.y = y;
+  prm.alpha = alpha;
+  prm.ne = op->ne;
+  const int n = P_ + 1;
+  for (int i = 0; i < Q_ * P_; i++) prm.Bo[i] = op->h_tab[i];
+  for (int i = 0; i < Q_ * n; i++) prm.Bc[i] = op->h_tab[Q_ * P_ + i];
+  for (int i = 0; i < Q_ * n; i++) prm.Gc[i] = op->h_tab[Q_ * P_ + Q_ * n + i];
+  const int nb = (op->ne + L::NEW - 1) / L::NEW;
+  int grid = op->ctx->sm_count * MINB;
+  if (grid > (nb + NW - 1) / NW) grid = (nb + NW - 1) / NW;
+  kern<<<grid, NW * 32, shmem, s>>>(prm);
+  B2P_CUDA(op->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+
+template <int P_, int Q_>
+int launch3_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+{
+  const bool a = op->assembled;
+  switch (op->kind)
+  {
+    case B2P_CURLCURL:
+      return a ? launch3<P_, Q_, B2P_CURLCURL, true>(op, lidx, alpha, x, y, s)
+               : launch3<P_, Q_, B2P_CURLCURL, false>(op, lidx, alpha, x, y, s);
+    case B2P_ND_MASS:
+      return a ? launch3<P_, Q_, B2P_ND_MASS, true>(op, lidx, alpha, x, y, s)
+               : launch3<P_, Q_, B2P_ND_MASS, false>(op, lidx, alpha, x, y, s);
+    case B2P_CURLCURL_MASS:
+      return a ? launch3<P_, Q_, B2P_CURLCURL_MASS, true>(op, lidx, alpha, x, y, s)
+               : launch3<P_, Q_, B2P_CURLCURL_MASS, false>(op, lidx, alpha, x, y, s);
+  }
+  set_error(op->ctx, "nd_hex_apply: unsupported kind %d", op->kind);
+  return B2P_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int launch_nd_hex_apply2(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+{
+#define B2P_CASE(PP, QQ) \
+  if (op->p == PP && op->q1d == QQ) return launch3_kind<PP, QQ>(op, lidx, alpha, x, y, s);
+  B2P_CASE(1, 2) B2P_CASE(1, 3) B2P_CASE(1, 4) B2P_CASE(1, 5) B2P_CASE(1, 6) B2P_CASE(1, 7)
+  B2P_CASE(2, 3) B2P_CASE(2, 4) B2P_CASE(2, 5) B2P_CASE(2, 6) B2P_CASE(2, 7)
+  B2P_CASE(3, 4) B2P_CASE(3, 5) B2P_CASE(3, 6) B2P_CASE(3, 7)
+  B2P_CASE(4, 5) B2P_CASE(4, 6) B2P_CASE(4, 7)
+  B2P_CASE(5, 6) B2P_CASE(5, 7)
+  B2P_CASE(6, 7)
+#undef B2P_CASE
+  set_error(op->ctx, "nd_hex_apply: no kernel for p=%d q1d=%d", op->p, op->q1d);
+  return B2P_ERR_UNSUPPORTED;
+}
+
+}  // namespace b2p

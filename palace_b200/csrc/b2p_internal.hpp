@@ -57,9 +57,18 @@ struct b2p_ctx
 };
 
 // Geometry q-data of one element block, device resident.
-//   qd[ne][10][Q]: {w detJ, (adjJ^T/detJ)[9] column-major}; attr[ne] int32 (1-based).
+//   qd[ne][10][Q]: {w detJ, (adjJ^T/detJ)[9] column-major}, points in qslot() order; attr[ne] int32 (1-based).
 // (The reference stores attr as an 11th double per point, mesh.cpp:188-195; it is constant per
 // element, so it is kept once per element here.)
+// Storage slot of quadrature point (qx,qy,qz) inside one component row of q-data: x SLOWEST, so that
+// a thread owning a (qy,qz) line reads consecutive words across the warp (conflict-free LDS, see
+// b2p_hex_nd2.cu). Logical point order everywhere else is x fastest (basis.cpp:18-19).
+__host__ __device__ inline int qslot(int q, int qx, int qy, int qz) { return qy + q * (qz + q * qx); }
+__host__ __device__ inline int qslot_of(int q, int iq) { return qslot(q, iq % q, (iq / q) % q, iq / (q * q)); }
+
+// Sentinel in the signed lexicographic restriction: dof masked out (essential BC) -> gathers 0, no scatter.
+#define B2P_SKIP_IDX (-2147483647 - 1)
+
 struct b2p_geom
 {
   b2p_ctx *ctx = nullptr;
@@ -74,11 +83,14 @@ struct b2p_op
   b2p_ctx *ctx = nullptr;
   b2p_geom *geom = nullptr;  // shared (refcounted)
   int kind = 0, p = 0, q1d = 0, ne = 0, P = 0;
+  int PS = 0;  // restriction row stride: P padded to a multiple of 4 (16-byte rows for TMA bulk copies)
   int64_t lsize = 0;
   int assembled = 0;
   // restriction in LEXICOGRAPHIC element order with the sign folded in:
   // lidx[e][l] >= 0 -> +x[lidx], < 0 -> -x[-1-lidx]   (layout [ne][P])
   int32_t *lidx = nullptr;
+  int32_t *lidx_bc = nullptr;  // same with essential dofs replaced by B2P_SKIP_IDX (optional)
+  std::vector<double> h_tab;   // host copy of the packed 1-D tables (kernel parameter block)
   // 1-D tables (device): Bo[q1d][p], Bc[q1d][p+1], Gc[q1d][p+1]
   double *tab = nullptr;  // packed Bo | Bc | Gc
   // coefficients: material tables + per-element material index for the two parts
@@ -88,6 +100,7 @@ struct b2p_op
   // assembled q-data (optional): aq[ne][ncomp][Q], symmetric 6 per part
   double *aq = nullptr;
   int aq_ncomp = 0;
+  int64_t aq_estride = 0;  // doubles per element (even, so every element block is 16-byte aligned for TMA)
   bool owns_coeff = true;  // coarsened operators share the fine operator's coefficient arrays
   b2p_op *parent = nullptr;
   int refcount = 1;
@@ -96,9 +109,10 @@ struct b2p_op
 namespace b2p
 {
 // Kernel launchers (defined in the .cu files).
-int launch_nd_hex_apply(b2p_op *op, const double *x, double *y, cudaStream_t s);
+int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s);
+int launch_nd_hex_apply2(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s);
 int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
-int launch_h1_hex_apply(b2p_op *op, const double *x, double *y, cudaStream_t s);
+int launch_h1_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s);
 int launch_h1_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
 int launch_assemble_qdata(b2p_op *op, cudaStream_t s);
 int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, const double *d_B, const double *d_G,

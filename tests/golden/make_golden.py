@@ -1,0 +1,67 @@
+"""Generates tests/golden/qf_golden.npz by running the REFERENCE's own QFunction headers
+(compiled in place from /root/reference by oracle/Makefile into oracle/_ref) on seeded inputs.
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+The fixture pins the oracle's restated pointwise arithmetic (tests/test_oracle_golden.py) on boxes
+where /root/reference does not exist."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as O  # noqa: E402
+from palace_b200.host import coeff as cf  # noqa: E402
+
+
+def main():
+    ref = O.ref()
+    assert ref is not None, "oracle/_ref not built (needs /root/reference)"
+    rng = np.random.default_rng(20260923)
+    Q = 96
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    # Jacobians: random well-conditioned, column-major components [9][Q]
+    J = np.empty((9, Q))
+    for i in range(Q):
+        M = np.eye(3) * (0.5 + rng.random()) + 0.3 * (rng.random((3, 3)) - 0.5)
+        J[:, i] = M.ravel(order="F")
+    n_attr = 5
+    attr = (1 + rng.integers(0, n_attr, size=Q)).astype(np.float64)
+    qw = 0.1 + rng.random(Q)
+    qdata = np.empty((11, Q))
+    assert ref.ref_build_geom_factor_33(Q, p(attr), p(qw), p(J), p(qdata)) == 0
+    am, mc = cf.test_suite_coefficient(n_attr, "matrix")
+    mc = mc + 0.05 * rng.random(mc.shape)  # non-symmetric on purpose
+    am2 = am.copy()
+    am2[1] = -1  # an unassigned attribute -> zero material (coefficient.cpp:78-88)
+    ctx_mass = cf.coeff_ctx(am, mc, a=1.3)
+    ctx_curl = cf.coeff_ctx(am2, mc[::-1].copy(), a=0.7, transpose=True)
+    ctx_pair = cf.coeff_ctx_pair(ctx_mass, ctx_curl)
+    ctx_id = cf.coeff_ctx(a=2.5)
+    u = rng.random((3, Q)) - 0.5
+    c = rng.random((3, Q)) - 0.5
+    out = dict(J=J, attr=attr, qw=qw, qdata=qdata, ctx_mass=ctx_mass, ctx_curl=ctx_curl, ctx_pair=ctx_pair, ctx_id=ctx_id, u=u, c=c)
+    v = np.empty((3, Q)); w = np.empty((3, Q))
+    assert ref.ref_apply_hcurl_33(p(ctx_mass), Q, p(qdata), p(u), p(v)) == 0
+    out["hcurl_v"] = v.copy()
+    assert ref.ref_apply_hcurl_33(p(ctx_id), Q, p(qdata), p(u), p(v)) == 0
+    out["hcurl_v_identity"] = v.copy()
+    assert ref.ref_apply_hdiv_33(p(ctx_curl), Q, p(qdata), p(c), p(w)) == 0
+    out["hdiv_w"] = w.copy()
+    assert ref.ref_apply_hdivmass_33(p(ctx_pair), Q, p(qdata), p(u), p(c), p(v), p(w)) == 0
+    out["hdivmass_v"], out["hdivmass_w"] = v.copy(), w.copy()
+    qd1 = np.empty((9, Q)); qd2 = np.empty((18, Q))
+    assert ref.ref_build_hcurl_33(p(ctx_mass), Q, p(qdata), p(qd1)) == 0
+    out["build_hcurl"] = qd1.copy()
+    assert ref.ref_build_hdiv_33(p(ctx_curl), Q, p(qdata), p(qd1)) == 0
+    out["build_hdiv"] = qd1.copy()
+    assert ref.ref_build_hdivmass_33(p(ctx_pair), Q, p(qdata), p(qd2)) == 0
+    out["build_hdivmass"] = qd2.copy()
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "qf_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -157,3 +157,29 @@ def test_set_coeff_updates_operator(b2p_ctx):
     yd = torch.empty(prob.nd.ndofs, dtype=torch.float64, device="cuda")
     op.apply(_dev(x), yd)
     assert _rel(yd.cpu().numpy(), common.oracle_apply(prob, kind, blob, x)) < RTOL
+
+
+@pytest.mark.parametrize("kind", [O.CURLCURL, O.ND_MASS, O.CURLCURL_MASS])
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_production_and_simple_kernels_agree_with_alpha_and_mask(b2p_ctx, p, kind):
+    """b2p_op_apply_add_ex: alpha scaling, the essential-dof mask (ParOperator semantics,
+    /root/reference/palace/linalg/rap.cpp:195-234) and the two kernel generations."""
+    prob = common.make_problem(p=p)
+    blob = common.coefficient(kind, 3, "matrix")
+    g = common.gpu_geom(b2p_ctx, prob)
+    op = common.gpu_op(b2p_ctx, g, prob, kind, blob)
+    ess = prob.nd.ess_dofs
+    op.set_essential(ess)
+    rng = np.random.default_rng(8)
+    x = rng.random(prob.nd.ndofs)
+    y0 = rng.random(prob.nd.ndofs)
+    xm = x.copy()
+    xm[ess] = 0.0
+    y_ref = common.oracle_apply(prob, kind, blob, xm)
+    y_ref[ess] = 0.0
+    expect = y0 - 0.75 * y_ref
+    for simple in (False, True):
+        yd = _dev(y0)
+        op.apply_add_ex(-0.75, _dev(x), yd, masked=True, simple_kernel=simple)
+        torch.cuda.synchronize()
+        assert _rel(yd.cpu().numpy(), expect) < RTOL
