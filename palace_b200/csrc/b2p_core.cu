@@ -322,12 +322,18 @@ int set_coeff(b2p_op *op, const void *blob, size_t bytes)
   {
     cudaFree(op->mat);
     cudaFree(op->emat);
+    cudaFree(op->ecoef);
   }
   op->owns_coeff = true;
   op->n_mat = (int)(mats.size() / 9);
   int rc;
   if ((rc = upload(ctx, mats.data(), mats.size(), &op->mat))) return rc;
   if ((rc = upload(ctx, emat.data(), emat.size(), &op->emat))) return rc;
+  std::vector<double> ecoef(18 * (size_t)op->ne);
+  for (int e = 0; e < op->ne; e++)
+    for (int part = 0; part < 2; part++)
+      for (int t = 0; t < 9; t++) ecoef[18 * (size_t)e + 9 * part + t] = mats[9 * (size_t)emat[2 * (size_t)e + part] + t];
+  if ((rc = upload(ctx, ecoef.data(), ecoef.size(), &op->ecoef))) return rc;
   return B2P_SUCCESS;
 }
 
@@ -451,6 +457,7 @@ int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *d, b2p_op **out)
   // share coefficient arrays and assembled q-data with the fine operator (kept alive by refcount)
   op->mat = fine->mat;
   op->emat = fine->emat;
+  op->ecoef = fine->ecoef;
   op->n_mat = fine->n_mat;
   op->aq = fine->aq;
   op->aq_ncomp = fine->aq_ncomp;
@@ -539,7 +546,7 @@ int64_t b2p_op_algorithmic_bytes(b2p_op *op)
   // x read once + y written once per unique dof, 4-byte index per element dof, q-data per point.
   const int64_t Q = op->geom->Q;
   const int64_t per_point = op->assembled ? op->aq_ncomp : 10;
-  return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->PS + 8 * per_point * Q + (op->assembled ? 0 : 8));  // +8: emat
+  return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->PS + 8 * per_point * Q + (op->assembled ? 0 : 144));  // +144: per-element coefficient block
 }
 
 void b2p_op_destroy(b2p_op *op)
@@ -557,6 +564,7 @@ void b2p_op_destroy(b2p_op *op)
   {
     cudaFree(op->mat);
     cudaFree(op->emat);
+    cudaFree(op->ecoef);
     cudaFree(op->aq);
   }
   b2p_geom_destroy(op->geom);

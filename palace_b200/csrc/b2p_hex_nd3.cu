@@ -43,6 +43,7 @@ struct ND2Params
   const double *aq;     // [ne][ncomp][Q] assembled D, x-slowest (or null)
   const double *mat;    // [n_mat][9]
   const int32_t *emat;  // [ne][2]
+  const double *ecoef;  // [ne][18] per-element coefficient matrices (value part, derivative part)
   const double *x;
   double *y;
   double alpha;
@@ -108,11 +109,11 @@ struct ND3Layout
   // per-warp shared memory (bytes), every block 16-byte aligned
   static constexpr int OFF_G = 0;
   static constexpr int OFF_W = OFF_G + NEW * GE * 8;
-  static constexpr int OFF_U = OFF_W + NEW * ES * 8;             // [2][NEW*PS] doubles
-  static constexpr int OFF_I = OFF_U + 2 * NEW * PS * 8;         // [2][NEW*PS] int32
-  static constexpr int OFF_C = OFF_I + 2 * NEW * PS * 4;         // [NEW*18] doubles
-  static constexpr int OFF_B = OFF_C + ((NEW * CE * 8 + 15) & ~15);  // 3 mbarriers
-  static constexpr int WS = (OFF_B + 3 * 8 + 15) & ~15;
+  static constexpr int OFF_U = OFF_W + NEW * ES * 8;             // [NEW*PS] doubles: staged x values
+  static constexpr int OFF_I = OFF_U + NEW * PS * 8;             // [3][NEW*PS] int32: restriction index ring
+  static constexpr int OFF_C = OFF_I + 3 * NEW * PS * 4;         // [NEW*18] doubles
+  static constexpr int OFF_B = OFF_C + ((NEW * CE * 8 + 15) & ~15);  // 4 mbarriers
+  static constexpr int WS = (OFF_B + 4 * 8 + 15) & ~15;
 };
 
 __device__ __forceinline__ void cp_async8(void *dst, const void *src)
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
   int32_t *sI = (int32_t *)(wbase + L::OFF_I);
   double *sC = (double *)(wbase + L::OFF_C);
   uint64_t *bar_g = (uint64_t *)(wbase + L::OFF_B);
-  uint64_t *bar_i = bar_g + 1;  // [2]
+  uint64_t *bar_i = bar_g + 1;  // [3]
 
   const int nb = (prm.ne + NEW - 1) / NEW;  // element batches
   const int GW = gridDim.x * NW;            // warps in the grid
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
     mbar_init(bar_g, 1);
     mbar_init(bar_i + 0, 1);
     mbar_init(bar_i + 1, 1);
+    mbar_init(bar_i + 2, 1);
   }
   __syncwarp();
 
@@ -179,62 +181,55 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
   {
     const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
     const uint32_t bytes = (uint32_t)(nel * GE * sizeof(double));
-    mbar_expect_tx(bar_g, bytes);
+    const uint32_t cbytes = ASM ? 0u : (uint32_t)(nel * 18 * sizeof(double));
+    mbar_expect_tx(bar_g, bytes + cbytes);
     tma_bulk_g2s(sG, (ASM ? prm.aq : prm.qd) + (size_t)e0 * GE, bytes, bar_g);
+    if (!ASM) tma_bulk_g2s(sC, prm.ecoef + (size_t)e0 * 18, cbytes, bar_g);
   };
+  // x values of batch bb -> sU (raw; the sign is applied when they are read)
   auto gather_x = [&](int bb, int slot)
   {
     const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
-    const int32_t *cI = sI + slot * NEW * PS;
-    double *cU = sU + slot * NEW * PS;
-    for (int l = lane; l < nel * PS; l += 32)
+    const int32_t *gI = sI + slot * NEW * PS;
+    constexpr int ITER = (NEW * PS + 31) / 32;
+#pragma unroll
+    for (int r = 0; r < ITER; r++)
     {
-      const int32_t gi = cI[l];
-      if (gi != B2P_SKIP_IDX) cp_async8(cU + l, prm.x + (gi >= 0 ? gi : -1 - gi));
+      const int l = lane + 32 * r;
+      if (l < nel * PS)
+      {
+        const int32_t gi = gI[l];
+        if (gi != B2P_SKIP_IDX) cp_async8(sU + l, prm.x + (gi >= 0 ? gi : -1 - gi));
+      }
     }
+    cp_async_commit();
   };
 
-  uint32_t par_g = 0, par_i = 0;  // mbarrier phase parities (par_i: bit per index slot)
+  // mbarrier phase parities: bit s of par_i for index slot s
+  uint32_t par_g = 0, par_i = 0;
   if (lane == 0)
   {
     issue_idx(b, 0);
     if (b + GW < nb) issue_idx(b + GW, 1);
+    if (b + 2 * GW < nb) issue_idx(b + 2 * GW, 2);
     issue_geom(b);
   }
-  mbar_wait(bar_i + 0, par_i & 1u);
+  mbar_wait(bar_i + 0, 0);
   par_i ^= 1u;
   gather_x(b, 0);
-  cp_async_commit();
 
   const double alpha = prm.alpha;
-  for (int it = 0; b < nb; b += GW, it++)
+  int slot = 0;
+  for (; b < nb; b += GW)
   {
-    const int slot = it & 1, nslot = slot ^ 1;
+    const int nslot = (slot == 2) ? 0 : slot + 1;
     const int bn = b + GW;
     const int e0 = b * NEW, nel = min(NEW, prm.ne - e0);
     const int32_t *cI = sI + slot * NEW * PS;
-    const double *cU = sU + slot * NEW * PS;
+    const double *cU = sU;
+    (void)e0;
 
-    // stage the next batch's x values while this batch computes
-    if (bn < nb)
-    {
-      mbar_wait(bar_i + nslot, (par_i >> nslot) & 1u);
-      par_i ^= (1u << nslot);
-      gather_x(bn, nslot);
-    }
-    cp_async_commit();
-    // coefficient matrices of this batch (tiny, L2 resident): load now, store after phase Z
-    double creg[(NEW * 18 + 31) / 32];
-    if (!ASM)
-    {
-#pragma unroll
-      for (int r = 0; r < (NEW * 18 + 31) / 32; r++)
-      {
-        const int w = lane + 32 * r, e = w / 18, i = w % 18;
-        creg[r] = (w < NEW * 18 && e < nel) ? __ldg(prm.mat + 9 * (size_t)__ldg(prm.emat + 2 * (size_t)(e0 + e) + (i / 9)) + (i % 9)) : 0.0;
-      }
-    }
-    cp_async_wait<1>();
+    cp_async_wait<0>();
     __syncwarp();
 
     // ------------------------------------------------------------------ phase Z (gather + z)
@@ -300,13 +295,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
       }
     }
 
-    if (!ASM)
-    {
-#pragma unroll
-      for (int r = 0; r < (NEW * 18 + 31) / 32; r++)
-        if (lane + 32 * r < NEW * 18) sC[lane + 32 * r] = creg[r];
-    }
     __syncwarp();
+    // the staged x values are consumed: gather the next batch's while this one computes
+    if (bn < nb)
+    {
+      mbar_wait(bar_i + nslot, (par_i >> nslot) & 1u);
+      par_i ^= (1u << nslot);
+      gather_x(bn, nslot);
+    }
 
     // ------------------------------------------------------------------ phase Y
     // items t' = qz + q*i ; reads Z[qz + q*(i + ni*j)] over j ; writes V[qy + q*t'] (thread-contiguous)
@@ -396,60 +392,65 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
 
     // ------------------------------------------------------------------ phase XDX
     // item s = qy + q*qz: reads V[s + q^2 i]; all qx of this line live in registers.
+    // Three sub-steps keep the live register set small: (1) x-contraction of the 7 staged arrays
+    // into u, curl u for all qx; (2) pointwise D in place; (3) transposed x-contraction, each
+    // output formed from the q values and stored at once.
     for (int w = lane; w < NEW * (QQ); w += 32)
     {
       const int e = w / QQ, s = w % QQ;
       double *W = sW + e * ES + s;
-      double x1[p], x2[p], x3[p], y1[n], y2[n], z1[n], z3[n];
-  #pragma unroll
-      for (int i = 0; i < p; i++)
+      double uu[q][3], cc[q][3];
       {
-        if (MASS) x1[i] = W[L::YX1 + QQ * i];
-        if (CURL) x2[i] = W[L::YX2 + QQ * i];
-        if (CURL) x3[i] = W[L::YX3 + QQ * i];
-      }
-  #pragma unroll
-      for (int i = 0; i < n; i++)
-      {
-        y1[i] = W[L::YY1 + QQ * i];
-        if (CURL) y2[i] = W[L::YY2 + QQ * i];
-        z1[i] = W[L::YZ1 + QQ * i];
-        if (CURL) z3[i] = W[L::YZ3 + QQ * i];
-      }
-      double ax1[p], ax2[p], ax3[p], ay1[n], ay2[n], az1[n], az3[n];
-  #pragma unroll
-      for (int i = 0; i < p; i++) ax1[i] = ax2[i] = ax3[i] = 0.0;
-  #pragma unroll
-      for (int i = 0; i < n; i++) ay1[i] = ay2[i] = az1[i] = az3[i] = 0.0;
-      const double *g = sG + e * GE + s;
-      const double *C = sC + e * 18;
-  #pragma unroll
-      for (int qx = 0; qx < q; qx++)
-      {
-        double u[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+        double x1[p], x2[p], x3[p], y1[n], y2[n], z1[n], z3[n];
+#pragma unroll
+        for (int i = 0; i < p; i++)
         {
-          double dzux = 0, dyux = 0, dzuy = 0, dxuy = 0, dyuz = 0, dxuz = 0;
-  #pragma unroll
+          if (MASS) x1[i] = W[L::YX1 + QQ * i];
+          if (CURL) x2[i] = W[L::YX2 + QQ * i];
+          if (CURL) x3[i] = W[L::YX3 + QQ * i];
+        }
+#pragma unroll
+        for (int i = 0; i < n; i++)
+        {
+          y1[i] = W[L::YY1 + QQ * i];
+          if (CURL) y2[i] = W[L::YY2 + QQ * i];
+          z1[i] = W[L::YZ1 + QQ * i];
+          if (CURL) z3[i] = W[L::YZ3 + QQ * i];
+        }
+#pragma unroll
+        for (int qx = 0; qx < q; qx++)
+        {
+          double u0 = 0, u1 = 0, u2 = 0, dzux = 0, dyux = 0, dzuy = 0, dxuy = 0, dyuz = 0, dxuz = 0;
+#pragma unroll
           for (int i = 0; i < p; i++)
           {
-            if (MASS) u[0] += prm.Bo[qx * p + i] * x1[i];
+            if (MASS) u0 += prm.Bo[qx * p + i] * x1[i];
             if (CURL) dzux += prm.Bo[qx * p + i] * x2[i];
             if (CURL) dyux += prm.Bo[qx * p + i] * x3[i];
           }
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < n; i++)
           {
-            if (MASS) u[1] += prm.Bc[qx * n + i] * y1[i];
+            if (MASS) u1 += prm.Bc[qx * n + i] * y1[i];
             if (CURL) dzuy += prm.Bc[qx * n + i] * y2[i];
             if (CURL) dxuy += prm.Gc[qx * n + i] * y1[i];
-            if (MASS) u[2] += prm.Bc[qx * n + i] * z1[i];
+            if (MASS) u2 += prm.Bc[qx * n + i] * z1[i];
             if (CURL) dyuz += prm.Bc[qx * n + i] * z3[i];
             if (CURL) dxuz += prm.Gc[qx * n + i] * z1[i];
           }
-          c[0] = dyuz - dzuy;
-          c[1] = dzux - dxuz;
-          c[2] = dxuy - dyux;
+          uu[qx][0] = u0;
+          uu[qx][1] = u1;
+          uu[qx][2] = u2;
+          cc[qx][0] = dyuz - dzuy;
+          cc[qx][1] = dzux - dxuz;
+          cc[qx][2] = dxuy - dyux;
         }
+      }
+      const double *g = sG + e * GE + s;
+      const double *C = sC + e * 18;
+#pragma unroll
+      for (int qx = 0; qx < q; qx++)
+      {
         double v[3] = {0, 0, 0}, cw[3] = {0, 0, 0};
         if (e < nel)
         {
@@ -459,67 +460,74 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
             const double *a = gq;
             if (MASS)
             {
-  #pragma unroll
-              for (int r = 0; r < 3; r++) v[r] = a[(r)*Q] * u[0] + a[(r + 3) * Q] * u[1] + a[(r + 6) * Q] * u[2];
+#pragma unroll
+              for (int r = 0; r < 3; r++) v[r] = a[(r)*Q] * uu[qx][0] + a[(r + 3) * Q] * uu[qx][1] + a[(r + 6) * Q] * uu[qx][2];
               a += 9 * Q;
             }
             if (CURL)
             {
-  #pragma unroll
-              for (int r = 0; r < 3; r++) cw[r] = a[(r)*Q] * c[0] + a[(r + 3) * Q] * c[1] + a[(r + 6) * Q] * c[2];
+#pragma unroll
+              for (int r = 0; r < 3; r++) cw[r] = a[(r)*Q] * cc[qx][0] + a[(r + 3) * Q] * cc[qx][1] + a[(r + 6) * Q] * cc[qx][2];
             }
           }
           else
           {
             const double wdetJ = gq[0];
             double A[9];
-  #pragma unroll
+#pragma unroll
             for (int i = 0; i < 9; i++) A[i] = gq[(1 + i) * Q];
-            if (MASS) AtCAx(A, C, u, wdetJ, v);
+            if (MASS) AtCAx(A, C, uu[qx], wdetJ, v);
             if (CURL)
             {
               double Jd[9];
               cofactor33(A, Jd);
-              AtCAx(Jd, C + 9, c, wdetJ, cw);
+              AtCAx(Jd, C + 9, cc[qx], wdetJ, cw);
             }
           }
         }
-        // transpose along x, accumulated in registers
-  #pragma unroll
-        for (int i = 0; i < p; i++)
+#pragma unroll
+        for (int r = 0; r < 3; r++)
         {
-          if (MASS) ax1[i] += prm.Bo[qx * p + i] * v[0];
-          if (CURL) ax2[i] += prm.Bo[qx * p + i] * cw[1];
-          if (CURL) ax3[i] -= prm.Bo[qx * p + i] * cw[2];
-        }
-  #pragma unroll
-        for (int i = 0; i < n; i++)
-        {
-          if (MASS) ay1[i] += prm.Bc[qx * n + i] * v[1];
-          if (CURL) ay1[i] += prm.Gc[qx * n + i] * cw[2];
-          if (CURL) ay2[i] -= prm.Bc[qx * n + i] * cw[0];
-          if (MASS) az1[i] += prm.Bc[qx * n + i] * v[2];
-          if (CURL) az1[i] -= prm.Gc[qx * n + i] * cw[1];
-          if (CURL) az3[i] += prm.Bc[qx * n + i] * cw[0];
+          uu[qx][r] = v[r];
+          cc[qx][r] = cw[r];
         }
       }
-  #pragma unroll
+      // transposed x-contraction: outputs formed one at a time
+#pragma unroll
       for (int i = 0; i < p; i++)
       {
-        if (MASS) W[L::YX1 + QQ * i] = ax1[i];
-        if (CURL) W[L::YX2 + QQ * i] = ax2[i];
-        if (CURL) W[L::YX3 + QQ * i] = ax3[i];
+        double a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int qx = 0; qx < q; qx++)
+        {
+          if (MASS) a1 += prm.Bo[qx * p + i] * uu[qx][0];
+          if (CURL) a2 += prm.Bo[qx * p + i] * cc[qx][1];
+          if (CURL) a3 -= prm.Bo[qx * p + i] * cc[qx][2];
+        }
+        if (MASS) W[L::YX1 + QQ * i] = a1;
+        if (CURL) W[L::YX2 + QQ * i] = a2;
+        if (CURL) W[L::YX3 + QQ * i] = a3;
       }
-  #pragma unroll
+#pragma unroll
       for (int i = 0; i < n; i++)
       {
-        W[L::YY1 + QQ * i] = ay1[i];
-        if (CURL) W[L::YY2 + QQ * i] = ay2[i];
-        W[L::YZ1 + QQ * i] = az1[i];
-        if (CURL) W[L::YZ3 + QQ * i] = az3[i];
+        double b1 = 0, b2 = 0, c1 = 0, c3 = 0;
+#pragma unroll
+        for (int qx = 0; qx < q; qx++)
+        {
+          if (MASS) b1 += prm.Bc[qx * n + i] * uu[qx][1];
+          if (CURL) b1 += prm.Gc[qx * n + i] * cc[qx][2];
+          if (CURL) b2 -= prm.Bc[qx * n + i] * cc[qx][0];
+          if (MASS) c1 += prm.Bc[qx * n + i] * uu[qx][2];
+          if (CURL) c1 -= prm.Gc[qx * n + i] * cc[qx][1];
+          if (CURL) c3 += prm.Bc[qx * n + i] * cc[qx][0];
+        }
+        W[L::YY1 + QQ * i] = b1;
+        if (CURL) W[L::YY2 + QQ * i] = b2;
+        W[L::YZ1 + QQ * i] = c1;
+        if (CURL) W[L::YZ3 + QQ * i] = c3;
       }
     }
-
     __syncwarp();
     if (bn < nb && lane == 0)
     {
@@ -686,11 +694,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
     }
 
     __syncwarp();
-    if (bn + GW < nb && lane == 0)
+    if (b + 3 * GW < nb && lane == 0)
     {
       fence_proxy_async();
-      issue_idx(bn + GW, slot);
+      issue_idx(b + 3 * GW, slot);  // this batch's index slot is free again
     }
+    slot = nslot;
   }
 }
 
@@ -717,6 +726,7 @@ int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   prm.aq = op->aq;
   prm.mat = op->mat;
   prm.emat = op->emat;
+  prm.ecoef = op->ecoef;
   prm.x = x;
   prm.y = y;
   prm.alpha = alpha;
