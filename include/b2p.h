@@ -131,6 +131,100 @@ int64_t b2p_op_lsize(b2p_op *op);
 int64_t b2p_op_algorithmic_bytes(b2p_op *op);
 void b2p_op_destroy(b2p_op *op);
 
+/* ---- element-local interpolators (P_l, G): replaces fem/bilinearform.cpp:203-282 + AssembleCeedInterpolator ---- */
+typedef struct
+{
+  int in_off;          /* offset of this component's input block inside the lexicographic input element vector */
+  int in_n[3];         /* input block dims (x fastest) */
+  int out_off;         /* offset of the output block */
+  int out_n[3];        /* output block dims */
+  const double *A[3];  /* 1-D matrices A_x, A_y, A_z, row-major [out_n[d]][in_n[d]] */
+} b2p_interp_comp;
+
+typedef struct
+{
+  int ne;
+  int in_P;                  /* input (trial) space: native restriction + GetDofMap(), as in b2p_op_desc */
+  int64_t in_lsize;
+  const int32_t *in_idx;
+  const int8_t *in_orient;
+  const int32_t *in_dof_map;
+  int out_P;                 /* output (test) space */
+  int64_t out_lsize;
+  const int32_t *out_idx;
+  const int8_t *out_orient;
+  const int32_t *out_dof_map;
+  int ncomp;                 /* output vector components (1: H1, 3: ND) */
+  b2p_interp_comp comps[3];
+} b2p_interp_desc;
+
+int b2p_interp_create(b2p_ctx *ctx, const b2p_interp_desc *desc, b2p_interp **out);
+/* y += alpha * (1/mult) .* I x   (transpose = 0, ceed::Operator::AddMult with dof multiplicity, operator.cpp:182-212)
+ * y += alpha * I^T ((1/mult) .* x) (transpose = 1) */
+int b2p_interp_apply_add(b2p_interp *it, int transpose, double alpha, const double *x, double *y, b2p_stream s);
+void b2p_interp_destroy(b2p_interp *it);
+
+/* ---- shared-dof exchange between partitions (P / P^T of ParOperator, linalg/rap.cpp:212-222) ---- */
+/* L-vector layout on every rank: [n_true owned | n_ghost ghosts grouped by owner rank in nbr_ranks order].
+ * send_idx: owned indices whose values neighbour k holds as ghosts, concatenated (send_counts[k] each), in the
+ * same (global dof) order as that neighbour's ghost segment. */
+int b2p_halo_create(b2p_ctx *ctx, int64_t n_true, int64_t n_ghost, int n_nbr, const int32_t *nbr_ranks,
+                    const int64_t *send_counts, const int32_t *send_idx, const int64_t *recv_counts, b2p_halo **out);
+int b2p_halo_forward(b2p_halo *h, double *lvec); /* owners -> ghosts (P) */
+int b2p_halo_reverse(b2p_halo *h, double *lvec); /* ghosts added into owners (P^T) */
+void b2p_halo_destroy(b2p_halo *h);
+
+/* ---- device-resident linear algebra (replaces linalg/vector.cpp kernels + MPI_Allreduce) ---- */
+int b2p_ctx_set_stream(b2p_ctx *ctx, b2p_stream s); /* stream used by everything below */
+int b2p_vec_axpby(b2p_ctx *ctx, int64_t n, double a, const double *x, double b, double *y);                 /* y = a x + b y  (vector.cpp:276-377) */
+int b2p_vec_axpbypcz(b2p_ctx *ctx, int64_t n, double a, const double *x, double b, const double *y, double g, double *z);
+int b2p_vec_dot(b2p_ctx *ctx, int64_t n, const double *x, const double *y, double *out);                    /* global: all-reduced over ranks */
+int b2p_vec_sum(b2p_ctx *ctx, int64_t n, const double *x, double *out);
+int b2p_vec_set_sub(b2p_ctx *ctx, double *y, const int32_t *idx_dev, int64_t nidx, double v);               /* vector.cpp:461-527 */
+int b2p_vec_set_random(b2p_ctx *ctx, int64_t n, double *y, uint64_t seed);
+/* Gram-Schmidt of w against V[0..m) (linalg/orthog.hpp:41-89): type 0 MGS, 1 CGS, 2 CGS2; H[m] on the host */
+int b2p_vec_orthogonalize(b2p_ctx *ctx, int type, int64_t n, int m, const double *const *V, double *w, double *H);
+
+/* ---- operators on true-dof vectors ---- */
+typedef struct b2p_operator b2p_operator;
+/* ParOperator over sum_i coef_i * op_i (BuildParSumOperator, rap.cpp:764-829) with essential true dofs;
+ * diag_policy 0 = DIAG_ZERO, 1 = DIAG_ONE; halo may be NULL (single partition). */
+int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coefs,
+                     const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_halo *halo, b2p_operator **out);
+int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_operator **out);
+int b2p_operator_mult(b2p_operator *A, const double *x, double *y);
+int b2p_operator_mult_transpose(b2p_operator *A, const double *x, double *y);
+int b2p_operator_add_mult(b2p_operator *A, const double *x, double *y, double a);
+int b2p_operator_assemble_diagonal(b2p_operator *A, double *d);
+int64_t b2p_operator_height(b2p_operator *A);
+int64_t b2p_operator_width(b2p_operator *A);
+void b2p_operator_destroy(b2p_operator *A);
+
+/* ---- solvers (palace::Solver<Operator>, linalg/solver.hpp:21-65) ---- */
+typedef struct b2p_solver b2p_solver;
+int b2p_solver_jacobi(b2p_ctx *ctx, double omega, double sf_max, b2p_solver **out);                                  /* jacobi.cpp */
+int b2p_solver_chebyshev(b2p_ctx *ctx, int smooth_it, int order, double sf_max, double sf_min, int fourth_kind,
+                         b2p_solver **out);                                                                           /* chebyshev.cpp */
+int b2p_solver_distrelax(b2p_ctx *ctx, b2p_operator *G, int smooth_it, int cheby_smooth_it, int cheby_order, double sf_max,
+                         double sf_min, int fourth_kind, b2p_solver **out);                                           /* distrelaxation.cpp */
+int b2p_solver_distrelax_set_operators(b2p_solver *s, b2p_operator *A, b2p_operator *A_G);
+/* coarse: level-0 solver (ownership moves to the multigrid solver); P[n_levels-1]; G[n_levels] or NULL */
+int b2p_solver_gmg(b2p_ctx *ctx, b2p_solver *coarse, int n_levels, b2p_operator *const *P, b2p_operator *const *G, int cycle_it,
+                   int smooth_it, int cheby_order, double sf_max, double sf_min, int fourth_kind, b2p_solver **out);  /* gmg.cpp */
+int b2p_solver_gmg_set_operators(b2p_solver *s, b2p_operator *const *A, b2p_operator *const *A_aux);
+/* type 0 CG, 1 GMRES, 2 FGMRES (iterative.cpp) */
+int b2p_solver_krylov(b2p_ctx *ctx, int type, b2p_solver **out);
+int b2p_solver_krylov_config(b2p_solver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side);
+int b2p_solver_set_preconditioner(b2p_solver *s, b2p_solver *pc);
+int b2p_solver_set_operator(b2p_solver *s, b2p_operator *A);
+int b2p_solver_set_initial_guess(b2p_solver *s, int flag);
+int b2p_solver_mult(b2p_solver *s, const double *x, double *y);
+int b2p_solver_mult2(b2p_solver *s, const double *x, double *y, double *r);
+int b2p_solver_mult_transpose2(b2p_solver *s, const double *x, double *y, double *r);
+int b2p_solver_stats(b2p_solver *s, int *its, double *initial_res, double *final_res, int *converged);
+int b2p_solver_lambda_max(b2p_solver *s, double *out); /* Chebyshev: estimated lambda_max(D^-1 A) * sf_max */
+void b2p_solver_destroy(b2p_solver *s);
+
 #ifdef __cplusplus
 }
 #endif

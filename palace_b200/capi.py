@@ -211,3 +211,256 @@ class Op:
         if self.h:
             lib().b2p_op_destroy(self.h)
             self.h = None
+
+
+# ------------------------------------------------------------------------------------------------
+# Interpolators, halo exchange, true-dof operators and solvers (linear algebra layer of include/b2p.h)
+# ------------------------------------------------------------------------------------------------
+
+
+class InterpComp(C.Structure):
+    _fields_ = [("in_off", C.c_int), ("in_n", C.c_int * 3), ("out_off", C.c_int), ("out_n", C.c_int * 3), ("A", C.c_void_p * 3)]
+
+
+class InterpDesc(C.Structure):
+    _fields_ = [
+        ("ne", C.c_int), ("in_P", C.c_int), ("in_lsize", C.c_int64), ("in_idx", C.c_void_p), ("in_orient", C.c_void_p),
+        ("in_dof_map", C.c_void_p), ("out_P", C.c_int), ("out_lsize", C.c_int64), ("out_idx", C.c_void_p),
+        ("out_orient", C.c_void_p), ("out_dof_map", C.c_void_p), ("ncomp", C.c_int), ("comps", InterpComp * 3),
+    ]
+
+
+class Interp:
+    """Element-local tensor interpolator between two hex spaces (p-prolongation, discrete gradient)."""
+
+    def __init__(self, ctx, in_space, out_space, comps):
+        """in_space/out_space: dicts(P, lsize, idx, orient, dof_map); comps: list of
+        dict(in_off, in_n, out_off, out_n, A=[Ax, Ay, Az])."""
+        keep = []
+        d = InterpDesc()
+        for pre, sp in (("in", in_space), ("out", out_space)):
+            idx = _np(sp["idx"], np.int32)
+            keep.append(idx)
+            setattr(d, pre + "_P", int(sp["P"]))
+            setattr(d, pre + "_lsize", int(sp["lsize"]))
+            setattr(d, pre + "_idx", _ptr(idx))
+            if sp.get("orient") is not None:
+                o = _np(sp["orient"], np.int8)
+                keep.append(o)
+                setattr(d, pre + "_orient", _ptr(o))
+            if sp.get("dof_map") is not None:
+                m = _np(sp["dof_map"], np.int32)
+                keep.append(m)
+                setattr(d, pre + "_dof_map", _ptr(m))
+        d.ne = _np(in_space["idx"], np.int32).shape[0]
+        d.ncomp = len(comps)
+        for c, cc in enumerate(comps):
+            d.comps[c].in_off, d.comps[c].out_off = int(cc["in_off"]), int(cc["out_off"])
+            for a in range(3):
+                d.comps[c].in_n[a], d.comps[c].out_n[a] = int(cc["in_n"][a]), int(cc["out_n"][a])
+                A = _np(cc["A"][a], np.float64)
+                assert A.shape == (cc["out_n"][a], cc["in_n"][a])
+                keep.append(A)
+                d.comps[c].A[a] = A.ctypes.data
+        h = C.c_void_p()
+        _chk(lib().b2p_interp_create(ctx.h, C.byref(d), C.byref(h)), ctx.h)
+        self.ctx, self.h = ctx, h
+        self.in_lsize, self.out_lsize = int(in_space["lsize"]), int(out_space["lsize"])
+
+    def apply_add(self, x, y, transpose=False, alpha=1.0, stream=None):
+        _chk(lib().b2p_interp_apply_add(self.h, int(transpose), C.c_double(alpha), _vp(x), _vp(y), _stream(stream)), self.ctx.h)
+
+
+class Halo:
+    def __init__(self, ctx, n_true, n_ghost, nbr_ranks, send_counts, send_idx, recv_counts):
+        nbr = _np(nbr_ranks, np.int32)
+        sc, rc = _np(send_counts, np.int64), _np(recv_counts, np.int64)
+        si = _np(send_idx, np.int32)
+        h = C.c_void_p()
+        _chk(lib().b2p_halo_create(ctx.h, C.c_int64(n_true), C.c_int64(n_ghost), int(nbr.size), _ptr(nbr), _ptr(sc), _ptr(si), _ptr(rc),
+                                   C.byref(h)), ctx.h)
+        self.ctx, self.h = ctx, h
+
+    def forward(self, lvec):
+        _chk(lib().b2p_halo_forward(self.h, _vp(lvec)), self.ctx.h)
+
+    def reverse(self, lvec):
+        _chk(lib().b2p_halo_reverse(self.h, _vp(lvec)), self.ctx.h)
+
+
+def set_stream(ctx, stream=None):
+    _chk(lib().b2p_ctx_set_stream(ctx.h, _stream(stream)), ctx.h)
+
+
+def vec_dot(ctx, x, y):
+    out = C.c_double()
+    _chk(lib().b2p_vec_dot(ctx.h, C.c_int64(x.numel()), _vp(x), _vp(y), C.byref(out)), ctx.h)
+    return out.value
+
+
+def vec_sum(ctx, x):
+    out = C.c_double()
+    _chk(lib().b2p_vec_sum(ctx.h, C.c_int64(x.numel()), _vp(x), C.byref(out)), ctx.h)
+    return out.value
+
+
+def vec_axpby(ctx, a, x, b, y):
+    _chk(lib().b2p_vec_axpby(ctx.h, C.c_int64(x.numel()), C.c_double(a), _vp(x), C.c_double(b), _vp(y)), ctx.h)
+
+
+def vec_axpbypcz(ctx, a, x, b, y, g, z):
+    _chk(lib().b2p_vec_axpbypcz(ctx.h, C.c_int64(x.numel()), C.c_double(a), _vp(x), C.c_double(b), _vp(y), C.c_double(g), _vp(z)), ctx.h)
+
+
+def vec_orthogonalize(ctx, kind, V, w):
+    """Gram-Schmidt of w against the list V (0 MGS, 1 CGS, 2 CGS2); returns H (numpy)."""
+    m = len(V)
+    ptrs = (C.c_void_p * m)(*[v.data_ptr() for v in V])
+    H = np.zeros(m)
+    _chk(lib().b2p_vec_orthogonalize(ctx.h, int(kind), C.c_int64(w.numel()), m, ptrs, _vp(w), _ptr(H)), ctx.h)
+    return H
+
+
+class Operator:
+    """True-dof operator handle (ParOperator / interpolator)."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    @classmethod
+    def par(cls, ctx, tsize, lsize, ops, coefs=None, ess_tdofs=None, diag_policy=1, halo=None):
+        n = len(ops)
+        arr = (C.c_void_p * n)(*[o.h for o in ops])
+        cf = _np(coefs if coefs is not None else np.ones(n), np.float64)
+        ess = _np(ess_tdofs if ess_tdofs is not None else np.zeros(0), np.int32)
+        h = C.c_void_p()
+        _chk(lib().b2p_operator_par(ctx.h, C.c_int64(tsize), C.c_int64(lsize), n, arr, _ptr(cf), _ptr(ess), C.c_int64(ess.size),
+                                    int(diag_policy), halo.h if halo else None, C.byref(h)), ctx.h)
+        o = cls(ctx, h)
+        o._keep = list(ops)
+        return o
+
+    @classmethod
+    def interp(cls, ctx, it: Interp):
+        h = C.c_void_p()
+        _chk(lib().b2p_operator_interp(ctx.h, it.h, C.byref(h)), ctx.h)
+        o = cls(ctx, h)
+        o._keep = [it]
+        return o
+
+    def mult(self, x, y):
+        _chk(lib().b2p_operator_mult(self.h, _vp(x), _vp(y)), self.ctx.h)
+
+    def mult_transpose(self, x, y):
+        _chk(lib().b2p_operator_mult_transpose(self.h, _vp(x), _vp(y)), self.ctx.h)
+
+    def add_mult(self, x, y, a=1.0):
+        _chk(lib().b2p_operator_add_mult(self.h, _vp(x), _vp(y), C.c_double(a)), self.ctx.h)
+
+    def assemble_diagonal(self, d):
+        _chk(lib().b2p_operator_assemble_diagonal(self.h, _vp(d)), self.ctx.h)
+
+    @property
+    def height(self):
+        lib().b2p_operator_height.restype = C.c_int64
+        return int(lib().b2p_operator_height(self.h))
+
+
+CG, GMRES, FGMRES = 0, 1, 2
+MGS, CGS, CGS2 = 0, 1, 2
+PC_RIGHT, PC_LEFT = 0, 1
+
+
+class Solver:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+        self._keep = []
+
+    @classmethod
+    def jacobi(cls, ctx, omega=1.0, sf_max=1.0):
+        h = C.c_void_p()
+        _chk(lib().b2p_solver_jacobi(ctx.h, C.c_double(omega), C.c_double(sf_max), C.byref(h)), ctx.h)
+        return cls(ctx, h)
+
+    @classmethod
+    def chebyshev(cls, ctx, smooth_it=1, order=4, sf_max=1.0, sf_min=0.0, fourth_kind=True):
+        h = C.c_void_p()
+        _chk(lib().b2p_solver_chebyshev(ctx.h, smooth_it, order, C.c_double(sf_max), C.c_double(sf_min), int(fourth_kind), C.byref(h)), ctx.h)
+        return cls(ctx, h)
+
+    @classmethod
+    def distrelax(cls, ctx, G: Operator, smooth_it=1, cheby_smooth_it=1, cheby_order=4, sf_max=1.0, sf_min=0.0, fourth_kind=True):
+        h = C.c_void_p()
+        _chk(lib().b2p_solver_distrelax(ctx.h, G.h, smooth_it, cheby_smooth_it, cheby_order, C.c_double(sf_max), C.c_double(sf_min),
+                                        int(fourth_kind), C.byref(h)), ctx.h)
+        s = cls(ctx, h)
+        s._keep.append(G)
+        return s
+
+    def distrelax_set_operators(self, A: Operator, A_G: Operator):
+        self._keep += [A, A_G]
+        _chk(lib().b2p_solver_distrelax_set_operators(self.h, A.h, A_G.h), self.ctx.h)
+
+    @classmethod
+    def gmg(cls, ctx, coarse, P, G=None, cycle_it=1, smooth_it=1, cheby_order=4, sf_max=1.0, sf_min=0.0, fourth_kind=True):
+        n_levels = len(P) + 1
+        Parr = (C.c_void_p * max(1, len(P)))(*[p.h for p in P])
+        Garr = None
+        if G is not None:
+            Garr = (C.c_void_p * n_levels)(*[(g.h if g is not None else None) for g in G])
+        h = C.c_void_p()
+        _chk(lib().b2p_solver_gmg(ctx.h, coarse.h, n_levels, Parr, Garr, cycle_it, smooth_it, cheby_order, C.c_double(sf_max),
+                                  C.c_double(sf_min), int(fourth_kind), C.byref(h)), ctx.h)
+        s = cls(ctx, h)
+        s._keep += [coarse, list(P), G]
+        s.n_levels = n_levels
+        return s
+
+    def gmg_set_operators(self, A, A_aux=None):
+        n = len(A)
+        Aarr = (C.c_void_p * n)(*[a.h for a in A])
+        Garr = None
+        if A_aux is not None:
+            Garr = (C.c_void_p * n)(*[(a.h if a is not None else None) for a in A_aux])
+        self._keep += [list(A), A_aux]
+        _chk(lib().b2p_solver_gmg_set_operators(self.h, Aarr, Garr), self.ctx.h)
+
+    @classmethod
+    def krylov(cls, ctx, kind, rel_tol=1e-6, abs_tol=0.0, max_it=100, max_dim=-1, orthog=MGS, pc_side=PC_RIGHT):
+        h = C.c_void_p()
+        _chk(lib().b2p_solver_krylov(ctx.h, int(kind), C.byref(h)), ctx.h)
+        s = cls(ctx, h)
+        _chk(lib().b2p_solver_krylov_config(h, C.c_double(rel_tol), C.c_double(abs_tol), int(max_it), int(max_dim), int(orthog),
+                                            int(pc_side)), ctx.h)
+        return s
+
+    def set_preconditioner(self, pc):
+        self._keep.append(pc)
+        _chk(lib().b2p_solver_set_preconditioner(self.h, pc.h if pc else None), self.ctx.h)
+
+    def set_operator(self, A: Operator):
+        self._keep.append(A)
+        _chk(lib().b2p_solver_set_operator(self.h, A.h), self.ctx.h)
+
+    def set_initial_guess(self, flag):
+        _chk(lib().b2p_solver_set_initial_guess(self.h, int(flag)), self.ctx.h)
+
+    def mult(self, x, y):
+        _chk(lib().b2p_solver_mult(self.h, _vp(x), _vp(y)), self.ctx.h)
+
+    def mult2(self, x, y, r):
+        _chk(lib().b2p_solver_mult2(self.h, _vp(x), _vp(y), _vp(r)), self.ctx.h)
+
+    def mult_transpose2(self, x, y, r):
+        _chk(lib().b2p_solver_mult_transpose2(self.h, _vp(x), _vp(y), _vp(r)), self.ctx.h)
+
+    def stats(self):
+        its, conv = C.c_int(), C.c_int()
+        r0, r1 = C.c_double(), C.c_double()
+        _chk(lib().b2p_solver_stats(self.h, C.byref(its), C.byref(r0), C.byref(r1), C.byref(conv)), self.ctx.h)
+        return dict(its=its.value, initial_res=r0.value, final_res=r1.value, converged=bool(conv.value))
+
+    def lambda_max(self):
+        out = C.c_double()
+        _chk(lib().b2p_solver_lambda_max(self.h, C.byref(out)), self.ctx.h)
+        return out.value

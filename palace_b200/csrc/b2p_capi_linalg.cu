@@ -1,0 +1,296 @@
+// C ABI of the linear-algebra / solver layer (include/b2p.h): thin handles over the C++ classes.
+#include "b2p_linalg.hpp"
+
+using namespace b2p;
+
+struct b2p_halo;
+namespace b2p
+{
+Halo *halo_of(b2p_halo *h);
+}
+
+struct b2p_operator
+{
+  std::unique_ptr<Operator> op;
+};
+struct b2p_solver
+{
+  std::unique_ptr<Solver> s;
+  bool owned_elsewhere = false;
+};
+
+#define B2P_TRY(ctx, stmt)                                   \
+  do                                                         \
+  {                                                          \
+    stmt;                                                    \
+    cudaError_t e__ = cudaPeekAtLastError();                 \
+    if (e__ != cudaSuccess)                                  \
+    {                                                        \
+      set_error(ctx, "CUDA error: %s", cudaGetErrorString(e__)); \
+      return B2P_ERR_CUDA;                                   \
+    }                                                        \
+  } while (0)
+
+extern "C"
+{
+
+int b2p_ctx_set_stream(b2p_ctx *ctx, b2p_stream s)
+{
+  if (!ctx) return B2P_ERR_ARG;
+  ctx->stream = (cudaStream_t)s;
+  return B2P_SUCCESS;
+}
+
+int b2p_vec_axpby(b2p_ctx *ctx, int64_t n, double a, const double *x, double b, double *y)
+{
+  B2P_TRY(ctx, vec::axpby(ctx, a, x, b, y, n));
+  return B2P_SUCCESS;
+}
+int b2p_vec_axpbypcz(b2p_ctx *ctx, int64_t n, double a, const double *x, double b, const double *y, double g, double *z)
+{
+  B2P_TRY(ctx, vec::axpbypcz(ctx, a, x, b, y, g, z, n));
+  return B2P_SUCCESS;
+}
+int b2p_vec_dot(b2p_ctx *ctx, int64_t n, const double *x, const double *y, double *out)
+{
+  B2P_TRY(ctx, *out = vec::dot(ctx, x, y, n));
+  return B2P_SUCCESS;
+}
+int b2p_vec_sum(b2p_ctx *ctx, int64_t n, const double *x, double *out)
+{
+  B2P_TRY(ctx, *out = vec::sum(ctx, x, n));
+  return B2P_SUCCESS;
+}
+int b2p_vec_set_sub(b2p_ctx *ctx, double *y, const int32_t *idx_dev, int64_t nidx, double v)
+{
+  B2P_TRY(ctx, vec::set_sub(ctx, y, idx_dev, nidx, v));
+  return B2P_SUCCESS;
+}
+int b2p_vec_set_random(b2p_ctx *ctx, int64_t n, double *y, uint64_t seed)
+{
+  B2P_TRY(ctx, vec::set_random(ctx, y, n, seed));
+  return B2P_SUCCESS;
+}
+int b2p_vec_orthogonalize(b2p_ctx *ctx, int type, int64_t n, int m, const double *const *V, double *w, double *H)
+{
+  if (m <= 0) return B2P_SUCCESS;
+  if (type == 0)
+  {
+    for (int j = 0; j < m; j++)
+    {
+      H[j] = vec::dot(ctx, w, V[j], n);
+      vec::axpy(ctx, -H[j], V[j], w, n);
+    }
+  }
+  else
+  {
+    vec::multi_dot(ctx, m, V, w, n, H);
+    vec::multi_axpy(ctx, m, H, V, w, n, -1.0);
+    if (type == 2)
+    {
+      std::vector<double> dH(m);
+      vec::multi_dot(ctx, m, V, w, n, dH.data());
+      vec::multi_axpy(ctx, m, dH.data(), V, w, n, -1.0);
+      for (int j = 0; j < m; j++) H[j] += dH[j];
+    }
+  }
+  cudaError_t e = cudaPeekAtLastError();
+  B2P_CHECK(ctx, e == cudaSuccess, B2P_ERR_CUDA, "orthogonalize: %s", cudaGetErrorString(e));
+  return B2P_SUCCESS;
+}
+
+int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coefs,
+                     const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_halo *halo, b2p_operator **out)
+{
+  B2P_CHECK(ctx, ctx && out && n_terms > 0 && ops, B2P_ERR_ARG, "b2p_operator_par: bad argument");
+  std::vector<ParOperator::Term> terms;
+  for (int i = 0; i < n_terms; i++)
+  {
+    B2P_CHECK(ctx, ops[i] && b2p_op_lsize(ops[i]) == lsize, B2P_ERR_ARG, "b2p_operator_par: term %d has the wrong L-size", i);
+    terms.push_back({ops[i], coefs ? coefs[i] : 1.0});
+  }
+  auto *h = new b2p_operator;
+  h->op = std::make_unique<ParOperator>(ctx, tsize, lsize, terms, ess_tdofs, n_ess, diag_policy, halo ? halo_of(halo) : nullptr);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_operator **out)
+{
+  B2P_CHECK(ctx, ctx && it && out, B2P_ERR_ARG, "b2p_operator_interp: bad argument");
+  auto *h = new b2p_operator;
+  h->op = std::make_unique<InterpOperator>(ctx, it);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_operator_mult(b2p_operator *A, const double *x, double *y)
+{
+  if (!A) return B2P_ERR_ARG;
+  B2P_TRY(A->op->ctx, A->op->Mult(x, y));
+  return B2P_SUCCESS;
+}
+int b2p_operator_mult_transpose(b2p_operator *A, const double *x, double *y)
+{
+  if (!A) return B2P_ERR_ARG;
+  B2P_TRY(A->op->ctx, A->op->MultTranspose(x, y));
+  return B2P_SUCCESS;
+}
+int b2p_operator_add_mult(b2p_operator *A, const double *x, double *y, double a)
+{
+  if (!A) return B2P_ERR_ARG;
+  B2P_TRY(A->op->ctx, A->op->AddMult(x, y, a));
+  return B2P_SUCCESS;
+}
+int b2p_operator_assemble_diagonal(b2p_operator *A, double *d)
+{
+  if (!A) return B2P_ERR_ARG;
+  B2P_TRY(A->op->ctx, A->op->AssembleDiagonal(d));
+  return B2P_SUCCESS;
+}
+int64_t b2p_operator_height(b2p_operator *A) { return A ? A->op->Height() : 0; }
+int64_t b2p_operator_width(b2p_operator *A) { return A ? A->op->Width() : 0; }
+void b2p_operator_destroy(b2p_operator *A) { delete A; }
+
+int b2p_solver_jacobi(b2p_ctx *ctx, double omega, double sf_max, b2p_solver **out)
+{
+  auto *h = new b2p_solver;
+  h->s = std::make_unique<JacobiSmoother>(ctx, omega, sf_max);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_solver_chebyshev(b2p_ctx *ctx, int smooth_it, int order, double sf_max, double sf_min, int fourth_kind, b2p_solver **out)
+{
+  B2P_CHECK(ctx, order > 0, B2P_ERR_ARG, "Polynomial order for Chebyshev smoothing must be positive!");
+  auto *h = new b2p_solver;
+  h->s = std::make_unique<ChebyshevSmoother>(ctx, smooth_it, order, sf_max, sf_min, fourth_kind != 0);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_solver_distrelax(b2p_ctx *ctx, b2p_operator *G, int smooth_it, int cheby_smooth_it, int cheby_order, double sf_max,
+                         double sf_min, int fourth_kind, b2p_solver **out)
+{
+  B2P_CHECK(ctx, G, B2P_ERR_ARG, "b2p_solver_distrelax: missing G");
+  auto *h = new b2p_solver;
+  h->s = std::make_unique<DistRelaxationSmoother>(ctx, *G->op, smooth_it, cheby_smooth_it, cheby_order, sf_max, sf_min,
+                                                  fourth_kind != 0);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_solver_distrelax_set_operators(b2p_solver *s, b2p_operator *A, b2p_operator *A_G)
+{
+  auto *d = s ? dynamic_cast<DistRelaxationSmoother *>(s->s.get()) : nullptr;
+  auto *pa = A ? dynamic_cast<ParOperator *>(A->op.get()) : nullptr;
+  auto *pg = A_G ? dynamic_cast<ParOperator *>(A_G->op.get()) : nullptr;
+  if (!d || !pa || !pg) return B2P_ERR_ARG;
+  B2P_TRY(d->ctx, d->SetOperators(*pa, *pg));
+  return B2P_SUCCESS;
+}
+int b2p_solver_gmg(b2p_ctx *ctx, b2p_solver *coarse, int n_levels, b2p_operator *const *P, b2p_operator *const *G, int cycle_it,
+                   int smooth_it, int cheby_order, double sf_max, double sf_min, int fourth_kind, b2p_solver **out)
+{
+  B2P_CHECK(ctx, coarse && coarse->s && n_levels >= 1 && out, B2P_ERR_ARG, "b2p_solver_gmg: bad argument");
+  std::vector<const Operator *> Pv, Gv;
+  for (int l = 0; l + 1 < n_levels; l++) Pv.push_back(P[l]->op.get());
+  if (G)
+    for (int l = 0; l < n_levels; l++) Gv.push_back(G[l] ? G[l]->op.get() : nullptr);
+  auto *h = new b2p_solver;
+  h->s = std::make_unique<GeometricMultigridSolver>(ctx, std::move(coarse->s), Pv, Gv, cycle_it, smooth_it, cheby_order, sf_max,
+                                                    sf_min, fourth_kind != 0);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_solver_gmg_set_operators(b2p_solver *s, b2p_operator *const *A, b2p_operator *const *A_aux)
+{
+  auto *g = s ? dynamic_cast<GeometricMultigridSolver *>(s->s.get()) : nullptr;
+  if (!g) return B2P_ERR_ARG;
+  std::vector<const ParOperator *> Av, Gv;
+  for (size_t l = 0; l < g->A.size(); l++)
+  {
+    auto *pa = dynamic_cast<ParOperator *>(A[l]->op.get());
+    B2P_CHECK(g->ctx, pa, B2P_ERR_ARG, "GeometricMultigridSolver requires ParOperator operators!");
+    Av.push_back(pa);
+    if (A_aux)
+    {
+      auto *pg = A_aux[l] ? dynamic_cast<ParOperator *>(A_aux[l]->op.get()) : nullptr;
+      Gv.push_back(pg);
+    }
+  }
+  B2P_TRY(g->ctx, g->SetOperators(Av, Gv));
+  return B2P_SUCCESS;
+}
+int b2p_solver_krylov(b2p_ctx *ctx, int type, b2p_solver **out)
+{
+  B2P_CHECK(ctx, type >= 0 && type <= 2, B2P_ERR_ARG, "b2p_solver_krylov: type must be 0 (CG), 1 (GMRES) or 2 (FGMRES)");
+  auto *h = new b2p_solver;
+  h->s = std::make_unique<IterativeSolver>(ctx, (KspType)type);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_solver_krylov_config(b2p_solver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side)
+{
+  auto *k = s ? dynamic_cast<IterativeSolver *>(s->s.get()) : nullptr;
+  if (!k) return B2P_ERR_ARG;
+  k->rel_tol = rel_tol;
+  k->abs_tol = abs_tol;
+  k->max_it = max_it;
+  k->max_dim = max_dim;
+  k->gs = (Orthog)orthog;
+  k->pc_side = (PcSide)pc_side;
+  return B2P_SUCCESS;
+}
+int b2p_solver_set_preconditioner(b2p_solver *s, b2p_solver *pc)
+{
+  auto *k = s ? dynamic_cast<IterativeSolver *>(s->s.get()) : nullptr;
+  if (!k) return B2P_ERR_ARG;
+  k->SetPreconditioner(pc ? pc->s.get() : nullptr);
+  return B2P_SUCCESS;
+}
+int b2p_solver_set_operator(b2p_solver *s, b2p_operator *A)
+{
+  if (!s || !s->s || !A) return B2P_ERR_ARG;
+  B2P_TRY(s->s->ctx, s->s->SetOperator(*A->op));
+  return B2P_SUCCESS;
+}
+int b2p_solver_set_initial_guess(b2p_solver *s, int flag)
+{
+  if (!s || !s->s) return B2P_ERR_ARG;
+  s->s->SetInitialGuess(flag != 0);
+  return B2P_SUCCESS;
+}
+int b2p_solver_mult(b2p_solver *s, const double *x, double *y)
+{
+  if (!s || !s->s) return B2P_ERR_ARG;
+  B2P_TRY(s->s->ctx, s->s->Mult(x, y));
+  return B2P_SUCCESS;
+}
+int b2p_solver_mult2(b2p_solver *s, const double *x, double *y, double *r)
+{
+  if (!s || !s->s) return B2P_ERR_ARG;
+  B2P_TRY(s->s->ctx, s->s->Mult2(x, y, r));
+  return B2P_SUCCESS;
+}
+int b2p_solver_mult_transpose2(b2p_solver *s, const double *x, double *y, double *r)
+{
+  if (!s || !s->s) return B2P_ERR_ARG;
+  B2P_TRY(s->s->ctx, s->s->MultTranspose2(x, y, r));
+  return B2P_SUCCESS;
+}
+int b2p_solver_stats(b2p_solver *s, int *its, double *initial_res, double *final_res, int *converged)
+{
+  auto *k = s ? dynamic_cast<IterativeSolver *>(s->s.get()) : nullptr;
+  if (!k) return B2P_ERR_ARG;
+  if (its) *its = k->final_it;
+  if (initial_res) *initial_res = k->initial_res;
+  if (final_res) *final_res = k->final_res;
+  if (converged) *converged = k->converged ? 1 : 0;
+  return B2P_SUCCESS;
+}
+int b2p_solver_lambda_max(b2p_solver *s, double *out)
+{
+  auto *c = s ? dynamic_cast<ChebyshevSmoother *>(s->s.get()) : nullptr;
+  if (!c || !out) return B2P_ERR_ARG;
+  *out = c->lambda_max;
+  return B2P_SUCCESS;
+}
+void b2p_solver_destroy(b2p_solver *s) { delete s; }
+
+}  // extern "C"

@@ -49,6 +49,7 @@ struct b2p_ctx
   int sm_count = 0;
   int rank = 0, nranks = 1;
   ncclComm *comm = nullptr;
+  cudaStream_t stream = 0;  // stream of the linear algebra / solver layer (b2p_ctx_set_stream)
   std::string last_error;
   // scratch for reductions (dot products): device partials + pinned host result
   double *d_red = nullptr;
@@ -105,6 +106,19 @@ struct b2p_op
   bool owns_coeff = true;  // coarsened operators share the fine operator's coefficient arrays
   b2p_op *parent = nullptr;
   int refcount = 1;
+};
+
+struct b2p_interp
+{
+  b2p_ctx *ctx = nullptr;
+  int ne = 0, in_P = 0, out_P = 0, in_PS = 0, out_PS = 0, ncomp = 0;
+  int64_t in_lsize = 0, out_lsize = 0;
+  int32_t *in_lidx = nullptr, *out_lidx = nullptr;  // signed lexicographic restrictions [ne][PS]
+  double *inv_mult = nullptr;                       // [out_lsize] 1 / (local elements touching the dof)
+  // per component: dims and matrix offsets into `mats`
+  int in_off[3], in_n[3][3], out_off[3], out_n[3][3], mat_off[3][3];
+  double *mats = nullptr;
+  int n_mats = 0;
 };
 
 namespace b2p

@@ -1,0 +1,278 @@
+// Element-local tensor-product interpolation between two hexahedral spaces on the same mesh:
+// the p-multigrid prolongation (ND->ND, H1->H1) and the discrete gradient (H1->ND).
+// Reference: DiscreteLinearOperator::PartialAssemble (/root/reference/palace/fem/bilinearform.cpp:203-282)
+// builds one element-dense [P_test x P_trial] matrix from GetTransferMatrix/ProjectGrad
+// (/root/reference/palace/fem/libceed/basis.cpp:116-165) and applies it through libCEED with an
+// identity QFunction (/root/reference/palace/fem/libceed/integrator.cpp:515-548); the output is scaled
+// by the inverse dof multiplicity on Mult and the input on MultTranspose
+// (/root/reference/palace/fem/libceed/operator.cpp:182-212). On hexes that dense matrix is a Kronecker
+// product of 1-D matrices per vector component; it is applied here in that factored form.
+#include "b2p_internal.hpp"
+#include "b2p_contract.cuh"
+
+
+namespace b2p
+{
+
+namespace
+{
+
+struct InterpParams
+{
+  const int32_t *in_lidx, *out_lidx;
+  const double *inv_mult, *mats, *x;
+  double *y;
+  double alpha;
+  int ne, in_P, out_P, in_PS, out_PS, ncomp, n_mats;
+  int in_off[3], in_n[3][3], out_off[3], out_n[3][3], mat_off[3][3];
+};
+
+// y[out] += alpha * inv_mult[out] * sum_e E_out^T (Ax (x) Ay (x) Az) E_in x
+template <bool TRANSPOSE>
+__global__ void interp_kernel(InterpParams prm, int neb)
+{
+  extern __shared__ double sm[];
+  double *smat = sm;                 // [n_mats]
+  double *sv = sm + prm.n_mats;      // [neb][src_P]
+  const int src_P = TRANSPOSE ? prm.out_P : prm.in_P;
+  const int dst_P = TRANSPOSE ? prm.in_P : prm.out_P;
+  const int src_PS = TRANSPOSE ? prm.out_PS : prm.in_PS;
+  const int dst_PS = TRANSPOSE ? prm.in_PS : prm.out_PS;
+  const int32_t *src_lidx = TRANSPOSE ? prm.out_lidx : prm.in_lidx;
+  const int32_t *dst_lidx = TRANSPOSE ? prm.in_lidx : prm.out_lidx;
+  for (int i = threadIdx.x; i < prm.n_mats; i += blockDim.x) smat[i] = prm.mats[i];
+  const int e0 = blockIdx.x * neb;
+  for (int w = threadIdx.x; w < neb * src_P; w += blockDim.x)
+  {
+    const int e = w / src_P, l = w % src_P;
+    double v = 0.0;
+    if (e0 + e < prm.ne)
+    {
+      const int32_t gi = src_lidx[(size_t)(e0 + e) * src_PS + l];
+      v = gather1(prm.x, gi);
+      if (TRANSPOSE && gi != B2P_SKIP_IDX) v *= prm.inv_mult[gi >= 0 ? gi : -1 - gi];
+    }
+    sv[w] = v;
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < neb * dst_P; w += blockDim.x)
+  {
+    const int e = w / dst_P, l = w % dst_P;
+    if (e0 + e >= prm.ne) continue;
+    // component of the destination dof
+    int c = 0;
+    if (!TRANSPOSE)
+    {
+      while (c + 1 < prm.ncomp && l >= prm.out_off[c + 1]) c++;
+    }
+    else
+    {
+      // transposed: destination lives in the input space; with one input block shared by all
+      // components (discrete gradient) every component contributes.
+      c = -1;
+    }
+    const double *src = sv + e * src_P;
+    double s = 0.0;
+    if (!TRANSPOSE)
+    {
+      const int r = l - prm.out_off[c];
+      const int ox = prm.out_n[c][0], oy = prm.out_n[c][1];
+      const int i = r % ox, j = (r / ox) % oy, k = r / (ox * oy);
+      const int nx = prm.in_n[c][0], ny = prm.in_n[c][1], nz = prm.in_n[c][2];
+      const double *Ax = smat + prm.mat_off[c][0] + i * nx;
+      const double *Ay = smat + prm.mat_off[c][1] + j * ny;
+      const double *Az = smat + prm.mat_off[c][2] + k * nz;
+      const double *in = src + prm.in_off[c];
+      for (int kk = 0; kk < nz; kk++)
+      {
+        double sy = 0.0;
+        for (int jj = 0; jj < ny; jj++)
+        {
+          double sx = 0.0;
+          for (int ii = 0; ii < nx; ii++) sx += Ax[ii] * in[ii + nx * (jj + ny * kk)];
+          sy += Ay[jj] * sx;
+        }
+        s += Az[kk] * sy;
+      }
+      const int32_t gi = dst_lidx[(size_t)(e0 + e) * dst_PS + l];
+      if (gi != B2P_SKIP_IDX) s *= prm.inv_mult[gi >= 0 ? gi : -1 - gi];
+      scatter1(prm.y, gi, prm.alpha * s);
+    }
+    else
+    {
+      for (int cc = 0; cc < prm.ncomp; cc++)
+      {
+        const int nx = prm.in_n[cc][0], ny = prm.in_n[cc][1], nz = prm.in_n[cc][2];
+        const int r = l - prm.in_off[cc];
+        if (r < 0 || r >= nx * ny * nz) continue;
+        const int ii = r % nx, jj = (r / nx) % ny, kk = r / (nx * ny);
+        const int ox = prm.out_n[cc][0], oy = prm.out_n[cc][1], oz = prm.out_n[cc][2];
+        const double *Ax = smat + prm.mat_off[cc][0] + ii;   // column ii, stride nx
+        const double *Ay = smat + prm.mat_off[cc][1] + jj;
+        const double *Az = smat + prm.mat_off[cc][2] + kk;
+        const double *out = src + prm.out_off[cc];
+        for (int k = 0; k < oz; k++)
+        {
+          double sy = 0.0;
+          for (int j = 0; j < oy; j++)
+          {
+            double sx = 0.0;
+            for (int i = 0; i < ox; i++) sx += Ax[i * nx] * out[i + ox * (j + oy * k)];
+            sy += Ay[j * ny] * sx;
+          }
+          s += Az[k * nz] * sy;
+        }
+      }
+      scatter1(prm.y, dst_lidx[(size_t)(e0 + e) * dst_PS + l], prm.alpha * s);
+    }
+  }
+}
+
+InterpParams make_params(const b2p_interp *it, double alpha, const double *x, double *y)
+{
+  InterpParams p;
+  p.in_lidx = it->in_lidx;
+  p.out_lidx = it->out_lidx;
+  p.inv_mult = it->inv_mult;
+  p.mats = it->mats;
+  p.x = x;
+  p.y = y;
+  p.alpha = alpha;
+  p.ne = it->ne;
+  p.in_P = it->in_P;
+  p.out_P = it->out_P;
+  p.in_PS = it->in_PS;
+  p.out_PS = it->out_PS;
+  p.ncomp = it->ncomp;
+  p.n_mats = it->n_mats;
+  for (int c = 0; c < 3; c++)
+  {
+    p.in_off[c] = it->in_off[c];
+    p.out_off[c] = it->out_off[c];
+    for (int d = 0; d < 3; d++)
+    {
+      p.in_n[c][d] = it->in_n[c][d];
+      p.out_n[c][d] = it->out_n[c][d];
+      p.mat_off[c][d] = it->mat_off[c][d];
+    }
+  }
+  return p;
+}
+
+int build_lidx(b2p_ctx *ctx, int ne, int P, int64_t lsize, const int32_t *idx, const int8_t *orient, const int32_t *dof_map,
+               int *PS_out, int32_t **d_out, std::vector<int32_t> *host_out)
+{
+  const int PS = (P + 3) & ~3;
+  *PS_out = PS;
+  std::vector<int32_t> lidx((size_t)ne * PS, (int32_t)B2P_SKIP_IDX);
+  for (int l = 0; l < P; l++)
+  {
+    int nat = dof_map ? dof_map[l] : l, sg = 1;
+    if (nat < 0)
+    {
+      nat = -1 - nat;
+      sg = -1;
+    }
+    B2P_CHECK(ctx, nat >= 0 && nat < P, B2P_ERR_ARG, "interp: dof_map[%d] out of range", l);
+    for (int e = 0; e < ne; e++)
+    {
+      const int32_t gi = idx[(size_t)e * P + nat];
+      B2P_CHECK(ctx, gi >= 0 && gi < lsize, B2P_ERR_ARG, "interp: idx out of range");
+      const int s = sg * (orient ? (int)orient[(size_t)e * P + nat] : 1);
+      lidx[(size_t)e * PS + l] = s >= 0 ? gi : -1 - gi;
+    }
+  }
+  if (host_out) *host_out = lidx;
+  return upload(ctx, lidx.data(), lidx.size(), d_out);
+}
+
+}  // namespace
+
+int interp_apply(const b2p_interp *it, bool transpose, double alpha, const double *x, double *y, cudaStream_t s)
+{
+  InterpParams prm = make_params(it, alpha, x, y);
+  const int src_P = transpose ? it->out_P : it->in_P;
+  int neb = std::max(1, 256 / std::max(it->out_P, it->in_P));
+  neb = std::min(neb, 16);
+  const size_t shmem = sizeof(double) * ((size_t)it->n_mats + (size_t)neb * src_P);
+  const int grid = (it->ne + neb - 1) / neb;
+  if (transpose)
+    interp_kernel<true><<<grid, 256, shmem, s>>>(prm, neb);
+  else
+    interp_kernel<false><<<grid, 256, shmem, s>>>(prm, neb);
+  B2P_CUDA(it->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+
+}  // namespace b2p
+
+using namespace b2p;
+
+extern "C"
+{
+
+int b2p_interp_create(b2p_ctx *ctx, const b2p_interp_desc *d, b2p_interp **out)
+{
+  B2P_CHECK(ctx, ctx && d && out, B2P_ERR_ARG, "b2p_interp_create: null argument");
+  B2P_CHECK(ctx, d->ncomp >= 1 && d->ncomp <= 3, B2P_ERR_ARG, "b2p_interp_create: ncomp must be 1..3");
+  b2p_interp *it = new b2p_interp;
+  it->ctx = ctx;
+  it->ne = d->ne;
+  it->in_P = d->in_P;
+  it->out_P = d->out_P;
+  it->in_lsize = d->in_lsize;
+  it->out_lsize = d->out_lsize;
+  it->ncomp = d->ncomp;
+  int rc;
+  std::vector<int32_t> out_host;
+  if ((rc = build_lidx(ctx, d->ne, d->in_P, d->in_lsize, d->in_idx, d->in_orient, d->in_dof_map, &it->in_PS, &it->in_lidx, nullptr)))
+    return rc;
+  if ((rc = build_lidx(ctx, d->ne, d->out_P, d->out_lsize, d->out_idx, d->out_orient, d->out_dof_map, &it->out_PS, &it->out_lidx,
+                       &out_host)))
+    return rc;
+  std::vector<double> mult((size_t)d->out_lsize, 0.0);
+  for (int32_t g : out_host)
+  {
+    if (g == (int32_t)B2P_SKIP_IDX) continue;
+    mult[g >= 0 ? g : -1 - g] += 1.0;
+  }
+  for (auto &m : mult) m = m > 0.0 ? 1.0 / m : 0.0;
+  if ((rc = upload(ctx, mult.data(), mult.size(), &it->inv_mult))) return rc;
+  std::vector<double> mats;
+  for (int c = 0; c < d->ncomp; c++)
+  {
+    const b2p_interp_comp &cc = d->comps[c];
+    it->in_off[c] = cc.in_off;
+    it->out_off[c] = cc.out_off;
+    for (int a = 0; a < 3; a++)
+    {
+      it->in_n[c][a] = cc.in_n[a];
+      it->out_n[c][a] = cc.out_n[a];
+      it->mat_off[c][a] = (int)mats.size();
+      B2P_CHECK(ctx, cc.A[a], B2P_ERR_ARG, "b2p_interp_create: missing 1-D matrix");
+      mats.insert(mats.end(), cc.A[a], cc.A[a] + (size_t)cc.out_n[a] * cc.in_n[a]);
+    }
+  }
+  it->n_mats = (int)mats.size();
+  if ((rc = upload(ctx, mats.data(), mats.size(), &it->mats))) return rc;
+  *out = it;
+  return B2P_SUCCESS;
+}
+
+int b2p_interp_apply_add(b2p_interp *it, int transpose, double alpha, const double *x, double *y, b2p_stream s)
+{
+  if (!it || !x || !y) return B2P_ERR_ARG;
+  return interp_apply(it, transpose != 0, alpha, x, y, (cudaStream_t)s);
+}
+
+void b2p_interp_destroy(b2p_interp *it)
+{
+  if (!it) return;
+  cudaFree(it->in_lidx);
+  cudaFree(it->out_lidx);
+  cudaFree(it->inv_mult);
+  cudaFree(it->mats);
+  delete it;
+}
+
+}  // extern "C"

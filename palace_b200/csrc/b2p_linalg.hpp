@@ -1,0 +1,260 @@
+// Device-resident linear algebra and solver layer (C++ host logic over sm_100a kernels), mirroring
+// the reference's class structure so that the C ABI (and a Palace adapter) maps one to one:
+//   palace::Operator / ParOperator / SumOperator        /root/reference/palace/linalg/{operator.hpp,rap.hpp}
+//   palace::Solver<OperType>                            /root/reference/palace/linalg/solver.hpp:21-65
+//   JacobiSmoother, ChebyshevSmoother(1stKind)          /root/reference/palace/linalg/{jacobi,chebyshev}.cpp
+//   DistRelaxationSmoother, GeometricMultigridSolver    /root/reference/palace/linalg/{distrelaxation,gmg}.cpp
+//   CgSolver, GmresSolver, FgmresSolver                 /root/reference/palace/linalg/iterative.cpp
+// Real-valued (OperType = Operator) instantiation; all vectors are raw device pointers (T-vectors).
+#pragma once
+#include <cmath>
+#include <memory>
+#include <vector>
+
+#include "b2p_internal.hpp"
+
+namespace b2p
+{
+
+// ---------------------------------------------------------------- vectors / BLAS-1 (b2p_vec.cu)
+struct DVec  // owning device vector
+{
+  b2p_ctx *ctx = nullptr;
+  double *p = nullptr;
+  int64_t n = 0;
+  DVec() = default;
+  DVec(b2p_ctx *c, int64_t n_) { resize(c, n_); }
+  DVec(const DVec &) = delete;
+  DVec &operator=(const DVec &) = delete;
+  ~DVec() { release(); }
+  void resize(b2p_ctx *c, int64_t n_);
+  void release();
+  operator double *() { return p; }
+  operator const double *() const { return p; }
+};
+
+namespace vec
+{
+void set(b2p_ctx *c, double *y, int64_t n, double v);
+void copy(b2p_ctx *c, double *y, const double *x, int64_t n);
+void scale(b2p_ctx *c, double *y, int64_t n, double a);
+void axpy(b2p_ctx *c, double a, const double *x, double *y, int64_t n);                       // y += a x
+void axpby(b2p_ctx *c, double a, const double *x, double b, double *y, int64_t n);            // y = a x + b y
+void axpbypcz(b2p_ctx *c, double a, const double *x, double b, const double *y, double g, double *z, int64_t n);
+void mult_diag(b2p_ctx *c, const double *d, const double *x, double *y, int64_t n);           // y = d .* x
+void reciprocal(b2p_ctx *c, double *y, int64_t n);
+void set_sub(b2p_ctx *c, double *y, const int32_t *idx, int64_t nidx, double v);              // y[idx] = v
+void set_sub_from(b2p_ctx *c, double *y, const int32_t *idx, int64_t nidx, const double *x);  // y[idx] = x[idx]
+void axpy_sub(b2p_ctx *c, double a, const double *x, const int32_t *idx, int64_t nidx, double *y);       // y[idx] += a x[idx]
+void set_random(b2p_ctx *c, double *y, int64_t n, uint64_t seed);                             // uniform [-1, 1]
+// Chebyshev fused updates (chebyshev.cpp:70-156 plus the y += d the reference does separately)
+void cheb_first(b2p_ctx *c, double sr, const double *dinv, const double *r, double *d, int64_t n);
+void cheb_next(b2p_ctx *c, double sd, double sr, const double *dinv, const double *r, double *d, int64_t n);
+// Global reductions: local device reduction (deterministic order) + NCCL all-reduce + one host sync.
+double dot(b2p_ctx *c, const double *x, const double *y, int64_t n);
+double sum(b2p_ctx *c, const double *x, int64_t n);
+void multi_dot(b2p_ctx *c, int m, const double *const *V, const double *w, int64_t n, double *out);  // out[j] = <w, V_j>
+void multi_axpy(b2p_ctx *c, int m, const double *coef, const double *const *V, double *w, int64_t n, double sign);  // w += sign * sum coef_j V_j
+inline double norml2(b2p_ctx *c, const double *x, int64_t n) { return std::sqrt(std::abs(dot(c, x, x, n))); }
+}  // namespace vec
+
+// ---------------------------------------------------------------- operators
+class Operator
+{
+public:
+  b2p_ctx *ctx;
+  int64_t height, width;
+  Operator(b2p_ctx *c, int64_t h, int64_t w) : ctx(c), height(h), width(w) {}
+  virtual ~Operator() = default;
+  virtual void Mult(const double *x, double *y) const = 0;
+  virtual void MultTranspose(const double *x, double *y) const { Mult(x, y); }
+  virtual void AddMult(const double *x, double *y, double a = 1.0) const;           // default: temp + axpy
+  virtual void AddMultTranspose(const double *x, double *y, double a = 1.0) const;
+  virtual void AssembleDiagonal(double *d) const;
+  int64_t Height() const { return height; }
+  int64_t Width() const { return width; }
+
+protected:
+  mutable DVec tmp_;
+};
+
+// P / P^T of one finite element space on this rank (linalg/rap.cpp:212-222): owned dofs first,
+// then ghosts. nranks == 1 (or no shared dofs): identity, zero copies.
+struct Halo;
+
+// ParOperator over the local partially assembled operators: y = P^T (sum_i c_i A_i) P x with
+// essential-dof elimination (rap.cpp:195-234,277-318,154-193; BuildParSumOperator rap.cpp:764-829).
+class ParOperator : public Operator
+{
+public:
+  struct Term
+  {
+    b2p_op *op;
+    double coef;
+  };
+  ParOperator(b2p_ctx *c, int64_t tsize, int64_t lsize, const std::vector<Term> &terms, const int32_t *ess_tdofs,
+              int64_t n_ess, int diag_policy, Halo *halo);
+  ~ParOperator() override;
+  void Mult(const double *x, double *y) const override;
+  void AddMult(const double *x, double *y, double a = 1.0) const override;
+  void AssembleDiagonal(double *d) const override;
+  const int32_t *EssentialTrueDofs() const { return d_ess; }
+  int64_t NumEssential() const { return n_ess; }
+  int64_t lsize;
+
+private:
+  std::vector<Term> terms;
+  int32_t *d_ess = nullptr;
+  int64_t n_ess = 0;
+  int diag_policy;  // 0 = DIAG_ZERO, 1 = DIAG_ONE
+  Halo *halo;
+  mutable DVec lx_, ly_;
+};
+
+// Element-local tensor-product interpolation between two hex spaces on the same mesh: the
+// p-multigrid prolongation P_l and the discrete gradient G (fem/bilinearform.cpp:203-282,
+// libceed/integrator.cpp:515-548, basis.cpp:116-165) with the reference's multiplicity scaling
+// (libceed/operator.cpp:182-212) and ParOperator(use_R) semantics.
+struct InterpDesc;
+class InterpOperator : public Operator
+{
+public:
+  InterpOperator(b2p_ctx *c, b2p_interp *impl);
+  void Mult(const double *x, double *y) const override;
+  void MultTranspose(const double *x, double *y) const override;
+  void AddMult(const double *x, double *y, double a = 1.0) const override;
+  b2p_interp *impl;
+};
+
+// ---------------------------------------------------------------- solvers
+class Solver : public Operator
+{
+public:
+  bool initial_guess = false;
+  Solver(b2p_ctx *c) : Operator(c, 0, 0) {}
+  virtual void SetOperator(const Operator &op) = 0;
+  void SetInitialGuess(bool g) { initial_guess = g; }
+  // y = y + B (x - A y) style application with a caller-supplied residual work vector
+  virtual void Mult2(const double *x, double *y, double *r) const;
+  virtual void MultTranspose2(const double *x, double *y, double *r) const { Mult2(x, y, r); }
+
+protected:
+  mutable DVec r_;
+};
+
+double SpectralNormDinvA(b2p_ctx *c, const Operator &A, const double *dinv, double tol = 1e-4, int max_it = 1000,
+                         uint64_t seed = 0);
+
+class JacobiSmoother : public Solver
+{
+public:
+  JacobiSmoother(b2p_ctx *c, double omega = 1.0, double sf_max = 1.0) : Solver(c), omega(omega), sf_max(sf_max) {}
+  void SetOperator(const Operator &op) override;
+  void Mult(const double *x, double *y) const override;
+  double omega, sf_max;
+  DVec dinv;
+};
+
+class ChebyshevSmoother : public Solver
+{
+public:
+  // fourth_kind: ChebyshevSmoother (4th kind, chebyshev.cpp:191-220) else ChebyshevSmoother1stKind (:261-293)
+  ChebyshevSmoother(b2p_ctx *c, int smooth_it, int order, double sf_max, double sf_min, bool fourth_kind)
+    : Solver(c), pc_it(smooth_it), order(order), sf_max(sf_max), sf_min(sf_min), fourth_kind(fourth_kind)
+  {
+  }
+  void SetOperator(const Operator &op) override;
+  void Mult(const double *x, double *y) const override { Mult2(x, y, work()); }
+  void Mult2(const double *x, double *y, double *r) const override;
+  int pc_it, order;
+  double sf_max, sf_min;
+  bool fourth_kind;
+  const Operator *A = nullptr;
+  double lambda_max = 0.0, theta = 0.0, delta = 0.0;
+  DVec dinv;
+  mutable DVec d;
+
+private:
+  double *work() const
+  {
+    if (r_.n != height) r_.resize(ctx, height);
+    return r_.p;
+  }
+};
+
+class DistRelaxationSmoother : public Solver
+{
+public:
+  DistRelaxationSmoother(b2p_ctx *c, const Operator &G, int smooth_it, int cheby_smooth_it, int cheby_order, double sf_max,
+                         double sf_min, bool fourth_kind);
+  void SetOperator(const Operator &) override;  // not used: needs both operators
+  void SetOperators(const ParOperator &op, const ParOperator &op_G);
+  void Mult(const double *x, double *y) const override;
+  void Mult2(const double *x, double *y, double *r) const override;
+  void MultTranspose2(const double *x, double *y, double *r) const override;
+  int pc_it;
+  const Operator *G;
+  const ParOperator *A = nullptr, *A_G = nullptr;
+  std::unique_ptr<ChebyshevSmoother> B, B_G;
+  mutable DVec x_G, y_G, r_G;
+};
+
+class GeometricMultigridSolver : public Solver
+{
+public:
+  // P[l]: level l -> l+1 prolongation (l = 0 .. n_levels-2); G[l]: aux (H1) -> primary (ND) gradient per level or empty.
+  GeometricMultigridSolver(b2p_ctx *c, std::unique_ptr<Solver> &&coarse, const std::vector<const Operator *> &P,
+                           const std::vector<const Operator *> &G, int cycle_it, int smooth_it, int cheby_order, double sf_max,
+                           double sf_min, bool fourth_kind);
+  void SetOperator(const Operator &) override;
+  void SetOperators(const std::vector<const ParOperator *> &A, const std::vector<const ParOperator *> &A_aux);
+  void Mult(const double *x, double *y) const override;
+  int pc_it;
+  std::vector<const Operator *> P;
+  std::vector<const ParOperator *> A;
+  std::vector<std::unique_ptr<Solver>> B;
+  mutable std::vector<DVec> X, Y, R;
+
+private:
+  void VCycle(int l, bool initial_guess) const;
+};
+
+enum class KspType { CG = 0, GMRES = 1, FGMRES = 2 };
+enum class Orthog { MGS = 0, CGS = 1, CGS2 = 2 };
+enum class PcSide { RIGHT = 0, LEFT = 1 };
+
+class IterativeSolver : public Solver
+{
+public:
+  IterativeSolver(b2p_ctx *c, KspType type) : Solver(c), type(type) {}
+  void SetOperator(const Operator &op) override
+  {
+    A = &op;
+    height = op.Height();
+    width = op.Width();
+  }
+  void SetPreconditioner(const Solver *pc) { B = pc; }
+  void Mult(const double *b, double *x) const override;
+  KspType type;
+  const Operator *A = nullptr;
+  const Solver *B = nullptr;
+  double rel_tol = 1e-6, abs_tol = 0.0;
+  int max_it = 100, max_dim = -1;
+  Orthog gs = Orthog::MGS;
+  PcSide pc_side = PcSide::RIGHT;
+  int print = 0;
+  // results
+  mutable bool converged = false;
+  mutable double initial_res = 1.0, final_res = 0.0;
+  mutable int final_it = 0;
+  mutable std::vector<double> res_history;
+
+private:
+  void MultCG(const double *b, double *x) const;
+  void MultGMRES(const double *b, double *x, bool flexible) const;
+  mutable std::vector<std::unique_ptr<DVec>> V, Z;
+  mutable DVec r, z, p;
+  mutable std::vector<double> H, s, cs, sn;
+};
+
+}  // namespace b2p

@@ -107,3 +107,66 @@ def gpu_op(ctx, geom, prob: Problem, kind, ctx_blob, assemble=False, space=None)
     t = hs.tables_1d(sp.p, prob.q1d)
     idx, ori = sp.native_restriction()
     return capi.Op.create(ctx, geom, kind, sp.p, sp.ndofs, idx, ori, sp.dof_map, t.Bo, t.Bc, t.Gc, ctx_blob, assemble)
+
+
+# ------------------------------------------------------------------------------------------------
+# Solver-level helpers: oracle sparse matrices and the matching C-ABI operators
+# ------------------------------------------------------------------------------------------------
+
+
+def oracle_matrix(prob: Problem, kind, ctx_blob, space=None, q1d=None, eliminate=True):
+    """Assembled sparse matrix of the oracle operator (optionally with essential dofs eliminated the
+    ParOperator way)."""
+    from oracle import solvers as S
+
+    q1d = prob.q1d if q1d is None else q1d
+    if kind == O.H1_DIFFUSION:
+        sp_ = prob.h1 if space is None else space
+        _, grad, _ = O.h1_hex_tables(sp_.p, q1d)
+        Ae = O.element_matrices(kind, None, grad, None, prob.qdata_ref, ctx_blob, sp_.P)
+        A = S.assemble_sparse(Ae, sp_.lex_gid, sp_.ndofs)
+    else:
+        sp_ = prob.nd if space is None else space
+        interp, curl, _ = O.nd_hex_tables(sp_.p, q1d)
+        idx, ori = sp_.native_restriction()
+        Ae = O.element_matrices(kind, interp, curl, ori, prob.qdata_ref, ctx_blob, sp_.P)
+        A = S.assemble_sparse(Ae, idx.astype(np.int64), sp_.ndofs)
+    return S.eliminate(A, sp_.ess_dofs) if eliminate else A
+
+
+def oracle_interp(in_space, out_space, I_loc):
+    from oracle import solvers as S
+
+    return S.interp_matrix(I_loc, in_space.lex_gid, in_space.lex_sign.astype(float), out_space.lex_gid,
+                           out_space.lex_sign.astype(float), in_space.ndofs, out_space.ndofs)
+
+
+def gpu_par_operator(ctx, geom, prob, kind, ctx_blob, space=None, fine_op=None, assemble=False):
+    """ParOperator over one local operator with the space's essential dofs (DIAG_ONE).
+    With ``fine_op`` the local operator is p-coarsened from it (shares quadrature and coefficient)."""
+    from palace_b200 import capi
+
+    if kind == O.H1_DIFFUSION:
+        sp_ = prob.h1 if space is None else space
+    else:
+        sp_ = prob.nd if space is None else space
+    if fine_op is None:
+        op = gpu_op(ctx, geom, prob, kind, ctx_blob, assemble, space=sp_)
+    else:
+        t = hs.tables_1d(sp_.p, prob.q1d)
+        if kind == O.H1_DIFFUSION:
+            op = fine_op.coarsen(sp_.p, sp_.ndofs, sp_.lex_gid.astype(np.int32), None, None, None, t.Bc, t.Gc)
+        else:
+            idx, ori = sp_.native_restriction()
+            op = fine_op.coarsen(sp_.p, sp_.ndofs, idx, ori, sp_.dof_map, t.Bo, t.Bc, t.Gc)
+    A = capi.Operator.par(ctx, sp_.ndofs, sp_.ndofs, [op], None, sp_.ess_dofs, diag_policy=1)
+    A.local_op = op
+    return A
+
+
+def gpu_interp(ctx, in_space, out_space, comps):
+    from palace_b200 import capi
+    from palace_b200.host import assemble as asm
+
+    it = capi.Interp(ctx, asm.space_dict(in_space), asm.space_dict(out_space), comps)
+    return capi.Operator.interp(ctx, it)
