@@ -45,12 +45,12 @@ def parse():
     return ap.parse_args()
 
 
-def build_problem(n, p, warp, mesh_order=1, origin=(0.0, 0.0, 0.0)):
+def build_problem(n, p, warp, mesh_order=1, origin=(0.0, 0.0, 0.0), size=(1.0, 1.0, 1.0)):
     from palace_b200.host import coeff as cf
     from palace_b200.host import hexmesh as hm
     from palace_b200.host import hexspace as hs
 
-    mesh = hm.box_mesh(n, (1.0, 1.0, 1.0), warp_amp=warp, n_attr=1, origin=origin)
+    mesh = hm.box_mesh(n, size, warp_amp=warp, n_attr=1, origin=origin)
     topo = hs.build_topology(mesh)
     nd = hs.build_nd_space(mesh, topo, p)
     q1d = p + 1
@@ -116,30 +116,36 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_apply(prob, nthreads, sample_elems, repeats=1):
-    """Time the reference algorithm (dense [3Q x P] interp/curl per element + reference QFunction
-    arithmetic, the oracle port) on the host cores over a bounded sample of elements."""
-    from oracle import pyoracle as O
+class CpuReference:
+    """The reference algorithm (dense [3Q x P] interp/curl per element + reference QFunction
+    arithmetic: the oracle port of the libCEED /cpu/self path) on the host cores."""
 
-    nd = prob["nd"]
-    p, q1d = prob["p"], prob["q1d"]
-    ne = prob["mesh"].ne
-    ns = ne if sample_elems <= 0 else min(ne, sample_elems)
-    interp, curl, _ = O.nd_hex_tables(p, q1d)
-    idx, ori = nd.native_restriction()
-    qd = O.geom_hex_qdata(prob["xe"][:ns], prob["mesh"].attr[:ns], prob["mesh_order"], q1d)
-    x = np.random.default_rng(1).random(nd.ndofs)
-    y = np.zeros(nd.ndofs)
-    idx_s, ori_s = np.ascontiguousarray(idx[:ns]), np.ascontiguousarray(ori[:ns])
-    O.apply_add_mt(nthreads, O.CURLCURL_MASS, interp, curl, idx_s[: max(1, ns // 20)], ori_s[: max(1, ns // 20)], qd, prob["blob"], x, y)
-    best = float("inf")
-    for _ in range(repeats):
-        y[:] = 0.0
+    def __init__(self, prob, sample_elems=0):
+        from oracle import pyoracle as O
+
+        self.O = O
+        nd = prob["nd"]
+        p, q1d = prob["p"], prob["q1d"]
+        self.ne = prob["mesh"].ne
+        self.ns = self.ne if sample_elems <= 0 else min(self.ne, sample_elems)
+        self.interp, self.curl, _ = O.nd_hex_tables(p, q1d)
+        idx, ori = nd.native_restriction()
+        self.idx, self.ori = np.ascontiguousarray(idx[: self.ns]), np.ascontiguousarray(ori[: self.ns])
+        self.qd = O.geom_hex_qdata(prob["xe"][: self.ns], prob["mesh"].attr[: self.ns], prob["mesh_order"], q1d)
+        self.blob = prob["blob"]
+        self.x = np.random.default_rng(1).random(nd.ndofs)
+        self.y = np.zeros(nd.ndofs)
+        self.ndofs = nd.ndofs
+
+    def step(self, nthreads):
+        self.y[:] = 0.0
         t0 = time.perf_counter()
-        O.apply_add_mt(nthreads, O.CURLCURL_MASS, interp, curl, idx_s, ori_s, qd, prob["blob"], x, y)
-        best = min(best, time.perf_counter() - t0)
-    dofs_equiv = nd.ndofs * (ns / ne)
-    return dofs_equiv / best / 1e6, ns, best
+        self.O.apply_add_mt(nthreads, self.O.CURLCURL_MASS, self.interp, self.curl, self.idx, self.ori, self.qd, self.blob, self.x, self.y)
+        return time.perf_counter() - t0
+
+    @property
+    def dofs_per_step(self):
+        return self.ndofs * (self.ns / self.ne)
 
 
 def run_reference(args, rank, world):
@@ -147,25 +153,19 @@ def run_reference(args, rank, world):
         return
     prob = build_problem(args.n, args.order, args.warp)
     cores = os.cpu_count() or 1
-    ne = prob["mesh"].ne
-    # bound each step to a few seconds of CPU work
-    sample = args.cpu_sample_elems or min(ne, max(cores * 64, 4096))
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_apply(prob, cores, min(sample, 512))
-    vals, t_tot = [], 0.0
+    ref = CpuReference(prob, args.cpu_sample_elems)  # default: the whole 2M-dof mesh every step
+    for _ in range(max(1, min(args.warmup, 2))):
+        ref.step(cores)
     steps = max(1, args.steps)
-    for _ in range(steps):
-        v, ns, dt = cpu_reference_apply(prob, cores, sample)
-        vals.append(v)
-        t_tot += dt
-    value = float(np.sum([prob["nd"].ndofs * (ns / ne)] * steps) / t_tot / 1e6)
+    t_tot = sum(ref.step(cores) for _ in range(steps))
+    value = float(ref.dofs_per_step * steps / t_tot / 1e6)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, prob, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{ns} of {ne} elements per step (dense non-tensor basis apply, oracle port of the libCEED /cpu/self path), dofs scaled by the element fraction"},
+                         "sample": f"{ref.ns} of {ref.ne} elements per step (dense non-tensor basis apply: oracle port of the libCEED /cpu/self path; the reference itself is unbuildable here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -174,11 +174,11 @@ def run_reference(args, rank, world):
 def workload_config(args, prob, world):
     nd = prob["nd"]
     return {
-        "workload": f"ND hex p={args.order} curl-curl+mass Mult on a uniform {args.n}^3-per-GPU box mesh, stored per-point geometry"
+        "workload": f"ND hex p={args.order} curl-curl+mass ParOperator Mult (P, local apply, P^T) on a uniform {args.n}^3-elements-per-GPU box mesh, stored per-point geometry"
                     + (" (assembled D)" if args.assemble_qdata else " (J^-T, w detJ; coefficient applied on the fly)"),
-        "order": args.order, "elements_per_gpu": int(prob["mesh"].ne), "dofs_per_gpu": int(nd.ndofs), "n_gpus": world,
-        "vector": "L-vector", "l2_policy": "inputs larger than L2 (q-data + x + y + indices > 126 MB)"
-        if prob["mesh"].ne * (10 * (args.order + 1) ** 3 * 8) > 126e6 else "L2 flushed between timed iterations",
+        "order": args.order, "elements_per_gpu": int(args.n ** 3), "global_true_dofs": int(nd.ndofs), "n_gpus": world,
+        "partition": "1 block per GPU, shared dofs summed by NCCL send/recv" if world > 1 else "single partition",
+        "vector": "true-dof (T) vector", "l2_policy": "L2 flushed (256 MiB write) between timed iterations",
     }
 
 
@@ -200,33 +200,62 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = capi.Ctx(local_rank)
+    parts = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
+    assert parts is not None, "--gpus must be 1, 2, 4 or 8"
+    if world > 1:
+        # one NCCL communicator inside the library (unique id from rank 0, shipped over torch.distributed)
+        uid = [capi.Ctx.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx = capi.Ctx(local_rank, nccl_uid=uid[0], rank=rank, nranks=world)
+    else:
+        ctx = capi.Ctx(local_rank)
+    capi.set_stream(ctx)
 
-    prob = build_problem(args.n, args.order, args.warp)
-    nd, p, q1d = prob["nd"], prob["p"], prob["q1d"]
-    geom = capi.Geom.hex(ctx, prob["xe"], prob["mesh"].attr, prob["mesh_order"], q1d, prob["nB"], prob["nG"], prob["tabs"].qw)
+    # weak scaling: an (n*px, n*py, n*pz) box split into px*py*pz blocks of n^3 elements, one per GPU
+    from palace_b200.host import hexmesh as hm
+    from palace_b200.host import partition as pt
+
+    gn = (args.n * parts[0], args.n * parts[1], args.n * parts[2])
+    prob = build_problem(gn, args.order, args.warp, size=(float(parts[0]), float(parts[1]), float(parts[2])))
+    p, q1d = prob["p"], prob["q1d"]
+    gnd = prob["nd"]
+    if world > 1:
+        elem_rank = hm.partition_box(gn, parts)
+        ls = pt.partition_space(gnd, elem_rank, rank, world)
+        nd, elems = ls.space, ls.elems
+        halo = capi.Halo(ctx, ls.n_true, ls.n_ghost, ls.nbr, ls.send_counts, ls.send_idx, ls.recv_counts)
+        n_true, lsize = ls.n_true, ls.lsize
+    else:
+        nd, elems, halo = gnd, np.arange(prob["mesh"].ne), None
+        n_true = lsize = gnd.ndofs
+    N_global = gnd.ndofs
+    geom = capi.Geom.hex(ctx, prob["xe"][elems], prob["mesh"].attr[elems], prob["mesh_order"], q1d, prob["nB"], prob["nG"],
+                         prob["tabs"].qw)
     idx, ori = nd.native_restriction()
     t = prob["tabs"]
-    op = capi.Op.create(ctx, geom, capi.CURLCURL_MASS, p, nd.ndofs, idx, ori, nd.dof_map, t.Bo, t.Bc, t.Gc, prob["blob"],
+    op = capi.Op.create(ctx, geom, capi.CURLCURL_MASS, p, lsize, idx, ori, nd.dof_map, t.Bo, t.Bc, t.Gc, prob["blob"],
                         assemble=bool(args.assemble_qdata))
-    N = nd.ndofs
+    A = capi.Operator.par(ctx, n_true, lsize, [op], None, None, diag_policy=1, halo=halo)
+    prob["local_ne"] = int(elems.size)
+    prob["local_dofs"] = int(lsize)
+    N = n_true
     xh = torch.from_numpy(np.random.default_rng(1 + rank).random(N)).pin_memory()
     yh = torch.empty(N, dtype=torch.float64).pin_memory()
     xd = xh.cuda()
     yd = torch.empty_like(xd)
+    xl = torch.zeros(lsize, dtype=torch.float64, device="cuda")
+    yl = torch.zeros(lsize, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream()
 
-    qbytes = prob["mesh"].ne * 10 * q1d ** 3 * 8
-    flush = None
-    if qbytes < 160e6:  # working set not safely larger than L2: flush explicitly
-        flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    qbytes = prob["local_ne"] * 10 * q1d ** 3 * 8
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2
 
     def step_device():
-        op.apply(xd, yd)
+        A.mult(xd, yd)  # ParOperator::Mult: P (halo), zero-fill, local apply, P^T (halo)
 
     def step_e2e():
         xd.copy_(xh, non_blocking=True)
-        op.apply(xd, yd)
+        A.mult(xd, yd)
         yh.copy_(yd, non_blocking=True)
 
     def barrier():
@@ -258,16 +287,16 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = float(tt.item())
-    value = world * N * args.steps / (total_ms * 1e-3) / 1e6
+    value = N_global * args.steps / (total_ms * 1e-3) / 1e6
 
     # ---- kernel-only timing for the roofline (memset excluded) ----
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
     for a, b in kev:
-        yd.zero_()
+        yl.zero_()
         if flush is not None:
             flush.zero_()
         a.record(stream)
-        op.apply_add(xd, yd)
+        op.apply_add(xl, yl)
         b.record(stream)
     torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
@@ -289,7 +318,7 @@ def main():
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * e2e_steps / (float(te.item()) * 1e-3) / 1e6
+    e2e_value = N_global * e2e_steps / (float(te.item()) * 1e-3) / 1e6
 
     line = None
     if rank == 0:
@@ -298,18 +327,21 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, prob, world),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N * 8), "d2h_bytes_per_step": int(N * 8)},
-            "gpu_launches": int(args.steps),  # one nd_hex_apply kernel per step (+1 cudaMemset node, not ours)
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N_global * 8), "d2h_bytes_per_step": int(N_global * 8)},
+            # per rank and step: the apply kernel (+ halo pack and unpack kernels when N > 1); memset/NCCL not counted
+            "gpu_launches": int(args.steps * (1 + (2 if world > 1 else 0))),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "nd_hex_apply_kernel", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(abytes)},
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = args.cpu_sample_elems or min(prob["mesh"].ne, max(cores * 64, 4096))
-            v, ns, dt = cpu_reference_apply(prob, cores, sample)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{ns} of {prob['mesh'].ne} elements, one dense-basis apply ({dt:.2f} s)"}
+            base_prob = prob if world == 1 else build_problem(args.n, args.order, args.warp)
+            ref = CpuReference(base_prob, args.cpu_sample_elems)
+            ref.step(cores)
+            dts = [ref.step(cores) for _ in range(5)]
+            line["cpu_baseline"] = {"value": ref.dofs_per_step / min(dts) / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{ref.ns} of {ref.ne} elements per apply, best of 5 ({min(dts):.3f} s); dense non-tensor basis apply (oracle port)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -191,7 +191,10 @@ typedef struct b2p_operator b2p_operator;
  * diag_policy 0 = DIAG_ZERO, 1 = DIAG_ONE; halo may be NULL (single partition). */
 int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coefs,
                      const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_halo *halo, b2p_operator **out);
-int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_operator **out);
+/* Interpolator on true-dof vectors (ParOperator(..., use_R) semantics); halos/true sizes of the input
+ * and output spaces, NULL / L-size for a single partition. */
+int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_halo *in_halo, int64_t in_tsize, b2p_halo *out_halo,
+                        int64_t out_tsize, b2p_operator **out);
 int b2p_operator_mult(b2p_operator *A, const double *x, double *y);
 int b2p_operator_mult_transpose(b2p_operator *A, const double *x, double *y);
 int b2p_operator_add_mult(b2p_operator *A, const double *x, double *y, double a);

@@ -494,7 +494,8 @@ void orc_diag_add(int kind, int ne, int P, int Q, const double *interp, const do
 
 // Multi-threaded variant for the CPU baseline timing (std::thread over contiguous element chunks,
 // like the reference's per-thread Ceed contexts, /root/reference/palace/fem/libceed/ceed.cpp:29-40,
-// operator.cpp:163-177): each thread accumulates into a private y and the results are summed.
+// operator.cpp:163-177): threads compute element vectors (E-vector) in parallel, then the
+// scatter-add into y is done over disjoint dof ranges in parallel.
 void orc_apply_add_mt(int nthreads, int kind, int ne, int P, int Q, const double *interp, const double *deriv,
                       const int *idx, const signed char *orient, const double *qdata, const void *ctx, const double *x,
                       double *y, long long lsize)
@@ -504,7 +505,9 @@ void orc_apply_add_mt(int nthreads, int kind, int ne, int P, int Q, const double
     orc_apply_add(kind, ne, P, Q, interp, deriv, idx, orient, qdata, ctx, x, y);
     return;
   }
-  std::vector<std::vector<double>> ys(nthreads);
+  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
+  const bool need_c = (kind != ND_MASS);
+  std::vector<double> Ye((size_t)ne * P);
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; t++)
   {
@@ -512,15 +515,72 @@ void orc_apply_add_mt(int nthreads, int kind, int ne, int P, int Q, const double
         [&, t]()
         {
           const int e0 = (int)((long long)ne * t / nthreads), e1 = (int)((long long)ne * (t + 1) / nthreads);
-          ys[t].assign((size_t)lsize, 0.0);
-          if (e1 > e0)
-            orc_apply_add(kind, e1 - e0, P, Q, interp, deriv, idx + (size_t)e0 * P, orient ? orient + (size_t)e0 * P : nullptr,
-                          qdata + (size_t)e0 * 11 * Q, ctx, x, ys[t].data());
+          std::vector<double> ue(P), u(3 * Q), c(3 * Q), v(3 * Q), w(3 * Q);
+          for (int e = e0; e < e1; e++)
+          {
+            const int *ie = idx + (size_t)e * P;
+            const signed char *oe = orient ? orient + (size_t)e * P : nullptr;
+            double *ye = Ye.data() + (size_t)e * P;
+            for (int i = 0; i < P; i++) ue[i] = (oe ? (double)oe[i] : 1.0) * x[ie[i]];
+            for (int d = 0; d < 3; d++)
+              for (int q = 0; q < Q; q++)
+              {
+                double su = 0, sc = 0;
+                if (need_u)
+                {
+                  const double *row = interp + ((size_t)d * Q + q) * P;
+                  for (int i = 0; i < P; i++) su += row[i] * ue[i];
+                }
+                if (need_c)
+                {
+                  const double *row = deriv + ((size_t)d * Q + q) * P;
+                  for (int i = 0; i < P; i++) sc += row[i] * ue[i];
+                }
+                u[d * Q + q] = su;
+                c[d * Q + q] = sc;
+              }
+            orc_apply_D(kind, ctx, Q, qdata + (size_t)e * 11 * Q, u.data(), c.data(), v.data(), w.data());
+            for (int i = 0; i < P; i++) ye[i] = 0.0;
+            for (int d = 0; d < 3; d++)
+              for (int q = 0; q < Q; q++)
+              {
+                if (need_u)
+                {
+                  const double *row = interp + ((size_t)d * Q + q) * P;
+                  const double sv = v[d * Q + q];
+                  for (int i = 0; i < P; i++) ye[i] += row[i] * sv;
+                }
+                if (need_c)
+                {
+                  const double *row = deriv + ((size_t)d * Q + q) * P;
+                  const double sw = w[d * Q + q];
+                  for (int i = 0; i < P; i++) ye[i] += row[i] * sw;
+                }
+              }
+            if (oe)
+              for (int i = 0; i < P; i++) ye[i] *= (double)oe[i];
+          }
         });
   }
   for (auto &t : th) t.join();
-  for (int t = 0; t < nthreads; t++)
-    for (long long i = 0; i < lsize; i++) y[i] += ys[t][i];
+  th.clear();
+  // scatter: thread t owns dofs in [lsize*t/nt, lsize*(t+1)/nt)
+  const int nts = nthreads > 16 ? 16 : nthreads;
+  for (int t = 0; t < nts; t++)
+  {
+    th.emplace_back(
+        [&, t]()
+        {
+          const long long lo = lsize * t / nts, hi = lsize * (t + 1) / nts;
+          const size_t tot = (size_t)ne * P;
+          for (size_t k = 0; k < tot; k++)
+          {
+            const long long g = idx[k];
+            if (g >= lo && g < hi) y[g] += Ye[k];
+          }
+        });
+  }
+  for (auto &t : th) t.join();
 }
 
 }  // extern "C"

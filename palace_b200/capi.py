@@ -341,9 +341,10 @@ class Operator:
         return o
 
     @classmethod
-    def interp(cls, ctx, it: Interp):
+    def interp(cls, ctx, it: Interp, in_halo=None, in_tsize=0, out_halo=None, out_tsize=0):
         h = C.c_void_p()
-        _chk(lib().b2p_operator_interp(ctx.h, it.h, C.byref(h)), ctx.h)
+        _chk(lib().b2p_operator_interp(ctx.h, it.h, in_halo.h if in_halo else None, C.c_int64(in_tsize),
+                                       out_halo.h if out_halo else None, C.c_int64(out_tsize), C.byref(h)), ctx.h)
         o = cls(ctx, h)
         o._keep = [it]
         return o

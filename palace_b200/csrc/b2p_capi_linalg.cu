@@ -114,11 +114,13 @@ int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2
   *out = h;
   return B2P_SUCCESS;
 }
-int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_operator **out)
+int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_halo *in_halo, int64_t in_tsize, b2p_halo *out_halo,
+                        int64_t out_tsize, b2p_operator **out)
 {
   B2P_CHECK(ctx, ctx && it && out, B2P_ERR_ARG, "b2p_operator_interp: bad argument");
   auto *h = new b2p_operator;
-  h->op = std::make_unique<InterpOperator>(ctx, it);
+  h->op = std::make_unique<InterpOperator>(ctx, it, in_halo ? halo_of(in_halo) : nullptr, in_tsize,
+                                           out_halo ? halo_of(out_halo) : nullptr, out_tsize);
   *out = h;
   return B2P_SUCCESS;
 }

@@ -119,11 +119,15 @@ struct InterpDesc;
 class InterpOperator : public Operator
 {
 public:
-  InterpOperator(b2p_ctx *c, b2p_interp *impl);
+  InterpOperator(b2p_ctx *c, b2p_interp *impl, Halo *in_halo, int64_t in_tsize, Halo *out_halo, int64_t out_tsize);
   void Mult(const double *x, double *y) const override;
   void MultTranspose(const double *x, double *y) const override;
   void AddMult(const double *x, double *y, double a = 1.0) const override;
   b2p_interp *impl;
+  Halo *in_halo, *out_halo;
+
+private:
+  mutable DVec lin_, lout_;
 };
 
 // ---------------------------------------------------------------- solvers

@@ -657,17 +657,61 @@ void IterativeSolver::MultGMRES(const double *b, double *x, bool flexible) const
 }
 
 // ------------------------------------------------------------------------------------ InterpOperator
-InterpOperator::InterpOperator(b2p_ctx *c, b2p_interp *impl_) : Operator(c, impl_->out_lsize, impl_->in_lsize), impl(impl_) {}
+InterpOperator::InterpOperator(b2p_ctx *c, b2p_interp *impl_, Halo *in_halo_, int64_t in_tsize, Halo *out_halo_, int64_t out_tsize)
+  : Operator(c, out_halo_ ? out_tsize : impl_->out_lsize, in_halo_ ? in_tsize : impl_->in_lsize), impl(impl_), in_halo(in_halo_),
+    out_halo(out_halo_)
+{
+}
+// y_T = R (1/mult) I P x_T   (ParOperator with use_R: no summation over ranks, libceed/operator.cpp:182-190)
+void InterpOperator::AddMult(const double *x, double *y, double a) const
+{
+  const double *lx = x;
+  if (in_halo)
+  {
+    if (lin_.n != impl->in_lsize) lin_.resize(ctx, impl->in_lsize);
+    vec::copy(ctx, lin_.p, x, width);
+    halo_forward(in_halo, lin_.p);
+    lx = lin_.p;
+  }
+  if (!out_halo)
+    interp_apply(impl, false, a, lx, y, ctx->stream);
+  else
+  {
+    if (lout_.n != impl->out_lsize) lout_.resize(ctx, impl->out_lsize);
+    vec::set(ctx, lout_.p, impl->out_lsize, 0.0);
+    interp_apply(impl, false, a, lx, lout_.p, ctx->stream);
+    vec::axpy(ctx, 1.0, lout_.p, y, height);
+  }
+}
 void InterpOperator::Mult(const double *x, double *y) const
 {
   vec::set(ctx, y, height, 0.0);
-  interp_apply(impl, false, 1.0, x, y, ctx->stream);
+  AddMult(x, y, 1.0);
 }
-void InterpOperator::AddMult(const double *x, double *y, double a) const { interp_apply(impl, false, a, x, y, ctx->stream); }
+// y_T = P^T I^T (1/mult) R^T x_T  (libceed/operator.cpp:214-240 with RestrictionMatrixMultTranspose)
 void InterpOperator::MultTranspose(const double *x, double *y) const
 {
-  vec::set(ctx, y, width, 0.0);
-  interp_apply(impl, true, 1.0, x, y, ctx->stream);
+  const double *lx = x;
+  if (out_halo)
+  {
+    if (lout_.n != impl->out_lsize) lout_.resize(ctx, impl->out_lsize);
+    vec::set(ctx, lout_.p, impl->out_lsize, 0.0);
+    vec::copy(ctx, lout_.p, x, height);
+    lx = lout_.p;
+  }
+  if (!in_halo)
+  {
+    vec::set(ctx, y, width, 0.0);
+    interp_apply(impl, true, 1.0, lx, y, ctx->stream);
+  }
+  else
+  {
+    if (lin_.n != impl->in_lsize) lin_.resize(ctx, impl->in_lsize);
+    vec::set(ctx, lin_.p, impl->in_lsize, 0.0);
+    interp_apply(impl, true, 1.0, lx, lin_.p, ctx->stream);
+    halo_reverse(in_halo, lin_.p);
+    vec::copy(ctx, y, lin_.p, width);
+  }
 }
 
 }  // namespace b2p

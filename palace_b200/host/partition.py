@@ -1,0 +1,80 @@
+"""Partition of a global hex space into per-rank L-vectors laid out [owned | ghosts grouped by owner]
+plus the neighbour exchange lists of the shared-dof assembly (stand-in for mfem::ParFiniteElementSpace's
+conforming prolongation, which Palace uses through ParOperator, /root/reference/palace/linalg/rap.cpp:212-222,
+after mesh::Partition, /root/reference/palace/driver.cpp:66-70). A dof is owned by the lowest rank
+whose elements touch it."""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+from .hexspace import HexSpace
+
+
+@dataclasses.dataclass
+class LocalSpace:
+    rank: int
+    elems: np.ndarray          # global element ids of this rank
+    n_true: int
+    n_ghost: int
+    local_to_global: np.ndarray  # [n_true + n_ghost]
+    space: HexSpace            # local space (lex_gid in local numbering, ndofs = n_true + n_ghost)
+    ess_tdofs: np.ndarray      # essential dofs among the owned ones (T-vector indices)
+    ess_ldofs: np.ndarray      # essential dofs among owned + ghosts (L-vector indices)
+    nbr: np.ndarray            # neighbour ranks (ascending)
+    send_counts: np.ndarray
+    send_idx: np.ndarray       # owned local indices, concatenated per neighbour, ascending global id
+    recv_counts: np.ndarray
+
+    @property
+    def lsize(self):
+        return self.n_true + self.n_ghost
+
+
+def dof_owner(space: HexSpace, elem_rank: np.ndarray, nranks: int) -> np.ndarray:
+    owner = np.full(space.ndofs, nranks, dtype=np.int64)
+    np.minimum.at(owner, space.lex_gid.ravel(), np.repeat(elem_rank.astype(np.int64), space.P))
+    return owner
+
+
+def partition_space(space: HexSpace, elem_rank: np.ndarray, rank: int, nranks: int, owner: np.ndarray | None = None) -> LocalSpace:
+    owner = dof_owner(space, elem_rank, nranks) if owner is None else owner
+    elems = np.nonzero(elem_rank == rank)[0]
+    gids = np.unique(space.lex_gid[elems])
+    own_mask = owner[gids] == rank
+    owned = gids[own_mask]
+    ghosts = gids[~own_mask]
+    gorder = np.lexsort((ghosts, owner[ghosts]))  # by owner rank, then global id
+    ghosts = ghosts[gorder]
+    l2g = np.concatenate([owned, ghosts])
+    g2l = np.full(space.ndofs, -1, dtype=np.int64)
+    g2l[l2g] = np.arange(l2g.size)
+    lex_local = g2l[space.lex_gid[elems]]
+    ess_mask = np.zeros(space.ndofs, dtype=bool)
+    ess_mask[space.ess_dofs] = True
+    ess_l = np.nonzero(ess_mask[l2g])[0]
+    ess_t = ess_l[ess_l < owned.size]
+    local = HexSpace(space.kind, space.p, int(l2g.size), space.P, lex_local, space.lex_sign[elems], space.dof_map, ess_l,
+                     np.bincount(lex_local.ravel(), minlength=l2g.size))
+    # receive side: ghosts grouped by owner
+    g_owner = owner[ghosts]
+    recv_from = np.unique(g_owner)
+    # send side: for every other rank s, my owned dofs that s touches
+    send_lists = {}
+    for s in range(nranks):
+        if s == rank:
+            continue
+        es = np.nonzero(elem_rank == s)[0]
+        if es.size == 0:
+            continue
+        touched = np.unique(space.lex_gid[es])
+        mine = touched[owner[touched] == rank]
+        if mine.size:
+            send_lists[s] = g2l[mine]  # ascending global id == the receiver's ghost order for owner `rank`
+    nbr = np.array(sorted(set(recv_from.tolist()) | set(send_lists.keys())), dtype=np.int32)
+    send_counts = np.array([send_lists[s].size if s in send_lists else 0 for s in nbr], dtype=np.int64)
+    recv_counts = np.array([(g_owner == s).sum() for s in nbr], dtype=np.int64)
+    send_idx = np.concatenate([send_lists[s] for s in nbr if s in send_lists]) if send_lists else np.zeros(0, dtype=np.int64)
+    return LocalSpace(rank, elems, int(owned.size), int(ghosts.size), l2g, local, ess_t, ess_l, nbr, send_counts,
+                      send_idx.astype(np.int32), recv_counts)

@@ -323,3 +323,18 @@ def test_fgmres_with_multigrid_preconditioner_solves_the_system(b2p_ctx, capi_mo
     st = K.stats()
     assert st["converged"] and st["its"] <= 25, st
     assert _rel(xd.cpu().numpy(), spla.spsolve(Ao.tocsc(), b)) < 1e-8
+
+
+def test_multi_gpu_partition_independence():
+    """Runs tools/dist_check.py under torchrun on 2 GPUs when the box has them (gpurun --gpus 2)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "dist_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
