@@ -119,6 +119,12 @@ enum
   B2P_APPLY_SIMPLE_KERNEL = 2
 };
 int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, int flags, b2p_stream s);
+/* Same over the element sub-range [e_begin, e_begin + e_count) with the L-vector in two pieces: dofs
+ * < n_owned in x / y (the true-dof vectors themselves), the rest in x_ghost / y_ghost. This is what lets
+ * a partitioned ParOperator run its interior elements while the ghost values are still in flight and
+ * never copy a T-vector into an L-vector (e_count < 0: to the end; n_owned < 0: everything owned). */
+int b2p_op_apply_add_split(b2p_op *op, double alpha, const double *x, const double *x_ghost, double *y, double *y_ghost,
+                           int64_t n_owned, int e_begin, int e_count, int flags, b2p_stream s);
 /* Essential (Dirichlet / PEC) L-vector dofs for the masked apply. */
 int b2p_op_set_essential(b2p_op *op, const int32_t *ess_ldofs, int64_t n);
 /* diag += diag(A) (ceed::Operator::AssembleDiagonal, operator.cpp:116-143) */
@@ -191,6 +197,9 @@ typedef struct b2p_operator b2p_operator;
  * diag_policy 0 = DIAG_ZERO, 1 = DIAG_ONE; halo may be NULL (single partition). */
 int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coefs,
                      const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_halo *halo, b2p_operator **out);
+/* Elements [0, ne_interior) of every local operator touch no ghost dof: they are applied while the forward
+ * shared-dof exchange is still in flight (element order chosen by the caller; 0 disables the overlap). */
+int b2p_operator_par_set_interior(b2p_operator *A, int ne_interior);
 /* Interpolator on true-dof vectors (ParOperator(..., use_R) semantics); halos/true sizes of the input
  * and output spaces, NULL / L-size for a single partition. */
 int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_halo *in_halo, int64_t in_tsize, b2p_halo *out_halo,

@@ -193,6 +193,10 @@ class Op:
         flags = (1 if masked else 0) | (2 if simple_kernel else 0)
         _chk(lib().b2p_op_apply_add_ex(self.h, C.c_double(alpha), _vp(x), _vp(y), flags, _stream(stream)), self.ctx.h)
 
+    def apply_add_split(self, alpha, x, xg, y, yg, n_owned, e_begin, e_count, masked=False, stream=None):
+        _chk(lib().b2p_op_apply_add_split(self.h, C.c_double(alpha), _vp(x), _vp(xg), _vp(y), _vp(yg), C.c_int64(n_owned), int(e_begin),
+                                          int(e_count), 1 if masked else 0, _stream(stream)), self.ctx.h)
+
     def set_essential(self, ess_ldofs):
         e = _np(ess_ldofs, np.int32)
         _chk(lib().b2p_op_set_essential(self.h, _ptr(e), C.c_int64(e.size)), self.ctx.h)
@@ -339,6 +343,9 @@ class Operator:
         o = cls(ctx, h)
         o._keep = list(ops)
         return o
+
+    def set_interior(self, ne_interior):
+        _chk(lib().b2p_operator_par_set_interior(self.h, int(ne_interior)), self.ctx.h)
 
     @classmethod
     def interp(cls, ctx, it: Interp, in_halo=None, in_tsize=0, out_halo=None, out_tsize=0):

@@ -114,6 +114,13 @@ int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2
   *out = h;
   return B2P_SUCCESS;
 }
+int b2p_operator_par_set_interior(b2p_operator *A, int ne_interior)
+{
+  auto *pa = A ? dynamic_cast<ParOperator *>(A->op.get()) : nullptr;
+  if (!pa || ne_interior < 0) return B2P_ERR_ARG;
+  pa->SetInteriorElements(ne_interior);
+  return B2P_SUCCESS;
+}
 int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_halo *in_halo, int64_t in_tsize, b2p_halo *out_halo,
                         int64_t out_tsize, b2p_operator **out)
 {

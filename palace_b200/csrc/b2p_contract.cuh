@@ -21,6 +21,30 @@ __device__ __forceinline__ void scatter1(double *y, int32_t gi, double v)
 // One pencil of a 3-D tensor contraction along axis AX.
 //   in  has dims (D0, D1, D2), x fastest; the contracted axis has NIN entries and becomes NOUT.
 //   out[o] (+)= sgn * sum_i M[o*mso + i*msi] * in[i]
+// L-vector stored in two pieces: owned dofs [0, n_owned) in the true-dof vector itself, ghost dofs
+// in a separate small buffer (so a ParOperator never copies T-vectors into L-vectors).
+struct VSplit
+{
+  long long n_owned;
+  const double *xg;
+  double *yg;
+};
+__device__ __forceinline__ const double *split_src(const double *x, const VSplit &sp, int32_t a)
+{
+  return a < sp.n_owned ? x + a : sp.xg + (a - sp.n_owned);
+}
+__device__ __forceinline__ double gather2(const double *__restrict__ x, const VSplit &sp, int32_t gi)
+{
+  if (gi == B2P_SKIP_IDX) return 0.0;
+  return (gi >= 0) ? __ldg(split_src(x, sp, gi)) : -__ldg(split_src(x, sp, -1 - gi));
+}
+__device__ __forceinline__ void scatter2(double *y, const VSplit &sp, int32_t gi, double v)
+{
+  if (gi == B2P_SKIP_IDX) return;
+  const int32_t a = gi >= 0 ? gi : -1 - gi;
+  atomicAdd(a < sp.n_owned ? y + a : sp.yg + (a - sp.n_owned), gi >= 0 ? v : -v);
+}
+
 template <int AX, int D0, int D1, int D2, int NIN, int NOUT, bool ACC>
 __device__ __forceinline__ void pencil(int r, const double *__restrict__ in, double *__restrict__ out,
                                        const double *__restrict__ M, int mso, int msi, double sgn)

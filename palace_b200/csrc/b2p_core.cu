@@ -87,6 +87,17 @@ int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, co
 
 }  // namespace b2p
 
+namespace b2p
+{
+int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, int flags,
+                cudaStream_t s)
+{
+  if (op->kind == B2P_H1_DIFFUSION) return launch_h1_hex_apply(op, lidx, alpha, x, y, rg, s);
+  if (flags & B2P_APPLY_SIMPLE_KERNEL) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
+  return launch_nd_hex_apply2(op, lidx, alpha, x, y, rg, s);
+}
+}  // namespace b2p
+
 using namespace b2p;
 
 extern "C"
@@ -484,9 +495,28 @@ int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, in
     B2P_CHECK(op->ctx, op->lidx_bc, B2P_ERR_ARG, "b2p_op_apply_add_ex: masked apply without b2p_op_set_essential");
     lidx = op->lidx_bc;
   }
-  if (op->kind == B2P_H1_DIFFUSION) return launch_h1_hex_apply(op, lidx, alpha, x, y, (cudaStream_t)s);
-  if (flags & B2P_APPLY_SIMPLE_KERNEL) return launch_nd_hex_apply(op, lidx, alpha, x, y, (cudaStream_t)s);
-  return launch_nd_hex_apply2(op, lidx, alpha, x, y, (cudaStream_t)s);
+  return b2p::apply_range(op, lidx, alpha, x, y, ApplyRange(), flags, (cudaStream_t)s);
+}
+
+int b2p_op_apply_add_split(b2p_op *op, double alpha, const double *x, const double *x_ghost, double *y, double *y_ghost,
+                           int64_t n_owned, int e_begin, int e_count, int flags, b2p_stream s)
+{
+  if (!op || !x || !y) return B2P_ERR_ARG;
+  const int32_t *lidx = op->lidx;
+  if (flags & B2P_APPLY_MASKED)
+  {
+    B2P_CHECK(op->ctx, op->lidx_bc, B2P_ERR_ARG, "b2p_op_apply_add_split: masked apply without b2p_op_set_essential");
+    lidx = op->lidx_bc;
+  }
+  B2P_CHECK(op->ctx, e_begin >= 0 && e_begin <= op->ne && (e_count < 0 || e_begin + e_count <= op->ne), B2P_ERR_ARG,
+            "b2p_op_apply_add_split: element range outside the operator");
+  ApplyRange rg;
+  rg.e_off = e_begin;
+  rg.e_cnt = e_count;
+  rg.n_owned = n_owned;
+  rg.xg = x_ghost;
+  rg.yg = y_ghost;
+  return b2p::apply_range(op, lidx, alpha, x, y, rg, flags, (cudaStream_t)s);
 }
 
 int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s) { return b2p_op_apply_add_ex(op, 1.0, x, y, 0, s); }

@@ -12,15 +12,6 @@
 namespace b2p
 {
 
-struct Halo
-{
-  b2p_ctx *ctx = nullptr;
-  int64_t n_true = 0, n_ghost = 0;
-  std::vector<int> nbr;                 // neighbour ranks
-  std::vector<int64_t> send_off, recv_off;  // prefix sums (size n_nbr + 1)
-  int32_t *d_send_idx = nullptr;        // owned L-indices to send, concatenated per neighbour
-  double *d_buf = nullptr;              // pack / unpack buffer (size send total)
-};
 
 namespace
 {
@@ -53,6 +44,43 @@ int halo_forward(Halo *h, double *lx)
   }
   ncclResult_t r = ncclGroupEnd();
   B2P_CHECK(c, r == ncclSuccess, B2P_ERR_NCCL, "halo_forward: %s", ncclGetErrorString(r));
+  return B2P_SUCCESS;
+}
+
+// Split variants: the owned part of the L-vector is the T-vector itself, ghosts live in h->d_xg / d_yg.
+int halo_forward_split(Halo *h, const double *x, cudaStream_t s)
+{
+  if (!h || h->nbr.empty()) return B2P_SUCCESS;
+  b2p_ctx *c = h->ctx;
+  const int64_t ns = h->send_off.back();
+  if (ns > 0) pack_kernel<<<(int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, s>>>(x, h->d_send_idx, ns, h->d_buf);
+  ncclGroupStart();
+  for (size_t k = 0; k < h->nbr.size(); k++)
+  {
+    const int64_t sc = h->send_off[k + 1] - h->send_off[k], rc = h->recv_off[k + 1] - h->recv_off[k];
+    if (sc > 0) ncclSend(h->d_buf + h->send_off[k], sc, ncclDouble, h->nbr[k], (ncclComm_t)c->comm, s);
+    if (rc > 0) ncclRecv(h->d_xg + h->recv_off[k], rc, ncclDouble, h->nbr[k], (ncclComm_t)c->comm, s);
+  }
+  ncclResult_t r = ncclGroupEnd();
+  B2P_CHECK(c, r == ncclSuccess, B2P_ERR_NCCL, "halo_forward_split: %s", ncclGetErrorString(r));
+  return B2P_SUCCESS;
+}
+
+int halo_reverse_split(Halo *h, double *y, cudaStream_t s)
+{
+  if (!h || h->nbr.empty()) return B2P_SUCCESS;
+  b2p_ctx *c = h->ctx;
+  const int64_t ns = h->send_off.back();
+  ncclGroupStart();
+  for (size_t k = 0; k < h->nbr.size(); k++)
+  {
+    const int64_t sc = h->send_off[k + 1] - h->send_off[k], rc = h->recv_off[k + 1] - h->recv_off[k];
+    if (rc > 0) ncclSend(h->d_yg + h->recv_off[k], rc, ncclDouble, h->nbr[k], (ncclComm_t)c->comm, s);
+    if (sc > 0) ncclRecv(h->d_buf + h->send_off[k], sc, ncclDouble, h->nbr[k], (ncclComm_t)c->comm, s);
+  }
+  ncclResult_t r = ncclGroupEnd();
+  B2P_CHECK(c, r == ncclSuccess, B2P_ERR_NCCL, "halo_reverse_split: %s", ncclGetErrorString(r));
+  if (ns > 0) unpack_add_kernel<<<(int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, s>>>(y, h->d_send_idx, ns, h->d_buf);
   return B2P_SUCCESS;
 }
 
@@ -118,6 +146,16 @@ int b2p_halo_create(b2p_ctx *ctx, int64_t n_true, int64_t n_ghost, int n_nbr, co
   int rc;
   if ((rc = upload(ctx, send_idx, (size_t)ns, &h.d_send_idx))) return rc;
   if (ns > 0) B2P_CUDA(ctx, cudaMalloc((void **)&h.d_buf, sizeof(double) * ns));
+  if (n_ghost > 0)
+  {
+    B2P_CUDA(ctx, cudaMalloc((void **)&h.d_xg, sizeof(double) * n_ghost));
+    B2P_CUDA(ctx, cudaMalloc((void **)&h.d_yg, sizeof(double) * n_ghost));
+  }
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  B2P_CUDA(ctx, cudaStreamCreateWithPriority(&h.comm_stream, cudaStreamNonBlocking, hi));
+  B2P_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_in, cudaEventDisableTiming));
+  B2P_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_fwd, cudaEventDisableTiming));
   B2P_CHECK(ctx, n_nbr == 0 || ctx->comm, B2P_ERR_NCCL, "b2p_halo_create: context has no NCCL communicator");
   *out = hh;
   return B2P_SUCCESS;
@@ -138,6 +176,11 @@ void b2p_halo_destroy(b2p_halo *h)
   if (!h) return;
   cudaFree(h->h.d_send_idx);
   cudaFree(h->h.d_buf);
+  cudaFree(h->h.d_xg);
+  cudaFree(h->h.d_yg);
+  if (h->h.comm_stream) cudaStreamDestroy(h->h.comm_stream);
+  if (h->h.ev_in) cudaEventDestroy(h->h.ev_in);
+  if (h->h.ev_fwd) cudaEventDestroy(h->h.ev_fwd);
   delete h;
 }
 

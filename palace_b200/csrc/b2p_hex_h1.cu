@@ -28,6 +28,7 @@ struct H1Params
   int64_t aq_estride;
   int ne;
   int PS;  // padded restriction row stride
+  VSplit sp;
 };
 
 template <int P_, int Q_>
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(NT) h1_hex_diffusion_kernel(H1Params prm)
     double v = 0.0;
     if (e0 + e < prm.ne)
     {
-      v = gather1(prm.x, prm.lidx[(size_t)(e0 + e) * prm.PS + l]);
+      v = gather2(prm.x, prm.sp, prm.lidx[(size_t)(e0 + e) * prm.PS + l]);
     }
     U[e * ES + l] = v;
   }
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(NT) h1_hex_diffusion_kernel(H1Params prm)
   {
     const int e = w / P, l = w % P;
     if (e0 + e >= prm.ne) continue;
-    scatter1(prm.y, prm.lidx[(size_t)(e0 + e) * prm.PS + l], prm.alpha * U[e * ES + l]);
+    scatter2(prm.y, prm.sp, prm.lidx[(size_t)(e0 + e) * prm.PS + l], prm.alpha * U[e * ES + l]);
   }
 }
 
@@ -166,26 +167,30 @@ __global__ void h1_hex_diag_kernel(H1Params prm, int p, int q, bool assembled)
   atomicAdd(prm.y + gi, s);
 }
 
-H1Params make_params(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y)
+H1Params make_params(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg = ApplyRange())
 {
   H1Params prm;
-  prm.lidx = lidx;
+  const int e_off = rg.e_off, e_cnt = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
+  prm.lidx = lidx + (size_t)e_off * op->PS;
   prm.alpha = alpha;
+  prm.sp.n_owned = rg.n_owned < 0 ? op->lsize : rg.n_owned;
+  prm.sp.xg = rg.xg;
+  prm.sp.yg = rg.yg;
   prm.aq_estride = op->aq_estride;
   prm.PS = op->PS;
   prm.tab = op->tab;
-  prm.qd = op->geom->qd;
+  prm.qd = op->geom->qd + (size_t)e_off * 10 * op->geom->Q;
   prm.mat = op->mat;
-  prm.emat = op->emat;
-  prm.aq = op->aq;
+  prm.emat = op->emat + 2 * (size_t)e_off;
+  prm.aq = op->aq ? op->aq + (size_t)e_off * op->aq_estride : nullptr;
   prm.x = x;
   prm.y = y;
-  prm.ne = op->ne;
+  prm.ne = e_cnt;
   return prm;
 }
 
 template <int P_, int Q_, bool ASM>
-int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
   using L = H1Layout<P_, Q_>;
   constexpr int per_elem_bytes = L::PER_ELEM * 8;
@@ -200,18 +205,20 @@ int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, do
     B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     configured = true;
   }
-  kern<<<(op->ne + NEB - 1) / NEB, NT, shmem, s>>>(make_params(op, lidx, alpha, x, y));
+  const int ne_run = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
+  if (ne_run <= 0) return B2P_SUCCESS;
+  kern<<<(ne_run + NEB - 1) / NEB, NT, shmem, s>>>(make_params(op, lidx, alpha, x, y, rg));
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
 
 }  // namespace
 
-int launch_h1_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+int launch_h1_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
 #define B2P_CASE(PP, QQ)                                                                              \
   if (op->p == PP && op->q1d == QQ)                                                                   \
-    return op->assembled ? launch_pq<PP, QQ, true>(op, lidx, alpha, x, y, s) : launch_pq<PP, QQ, false>(op, lidx, alpha, x, y, s);
+    return op->assembled ? launch_pq<PP, QQ, true>(op, lidx, alpha, x, y, rg, s) : launch_pq<PP, QQ, false>(op, lidx, alpha, x, y, rg, s);
   B2P_CASE(1, 2) B2P_CASE(1, 3) B2P_CASE(1, 4) B2P_CASE(1, 5) B2P_CASE(1, 6) B2P_CASE(1, 7)
   B2P_CASE(2, 3) B2P_CASE(2, 4) B2P_CASE(2, 5) B2P_CASE(2, 6) B2P_CASE(2, 7)
   B2P_CASE(3, 4) B2P_CASE(3, 5) B2P_CASE(3, 6) B2P_CASE(3, 7)

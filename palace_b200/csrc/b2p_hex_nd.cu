@@ -52,6 +52,7 @@ struct NDParams
   int64_t aq_estride;
   int ne;
   int PS;  // padded restriction row stride
+  VSplit sp;
 };
 
 // KIND: B2P_CURLCURL / B2P_ND_MASS / B2P_CURLCURL_MASS. ASM: assembled q-data.
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(NT) nd_hex_apply_kernel(NDParams prm)
     double v = 0.0;
     if (e0 + e < prm.ne)
     {
-      v = gather1(prm.x, prm.lidx[(size_t)(e0 + e) * prm.PS + l]);
+      v = gather2(prm.x, prm.sp, prm.lidx[(size_t)(e0 + e) * prm.PS + l]);
     }
     U[e * ES + l] = v;
   }
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(NT) nd_hex_apply_kernel(NDParams prm)
   {
     const int e = w / P, l = w % P;
     if (e0 + e >= prm.ne) continue;
-    scatter1(prm.y, prm.lidx[(size_t)(e0 + e) * prm.PS + l], prm.alpha * U[e * ES + l]);
+    scatter2(prm.y, prm.sp, prm.lidx[(size_t)(e0 + e) * prm.PS + l], prm.alpha * U[e * ES + l]);
   }
 }
 
@@ -381,26 +382,30 @@ __global__ void nd_assemble_qdata_kernel(NDParams prm, int Q, double *aq)
   }
 }
 
-NDParams make_params(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y)
+NDParams make_params(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg = ApplyRange())
 {
   NDParams prm;
-  prm.lidx = lidx;
+  const int e_off = rg.e_off, e_cnt = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
+  prm.lidx = lidx + (size_t)e_off * op->PS;
   prm.alpha = alpha;
+  prm.sp.n_owned = rg.n_owned < 0 ? op->lsize : rg.n_owned;
+  prm.sp.xg = rg.xg;
+  prm.sp.yg = rg.yg;
   prm.aq_estride = op->aq_estride;
   prm.PS = op->PS;
   prm.tab = op->tab;
-  prm.qd = op->geom->qd;
+  prm.qd = op->geom->qd + (size_t)e_off * 10 * op->geom->Q;
   prm.mat = op->mat;
-  prm.emat = op->emat;
-  prm.aq = op->aq;
+  prm.emat = op->emat + 2 * (size_t)e_off;
+  prm.aq = op->aq ? op->aq + (size_t)e_off * op->aq_estride : nullptr;
   prm.x = x;
   prm.y = y;
-  prm.ne = op->ne;
+  prm.ne = e_cnt;
   return prm;
 }
 
 template <int P_, int Q_, int KIND, bool ASM>
-int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
   using L = NDLayout<P_, Q_>;
   // elements per block: keep shared memory under ~96 KB and at least 128 threads of work
@@ -416,25 +421,27 @@ int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, do
     B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     configured = true;
   }
-  const int grid = (op->ne + NEB - 1) / NEB;
-  kern<<<grid, NT, shmem, s>>>(make_params(op, lidx, alpha, x, y));
+  const int ne_run = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
+  if (ne_run <= 0) return B2P_SUCCESS;
+  const int grid = (ne_run + NEB - 1) / NEB;
+  kern<<<grid, NT, shmem, s>>>(make_params(op, lidx, alpha, x, y, rg));
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
 
 template <int P_, int Q_>
-int launch_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+int launch_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
   const bool a = op->assembled;
   switch (op->kind)
   {
     case B2P_CURLCURL:
-      return a ? launch_pq<P_, Q_, B2P_CURLCURL, true>(op, lidx, alpha, x, y, s) : launch_pq<P_, Q_, B2P_CURLCURL, false>(op, lidx, alpha, x, y, s);
+      return a ? launch_pq<P_, Q_, B2P_CURLCURL, true>(op, lidx, alpha, x, y, rg, s) : launch_pq<P_, Q_, B2P_CURLCURL, false>(op, lidx, alpha, x, y, rg, s);
     case B2P_ND_MASS:
-      return a ? launch_pq<P_, Q_, B2P_ND_MASS, true>(op, lidx, alpha, x, y, s) : launch_pq<P_, Q_, B2P_ND_MASS, false>(op, lidx, alpha, x, y, s);
+      return a ? launch_pq<P_, Q_, B2P_ND_MASS, true>(op, lidx, alpha, x, y, rg, s) : launch_pq<P_, Q_, B2P_ND_MASS, false>(op, lidx, alpha, x, y, rg, s);
     case B2P_CURLCURL_MASS:
-      return a ? launch_pq<P_, Q_, B2P_CURLCURL_MASS, true>(op, lidx, alpha, x, y, s)
-               : launch_pq<P_, Q_, B2P_CURLCURL_MASS, false>(op, lidx, alpha, x, y, s);
+      return a ? launch_pq<P_, Q_, B2P_CURLCURL_MASS, true>(op, lidx, alpha, x, y, rg, s)
+               : launch_pq<P_, Q_, B2P_CURLCURL_MASS, false>(op, lidx, alpha, x, y, rg, s);
   }
   set_error(op->ctx, "nd_hex_apply: unsupported kind %d", op->kind);
   return B2P_ERR_UNSUPPORTED;
@@ -442,10 +449,10 @@ int launch_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
 
 }  // namespace
 
-int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
 #define B2P_CASE(PP, QQ) \
-  if (op->p == PP && op->q1d == QQ) return launch_kind<PP, QQ>(op, lidx, alpha, x, y, s);
+  if (op->p == PP && op->q1d == QQ) return launch_kind<PP, QQ>(op, lidx, alpha, x, y, rg, s);
   // (p, q1d): q1d = p+1 for a stand-alone operator; larger q1d for p-coarsened operators that
   // reuse the fine level's quadrature (CeedOperatorCoarsen, libceed/operator.cpp:525-585).
   B2P_CASE(1, 2) B2P_CASE(1, 3) B2P_CASE(1, 4) B2P_CASE(1, 5) B2P_CASE(1, 6) B2P_CASE(1, 7)

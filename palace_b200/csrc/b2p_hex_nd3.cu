@@ -48,6 +48,7 @@ struct ND2Params
   double *y;
   double alpha;
   int ne;
+  VSplit sp;
   double Bo[Q_ * P_];
   double Bc[Q_ * (P_ + 1)];
   double Gc[Q_ * (P_ + 1)];
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
       if (l < nel * PS)
       {
         const int32_t gi = gI[l];
-        if (gi != B2P_SKIP_IDX) cp_async8(sU + l, prm.x + (gi >= 0 ? gi : -1 - gi));
+        if (gi != B2P_SKIP_IDX) cp_async8(sU + l, split_src(prm.x, prm.sp, gi >= 0 ? gi : -1 - gi));
       }
     }
     cp_async_commit();
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
           o += prm.Bc[qz * n + k] * a[qz];
           if (CURL) o += prm.Gc[qz * n + k] * b[qz];
         }
-        scatter1(prm.y, li[p * n * k], alpha * o);
+        scatter2(prm.y, prm.sp, li[p * n * k], alpha * o);
       }
     }
     for (int w = lane; w < NEW * (n * p); w += 32)
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
           o += prm.Bc[qz * n + k] * a[qz];
           if (CURL) o += prm.Gc[qz * n + k] * b[qz];
         }
-        scatter1(prm.y, li[n * p * k], alpha * o);
+        scatter2(prm.y, prm.sp, li[n * p * k], alpha * o);
       }
     }
     for (int w = lane; w < NEW * (n * n); w += 32)
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
         double o = 0.0;
   #pragma unroll
         for (int qz = 0; qz < q; qz++) o += prm.Bo[qz * p + k] * a[qz];
-        scatter1(prm.y, li[n * n * k], alpha * o);
+        scatter2(prm.y, prm.sp, li[n * n * k], alpha * o);
       }
     }
 
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
 }
 
 template <int P_, int Q_, int KIND, bool ASM>
-int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
   using L = ND3Layout<P_, Q_, KIND, ASM>;
   // warps per CTA / CTAs per SM from the per-warp shared-memory footprint
@@ -721,21 +722,26 @@ int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
     configured = true;
   }
   ND2Params<P_, Q_> prm;
-  prm.lidx = lidx;
-  prm.qd = op->geom->qd;
-  prm.aq = op->aq;
+  const int e_off = rg.e_off, e_cnt = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
+  if (e_cnt <= 0) return B2P_SUCCESS;
+  prm.lidx = lidx + (size_t)e_off * op->PS;
+  prm.qd = op->geom->qd + (size_t)e_off * 10 * op->geom->Q;
+  prm.aq = op->aq ? op->aq + (size_t)e_off * op->aq_estride : nullptr;
   prm.mat = op->mat;
-  prm.emat = op->emat;
-  prm.ecoef = op->ecoef;
+  prm.emat = op->emat + 2 * (size_t)e_off;
+  prm.ecoef = op->ecoef ? op->ecoef + 18 * (size_t)e_off : nullptr;
   prm.x = x;
   prm.y = y;
   prm.alpha = alpha;
-  prm.ne = op->ne;
+  prm.ne = e_cnt;
+  prm.sp.n_owned = rg.n_owned < 0 ? op->lsize : rg.n_owned;
+  prm.sp.xg = rg.xg;
+  prm.sp.yg = rg.yg;
   const int n = P_ + 1;
   for (int i = 0; i < Q_ * P_; i++) prm.Bo[i] = op->h_tab[i];
   for (int i = 0; i < Q_ * n; i++) prm.Bc[i] = op->h_tab[Q_ * P_ + i];
   for (int i = 0; i < Q_ * n; i++) prm.Gc[i] = op->h_tab[Q_ * P_ + Q_ * n + i];
-  const int nb = (op->ne + L::NEW - 1) / L::NEW;
+  const int nb = (e_cnt + L::NEW - 1) / L::NEW;
   int grid = op->ctx->sm_count * MINB;
   if (grid > (nb + NW - 1) / NW) grid = (nb + NW - 1) / NW;
   kern<<<grid, NW * 32, shmem, s>>>(prm);
@@ -744,20 +750,20 @@ int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
 }
 
 template <int P_, int Q_>
-int launch3_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+int launch3_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
   const bool a = op->assembled;
   switch (op->kind)
   {
     case B2P_CURLCURL:
-      return a ? launch3<P_, Q_, B2P_CURLCURL, true>(op, lidx, alpha, x, y, s)
-               : launch3<P_, Q_, B2P_CURLCURL, false>(op, lidx, alpha, x, y, s);
+      return a ? launch3<P_, Q_, B2P_CURLCURL, true>(op, lidx, alpha, x, y, rg, s)
+               : launch3<P_, Q_, B2P_CURLCURL, false>(op, lidx, alpha, x, y, rg, s);
     case B2P_ND_MASS:
-      return a ? launch3<P_, Q_, B2P_ND_MASS, true>(op, lidx, alpha, x, y, s)
-               : launch3<P_, Q_, B2P_ND_MASS, false>(op, lidx, alpha, x, y, s);
+      return a ? launch3<P_, Q_, B2P_ND_MASS, true>(op, lidx, alpha, x, y, rg, s)
+               : launch3<P_, Q_, B2P_ND_MASS, false>(op, lidx, alpha, x, y, rg, s);
     case B2P_CURLCURL_MASS:
-      return a ? launch3<P_, Q_, B2P_CURLCURL_MASS, true>(op, lidx, alpha, x, y, s)
-               : launch3<P_, Q_, B2P_CURLCURL_MASS, false>(op, lidx, alpha, x, y, s);
+      return a ? launch3<P_, Q_, B2P_CURLCURL_MASS, true>(op, lidx, alpha, x, y, rg, s)
+               : launch3<P_, Q_, B2P_CURLCURL_MASS, false>(op, lidx, alpha, x, y, rg, s);
   }
   set_error(op->ctx, "nd_hex_apply: unsupported kind %d", op->kind);
   return B2P_ERR_UNSUPPORTED;
@@ -765,10 +771,10 @@ int launch3_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x,
 
 }  // namespace
 
-int launch_nd_hex_apply2(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s)
+int launch_nd_hex_apply2(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
 #define B2P_CASE(PP, QQ) \
-  if (op->p == PP && op->q1d == QQ) return launch3_kind<PP, QQ>(op, lidx, alpha, x, y, s);
+  if (op->p == PP && op->q1d == QQ) return launch3_kind<PP, QQ>(op, lidx, alpha, x, y, rg, s);
   B2P_CASE(1, 2) B2P_CASE(1, 3) B2P_CASE(1, 4) B2P_CASE(1, 5) B2P_CASE(1, 6) B2P_CASE(1, 7)
   B2P_CASE(2, 3) B2P_CASE(2, 4) B2P_CASE(2, 5) B2P_CASE(2, 6) B2P_CASE(2, 7)
   B2P_CASE(3, 4) B2P_CASE(3, 5) B2P_CASE(3, 6) B2P_CASE(3, 7)

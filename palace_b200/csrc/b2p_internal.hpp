@@ -123,11 +123,21 @@ struct b2p_interp
 
 namespace b2p
 {
+// Element sub-range and owned/ghost split of one apply (defaults: all elements, no ghosts).
+struct ApplyRange
+{
+  int e_off = 0, e_cnt = -1;
+  long long n_owned = -1;      // dofs below this index live in x / y, the rest in xg / yg
+  const double *xg = nullptr;
+  double *yg = nullptr;
+};
 // Kernel launchers (defined in the .cu files).
-int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s);
-int launch_nd_hex_apply2(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s);
+int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
+int launch_nd_hex_apply2(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
+int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, int flags,
+                cudaStream_t s);
 int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
-int launch_h1_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, cudaStream_t s);
+int launch_h1_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
 int launch_h1_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
 int launch_assemble_qdata(b2p_op *op, cudaStream_t s);
 int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, const double *d_B, const double *d_G,

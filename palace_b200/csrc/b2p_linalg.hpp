@@ -8,6 +8,7 @@
 // Real-valued (OperType = Operator) instantiation; all vectors are raw device pointers (T-vectors).
 #pragma once
 #include <cmath>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -80,7 +81,18 @@ protected:
 
 // P / P^T of one finite element space on this rank (linalg/rap.cpp:212-222): owned dofs first,
 // then ghosts. nranks == 1 (or no shared dofs): identity, zero copies.
-struct Halo;
+struct Halo
+{
+  b2p_ctx *ctx = nullptr;
+  int64_t n_true = 0, n_ghost = 0;
+  std::vector<int> nbr;                 // neighbour ranks
+  std::vector<int64_t> send_off, recv_off;  // prefix sums (size n_nbr + 1)
+  int32_t *d_send_idx = nullptr;        // owned L-indices to send, concatenated per neighbour
+  double *d_buf = nullptr;              // pack / unpack buffer (size send total)
+  double *d_xg = nullptr, *d_yg = nullptr;  // ghost pieces of the input / output L-vectors
+  cudaStream_t comm_stream = nullptr;   // high-priority stream: the forward exchange overlaps interior elements
+  cudaEvent_t ev_in = nullptr, ev_fwd = nullptr;
+};
 
 // ParOperator over the local partially assembled operators: y = P^T (sum_i c_i A_i) P x with
 // essential-dof elimination (rap.cpp:195-234,277-318,154-193; BuildParSumOperator rap.cpp:764-829).
@@ -98,6 +110,7 @@ public:
   void Mult(const double *x, double *y) const override;
   void AddMult(const double *x, double *y, double a = 1.0) const override;
   void AssembleDiagonal(double *d) const override;
+  void SetInteriorElements(int n) { ne_interior = n; }  // elements [0, n) touch no ghost dof
   const int32_t *EssentialTrueDofs() const { return d_ess; }
   int64_t NumEssential() const { return n_ess; }
   int64_t lsize;
@@ -108,7 +121,14 @@ private:
   int64_t n_ess = 0;
   int diag_policy;  // 0 = DIAG_ZERO, 1 = DIAG_ONE
   Halo *halo;
+  int ne_interior = 0;
   mutable DVec lx_, ly_;
+  // The partitioned Mult is ~a dozen stream operations (events, pack, NCCL groups, memsets, two element
+  // kernels, unpack): launch-bound when issued one by one, so it is captured once per (x, y) pair into a
+  // CUDA graph and replayed (solver loops reuse a handful of vector pairs).
+  void MultHaloBody(const double *x, double *y, cudaStream_t s) const;
+  mutable std::map<std::pair<const double *, double *>, cudaGraphExec_t> graphs_;
+  mutable bool warmed_ = false;
 };
 
 // Element-local tensor-product interpolation between two hex spaces on the same mesh: the

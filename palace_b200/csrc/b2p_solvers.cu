@@ -8,6 +8,8 @@ namespace b2p
 
 int halo_forward(Halo *h, double *lx);
 int halo_reverse(Halo *h, double *ly);
+int halo_forward_split(Halo *h, const double *x, cudaStream_t s);
+int halo_reverse_split(Halo *h, double *y, cudaStream_t s);
 int interp_apply(const b2p_interp *it, bool transpose, double alpha, const double *x, double *y, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------ Operator
@@ -39,7 +41,40 @@ ParOperator::ParOperator(b2p_ctx *c, int64_t tsize, int64_t lsize_, const std::v
   for (auto &t : terms)
     if (!t.op->lidx_bc) b2p_op_set_essential(t.op, ess_tdofs, n_ess);
 }
-ParOperator::~ParOperator() { cudaFree(d_ess); }
+ParOperator::~ParOperator()
+{
+  cudaFree(d_ess);
+  for (auto &g : graphs_) cudaGraphExecDestroy(g.second);
+}
+
+void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
+{
+  // Owned dofs are read from x and accumulated into y directly; ghosts live in the halo's buffers.
+  //   main stream : zero y, y_ghost; forward exchange (P); INTERFACE elements (the few that touch ghosts)
+  //   comm stream : reverse exchange (P^T) + add into y   |  main stream: INTERIOR elements
+  // The persistent element kernel fills every SM, so a collective can only overlap it if its kernel is
+  // already resident: the reverse exchange is therefore launched just before the interior elements.
+  // (Measured on 2 x B200, p = 3, 2M dofs/GPU: exchange ~13 us per direction, interface 9 us, interior 60 us.)
+  Halo *h = halo;
+  vec::set(ctx, y, height, 0.0);
+  if (h->n_ghost > 0) cudaMemsetAsync(h->d_yg, 0, sizeof(double) * h->n_ghost, s);
+  halo_forward_split(h, x, s);
+  const int n_int = ne_interior;
+  for (auto &t : terms)
+    b2p_op_apply_add_split(t.op, t.coef, x, h->d_xg, y, h->d_yg, height, n_int, -1, B2P_APPLY_MASKED, s);
+  if (n_int > 0)
+  {
+    cudaEventRecord(h->ev_in, s);
+    cudaStreamWaitEvent(h->comm_stream, h->ev_in, 0);
+    halo_reverse_split(h, y, h->comm_stream);
+    cudaEventRecord(h->ev_fwd, h->comm_stream);
+    for (auto &t : terms)
+      b2p_op_apply_add_split(t.op, t.coef, x, nullptr, y, nullptr, height, 0, n_int, B2P_APPLY_MASKED, s);
+    cudaStreamWaitEvent(s, h->ev_fwd, 0);
+  }
+  else
+    halo_reverse_split(h, y, s);
+}
 
 // rap.cpp:195-234
 void ParOperator::Mult(const double *x, double *y) const
@@ -52,14 +87,38 @@ void ParOperator::Mult(const double *x, double *y) const
   }
   else
   {
-    if (lx_.n != lsize) lx_.resize(ctx, lsize);
-    if (ly_.n != lsize) ly_.resize(ctx, lsize);
-    vec::copy(ctx, lx_.p, x, height);
-    halo_forward(halo, lx_.p);
-    vec::set(ctx, ly_.p, lsize, 0.0);
-    for (auto &t : terms) b2p_op_apply_add_ex(t.op, t.coef, lx_.p, ly_.p, B2P_APPLY_MASKED, s);
-    halo_reverse(halo, ly_.p);
-    vec::copy(ctx, y, ly_.p, height);
+    const auto key = std::make_pair(x, y);
+    auto it = graphs_.find(key);
+    if (!warmed_)
+    {
+      // first call runs eagerly: one-time kernel attribute setup must not happen inside a capture
+      warmed_ = true;
+      MultHaloBody(x, y, s);
+    }
+    else if (it == graphs_.end())
+    {
+      if (graphs_.size() >= 64)
+      {
+        for (auto &g : graphs_) cudaGraphExecDestroy(g.second);
+        graphs_.clear();
+      }
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
+      {
+        MultHaloBody(x, y, s);
+        if (cudaStreamEndCapture(s, &graph) == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)
+          it = graphs_.emplace(key, exec).first;
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (it == graphs_.end())
+      {
+        cudaGetLastError();
+        set_error(ctx, "ParOperator::Mult: CUDA graph capture of the partitioned apply failed");
+        MultHaloBody(x, y, s);
+      }
+    }
+    if (it != graphs_.end()) cudaGraphLaunch(it->second, s);
   }
   if (n_ess > 0)
   {

@@ -26,6 +26,7 @@ class LocalSpace:
     send_counts: np.ndarray
     send_idx: np.ndarray       # owned local indices, concatenated per neighbour, ascending global id
     recv_counts: np.ndarray
+    n_interior: int = 0        # elems[:n_interior] touch no ghost dof
 
     @property
     def lsize(self):
@@ -38,9 +39,26 @@ def dof_owner(space: HexSpace, elem_rank: np.ndarray, nranks: int) -> np.ndarray
     return owner
 
 
-def partition_space(space: HexSpace, elem_rank: np.ndarray, rank: int, nranks: int, owner: np.ndarray | None = None) -> LocalSpace:
-    owner = dof_owner(space, elem_rank, nranks) if owner is None else owner
+def interface_order(mesh_elems: np.ndarray, elem_rank: np.ndarray, rank: int):
+    """Element order of one rank shared by ALL its spaces: elements that touch no vertex of another
+    rank's elements first (they can never touch a ghost dof of any space), interface elements last."""
+    nv = int(mesh_elems.max()) + 1
+    vmin = np.full(nv, np.iinfo(np.int64).max, dtype=np.int64)
+    vmax = np.full(nv, -1, dtype=np.int64)
+    er = np.repeat(elem_rank.astype(np.int64), mesh_elems.shape[1])
+    np.minimum.at(vmin, mesh_elems.ravel(), er)
+    np.maximum.at(vmax, mesh_elems.ravel(), er)
+    shared_v = vmin != vmax
     elems = np.nonzero(elem_rank == rank)[0]
+    iface = shared_v[mesh_elems[elems]].any(axis=1)
+    return np.concatenate([elems[~iface], elems[iface]]), int((~iface).sum())
+
+
+def partition_space(space: HexSpace, elem_rank: np.ndarray, rank: int, nranks: int, owner: np.ndarray | None = None,
+                    order=None) -> LocalSpace:
+    """``order`` = (elems, n_interior) from interface_order() to share one element order across spaces."""
+    owner = dof_owner(space, elem_rank, nranks) if owner is None else owner
+    elems = np.nonzero(elem_rank == rank)[0] if order is None else order[0]
     gids = np.unique(space.lex_gid[elems])
     own_mask = owner[gids] == rank
     owned = gids[own_mask]
@@ -50,6 +68,14 @@ def partition_space(space: HexSpace, elem_rank: np.ndarray, rank: int, nranks: i
     l2g = np.concatenate([owned, ghosts])
     g2l = np.full(space.ndofs, -1, dtype=np.int64)
     g2l[l2g] = np.arange(l2g.size)
+    # interior elements (touching no ghost dof) first: they can run while the ghost exchange is in flight
+    touches_ghost = (g2l[space.lex_gid[elems]] >= owned.size).any(axis=1)
+    if order is None:
+        elems = np.concatenate([elems[~touches_ghost], elems[touches_ghost]])
+        n_interior = int((~touches_ghost).sum())
+    else:
+        n_interior = int(order[1])
+        assert not touches_ghost[:n_interior].any()
     lex_local = g2l[space.lex_gid[elems]]
     ess_mask = np.zeros(space.ndofs, dtype=bool)
     ess_mask[space.ess_dofs] = True
@@ -77,4 +103,4 @@ def partition_space(space: HexSpace, elem_rank: np.ndarray, rank: int, nranks: i
     recv_counts = np.array([(g_owner == s).sum() for s in nbr], dtype=np.int64)
     send_idx = np.concatenate([send_lists[s] for s in nbr if s in send_lists]) if send_lists else np.zeros(0, dtype=np.int64)
     return LocalSpace(rank, elems, int(owned.size), int(ghosts.size), l2g, local, ess_t, ess_l, nbr, send_counts,
-                      send_idx.astype(np.int32), recv_counts)
+                      send_idx.astype(np.int32), recv_counts, n_interior)

@@ -42,8 +42,9 @@ def main():
     blob_h1 = common.coefficient(O.H1_DIFFUSION, 2, "matrix", a_mass=1.0)
     nd = {q: hs.build_nd_space(prob.mesh, prob.topo, q) for q in orders}
     h1 = {q: hs.build_h1_space(prob.mesh, prob.topo, q) for q in orders}
-    lnd = {q: pt.partition_space(nd[q], elem_rank, rank, world) for q in orders}
-    lh1 = {q: pt.partition_space(h1[q], elem_rank, rank, world) for q in orders}
+    order = pt.interface_order(prob.mesh.elems, elem_rank, rank)
+    lnd = {q: pt.partition_space(nd[q], elem_rank, rank, world, order=order) for q in orders}
+    lh1 = {q: pt.partition_space(h1[q], elem_rank, rank, world, order=order) for q in orders}
     elems = lnd[p].elems
     nB, nG = prob.node_tabs
     geom = capi.Geom.hex(ctx, prob.xe[elems], prob.mesh.attr[elems], prob.mesh_order, prob.q1d, nB, nG, prob.tabs.qw)
@@ -68,6 +69,7 @@ def main():
             op = fine.coarsen(*args)
         op.set_essential(ls.ess_ldofs)  # owned + ghost copies
         A = capi.Operator.par(ctx, ls.n_true, ls.lsize, [op], None, ls.ess_tdofs, 1, halo)
+        A.set_interior(ls.n_interior)
         A.local_op = op
         return A
 
