@@ -1,0 +1,135 @@
+// Header-only Palace/MFEM adapters over the C ABI of b2p.h. Compiled only inside a Palace build
+// (needs <mfem.hpp> and Palace's own headers); nothing here is built or tested in this repository,
+// where MFEM is not available — it documents exactly which reference interface each entry point
+// replaces. See INTEGRATION.md.
+//
+//   b2p::palace::Operator            replaces palace::ceed::Operator   (palace/fem/libceed/operator.hpp:32-65)
+//   b2p::palace::ParOperatorAdapter  replaces palace::ParOperator      (palace/linalg/rap.hpp:24-121)
+//   b2p::palace::SolverAdapter       wraps any b2p_solver as palace::Solver<palace::Operator>
+//                                    (palace/linalg/solver.hpp:21-65): Chebyshev, Jacobi, DistRelaxation,
+//                                    GeometricMultigrid, Cg/Gmres/Fgmres.
+#pragma once
+#if defined(MFEM_VERSION) || __has_include(<mfem.hpp>)
+#include <mfem.hpp>
+
+#include <memory>
+#include <vector>
+
+#include "b2p.h"
+
+namespace b2p::palace
+{
+
+inline void Check(int rc, b2p_ctx *ctx)
+{
+  if (rc != B2P_SUCCESS)
+  {
+    MFEM_ABORT("b2p error " << rc << ": " << b2p_last_error(ctx));  // PalaceCeedCall semantics, ceed.hpp:13-33
+  }
+}
+
+// Same five methods as ceed::Operator; sub-operators are b2p_op handles created by the integrator glue.
+class Operator : public mfem::Operator
+{
+protected:
+  b2p_ctx *ctx;
+  std::vector<b2p_op *> ops;  // owned (AddSubOperator takes ownership, operator.cpp:60-87)
+
+public:
+  Operator(b2p_ctx *ctx, int h, int w) : mfem::Operator(h, w), ctx(ctx) {}
+  ~Operator() override
+  {
+    for (auto *op : ops) b2p_op_destroy(op);
+  }
+  void AddSubOperator(b2p_op *sub_op) { ops.push_back(sub_op); }
+  void Finalize() {}
+  void DestroyAssemblyData() const {}
+  const std::vector<b2p_op *> &SubOperators() const { return ops; }
+
+  void Mult(const mfem::Vector &x, mfem::Vector &y) const override
+  {
+    y = 0.0;  // operator.cpp:184
+    AddMult(x, y, 1.0);
+  }
+  void AddMult(const mfem::Vector &x, mfem::Vector &y, const double a = 1.0) const override
+  {
+    const double *xd = x.Read(true);  // zero-copy device pointers, operator.cpp:160-161
+    double *yd = y.ReadWrite(true);
+    for (auto *op : ops) Check(b2p_op_apply_add_ex(op, a, xd, yd, 0, nullptr), ctx);
+  }
+  void MultTranspose(const mfem::Vector &x, mfem::Vector &y) const override { Mult(x, y); }  // SymmetricOperator
+  void AddMultTranspose(const mfem::Vector &x, mfem::Vector &y, const double a = 1.0) const override { AddMult(x, y, a); }
+  void AssembleDiagonal(mfem::Vector &diag) const override
+  {
+    diag = 0.0;
+    double *d = diag.ReadWrite(true);
+    for (auto *op : ops) Check(b2p_op_diag_add(op, d, nullptr), ctx);
+  }
+};
+
+// y = P^T (sum_i c_i A_i) P x with essential-dof elimination done inside the element kernels.
+class ParOperatorAdapter : public mfem::Operator
+{
+  b2p_ctx *ctx;
+  b2p_operator *A = nullptr;
+  mfem::Array<int> dbc_tdof_list;
+
+public:
+  ParOperatorAdapter(b2p_ctx *ctx, int tsize, int lsize, const std::vector<b2p_op *> &ops, const std::vector<double> &coefs,
+                     const mfem::Array<int> &dbc, int diag_policy, b2p_halo *halo)
+    : mfem::Operator(tsize), ctx(ctx), dbc_tdof_list(dbc)
+  {
+    Check(b2p_operator_par(ctx, tsize, lsize, (int)ops.size(), ops.data(), coefs.data(), dbc.HostRead(), dbc.Size(), diag_policy,
+                           halo, &A),
+          ctx);
+  }
+  ~ParOperatorAdapter() override { b2p_operator_destroy(A); }
+  b2p_operator *Handle() const { return A; }
+  const mfem::Array<int> *GetEssentialTrueDofs() const { return dbc_tdof_list.Size() ? &dbc_tdof_list : nullptr; }
+  void Mult(const mfem::Vector &x, mfem::Vector &y) const override { Check(b2p_operator_mult(A, x.Read(true), y.Write(true)), ctx); }
+  void MultTranspose(const mfem::Vector &x, mfem::Vector &y) const override { Mult(x, y); }
+  void AddMult(const mfem::Vector &x, mfem::Vector &y, const double a = 1.0) const override
+  {
+    Check(b2p_operator_add_mult(A, x.Read(true), y.ReadWrite(true), a), ctx);
+  }
+  void AssembleDiagonal(mfem::Vector &d) const override { Check(b2p_operator_assemble_diagonal(A, d.Write(true)), ctx); }
+};
+
+// palace::Solver<Operator> over a b2p_solver handle.
+class SolverAdapter : public mfem::Solver
+{
+protected:
+  b2p_ctx *ctx;
+  b2p_solver *S;
+  bool initial_guess = false;
+
+public:
+  SolverAdapter(b2p_ctx *ctx, b2p_solver *S) : mfem::Solver(), ctx(ctx), S(S) {}
+  ~SolverAdapter() override { b2p_solver_destroy(S); }
+  b2p_solver *Handle() const { return S; }
+  void SetInitialGuess(bool guess)
+  {
+    initial_guess = guess;
+    Check(b2p_solver_set_initial_guess(S, guess), ctx);
+  }
+  void SetOperator(const mfem::Operator &op) override
+  {
+    const auto *par = dynamic_cast<const ParOperatorAdapter *>(&op);
+    MFEM_VERIFY(par, "b2p solvers require a b2p ParOperatorAdapter!");
+    Check(b2p_solver_set_operator(S, par->Handle()), ctx);
+    height = op.Height();
+    width = op.Width();
+  }
+  void Mult(const mfem::Vector &x, mfem::Vector &y) const override { Check(b2p_solver_mult(S, x.Read(true), y.ReadWrite(true)), ctx); }
+  void Mult2(const mfem::Vector &x, mfem::Vector &y, mfem::Vector &r) const
+  {
+    Check(b2p_solver_mult2(S, x.Read(true), y.ReadWrite(true), r.Write(true)), ctx);
+  }
+  void MultTranspose2(const mfem::Vector &x, mfem::Vector &y, mfem::Vector &r) const
+  {
+    Check(b2p_solver_mult_transpose2(S, x.Read(true), y.ReadWrite(true), r.Write(true)), ctx);
+  }
+};
+
+}  // namespace b2p::palace
+#endif
