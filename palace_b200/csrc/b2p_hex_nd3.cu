@@ -25,6 +25,8 @@
 // Reference semantics: ceed::Operator::AddMult over CeedOperatorApplyAdd
 // (/root/reference/palace/fem/libceed/operator.cpp:148-178,192-212); D from
 // /root/reference/palace/fem/qfunctions/33/{hdiv,hcurl,hdivmass}_33_qf.h.
+#include <cstdlib>
+
 #include "b2p_internal.hpp"
 #include "b2p_qf.cuh"
 #include "b2p_contract.cuh"
@@ -129,16 +131,35 @@ __device__ __forceinline__ void cp_async_wait()
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Staged dof value with the restriction's sign; masked / out-of-range entries read as zero.
+// Staged dof value with the restriction's sign (masked / padded slots were staged as zero):
+// the sign bit of the index is XORed into the high word of the value.
 __device__ __forceinline__ double staged(const int32_t *cI, const double *cU, int pos, bool valid)
 {
   const int32_t gi = cI[pos];
   const double v = cU[pos];
-  if (!valid || gi == B2P_SKIP_IDX) return 0.0;
-  return gi >= 0 ? v : -v;
+  int hi = __double2hiint(v) ^ (gi & (int)0x80000000);
+  const double r = __hiloint2double(hi, __double2loint(v));
+  return valid ? r : 0.0;
+}
+// |index| of a signed restriction entry (-1 - gi == ~gi for negative entries)
+__device__ __forceinline__ int32_t abs_idx(int32_t gi) { return gi ^ (gi >> 31); }
+// Predicated RED.F64 of value (with the entry's sign) at y[|gi|]; masked entries are skipped.
+__device__ __forceinline__ void scatter_fast(double *y, int32_t gi, double v)
+{
+  const int hi = __double2hiint(v) ^ (gi & (int)0x80000000);
+  const double sv = __hiloint2double(hi, __double2loint(v));
+  double *addr = y + (uint32_t)abs_idx(gi);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %2, 0x80000000;\n"
+      "@p red.global.add.f64 [%0], %1;\n"
+      "}\n" ::"l"(addr),
+      "d"(sv), "r"(gi)
+      : "memory");
 }
 
-template <int P_, int Q_, int KIND, bool ASM, int NW, int MINB>
+template <int P_, int Q_, int KIND, bool ASM, bool SPLIT, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __grid_constant__ ND2Params<P_, Q_> prm)
 {
   using L = ND3Layout<P_, Q_, KIND, ASM>;
@@ -200,7 +221,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
       if (l < nel * PS)
       {
         const int32_t gi = gI[l];
-        if (gi != B2P_SKIP_IDX) cp_async8(sU + l, split_src(prm.x, prm.sp, gi >= 0 ? gi : -1 - gi));
+        if (gi == B2P_SKIP_IDX)
+          sU[l] = 0.0;  // masked / padding: reads as zero
+        else if (SPLIT)
+          cp_async8(sU + l, split_src(prm.x, prm.sp, abs_idx(gi)));
+        else
+          cp_async8(sU + l, prm.x + (uint32_t)abs_idx(gi));
       }
     }
     cp_async_commit();
@@ -233,69 +259,65 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
     cp_async_wait<0>();
     __syncwarp();
 
-    // ------------------------------------------------------------------ phase Z (gather + z)
-    // x-directed: t = i + p*j (i<p open, j<n), k<n closed
-    for (int w = lane; w < NEW * (p * n); w += 32)
+    // ------------------------------------------------------------------ phase Z (z-contraction)
+    // All loads of a round are issued before any arithmetic or store (shared-memory stores would
+    // otherwise fence the next component's loads): x-, y- and z-directed items of lane `w`.
     {
-      const int e = w / (p * n), t = w % (p * n);
-      double u[n];
-  #pragma unroll
-      for (int k = 0; k < n; k++) u[k] = staged(cI, cU, e * PS + t + p * n * k, e < nel);
-      double *za = sW + e * ES + L::ZXA + q * t, *zb = sW + e * ES + L::ZXB + q * t;
-  #pragma unroll
-      for (int qz = 0; qz < q; qz++)
+      constexpr int IX = NEW * p * n, IZZ = NEW * n * n;
+      constexpr int ROUNDS = ((IX > IZZ ? IX : IZZ) + 31) / 32;
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
       {
-        double a = 0.0, b = 0.0;
-  #pragma unroll
+        const int w = lane + 32 * r;
+        const bool vx = w < IX, vz = w < IZZ;
+        const int wx = vx ? w : 0, wz = vz ? w : 0;
+        const int ex = wx / (p * n), tx = wx % (p * n);
+        const int ez = wz / (n * n), tz = wz % (n * n);
+        double ux[n], uy[n], uz[p];
+#pragma unroll
         for (int k = 0; k < n; k++)
         {
-          a += prm.Bc[qz * n + k] * u[k];
-          if (CURL) b += prm.Gc[qz * n + k] * u[k];
+          ux[k] = staged(cI, cU, ex * PS + tx + p * n * k, ex < nel);
+          uy[k] = staged(cI, cU, ex * PS + D3 + tx + n * p * k, ex < nel);
         }
-        za[qz] = a;
-        if (CURL) zb[qz] = b;
-      }
-    }
-    // y-directed: t = i + n*j (i<n, j<p open), k<n closed
-    for (int w = lane; w < NEW * (n * p); w += 32)
-    {
-      const int e = w / (n * p), t = w % (n * p);
-      double u[n];
-  #pragma unroll
-      for (int k = 0; k < n; k++) u[k] = staged(cI, cU, e * PS + D3 + t + n * p * k, e < nel);
-      double *za = sW + e * ES + L::ZYA + q * t, *zb = sW + e * ES + L::ZYB + q * t;
-  #pragma unroll
-      for (int qz = 0; qz < q; qz++)
-      {
-        double a = 0.0, b = 0.0;
-  #pragma unroll
-        for (int k = 0; k < n; k++)
+#pragma unroll
+        for (int k = 0; k < p; k++) uz[k] = staged(cI, cU, ez * PS + 2 * D3 + tz + n * n * k, ez < nel);
+        if (vx)
         {
-          a += prm.Bc[qz * n + k] * u[k];
-          if (CURL) b += prm.Gc[qz * n + k] * u[k];
+          double *xa = sW + ex * ES + L::ZXA + q * tx, *xb = sW + ex * ES + L::ZXB + q * tx;
+          double *ya = sW + ex * ES + L::ZYA + q * tx, *yb = sW + ex * ES + L::ZYB + q * tx;
+#pragma unroll
+          for (int qz = 0; qz < q; qz++)
+          {
+            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+#pragma unroll
+            for (int k = 0; k < n; k++)
+            {
+              a += prm.Bc[qz * n + k] * ux[k];
+              c += prm.Bc[qz * n + k] * uy[k];
+              if (CURL) b += prm.Gc[qz * n + k] * ux[k];
+              if (CURL) d += prm.Gc[qz * n + k] * uy[k];
+            }
+            xa[qz] = a;
+            ya[qz] = c;
+            if (CURL) xb[qz] = b;
+            if (CURL) yb[qz] = d;
+          }
         }
-        za[qz] = a;
-        if (CURL) zb[qz] = b;
+        if (vz)
+        {
+          double *za = sW + ez * ES + L::ZZA + q * tz;
+#pragma unroll
+          for (int qz = 0; qz < q; qz++)
+          {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < p; k++) a += prm.Bo[qz * p + k] * uz[k];
+            za[qz] = a;
+          }
+        }
       }
     }
-    // z-directed: t = i + n*j (i,j<n), k<p open
-    for (int w = lane; w < NEW * (n * n); w += 32)
-    {
-      const int e = w / (n * n), t = w % (n * n);
-      double u[p];
-  #pragma unroll
-      for (int k = 0; k < p; k++) u[k] = staged(cI, cU, e * PS + 2 * D3 + t + n * n * k, e < nel);
-      double *za = sW + e * ES + L::ZZA + q * t;
-  #pragma unroll
-      for (int qz = 0; qz < q; qz++)
-      {
-        double a = 0.0;
-  #pragma unroll
-        for (int k = 0; k < p; k++) a += prm.Bo[qz * p + k] * u[k];
-        za[qz] = a;
-      }
-    }
-
     __syncwarp();
     // the staged x values are consumed: gather the next batch's while this one computes
     if (bn < nb)
@@ -305,88 +327,88 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
       gather_x(bn, nslot);
     }
 
-    // ------------------------------------------------------------------ phase Y
+    // ------------------------------------------------------------------ phase Y (y-contraction)
     // items t' = qz + q*i ; reads Z[qz + q*(i + ni*j)] over j ; writes V[qy + q*t'] (thread-contiguous)
-    // x-directed (ni = p, j<n closed): V1 = Bc_y a, V3 = Gc_y a, V2 = Bc_y b
-    for (int w = lane; w < NEW * (p * q); w += 32)
     {
-      const int e = w / (p * q), t = w % (p * q), qz = t % q, i = t / q;
-      const double *za = sW + e * ES + L::ZXA + qz + q * i, *zb = sW + e * ES + L::ZXB + qz + q * i;
-      double a[n], b[n];
-  #pragma unroll
-      for (int j = 0; j < n; j++)
+      constexpr int IX = NEW * p * q, IN = NEW * n * q;  // x-directed items; y- and z-directed items
+      constexpr int ROUNDS = (IN + 31) / 32;
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
       {
-        a[j] = za[q * p * j];
-        if (CURL) b[j] = zb[q * p * j];
-      }
-      double *v1 = sW + e * ES + L::YX1 + q * t, *v2 = sW + e * ES + L::YX2 + q * t, *v3 = sW + e * ES + L::YX3 + q * t;
-  #pragma unroll
-      for (int qy = 0; qy < q; qy++)
-      {
-        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  #pragma unroll
-        for (int j = 0; j < n; j++)
+        const int w = lane + 32 * r;
+        const bool vx = w < IX, vn = w < IN;
+        const int wx = vx ? w : 0, wn = vn ? w : 0;
+        const int ex = wx / (p * q), tx = wx % (p * q), qzx = tx % q, ix = tx / q;
+        const int en = wn / (n * q), tn = wn % (n * q), qzn = tn % q, in_ = tn / q;
+        double xa[n], xb[n], ya[p], yb[p], za[n];
         {
-          if (MASS) s1 += prm.Bc[qy * n + j] * a[j];
-          if (CURL) s2 += prm.Bc[qy * n + j] * b[j];
-          if (CURL) s3 += prm.Gc[qy * n + j] * a[j];
+          const double *pa = sW + ex * ES + L::ZXA + qzx + q * ix, *pb = sW + ex * ES + L::ZXB + qzx + q * ix;
+#pragma unroll
+          for (int j = 0; j < n; j++)
+          {
+            xa[j] = pa[q * p * j];
+            if (CURL) xb[j] = pb[q * p * j];
+          }
+          const double *qa = sW + en * ES + L::ZYA + qzn + q * in_, *qb = sW + en * ES + L::ZYB + qzn + q * in_;
+#pragma unroll
+          for (int j = 0; j < p; j++)
+          {
+            ya[j] = qa[q * n * j];
+            if (CURL) yb[j] = qb[q * n * j];
+          }
+          const double *ra = sW + en * ES + L::ZZA + qzn + q * in_;
+#pragma unroll
+          for (int j = 0; j < n; j++) za[j] = ra[q * n * j];
         }
-        if (MASS) v1[qy] = s1;
-        if (CURL) v2[qy] = s2;
-        if (CURL) v3[qy] = s3;
+        if (vx)
+        {
+          // x-directed (j<n closed): V1 = Bc_y a, V3 = Gc_y a, V2 = Bc_y b
+          double *v1 = sW + ex * ES + L::YX1 + q * tx, *v2 = sW + ex * ES + L::YX2 + q * tx, *v3 = sW + ex * ES + L::YX3 + q * tx;
+#pragma unroll
+          for (int qy = 0; qy < q; qy++)
+          {
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < n; j++)
+            {
+              if (MASS) s1 += prm.Bc[qy * n + j] * xa[j];
+              if (CURL) s2 += prm.Bc[qy * n + j] * xb[j];
+              if (CURL) s3 += prm.Gc[qy * n + j] * xa[j];
+            }
+            if (MASS) v1[qy] = s1;
+            if (CURL) v2[qy] = s2;
+            if (CURL) v3[qy] = s3;
+          }
+        }
+        if (vn)
+        {
+          // y-directed (j<p open): V1 = Bo_y a, V2 = Bo_y b ; z-directed (j<n closed): V1 = Bc_y a, V3 = Gc_y a
+          double *v1 = sW + en * ES + L::YY1 + q * tn, *v2 = sW + en * ES + L::YY2 + q * tn;
+          double *z1 = sW + en * ES + L::YZ1 + q * tn, *z3 = sW + en * ES + L::YZ3 + q * tn;
+#pragma unroll
+          for (int qy = 0; qy < q; qy++)
+          {
+            double s1 = 0.0, s2 = 0.0, t1 = 0.0, t3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < p; j++)
+            {
+              s1 += prm.Bo[qy * p + j] * ya[j];
+              if (CURL) s2 += prm.Bo[qy * p + j] * yb[j];
+            }
+#pragma unroll
+            for (int j = 0; j < n; j++)
+            {
+              t1 += prm.Bc[qy * n + j] * za[j];
+              if (CURL) t3 += prm.Gc[qy * n + j] * za[j];
+            }
+            v1[qy] = s1;
+            if (CURL) v2[qy] = s2;
+            z1[qy] = t1;
+            if (CURL) z3[qy] = t3;
+          }
+        }
       }
     }
-    // y-directed (ni = n, j<p open): V1 = Bo_y a, V2 = Bo_y b
-    for (int w = lane; w < NEW * (n * q); w += 32)
-    {
-      const int e = w / (n * q), t = w % (n * q), qz = t % q, i = t / q;
-      const double *za = sW + e * ES + L::ZYA + qz + q * i, *zb = sW + e * ES + L::ZYB + qz + q * i;
-      double a[p], b[p];
-  #pragma unroll
-      for (int j = 0; j < p; j++)
-      {
-        a[j] = za[q * n * j];
-        if (CURL) b[j] = zb[q * n * j];
-      }
-      double *v1 = sW + e * ES + L::YY1 + q * t, *v2 = sW + e * ES + L::YY2 + q * t;
-  #pragma unroll
-      for (int qy = 0; qy < q; qy++)
-      {
-        double s1 = 0.0, s2 = 0.0;
-  #pragma unroll
-        for (int j = 0; j < p; j++)
-        {
-          s1 += prm.Bo[qy * p + j] * a[j];
-          if (CURL) s2 += prm.Bo[qy * p + j] * b[j];
-        }
-        v1[qy] = s1;
-        if (CURL) v2[qy] = s2;
-      }
-    }
-    // z-directed (ni = n, j<n closed): V1 = Bc_y a, V3 = Gc_y a
-    for (int w = lane; w < NEW * (n * q); w += 32)
-    {
-      const int e = w / (n * q), t = w % (n * q), qz = t % q, i = t / q;
-      const double *za = sW + e * ES + L::ZZA + qz + q * i;
-      double a[n];
-  #pragma unroll
-      for (int j = 0; j < n; j++) a[j] = za[q * n * j];
-      double *v1 = sW + e * ES + L::YZ1 + q * t, *v3 = sW + e * ES + L::YZ3 + q * t;
-  #pragma unroll
-      for (int qy = 0; qy < q; qy++)
-      {
-        double s1 = 0.0, s3 = 0.0;
-  #pragma unroll
-        for (int j = 0; j < n; j++)
-        {
-          s1 += prm.Bc[qy * n + j] * a[j];
-          if (CURL) s3 += prm.Gc[qy * n + j] * a[j];
-        }
-        v1[qy] = s1;
-        if (CURL) v3[qy] = s3;
-      }
-    }
-
     __syncwarp();
     mbar_wait(bar_g, par_g);  // q-data of this batch has landed
     par_g ^= 1;
@@ -462,18 +484,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
             if (MASS)
             {
 #pragma unroll
-              for (int r = 0; r < 3; r++) v[r] = a[(r)*Q] * uu[qx][0] + a[(r + 3) * Q] * uu[qx][1] + a[(r + 6) * Q] * uu[qx][2];
+              for (int r = 0; r < 3; r++) v[r] = alpha * (a[(r)*Q] * uu[qx][0] + a[(r + 3) * Q] * uu[qx][1] + a[(r + 6) * Q] * uu[qx][2]);
               a += 9 * Q;
             }
             if (CURL)
             {
 #pragma unroll
-              for (int r = 0; r < 3; r++) cw[r] = a[(r)*Q] * cc[qx][0] + a[(r + 3) * Q] * cc[qx][1] + a[(r + 6) * Q] * cc[qx][2];
+              for (int r = 0; r < 3; r++) cw[r] = alpha * (a[(r)*Q] * cc[qx][0] + a[(r + 3) * Q] * cc[qx][1] + a[(r + 6) * Q] * cc[qx][2]);
             }
           }
           else
           {
-            const double wdetJ = gq[0];
+            const double wdetJ = alpha * gq[0];  // alpha folded into the quadrature weight
             double A[9];
 #pragma unroll
             for (int i = 0; i < 9; i++) A[i] = gq[(1 + i) * Q];
@@ -536,164 +558,157 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
       issue_geom(bn);  // refill the single q-data buffer for the next batch
     }
 
-    // ------------------------------------------------------------------ phase Yt
-    // x-directed: Za'[j] = sum_qy Bc[qy][j] W1 + Gc[qy][j] W3 ; Zb'[j] = sum_qy Bc[qy][j] W2
-    for (int w = lane; w < NEW * (p * q); w += 32)
+    // ------------------------------------------------------------------ phase Yt (transposed y-contraction)
     {
-      const int e = w / (p * q), t = w % (p * q), qz = t % q, i = t / q;
-      const double *v1 = sW + e * ES + L::YX1 + q * t, *v2 = sW + e * ES + L::YX2 + q * t, *v3 = sW + e * ES + L::YX3 + q * t;
-      double w1[q], w2[q], w3[q];
-  #pragma unroll
-      for (int qy = 0; qy < q; qy++)
+      constexpr int IX = NEW * p * q, IN = NEW * n * q;
+      constexpr int ROUNDS = (IN + 31) / 32;
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
       {
-        if (MASS) w1[qy] = v1[qy];
-        if (CURL) w2[qy] = v2[qy];
-        if (CURL) w3[qy] = v3[qy];
-      }
-      double *za = sW + e * ES + L::ZXA + qz + q * i, *zb = sW + e * ES + L::ZXB + qz + q * i;
-  #pragma unroll
-      for (int j = 0; j < n; j++)
-      {
-        double a = 0.0, b = 0.0;
-  #pragma unroll
-        for (int qy = 0; qy < q; qy++)
+        const int w = lane + 32 * r;
+        const bool vx = w < IX, vn = w < IN;
+        const int wx = vx ? w : 0, wn = vn ? w : 0;
+        const int ex = wx / (p * q), tx = wx % (p * q), qzx = tx % q, ix = tx / q;
+        const int en = wn / (n * q), tn = wn % (n * q), qzn = tn % q, in_ = tn / q;
+        double x1[q], x2[q], x3[q], y1[q], y2[q], z1[q], z3[q];
         {
-          if (MASS) a += prm.Bc[qy * n + j] * w1[qy];
-          if (CURL) a += prm.Gc[qy * n + j] * w3[qy];
-          if (CURL) b += prm.Bc[qy * n + j] * w2[qy];
+          const double *v1 = sW + ex * ES + L::YX1 + q * tx, *v2 = sW + ex * ES + L::YX2 + q * tx, *v3 = sW + ex * ES + L::YX3 + q * tx;
+          const double *u1 = sW + en * ES + L::YY1 + q * tn, *u2 = sW + en * ES + L::YY2 + q * tn;
+          const double *t1 = sW + en * ES + L::YZ1 + q * tn, *t3 = sW + en * ES + L::YZ3 + q * tn;
+#pragma unroll
+          for (int qy = 0; qy < q; qy++)
+          {
+            if (MASS) x1[qy] = v1[qy];
+            if (CURL) x2[qy] = v2[qy];
+            if (CURL) x3[qy] = v3[qy];
+            y1[qy] = u1[qy];
+            if (CURL) y2[qy] = u2[qy];
+            z1[qy] = t1[qy];
+            if (CURL) z3[qy] = t3[qy];
+          }
         }
-        za[q * p * j] = a;
-        if (CURL) zb[q * p * j] = b;
+        if (vx)
+        {
+          // x-directed: Za'[j] = sum_qy Bc[qy][j] W1 + Gc[qy][j] W3 ; Zb'[j] = sum_qy Bc[qy][j] W2
+          double *za = sW + ex * ES + L::ZXA + qzx + q * ix, *zb = sW + ex * ES + L::ZXB + qzx + q * ix;
+#pragma unroll
+          for (int j = 0; j < n; j++)
+          {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int qy = 0; qy < q; qy++)
+            {
+              if (MASS) a += prm.Bc[qy * n + j] * x1[qy];
+              if (CURL) a += prm.Gc[qy * n + j] * x3[qy];
+              if (CURL) b += prm.Bc[qy * n + j] * x2[qy];
+            }
+            za[q * p * j] = a;
+            if (CURL) zb[q * p * j] = b;
+          }
+        }
+        if (vn)
+        {
+          // y-directed: Za'[j<p] = sum_qy Bo[qy][j] W1 ; Zb' = sum_qy Bo[qy][j] W2
+          double *ya = sW + en * ES + L::ZYA + qzn + q * in_, *yb = sW + en * ES + L::ZYB + qzn + q * in_;
+#pragma unroll
+          for (int j = 0; j < p; j++)
+          {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int qy = 0; qy < q; qy++)
+            {
+              a += prm.Bo[qy * p + j] * y1[qy];
+              if (CURL) b += prm.Bo[qy * p + j] * y2[qy];
+            }
+            ya[q * n * j] = a;
+            if (CURL) yb[q * n * j] = b;
+          }
+          // z-directed: Za'[j] = sum_qy Bc[qy][j] W1 + Gc[qy][j] W3
+          double *za = sW + en * ES + L::ZZA + qzn + q * in_;
+#pragma unroll
+          for (int j = 0; j < n; j++)
+          {
+            double a = 0.0;
+#pragma unroll
+            for (int qy = 0; qy < q; qy++)
+            {
+              a += prm.Bc[qy * n + j] * z1[qy];
+              if (CURL) a += prm.Gc[qy * n + j] * z3[qy];
+            }
+            za[q * n * j] = a;
+          }
+        }
       }
     }
-    // y-directed: Za'[j<p] = sum_qy Bo[qy][j] W1 ; Zb' = sum_qy Bo[qy][j] W2
-    for (int w = lane; w < NEW * (n * q); w += 32)
-    {
-      const int e = w / (n * q), t = w % (n * q), qz = t % q, i = t / q;
-      const double *v1 = sW + e * ES + L::YY1 + q * t, *v2 = sW + e * ES + L::YY2 + q * t;
-      double w1[q], w2[q];
-  #pragma unroll
-      for (int qy = 0; qy < q; qy++)
-      {
-        w1[qy] = v1[qy];
-        if (CURL) w2[qy] = v2[qy];
-      }
-      double *za = sW + e * ES + L::ZYA + qz + q * i, *zb = sW + e * ES + L::ZYB + qz + q * i;
-  #pragma unroll
-      for (int j = 0; j < p; j++)
-      {
-        double a = 0.0, b = 0.0;
-  #pragma unroll
-        for (int qy = 0; qy < q; qy++)
-        {
-          a += prm.Bo[qy * p + j] * w1[qy];
-          if (CURL) b += prm.Bo[qy * p + j] * w2[qy];
-        }
-        za[q * n * j] = a;
-        if (CURL) zb[q * n * j] = b;
-      }
-    }
-    // z-directed: Za'[j] = sum_qy Bc[qy][j] W1 + Gc[qy][j] W3
-    for (int w = lane; w < NEW * (n * q); w += 32)
-    {
-      const int e = w / (n * q), t = w % (n * q), qz = t % q, i = t / q;
-      const double *v1 = sW + e * ES + L::YZ1 + q * t, *v3 = sW + e * ES + L::YZ3 + q * t;
-      double w1[q], w3[q];
-  #pragma unroll
-      for (int qy = 0; qy < q; qy++)
-      {
-        w1[qy] = v1[qy];
-        if (CURL) w3[qy] = v3[qy];
-      }
-      double *za = sW + e * ES + L::ZZA + qz + q * i;
-  #pragma unroll
-      for (int j = 0; j < n; j++)
-      {
-        double a = 0.0;
-  #pragma unroll
-        for (int qy = 0; qy < q; qy++)
-        {
-          a += prm.Bc[qy * n + j] * w1[qy];
-          if (CURL) a += prm.Gc[qy * n + j] * w3[qy];
-        }
-        za[q * n * j] = a;
-      }
-    }
-
     __syncwarp();
 
-    // ------------------------------------------------------------------ phase Zt (+ scatter)
-    for (int w = lane; w < NEW * (p * n); w += 32)
+    // ------------------------------------------------------------------ phase Zt (transposed z-contraction + scatter)
     {
-      const int e = w / (p * n), t = w % (p * n);
-      if (e >= nel) continue;
-      const double *za = sW + e * ES + L::ZXA + q * t, *zb = sW + e * ES + L::ZXB + q * t;
-      double a[q], b[q];
-  #pragma unroll
-      for (int qz = 0; qz < q; qz++)
+      constexpr int IX = NEW * p * n, IZZ = NEW * n * n;
+      constexpr int ROUNDS = ((IX > IZZ ? IX : IZZ) + 31) / 32;
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
       {
-        a[qz] = za[qz];
-        if (CURL) b[qz] = zb[qz];
-      }
-      const int32_t *li = cI + e * PS + t;
-  #pragma unroll
-      for (int k = 0; k < n; k++)
-      {
-        double o = 0.0;
-  #pragma unroll
-        for (int qz = 0; qz < q; qz++)
+        const int w = lane + 32 * r;
+        const int wx = w < IX ? w : 0, wz = w < IZZ ? w : 0;
+        const int ex = wx / (p * n), tx = wx % (p * n);
+        const int ez = wz / (n * n), tz = wz % (n * n);
+        const bool vx = w < IX && ex < nel, vz = w < IZZ && ez < nel;
+        double xa[q], xb[q], ya[q], yb[q], za[q];
+        int32_t gx[n], gy[n], gz[p];
         {
-          o += prm.Bc[qz * n + k] * a[qz];
-          if (CURL) o += prm.Gc[qz * n + k] * b[qz];
+          const double *pxa = sW + ex * ES + L::ZXA + q * tx, *pxb = sW + ex * ES + L::ZXB + q * tx;
+          const double *pya = sW + ex * ES + L::ZYA + q * tx, *pyb = sW + ex * ES + L::ZYB + q * tx;
+          const double *pza = sW + ez * ES + L::ZZA + q * tz;
+#pragma unroll
+          for (int qz = 0; qz < q; qz++)
+          {
+            xa[qz] = pxa[qz];
+            ya[qz] = pya[qz];
+            za[qz] = pza[qz];
+            if (CURL) xb[qz] = pxb[qz];
+            if (CURL) yb[qz] = pyb[qz];
+          }
+#pragma unroll
+          for (int k = 0; k < n; k++)
+          {
+            gx[k] = cI[ex * PS + tx + p * n * k];
+            gy[k] = cI[ex * PS + D3 + tx + n * p * k];
+          }
+#pragma unroll
+          for (int k = 0; k < p; k++) gz[k] = cI[ez * PS + 2 * D3 + tz + n * n * k];
         }
-        scatter2(prm.y, prm.sp, li[p * n * k], alpha * o);
-      }
-    }
-    for (int w = lane; w < NEW * (n * p); w += 32)
-    {
-      const int e = w / (n * p), t = w % (n * p);
-      if (e >= nel) continue;
-      const double *za = sW + e * ES + L::ZYA + q * t, *zb = sW + e * ES + L::ZYB + q * t;
-      double a[q], b[q];
-  #pragma unroll
-      for (int qz = 0; qz < q; qz++)
-      {
-        a[qz] = za[qz];
-        if (CURL) b[qz] = zb[qz];
-      }
-      const int32_t *li = cI + e * PS + D3 + t;
-  #pragma unroll
-      for (int k = 0; k < n; k++)
-      {
-        double o = 0.0;
-  #pragma unroll
-        for (int qz = 0; qz < q; qz++)
+        if (vx)
         {
-          o += prm.Bc[qz * n + k] * a[qz];
-          if (CURL) o += prm.Gc[qz * n + k] * b[qz];
+#pragma unroll
+          for (int k = 0; k < n; k++)
+          {
+            double o = 0.0, o2 = 0.0;
+#pragma unroll
+            for (int qz = 0; qz < q; qz++)
+            {
+              o += prm.Bc[qz * n + k] * xa[qz];
+              o2 += prm.Bc[qz * n + k] * ya[qz];
+              if (CURL) o += prm.Gc[qz * n + k] * xb[qz];
+              if (CURL) o2 += prm.Gc[qz * n + k] * yb[qz];
+            }
+            if (SPLIT) scatter2(prm.y, prm.sp, gx[k], o); else scatter_fast(prm.y, gx[k], o);
+            if (SPLIT) scatter2(prm.y, prm.sp, gy[k], o2); else scatter_fast(prm.y, gy[k], o2);
+          }
         }
-        scatter2(prm.y, prm.sp, li[n * p * k], alpha * o);
+        if (vz)
+        {
+#pragma unroll
+          for (int k = 0; k < p; k++)
+          {
+            double o = 0.0;
+#pragma unroll
+            for (int qz = 0; qz < q; qz++) o += prm.Bo[qz * p + k] * za[qz];
+            if (SPLIT) scatter2(prm.y, prm.sp, gz[k], o); else scatter_fast(prm.y, gz[k], o);
+          }
+        }
       }
     }
-    for (int w = lane; w < NEW * (n * n); w += 32)
-    {
-      const int e = w / (n * n), t = w % (n * n);
-      if (e >= nel) continue;
-      const double *za = sW + e * ES + L::ZZA + q * t;
-      double a[q];
-  #pragma unroll
-      for (int qz = 0; qz < q; qz++) a[qz] = za[qz];
-      const int32_t *li = cI + e * PS + 2 * D3 + t;
-  #pragma unroll
-      for (int k = 0; k < p; k++)
-      {
-        double o = 0.0;
-  #pragma unroll
-        for (int qz = 0; qz < q; qz++) o += prm.Bo[qz * p + k] * a[qz];
-        scatter2(prm.y, prm.sp, li[n * n * k], alpha * o);
-      }
-    }
-
     __syncwarp();
     if (b + 3 * GW < nb && lane == 0)
     {
@@ -710,16 +725,19 @@ int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   using L = ND3Layout<P_, Q_, KIND, ASM>;
   // warps per CTA / CTAs per SM from the per-warp shared-memory footprint
   constexpr int SMEM_SM = 222 * 1024;
-  constexpr int WPS = (SMEM_SM / L::WS) < 1 ? 1 : (SMEM_SM / L::WS > 10 ? 10 : SMEM_SM / L::WS);  // warps per SM (<= 10: 204 regs)
+  constexpr int WPS0 = (SMEM_SM / L::WS) < 1 ? 1 : SMEM_SM / L::WS;  // warps per SM that fit in shared memory
+  constexpr int WPS = WPS0 > 10 ? 10 : WPS0;  // register file: 10 warps at ~204 registers
   constexpr int MINB = (WPS >= 8) ? 2 : 1;
   constexpr int NW = (WPS / MINB) < 1 ? 1 : WPS / MINB;
   const size_t shmem = (size_t)NW * L::WS;
-  auto kern = nd_hex_apply3_kernel<P_, Q_, KIND, ASM, NW, MINB>;
-  static bool configured = false;
-  if (!configured)
+  // SPLIT: the L-vector comes in two pieces (owned part in x / y, ghosts in separate buffers)
+  const bool split = rg.xg || rg.yg || (rg.n_owned >= 0 && rg.n_owned < op->lsize);
+  auto kern = split ? nd_hex_apply3_kernel<P_, Q_, KIND, ASM, true, NW, MINB> : nd_hex_apply3_kernel<P_, Q_, KIND, ASM, false, NW, MINB>;
+  static bool configured[2] = {false, false};
+  if (!configured[split])
   {
     B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    configured = true;
+    configured[split] = true;
   }
   ND2Params<P_, Q_> prm;
   const int e_off = rg.e_off, e_cnt = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
