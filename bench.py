@@ -225,6 +225,12 @@ def main():
         nd, elems = ls.space, ls.elems
         halo = capi.Halo(ctx, ls.n_true, ls.n_ghost, ls.nbr, ls.send_counts, ls.send_idx, ls.recv_counts)
         n_true, lsize = ls.n_true, ls.lsize
+        if os.environ.get("B2P_HALO_P2P", "1") == "1":  # NVLink peer-memory exchange instead of NCCL send/recv
+            def gather(blob):
+                out = [None] * world
+                dist.all_gather_object(out, blob)
+                return out
+            halo.enable_p2p(gather)
     else:
         nd, elems, halo = gnd, np.arange(prob["mesh"].ne), None
         n_true = lsize = gnd.ndofs
@@ -237,7 +243,8 @@ def main():
                         assemble=bool(args.assemble_qdata))
     A = capi.Operator.par(ctx, n_true, lsize, [op], None, None, diag_policy=1, halo=halo)
     if world > 1:
-        A.set_interior(ls.n_interior)
+        A.set_interior(ls.n_interior)  # interior elements first: the kernel waits for ghosts only when it reaches the interface
+
     prob["local_ne"] = int(elems.size)
     prob["local_dofs"] = int(lsize)
     N = n_true

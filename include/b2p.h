@@ -178,6 +178,11 @@ int b2p_halo_create(b2p_ctx *ctx, int64_t n_true, int64_t n_ghost, int n_nbr, co
                     const int64_t *send_counts, const int32_t *send_idx, const int64_t *recv_counts, b2p_halo **out);
 int b2p_halo_forward(b2p_halo *h, double *lvec); /* owners -> ghosts (P) */
 int b2p_halo_reverse(b2p_halo *h, double *lvec); /* ghosts added into owners (P^T) */
+/* Optional peer-memory (NVLink) exchange for ParOperator::Mult instead of NCCL send/recv: every rank exports a
+ * blob (CUDA IPC handle of its mailbox + exchange offsets; call with blob == NULL to get the size), the caller
+ * all-gathers the blobs (MPI_Allgather in Palace, torch.distributed in the harness) and every rank imports them. */
+int b2p_halo_p2p_export(b2p_halo *h, void *blob, size_t *bytes);
+int b2p_halo_p2p_import(b2p_halo *h, const void *blobs, size_t stride, int nranks);
 void b2p_halo_destroy(b2p_halo *h);
 
 /* ---- device-resident linear algebra (replaces linalg/vector.cpp kernels + MPI_Allreduce) ---- */

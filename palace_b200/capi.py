@@ -285,6 +285,18 @@ class Halo:
                                    C.byref(h)), ctx.h)
         self.ctx, self.h = ctx, h
 
+    def enable_p2p(self, all_gather):
+        """Switch ParOperator::Mult's exchange to peer-memory stores. ``all_gather(bytes) -> list[bytes]``
+        gathers one blob per rank (e.g. torch.distributed.all_gather_object)."""
+        n = C.c_size_t()
+        _chk(lib().b2p_halo_p2p_export(self.h, None, C.byref(n)), self.ctx.h)
+        buf = (C.c_char * n.value)()
+        _chk(lib().b2p_halo_p2p_export(self.h, buf, C.byref(n)), self.ctx.h)
+        blobs = all_gather(bytes(buf))
+        allb = b"".join(blobs)
+        arr = (C.c_char * len(allb)).from_buffer_copy(allb)
+        _chk(lib().b2p_halo_p2p_import(self.h, arr, C.c_size_t(n.value), len(blobs)), self.ctx.h)
+
     def forward(self, lvec):
         _chk(lib().b2p_halo_forward(self.h, _vp(lvec)), self.ctx.h)
 

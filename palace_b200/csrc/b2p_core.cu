@@ -33,6 +33,7 @@ int upload(b2p_ctx *ctx, const T *host, size_t n, T **dptr)
 template int upload<double>(b2p_ctx *, const double *, size_t, double **);
 template int upload<int32_t>(b2p_ctx *, const int32_t *, size_t, int32_t **);
 template int upload<int8_t>(b2p_ctx *, const int8_t *, size_t, int8_t **);
+template int upload<int64_t>(b2p_ctx *, const int64_t *, size_t, int64_t **);
 
 namespace
 {

@@ -29,6 +29,88 @@ __global__ void unpack_add_kernel(double *__restrict__ y, const int32_t *__restr
 }
 }  // namespace
 
+// ---- peer-memory exchange (NVLink stores + flags) ------------------------------------------------
+// Mailbox of a rank (one cudaMalloc, IPC-shared with its neighbours):
+//   [ fwd_recv : n_ghost doubles ][ rev_recv : n_send doubles ][ flag_fwd : n_nbr u64 ][ flag_rev : n_nbr u64 ]
+// A sender packs straight into the peer's mailbox and then raises the peer's flag to its own running
+// epoch; the receiver spins on its local flag. Epochs live in device memory, so the sequence can be
+// replayed from a CUDA graph. Used only by the paired forward/reverse exchange of ParOperator::Mult.
+namespace
+{
+// grid = (GX, n_nbr): blocks of column k copy segment k into the peer's mailbox; the last block of the
+// column to finish (device counter) publishes the data: fence, then release-store of the new epoch into
+// the peer's flag.
+__global__ void p2p_push_kernel(const double *__restrict__ src, const int32_t *__restrict__ idx, const long long *seg_off,
+                                double *const *dst_ptr, unsigned long long *const *flag_ptr, unsigned long long *epoch,
+                                unsigned int *done, unsigned long long *bump_expect, const int *recv_has = nullptr)
+{
+  const int k = blockIdx.y;
+  const long long b = seg_off[k], e = seg_off[k + 1];
+  double *dst = dst_ptr[k];
+  for (long long i = b + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (long long)gridDim.x * blockDim.x)
+    dst[i - b] = idx ? src[idx[i]] : src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const unsigned int prev = atomicAdd(done + k, 1u);
+    if (prev == gridDim.x - 1)
+    {
+      done[k] = 0;
+      // the consumer kernel (next in stream order) waits for this epoch itself; only neighbours that
+      // actually send me ghosts (recv_has[k]) ever raise my flag
+      if (bump_expect && recv_has[k]) ++bump_expect[k];
+      const unsigned long long ep = ++epoch[k];
+      if (e > b)
+      {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_ptr[k]), "l"(ep) : "memory");
+      }
+    }
+  }
+}
+__global__ void p2p_wait_kernel(int nseg, const long long *seg_off, const unsigned long long *flags, unsigned long long *expect)
+{
+  const int k = threadIdx.x;
+  if (k >= nseg) return;
+  const unsigned long long ep = ++expect[k];
+  if (seg_off[k + 1] > seg_off[k])
+  {
+    unsigned long long v;
+    do
+    {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + k) : "memory");
+    } while (v < ep);
+  }
+}
+}  // namespace
+
+int halo_forward_p2p(Halo *h, const double *x, bool in_kernel_wait, cudaStream_t s)
+{
+  const int nn = (int)h->nbr.size();
+  const long long ns = h->send_off.back();
+  dim3 grid((unsigned)std::min<long long>((ns / nn + 255) / 256 + 1, 32), nn);
+  p2p_push_kernel<<<grid, 256, 0, s>>>(x, h->d_send_idx, h->d_send_off, h->d_peer_fwd, h->d_peer_flag_fwd, h->d_epoch, h->d_done,
+                                       in_kernel_wait ? h->d_epoch + 2 * 32 : nullptr, h->d_recv_has);
+  if (!in_kernel_wait) p2p_wait_kernel<<<1, 32, 0, s>>>(nn, h->d_recv_off, h->d_flags, h->d_epoch + 2 * 32);
+  B2P_CUDA(h->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+
+int halo_reverse_p2p(Halo *h, double *y, cudaStream_t s)
+{
+  const int nn = (int)h->nbr.size();
+  const long long nr = h->recv_off.back(), ns = h->send_off.back();
+  dim3 grid((unsigned)std::min<long long>((nr / nn + 255) / 256 + 1, 32), nn);
+  p2p_push_kernel<<<grid, 256, 0, s>>>(h->d_yg ? h->d_yg : h->d_mail, nullptr, h->d_recv_off, h->d_peer_rev, h->d_peer_flag_rev, h->d_epoch + 32,
+                                       h->d_done + 32, nullptr);
+  p2p_wait_kernel<<<1, 32, 0, s>>>(nn, h->d_send_off, h->d_flags + 32, h->d_epoch + 3 * 32);
+  if (ns > 0)
+    unpack_add_kernel<<<(int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, s>>>(y, h->d_send_idx, ns, h->d_mail_rev);
+  B2P_CUDA(h->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+
 int halo_forward(Halo *h, double *lx)
 {
   if (!h || h->nbr.empty()) return B2P_SUCCESS;
@@ -161,6 +243,105 @@ int b2p_halo_create(b2p_ctx *ctx, int64_t n_true, int64_t n_ghost, int n_nbr, co
   return B2P_SUCCESS;
 }
 
+// Blob exchanged between ranks at set-up (caller all-gathers it): IPC handle + exchange offsets.
+struct P2PBlob
+{
+  cudaIpcMemHandle_t handle;
+  int rank, n_nbr;
+  long long n_ghost, n_send;
+  int nbr[26];
+  long long send_off[27], recv_off[27];
+};
+
+int b2p_halo_p2p_export(b2p_halo *hh, void *blob, size_t *bytes)
+{
+  if (!hh || !bytes) return B2P_ERR_ARG;
+  *bytes = sizeof(P2PBlob);
+  if (!blob) return B2P_SUCCESS;
+  Halo &h = hh->h;
+  b2p_ctx *ctx = h.ctx;
+  B2P_CHECK(ctx, h.nbr.size() <= 26, B2P_ERR_UNSUPPORTED, "b2p_halo_p2p_export: more than 26 neighbours");
+  const long long ns = h.send_off.back();
+  if (!h.d_mail)
+  {
+    const size_t words = (size_t)h.n_ghost + (size_t)ns + 64;
+    B2P_CUDA(ctx, cudaMalloc((void **)&h.d_mail, words * 8));
+    B2P_CUDA(ctx, cudaMemset(h.d_mail, 0, words * 8));
+    h.d_mail_rev = h.d_mail + h.n_ghost;
+    h.d_flags = (unsigned long long *)(h.d_mail + h.n_ghost + ns);
+  }
+  P2PBlob b;
+  memset(&b, 0, sizeof(b));
+  B2P_CUDA(ctx, cudaIpcGetMemHandle(&b.handle, h.d_mail));
+  b.rank = ctx->rank;
+  b.n_nbr = (int)h.nbr.size();
+  b.n_ghost = h.n_ghost;
+  b.n_send = ns;
+  for (size_t k = 0; k < h.nbr.size(); k++) b.nbr[k] = h.nbr[k];
+  for (size_t k = 0; k <= h.nbr.size(); k++)
+  {
+    b.send_off[k] = h.send_off[k];
+    b.recv_off[k] = h.recv_off[k];
+  }
+  memcpy(blob, &b, sizeof(b));
+  return B2P_SUCCESS;
+}
+
+int b2p_halo_p2p_import(b2p_halo *hh, const void *blobs, size_t stride, int nranks)
+{
+  if (!hh || !blobs) return B2P_ERR_ARG;
+  Halo &h = hh->h;
+  b2p_ctx *ctx = h.ctx;
+  B2P_CHECK(ctx, h.d_mail && stride >= sizeof(P2PBlob) && nranks == ctx->nranks, B2P_ERR_ARG, "b2p_halo_p2p_import: export first");
+  const int nn = (int)h.nbr.size();
+  std::vector<double *> pf(nn), pr(nn);
+  std::vector<unsigned long long *> ff(nn), fr(nn);
+  for (int k = 0; k < nn; k++)
+  {
+    P2PBlob pb;
+    memcpy(&pb, (const char *)blobs + (size_t)h.nbr[k] * stride, sizeof(pb));
+    B2P_CHECK(ctx, pb.rank == h.nbr[k], B2P_ERR_ARG, "b2p_halo_p2p_import: blob %d is from rank %d", h.nbr[k], pb.rank);
+    int kk = -1;
+    for (int j = 0; j < pb.n_nbr; j++)
+      if (pb.nbr[j] == ctx->rank) kk = j;
+    B2P_CHECK(ctx, kk >= 0, B2P_ERR_ARG, "b2p_halo_p2p_import: rank %d does not list me as a neighbour", h.nbr[k]);
+    B2P_CHECK(ctx, pb.recv_off[kk + 1] - pb.recv_off[kk] == h.send_off[k + 1] - h.send_off[k] &&
+                       pb.send_off[kk + 1] - pb.send_off[kk] == h.recv_off[k + 1] - h.recv_off[k],
+              B2P_ERR_ARG, "b2p_halo_p2p_import: exchange sizes with rank %d do not match", h.nbr[k]);
+    void *base = nullptr;
+    B2P_CUDA(ctx, cudaIpcOpenMemHandle(&base, pb.handle, cudaIpcMemLazyEnablePeerAccess));
+    h.peer_maps.push_back(base);
+    double *mail = (double *)base;
+    unsigned long long *flags = (unsigned long long *)(mail + pb.n_ghost + pb.n_send);
+    pf[k] = mail + pb.recv_off[kk];               // my forward data -> the peer's ghost segment for me
+    pr[k] = mail + pb.n_ghost + pb.send_off[kk];  // my reverse data -> the peer's receive block for me
+    ff[k] = flags + kk;
+    fr[k] = flags + 32 + kk;
+  }
+  int rc;
+  std::vector<long long> so(h.send_off.begin(), h.send_off.end()), ro(h.recv_off.begin(), h.recv_off.end());
+  if ((rc = upload(ctx, (const int64_t *)so.data(), so.size(), (int64_t **)&h.d_send_off))) return rc;
+  if ((rc = upload(ctx, (const int64_t *)ro.data(), ro.size(), (int64_t **)&h.d_recv_off))) return rc;
+  if ((rc = upload(ctx, (const int64_t *)pf.data(), pf.size(), (int64_t **)&h.d_peer_fwd))) return rc;
+  if ((rc = upload(ctx, (const int64_t *)pr.data(), pr.size(), (int64_t **)&h.d_peer_rev))) return rc;
+  if ((rc = upload(ctx, (const int64_t *)ff.data(), ff.size(), (int64_t **)&h.d_peer_flag_fwd))) return rc;
+  if ((rc = upload(ctx, (const int64_t *)fr.data(), fr.size(), (int64_t **)&h.d_peer_flag_rev))) return rc;
+  B2P_CUDA(ctx, cudaMalloc((void **)&h.d_epoch, 128 * 8));
+  B2P_CUDA(ctx, cudaMemset(h.d_epoch, 0, 128 * 8));
+  {
+    std::vector<int32_t> has(32, 0);
+    for (int k = 0; k < nn; k++) has[k] = h.recv_off[k + 1] > h.recv_off[k] ? 1 : 0;
+    if ((rc = upload(ctx, has.data(), has.size(), (int32_t **)&h.d_recv_has))) return rc;
+  }
+  B2P_CUDA(ctx, cudaMalloc((void **)&h.d_done, 64 * 4));
+  B2P_CUDA(ctx, cudaMemset(h.d_done, 0, 64 * 4));
+  // the forward data lands directly in the ghost piece of the input L-vector
+  cudaFree(h.d_xg);
+  h.d_xg = h.d_mail;
+  h.p2p = true;
+  return B2P_SUCCESS;
+}
+
 int b2p_halo_forward(b2p_halo *h, double *lvec)
 {
   if (!h || !lvec) return B2P_ERR_ARG;
@@ -176,8 +357,19 @@ void b2p_halo_destroy(b2p_halo *h)
   if (!h) return;
   cudaFree(h->h.d_send_idx);
   cudaFree(h->h.d_buf);
-  cudaFree(h->h.d_xg);
+  if (!h->h.p2p) cudaFree(h->h.d_xg);
   cudaFree(h->h.d_yg);
+  for (void *m : h->h.peer_maps) cudaIpcCloseMemHandle(m);
+  cudaFree(h->h.d_mail);
+  cudaFree(h->h.d_epoch);
+  cudaFree(h->h.d_done);
+  cudaFree(h->h.d_recv_has);
+  cudaFree(h->h.d_send_off);
+  cudaFree(h->h.d_recv_off);
+  cudaFree(h->h.d_peer_fwd);
+  cudaFree(h->h.d_peer_rev);
+  cudaFree(h->h.d_peer_flag_fwd);
+  cudaFree(h->h.d_peer_flag_rev);
   if (h->h.comm_stream) cudaStreamDestroy(h->h.comm_stream);
   if (h->h.ev_in) cudaEventDestroy(h->h.ev_in);
   if (h->h.ev_fwd) cudaEventDestroy(h->h.ev_fwd);

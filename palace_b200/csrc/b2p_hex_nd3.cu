@@ -51,6 +51,8 @@ struct ND2Params
   double alpha;
   int ne;
   VSplit sp;
+  const unsigned long long *wait_flags, *wait_expect;  // peer-memory halo flags (SPLIT kernels only)
+  int wait_n, wait_from_elem;
   double Bo[Q_ * P_];
   double Bc[Q_ * (P_ + 1)];
   double Gc[Q_ * (P_ + 1)];
@@ -232,6 +234,24 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
     cp_async_commit();
   };
 
+  // Peer-memory halo: ghost values of this step are complete once every neighbour's flag reached the expected epoch.
+  bool ghosts_ready = !(SPLIT && prm.wait_n > 0);
+  auto wait_ghosts = [&](int bb)
+  {
+    if (ghosts_ready || (bb + 1) * NEW <= prm.wait_from_elem) return;
+    if (lane < prm.wait_n)
+    {
+      const unsigned long long want = prm.wait_expect[lane];
+      unsigned long long v;
+      do
+      {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(prm.wait_flags + lane) : "memory");
+      } while (v < want);
+    }
+    __syncwarp();
+    ghosts_ready = true;
+  };
+
   // mbarrier phase parities: bit s of par_i for index slot s
   uint32_t par_g = 0, par_i = 0;
   if (lane == 0)
@@ -243,6 +263,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
   }
   mbar_wait(bar_i + 0, 0);
   par_i ^= 1u;
+  wait_ghosts(b);
   gather_x(b, 0);
 
   const double alpha = prm.alpha;
@@ -324,6 +345,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
     {
       mbar_wait(bar_i + nslot, (par_i >> nslot) & 1u);
       par_i ^= (1u << nslot);
+      wait_ghosts(bn);
       gather_x(bn, nslot);
     }
 
@@ -755,6 +777,10 @@ int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   prm.sp.n_owned = rg.n_owned < 0 ? op->lsize : rg.n_owned;
   prm.sp.xg = rg.xg;
   prm.sp.yg = rg.yg;
+  prm.wait_flags = rg.wait_flags;
+  prm.wait_expect = rg.wait_expect;
+  prm.wait_n = rg.wait_n;
+  prm.wait_from_elem = rg.wait_from_elem;
   const int n = P_ + 1;
   for (int i = 0; i < Q_ * P_; i++) prm.Bo[i] = op->h_tab[i];
   for (int i = 0; i < Q_ * n; i++) prm.Bc[i] = op->h_tab[Q_ * P_ + i];

@@ -117,6 +117,7 @@ struct b2p_interp
   double *inv_mult = nullptr;                       // [out_lsize] 1 / (local elements touching the dof)
   // per component: dims and matrix offsets into `mats`
   int in_off[3], in_n[3][3], out_off[3], out_n[3][3], mat_off[3][3];
+  int ident[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   double *mats = nullptr;
   int n_mats = 0;
 };
@@ -130,6 +131,10 @@ struct ApplyRange
   long long n_owned = -1;      // dofs below this index live in x / y, the rest in xg / yg
   const double *xg = nullptr;
   double *yg = nullptr;
+  // peer-memory halo: elements >= wait_from_elem need the ghost values; before touching them a warp
+  // waits until flags[k] >= expect[k] for k < wait_n (acquire at system scope)
+  const unsigned long long *wait_flags = nullptr, *wait_expect = nullptr;
+  int wait_n = 0, wait_from_elem = 0;
 };
 // Kernel launchers (defined in the .cu files).
 int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);

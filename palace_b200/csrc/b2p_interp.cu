@@ -25,6 +25,7 @@ struct InterpParams
   double alpha;
   int ne, in_P, out_P, in_PS, out_PS, ncomp, n_mats;
   int in_off[3], in_n[3][3], out_off[3], out_n[3][3], mat_off[3][3];
+  int ident[3][3];  // 1-D factor is the identity: skip its loop
 };
 
 // y[out] += alpha * inv_mult[out] * sum_e E_out^T (Ax (x) Ay (x) Az) E_in x
@@ -83,13 +84,15 @@ __global__ void interp_kernel(InterpParams prm, int neb)
       const double *Ay = smat + prm.mat_off[c][1] + j * ny;
       const double *Az = smat + prm.mat_off[c][2] + k * nz;
       const double *in = src + prm.in_off[c];
-      for (int kk = 0; kk < nz; kk++)
+      const bool ix = prm.ident[c][0], iy = prm.ident[c][1], iz = prm.ident[c][2];
+      const int k0 = iz ? k : 0, k1 = iz ? k + 1 : nz, j0 = iy ? j : 0, j1 = iy ? j + 1 : ny, i0 = ix ? i : 0, i1 = ix ? i + 1 : nx;
+      for (int kk = k0; kk < k1; kk++)
       {
         double sy = 0.0;
-        for (int jj = 0; jj < ny; jj++)
+        for (int jj = j0; jj < j1; jj++)
         {
           double sx = 0.0;
-          for (int ii = 0; ii < nx; ii++) sx += Ax[ii] * in[ii + nx * (jj + ny * kk)];
+          for (int ii = i0; ii < i1; ii++) sx += Ax[ii] * in[ii + nx * (jj + ny * kk)];
           sy += Ay[jj] * sx;
         }
         s += Az[kk] * sy;
@@ -111,13 +114,15 @@ __global__ void interp_kernel(InterpParams prm, int neb)
         const double *Ay = smat + prm.mat_off[cc][1] + jj;
         const double *Az = smat + prm.mat_off[cc][2] + kk;
         const double *out = src + prm.out_off[cc];
-        for (int k = 0; k < oz; k++)
+        const bool ix = prm.ident[cc][0], iy = prm.ident[cc][1], iz = prm.ident[cc][2];
+        const int k0 = iz ? kk : 0, k1 = iz ? kk + 1 : oz, j0 = iy ? jj : 0, j1 = iy ? jj + 1 : oy, i0 = ix ? ii : 0, i1 = ix ? ii + 1 : ox;
+        for (int k = k0; k < k1; k++)
         {
           double sy = 0.0;
-          for (int j = 0; j < oy; j++)
+          for (int j = j0; j < j1; j++)
           {
             double sx = 0.0;
-            for (int i = 0; i < ox; i++) sx += Ax[i * nx] * out[i + ox * (j + oy * k)];
+            for (int i = i0; i < i1; i++) sx += Ax[i * nx] * out[i + ox * (j + oy * k)];
             sy += Ay[j * ny] * sx;
           }
           s += Az[k * nz] * sy;
@@ -154,6 +159,7 @@ InterpParams make_params(const b2p_interp *it, double alpha, const double *x, do
       p.in_n[c][d] = it->in_n[c][d];
       p.out_n[c][d] = it->out_n[c][d];
       p.mat_off[c][d] = it->mat_off[c][d];
+      p.ident[c][d] = it->ident[c][d];
     }
   }
   return p;
@@ -192,7 +198,9 @@ int interp_apply(const b2p_interp *it, bool transpose, double alpha, const doubl
 {
   InterpParams prm = make_params(it, alpha, x, y);
   const int src_P = transpose ? it->out_P : it->in_P;
-  int neb = std::max(1, 256 / std::max(it->out_P, it->in_P));
+  // enough elements per block that every thread has at least two destination dofs
+  const int dst_P = transpose ? it->in_P : it->out_P;
+  int neb = std::max(1, (2 * 256 + dst_P - 1) / dst_P);
   neb = std::min(neb, 16);
   const size_t shmem = sizeof(double) * ((size_t)it->n_mats + (size_t)neb * src_P);
   const int grid = (it->ne + neb - 1) / neb;
@@ -250,6 +258,10 @@ int b2p_interp_create(b2p_ctx *ctx, const b2p_interp_desc *d, b2p_interp **out)
       it->out_n[c][a] = cc.out_n[a];
       it->mat_off[c][a] = (int)mats.size();
       B2P_CHECK(ctx, cc.A[a], B2P_ERR_ARG, "b2p_interp_create: missing 1-D matrix");
+      bool id = cc.out_n[a] == cc.in_n[a];
+      for (int r = 0; id && r < cc.out_n[a]; r++)
+        for (int q2 = 0; q2 < cc.in_n[a]; q2++) id = id && cc.A[a][(size_t)r * cc.in_n[a] + q2] == (r == q2 ? 1.0 : 0.0);
+      it->ident[c][a] = id ? 1 : 0;
       mats.insert(mats.end(), cc.A[a], cc.A[a] + (size_t)cc.out_n[a] * cc.in_n[a]);
     }
   }

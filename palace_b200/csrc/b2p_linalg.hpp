@@ -90,6 +90,18 @@ struct Halo
   int32_t *d_send_idx = nullptr;        // owned L-indices to send, concatenated per neighbour
   double *d_buf = nullptr;              // pack / unpack buffer (size send total)
   double *d_xg = nullptr, *d_yg = nullptr;  // ghost pieces of the input / output L-vectors
+  // peer-memory mailboxes (optional, b2p_halo_p2p_*): see b2p_halo.cu
+  bool p2p = false;
+  double *d_mail = nullptr;                     // this rank's mailbox
+  double *d_mail_rev = nullptr;                 // = d_mail + n_ghost
+  unsigned long long *d_flags = nullptr;        // [64]: fwd flags [0,32), rev flags [32,64)
+  int *d_recv_has = nullptr;                    // [32] neighbour k sends me ghosts
+  unsigned int *d_done = nullptr;               // [64] block-completion counters of the push kernels
+  unsigned long long *d_epoch = nullptr;        // [128]: send-fwd, send-rev, expect-fwd, expect-rev (32 each)
+  long long *d_send_off = nullptr, *d_recv_off = nullptr;  // prefix sums on the device
+  double **d_peer_fwd = nullptr, **d_peer_rev = nullptr;   // per neighbour: where my data lands in the peer's mailbox
+  unsigned long long **d_peer_flag_fwd = nullptr, **d_peer_flag_rev = nullptr;
+  std::vector<void *> peer_maps;                // cudaIpcOpenMemHandle results
   cudaStream_t comm_stream = nullptr;   // high-priority stream: the forward exchange overlaps interior elements
   cudaEvent_t ev_in = nullptr, ev_fwd = nullptr;
 };

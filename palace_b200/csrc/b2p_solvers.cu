@@ -10,6 +10,8 @@ int halo_forward(Halo *h, double *lx);
 int halo_reverse(Halo *h, double *ly);
 int halo_forward_split(Halo *h, const double *x, cudaStream_t s);
 int halo_reverse_split(Halo *h, double *y, cudaStream_t s);
+int halo_forward_p2p(Halo *h, const double *x, bool in_kernel_wait, cudaStream_t s);
+int halo_reverse_p2p(Halo *h, double *y, cudaStream_t s);
 int interp_apply(const b2p_interp *it, bool transpose, double alpha, const double *x, double *y, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------ Operator
@@ -49,29 +51,41 @@ ParOperator::~ParOperator()
 
 void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
 {
-  // Owned dofs are read from x and accumulated into y directly; ghosts live in the halo's buffers.
-  //   main stream : zero y, y_ghost; forward exchange (P); INTERFACE elements (the few that touch ghosts)
-  //   comm stream : reverse exchange (P^T) + add into y   |  main stream: INTERIOR elements
-  // The persistent element kernel fills every SM, so a collective can only overlap it if its kernel is
-  // already resident: the reverse exchange is therefore launched just before the interior elements.
-  // (Measured on 2 x B200, p = 3, 2M dofs/GPU: exchange ~13 us per direction, interface 9 us, interior 60 us.)
+  // Owned dofs are read from x and accumulated into y directly; ghosts live in the halo's buffers:
+  //   zero y and y_ghost; forward exchange (P); all elements; reverse exchange (P^T) + add into y.
+  // With peer mailboxes (b2p_halo_p2p_*) the exchanges are NVLink stores + flags issued from small
+  // kernels on this stream; otherwise NCCL grouped send/recv. (An interior/interface split that overlaps
+  // the collectives with the element kernel was measured to give nothing on B200: the persistent element
+  // kernel fills every SM, so a collective kernel launched beside it only starts when it retires.)
   Halo *h = halo;
   vec::set(ctx, y, height, 0.0);
   if (h->n_ghost > 0) cudaMemsetAsync(h->d_yg, 0, sizeof(double) * h->n_ghost, s);
-  halo_forward_split(h, x, s);
-  const int n_int = ne_interior;
+  // In-kernel wait: with elements ordered interior-first (SetInteriorElements) the ND element kernel itself
+  // checks the neighbours' flags just before it reaches the first interface element, so the forward exchange
+  // costs nothing on the critical path. (H1 operators use the separate wait kernel.)
+  bool in_kernel = h->p2p && ne_interior > 0;
+  for (auto &t : terms) in_kernel = in_kernel && t.op->kind != B2P_H1_DIFFUSION;
+  if (h->p2p)
+    halo_forward_p2p(h, x, in_kernel, s);
+  else
+    halo_forward_split(h, x, s);
   for (auto &t : terms)
-    b2p_op_apply_add_split(t.op, t.coef, x, h->d_xg, y, h->d_yg, height, n_int, -1, B2P_APPLY_MASKED, s);
-  if (n_int > 0)
   {
-    cudaEventRecord(h->ev_in, s);
-    cudaStreamWaitEvent(h->comm_stream, h->ev_in, 0);
-    halo_reverse_split(h, y, h->comm_stream);
-    cudaEventRecord(h->ev_fwd, h->comm_stream);
-    for (auto &t : terms)
-      b2p_op_apply_add_split(t.op, t.coef, x, nullptr, y, nullptr, height, 0, n_int, B2P_APPLY_MASKED, s);
-    cudaStreamWaitEvent(s, h->ev_fwd, 0);
+    ApplyRange rg;
+    rg.n_owned = height;
+    rg.xg = h->d_xg;
+    rg.yg = h->d_yg;
+    if (in_kernel)
+    {
+      rg.wait_flags = h->d_flags;
+      rg.wait_expect = h->d_epoch + 2 * 32;
+      rg.wait_n = (int)h->nbr.size();
+      rg.wait_from_elem = ne_interior;
+    }
+    apply_range(t.op, t.op->lidx_bc ? t.op->lidx_bc : t.op->lidx, t.coef, x, y, rg, 0, s);
   }
+  if (h->p2p)
+    halo_reverse_p2p(h, y, s);
   else
     halo_reverse_split(h, y, s);
 }

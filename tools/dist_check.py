@@ -54,6 +54,14 @@ def main():
 
     hnd = {q: halo_of(lnd[q]) for q in orders}
     hh1 = {q: halo_of(lh1[q]) for q in orders}
+    if os.environ.get("B2P_HALO_P2P", "1") == "1":
+        def gather(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+        for q in orders:
+            hnd[q].enable_p2p(gather)
+            hh1[q].enable_p2p(gather)
 
     def par_op(kind, ls, halo, blob_, fine=None):
         sp = ls.space
