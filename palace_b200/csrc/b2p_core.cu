@@ -93,8 +93,9 @@ namespace b2p
 int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, int flags,
                 cudaStream_t s)
 {
-  if (op->kind == B2P_H1_DIFFUSION) return launch_h1_hex_apply(op, lidx, alpha, x, y, rg, s);
-  if (flags & B2P_APPLY_SIMPLE_KERNEL) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
+  const bool simple = flags & B2P_APPLY_SIMPLE_KERNEL;
+  if (op->kind == B2P_H1_DIFFUSION) return simple ? launch_h1_hex_apply(op, lidx, alpha, x, y, rg, s) : launch_h1_hex_apply3(op, lidx, alpha, x, y, rg, s);
+  if (simple) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
   return launch_nd_hex_apply2(op, lidx, alpha, x, y, rg, s);
 }
 }  // namespace b2p

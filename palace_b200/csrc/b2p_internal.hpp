@@ -143,6 +143,8 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
                 cudaStream_t s);
 int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
 int launch_h1_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
+int launch_h1_hex_apply3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg,
+                         cudaStream_t s);
 int launch_h1_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
 int launch_assemble_qdata(b2p_op *op, cudaStream_t s);
 int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, const double *d_B, const double *d_G,

@@ -1,0 +1,83 @@
+// Device helpers of the warp-autonomous element pipelines (b2p_hex_nd3.cu, b2p_hex_h1v3.cu):
+// mbarrier + TMA bulk copies, cp.async staging, signed-restriction gather/scatter fast paths.
+#pragma once
+#include "b2p_contract.cuh"
+
+namespace b2p
+{
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t ok = 0;
+  while (!ok)
+  {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Staged dof value with the restriction's sign (masked / padded slots were staged as zero):
+// the sign bit of the index is XORed into the high word of the value.
+__device__ __forceinline__ double staged(const int32_t *cI, const double *cU, int pos, bool valid)
+{
+  const int32_t gi = cI[pos];
+  const double v = cU[pos];
+  int hi = __double2hiint(v) ^ (gi & (int)0x80000000);
+  const double r = __hiloint2double(hi, __double2loint(v));
+  return valid ? r : 0.0;
+}
+// |index| of a signed restriction entry (-1 - gi == ~gi for negative entries)
+__device__ __forceinline__ int32_t abs_idx(int32_t gi) { return gi ^ (gi >> 31); }
+// Predicated RED.F64 of value (with the entry's sign) at y[|gi|]; masked entries are skipped.
+__device__ __forceinline__ void scatter_fast(double *y, int32_t gi, double v)
+{
+  const int hi = __double2hiint(v) ^ (gi & (int)0x80000000);
+  const double sv = __hiloint2double(hi, __double2loint(v));
+  double *addr = y + (uint32_t)abs_idx(gi);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %2, 0x80000000;\n"
+      "@p red.global.add.f64 [%0], %1;\n"
+      "}\n" ::"l"(addr),
+      "d"(sv), "r"(gi)
+      : "memory");
+}
+
+}  // namespace b2p

@@ -183,3 +183,24 @@ def test_production_and_simple_kernels_agree_with_alpha_and_mask(b2p_ctx, p, kin
         op.apply_add_ex(-0.75, _dev(x), yd, masked=True, simple_kernel=simple)
         torch.cuda.synchronize()
         assert _rel(yd.cpu().numpy(), expect) < RTOL
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_h1_production_and_simple_kernels_agree_with_alpha_and_mask(b2p_ctx, p):
+    prob = common.make_problem(p=p)
+    blob = common.coefficient(O.H1_DIFFUSION, 3, "matrix")
+    g = common.gpu_geom(b2p_ctx, prob)
+    op = common.gpu_op(b2p_ctx, g, prob, O.H1_DIFFUSION, blob)
+    ess = prob.h1.ess_dofs
+    op.set_essential(ess)
+    rng = np.random.default_rng(12)
+    x, y0 = rng.random(prob.h1.ndofs), rng.random(prob.h1.ndofs)
+    xm = x.copy()
+    xm[ess] = 0.0
+    y_ref = common.oracle_apply(prob, O.H1_DIFFUSION, blob, xm)
+    y_ref[ess] = 0.0
+    for simple in (False, True):
+        yd = _dev(y0)
+        op.apply_add_ex(1.25, _dev(x), yd, masked=True, simple_kernel=simple)
+        torch.cuda.synchronize()
+        assert _rel(yd.cpu().numpy(), y0 + 1.25 * y_ref) < RTOL
