@@ -339,6 +339,13 @@ int set_coeff(b2p_op *op, const void *blob, size_t bytes)
   }
   op->owns_coeff = true;
   op->n_mat = (int)(mats.size() / 9);
+  op->iso = true;
+  for (size_t m = 0; m < mats.size() / 9 && op->iso; m++)
+    for (int t = 0; t < 9; t++)
+    {
+      const double v = mats[9 * m + t], d = mats[9 * m];
+      if ((t % 4 == 0) ? (v != d) : (v != 0.0)) op->iso = false;
+    }
   int rc;
   if ((rc = upload(ctx, mats.data(), mats.size(), &op->mat))) return rc;
   if ((rc = upload(ctx, emat.data(), emat.size(), &op->emat))) return rc;
@@ -471,6 +478,7 @@ int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *d, b2p_op **out)
   op->mat = fine->mat;
   op->emat = fine->emat;
   op->ecoef = fine->ecoef;
+  op->iso = fine->iso;
   op->n_mat = fine->n_mat;
   op->aq = fine->aq;
   op->aq_ncomp = fine->aq_ncomp;

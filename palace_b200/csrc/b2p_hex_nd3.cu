@@ -54,6 +54,7 @@ struct ND2Params
   VSplit sp;
   const unsigned long long *wait_flags, *wait_expect;  // peer-memory halo flags (SPLIT kernels only)
   int wait_n, wait_from_elem;
+  int iso;  // all coefficient matrices are multiples of the identity
   double Bo[Q_ * P_];
   double Bc[Q_ * (P_ + 1)];
   double Gc[Q_ * (P_ + 1)];
@@ -448,12 +449,26 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
             double A[9];
 #pragma unroll
             for (int i = 0; i < 9; i++) A[i] = gq[(1 + i) * Q];
-            if (MASS) AtCAx(A, C, uu[qx], wdetJ, v);
-            if (CURL)
+            if (prm.iso)
             {
-              double Jd[9];
-              cofactor33(A, Jd);
-              AtCAx(Jd, C + 9, cc[qx], wdetJ, cw);
+              // every material is a multiple of the identity (the common isotropic case): C = c I
+              if (MASS) AtAx(A, uu[qx], wdetJ * C[0], v);
+              if (CURL)
+              {
+                double Jd[9];
+                cofactor33(A, Jd);
+                AtAx(Jd, cc[qx], wdetJ * C[9], cw);
+              }
+            }
+            else
+            {
+              if (MASS) AtCAx(A, C, uu[qx], wdetJ, v);
+              if (CURL)
+              {
+                double Jd[9];
+                cofactor33(A, Jd);
+                AtCAx(Jd, C + 9, cc[qx], wdetJ, cw);
+              }
             }
           }
         }
@@ -708,6 +723,7 @@ int launch3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   prm.wait_expect = rg.wait_expect;
   prm.wait_n = rg.wait_n;
   prm.wait_from_elem = rg.wait_from_elem;
+  prm.iso = op->iso ? 1 : 0;
   const int n = P_ + 1;
   for (int i = 0; i < Q_ * P_; i++) prm.Bo[i] = op->h_tab[i];
   for (int i = 0; i < Q_ * n; i++) prm.Bc[i] = op->h_tab[Q_ * P_ + i];

@@ -98,6 +98,7 @@ struct b2p_op
   double *mat = nullptr;       // [n_mat_total][9] column-major (mass part first, then curl part)
   int32_t *emat = nullptr;     // [ne][2] indices into mat (value part, derivative part)
   int n_mat = 0;
+  bool iso = false;            // every material matrix is c * I
   double *ecoef = nullptr;     // [ne][18] per-element coefficient matrices (TMA-friendly copy of mat[emat])
   // assembled q-data (optional): aq[ne][ncomp][Q], symmetric 6 per part
   double *aq = nullptr;

@@ -23,6 +23,17 @@ __device__ __forceinline__ void AtCAx(const double A[9], const double C[9], cons
   y[2] = s * (A[6] * z0 + A[7] * z1 + A[8] * z2);
 }
 
+// y = s * A^T (A x)   (isotropic coefficient: C = c I folded into s)
+__device__ __forceinline__ void AtAx(const double A[9], const double x[3], double s, double y[3])
+{
+  const double t0 = A[0] * x[0] + A[3] * x[1] + A[6] * x[2];
+  const double t1 = A[1] * x[0] + A[4] * x[1] + A[7] * x[2];
+  const double t2 = A[2] * x[0] + A[5] * x[1] + A[8] * x[2];
+  y[0] = s * (A[0] * t0 + A[1] * t1 + A[2] * t2);
+  y[1] = s * (A[3] * t0 + A[4] * t1 + A[5] * t2);
+  y[2] = s * (A[6] * t0 + A[7] * t1 + A[8] * t2);
+}
+
 // Cofactor matrix (adj^T) of a column-major 3x3: for A = J^-T this is J/detJ (utils_33_qf.h:20-37).
 __device__ __forceinline__ void cofactor33(const double J[9], double A[9])
 {
