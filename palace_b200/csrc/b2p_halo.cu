@@ -42,8 +42,13 @@ namespace
 // the peer's flag.
 __global__ void p2p_push_kernel(const double *__restrict__ src, const int32_t *__restrict__ idx, const long long *seg_off,
                                 double *const *dst_ptr, unsigned long long *const *flag_ptr, unsigned long long *epoch,
-                                unsigned int *done, unsigned long long *bump_expect, const int *recv_has = nullptr)
+                                unsigned int *done, unsigned long long *bump_expect, const int *recv_has = nullptr,
+                                double *zero_buf = nullptr, long long zero_n = 0)
 {
+  // (optionally) clear the ghost accumulation buffer of this step in the same launch
+  for (long long i = (long long)(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < zero_n;
+       i += (long long)gridDim.x * gridDim.y * blockDim.x)
+    zero_buf[i] = 0.0;
   const int k = blockIdx.y;
   const long long b = seg_off[k], e = seg_off[k + 1];
   double *dst = dst_ptr[k];
@@ -69,6 +74,27 @@ __global__ void p2p_push_kernel(const double *__restrict__ src, const int32_t *_
     }
   }
 }
+// Reverse exchange, receiving side: block k waits for neighbour k's flag, then adds its segment into y.
+__global__ void p2p_wait_add_kernel(const long long *seg_off, const unsigned long long *flags, unsigned long long *expect,
+                                    double *__restrict__ y, const int32_t *__restrict__ idx, const double *__restrict__ buf)
+{
+  const int k = blockIdx.x;
+  const long long b = seg_off[k], e = seg_off[k + 1];
+  __shared__ unsigned long long want;
+  if (threadIdx.x == 0) want = ++expect[k];
+  __syncthreads();
+  if (e <= b) return;
+  if (threadIdx.x == 0)
+  {
+    unsigned long long v;
+    do
+    {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + k) : "memory");
+    } while (v < want);
+  }
+  __syncthreads();
+  for (long long i = b + threadIdx.x; i < e; i += blockDim.x) atomicAdd(y + idx[i], __ldcv(buf + i));
+}
 __global__ void p2p_wait_kernel(int nseg, const long long *seg_off, const unsigned long long *flags, unsigned long long *expect)
 {
   const int k = threadIdx.x;
@@ -88,10 +114,11 @@ __global__ void p2p_wait_kernel(int nseg, const long long *seg_off, const unsign
 int halo_forward_p2p(Halo *h, const double *x, bool in_kernel_wait, cudaStream_t s)
 {
   const int nn = (int)h->nbr.size();
+  if (nn == 0) return B2P_SUCCESS;
   const long long ns = h->send_off.back();
   dim3 grid((unsigned)std::min<long long>((ns / nn + 255) / 256 + 1, 32), nn);
   p2p_push_kernel<<<grid, 256, 0, s>>>(x, h->d_send_idx, h->d_send_off, h->d_peer_fwd, h->d_peer_flag_fwd, h->d_epoch, h->d_done,
-                                       in_kernel_wait ? h->d_epoch + 2 * 32 : nullptr, h->d_recv_has);
+                                       in_kernel_wait ? h->d_epoch + 2 * 32 : nullptr, h->d_recv_has, h->d_yg, h->n_ghost);
   if (!in_kernel_wait) p2p_wait_kernel<<<1, 32, 0, s>>>(nn, h->d_recv_off, h->d_flags, h->d_epoch + 2 * 32);
   B2P_CUDA(h->ctx, cudaGetLastError());
   return B2P_SUCCESS;
@@ -100,13 +127,13 @@ int halo_forward_p2p(Halo *h, const double *x, bool in_kernel_wait, cudaStream_t
 int halo_reverse_p2p(Halo *h, double *y, cudaStream_t s)
 {
   const int nn = (int)h->nbr.size();
+  if (nn == 0) return B2P_SUCCESS;
   const long long nr = h->recv_off.back(), ns = h->send_off.back();
   dim3 grid((unsigned)std::min<long long>((nr / nn + 255) / 256 + 1, 32), nn);
   p2p_push_kernel<<<grid, 256, 0, s>>>(h->d_yg ? h->d_yg : h->d_mail, nullptr, h->d_recv_off, h->d_peer_rev, h->d_peer_flag_rev, h->d_epoch + 32,
                                        h->d_done + 32, nullptr);
-  p2p_wait_kernel<<<1, 32, 0, s>>>(nn, h->d_send_off, h->d_flags + 32, h->d_epoch + 3 * 32);
-  if (ns > 0)
-    unpack_add_kernel<<<(int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, s>>>(y, h->d_send_idx, ns, h->d_mail_rev);
+  (void)ns;
+  p2p_wait_add_kernel<<<nn, 1024, 0, s>>>(h->d_send_off, h->d_flags + 32, h->d_epoch + 3 * 32, y, h->d_send_idx, h->d_mail_rev);
   B2P_CUDA(h->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) h1_hex_apply3_kernel(const __gr
         if (gi == B2P_SKIP_IDX)
           sU[l] = 0.0;
         else if (SPLIT)
-          cp_async8(sU + l, split_src(prm.x, prm.sp, abs_idx(gi)));
+          cp_async8(sU + l, split_src_fast(prm.x, prm.sp, abs_idx(gi)));
         else
           cp_async8(sU + l, prm.x + (uint32_t)abs_idx(gi));
       }
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) h1_hex_apply3_kernel(const __gr
 #pragma unroll
             for (int qz = 0; qz < q; qz++) o += prm.Bc[qz * n + k] * a[qz] + prm.Gc[qz * n + k] * bb[qz];
             if (SPLIT)
-              scatter2(prm.y, prm.sp, gk[k], o);
+              scatter_fast_split(prm.y, prm.sp, gk[k], o);
             else
               scatter_fast(prm.y, gk[k], o);
           }

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
         if (gi == B2P_SKIP_IDX)
           sU[l] = 0.0;  // masked / padding: reads as zero
         else if (SPLIT)
-          cp_async8(sU + l, split_src(prm.x, prm.sp, abs_idx(gi)));
+          cp_async8(sU + l, split_src_fast(prm.x, prm.sp, abs_idx(gi)));
         else
           cp_async8(sU + l, prm.x + (uint32_t)abs_idx(gi));
       }
@@ -656,8 +656,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
               if (CURL) o += prm.Gc[qz * n + k] * xb[qz];
               if (CURL) o2 += prm.Gc[qz * n + k] * yb[qz];
             }
-            if (SPLIT) scatter2(prm.y, prm.sp, gx[k], o); else scatter_fast(prm.y, gx[k], o);
-            if (SPLIT) scatter2(prm.y, prm.sp, gy[k], o2); else scatter_fast(prm.y, gy[k], o2);
+            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gx[k], o); else scatter_fast(prm.y, gx[k], o);
+            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gy[k], o2); else scatter_fast(prm.y, gy[k], o2);
           }
         }
         if (vz)
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply3_kernel(const __gr
             double o = 0.0;
 #pragma unroll
             for (int qz = 0; qz < q; qz++) o += prm.Bo[qz * p + k] * za[qz];
-            if (SPLIT) scatter2(prm.y, prm.sp, gz[k], o); else scatter_fast(prm.y, gz[k], o);
+            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gz[k], o); else scatter_fast(prm.y, gz[k], o);
           }
         }
       }

@@ -80,4 +80,28 @@ __device__ __forceinline__ void scatter_fast(double *y, int32_t gi, double v)
       : "memory");
 }
 
+
+// Same with the L-vector in two pieces (owned part in y, ghosts in sp.yg): one compare + select on
+// 32-bit indices picks the base, the rest is the fast path.
+__device__ __forceinline__ void scatter_fast_split(double *y, const VSplit &sp, int32_t gi, double v)
+{
+  const int hi = __double2hiint(v) ^ (gi & (int)0x80000000);
+  const double sv = __hiloint2double(hi, __double2loint(v));
+  const uint32_t a = (uint32_t)abs_idx(gi), no = (uint32_t)sp.n_owned;
+  double *addr = (a < no) ? y + a : sp.yg + (a - no);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %2, 0x80000000;\n"
+      "@p red.global.add.f64 [%0], %1;\n"
+      "}\n" ::"l"(addr),
+      "d"(sv), "r"(gi)
+      : "memory");
+}
+__device__ __forceinline__ const double *split_src_fast(const double *x, const VSplit &sp, int32_t a)
+{
+  const uint32_t ua = (uint32_t)a, no = (uint32_t)sp.n_owned;
+  return (ua < no) ? x + ua : sp.xg + (ua - no);
+}
+
 }  // namespace b2p

@@ -1,6 +1,8 @@
 // Host logic of the device-resident solver loop. Every vector operation is a kernel on ctx->stream;
 // the only host synchronisations are the scalar reductions that steer the recurrences.
 // Class-by-class restatement of the reference (file:line in each method).
+#include <cstdlib>
+
 #include "b2p_linalg.hpp"
 
 namespace b2p
@@ -59,7 +61,7 @@ void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
   // kernel fills every SM, so a collective kernel launched beside it only starts when it retires.)
   Halo *h = halo;
   vec::set(ctx, y, height, 0.0);
-  if (h->n_ghost > 0) cudaMemsetAsync(h->d_yg, 0, sizeof(double) * h->n_ghost, s);
+  if (h->n_ghost > 0 && !h->p2p) cudaMemsetAsync(h->d_yg, 0, sizeof(double) * h->n_ghost, s);  // (the p2p push kernel clears it)
   // In-kernel wait: with elements ordered interior-first (SetInteriorElements) the ND element kernel itself
   // checks the neighbours' flags just before it reaches the first interface element, so the forward exchange
   // costs nothing on the critical path. (H1 operators use the separate wait kernel.)
@@ -103,7 +105,12 @@ void ParOperator::Mult(const double *x, double *y) const
   {
     const auto key = std::make_pair(x, y);
     auto it = graphs_.find(key);
-    if (!warmed_)
+    static const bool no_graph = []() { const char *e = getenv("B2P_NO_GRAPH"); return e && e[0] == '1'; }();
+    if (no_graph)
+    {
+      MultHaloBody(x, y, s);
+    }
+    else if (!warmed_)
     {
       // first call runs eagerly: one-time kernel attribute setup must not happen inside a capture
       warmed_ = true;

@@ -28,13 +28,14 @@ def main():
         for _ in range(it): f()
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / it * 1e3
-    t_fwd = timeit(lambda: halo.forward(lv))
-    t_rev = timeit(lambda: halo.reverse(lv))
-    t_both = timeit(lambda: (halo.forward(lv), halo.reverse(lv)))
+    t_fwd = t_rev = t_both = 0.0
     nd = ls.space
     geom = capi.Geom.hex(ctx, prob["xe"][ls.elems], prob["mesh"].attr[ls.elems], 1, prob["q1d"], prob["nB"], prob["nG"], prob["tabs"].qw)
     idx, ori = nd.native_restriction(); t = prob["tabs"]
     op = capi.Op.create(ctx, geom, capi.CURLCURL_MASS, 3, ls.lsize, idx, ori, nd.dof_map, t.Bo, t.Bc, t.Gc, prob["blob"])
+    def gather(blob):
+        out = [None] * world; dist.all_gather_object(out, blob); return out
+    if os.environ.get("B2P_HALO_P2P", "1") == "1": halo.enable_p2p(gather)
     A = capi.Operator.par(ctx, ls.n_true, ls.lsize, [op], None, None, 1, halo); A.set_interior(ls.n_interior)
     A0 = capi.Operator.par(ctx, ls.n_true, ls.lsize, [op], None, None, 1, halo)
     x = torch.rand(ls.n_true, dtype=torch.float64, device="cuda"); y = torch.zeros_like(x)
@@ -45,6 +46,9 @@ def main():
     t_ifc = timeit(lambda: op.apply_add_split(1.0, x, xg, y, yg, ls.n_true, ls.n_interior, -1))
     t_all = timeit(lambda: op.apply_add_split(1.0, x, xg, y, yg, ls.n_true, 0, -1))
     t_ms = timeit(lambda: y.zero_())
+    xl = torch.rand(ls.lsize, dtype=torch.float64, device="cuda"); yl = torch.zeros_like(xl)
+    t_nosplit = timeit(lambda: op.apply_add(xl, yl))
+    print(f"rank {rank}: nosplit_kernel={t_nosplit:.1f} us", flush=True)
     print(f"rank {rank}: mult_overlap={t_full:.1f} mult_nooverlap={t_noov:.1f} interior={t_int:.1f} interface={t_ifc:.1f} all={t_all:.1f} memset={t_ms:.1f} us", flush=True)
     print(f"rank {rank}: n_true={ls.n_true} n_ghost={ls.n_ghost} n_interior={ls.n_interior}/{ls.elems.size} send={ls.send_counts.tolist()} "
           f"fwd={t_fwd:.1f}us rev={t_rev:.1f}us both={t_both:.1f}us", flush=True)
