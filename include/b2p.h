@@ -75,6 +75,9 @@ int b2p_geom_create_hex(b2p_ctx *ctx, int ne, int mesh_order, int q1d, const dou
                         const double *nodeG, const double *qw1d, const int32_t *attr, b2p_geom **out);
 /* Prebuilt q-data in the reference layout qdata[ne][11][Q] = {attr, w detJ, adjJt/detJ[9]} (host). */
 int b2p_geom_create_qdata(b2p_ctx *ctx, int ne, int q1d, const double *qdata, b2p_geom **out);
+/* Same for any element type / quadrature rule (Q points per element, caller's point order): feeds the
+ * dense-basis operators below. */
+int b2p_geom_create_qdata_general(b2p_ctx *ctx, int ne, int Q, const double *qdata, b2p_geom **out);
 /* Copy the device q-data back in the reference layout [ne][11][Q] (for parity tests). */
 int b2p_geom_get_qdata(b2p_geom *g, double *qdata_host);
 void b2p_geom_destroy(b2p_geom *g);
@@ -99,6 +102,26 @@ typedef struct
 } b2p_op_desc;
 
 int b2p_op_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_op_desc *desc, b2p_op **out);
+/* Dense-basis (non-tensor) operator: what Palace builds for every vector element and every simplex
+ * (InitNonTensorBasis -> CeedBasisCreateHcurl, fem/libceed/basis.cpp:40-85): tables exactly as
+ * fe.GetDofToQuad(ir, FULL) supplies them, interp[3][Q][P] and deriv[3][Q][P] (curl for ND kinds, grad for
+ * B2P_H1_DIFFUSION) in NATIVE dof order; restriction idx[ne][P] with either sign orientation `orient`
+ * (restriction.cpp:290-297) or the row-major tridiagonal `curl_orient[ne][P][3]` of ND tets / prisms with
+ * p >= 2 (restriction.cpp:301-368). Applied as one FP64 tensor-core (DMMA) GEMM per batch of 8 elements. */
+typedef struct
+{
+  int kind;
+  int P, Q, ne;
+  int64_t lsize;
+  const int32_t *idx;
+  const int8_t *orient;       /* or NULL */
+  const int8_t *curl_orient;  /* or NULL */
+  const double *interp;       /* [3][Q][P] (ND mass kinds) or NULL */
+  const double *deriv;        /* [3][Q][P] */
+  const void *coeff_ctx;
+  size_t coeff_ctx_bytes;
+} b2p_dense_op_desc;
+int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *desc, b2p_op **out);
 /* p-coarsening that shares the fine operator's quadrature, geometry and coefficient
  * (ceed::CeedOperatorCoarsen, fem/libceed/operator.cpp:525-585): only space fields of desc are read
  * (p, lsize, idx, orient, dof_map, Bo/Bc/Gc evaluated at the FINE q1d points). */

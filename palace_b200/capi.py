@@ -105,9 +105,27 @@ class Ctx:
             self.h = None
 
 
+class DenseOpDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("P", C.c_int), ("Q", C.c_int), ("ne", C.c_int), ("lsize", C.c_int64), ("idx", C.c_void_p),
+        ("orient", C.c_void_p), ("curl_orient", C.c_void_p), ("interp", C.c_void_p), ("deriv", C.c_void_p),
+        ("coeff_ctx", C.c_void_p), ("coeff_ctx_bytes", C.c_size_t),
+    ]
+
+
 class Geom:
     def __init__(self, ctx: Ctx, h):
         self.ctx, self.h = ctx, h
+
+    @classmethod
+    def general(cls, ctx, qdata):
+        """Prebuilt q-data [ne][11][Q] for any element type (dense-basis operators)."""
+        qdata = _np(qdata, np.float64)
+        h = C.c_void_p()
+        _chk(lib().b2p_geom_create_qdata_general(ctx.h, int(qdata.shape[0]), int(qdata.shape[2]), _ptr(qdata), C.byref(h)), ctx.h)
+        g = cls(ctx, h)
+        g.ne, g.q1d = qdata.shape[0], 0
+        return g
 
     @classmethod
     def hex(cls, ctx, xe, attr, mesh_order, q1d, nodeB, nodeG, qw1d):
@@ -175,6 +193,27 @@ class Op:
         d, keep = _desc(kind, p, lsize, idx, orient, dof_map, Bo, Bc, Gc, coeff, assemble)
         h = C.c_void_p()
         _chk(lib().b2p_op_create(ctx.h, geom.h, C.byref(d), C.byref(h)), ctx.h)
+        return cls(ctx, h, lsize)
+
+    @classmethod
+    def create_dense(cls, ctx, geom, kind, lsize, idx, orient, interp, deriv, coeff, curl_orient=None):
+        """Dense-basis operator from FULL DofToQuad tables (native dof order)."""
+        keep = []
+        d = DenseOpDesc()
+        idx = _np(idx, np.int32)
+        d.kind, d.ne, d.P, d.lsize = int(kind), idx.shape[0], idx.shape[1], int(lsize)
+        tab = deriv if deriv is not None else interp
+        d.Q = int(np.asarray(tab).shape[1])
+        for name, arr, dt in (("idx", idx, np.int32), ("orient", orient, np.int8), ("curl_orient", curl_orient, np.int8),
+                              ("interp", interp, np.float64), ("deriv", deriv, np.float64)):
+            if arr is not None:
+                a = _np(arr, dt)
+                keep.append(a)
+                setattr(d, name, _ptr(a))
+        c = _np(coeff, np.float64)
+        d.coeff_ctx, d.coeff_ctx_bytes = _ptr(c), c.nbytes
+        h = C.c_void_p()
+        _chk(lib().b2p_op_create_dense(ctx.h, geom.h, C.byref(d), C.byref(h)), ctx.h)
         return cls(ctx, h, lsize)
 
     def coarsen(self, p, lsize, idx, orient, dof_map, Bo, Bc, Gc):

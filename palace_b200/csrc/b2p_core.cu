@@ -93,6 +93,7 @@ namespace b2p
 int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, int flags,
                 cudaStream_t s)
 {
+  if (op->dense) return launch_dense_apply(op, lidx, alpha, x, y, rg, s);
   const bool simple = flags & B2P_APPLY_SIMPLE_KERNEL;
   if (op->kind == B2P_H1_DIFFUSION) return simple ? launch_h1_hex_apply(op, lidx, alpha, x, y, rg, s) : launch_h1_hex_apply3(op, lidx, alpha, x, y, rg, s);
   if (simple) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
@@ -214,6 +215,29 @@ int b2p_geom_create_qdata(b2p_ctx *ctx, int ne, int q1d, const double *qdata, b2
   g->ctx = ctx;
   g->ne = ne;
   g->q1d = q1d;
+  g->Q = Q;
+  int rc;
+  if ((rc = upload(ctx, qd.data(), qd.size(), &g->qd))) return rc;
+  if ((rc = upload(ctx, attr.data(), attr.size(), &g->attr))) return rc;
+  *out = g;
+  return B2P_SUCCESS;
+}
+
+// General (non-tensor) quadrature: any element type; points in the caller's order.
+int b2p_geom_create_qdata_general(b2p_ctx *ctx, int ne, int Q, const double *qdata, b2p_geom **out)
+{
+  B2P_CHECK(ctx, ctx && out && qdata && ne > 0 && Q > 0, B2P_ERR_ARG, "b2p_geom_create_qdata_general: bad argument");
+  std::vector<double> qd((size_t)ne * 10 * Q);
+  std::vector<int32_t> attr(ne);
+  for (int e = 0; e < ne; e++)
+  {
+    attr[e] = (int32_t)qdata[(size_t)e * 11 * Q];
+    std::memcpy(&qd[(size_t)e * 10 * Q], &qdata[((size_t)e * 11 + 1) * Q], sizeof(double) * 10 * Q);
+  }
+  b2p_geom *g = new b2p_geom;
+  g->ctx = ctx;
+  g->ne = ne;
+  g->q1d = 0;
   g->Q = Q;
   int rc;
   if ((rc = upload(ctx, qd.data(), qd.size(), &g->qd))) return rc;
@@ -457,10 +481,74 @@ int b2p_op_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_op_desc *d, b2p_op **o
   return B2P_SUCCESS;
 }
 
+// Dense-basis operator on any element type (see b2p_dense.cu).
+int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d, b2p_op **out)
+{
+  B2P_CHECK(ctx, ctx && geom && d && out, B2P_ERR_ARG, "b2p_op_create_dense: null argument");
+  B2P_CHECK(ctx, d->kind >= B2P_CURLCURL && d->kind <= B2P_H1_DIFFUSION, B2P_ERR_ARG, "b2p_op_create_dense: bad kind %d", d->kind);
+  B2P_CHECK(ctx, geom->q1d == 0 && geom->Q == d->Q && geom->ne == d->ne, B2P_ERR_ARG,
+            "b2p_op_create_dense: needs a general geometry (b2p_geom_create_qdata_general) with matching ne / Q");
+  const bool need_u = (d->kind == B2P_ND_MASS || d->kind == B2P_CURLCURL_MASS), need_c = (d->kind != B2P_ND_MASS);
+  B2P_CHECK(ctx, (!need_u || d->interp) && (!need_c || d->deriv) && d->idx && d->lsize > 0 && d->P > 0, B2P_ERR_ARG,
+            "b2p_op_create_dense: missing tables / restriction");
+  b2p_op *op = new b2p_op;
+  op->ctx = ctx;
+  op->geom = geom;
+  geom->refcount++;
+  op->dense = true;
+  op->kind = d->kind;
+  op->p = 0;
+  op->q1d = 0;
+  op->ne = d->ne;
+  op->P = d->P;
+  op->lsize = d->lsize;
+  const int P = d->P, Q = d->Q;
+  op->dense_Ppad = (P + 7) & ~7;
+  int rows = 0;
+  if (need_u)
+  {
+    op->dense_row_u = rows;
+    rows += 3 * Q;
+  }
+  if (need_c)
+  {
+    op->dense_row_c = rows;
+    rows += 3 * Q;
+  }
+  op->dense_Rpad = (rows + 7) & ~7;
+  std::vector<double> T((size_t)op->dense_Rpad * op->dense_Ppad, 0.0);
+  for (int r = 0; r < 3 * Q; r++)
+    for (int i = 0; i < P; i++)
+    {
+      if (need_u) T[(size_t)(op->dense_row_u + r) * op->dense_Ppad + i] = d->interp[(size_t)r * P + i];
+      if (need_c) T[(size_t)(op->dense_row_c + r) * op->dense_Ppad + i] = d->deriv[(size_t)r * P + i];
+    }
+  b2p_op_desc rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.idx = d->idx;
+  rd.orient = d->curl_orient ? nullptr : d->orient;  // the tridiagonal matrix already carries the signs
+  rd.dof_map = nullptr;                              // native order
+  int rc;
+  if ((rc = build_restriction(op, &rd)) || (rc = upload(ctx, T.data(), T.size(), &op->dense_T)) ||
+      (rc = set_coeff(op, d->coeff_ctx, d->coeff_ctx_bytes)))
+  {
+    b2p_op_destroy(op);
+    return rc;
+  }
+  if (d->curl_orient && (rc = upload(ctx, d->curl_orient, (size_t)d->ne * P * 3, &op->curl_orient)))
+  {
+    b2p_op_destroy(op);
+    return rc;
+  }
+  *out = op;
+  return B2P_SUCCESS;
+}
+
 int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *d, b2p_op **out)
 {
   B2P_CHECK(fine ? fine->ctx : nullptr, fine && d && out, B2P_ERR_ARG, "b2p_op_coarsen: null argument");
   b2p_ctx *ctx = fine->ctx;
+  B2P_CHECK(ctx, !fine->dense, B2P_ERR_UNSUPPORTED, "b2p_op_coarsen: not available for dense-basis operators");
   B2P_CHECK(ctx, d->p >= 1 && d->p <= fine->p, B2P_ERR_ARG, "b2p_op_coarsen: coarse p=%d must be <= fine p=%d", d->p, fine->p);
   B2P_CHECK(ctx, d->idx && d->lsize > 0, B2P_ERR_ARG, "b2p_op_coarsen: missing restriction");
   b2p_op *op = new b2p_op;
@@ -564,6 +652,7 @@ int b2p_op_set_essential(b2p_op *op, const int32_t *ess_ldofs, int64_t n)
 int b2p_op_diag_add(b2p_op *op, double *diag, b2p_stream s)
 {
   if (!op || !diag) return B2P_ERR_ARG;
+  if (op->dense) return launch_dense_diag(op, diag, (cudaStream_t)s);
   if (op->kind == B2P_H1_DIFFUSION) return launch_h1_hex_diag(op, diag, (cudaStream_t)s);
   return launch_nd_hex_diag(op, diag, (cudaStream_t)s);
 }
@@ -585,6 +674,8 @@ int64_t b2p_op_algorithmic_bytes(b2p_op *op)
   if (!op) return 0;
   // x read once + y written once per unique dof, 4-byte index per element dof, q-data per point.
   const int64_t Q = op->geom->Q;
+  if (op->dense)  // + the tables once (L2 resident)
+    return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->PS + 80 * Q + 144) + 8 * (int64_t)op->dense_Rpad * op->dense_Ppad;
   const int64_t per_point = op->assembled ? op->aq_ncomp : 10;
   return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->PS + 8 * per_point * Q + (op->assembled ? 0 : 144));  // +144: per-element coefficient block
 }
@@ -596,6 +687,8 @@ void b2p_op_destroy(b2p_op *op)
   cudaFree(op->lidx);
   cudaFree(op->lidx_bc);
   cudaFree(op->tab);
+  cudaFree(op->dense_T);
+  cudaFree(op->curl_orient);
   if (op->parent)
   {
     b2p_op_destroy(op->parent);

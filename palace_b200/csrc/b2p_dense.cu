@@ -1,0 +1,295 @@
+// Dense-basis (non-tensor) element operator: the general path the reference takes for every
+// vector-valued element and every simplex (InitNonTensorBasis -> CeedBasisCreateHcurl,
+// /root/reference/palace/fem/libceed/basis.cpp:40-85,169-186): per element a dense
+// [3Q x P] interp and curl (or grad) table is applied, then the pointwise QFunction, then the
+// transposes. Native dof order, orientation by sign (restriction.cpp:281-297) or by the tridiagonal
+// "curl-oriented" matrix of ND tets/prisms with p >= 2 (restriction.cpp:301-368). The reference runs
+// this through MAGMA batched GEMM on GPUs; here the element batch is one FP64 tensor-core GEMM:
+//
+//   V[R x NEB] = T[R x P] * U[P x NEB]        (R = rows of interp + deriv tables, NEB = 8 elements)
+//   Y[P x NEB] = T^T[P x R] * D(V)[R x NEB]
+//
+// issued as mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): A fragments stream from the (L2-resident) table,
+// B fragments from the element vectors in shared memory, the 8 elements of the batch are the N
+// dimension. tcgen05 has no FP64 kind, so DMMA is the tensor path for double precision on sm_100a.
+// The sum-factorised hex kernels (b2p_hex_nd3.cu) do the same operator in O(p^4) and are ~4x faster;
+// this kernel is the fallback that covers every other element type MFEM can describe by tables.
+#include "b2p_internal.hpp"
+#include "b2p_qf.cuh"
+#include "b2p_contract.cuh"
+
+namespace b2p
+{
+
+namespace
+{
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct DenseParams
+{
+  const int32_t *lidx;        // [ne][PS] signed native restriction
+  const int8_t *curl_orient;  // [ne][P][3] row-major tridiagonal or null
+  const double *T;            // [Rpad][Ppad] stacked tables (interp rows first when present, then deriv), zero padded
+  const double *qd;           // [ne][10][Q] geometry, plain point order
+  const double *ecoef;        // [ne][18]
+  const double *x;
+  double *y;
+  double alpha;
+  VSplit sp;
+  int ne, P, PS, Ppad, Q, Rpad, row_u, row_c;  // row_u / row_c: first row of the interp / deriv block (-1: absent)
+  int kind;
+};
+
+constexpr int NEB = 8;
+
+__global__ void __launch_bounds__(256) dense_apply_kernel(DenseParams prm)
+{
+  extern __shared__ double sm[];
+  double *U = sm;                       // [Ppad][NEB]
+  double *V = U + prm.Ppad * NEB;       // [Rpad][NEB]
+  double *X = V + prm.Rpad * NEB;       // [P][NEB] raw gathered values (curl-oriented restriction only)
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int e0 = blockIdx.x * NEB;
+  const int P = prm.P, Q = prm.Q;
+
+  // ---- restriction (E): native order, sign or tridiagonal orientation ----
+  for (int w = tid; w < prm.Ppad * NEB; w += blockDim.x)
+  {
+    const int i = w / NEB, e = w % NEB;
+    double v = 0.0;
+    if (i < P && e0 + e < prm.ne)
+    {
+      const int32_t gi = prm.lidx[(size_t)(e0 + e) * prm.PS + i];
+      if (prm.curl_orient)
+        v = (gi == B2P_SKIP_IDX) ? 0.0 : __ldg(split_src(prm.x, prm.sp, gi >= 0 ? gi : -1 - gi));
+      else
+        v = gather2(prm.x, prm.sp, gi);
+    }
+    (prm.curl_orient ? X : U)[w] = v;
+  }
+  if (prm.curl_orient)
+  {
+    __syncthreads();
+    for (int w = tid; w < prm.Ppad * NEB; w += blockDim.x)
+    {
+      const int i = w / NEB, e = w % NEB;
+      double v = 0.0;
+      if (i < P && e0 + e < prm.ne)
+      {
+        const int8_t *co = prm.curl_orient + ((size_t)(e0 + e) * P + i) * 3;
+        v = (double)co[1] * X[i * NEB + e];
+        if (i > 0) v += (double)co[0] * X[(i - 1) * NEB + e];
+        if (i < P - 1) v += (double)co[2] * X[(i + 1) * NEB + e];
+      }
+      U[w] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- V = T U : m-tiles over table rows, k over dofs ----
+  for (int mt = wid; mt < prm.Rpad / 8; mt += nw)
+  {
+    double c0 = 0.0, c1 = 0.0;
+    const double *Arow = prm.T + (size_t)(mt * 8 + lane / 4) * prm.Ppad + (lane % 4);
+    const double *Bcol = U + (lane % 4) * NEB + lane / 4;
+    for (int k0 = 0; k0 < prm.Ppad; k0 += 4) dmma884(c0, c1, __ldg(Arow + k0), Bcol[k0 * NEB]);
+    double *o = V + (mt * 8 + lane / 4) * NEB + 2 * (lane % 4);
+    o[0] = c0;
+    o[1] = c1;
+  }
+  __syncthreads();
+
+  // ---- D at the quadrature points (in place) ----
+  const bool MASS = (prm.kind == B2P_ND_MASS || prm.kind == B2P_CURLCURL_MASS);
+  const bool CURL = (prm.kind == B2P_CURLCURL || prm.kind == B2P_CURLCURL_MASS);
+  const bool H1 = (prm.kind == B2P_H1_DIFFUSION);
+  for (int w = tid; w < Q * NEB; w += blockDim.x)
+  {
+    const int iq = w / NEB, e = w % NEB;
+    if (e0 + e >= prm.ne) continue;
+    const double *g = prm.qd + (size_t)(e0 + e) * 10 * Q + iq;
+    const double *C = prm.ecoef + (size_t)(e0 + e) * 18;
+    const double wdetJ = prm.alpha * g[0];
+    double A[9], Cm[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) A[i] = g[(1 + i) * Q];
+    if (MASS || H1)
+    {
+      const int r0 = MASS ? prm.row_u : prm.row_c;
+      double u[3] = {V[(r0 + iq) * NEB + e], V[(r0 + Q + iq) * NEB + e], V[(r0 + 2 * Q + iq) * NEB + e]}, v[3];
+#pragma unroll
+      for (int i = 0; i < 9; i++) Cm[i] = C[i];
+      AtCAx(A, Cm, u, wdetJ, v);
+      V[(r0 + iq) * NEB + e] = v[0];
+      V[(r0 + Q + iq) * NEB + e] = v[1];
+      V[(r0 + 2 * Q + iq) * NEB + e] = v[2];
+    }
+    if (CURL)
+    {
+      const int r0 = prm.row_c;
+      double c[3] = {V[(r0 + iq) * NEB + e], V[(r0 + Q + iq) * NEB + e], V[(r0 + 2 * Q + iq) * NEB + e]}, v[3], Jd[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) Cm[i] = C[9 + i];
+      cofactor33(A, Jd);
+      AtCAx(Jd, Cm, c, wdetJ, v);
+      V[(r0 + iq) * NEB + e] = v[0];
+      V[(r0 + Q + iq) * NEB + e] = v[1];
+      V[(r0 + 2 * Q + iq) * NEB + e] = v[2];
+    }
+  }
+  __syncthreads();
+
+  // ---- Y = T^T V : m-tiles over dofs, k over table rows; result overwrites U ----
+  for (int mt = wid; mt < prm.Ppad / 8; mt += nw)
+  {
+    double c0 = 0.0, c1 = 0.0;
+    const double *Acol = prm.T + (size_t)(lane % 4) * prm.Ppad + mt * 8 + lane / 4;
+    const double *Bcol = V + (lane % 4) * NEB + lane / 4;
+    for (int k0 = 0; k0 < prm.Rpad; k0 += 4) dmma884(c0, c1, __ldg(Acol + (size_t)k0 * prm.Ppad), Bcol[k0 * NEB]);
+    double *o = U + (mt * 8 + lane / 4) * NEB + 2 * (lane % 4);
+    o[0] = c0;
+    o[1] = c1;
+  }
+  __syncthreads();
+
+  // ---- E^T ----
+  if (prm.curl_orient)
+  {
+    for (int w = tid; w < prm.Ppad * NEB; w += blockDim.x)
+    {
+      const int i = w / NEB, e = w % NEB;
+      double v = 0.0;
+      if (i < P && e0 + e < prm.ne)
+      {
+        const int8_t *co = prm.curl_orient + ((size_t)(e0 + e) * P) * 3;
+        v = (double)co[3 * i + 1] * U[i * NEB + e];
+        if (i > 0) v += (double)co[3 * (i - 1) + 2] * U[(i - 1) * NEB + e];
+        if (i < P - 1) v += (double)co[3 * (i + 1) + 0] * U[(i + 1) * NEB + e];
+      }
+      X[w] = v;
+    }
+    __syncthreads();
+  }
+  const double *src = prm.curl_orient ? X : U;
+  for (int w = tid; w < P * NEB; w += blockDim.x)
+  {
+    const int i = w / NEB, e = w % NEB;
+    if (e0 + e >= prm.ne) continue;
+    const int32_t gi = prm.lidx[(size_t)(e0 + e) * prm.PS + i];
+    if (prm.curl_orient)
+    {
+      if (gi != B2P_SKIP_IDX) scatter2(prm.y, prm.sp, gi >= 0 ? gi : -1 - gi, src[w]);
+    }
+    else
+      scatter2(prm.y, prm.sp, gi, src[w]);
+  }
+}
+
+// diag[g(i)] += sum_q T(:,q,i)^T D_q T(:,q,i)   (exact for sign orientation; for the tridiagonal
+// orientation this is libCEED's approximation the reference accepts, test-libceed.cpp:358-372)
+__global__ void dense_diag_kernel(DenseParams prm)
+{
+  const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (size_t)prm.ne * prm.P) return;
+  const int e = (int)(w / prm.P), i = (int)(w % prm.P), Q = prm.Q;
+  const bool MASS = (prm.kind == B2P_ND_MASS || prm.kind == B2P_CURLCURL_MASS);
+  const bool CURL = (prm.kind == B2P_CURLCURL || prm.kind == B2P_CURLCURL_MASS);
+  const bool H1 = (prm.kind == B2P_H1_DIFFUSION);
+  const double *C = prm.ecoef + (size_t)e * 18;
+  double C0[9], C1[9];
+  for (int t = 0; t < 9; t++)
+  {
+    C0[t] = C[t];
+    C1[t] = C[9 + t];
+  }
+  double s = 0.0;
+  for (int iq = 0; iq < Q; iq++)
+  {
+    const double *g = prm.qd + (size_t)e * 10 * Q + iq;
+    double A[9], v[3];
+    for (int t = 0; t < 9; t++) A[t] = g[(1 + t) * Q];
+    if (MASS || H1)
+    {
+      const int r0 = MASS ? prm.row_u : prm.row_c;
+      double u[3] = {prm.T[(size_t)(r0 + iq) * prm.Ppad + i], prm.T[(size_t)(r0 + Q + iq) * prm.Ppad + i],
+                     prm.T[(size_t)(r0 + 2 * Q + iq) * prm.Ppad + i]};
+      AtCAx(A, C0, u, g[0], v);
+      s += u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
+    }
+    if (CURL)
+    {
+      const int r0 = prm.row_c;
+      double c[3] = {prm.T[(size_t)(r0 + iq) * prm.Ppad + i], prm.T[(size_t)(r0 + Q + iq) * prm.Ppad + i],
+                     prm.T[(size_t)(r0 + 2 * Q + iq) * prm.Ppad + i]}, Jd[9];
+      cofactor33(A, Jd);
+      AtCAx(Jd, C1, c, g[0], v);
+      s += c[0] * v[0] + c[1] * v[1] + c[2] * v[2];
+    }
+  }
+  int gi = prm.lidx[(size_t)e * prm.PS + i];
+  if (gi == B2P_SKIP_IDX) return;
+  if (gi < 0) gi = -1 - gi;
+  atomicAdd(prm.y + gi, s);
+}
+
+DenseParams make_params(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg)
+{
+  DenseParams p;
+  const int e_off = rg.e_off, e_cnt = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
+  p.lidx = lidx + (size_t)e_off * op->PS;
+  p.curl_orient = op->curl_orient ? op->curl_orient + (size_t)e_off * op->P * 3 : nullptr;
+  p.T = op->dense_T;
+  p.qd = op->geom->qd + (size_t)e_off * 10 * op->geom->Q;
+  p.ecoef = op->ecoef + 18 * (size_t)e_off;
+  p.x = x;
+  p.y = y;
+  p.alpha = alpha;
+  p.sp.n_owned = rg.n_owned < 0 ? op->lsize : rg.n_owned;
+  p.sp.xg = rg.xg;
+  p.sp.yg = rg.yg;
+  p.ne = e_cnt;
+  p.P = op->P;
+  p.PS = op->PS;
+  p.Ppad = op->dense_Ppad;
+  p.Q = op->geom->Q;
+  p.Rpad = op->dense_Rpad;
+  p.row_u = op->dense_row_u;
+  p.row_c = op->dense_row_c;
+  p.kind = op->kind;
+  return p;
+}
+
+}  // namespace
+
+int launch_dense_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg,
+                       cudaStream_t s)
+{
+  DenseParams prm = make_params(op, lidx, alpha, x, y, rg);
+  if (prm.ne <= 0) return B2P_SUCCESS;
+  const size_t shmem = sizeof(double) * NEB * ((size_t)prm.Ppad + prm.Rpad + (op->curl_orient ? prm.Ppad : 0));
+  static size_t configured = 0;
+  if (shmem > configured)
+  {
+    B2P_CHECK(op->ctx, shmem <= 227 * 1024, B2P_ERR_UNSUPPORTED, "dense operator: element too large for shared memory (%zu B)", shmem);
+    B2P_CUDA(op->ctx, cudaFuncSetAttribute(dense_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    configured = shmem;
+  }
+  dense_apply_kernel<<<(prm.ne + NEB - 1) / NEB, 256, shmem, s>>>(prm);
+  B2P_CUDA(op->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+
+int launch_dense_diag(b2p_op *op, double *diag, cudaStream_t s)
+{
+  DenseParams prm = make_params(op, op->lidx, 1.0, nullptr, diag, ApplyRange());
+  const size_t total = (size_t)op->ne * op->P;
+  dense_diag_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(prm);
+  B2P_CUDA(op->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+
+}  // namespace b2p

@@ -73,7 +73,7 @@ __host__ __device__ inline int qslot_of(int q, int iq) { return qslot(q, iq % q,
 struct b2p_geom
 {
   b2p_ctx *ctx = nullptr;
-  int ne = 0, q1d = 0, Q = 0;
+  int ne = 0, q1d = 0, Q = 0;  // q1d == 0: general (non-tensor) point set in plain order
   double *qd = nullptr;
   int32_t *attr = nullptr;
   int refcount = 1;
@@ -104,6 +104,11 @@ struct b2p_op
   double *aq = nullptr;
   int aq_ncomp = 0;
   int64_t aq_estride = 0;  // doubles per element (even, so every element block is 16-byte aligned for TMA)
+  // dense-basis (non-tensor) operators (b2p_dense.cu)
+  bool dense = false;
+  double *dense_T = nullptr;   // [Rpad][Ppad] stacked interp/deriv tables, zero padded
+  int dense_Ppad = 0, dense_Rpad = 0, dense_row_u = -1, dense_row_c = -1;
+  int8_t *curl_orient = nullptr;  // [ne][P][3] tridiagonal orientation (ND tets/prisms p >= 2) or null
   bool owns_coeff = true;  // coarsened operators share the fine operator's coefficient arrays
   b2p_op *parent = nullptr;
   int refcount = 1;
@@ -148,6 +153,9 @@ int launch_h1_hex_apply3(b2p_op *op, const int32_t *lidx, double alpha, const do
                          cudaStream_t s);
 int launch_h1_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
 int launch_assemble_qdata(b2p_op *op, cudaStream_t s);
+int launch_dense_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg,
+                       cudaStream_t s);
+int launch_dense_diag(b2p_op *op, double *diag, cudaStream_t s);
 int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, const double *d_B, const double *d_G,
                     const double *d_qw, double *d_qd, cudaStream_t s);
 }  // namespace b2p
