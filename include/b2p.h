@@ -265,6 +265,36 @@ int b2p_solver_stats(b2p_solver *s, int *its, double *initial_res, double *final
 int b2p_solver_lambda_max(b2p_solver *s, double *out); /* Chebyshev: estimated lambda_max(D^-1 A) * sf_max */
 void b2p_solver_destroy(b2p_solver *s);
 
+/* ---- complex-valued operators and Krylov solvers on split (real, imag) vectors ---------------------
+ * Palace's ComplexVector is two real vectors (linalg/vector.hpp:23-27); every entry takes the two device
+ * pointers separately. Inner product convention Dot(x, y) = y^H x (linalg/vector.cpp:674-685). */
+typedef struct b2p_coperator b2p_coperator;
+typedef struct b2p_csolver b2p_csolver;
+int b2p_vec_cdot(b2p_ctx *ctx, int64_t n, const double *xr, const double *xi, const double *yr, const double *yi, double out[2]);
+int b2p_vec_caxpy(b2p_ctx *ctx, int64_t n, double ar, double ai, const double *xr, const double *xi, double *yr, double *yi);
+/* A = sum_i (coef_re[i] + i coef_im[i]) * op_i with real partially assembled op_i: ComplexParOperator over
+ * BuildParSumOperator / ComplexWrapperOperator (linalg/rap.cpp:481-517,843-919, linalg/operator.cpp:98-134).
+ * Single partition only in this round (tsize == lsize). */
+int b2p_coperator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coef_re,
+                      const double *coef_im, const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_coperator **out);
+int b2p_coperator_mult(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi);
+int b2p_coperator_mult_hermitian_transpose(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi);
+int b2p_coperator_add_mult(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi, double ar, double ai);
+int b2p_coperator_assemble_diagonal(b2p_coperator *A, double *dr, double *di);
+void b2p_coperator_destroy(b2p_coperator *A);
+/* A real preconditioner (any b2p_solver, e.g. the multigrid) applied to the real and imaginary parts: the
+ * "PCMatReal" configuration (models/spaceoperator.cpp:1098-1105, utils/configfile.hpp:1051). */
+int b2p_csolver_real_pc(b2p_ctx *ctx, b2p_solver *real_pc, b2p_csolver **out);
+/* CgSolver / GmresSolver / FgmresSolver<ComplexOperator> (linalg/iterative.cpp:361-871; type 0/1/2) */
+int b2p_csolver_krylov(b2p_ctx *ctx, int type, b2p_csolver **out);
+int b2p_csolver_krylov_config(b2p_csolver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side);
+int b2p_csolver_set_operator(b2p_csolver *s, b2p_coperator *A);
+int b2p_csolver_set_preconditioner(b2p_csolver *s, b2p_csolver *pc);
+int b2p_csolver_set_initial_guess(b2p_csolver *s, int flag);
+int b2p_csolver_mult(b2p_csolver *s, const double *br, const double *bi, double *xr, double *xi);
+int b2p_csolver_stats(b2p_csolver *s, int *its, double *initial_res, double *final_res, int *converged);
+void b2p_csolver_destroy(b2p_csolver *s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -312,3 +312,111 @@ def gmres(A, b, B=None, rel_tol=1e-6, abs_tol=0.0, max_it=100, max_dim=None, ort
         restart += 1
     hist.append(beta)
     return x, it, hist
+
+
+# ---- complex variants (OperType = ComplexOperator) ------------------------------------------------
+def _cplane_rotation(dx, dy):
+    """iterative.cpp:112-226 (well-scaled branches) -> (cs real, sn complex)."""
+    if dy == 0.0:
+        return 1.0, 0.0 + 0.0j
+    if dx == 0.0:
+        return 0.0, np.conj(dy) / abs(dy)
+    dx2, dy2 = abs(dx) ** 2, abs(dy) ** 2
+    dz2 = dx2 + dy2
+    return np.sqrt(dx2 / dz2), np.conj(dy) * (dx / np.sqrt(dx2 * dz2))
+
+
+def _capply_rot(dx, dy, cs, sn):
+    return cs * dx + sn * dy, -np.conj(sn) * dx + cs * dy
+
+
+def corthogonalize(kind, V, w):
+    """orthog.hpp:41-89 with Dot(w, V_j) = V_j^H w (vector.cpp:674-685)."""
+    w = w.copy()
+    m = len(V)
+    H = np.zeros(m, dtype=complex)
+    if kind == 0:
+        for j in range(m):
+            H[j] = np.vdot(V[j], w)
+            w -= H[j] * V[j]
+    else:
+        H = np.array([np.vdot(V[j], w) for j in range(m)])
+        for j in range(m):
+            w -= H[j] * V[j]
+        if kind == 2:
+            dH = np.array([np.vdot(V[j], w) for j in range(m)])
+            for j in range(m):
+                w -= dH[j] * V[j]
+            H = H + dH
+    return H, w
+
+
+def cgmres(A, b, B=None, rel_tol=1e-6, abs_tol=0.0, max_it=100, max_dim=None, orthog=0, flexible=False, right=True):
+    """GmresSolver / FgmresSolver<ComplexOperator> (iterative.cpp:544-871), zero initial guess."""
+    n = b.size
+    mdim = max_it if max_dim is None or max_dim < 0 else max_dim
+    x = np.zeros(n, dtype=complex)
+    it, restart = 0, 0
+    right = right or flexible
+    beta, eps, converged = 0.0, 0.0, False
+    while it < max_it:
+        ig = restart > 0
+        if B and not right:
+            r = B(b - A @ x) if ig else B(b)
+        else:
+            r = (b - A @ x) if ig else b.astype(complex)
+        true_beta = np.linalg.norm(r)
+        if it == 0:
+            eps = max(rel_tol * true_beta, abs_tol)
+        beta = true_beta
+        if beta < eps:
+            converged = True
+            break
+        V, Z = [r / beta], []
+        H = np.zeros((mdim + 1, mdim), dtype=complex)
+        s = np.zeros(mdim + 1, dtype=complex)
+        cs, sn = np.zeros(mdim + 1), np.zeros(mdim + 1, dtype=complex)
+        s[0] = beta
+        j = 0
+        while True:
+            if B and not right:
+                w = B(A @ V[j])
+            elif B:
+                zj = B(V[j])
+                if flexible:
+                    Z.append(zj)
+                w = A @ zj
+            else:
+                w = A @ V[j]
+            Hj, w = corthogonalize(orthog, V, w)
+            H[: j + 1, j] = Hj
+            H[j + 1, j] = np.linalg.norm(w)
+            V.append(w / H[j + 1, j])
+            for k in range(j):
+                H[k, j], H[k + 1, j] = _capply_rot(H[k, j], H[k + 1, j], cs[k], sn[k])
+            cs[j], sn[j] = _cplane_rotation(H[j, j], H[j + 1, j])
+            H[j, j], H[j + 1, j] = _capply_rot(H[j, j], H[j + 1, j], cs[j], sn[j])
+            s[j], s[j + 1] = _capply_rot(s[j], s[j + 1], cs[j], sn[j])
+            beta = abs(s[j + 1])
+            converged = beta < eps
+            if converged or j + 1 == mdim or it + 1 == max_it:
+                it += 1
+                break
+            j += 1
+            it += 1
+        for i in range(j, -1, -1):
+            s[i] /= H[i, i]
+            for k in range(i - 1, -1, -1):
+                s[k] -= H[k, i] * s[i]
+        if flexible:
+            for k in range(j + 1):
+                x += s[k] * Z[k]
+        elif (not B) or (not right):
+            for k in range(j + 1):
+                x += s[k] * V[k]
+        else:
+            x += B(sum(s[k] * V[k] for k in range(j + 1)))
+        if converged:
+            break
+        restart += 1
+    return x, it, converged

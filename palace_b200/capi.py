@@ -523,3 +523,93 @@ class Solver:
         out = C.c_double()
         _chk(lib().b2p_solver_lambda_max(self.h, C.byref(out)), self.ctx.h)
         return out.value
+
+
+# ------------------------------------------------------------------------------------------------
+# Complex operators / solvers on split (real, imag) vectors
+# ------------------------------------------------------------------------------------------------
+
+
+def vec_cdot(ctx, xr, xi, yr, yi):
+    out = (C.c_double * 2)()
+    _chk(lib().b2p_vec_cdot(ctx.h, C.c_int64(xr.numel()), _vp(xr), _vp(xi), _vp(yr), _vp(yi), out), ctx.h)
+    return complex(out[0], out[1])
+
+
+def vec_caxpy(ctx, a, xr, xi, yr, yi):
+    a = complex(a)
+    _chk(lib().b2p_vec_caxpy(ctx.h, C.c_int64(xr.numel()), C.c_double(a.real), C.c_double(a.imag), _vp(xr), _vp(xi), _vp(yr), _vp(yi)), ctx.h)
+
+
+class ComplexOperator:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    @classmethod
+    def par(cls, ctx, tsize, lsize, ops, coefs, ess_tdofs=None, diag_policy=1):
+        n = len(ops)
+        arr = (C.c_void_p * n)(*[o.h for o in ops])
+        cr = _np([complex(c).real for c in coefs], np.float64)
+        ci = _np([complex(c).imag for c in coefs], np.float64)
+        ess = _np(ess_tdofs if ess_tdofs is not None else np.zeros(0), np.int32)
+        h = C.c_void_p()
+        _chk(lib().b2p_coperator_par(ctx.h, C.c_int64(tsize), C.c_int64(lsize), n, arr, _ptr(cr), _ptr(ci), _ptr(ess), C.c_int64(ess.size),
+                                     int(diag_policy), C.byref(h)), ctx.h)
+        o = cls(ctx, h)
+        o._keep = list(ops)
+        return o
+
+    def mult(self, xr, xi, yr, yi):
+        _chk(lib().b2p_coperator_mult(self.h, _vp(xr), _vp(xi), _vp(yr), _vp(yi)), self.ctx.h)
+
+    def mult_hermitian_transpose(self, xr, xi, yr, yi):
+        _chk(lib().b2p_coperator_mult_hermitian_transpose(self.h, _vp(xr), _vp(xi), _vp(yr), _vp(yi)), self.ctx.h)
+
+    def add_mult(self, xr, xi, yr, yi, a):
+        a = complex(a)
+        _chk(lib().b2p_coperator_add_mult(self.h, _vp(xr), _vp(xi), _vp(yr), _vp(yi), C.c_double(a.real), C.c_double(a.imag)), self.ctx.h)
+
+    def assemble_diagonal(self, dr, di):
+        _chk(lib().b2p_coperator_assemble_diagonal(self.h, _vp(dr), _vp(di)), self.ctx.h)
+
+
+class ComplexSolver:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+        self._keep = []
+
+    @classmethod
+    def real_pc(cls, ctx, real_solver: Solver):
+        h = C.c_void_p()
+        _chk(lib().b2p_csolver_real_pc(ctx.h, real_solver.h, C.byref(h)), ctx.h)
+        s = cls(ctx, h)
+        s._keep.append(real_solver)
+        return s
+
+    @classmethod
+    def krylov(cls, ctx, kind, rel_tol=1e-6, abs_tol=0.0, max_it=100, max_dim=-1, orthog=MGS, pc_side=PC_RIGHT):
+        h = C.c_void_p()
+        _chk(lib().b2p_csolver_krylov(ctx.h, int(kind), C.byref(h)), ctx.h)
+        _chk(lib().b2p_csolver_krylov_config(h, C.c_double(rel_tol), C.c_double(abs_tol), int(max_it), int(max_dim), int(orthog),
+                                             int(pc_side)), ctx.h)
+        return cls(ctx, h)
+
+    def set_operator(self, A: ComplexOperator):
+        self._keep.append(A)
+        _chk(lib().b2p_csolver_set_operator(self.h, A.h), self.ctx.h)
+
+    def set_preconditioner(self, pc):
+        self._keep.append(pc)
+        _chk(lib().b2p_csolver_set_preconditioner(self.h, pc.h if pc else None), self.ctx.h)
+
+    def set_initial_guess(self, flag):
+        _chk(lib().b2p_csolver_set_initial_guess(self.h, int(flag)), self.ctx.h)
+
+    def mult(self, br, bi, xr, xi):
+        _chk(lib().b2p_csolver_mult(self.h, _vp(br), _vp(bi), _vp(xr), _vp(xi)), self.ctx.h)
+
+    def stats(self):
+        its, conv = C.c_int(), C.c_int()
+        r0, r1 = C.c_double(), C.c_double()
+        _chk(lib().b2p_csolver_stats(self.h, C.byref(its), C.byref(r0), C.byref(r1), C.byref(conv)), self.ctx.h)
+        return dict(its=its.value, initial_res=r0.value, final_res=r1.value, converged=bool(conv.value))

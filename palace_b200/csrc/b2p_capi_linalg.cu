@@ -19,6 +19,11 @@ struct b2p_solver
   bool owned_elsewhere = false;
 };
 
+namespace b2p
+{
+Solver *solver_of(b2p_solver *s) { return s ? s->s.get() : nullptr; }
+}  // namespace b2p
+
 #define B2P_TRY(ctx, stmt)                                   \
   do                                                         \
   {                                                          \

@@ -1,0 +1,783 @@
+// Complex-valued operators and Krylov solvers on split (real, imag) device vectors, as Palace
+// represents them (ComplexVector = two mfem::Vectors, /root/reference/palace/linalg/vector.hpp:23-27):
+//   ComplexParOperator   = ComplexParOperator over ComplexWrapperOperator / BuildParSumOperator with complex
+//                          coefficients (/root/reference/palace/linalg/rap.cpp:481-517,843-919,
+//                          /root/reference/palace/linalg/operator.cpp:98-134): A = sum_i (c_i^r + i c_i^i) A_i
+//                          with real partially assembled A_i
+//   RealPcSolver         = a real preconditioner applied to the real and imaginary parts, i.e. the
+//                          "PCMatReal" configuration (/root/reference/palace/models/spaceoperator.cpp:1098-1105)
+//   ComplexIterativeSolver = CgSolver / GmresSolver / FgmresSolver<ComplexOperator>
+//                          (/root/reference/palace/linalg/iterative.cpp:361-871, complex Givens :112-226)
+// Inner product convention: Dot(x, y) = y^H x (vector.cpp:674-685); Gram-Schmidt calls dot(w, V_j) (orthog.hpp:48-49).
+#include <complex>
+
+#include "b2p_linalg.hpp"
+
+namespace b2p
+{
+
+using cplx = std::complex<double>;
+
+namespace
+{
+constexpr int NT = 256;
+constexpr int RED_BLOCKS = 296;
+constexpr int MAXM = 4;  // complex vectors per multi-dot pass
+
+struct CVecList
+{
+  const double *re[MAXM], *im[MAXM];
+};
+
+// out[2j] = sum wr*vr + wi*vi ; out[2j+1] = sum wi*vr - wr*vi   (= V_j^H w)
+__global__ void __launch_bounds__(NT) cmulti_dot_kernel(CVecList V, const double *__restrict__ wr, const double *__restrict__ wi, int64_t n,
+                                                        int m, double *part)
+{
+  double acc[2 * MAXM];
+#pragma unroll
+  for (int j = 0; j < 2 * MAXM; j++) acc[j] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const double a = wr[i], b = wi[i];
+#pragma unroll
+    for (int j = 0; j < MAXM; j++)
+      if (j < m)
+      {
+        const double vr = V.re[j][i], vi = V.im[j][i];
+        acc[2 * j] += a * vr + b * vi;
+        acc[2 * j + 1] += b * vr - a * vi;
+      }
+  }
+  __shared__ double sh[2 * MAXM][NT / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 2 * MAXM; j++)
+  {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[j][wid] = v;
+  }
+  __syncthreads();
+  if (wid == 0)
+  {
+#pragma unroll
+    for (int j = 0; j < 2 * MAXM; j++)
+    {
+      double v = lane < NT / 32 ? sh[j][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) part[(size_t)j * RED_BLOCKS + blockIdx.x] = v;
+    }
+  }
+}
+
+__global__ void creduce_kernel(const double *part, int nblocks, double *out)
+{
+  const int j = blockIdx.x;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 32) v += part[(size_t)j * RED_BLOCKS + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (threadIdx.x == 0) out[j] = v;
+}
+
+// w += sign * sum_j (cr_j + i ci_j) V_j
+__global__ void cmulti_axpy_kernel(CVecList V, const double *__restrict__ coef, int m, double sign, double *__restrict__ wr,
+                                   double *__restrict__ wi, int64_t n)
+{
+  __shared__ double sc[2 * MAXM];
+  if (threadIdx.x < 2 * m) sc[threadIdx.x] = sign * coef[threadIdx.x];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    double a = wr[i], b = wi[i];
+    for (int j = 0; j < m; j++)
+    {
+      const double vr = V.re[j][i], vi = V.im[j][i];
+      a += sc[2 * j] * vr - sc[2 * j + 1] * vi;
+      b += sc[2 * j + 1] * vr + sc[2 * j] * vi;
+    }
+    wr[i] = a;
+    wi[i] = b;
+  }
+}
+
+inline int grid_for(b2p_ctx *c, int64_t n)
+{
+  const int64_t want = (n + 2 * NT - 1) / (2 * NT), cap = (int64_t)c->sm_count * 8;
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ complex vector ops
+struct CPtr
+{
+  double *re, *im;
+};
+struct CCPtr
+{
+  const double *re, *im;
+};
+
+void cmulti_dot(b2p_ctx *c, int m, const CCPtr *V, CCPtr w, int64_t n, cplx *out)
+{
+  double *part = c->d_red, *res = c->d_red + (size_t)2 * MAXM * RED_BLOCKS;
+  for (int j0 = 0; j0 < m; j0 += MAXM)
+  {
+    const int mm = std::min(MAXM, m - j0);
+    CVecList L;
+    for (int j = 0; j < MAXM; j++)
+    {
+      L.re[j] = j < mm ? V[j0 + j].re : nullptr;
+      L.im[j] = j < mm ? V[j0 + j].im : nullptr;
+    }
+    cmulti_dot_kernel<<<RED_BLOCKS, NT, 0, c->stream>>>(L, w.re, w.im, n, mm, part);
+    creduce_kernel<<<2 * mm, 32, 0, c->stream>>>(part, RED_BLOCKS, res);
+    if (c->nranks > 1 && c->comm) b2p_allreduce_sum(c, res, 2 * mm);
+    cudaMemcpyAsync(c->h_red, res, sizeof(double) * 2 * mm, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    for (int j = 0; j < mm; j++) out[j0 + j] = cplx(c->h_red[2 * j], c->h_red[2 * j + 1]);
+  }
+}
+
+cplx cdot(b2p_ctx *c, CCPtr x, CCPtr y, int64_t n)  // y^H x
+{
+  cplx out;
+  cmulti_dot(c, 1, &y, x, n, &out);
+  return out;
+}
+double cnorm(b2p_ctx *c, CCPtr x, int64_t n) { return std::sqrt(std::abs(cdot(c, x, x, n).real())); }
+
+void cmulti_axpy(b2p_ctx *c, int m, const cplx *coef, const CCPtr *V, CPtr w, int64_t n, double sign)
+{
+  double *dcoef = c->d_red + (size_t)2 * MAXM * RED_BLOCKS + 2 * MAXM;
+  for (int j0 = 0; j0 < m; j0 += MAXM)
+  {
+    const int mm = std::min(MAXM, m - j0);
+    CVecList L;
+    double h[2 * MAXM];
+    for (int j = 0; j < MAXM; j++)
+    {
+      L.re[j] = j < mm ? V[j0 + j].re : nullptr;
+      L.im[j] = j < mm ? V[j0 + j].im : nullptr;
+      if (j < mm)
+      {
+        h[2 * j] = coef[j0 + j].real();
+        h[2 * j + 1] = coef[j0 + j].imag();
+      }
+    }
+    cudaMemcpyAsync(dcoef, h, sizeof(double) * 2 * mm, cudaMemcpyHostToDevice, c->stream);
+    cudaStreamSynchronize(c->stream);  // h lives on this stack frame
+    cmulti_axpy_kernel<<<grid_for(c, n), NT, 0, c->stream>>>(L, dcoef, mm, sign, w.re, w.im, n);
+  }
+}
+void caxpy(b2p_ctx *c, cplx a, CCPtr x, CPtr y, int64_t n) { cmulti_axpy(c, 1, &a, &x, y, n, 1.0); }
+
+// ------------------------------------------------------------------------------------ ComplexOperator
+class ComplexOperator
+{
+public:
+  b2p_ctx *ctx;
+  int64_t n;
+  ComplexOperator(b2p_ctx *c, int64_t n_) : ctx(c), n(n_) {}
+  virtual ~ComplexOperator() = default;
+  virtual void Mult(CCPtr x, CPtr y) const = 0;
+  virtual void MultHermitianTranspose(CCPtr x, CPtr y) const = 0;
+  virtual void AssembleDiagonal(CPtr d) const = 0;
+  void AddMult(CCPtr x, CPtr y, cplx a) const
+  {
+    if (tmp_.n != 2 * n) tmp_.resize(ctx, 2 * n);
+    CPtr t{tmp_.p, tmp_.p + n};
+    Mult(x, t);
+    caxpy(ctx, a, CCPtr{t.re, t.im}, y, n);
+  }
+
+protected:
+  mutable DVec tmp_;
+};
+
+class ComplexParOperator : public ComplexOperator
+{
+public:
+  struct Term
+  {
+    b2p_op *op;
+    double cr, ci;
+  };
+  ComplexParOperator(b2p_ctx *c, int64_t tsize, const std::vector<Term> &terms_, const int32_t *ess, int64_t n_ess_, int diag_policy_)
+    : ComplexOperator(c, tsize), terms(terms_), n_ess(n_ess_), diag_policy(diag_policy_)
+  {
+    if (n_ess > 0) upload(c, ess, (size_t)n_ess, &d_ess);
+    for (auto &t : terms)
+      if (!t.op->lidx_bc) b2p_op_set_essential(t.op, ess, n_ess);
+  }
+  ~ComplexParOperator() override { cudaFree(d_ess); }
+
+  // operator.cpp:98-134 with A = sum_i c_i A_i: y_r = sum (c^r A x_r - c^i A x_i), y_i = sum (c^i A x_r + c^r A x_i);
+  // essential rows as in ComplexParOperator::Mult (rap.cpp:481-517)
+  void apply(CCPtr x, CPtr y, bool herm) const
+  {
+    cudaStream_t s = ctx->stream;
+    vec::set(ctx, y.re, n, 0.0);
+    vec::set(ctx, y.im, n, 0.0);
+    for (auto &t : terms)
+    {
+      const double ci = herm ? -t.ci : t.ci;
+      if (t.cr != 0.0)
+      {
+        b2p_op_apply_add_ex(t.op, t.cr, x.re, y.re, B2P_APPLY_MASKED, s);
+        b2p_op_apply_add_ex(t.op, t.cr, x.im, y.im, B2P_APPLY_MASKED, s);
+      }
+      if (ci != 0.0)
+      {
+        b2p_op_apply_add_ex(t.op, -ci, x.im, y.re, B2P_APPLY_MASKED, s);
+        b2p_op_apply_add_ex(t.op, ci, x.re, y.im, B2P_APPLY_MASKED, s);
+      }
+    }
+    if (n_ess > 0)
+    {
+      if (diag_policy == 1)
+      {
+        vec::set_sub_from(ctx, y.re, d_ess, n_ess, x.re);
+        vec::set_sub_from(ctx, y.im, d_ess, n_ess, x.im);
+      }
+      else
+      {
+        vec::set_sub(ctx, y.re, d_ess, n_ess, 0.0);
+        vec::set_sub(ctx, y.im, d_ess, n_ess, 0.0);
+      }
+    }
+  }
+  void Mult(CCPtr x, CPtr y) const override { apply(x, y, false); }
+  void MultHermitianTranspose(CCPtr x, CPtr y) const override { apply(x, y, true); }
+  void AssembleDiagonal(CPtr d) const override
+  {
+    cudaStream_t s = ctx->stream;
+    vec::set(ctx, d.re, n, 0.0);
+    vec::set(ctx, d.im, n, 0.0);
+    if (tmp_.n != 2 * n) tmp_.resize(ctx, 2 * n);
+    for (auto &t : terms)
+    {
+      vec::set(ctx, tmp_.p, n, 0.0);
+      b2p_op_diag_add(t.op, tmp_.p, s);
+      if (t.cr != 0.0) vec::axpy(ctx, t.cr, tmp_.p, d.re, n);
+      if (t.ci != 0.0) vec::axpy(ctx, t.ci, tmp_.p, d.im, n);
+    }
+    if (n_ess > 0)
+    {
+      vec::set_sub(ctx, d.re, d_ess, n_ess, diag_policy == 1 ? 1.0 : 0.0);
+      vec::set_sub(ctx, d.im, d_ess, n_ess, 0.0);
+    }
+  }
+
+private:
+  std::vector<Term> terms;
+  int32_t *d_ess = nullptr;
+  int64_t n_ess;
+  int diag_policy;
+};
+
+// ------------------------------------------------------------------------------------ complex solvers
+class ComplexSolver
+{
+public:
+  b2p_ctx *ctx;
+  bool initial_guess = false;
+  ComplexSolver(b2p_ctx *c) : ctx(c) {}
+  virtual ~ComplexSolver() = default;
+  virtual void Mult(CCPtr x, CPtr y) const = 0;
+};
+
+// PCMatReal: the (real) preconditioner acts on real and imaginary parts separately.
+class RealPcSolver : public ComplexSolver
+{
+public:
+  RealPcSolver(b2p_ctx *c, const Solver *B_) : ComplexSolver(c), B(B_) {}
+  void Mult(CCPtr x, CPtr y) const override
+  {
+    B->Mult(x.re, y.re);
+    B->Mult(x.im, y.im);
+  }
+  const Solver *B;
+};
+
+namespace
+{
+// iterative.cpp:112-226, well-scaled branches
+inline void GeneratePlaneRotation(const cplx dx, const cplx dy, double &cs, cplx &sn)
+{
+  if (dy == 0.0)
+  {
+    cs = 1.0;
+    sn = 0.0;
+    return;
+  }
+  if (dx == 0.0)
+  {
+    cs = 0.0;
+    sn = std::conj(dy) / std::abs(dy);
+    return;
+  }
+  const double dx2 = std::norm(dx), dy2 = std::norm(dy), dz2 = dx2 + dy2;
+  cs = std::sqrt(dx2 / dz2);
+  sn = std::conj(dy) * (dx / std::sqrt(dx2 * dz2));
+}
+inline void ApplyPlaneRotation(cplx &dx, cplx &dy, const double cs, const cplx sn)
+{
+  const cplx t = cs * dx + sn * dy;
+  dy = -std::conj(sn) * dx + cs * dy;
+  dx = t;
+}
+}  // namespace
+
+class ComplexIterativeSolver : public ComplexSolver
+{
+public:
+  ComplexIterativeSolver(b2p_ctx *c, KspType type_) : ComplexSolver(c), type(type_) {}
+  KspType type;
+  const ComplexOperator *A = nullptr;
+  const ComplexSolver *B = nullptr;
+  double rel_tol = 1e-6, abs_tol = 0.0;
+  int max_it = 100, max_dim = -1;
+  Orthog gs = Orthog::MGS;
+  PcSide pc_side = PcSide::RIGHT;
+  mutable bool converged = false;
+  mutable double initial_res = 1.0, final_res = 0.0;
+  mutable int final_it = 0;
+
+  void Mult(CCPtr b, CPtr x) const override
+  {
+    if (type == KspType::CG)
+      MultCG(b, x);
+    else
+      MultGMRES(b, x, type == KspType::FGMRES);
+  }
+
+private:
+  mutable std::vector<std::unique_ptr<DVec>> V, Z;
+  mutable DVec r_, z_, p_;
+  CPtr cp(DVec &v, int64_t n) const
+  {
+    if (v.n != 2 * n) v.resize(ctx, 2 * n);
+    return CPtr{v.p, v.p + n};
+  }
+  static CCPtr cc(CPtr p) { return CCPtr{p.re, p.im}; }
+  void ccopy(CPtr y, CCPtr x, int64_t n) const
+  {
+    vec::copy(ctx, y.re, x.re, n);
+    vec::copy(ctx, y.im, x.im, n);
+  }
+  void czero(CPtr y, int64_t n) const
+  {
+    vec::set(ctx, y.re, n, 0.0);
+    vec::set(ctx, y.im, n, 0.0);
+  }
+  // r = b - r
+  void residual(CCPtr b, CPtr r, int64_t n) const
+  {
+    vec::axpby(ctx, 1.0, b.re, -1.0, r.re, n);
+    vec::axpby(ctx, 1.0, b.im, -1.0, r.im, n);
+  }
+
+  // iterative.cpp:361-486 with complex scalars
+  void MultCG(CCPtr b, CPtr x) const
+  {
+    const int64_t n = A->n;
+    CPtr r = cp(r_, n), z = cp(z_, n), p = cp(p_, n);
+    cplx beta, beta_prev = 0.0, alpha, denom;
+    double res, eps;
+    if (initial_guess)
+    {
+      A->Mult(cc(x), r);
+      residual(b, r, n);
+    }
+    else
+    {
+      ccopy(r, b, n);
+      czero(x, n);
+    }
+    if (B)
+      B->Mult(cc(r), z);
+    else
+      ccopy(z, cc(r), n);
+    beta = cdot(ctx, cc(z), cc(r), n);
+    res = std::sqrt(std::abs(beta));
+    if (initial_guess)
+    {
+      cplx beta_rhs;
+      if (B)
+      {
+        B->Mult(b, p);
+        beta_rhs = cdot(ctx, cc(p), b, n);
+      }
+      else
+        beta_rhs = cnorm(ctx, b, n);
+      initial_res = std::sqrt(std::abs(beta_rhs));
+    }
+    else
+      initial_res = res;
+    eps = std::max(rel_tol * initial_res, abs_tol);
+    converged = (res < eps);
+    int it = 0;
+    for (; it < max_it && !converged; it++)
+    {
+      if (!it)
+        ccopy(p, cc(z), n);
+      else
+      {
+        // p = z + (beta / beta_prev) p
+        const cplx g = beta / beta_prev;
+        if (tmp_.n != 2 * n) tmp_.resize(ctx, 2 * n);
+        CPtr t{tmp_.p, tmp_.p + n};
+        ccopy(t, cc(z), n);
+        caxpy(ctx, g, cc(p), t, n);
+        ccopy(p, cc(t), n);
+      }
+      A->Mult(cc(p), z);
+      denom = cdot(ctx, cc(z), cc(p), n);
+      alpha = beta / denom;
+      caxpy(ctx, alpha, cc(p), x, n);
+      caxpy(ctx, -alpha, cc(z), r, n);
+      beta_prev = beta;
+      if (B)
+        B->Mult(cc(r), z);
+      else
+        ccopy(z, cc(r), n);
+      beta = cdot(ctx, cc(z), cc(r), n);
+      res = std::sqrt(std::abs(beta));
+      converged = (res < eps);
+    }
+    final_res = res;
+    final_it = it;
+  }
+
+  // iterative.cpp:544-705 / :734-871 with complex scalars
+  void MultGMRES(CCPtr b, CPtr x, bool flexible) const
+  {
+    const int64_t n = A->n;
+    const int mdim = (max_dim < 0) ? max_it : max_dim;
+    CPtr r = cp(r_, n);
+    auto ensure = [&](std::vector<std::unique_ptr<DVec>> &W, int k)
+    {
+      if ((int)W.size() <= k) W.resize(k + 1);
+      if (!W[k]) W[k] = std::make_unique<DVec>(ctx, 2 * n);
+      if (W[k]->n != 2 * n) W[k]->resize(ctx, 2 * n);
+      return CPtr{W[k]->p, W[k]->p + n};
+    };
+    std::vector<cplx> H((size_t)(mdim + 1) * mdim, 0.0), s(mdim + 1, 0.0), sn(mdim + 1, 0.0);
+    std::vector<double> cs(mdim + 1, 0.0);
+    const bool right = flexible || pc_side == PcSide::RIGHT;
+    double beta = 0.0, true_beta, eps = 0.0;
+    converged = false;
+    int it = 0, restart = 0;
+    for (; it < max_it; restart++)
+    {
+      CPtr V0 = ensure(V, 0);
+      CPtr rv = flexible ? ensure(Z, 0) : r;
+      const bool ig = initial_guess || restart > 0;
+      if (B && !right)
+      {
+        if (ig)
+        {
+          A->Mult(cc(x), V0);
+          residual(b, V0, n);
+          B->Mult(cc(V0), rv);
+        }
+        else
+        {
+          B->Mult(b, rv);
+          czero(x, n);
+        }
+      }
+      else
+      {
+        if (ig)
+        {
+          A->Mult(cc(x), rv);
+          residual(b, rv, n);
+        }
+        else
+        {
+          ccopy(rv, b, n);
+          czero(x, n);
+        }
+      }
+      true_beta = cnorm(ctx, cc(rv), n);
+      if (it == 0)
+      {
+        if (initial_guess)
+        {
+          if (B && !right)
+          {
+            B->Mult(b, V0);
+            initial_res = cnorm(ctx, cc(V0), n);
+          }
+          else
+            initial_res = cnorm(ctx, b, n);
+        }
+        else
+          initial_res = true_beta;
+        eps = std::max(rel_tol * initial_res, abs_tol);
+      }
+      beta = true_beta;
+      if (beta < eps)
+      {
+        converged = true;
+        break;
+      }
+      vec::axpby(ctx, 1.0 / beta, rv.re, 0.0, V0.re, n);
+      vec::axpby(ctx, 1.0 / beta, rv.im, 0.0, V0.im, n);
+      std::fill(s.begin(), s.end(), cplx(0.0));
+      s[0] = beta;
+      int j = 0;
+      for (;; j++, it++)
+      {
+        CPtr Vj = ensure(V, j), w = ensure(V, j + 1);
+        if (B && !right)
+        {
+          A->Mult(cc(Vj), r);
+          B->Mult(cc(r), w);
+        }
+        else if (B)
+        {
+          CPtr zj = flexible ? ensure(Z, j) : r;
+          B->Mult(cc(Vj), zj);
+          A->Mult(cc(zj), w);
+        }
+        else
+          A->Mult(cc(Vj), w);
+        cplx *Hj = H.data() + (size_t)j * (mdim + 1);
+        std::vector<CCPtr> Vp(j + 1);
+        for (int k = 0; k <= j; k++) Vp[k] = CCPtr{V[k]->p, V[k]->p + n};
+        if (gs == Orthog::MGS)
+        {
+          for (int k = 0; k <= j; k++)
+          {
+            Hj[k] = cdot(ctx, cc(w), Vp[k], n);
+            caxpy(ctx, -Hj[k], Vp[k], w, n);
+          }
+        }
+        else
+        {
+          cmulti_dot(ctx, j + 1, Vp.data(), cc(w), n, Hj);
+          cmulti_axpy(ctx, j + 1, Hj, Vp.data(), w, n, -1.0);
+          if (gs == Orthog::CGS2)
+          {
+            std::vector<cplx> dH(j + 1);
+            cmulti_dot(ctx, j + 1, Vp.data(), cc(w), n, dH.data());
+            cmulti_axpy(ctx, j + 1, dH.data(), Vp.data(), w, n, -1.0);
+            for (int k = 0; k <= j; k++) Hj[k] += dH[k];
+          }
+        }
+        const double hn = cnorm(ctx, cc(w), n);
+        Hj[j + 1] = hn;
+        vec::scale(ctx, w.re, n, 1.0 / hn);
+        vec::scale(ctx, w.im, n, 1.0 / hn);
+        for (int k = 0; k < j; k++) ApplyPlaneRotation(Hj[k], Hj[k + 1], cs[k], sn[k]);
+        GeneratePlaneRotation(Hj[j], Hj[j + 1], cs[j], sn[j]);
+        ApplyPlaneRotation(Hj[j], Hj[j + 1], cs[j], sn[j]);
+        ApplyPlaneRotation(s[j], s[j + 1], cs[j], sn[j]);
+        beta = std::abs(s[j + 1]);
+        converged = (beta < eps);
+        if (converged || j + 1 == mdim || it + 1 == max_it)
+        {
+          it++;
+          break;
+        }
+      }
+      for (int i = j; i >= 0; i--)
+      {
+        cplx *Hi = H.data() + (size_t)i * (mdim + 1);
+        s[i] /= Hi[i];
+        for (int k = i - 1; k >= 0; k--) s[k] -= Hi[k] * s[i];
+      }
+      std::vector<CCPtr> W(j + 1);
+      if (flexible)
+      {
+        for (int k = 0; k <= j; k++) W[k] = CCPtr{Z[k]->p, Z[k]->p + n};
+        cmulti_axpy(ctx, j + 1, s.data(), W.data(), x, n, 1.0);
+      }
+      else
+      {
+        for (int k = 0; k <= j; k++) W[k] = CCPtr{V[k]->p, V[k]->p + n};
+        if (!B || !right)
+          cmulti_axpy(ctx, j + 1, s.data(), W.data(), x, n, 1.0);
+        else
+        {
+          czero(r, n);
+          cmulti_axpy(ctx, j + 1, s.data(), W.data(), r, n, 1.0);
+          CPtr V0b = ensure(V, 0);
+          B->Mult(cc(r), V0b);
+          caxpy(ctx, 1.0, cc(V0b), x, n);
+        }
+      }
+      if (converged) break;
+    }
+    final_res = beta;
+    final_it = it;
+  }
+  mutable DVec tmp_;
+};
+
+}  // namespace b2p
+
+using namespace b2p;
+
+struct b2p_operator;
+struct b2p_solver;
+namespace b2p
+{
+Solver *solver_of(b2p_solver *s);
+}
+
+struct b2p_coperator
+{
+  std::unique_ptr<ComplexOperator> op;
+};
+struct b2p_csolver
+{
+  std::unique_ptr<ComplexSolver> s;
+};
+
+#define B2P_CTRY(ctx, stmt)                                      \
+  do                                                             \
+  {                                                              \
+    stmt;                                                        \
+    cudaError_t e__ = cudaPeekAtLastError();                     \
+    if (e__ != cudaSuccess)                                      \
+    {                                                            \
+      set_error(ctx, "CUDA error: %s", cudaGetErrorString(e__)); \
+      return B2P_ERR_CUDA;                                       \
+    }                                                            \
+  } while (0)
+
+extern "C"
+{
+
+int b2p_vec_cdot(b2p_ctx *ctx, int64_t n, const double *xr, const double *xi, const double *yr, const double *yi, double out[2])
+{
+  cplx d;
+  B2P_CTRY(ctx, d = cdot(ctx, CCPtr{xr, xi}, CCPtr{yr, yi}, n));
+  out[0] = d.real();
+  out[1] = d.imag();
+  return B2P_SUCCESS;
+}
+int b2p_vec_caxpy(b2p_ctx *ctx, int64_t n, double ar, double ai, const double *xr, const double *xi, double *yr, double *yi)
+{
+  B2P_CTRY(ctx, caxpy(ctx, cplx(ar, ai), CCPtr{xr, xi}, CPtr{yr, yi}, n));
+  return B2P_SUCCESS;
+}
+
+int b2p_coperator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coef_re,
+                      const double *coef_im, const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_coperator **out)
+{
+  B2P_CHECK(ctx, ctx && out && n_terms > 0 && ops && coef_re && coef_im, B2P_ERR_ARG, "b2p_coperator_par: bad argument");
+  B2P_CHECK(ctx, tsize == lsize, B2P_ERR_UNSUPPORTED, "b2p_coperator_par: partitioned complex operators are not implemented yet");
+  std::vector<ComplexParOperator::Term> terms;
+  for (int i = 0; i < n_terms; i++)
+  {
+    B2P_CHECK(ctx, ops[i] && b2p_op_lsize(ops[i]) == lsize, B2P_ERR_ARG, "b2p_coperator_par: term %d has the wrong L-size", i);
+    terms.push_back({ops[i], coef_re[i], coef_im[i]});
+  }
+  auto *h = new b2p_coperator;
+  h->op = std::make_unique<ComplexParOperator>(ctx, tsize, terms, ess_tdofs, n_ess, diag_policy);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_coperator_mult(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi)
+{
+  if (!A) return B2P_ERR_ARG;
+  B2P_CTRY(A->op->ctx, A->op->Mult(CCPtr{xr, xi}, CPtr{yr, yi}));
+  return B2P_SUCCESS;
+}
+int b2p_coperator_mult_hermitian_transpose(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi)
+{
+  if (!A) return B2P_ERR_ARG;
+  B2P_CTRY(A->op->ctx, A->op->MultHermitianTranspose(CCPtr{xr, xi}, CPtr{yr, yi}));
+  return B2P_SUCCESS;
+}
+int b2p_coperator_add_mult(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi, double ar, double ai)
+{
+  if (!A) return B2P_ERR_ARG;
+  B2P_CTRY(A->op->ctx, A->op->AddMult(CCPtr{xr, xi}, CPtr{yr, yi}, cplx(ar, ai)));
+  return B2P_SUCCESS;
+}
+int b2p_coperator_assemble_diagonal(b2p_coperator *A, double *dr, double *di)
+{
+  if (!A) return B2P_ERR_ARG;
+  B2P_CTRY(A->op->ctx, A->op->AssembleDiagonal(CPtr{dr, di}));
+  return B2P_SUCCESS;
+}
+void b2p_coperator_destroy(b2p_coperator *A) { delete A; }
+
+int b2p_csolver_real_pc(b2p_ctx *ctx, b2p_solver *real_pc, b2p_csolver **out)
+{
+  B2P_CHECK(ctx, ctx && real_pc && out, B2P_ERR_ARG, "b2p_csolver_real_pc: bad argument");
+  auto *h = new b2p_csolver;
+  h->s = std::make_unique<RealPcSolver>(ctx, solver_of(real_pc));
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_csolver_krylov(b2p_ctx *ctx, int type, b2p_csolver **out)
+{
+  B2P_CHECK(ctx, type >= 0 && type <= 2 && out, B2P_ERR_ARG, "b2p_csolver_krylov: type must be 0 (CG), 1 (GMRES) or 2 (FGMRES)");
+  auto *h = new b2p_csolver;
+  h->s = std::make_unique<ComplexIterativeSolver>(ctx, (KspType)type);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_csolver_krylov_config(b2p_csolver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side)
+{
+  auto *k = s ? dynamic_cast<ComplexIterativeSolver *>(s->s.get()) : nullptr;
+  if (!k) return B2P_ERR_ARG;
+  k->rel_tol = rel_tol;
+  k->abs_tol = abs_tol;
+  k->max_it = max_it;
+  k->max_dim = max_dim;
+  k->gs = (Orthog)orthog;
+  k->pc_side = (PcSide)pc_side;
+  return B2P_SUCCESS;
+}
+int b2p_csolver_set_operator(b2p_csolver *s, b2p_coperator *A)
+{
+  auto *k = s ? dynamic_cast<ComplexIterativeSolver *>(s->s.get()) : nullptr;
+  if (!k || !A) return B2P_ERR_ARG;
+  k->A = A->op.get();
+  return B2P_SUCCESS;
+}
+int b2p_csolver_set_preconditioner(b2p_csolver *s, b2p_csolver *pc)
+{
+  auto *k = s ? dynamic_cast<ComplexIterativeSolver *>(s->s.get()) : nullptr;
+  if (!k) return B2P_ERR_ARG;
+  k->B = pc ? pc->s.get() : nullptr;
+  return B2P_SUCCESS;
+}
+int b2p_csolver_set_initial_guess(b2p_csolver *s, int flag)
+{
+  if (!s || !s->s) return B2P_ERR_ARG;
+  s->s->initial_guess = flag != 0;
+  return B2P_SUCCESS;
+}
+int b2p_csolver_mult(b2p_csolver *s, const double *br, const double *bi, double *xr, double *xi)
+{
+  if (!s || !s->s) return B2P_ERR_ARG;
+  B2P_CTRY(s->s->ctx, s->s->Mult(CCPtr{br, bi}, CPtr{xr, xi}));
+  return B2P_SUCCESS;
+}
+int b2p_csolver_stats(b2p_csolver *s, int *its, double *initial_res, double *final_res, int *converged)
+{
+  auto *k = s ? dynamic_cast<ComplexIterativeSolver *>(s->s.get()) : nullptr;
+  if (!k) return B2P_ERR_ARG;
+  if (its) *its = k->final_it;
+  if (initial_res) *initial_res = k->initial_res;
+  if (final_res) *final_res = k->final_res;
+  if (converged) *converged = k->converged ? 1 : 0;
+  return B2P_SUCCESS;
+}
+void b2p_csolver_destroy(b2p_csolver *s) { delete s; }
+
+}  // extern "C"

@@ -34,6 +34,8 @@ struct DVec  // owning device vector
   operator const double *() const { return p; }
 };
 
+void b2p_allreduce_sum(b2p_ctx *c, double *dbuf, int n);  // in place, on ctx->stream (no-op for one rank)
+
 namespace vec
 {
 void set(b2p_ctx *c, double *y, int64_t n, double v);

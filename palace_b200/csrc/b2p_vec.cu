@@ -170,6 +170,11 @@ void reduce_finish(b2p_ctx *c, int m, double *host_out)
 
 }  // namespace
 
+void b2p_allreduce_sum(b2p_ctx *c, double *dbuf, int n)
+{
+  if (c->nranks > 1 && c->comm) ncclAllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
+}
+
 namespace vec
 {
 

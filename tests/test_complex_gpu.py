@@ -1,0 +1,172 @@
+"""GPU parity of the complex (split real/imag) operator and Krylov layer: ComplexParOperator over a sum of real
+partially assembled operators with complex coefficients (the a0 K + a2 M system matrix of a lossy driven /
+eigen problem, /root/reference/palace/linalg/rap.cpp:843-919, operator.cpp:98-134), complex inner products
+(vector.cpp:674-685), complex (F)GMRES (iterative.cpp:544-871) and the PCMatReal preconditioner
+configuration (models/spaceoperator.cpp:1098-1105), against NumPy complex arithmetic on oracle matrices."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from oracle import pyoracle as O
+from oracle import solvers as S
+from palace_b200.host import assemble as asm
+from palace_b200.host import coeff as cf
+from palace_b200.host import hexspace as hs
+from tests import common
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _cvec(z):
+    return _dev(z.real), _dev(z.imag)
+
+
+def _host(zr, zi):
+    return zr.cpu().numpy() + 1j * zi.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def setup(b2p_ctx):
+    from palace_b200 import capi
+
+    capi.set_stream(b2p_ctx)
+    prob = common.make_problem(n=(3, 2, 2), p=2, n_attr=2)
+    geom = common.gpu_geom(b2p_ctx, prob)
+    nd = prob.nd
+    ident = cf.coeff_ctx()
+    K = common.gpu_op(b2p_ctx, geom, prob, O.CURLCURL, ident)
+    M = common.gpu_op(b2p_ctx, geom, prob, O.ND_MASS, common.coefficient(O.ND_MASS, 2, "matrix"))
+    # lossy medium: A = K - omega^2 (1 - i tan delta) M
+    w2, tand = 9.0, 0.05
+    coefs = [1.0 + 0.0j, -w2 * (1.0 - 1j * tand)]
+    A = capi.ComplexOperator.par(b2p_ctx, nd.ndofs, nd.ndofs, [K, M], coefs, nd.ess_dofs, 1)
+    Ko = common.oracle_matrix(prob, O.CURLCURL, ident, eliminate=False)
+    Mo = common.oracle_matrix(prob, O.ND_MASS, common.coefficient(O.ND_MASS, 2, "matrix"), eliminate=False)
+    Ao = (coefs[0] * Ko + coefs[1] * Mo).tolil()
+    ess = nd.ess_dofs
+    Ao[ess, :] = 0
+    Ao[:, ess] = 0
+    Ao[ess, ess] = 1.0
+    return dict(capi=capi, prob=prob, geom=geom, A=A, Ao=Ao.tocsr(), Ko=Ko, Mo=Mo, K=K, M=M, coefs=coefs, w2=w2)
+
+
+def test_complex_dot_and_axpy(b2p_ctx, setup):
+    capi = setup["capi"]
+    rng = np.random.default_rng(0)
+    n = 40001
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    y = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    xr, xi = _cvec(x)
+    yr, yi = _cvec(y)
+    d = capi.vec_cdot(b2p_ctx, xr, xi, yr, yi)
+    assert abs(d - np.vdot(y, x)) < 1e-10 * np.sqrt(n)  # Dot(x, y) = y^H x
+    a = 0.3 - 1.7j
+    capi.vec_caxpy(b2p_ctx, a, xr, xi, yr, yi)
+    assert _rel(_host(yr, yi), y + a * x) < 1e-15
+
+
+def test_complex_par_operator(b2p_ctx, setup):
+    A, Ao = setup["A"], setup["Ao"]
+    n = Ao.shape[0]
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    xr, xi = _cvec(x)
+    yr, yi = torch.empty_like(xr), torch.empty_like(xi)
+    A.mult(xr, xi, yr, yi)
+    assert _rel(_host(yr, yi), Ao @ x) < 1e-12
+    A.mult_hermitian_transpose(xr, xi, yr, yi)
+    assert _rel(_host(yr, yi), Ao.conj().T @ x) < 1e-12
+    y0 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    yr, yi = _cvec(y0)
+    a = -0.5 + 0.25j
+    A.add_mult(xr, xi, yr, yi, a)
+    assert _rel(_host(yr, yi), y0 + a * (Ao @ x)) < 1e-12
+    dr, di = torch.empty_like(xr), torch.empty_like(xi)
+    A.assemble_diagonal(dr, di)
+    assert _rel(_host(dr, di), Ao.diagonal()) < 1e-12
+
+
+@pytest.mark.parametrize("kind,orth,side", [(1, 0, 0), (1, 2, 1), (2, 1, 0)])
+def test_complex_gmres_matches_reference_recurrence(b2p_ctx, setup, kind, orth, side):
+    """Complex (F)GMRES with a Jacobi-like real preconditioner applied to both parts."""
+    capi, A, Ao, prob = setup["capi"], setup["A"], setup["Ao"], setup["prob"]
+    n = Ao.shape[0]
+    # real preconditioner matrix: K + omega^2 M (PCMatShifted + PCMatReal), Jacobi on it
+    blobP = cf.coeff_ctx_pair(common.coefficient(O.ND_MASS, 2, "matrix", a_mass=setup["w2"]), cf.coeff_ctx(a=1.0))
+    Pr = common.gpu_par_operator(b2p_ctx, setup["geom"], prob, O.CURLCURL_MASS, blobP)
+    J = capi.Solver.jacobi(b2p_ctx)
+    J.set_operator(Pr)
+    pc = capi.ComplexSolver.real_pc(b2p_ctx, J)
+    Ks = capi.ComplexSolver.krylov(b2p_ctx, kind, rel_tol=1e-9, max_it=400, max_dim=400, orthog=orth, pc_side=side)
+    Ks.set_operator(A)
+    Ks.set_preconditioner(pc)
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    b[prob.nd.ess_dofs] = 0.0
+    br, bi = _cvec(b)
+    xr, xi = torch.zeros_like(br), torch.zeros_like(bi)
+    Ks.mult(br, bi, xr, xi)
+    st = Ks.stats()
+    Po = (setup["Ko"] + setup["w2"] * setup["Mo"]).tolil()
+    ess = prob.nd.ess_dofs
+    Po[ess, :] = 0
+    Po[:, ess] = 0
+    Po[ess, ess] = 1.0
+    dinv = 1.0 / Po.tocsr().diagonal()
+    x_ref, it_ref, conv_ref = S.cgmres(Ao, b, lambda r: dinv * r, rel_tol=1e-9, max_it=400, max_dim=400, orthog=orth,
+                                       flexible=(kind == 2), right=(side == 0))
+    assert st["converged"] and conv_ref
+    assert abs(st["its"] - it_ref) <= max(2, it_ref // 10)
+    x_direct = spla.spsolve(Ao.tocsc(), b)
+    assert _rel(_host(xr, xi), x_direct) < 1e-6
+
+
+def test_lossy_system_with_real_multigrid_preconditioner(b2p_ctx, setup):
+    """FGMRES on the complex lossy system, preconditioned by the real p-multigrid of K + omega^2 M applied
+    to real and imaginary parts (PCMatReal + PCMatShifted)."""
+    capi, prob, geom = setup["capi"], setup["prob"], setup["geom"]
+    p = prob.p
+    orders = asm.p_sequence(p)
+    nd = {q: hs.build_nd_space(prob.mesh, prob.topo, q) for q in orders}
+    h1 = {q: hs.build_h1_space(prob.mesh, prob.topo, q) for q in orders}
+    blobP = cf.coeff_ctx_pair(common.coefficient(O.ND_MASS, 2, "matrix", a_mass=setup["w2"]), cf.coeff_ctx(a=1.0))
+    blobG = common.coefficient(O.H1_DIFFUSION, 2, "matrix", a_mass=setup["w2"])
+    Pl, AG = {}, {}
+    Pl[p] = common.gpu_par_operator(b2p_ctx, geom, prob, O.CURLCURL_MASS, blobP, space=nd[p])
+    AG[p] = common.gpu_par_operator(b2p_ctx, geom, prob, O.H1_DIFFUSION, blobG, space=h1[p])
+    for q in orders[:-1]:
+        Pl[q] = common.gpu_par_operator(b2p_ctx, geom, prob, O.CURLCURL_MASS, blobP, space=nd[q], fine_op=Pl[p].local_op)
+        AG[q] = common.gpu_par_operator(b2p_ctx, geom, prob, O.H1_DIFFUSION, blobG, space=h1[q], fine_op=AG[p].local_op)
+    G = [common.gpu_interp(b2p_ctx, h1[q], nd[q], asm.gradient_comps(q)) for q in orders]
+    P = [common.gpu_interp(b2p_ctx, nd[a], nd[b], asm.nd_prolongation_comps(a, b)) for a, b in zip(orders[:-1], orders[1:])]
+    coarse = capi.Solver.krylov(b2p_ctx, capi.CG, rel_tol=1e-12, max_it=2000)
+    cj = capi.Solver.jacobi(b2p_ctx)
+    cj.set_operator(Pl[orders[0]])
+    coarse.set_preconditioner(cj)
+    coarse.set_operator(Pl[orders[0]])
+    mg = capi.Solver.gmg(b2p_ctx, coarse, P, G, cycle_it=1, smooth_it=1, cheby_order=4)
+    mg.gmg_set_operators([Pl[q] for q in orders], [AG[q] for q in orders])
+    pc = capi.ComplexSolver.real_pc(b2p_ctx, mg)
+    Ks = capi.ComplexSolver.krylov(b2p_ctx, capi.FGMRES, rel_tol=1e-10, max_it=300, max_dim=300)
+    Ks.set_operator(setup["A"])
+    Ks.set_preconditioner(pc)
+    Ao = setup["Ao"]
+    n = Ao.shape[0]
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    b[prob.nd.ess_dofs] = 0.0
+    br, bi = _cvec(b)
+    xr, xi = torch.zeros_like(br), torch.zeros_like(bi)
+    Ks.mult(br, bi, xr, xi)
+    st = Ks.stats()
+    assert st["converged"] and 60 <= st["its"] <= 95, st  # NumPy restatement of the same configuration: 78
+    assert _rel(_host(xr, xi), spla.spsolve(Ao.tocsc(), b)) < 1e-7
