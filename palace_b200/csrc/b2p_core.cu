@@ -1,4 +1,5 @@
 // Context, errors, device memory helpers, geometry q-data and operator construction for the C ABI.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -97,7 +98,14 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   const bool simple = flags & B2P_APPLY_SIMPLE_KERNEL;
   if (op->kind == B2P_H1_DIFFUSION) return simple ? launch_h1_hex_apply(op, lidx, alpha, x, y, rg, s) : launch_h1_hex_apply3(op, lidx, alpha, x, y, rg, s);
   if (simple) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
-  return launch_nd_hex_apply2(op, lidx, alpha, x, y, rg, s);
+  // B2P_ND_KERNEL=3 selects the previous shared-memory layout (kept for A/B measurements)
+  static const int nd_kernel = []
+  {
+    const char *e = std::getenv("B2P_ND_KERNEL");
+    return e ? std::atoi(e) : 4;
+  }();
+  if (nd_kernel == 3) return launch_nd_hex_apply2(op, lidx, alpha, x, y, rg, s);
+  return launch_nd_hex_apply4(op, lidx, alpha, x, y, rg, s);
 }
 }  // namespace b2p
 
