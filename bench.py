@@ -315,7 +315,7 @@ def main():
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tr = json.load(f)
         if args.order == 3 and args.n == 29 and not args.assemble_qdata and world == 1:
-            k = tr["nd_hex_apply3_kernel<3,4,CURLCURL_MASS,geom>"]
+            k = tr["nd_hex_apply4_kernel<3,4,CURLCURL_MASS,geom>"]
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     except Exception:
         pass
@@ -349,7 +349,7 @@ def main():
             # per rank and step: the apply kernel (+ halo pack and unpack kernels when N > 1); memset/NCCL not counted
             "gpu_launches": int(args.steps * (1 + (2 if world > 1 else 0))),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "nd_hex_apply3_kernel", "kernel_ms": k_ms,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "nd_hex_apply4_kernel", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(abytes)},
         }
         if not args.no_cpu_baseline:
