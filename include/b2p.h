@@ -135,11 +135,14 @@ int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s);
  *                            masked inputs read as 0 and masked outputs are not written, which is what
  *                            ParOperator::Mult does with SetSubVector(tx, dbc_tdof_list, 0.0) before P and
  *                            the overwrite of y at those rows after P^T (rap.cpp:207-233)
- *   B2P_APPLY_SIMPLE_KERNEL  run the simple cross-check kernel instead of the production one */
+ *   B2P_APPLY_SIMPLE_KERNEL  run the simple cross-check kernel instead of the production one
+ *   B2P_APPLY_HALFWARP_KERNEL  run the one-element-per-warp ND kernel where it applies (p = 3, q1d = 4,
+ *                            mirror-symmetric 1-D tables; ignored otherwise) */
 enum
 {
   B2P_APPLY_MASKED = 1,
-  B2P_APPLY_SIMPLE_KERNEL = 2
+  B2P_APPLY_SIMPLE_KERNEL = 2,
+  B2P_APPLY_HALFWARP_KERNEL = 4
 };
 int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, int flags, b2p_stream s);
 /* Same over the element sub-range [e_begin, e_begin + e_count) with the L-vector in two pieces: dofs

@@ -98,13 +98,15 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   const bool simple = flags & B2P_APPLY_SIMPLE_KERNEL;
   if (op->kind == B2P_H1_DIFFUSION) return simple ? launch_h1_hex_apply(op, lidx, alpha, x, y, rg, s) : launch_h1_hex_apply3(op, lidx, alpha, x, y, rg, s);
   if (simple) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
-  // B2P_ND_KERNEL=3 selects the previous shared-memory layout (kept for A/B measurements)
+  // One-element-per-warp variant (p = 3, q1d = 4, mirror-symmetric tables): opt-in through the apply flag or
+  // B2P_ND_KERNEL=5; measured slower than nd_hex_apply4_kernel on B200, kept for the analysis.
   static const int nd_kernel = []
   {
     const char *e = std::getenv("B2P_ND_KERNEL");
     return e ? std::atoi(e) : 4;
   }();
-  if (nd_kernel == 3) return launch_nd_hex_apply2(op, lidx, alpha, x, y, rg, s);
+  if (((flags & B2P_APPLY_HALFWARP_KERNEL) || nd_kernel == 5) && nd_hex_apply5_eligible(op))
+    return launch_nd_hex_apply5(op, lidx, alpha, x, y, rg, s);
   return launch_nd_hex_apply4(op, lidx, alpha, x, y, rg, s);
 }
 }  // namespace b2p

@@ -1,14 +1,13 @@
 #!/bin/bash
-# A/B of the ND kernel layouts + parity tests
+# Parity tests, then A/B of the ND apply kernels on the headline workload (run on the GPU box).
 cd /root/repo
-timeout 240 python -m pytest tests/test_apply_gpu.py -m gpu -x -q 2>&1 | tail -4
-for k in 3 4; do
-  for p in 3; do
-    echo "kernel $k order $p"
-    B2P_ND_KERNEL=$k timeout 120 python bench.py --steps 200 --warmup 10 --order $p --no-cpu-baseline 2>&1 | tail -1
-  done
-done
-for p in 2 4; do
-  echo "kernel 4 order $p"
-  timeout 120 python bench.py --steps 100 --warmup 10 --order $p --n $((p==1?64:(p==2?40:23))) --no-cpu-baseline 2>&1 | tail -1
+timeout 300 python -m pytest tests/test_apply_gpu.py -m gpu -x -q 2>&1 | tail -4
+B2P_ND5_MINB=4 timeout 300 python -m pytest tests/test_apply_gpu.py -m gpu -x -q 2>&1 | tail -2
+for cfg in "4 3" "5 3" "5 4"; do
+  set -- $cfg
+  echo "kernel $1 minb $2"
+  B2P_ND_KERNEL=$1 B2P_ND5_MINB=$2 timeout 120 python bench.py --steps 200 --warmup 10 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+print('  value %.0f MDoF/s  ms/step %.5f  kernel_ms %.5f  frac %.4f' % (d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac']))"
 done
