@@ -123,6 +123,7 @@ class CpuReference:
     def __init__(self, prob, sample_elems=0):
         from oracle import pyoracle as O
 
+        self.native = O.use_native_build()  # -march=native on this host (falls back to the portable prebuilt library)
         self.O = O
         nd = prob["nd"]
         p, q1d = prob["p"], prob["q1d"]
@@ -165,7 +166,8 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, prob, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{ref.ns} of {ref.ne} elements per step (dense non-tensor basis apply: oracle port of the libCEED /cpu/self path; the reference itself is unbuildable here)"},
+                         "sample": f"{ref.ns} of {ref.ne} elements per step (dense non-tensor basis apply: oracle port of the libCEED /cpu/self path, "
+                                   f"{'-march=native build on this host' if ref.native else 'portable x86-64-v3 build'}; the reference itself is unbuildable here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -323,6 +325,7 @@ def main():
     achieved = abytes / (k_ms * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers ----
+    # serial (latency of one call): pinned host x -> device, Mult, device y -> pinned host, on one stream
     for _ in range(3):
         step_e2e()
     barrier()
@@ -336,7 +339,56 @@ def main():
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = N_global * e2e_steps / (float(te.item()) * 1e-3) / 1e6
+    e2e_serial = N_global * e2e_steps / (float(te.item()) * 1e-3) / 1e6
+    e2e_value, e2e_mode = e2e_serial, "serial: H2D, Mult, D2H on one stream"
+    if world == 1 and os.environ.get("B2P_E2E_PIPELINE", "1") == "1":
+        # throughput of independent calls: double-buffered device vectors on three streams, so the H2D copy of
+        # step k+1 and the D2H copy of step k-1 (opposite PCIe directions) overlap the Mult of step k. Every
+        # step still copies its own x from pinned host memory and its own y back inside the timed region.
+        s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        xb = [torch.empty_like(xd) for _ in range(2)]
+        yb = [torch.empty_like(yd) for _ in range(2)]
+        yhb = [torch.empty(N, dtype=torch.float64).pin_memory() for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        capi.set_stream(ctx, s_cmp.cuda_stream)
+
+        def step_pipe(k):
+            b = k & 1
+            with torch.cuda.stream(s_in):
+                if k >= 2:
+                    s_in.wait_event(ev_cmp[b])  # Mult k-2 has consumed xb[b]
+                xb[b].copy_(xh, non_blocking=True)
+                ev_in[b].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[b])
+                if k >= 2:
+                    s_cmp.wait_event(ev_out[b])  # yb[b] of step k-2 has been copied out
+                A.mult(xb[b], yb[b])  # enqueued on the context stream (= s_cmp)
+                ev_cmp[b].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[b])
+                yhb[b].copy_(yb[b], non_blocking=True)
+                ev_out[b].record(s_out)
+
+        for k in range(4):
+            step_pipe(k)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(s_in)
+        for k in range(e2e_steps):
+            step_pipe(k)
+        p1.record(s_out)  # after the last D2H copy
+        barrier()
+        capi.set_stream(ctx, stream.cuda_stream)
+        # same x every step: the pipelined result must equal the serial one (up to the order of the scatter-adds)
+        ok = bool(torch.allclose(yhb[(e2e_steps - 1) & 1], yh, rtol=1e-11, atol=1e-13))
+        if ok:
+            e2e_value = N_global * e2e_steps / (p0.elapsed_time(p1) * 1e-3) / 1e6
+            e2e_mode = "pipelined: double-buffered, H2D(k+1) and D2H(k-1) overlap Mult(k) on three streams"
+        else:
+            e2e_mode += " (pipelined result mismatch: not reported)"
 
     line = None
     if rank == 0:
@@ -345,7 +397,8 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, prob, world),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N_global * 8), "d2h_bytes_per_step": int(N_global * 8)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N_global * 8), "d2h_bytes_per_step": int(N_global * 8),
+                    "mode": e2e_mode, "serial_value": e2e_serial},
             # per rank and step: the apply kernel (+ halo pack and unpack kernels when N > 1); memset/NCCL not counted
             "gpu_launches": int(args.steps * (1 + (2 if world > 1 else 0))),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -359,7 +412,8 @@ def main():
             ref.step(cores)
             dts = [ref.step(cores) for _ in range(5)]
             line["cpu_baseline"] = {"value": ref.dofs_per_step / min(dts) / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{ref.ns} of {ref.ne} elements per apply, best of 5 ({min(dts):.3f} s); dense non-tensor basis apply (oracle port)"}
+                                    "sample": f"{ref.ns} of {ref.ne} elements per apply, best of 5 ({min(dts):.3f} s); dense non-tensor basis apply (oracle port, "
+                                              f"{'-march=native' if ref.native else 'x86-64-v3'} build)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -34,6 +34,21 @@ def lib():
     return _LIB
 
 
+def use_native_build():
+    """Timed CPU baseline only (bench.py): rebuild the oracle with -march=native ON THIS HOST into
+    oracle/_native/ and switch to it, so the baseline is not handicapped by the portable ISA level of the
+    prebuilt library. Returns True when the native build is in use."""
+    global _LIB
+    try:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                              timeout=300)
+        _LIB = C.CDLL(os.path.join(_HERE, "_native", "liboracle.so"))
+        _LIB.orc_nd_hex_ndof.restype = C.c_int
+        return True
+    except Exception:
+        return False
+
+
 def ref():
     """The compiled reference QFunctions, or None when oracle/_ref was never built."""
     global _REF
