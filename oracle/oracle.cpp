@@ -430,6 +430,74 @@ void orc_apply_add(int kind, int ne, int P, int Q, const double *interp, const d
   }
 }
 
+// y_L += sum_e E_e^T T_e^T (B^T D B) T_e E_e x_L with the "curl-oriented" restriction of ND tets/prisms at
+// p >= 2: T_e is the row-major tridiagonal int8 matrix co[ne][P][3] = {T(i,i-1), T(i,i), T(i,i+1)} that Palace
+// fills column by column from the element's DofTransformation (restriction.cpp:301-329) and libCEED applies as
+// x_e = T_e x[idx_e] (CeedElemRestrictionCreateCurlOriented), transposed on the way back.
+void orc_apply_add_co(int kind, int ne, int P, int Q, const double *interp, const double *deriv, const int *idx,
+                      const signed char *co, const double *qdata, const void *ctx, const double *x, double *y)
+{
+  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
+  const bool need_c = (kind != ND_MASS);
+  std::vector<double> xe(P), ue(P), ye(P), u(3 * Q), c(3 * Q), v(3 * Q), w(3 * Q);
+  for (int e = 0; e < ne; e++)
+  {
+    const int *ie = idx + (size_t)e * P;
+    const signed char *ce = co + (size_t)e * P * 3;
+    for (int i = 0; i < P; i++) xe[i] = x[ie[i]];
+    for (int i = 0; i < P; i++)
+    {
+      double s = (double)ce[3 * i + 1] * xe[i];
+      if (i > 0) s += (double)ce[3 * i + 0] * xe[i - 1];
+      if (i < P - 1) s += (double)ce[3 * i + 2] * xe[i + 1];
+      ue[i] = s;
+    }
+    for (int d = 0; d < 3; d++)
+      for (int q = 0; q < Q; q++)
+      {
+        double su = 0, sc = 0;
+        if (need_u)
+        {
+          const double *row = interp + ((size_t)d * Q + q) * P;
+          for (int i = 0; i < P; i++) su += row[i] * ue[i];
+        }
+        if (need_c)
+        {
+          const double *row = deriv + ((size_t)d * Q + q) * P;
+          for (int i = 0; i < P; i++) sc += row[i] * ue[i];
+        }
+        u[d * Q + q] = su;
+        c[d * Q + q] = sc;
+      }
+    orc_apply_D(kind, ctx, Q, qdata + (size_t)e * 11 * Q, u.data(), c.data(), v.data(), w.data());
+    std::fill(ye.begin(), ye.end(), 0.0);
+    for (int d = 0; d < 3; d++)
+      for (int q = 0; q < Q; q++)
+      {
+        if (need_u)
+        {
+          const double *row = interp + ((size_t)d * Q + q) * P;
+          const double s = v[d * Q + q];
+          for (int i = 0; i < P; i++) ye[i] += row[i] * s;
+        }
+        if (need_c)
+        {
+          const double *row = deriv + ((size_t)d * Q + q) * P;
+          const double s = w[d * Q + q];
+          for (int i = 0; i < P; i++) ye[i] += row[i] * s;
+        }
+      }
+    for (int i = 0; i < P; i++)
+    {
+      // (T^T y_e)_i = T(i,i) y_i + T(i-1,i) y_{i-1} + T(i+1,i) y_{i+1}
+      double s = (double)ce[3 * i + 1] * ye[i];
+      if (i > 0) s += (double)ce[3 * (i - 1) + 2] * ye[i - 1];
+      if (i < P - 1) s += (double)ce[3 * (i + 1) + 0] * ye[i + 1];
+      y[ie[i]] += s;
+    }
+  }
+}
+
 // Element matrices Ae[ne][P][P] (row-major, in the restricted/oriented basis, i.e. including
 // the sign flips), for assembling the reference-equivalent sparse matrix in tests.
 void orc_element_matrices(int kind, int ne, int P, int Q, const double *interp, const double *deriv,

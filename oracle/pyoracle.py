@@ -128,6 +128,15 @@ def apply_add(kind, interp, deriv, idx, orient, qdata, ctx, x, y):
     return y
 
 
+def apply_add_co(kind, interp, deriv, idx, curl_orient, qdata, ctx, x, y):
+    """y += A x with the tridiagonal curl-oriented restriction (int8 [ne][P][3], row-major)."""
+    ne, P = idx.shape
+    Q = qdata.shape[-1]
+    co = np.ascontiguousarray(curl_orient, dtype=np.int8)
+    lib().orc_apply_add_co(kind, ne, P, Q, _p(interp), _p(deriv), _p(idx), _p(co), _p(qdata), _p(ctx), _p(x), _p(y))
+    return y
+
+
 def element_matrices(kind, interp, deriv, orient, qdata, ctx, P):
     ne = qdata.shape[0]
     Q = qdata.shape[-1]

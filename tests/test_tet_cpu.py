@@ -1,0 +1,194 @@
+"""CPU checks of the tetrahedral Nedelec path (caller-side stand-in palace_b200/host/tetspace.py + the
+oracle's dense curl-oriented apply): what Palace feeds libCEED for simplices
+(/root/reference/palace/fem/libceed/basis.cpp:40-85, restriction.cpp:281-368). MFEM is not available
+here, so the element, the face-pair transformations and the q-data layout are pinned by identities that
+fail for any wrong node, tangent, sign, permutation or Piola convention."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from palace_b200.host import coeff as cf
+from palace_b200.host import tetspace as ts
+
+
+def _problem(p, n=(2, 1, 1), jitter=0.25, seed=5, geom_order=1, warp=0.0, degree=None, n_attr=1):
+    mesh = ts.box_tet_mesh(n, (1.0, 0.8, 0.9), jitter=jitter, scramble_seed=seed, n_attr=n_attr, warp_amp=warp)
+    sp = ts.build_nd_tet_space(mesh, p)
+    interp, curl, qpts, qw = ts.nd_tet_tables(p, degree)
+    qd = ts.geom_qdata(mesh.node_coords(geom_order), mesh.attr, geom_order, qpts, qw)
+    return mesh, sp, interp, curl, qpts, qw, qd
+
+
+def _apply(kind, sp, interp, curl, qd, blob, x):
+    return O.apply_add_co(kind, interp, curl, sp.idx, sp.curl_orient, qd, blob, np.ascontiguousarray(x), np.zeros(sp.ndofs))
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_reference_element_is_unisolvent_and_dual(p):
+    el = ts.nd_tet_element(p)
+    assert el.P == ts.nd_tet_ndof(p) == p * (p + 2) * (p + 3) // 2
+    assert el.cond < 1e7
+    interp, _ = el.tabulate(el.nodes)                      # [3][P nodes][P shapes]
+    dual = np.einsum("cnd,nc->nd", interp, el.tangents)    # functional n of shape d
+    assert np.abs(dual - np.eye(el.P)).max() < 1e-9 * max(1.0, el.cond * 1e-4)
+
+
+def test_quadrature_is_exact_to_its_degree():
+    from math import factorial
+
+    for deg in (2, 5, 8, 12):
+        pts, w = ts.tet_quadrature(deg)
+        assert (pts >= 0).all() and (pts.sum(axis=1) <= 1 + 1e-14).all() and (w > 0).all()
+        for a in range(deg + 1):
+            for b in range(deg + 1 - a):
+                c = deg - a - b
+                exact = factorial(a) * factorial(b) * factorial(c) / factorial(a + b + c + 3)
+                assert abs((w * pts[:, 0] ** a * pts[:, 1] ** b * pts[:, 2] ** c).sum() - exact) < 1e-15
+
+
+def test_qdata_layout_matches_the_hex_oracle_convention():
+    """Same J -> {w detJ, adj(J)^T/detJ column-major} packing as orc_geom_hex_qdata (geom_33_qf.h:9-34):
+    an affine map applied to a hex and to a tet must give the same per-point factors."""
+    A = np.array([[1.3, 0.2, -0.1], [0.1, 0.9, 0.3], [-0.2, 0.05, 1.1]])
+    # hex: trilinear nodes of the unit cube mapped by A (lexicographic, component-major)
+    from palace_b200.host import hexspace as hs
+
+    nodes = hs.gauss_lobatto(2)
+    g = np.array([[x, y, z] for z in nodes for y in nodes for x in nodes])
+    xe_hex = (g @ A.T).T[None]
+    qh = O.geom_hex_qdata(np.ascontiguousarray(xe_hex), np.array([1], dtype=np.int32), 1, 2)
+    mesh = ts.TetMesh(ts._REF_VERTS @ A.T, np.array([[0, 1, 2, 3]]), np.array([1], dtype=np.int32))
+    pts, w = ts.tet_quadrature(2)
+    qt = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, pts, w)
+    assert np.allclose(qt[0, 2:, 0], qh[0, 2:, 0], rtol=1e-13, atol=1e-14)
+    assert np.isclose(qt[0, 1, :].sum(), np.linalg.det(A) / 6.0, rtol=1e-13)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_space_dimension_and_transformations(p):
+    mesh = ts.box_tet_mesh((2, 2, 1), jitter=0.2, scramble_seed=11)
+    sp = ts.build_nd_tet_space(mesh, p)
+    assert sp.ndofs == p * sp.n_edges + p * (p - 1) * sp.n_faces + p * (p - 1) * (p - 2) // 2 * mesh.ne
+    assert sorted(np.unique(sp.idx)) == list(range(sp.ndofs))
+    co = sp.curl_orient
+    assert co.dtype == np.int8 and np.abs(co).max() <= 1            # the reference casts to int8 (restriction.cpp:318-329)
+    for e in range(mesh.ne):
+        T = sp.dense_T(e)
+        assert abs(round(abs(np.linalg.det(T))) - 1) == 0            # unimodular: a change of basis on the shared face
+    if p == 1:
+        assert not co[:, :, 0].any() and not co[:, :, 2].any()
+    else:
+        assert co[:, :, 0].any() or co[:, :, 2].any()                # scrambled orders do need off-diagonal entries
+
+
+def _poly_field(deg, seed):
+    """Random vector polynomial of total degree <= deg, its curl, as callables on [n][3] points."""
+    rng = np.random.default_rng(seed)
+    expo = [(a, b, c) for a in range(deg + 1) for b in range(deg + 1 - a) for c in range(deg + 1 - a - b)]
+    coef = rng.standard_normal((3, len(expo)))
+
+    def mono(X, e, d=None):
+        e = list(e)
+        k = 1.0
+        if d is not None:
+            if e[d] == 0:
+                return np.zeros(X.shape[0])
+            k = e[d]
+            e[d] -= 1
+        return k * X[:, 0] ** e[0] * X[:, 1] ** e[1] * X[:, 2] ** e[2]
+
+    def field(X):
+        X = np.atleast_2d(X)
+        return np.stack([sum(coef[c, m] * mono(X, e) for m, e in enumerate(expo)) for c in range(3)], axis=1)
+
+    def dfield(X, c, d):
+        return sum(coef[c, m] * mono(X, e, d) for m, e in enumerate(expo))
+
+    def curl(X):
+        X = np.atleast_2d(X)
+        return np.stack([dfield(X, 2, 1) - dfield(X, 1, 2), dfield(X, 0, 2) - dfield(X, 2, 0), dfield(X, 1, 0) - dfield(X, 0, 1)], axis=1)
+
+    return (lambda x: field(x)[0] if np.ndim(x) == 1 else field(x)), curl
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_polynomial_fields_are_reproduced_on_scrambled_tets(p):
+    """Interpolate E in P_{p-1}^3 through the GLOBAL functionals, pull the dofs back through idx + the
+    tridiagonal transformation, evaluate with the reference tables and the covariant Piola map: must
+    return E (and curl E through the contravariant map) at every quadrature point of every element."""
+    mesh, sp, interp, curl, qpts, qw, qd = _problem(p, n=(2, 2, 1))
+    E, curlE = _poly_field(p - 1, 3)
+    x = ts.interpolate(mesh, sp, E)
+    for e in range(mesh.ne):
+        v = mesh.verts[mesh.elems[e]]
+        J = np.stack([v[1] - v[0], v[2] - v[0], v[3] - v[0]], axis=1)
+        xe = sp.dense_T(e) @ x[sp.idx[e]]
+        X = v[0] + qpts @ J.T
+        u_ref = np.einsum("cqd,d->qc", interp, xe)
+        c_ref = np.einsum("cqd,d->qc", curl, xe)
+        u = u_ref @ np.linalg.inv(J)                  # J^-T u_ref, row-vector form
+        c = c_ref @ J.T / np.linalg.det(J)            # J c_ref / detJ
+        scale = max(1.0, np.abs(E(X)).max())
+        assert np.abs(u - E(X)).max() < 1e-10 * scale
+        assert np.abs(c - curlE(X)).max() < 1e-9 * max(1.0, np.abs(curlE(X)).max())
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_energies_and_curl_of_gradients(p):
+    mesh, sp, interp, curl, qpts, qw, qd = _problem(p, n=(2, 1, 2), n_attr=1)
+    one = cf.coeff_ctx(a=1.0)
+    E, curlE = _poly_field(p - 1, 7)
+    x = ts.interpolate(mesh, sp, E)
+    Mx = _apply(O.ND_MASS, sp, interp, curl, qd, one, x)
+    Kx = _apply(O.CURLCURL, sp, interp, curl, qd, one, x)
+    # direct integration of |E|^2 and |curl E|^2 with the same rule (degree 2p >= 2(p-1): exact)
+    m_ref = k_ref = 0.0
+    for e in range(mesh.ne):
+        v = mesh.verts[mesh.elems[e]]
+        J = np.stack([v[1] - v[0], v[2] - v[0], v[3] - v[0]], axis=1)
+        X = v[0] + qpts @ J.T
+        wq = qw * np.linalg.det(J)
+        m_ref += (wq * (E(X) ** 2).sum(axis=1)).sum()
+        k_ref += (wq * (curlE(X) ** 2).sum(axis=1)).sum()
+    assert abs(x @ Mx - m_ref) < 1e-10 * m_ref
+    assert abs(x @ Kx - k_ref) < 1e-9 * max(k_ref, 1e-3 * m_ref)
+    # gradient of a degree-p scalar lies in P_{p-1}^3: the curl-curl operator annihilates it
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal(3)
+    if p == 1:
+        grad = lambda X: np.broadcast_to(a, np.atleast_2d(X).shape) if np.ndim(X) > 1 else a
+    else:
+        B = rng.standard_normal((3, 3))
+        B = B + B.T  # phi = a.x + x^T B x / 2 -> grad = a + B x  (degree 1 <= p - 1)
+        grad = lambda X: a + np.asarray(X) @ B
+    g = ts.interpolate(mesh, sp, grad)
+    Kg = _apply(O.CURLCURL, sp, interp, curl, qd, one, g)
+    Mg = _apply(O.ND_MASS, sp, interp, curl, qd, one, g)
+    assert np.linalg.norm(Kg) < 1e-10 * np.linalg.norm(Mg)
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_operator_is_symmetric_on_curved_tets_with_matrix_coefficients(p):
+    mesh, sp, interp, curl, qpts, qw, qd = _problem(p, n=(2, 1, 1), geom_order=2, warp=0.03, n_attr=3, degree=2 * p + 2)
+    assert (qd[:, 1, :] > 0).all()
+    am, mc = cf.test_suite_coefficient(3, "matrix")
+    blob = cf.coeff_ctx_pair(cf.coeff_ctx(am, mc, a=1.3), cf.coeff_ctx(am, mc[::-1].copy(), a=0.7, transpose=True))
+    rng = np.random.default_rng(4)
+    x, y = rng.random(sp.ndofs), rng.random(sp.ndofs)
+    Ax = _apply(O.CURLCURL_MASS, sp, interp, curl, qd, blob, x)
+    Ay = _apply(O.CURLCURL_MASS, sp, interp, curl, qd, blob, y)
+    assert abs(y @ Ax - x @ Ay) < 1e-12 * abs(y @ Ax)
+    assert x @ Ax > 0
+
+
+def test_curl_oriented_oracle_equals_element_matrix_assembly():
+    mesh, sp, interp, curl, qpts, qw, qd = _problem(2, n=(1, 1, 2))
+    blob = cf.coeff_ctx_pair(cf.coeff_ctx(a=1.0), cf.coeff_ctx(a=2.0))
+    Ae = O.element_matrices(O.CURLCURL_MASS, interp, curl, None, qd, blob, sp.P)
+    x = np.random.default_rng(0).random(sp.ndofs)
+    y_ref = np.zeros(sp.ndofs)
+    for e in range(mesh.ne):
+        T = sp.dense_T(e)
+        np.add.at(y_ref, sp.idx[e], T.T @ (Ae[e] @ (T @ x[sp.idx[e]])))
+    y = _apply(O.CURLCURL_MASS, sp, interp, curl, qd, blob, x)
+    assert np.linalg.norm(y - y_ref) < 1e-13 * np.linalg.norm(y_ref)
