@@ -135,8 +135,8 @@ void cmulti_dot(b2p_ctx *c, int m, const CCPtr *V, CCPtr w, int64_t n, cplx *out
       L.re[j] = j < mm ? V[j0 + j].re : nullptr;
       L.im[j] = j < mm ? V[j0 + j].im : nullptr;
     }
-    cmulti_dot_kernel<<<RED_BLOCKS, NT, 0, c->stream>>>(L, w.re, w.im, n, mm, part);
-    creduce_kernel<<<2 * mm, 32, 0, c->stream>>>(part, RED_BLOCKS, res);
+    B2P_LAUNCH(cmulti_dot_kernel, RED_BLOCKS, NT, 0, c->stream, L, w.re, w.im, n, mm, part);
+    B2P_LAUNCH(creduce_kernel, 2 * mm, 32, 0, c->stream, part, RED_BLOCKS, res);
     if (c->nranks > 1 && c->comm) b2p_allreduce_sum(c, res, 2 * mm);
     cudaMemcpyAsync(c->h_red, res, sizeof(double) * 2 * mm, cudaMemcpyDeviceToHost, c->stream);
     cudaStreamSynchronize(c->stream);
@@ -172,7 +172,7 @@ void cmulti_axpy(b2p_ctx *c, int m, const cplx *coef, const CCPtr *V, CPtr w, in
     }
     cudaMemcpyAsync(dcoef, h, sizeof(double) * 2 * mm, cudaMemcpyHostToDevice, c->stream);
     cudaStreamSynchronize(c->stream);  // h lives on this stack frame
-    cmulti_axpy_kernel<<<grid_for(c, n), NT, 0, c->stream>>>(L, dcoef, mm, sign, w.re, w.im, n);
+    B2P_LAUNCH(cmulti_axpy_kernel, grid_for(c, n), NT, 0, c->stream, L, dcoef, mm, sign, w.re, w.im, n);
   }
 }
 void caxpy(b2p_ctx *c, cplx a, CCPtr x, CPtr y, int64_t n) { cmulti_axpy(c, 1, &a, &x, y, n, 1.0); }

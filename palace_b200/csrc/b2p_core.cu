@@ -82,7 +82,7 @@ int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, co
 {
   const size_t total = (size_t)ne * q1d * q1d * q1d;
   const int nt = 128;
-  geom_hex_kernel<<<(unsigned)((total + nt - 1) / nt), nt, 0, s>>>(ne, k, q1d, d_xe, d_B, d_G, d_qw, d_qd);
+  B2P_LAUNCH(geom_hex_kernel, (unsigned)((total + nt - 1) / nt), nt, 0, s, ne, k, q1d, d_xe, d_B, d_G, d_qw, d_qd);
   B2P_CUDA(ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

@@ -17,17 +17,13 @@
 #include "b2p_internal.hpp"
 #include "b2p_qf.cuh"
 #include "b2p_contract.cuh"
+#include "b2p_pipe.cuh"
 
 namespace b2p
 {
 
 namespace
 {
-
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
-{
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 
 struct DenseParams
 {
@@ -48,7 +44,7 @@ constexpr int NEB = 8;
 
 __global__ void __launch_bounds__(256) dense_apply_kernel(DenseParams prm)
 {
-  extern __shared__ double sm[];
+  B2P_DYN_SMEM(double, sm);
   double *U = sm;                       // [Ppad][NEB]
   double *V = U + prm.Ppad * NEB;       // [Rpad][NEB]
   double *X = V + prm.Rpad * NEB;       // [P][NEB] raw gathered values (curl-oriented restriction only)
@@ -278,7 +274,7 @@ int launch_dense_apply(b2p_op *op, const int32_t *lidx, double alpha, const doub
     B2P_CUDA(op->ctx, cudaFuncSetAttribute(dense_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     configured = shmem;
   }
-  dense_apply_kernel<<<(prm.ne + NEB - 1) / NEB, 256, shmem, s>>>(prm);
+  B2P_LAUNCH(dense_apply_kernel, (prm.ne + NEB - 1) / NEB, 256, shmem, s, prm);
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
@@ -287,7 +283,7 @@ int launch_dense_diag(b2p_op *op, double *diag, cudaStream_t s)
 {
   DenseParams prm = make_params(op, op->lidx, 1.0, nullptr, diag, ApplyRange());
   const size_t total = (size_t)op->ne * op->P;
-  dense_diag_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(prm);
+  B2P_LAUNCH(dense_diag_kernel, (unsigned)((total + 127) / 128), 128, 0, s, prm);
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

@@ -8,6 +8,7 @@
 #include <nccl.h>
 
 #include "b2p_linalg.hpp"
+#include "b2p_pipe.cuh"
 
 namespace b2p
 {
@@ -69,7 +70,7 @@ __global__ void p2p_push_kernel(const double *__restrict__ src, const int32_t *_
       if (e > b)
       {
         __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_ptr[k]), "l"(ep) : "memory");
+        st_release_sys_u64(flag_ptr[k], ep);
       }
     }
   }
@@ -89,7 +90,7 @@ __global__ void p2p_wait_add_kernel(const long long *seg_off, const unsigned lon
     unsigned long long v;
     do
     {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + k) : "memory");
+      v = ld_acquire_sys_u64(flags + k);
     } while (v < want);
   }
   __syncthreads();
@@ -105,7 +106,7 @@ __global__ void p2p_wait_kernel(int nseg, const long long *seg_off, const unsign
     unsigned long long v;
     do
     {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + k) : "memory");
+      v = ld_acquire_sys_u64(flags + k);
     } while (v < ep);
   }
 }
@@ -117,9 +118,9 @@ int halo_forward_p2p(Halo *h, const double *x, bool in_kernel_wait, cudaStream_t
   if (nn == 0) return B2P_SUCCESS;
   const long long ns = h->send_off.back();
   dim3 grid((unsigned)std::min<long long>((ns / nn + 255) / 256 + 1, 32), nn);
-  p2p_push_kernel<<<grid, 256, 0, s>>>(x, h->d_send_idx, h->d_send_off, h->d_peer_fwd, h->d_peer_flag_fwd, h->d_epoch, h->d_done,
+  B2P_LAUNCH(p2p_push_kernel, grid, 256, 0, s, x, h->d_send_idx, h->d_send_off, h->d_peer_fwd, h->d_peer_flag_fwd, h->d_epoch, h->d_done,
                                        in_kernel_wait ? h->d_epoch + 2 * 32 : nullptr, h->d_recv_has, h->d_yg, h->n_ghost);
-  if (!in_kernel_wait) p2p_wait_kernel<<<1, 32, 0, s>>>(nn, h->d_recv_off, h->d_flags, h->d_epoch + 2 * 32);
+  if (!in_kernel_wait) B2P_LAUNCH(p2p_wait_kernel, 1, 32, 0, s, nn, h->d_recv_off, h->d_flags, h->d_epoch + 2 * 32);
   B2P_CUDA(h->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
@@ -130,10 +131,10 @@ int halo_reverse_p2p(Halo *h, double *y, cudaStream_t s)
   if (nn == 0) return B2P_SUCCESS;
   const long long nr = h->recv_off.back(), ns = h->send_off.back();
   dim3 grid((unsigned)std::min<long long>((nr / nn + 255) / 256 + 1, 32), nn);
-  p2p_push_kernel<<<grid, 256, 0, s>>>(h->d_yg ? h->d_yg : h->d_mail, nullptr, h->d_recv_off, h->d_peer_rev, h->d_peer_flag_rev, h->d_epoch + 32,
+  B2P_LAUNCH(p2p_push_kernel, grid, 256, 0, s, h->d_yg ? h->d_yg : h->d_mail, nullptr, h->d_recv_off, h->d_peer_rev, h->d_peer_flag_rev, h->d_epoch + 32,
                                        h->d_done + 32, nullptr);
   (void)ns;
-  p2p_wait_add_kernel<<<nn, 1024, 0, s>>>(h->d_send_off, h->d_flags + 32, h->d_epoch + 3 * 32, y, h->d_send_idx, h->d_mail_rev);
+  B2P_LAUNCH(p2p_wait_add_kernel, nn, 1024, 0, s, h->d_send_off, h->d_flags + 32, h->d_epoch + 3 * 32, y, h->d_send_idx, h->d_mail_rev);
   B2P_CUDA(h->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
@@ -143,7 +144,7 @@ int halo_forward(Halo *h, double *lx)
   if (!h || h->nbr.empty()) return B2P_SUCCESS;
   b2p_ctx *c = h->ctx;
   const int64_t ns = h->send_off.back();
-  if (ns > 0) pack_kernel<<<(int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, c->stream>>>(lx, h->d_send_idx, ns, h->d_buf);
+  if (ns > 0) B2P_LAUNCH(pack_kernel, (int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, c->stream, lx, h->d_send_idx, ns, h->d_buf);
   ncclGroupStart();
   for (size_t k = 0; k < h->nbr.size(); k++)
   {
@@ -162,7 +163,7 @@ int halo_forward_split(Halo *h, const double *x, cudaStream_t s)
   if (!h || h->nbr.empty()) return B2P_SUCCESS;
   b2p_ctx *c = h->ctx;
   const int64_t ns = h->send_off.back();
-  if (ns > 0) pack_kernel<<<(int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, s>>>(x, h->d_send_idx, ns, h->d_buf);
+  if (ns > 0) B2P_LAUNCH(pack_kernel, (int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, s, x, h->d_send_idx, ns, h->d_buf);
   ncclGroupStart();
   for (size_t k = 0; k < h->nbr.size(); k++)
   {
@@ -189,7 +190,7 @@ int halo_reverse_split(Halo *h, double *y, cudaStream_t s)
   }
   ncclResult_t r = ncclGroupEnd();
   B2P_CHECK(c, r == ncclSuccess, B2P_ERR_NCCL, "halo_reverse_split: %s", ncclGetErrorString(r));
-  if (ns > 0) unpack_add_kernel<<<(int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, s>>>(y, h->d_send_idx, ns, h->d_buf);
+  if (ns > 0) B2P_LAUNCH(unpack_add_kernel, (int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, s, y, h->d_send_idx, ns, h->d_buf);
   return B2P_SUCCESS;
 }
 
@@ -208,7 +209,7 @@ int halo_reverse(Halo *h, double *ly)
   ncclResult_t r = ncclGroupEnd();
   B2P_CHECK(c, r == ncclSuccess, B2P_ERR_NCCL, "halo_reverse: %s", ncclGetErrorString(r));
   if (ns > 0)
-    unpack_add_kernel<<<(int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, c->stream>>>(ly, h->d_send_idx, ns, h->d_buf);
+    B2P_LAUNCH(unpack_add_kernel, (int)std::min<int64_t>((ns + 255) / 256, 1024), 256, 0, c->stream, ly, h->d_send_idx, ns, h->d_buf);
   return B2P_SUCCESS;
 }
 

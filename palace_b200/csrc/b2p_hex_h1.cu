@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(NT) h1_hex_diffusion_kernel(H1Params prm)
 {
   using L = H1Layout<P_, Q_>;
   constexpr int p = L::p, q = L::q, n = L::n, P = L::P, Q = L::Q, N1 = L::N1, N2 = L::N2, ES = L::PER_ELEM;
-  extern __shared__ double smem[];
+  B2P_DYN_SMEM(double, smem);
   double *sBc = smem;
   double *sGc = sBc + q * n;
   double *U = sGc + q * n;
@@ -207,7 +207,7 @@ int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, do
   }
   const int ne_run = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
   if (ne_run <= 0) return B2P_SUCCESS;
-  kern<<<(ne_run + NEB - 1) / NEB, NT, shmem, s>>>(make_params(op, lidx, alpha, x, y, rg));
+  B2P_LAUNCH(kern, (ne_run + NEB - 1) / NEB, NT, shmem, s, make_params(op, lidx, alpha, x, y, rg));
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
@@ -235,7 +235,7 @@ int launch_h1_hex_diag(b2p_op *op, double *diag, cudaStream_t s)
   H1Params prm = make_params(op, op->lidx, 1.0, nullptr, diag);
   const size_t total = (size_t)op->ne * op->P;
   const int nt = 128;
-  h1_hex_diag_kernel<<<(unsigned)((total + nt - 1) / nt), nt, 0, s>>>(prm, op->p, op->q1d, op->assembled);
+  B2P_LAUNCH(h1_hex_diag_kernel, (unsigned)((total + nt - 1) / nt), nt, 0, s, prm, op->p, op->q1d, op->assembled);
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) h1_hex_apply3_kernel(const __gr
   constexpr int q = L::q, n = L::n, Q = L::Q, ES = L::ES, GE = L::GE, PS = L::PS, NEW = L::NEW;
   constexpr int QQ = q * q;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  B2P_DYN_SMEM_ALIGNED16(unsigned char, smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned char *wbase = smem_raw + (size_t)wid * L::WS;
   double *sG = (double *)(wbase + L::OFF_G);
@@ -437,7 +437,7 @@ int launch_h1v3(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   const int nb = (e_cnt + L::NEW - 1) / L::NEW;
   int grid = op->ctx->sm_count * MINB;
   if (grid > (nb + NW - 1) / NW) grid = (nb + NW - 1) / NW;
-  kern<<<grid, NW * 32, shmem, s>>>(prm);
+  B2P_LAUNCH(kern, grid, NW * 32, shmem, s, prm);
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

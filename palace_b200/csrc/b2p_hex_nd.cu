@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(NT) nd_hex_apply_kernel(NDParams prm)
   constexpr bool CURL = (KIND == B2P_CURLCURL || KIND == B2P_CURLCURL_MASS);
   constexpr int ES = L::PER_ELEM;
 
-  extern __shared__ double smem[];
+  B2P_DYN_SMEM(double, smem);
   double *sBo = smem;            // [q][p]
   double *sBc = sBo + q * p;     // [q][n]
   double *sGc = sBc + q * n;     // [q][n]
@@ -424,7 +424,7 @@ int launch_pq(b2p_op *op, const int32_t *lidx, double alpha, const double *x, do
   const int ne_run = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
   if (ne_run <= 0) return B2P_SUCCESS;
   const int grid = (ne_run + NEB - 1) / NEB;
-  kern<<<grid, NT, shmem, s>>>(make_params(op, lidx, alpha, x, y, rg));
+  B2P_LAUNCH(kern, grid, NT, shmem, s, make_params(op, lidx, alpha, x, y, rg));
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }
@@ -474,10 +474,10 @@ int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s)
   const unsigned grid = (unsigned)((total + nt - 1) / nt);
   switch (op->kind)
   {
-    case B2P_CURLCURL: nd_hex_diag_kernel<B2P_CURLCURL><<<grid, nt, 0, s>>>(prm, op->p, op->q1d, op->assembled); break;
-    case B2P_ND_MASS: nd_hex_diag_kernel<B2P_ND_MASS><<<grid, nt, 0, s>>>(prm, op->p, op->q1d, op->assembled); break;
+    case B2P_CURLCURL: B2P_LAUNCH(nd_hex_diag_kernel<B2P_CURLCURL>, grid, nt, 0, s, prm, op->p, op->q1d, op->assembled); break;
+    case B2P_ND_MASS: B2P_LAUNCH(nd_hex_diag_kernel<B2P_ND_MASS>, grid, nt, 0, s, prm, op->p, op->q1d, op->assembled); break;
     case B2P_CURLCURL_MASS:
-      nd_hex_diag_kernel<B2P_CURLCURL_MASS><<<grid, nt, 0, s>>>(prm, op->p, op->q1d, op->assembled);
+      B2P_LAUNCH(nd_hex_diag_kernel<B2P_CURLCURL_MASS>, grid, nt, 0, s, prm, op->p, op->q1d, op->assembled);
       break;
     default: set_error(op->ctx, "nd_hex_diag: unsupported kind %d", op->kind); return B2P_ERR_UNSUPPORTED;
   }
@@ -494,10 +494,10 @@ int launch_assemble_qdata(b2p_op *op, cudaStream_t s)
   const unsigned grid = (unsigned)((total + nt - 1) / nt);
   switch (op->kind)
   {
-    case B2P_CURLCURL: nd_assemble_qdata_kernel<B2P_CURLCURL><<<grid, nt, 0, s>>>(prm, Q, op->aq); break;
-    case B2P_ND_MASS: nd_assemble_qdata_kernel<B2P_ND_MASS><<<grid, nt, 0, s>>>(prm, Q, op->aq); break;
-    case B2P_CURLCURL_MASS: nd_assemble_qdata_kernel<B2P_CURLCURL_MASS><<<grid, nt, 0, s>>>(prm, Q, op->aq); break;
-    case B2P_H1_DIFFUSION: nd_assemble_qdata_kernel<B2P_H1_DIFFUSION><<<grid, nt, 0, s>>>(prm, Q, op->aq); break;
+    case B2P_CURLCURL: B2P_LAUNCH(nd_assemble_qdata_kernel<B2P_CURLCURL>, grid, nt, 0, s, prm, Q, op->aq); break;
+    case B2P_ND_MASS: B2P_LAUNCH(nd_assemble_qdata_kernel<B2P_ND_MASS>, grid, nt, 0, s, prm, Q, op->aq); break;
+    case B2P_CURLCURL_MASS: B2P_LAUNCH(nd_assemble_qdata_kernel<B2P_CURLCURL_MASS>, grid, nt, 0, s, prm, Q, op->aq); break;
+    case B2P_H1_DIFFUSION: B2P_LAUNCH(nd_assemble_qdata_kernel<B2P_H1_DIFFUSION>, grid, nt, 0, s, prm, Q, op->aq); break;
     default: set_error(op->ctx, "assemble_qdata: unsupported kind %d", op->kind); return B2P_ERR_UNSUPPORTED;
   }
   B2P_CUDA(op->ctx, cudaGetLastError());

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
   constexpr bool MASS = L::MASS, CURL = L::CURL;
   constexpr int QQ = q * q;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  B2P_DYN_SMEM_ALIGNED16(unsigned char, smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned char *wbase = smem_raw + (size_t)wid * L::WS;
   double *sG = (double *)(wbase + L::OFF_G);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
       unsigned long long v;
       do
       {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(prm.wait_flags + lane) : "memory");
+        v = ld_acquire_sys_u64(prm.wait_flags + lane);
       } while (v < want);
     }
     __syncwarp();
@@ -771,7 +771,7 @@ int launch4(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   const int nb = (e_cnt + L::NEW - 1) / L::NEW;
   int grid = op->ctx->sm_count * MINB;
   if (grid > (nb + NW - 1) / NW) grid = (nb + NW - 1) / NW;
-  kern<<<grid, NW * 32, shmem, s>>>(prm);
+  B2P_LAUNCH(kern, grid, NW * 32, shmem, s, prm);
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply5_kernel(const __gr
   constexpr int IPX = p * n, IPZ = n * n, IX = p * q, IN = n * q;
   static_assert(IPX <= 16 && IPZ <= 16 && IX <= 16 && IN <= 16, "one half-warp per item set");
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  B2P_DYN_SMEM_ALIGNED16(unsigned char, smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int h = lane >> 4, t = lane & 15;
   const double sgn = h ? -1.0 : 1.0;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply5_kernel(const __gr
       unsigned long long v;
       do
       {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(prm.wait_flags + lane) : "memory");
+        v = ld_acquire_sys_u64(prm.wait_flags + lane);
       } while (v < want);
     }
     __syncwarp();
@@ -691,7 +691,7 @@ int launch5(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   for (int i = 0; i < q * n; i++) prm.Gc[i] = op->h_tab[q * P_ + q * n + i];
   int grid = op->ctx->sm_count * MINB;
   if (grid > (e_cnt + NW - 1) / NW) grid = (e_cnt + NW - 1) / NW;
-  kern<<<grid, NW * 32, shmem, s>>>(prm);
+  B2P_LAUNCH(kern, grid, NW * 32, shmem, s, prm);
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

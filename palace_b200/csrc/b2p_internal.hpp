@@ -41,6 +41,20 @@ void set_error(b2p_ctx *ctx, const char *fmt, ...);
 template <typename T>
 int upload(b2p_ctx *ctx, const T *host, size_t n, T **dptr);
 
+// Kernel launch and dynamic shared memory go through these two macros so that the kernel SOURCES can also be
+// compiled for the host-thread SIMT emulation of tests/emu (test infrastructure: B2P_EMU is defined only by
+// tests/emu/Makefile, never for libb2p.so). In the product build they expand to the plain CUDA constructs.
+#ifdef B2P_EMU
+#define B2P_LAUNCH(kern, grid, block, shmem, stream, ...) \
+  ::cuda_emu::launch(dim3(grid), dim3(block), (size_t)(shmem), [=]() { kern(__VA_ARGS__); })
+#define B2P_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(::cuda_emu::dyn_smem())
+#define B2P_DYN_SMEM_ALIGNED16(type, name) B2P_DYN_SMEM(type, name)
+#else
+#define B2P_LAUNCH(kern, grid, block, shmem, stream, ...) kern<<<(grid), (block), (shmem), (stream)>>>(__VA_ARGS__)
+#define B2P_DYN_SMEM(type, name) extern __shared__ type name[]
+#define B2P_DYN_SMEM_ALIGNED16(type, name) extern __shared__ __align__(16) type name[]
+#endif
+
 }  // namespace b2p
 
 struct b2p_ctx

@@ -32,7 +32,7 @@ struct InterpParams
 template <bool TRANSPOSE>
 __global__ void interp_kernel(InterpParams prm, int neb)
 {
-  extern __shared__ double sm[];
+  B2P_DYN_SMEM(double, sm);
   double *smat = sm;                 // [n_mats]
   double *sv = sm + prm.n_mats;      // [neb][src_P]
   const int src_P = TRANSPOSE ? prm.out_P : prm.in_P;
@@ -205,9 +205,9 @@ int interp_apply(const b2p_interp *it, bool transpose, double alpha, const doubl
   const size_t shmem = sizeof(double) * ((size_t)it->n_mats + (size_t)neb * src_P);
   const int grid = (it->ne + neb - 1) / neb;
   if (transpose)
-    interp_kernel<true><<<grid, 256, shmem, s>>>(prm, neb);
+    B2P_LAUNCH(interp_kernel<true>, grid, 256, shmem, s, prm, neb);
   else
-    interp_kernel<false><<<grid, 256, shmem, s>>>(prm, neb);
+    B2P_LAUNCH(interp_kernel<false>, grid, 256, shmem, s, prm, neb);
   B2P_CUDA(it->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

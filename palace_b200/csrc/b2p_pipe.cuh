@@ -6,6 +6,36 @@
 namespace b2p
 {
 
+#ifdef B2P_EMU
+// Host-thread SIMT emulation (tests/emu/cuda_emu.hpp, test infrastructure): same protocol, no PTX.
+inline void mbar_init(uint64_t *bar, int count) { ::cuda_emu::mbar_init(bar, count); }
+inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { ::cuda_emu::mbar_expect_tx(bar, bytes); }
+inline void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { ::cuda_emu::tma_bulk_g2s(dst, src, bytes, bar); }
+inline void mbar_wait(uint64_t *bar, uint32_t parity) { ::cuda_emu::mbar_wait(bar, parity); }
+inline void cp_async8(void *dst, const void *src) { ::cuda_emu::cp_async(dst, src, 8); }
+inline void cp_async_commit() { ::cuda_emu::cp_async_commit(); }
+template <int N>
+inline void cp_async_wait()
+{
+  ::cuda_emu::cp_async_wait(N);
+}
+inline void fence_proxy_async() {}
+inline unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+  ::cuda_emu::yield();  // (spin loops on the halo flags: let the other fibers run)
+  return *(const volatile unsigned long long *)p;
+}
+inline void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+  *(volatile unsigned long long *)p = v;
+  ::cuda_emu::st().events++;
+}
+inline void dmma884(double &c0, double &c1, double a, double b) { ::cuda_emu::dmma884(c0, c1, a, b); }
+inline void red_add_f64_if(double *addr, double v, bool pred)
+{
+  if (pred) atomicAdd(addr, v);
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -52,6 +82,24 @@ __device__ __forceinline__ void cp_async_wait()
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// FP64 tensor-core MMA, D(8x8) = A(8x4) B(4x8) + C: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// {c0, c1} = C[lane/4][2 (lane%4) + {0, 1}]  (SASS DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
+
 // Staged dof value with the restriction's sign (masked / padded slots were staged as zero):
 // the sign bit of the index is XORed into the high word of the value.
 __device__ __forceinline__ double staged(const int32_t *cI, const double *cU, int pos, bool valid)
@@ -70,6 +118,9 @@ __device__ __forceinline__ void scatter_fast(double *y, int32_t gi, double v)
   const int hi = __double2hiint(v) ^ (gi & (int)0x80000000);
   const double sv = __hiloint2double(hi, __double2loint(v));
   double *addr = y + (uint32_t)abs_idx(gi);
+#ifdef B2P_EMU
+  red_add_f64_if(addr, sv, gi != (int32_t)0x80000000);
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -78,6 +129,7 @@ __device__ __forceinline__ void scatter_fast(double *y, int32_t gi, double v)
       "}\n" ::"l"(addr),
       "d"(sv), "r"(gi)
       : "memory");
+#endif
 }
 
 
@@ -89,6 +141,9 @@ __device__ __forceinline__ void scatter_fast_split(double *y, const VSplit &sp, 
   const double sv = __hiloint2double(hi, __double2loint(v));
   const uint32_t a = (uint32_t)abs_idx(gi), no = (uint32_t)sp.n_owned;
   double *addr = (a < no) ? y + a : sp.yg + (a - no);
+#ifdef B2P_EMU
+  red_add_f64_if(addr, sv, gi != (int32_t)0x80000000);
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -97,6 +152,7 @@ __device__ __forceinline__ void scatter_fast_split(double *y, const VSplit &sp, 
       "}\n" ::"l"(addr),
       "d"(sv), "r"(gi)
       : "memory");
+#endif
 }
 __device__ __forceinline__ const double *split_src_fast(const double *x, const VSplit &sp, int32_t a)
 {

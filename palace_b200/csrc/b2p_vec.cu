@@ -57,7 +57,7 @@ template <typename F>
 void launch_ew(b2p_ctx *c, int64_t n, F f)
 {
   if (n <= 0) return;
-  ew_kernel<<<grid_for(c, n), NT, 0, c->stream>>>(n, f);
+  B2P_LAUNCH(ew_kernel, grid_for(c, n), NT, 0, c->stream, n, f);
 }
 
 // Block reduction of up to MAXM partial sums per thread.
@@ -160,7 +160,7 @@ double *red_results(b2p_ctx *c) { return c->d_red + (size_t)MAXM * RED_BLOCKS; }
 
 void reduce_finish(b2p_ctx *c, int m, double *host_out)
 {
-  final_reduce_kernel<<<m, 32, 0, c->stream>>>(red_partials(c), m, RED_BLOCKS, red_results(c));
+  B2P_LAUNCH(final_reduce_kernel, m, 32, 0, c->stream, red_partials(c), m, RED_BLOCKS, red_results(c));
   if (c->nranks > 1 && c->comm)
     ncclAllReduce(red_results(c), red_results(c), m, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
   cudaMemcpyAsync(c->h_red, red_results(c), sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
@@ -259,13 +259,13 @@ void multi_dot(b2p_ctx *c, int m, const double *const *V, const double *w, int64
     VecList L;
     for (int j = 0; j < MAXM; j++) L.v[j] = j < mm ? V[j0 + j] : nullptr;
     if (mm == 1)
-      multi_dot_kernel<1><<<RED_BLOCKS, NT, 0, c->stream>>>(L, w, n, mm, red_partials(c));
+      B2P_LAUNCH(multi_dot_kernel<1>, RED_BLOCKS, NT, 0, c->stream, L, w, n, mm, red_partials(c));
     else if (mm == 2)
-      multi_dot_kernel<2><<<RED_BLOCKS, NT, 0, c->stream>>>(L, w, n, mm, red_partials(c));
+      B2P_LAUNCH(multi_dot_kernel<2>, RED_BLOCKS, NT, 0, c->stream, L, w, n, mm, red_partials(c));
     else if (mm <= 4)
-      multi_dot_kernel<4><<<RED_BLOCKS, NT, 0, c->stream>>>(L, w, n, mm, red_partials(c));
+      B2P_LAUNCH(multi_dot_kernel<4>, RED_BLOCKS, NT, 0, c->stream, L, w, n, mm, red_partials(c));
     else
-      multi_dot_kernel<8><<<RED_BLOCKS, NT, 0, c->stream>>>(L, w, n, mm, red_partials(c));
+      B2P_LAUNCH(multi_dot_kernel<8>, RED_BLOCKS, NT, 0, c->stream, L, w, n, mm, red_partials(c));
     reduce_finish(c, mm, out + j0);
   }
 }
@@ -280,7 +280,7 @@ double dot(b2p_ctx *c, const double *x, const double *y, int64_t n)
 
 double sum(b2p_ctx *c, const double *x, int64_t n)
 {
-  sum_kernel<<<RED_BLOCKS, NT, 0, c->stream>>>(x, n, red_partials(c));
+  B2P_LAUNCH(sum_kernel, RED_BLOCKS, NT, 0, c->stream, x, n, red_partials(c));
   double out = 0.0;
   reduce_finish(c, 1, &out);
   return out;
@@ -296,7 +296,7 @@ void multi_axpy(b2p_ctx *c, int m, const double *coef, const double *const *V, d
     for (int j = 0; j < MAXM; j++) L.v[j] = j < mm ? V[j0 + j] : nullptr;
     double *dcoef = red_results(c) + MAXM;  // scratch after the results
     cudaMemcpyAsync(dcoef, coef + j0, sizeof(double) * mm, cudaMemcpyHostToDevice, c->stream);
-    multi_axpy_kernel<<<grid_for(c, n), NT, 0, c->stream>>>(L, dcoef, mm, sign, w, n);
+    B2P_LAUNCH(multi_axpy_kernel, grid_for(c, n), NT, 0, c->stream, L, dcoef, mm, sign, w, n);
   }
 }
 

@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    if os.environ.get("B2P_EMU_TESTS") == "1":
+        # pre-GPU validation: the same tests against the host-thread SIMT emulation build of the kernel sources
+        from tests.emu import emu_mode
+
+        emu_mode.enable()
 
 
 @pytest.fixture(scope="session")
