@@ -284,6 +284,9 @@ int b2p_coperator_mult(b2p_coperator *A, const double *xr, const double *xi, dou
 int b2p_coperator_mult_hermitian_transpose(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi);
 int b2p_coperator_add_mult(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi, double ar, double ai);
 int b2p_coperator_assemble_diagonal(b2p_coperator *A, double *dr, double *di);
+/* Number of Mult / MultHermitianTranspose calls served by the fused complex element kernel (one pass over the geometry
+ * for all terms and both vector parts) instead of 2-4 real applies per term; -1 if A is not a sum operator. */
+long b2p_coperator_fused_applies(b2p_coperator *A);
 void b2p_coperator_destroy(b2p_coperator *A);
 /* A real preconditioner (any b2p_solver, e.g. the multigrid) applied to the real and imaginary parts: the
  * "PCMatReal" configuration (models/spaceoperator.cpp:1098-1105, utils/configfile.hpp:1051). */

@@ -562,6 +562,11 @@ class ComplexOperator:
     def mult(self, xr, xi, yr, yi):
         _chk(lib().b2p_coperator_mult(self.h, _vp(xr), _vp(xi), _vp(yr), _vp(yi)), self.ctx.h)
 
+    def fused_applies(self):
+        f = lib().b2p_coperator_fused_applies
+        f.restype = C.c_long
+        return int(f(self.h))
+
     def mult_hermitian_transpose(self, xr, xi, yr, yi):
         _chk(lib().b2p_coperator_mult_hermitian_transpose(self.h, _vp(xr), _vp(xi), _vp(yr), _vp(yi)), self.ctx.h)
 

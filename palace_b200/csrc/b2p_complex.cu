@@ -214,8 +214,80 @@ public:
     if (n_ess > 0) upload(c, ess, (size_t)n_ess, &d_ess);
     for (auto &t : terms)
       if (!t.op->lidx_bc) b2p_op_set_essential(t.op, ess, n_ess);
+    build_fused();
   }
-  ~ComplexParOperator() override { cudaFree(d_ess); }
+  ~ComplexParOperator() override
+  {
+    cudaFree(d_ess);
+    cudaFree(zcoef);
+    cudaFree(zcoef_h);
+  }
+
+  // Fused path: when every term is a sum-factorised ND operator over the same geometry, space and essential set,
+  // the complex sum  sum_i (c_i^r + i c_i^i) A_i  is ONE element operator whose pointwise coefficient is complex:
+  // per element {mass Re, mass Im, curl Re, curl Im} 3x3 tensors = sum_i c_i * (material tensor of term i). One
+  // kernel launch then replaces the 2-4 real applies per term of the reference's ComplexWrapperOperator
+  // (operator.cpp:98-134) and streams the geometry once.
+  void build_fused()
+  {
+    // Opt-in for now (B2P_COMPLEX_FUSED=1): validated against the term-by-term path under the SIMT emulation of
+    // tests/emu and by tests/test_zfused_gpu.py; becomes the default once measured on a B200.
+    const char *env = std::getenv("B2P_COMPLEX_FUSED");
+    if (!env || env[0] != '1') return;
+    const b2p_op *o0 = terms[0].op;
+    for (auto &t : terms)
+    {
+      const b2p_op *o = t.op;
+      if (!nd_hex_apply4z_eligible(o) || o->geom != o0->geom || o->p != o0->p || o->q1d != o0->q1d || o->ne != o0->ne ||
+          o->lsize != o0->lsize || o->PS != o0->PS || !o->ecoef || !o->lidx_bc)
+        return;
+    }
+    const size_t nidx = (size_t)o0->ne * o0->PS;
+    std::vector<int32_t> a(nidx), b(nidx);
+    if (cudaMemcpy(a.data(), o0->lidx_bc, nidx * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    for (size_t i = 1; i < terms.size(); i++)
+    {
+      if (cudaMemcpy(b.data(), terms[i].op->lidx_bc, nidx * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+      if (a != b) return;  // different restriction or essential set
+    }
+    const int ne = o0->ne;
+    std::vector<double> z((size_t)36 * ne, 0.0), e18((size_t)18 * ne);
+    bool mass = false, curl = false;
+    fused_imag = false;
+    for (auto &t : terms)
+    {
+      if (cudaMemcpy(e18.data(), t.op->ecoef, e18.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+      const bool m = (t.op->kind == B2P_ND_MASS || t.op->kind == B2P_CURLCURL_MASS);
+      const bool k = (t.op->kind == B2P_CURLCURL || t.op->kind == B2P_CURLCURL_MASS);
+      mass = mass || m;
+      curl = curl || k;
+      fused_imag = fused_imag || t.ci != 0.0;
+      for (int e = 0; e < ne; e++)
+        for (int i = 0; i < 9; i++)
+        {
+          if (m)
+          {
+            z[(size_t)36 * e + i] += t.cr * e18[(size_t)18 * e + i];
+            z[(size_t)36 * e + 9 + i] += t.ci * e18[(size_t)18 * e + i];
+          }
+          if (k)
+          {
+            z[(size_t)36 * e + 18 + i] += t.cr * e18[(size_t)18 * e + 9 + i];
+            z[(size_t)36 * e + 27 + i] += t.ci * e18[(size_t)18 * e + 9 + i];
+          }
+        }
+    }
+    fused_kind = mass && curl ? B2P_CURLCURL_MASS : (mass ? B2P_ND_MASS : B2P_CURLCURL);
+    if (upload(ctx, z.data(), z.size(), &zcoef)) return;
+    for (int e = 0; e < ne; e++)  // Hermitian transpose: conjugated coefficients (the A_i are real symmetric)
+      for (int i = 0; i < 9; i++)
+      {
+        z[(size_t)36 * e + 9 + i] = -z[(size_t)36 * e + 9 + i];
+        z[(size_t)36 * e + 27 + i] = -z[(size_t)36 * e + 27 + i];
+      }
+    if (upload(ctx, z.data(), z.size(), &zcoef_h)) return;
+    fused = true;
+  }
 
   // operator.cpp:98-134 with A = sum_i c_i A_i: y_r = sum (c^r A x_r - c^i A x_i), y_i = sum (c^i A x_r + c^r A x_i);
   // essential rows as in ComplexParOperator::Mult (rap.cpp:481-517)
@@ -224,6 +296,11 @@ public:
     cudaStream_t s = ctx->stream;
     vec::set(ctx, y.re, n, 0.0);
     vec::set(ctx, y.im, n, 0.0);
+    b2p_op *o0 = terms[0].op;
+    if (fused && launch_nd_hex_apply4z(o0, fused_kind, o0->lidx_bc, herm ? zcoef_h : zcoef, fused_imag ? 1 : 0, 1.0, x.re, x.im, y.re,
+                                       y.im, s) == B2P_SUCCESS)
+      n_fused_applies++;
+    else
     for (auto &t : terms)
     {
       const double ci = herm ? -t.ci : t.ci;
@@ -277,6 +354,13 @@ public:
 private:
   std::vector<Term> terms;
   int32_t *d_ess = nullptr;
+  // fused complex element operator (build_fused)
+  bool fused = false, fused_imag = false;
+  int fused_kind = 0;
+  double *zcoef = nullptr, *zcoef_h = nullptr;
+
+public:
+  mutable long n_fused_applies = 0;
   int64_t n_ess;
   int diag_policy;
 };
@@ -711,6 +795,11 @@ int b2p_coperator_assemble_diagonal(b2p_coperator *A, double *dr, double *di)
   if (!A) return B2P_ERR_ARG;
   B2P_CTRY(A->op->ctx, A->op->AssembleDiagonal(CPtr{dr, di}));
   return B2P_SUCCESS;
+}
+long b2p_coperator_fused_applies(b2p_coperator *A)
+{
+  auto *p = A ? dynamic_cast<ComplexParOperator *>(A->op.get()) : nullptr;
+  return p ? p->n_fused_applies : -1;
 }
 void b2p_coperator_destroy(b2p_coperator *A) { delete A; }
 

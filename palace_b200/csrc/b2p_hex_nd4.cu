@@ -29,6 +29,7 @@
 // (/root/reference/palace/fem/libceed/operator.cpp:148-178,192-212); D from
 // /root/reference/palace/fem/qfunctions/33/{hdiv,hcurl,hdivmass}_33_qf.h.
 #include <cstdlib>
+#include <type_traits>
 
 #include "b2p_internal.hpp"
 #include "b2p_qf.cuh"
@@ -63,6 +64,22 @@ struct ND4Params
   double Gc[Q_ * (P_ + 1)];
 };
 
+// Fused complex apply (CPLX kernels): y_r + i y_i += alpha * E^T B^T (D_r + i D_i) B E (x_r + i x_i) in ONE pass
+// over the geometry. The two parts of a vector ride in adjacent element slots of a warp, so restriction indices,
+// q-data and coefficient block are fetched once for both. zcoef[ne][36] holds the per-element complex coefficient
+// tensors {mass Re, mass Im, curl Re, curl Im} (column-major 3x3 each): the sum over the terms of a complex
+// operator of (c_r + i c_i) * material tensor, so K, M and every mass-type loss term of
+// /root/reference/palace/linalg/operator.cpp:98-134 (ComplexWrapperOperator: four real applies per term)
+// cost one kernel launch and one geometry stream.
+template <int P_, int Q_>
+struct ND4ParamsZ : ND4Params<P_, Q_>
+{
+  const double *xi;     // imaginary part of the input
+  double *yi;           // imaginary part of the output
+  const double *zcoef;  // [ne][36]
+  int has_imag;         // some coefficient has an imaginary part (otherwise the parts never mix)
+};
+
 struct Nd4Pad
 {
   int p, q, kind, a, b, y;
@@ -90,7 +107,7 @@ constexpr int nd4_lane_stride(int items, int nel)
   return (nel * pc <= 32 * rounds) ? pc : items;
 }
 
-template <int P_, int Q_, int KIND, bool ASM>
+template <int P_, int Q_, int KIND, bool ASM, bool CPLX = false>
 struct ND4Layout
 {
   static constexpr int p = P_, q = Q_, n = P_ + 1, Q = q * q * q, P = 3 * p * n * n, D3 = p * n * n;
@@ -98,7 +115,9 @@ struct ND4Layout
   static constexpr bool MASS = (KIND == B2P_ND_MASS || KIND == B2P_CURLCURL_MASS);
   static constexpr bool CURL = (KIND == B2P_CURLCURL || KIND == B2P_CURLCURL_MASS);
   // elements per warp: enough (qy,qz) lines to fill the 32 lanes in the XDX phase
-  static constexpr int NEW = (q * q >= 32) ? 1 : 32 / (q * q);
+  static constexpr int NEW0 = (q * q >= 32) ? 1 : 32 / (q * q);
+  // CPLX: the slots of a warp are (element, part) pairs, parts adjacent -> an even number of slots
+  static constexpr int NPART = CPLX ? 2 : 1, NEW = CPLX ? (NEW0 & ~1) : NEW0, NEB = NEW / NPART;
   static constexpr Nd4Pad PAD = nd4_pads(P_, Q_, KIND);
   // items of one element inside a row, in the consumer's order t = qz + q*i
   static constexpr int NXA = p * q, NNA = n * q;
@@ -116,22 +135,27 @@ struct ND4Layout
   static constexpr int LSX = nd4_lane_stride(p * n, NEW), LSZ = nd4_lane_stride(n * n, NEW);
   static constexpr int GCOMP = ASM ? ((MASS ? 9 : 0) + (CURL ? 9 : 0)) : 10;
   static constexpr int GE = (GCOMP * Q + 1) & ~1;  // doubles of q-data per element (even: 16-byte blocks for TMA)
-  static constexpr int CE = 18;                    // coefficient matrices per element
+  static constexpr int CE = CPLX ? 36 : 18;        // coefficient matrices per element
   // per-warp shared memory (bytes), every block 16-byte aligned
   static constexpr int OFF_G = 0;
-  static constexpr int OFF_W = OFF_G + NEW * GE * 8;
+  static constexpr int OFF_W = OFF_G + NEB * GE * 8;
   static constexpr int OFF_U = OFF_W + WTOT * 8;                 // [NEW*PS] doubles: staged x values
-  static constexpr int OFF_I = OFF_U + NEW * PS * 8;             // [3][NEW*PS] int32: restriction index ring
-  static constexpr int OFF_C = OFF_I + 3 * NEW * PS * 4;         // [NEW*18] doubles
-  static constexpr int OFF_B = OFF_C + ((NEW * CE * 8 + 15) & ~15);  // 4 mbarriers
+  static constexpr int OFF_I = OFF_U + NEW * PS * 8;             // [3][NEB*PS] int32: restriction index ring
+  static constexpr int OFF_C = OFF_I + 3 * NEB * PS * 4;         // [NEB*CE] doubles
+  static constexpr int OFF_B = OFF_C + ((NEB * CE * 8 + 15) & ~15);  // 4 mbarriers
   static constexpr int WS = (OFF_B + 4 * 8 + 15) & ~15;
 };
 
-template <int P_, int Q_, int KIND, bool ASM, bool SPLIT, int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __grid_constant__ ND4Params<P_, Q_> prm)
+template <int P_, int Q_, bool CPLX>
+using ND4ParamsT = std::conditional_t<CPLX, ND4ParamsZ<P_, Q_>, ND4Params<P_, Q_>>;
+
+template <int P_, int Q_, int KIND, bool ASM, bool SPLIT, int NW, int MINB, bool CPLX = false>
+__global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __grid_constant__ ND4ParamsT<P_, Q_, CPLX> prm)
 {
-  using L = ND4Layout<P_, Q_, KIND, ASM>;
+  using L = ND4Layout<P_, Q_, KIND, ASM, CPLX>;
+  static_assert(!CPLX || (!SPLIT && !ASM && L::NEW >= 2), "fused complex apply: single partition, on-the-fly D, two slots per warp");
   constexpr int p = L::p, q = L::q, n = L::n, Q = L::Q, D3 = L::D3, GE = L::GE, PS = L::PS, NEW = L::NEW;
+  constexpr int NPART = L::NPART, NEB = L::NEB, CE = L::CE;  // slot e = (element e / NPART, part e % NPART)
   constexpr int RSA = L::RSA, RSB = L::RSB, RSY = L::RSY, NXA = L::NXA, NNA = L::NNA;
   constexpr bool MASS = L::MASS, CURL = L::CURL;
   constexpr int QQ = q * q;
@@ -147,7 +171,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
   uint64_t *bar_g = (uint64_t *)(wbase + L::OFF_B);
   uint64_t *bar_i = bar_g + 1;  // [3]
 
-  const int nb = (prm.ne + NEW - 1) / NEW;  // element batches
+  const int nb = (prm.ne + NEB - 1) / NEB;  // element batches
   const int GW = gridDim.x * NW;            // warps in the grid
   int b = blockIdx.x * NW + wid;
   if (b >= nb) return;                      // (whole warp)
@@ -163,25 +187,28 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
 
   auto issue_idx = [&](int bb, int slot)
   {
-    const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
+    const int e0 = bb * NEB, nel = min(NEB, prm.ne - e0);
     const uint32_t bytes = (uint32_t)(nel * PS * sizeof(int32_t));
     mbar_expect_tx(bar_i + slot, bytes);
-    tma_bulk_g2s(sI + slot * NEW * PS, prm.lidx + (size_t)e0 * PS, bytes, bar_i + slot);
+    tma_bulk_g2s(sI + slot * NEB * PS, prm.lidx + (size_t)e0 * PS, bytes, bar_i + slot);
   };
   auto issue_geom = [&](int bb)
   {
-    const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
+    const int e0 = bb * NEB, nel = min(NEB, prm.ne - e0);
     const uint32_t bytes = (uint32_t)(nel * GE * sizeof(double));
-    const uint32_t cbytes = ASM ? 0u : (uint32_t)(nel * 18 * sizeof(double));
+    const uint32_t cbytes = ASM ? 0u : (uint32_t)(nel * CE * sizeof(double));
     mbar_expect_tx(bar_g, bytes + cbytes);
     tma_bulk_g2s(sG, (ASM ? prm.aq : prm.qd) + (size_t)e0 * GE, bytes, bar_g);
-    if (!ASM) tma_bulk_g2s(sC, prm.ecoef + (size_t)e0 * 18, cbytes, bar_g);
+    if constexpr (CPLX)
+      tma_bulk_g2s(sC, prm.zcoef + (size_t)e0 * CE, cbytes, bar_g);
+    else if (!ASM)
+      tma_bulk_g2s(sC, prm.ecoef + (size_t)e0 * 18, cbytes, bar_g);
   };
   // x values of batch bb -> sU (raw; the sign is applied when they are read)
   auto gather_x = [&](int bb, int slot)
   {
-    const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
-    const int32_t *gI = sI + slot * NEW * PS;
+    const int e0 = bb * NEB, nel = NPART * min(NEB, prm.ne - e0);
+    const int32_t *gI = sI + slot * NEB * PS;
     constexpr int ITER = (NEW * PS + 31) / 32;
 #pragma unroll
     for (int r = 0; r < ITER; r++)
@@ -189,13 +216,26 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
       const int l = lane + 32 * r;
       if (l < nel * PS)
       {
-        const int32_t gi = gI[l];
-        if (gi == B2P_SKIP_IDX)
-          sU[l] = 0.0;  // masked / padding: reads as zero
-        else if (SPLIT)
-          cp_async8(sU + l, split_src_fast(prm.x, prm.sp, abs_idx(gi)));
+        if constexpr (CPLX)
+        {
+          // slot (element, part): both parts read through the element's one index row
+          const int e = l / PS, t = l % PS;
+          const int32_t gi = gI[(e / NPART) * PS + t];
+          if (gi == B2P_SKIP_IDX)
+            sU[l] = 0.0;
+          else
+            cp_async8(sU + l, ((e % NPART) ? prm.xi : prm.x) + (uint32_t)abs_idx(gi));
+        }
         else
-          cp_async8(sU + l, prm.x + (uint32_t)abs_idx(gi));
+        {
+          const int32_t gi = gI[l];
+          if (gi == B2P_SKIP_IDX)
+            sU[l] = 0.0;  // masked / padding: reads as zero
+          else if (SPLIT)
+            cp_async8(sU + l, split_src_fast(prm.x, prm.sp, abs_idx(gi)));
+          else
+            cp_async8(sU + l, prm.x + (uint32_t)abs_idx(gi));
+        }
       }
     }
     cp_async_commit();
@@ -205,7 +245,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
   bool ghosts_ready = !(SPLIT && prm.wait_n > 0);
   auto wait_ghosts = [&](int bb)
   {
-    if (ghosts_ready || (bb + 1) * NEW <= prm.wait_from_elem) return;
+    if (ghosts_ready || (bb + 1) * NEB <= prm.wait_from_elem) return;
     if (lane < prm.wait_n)
     {
       const unsigned long long want = prm.wait_expect[lane];
@@ -239,8 +279,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
   {
     const int nslot = (slot == 2) ? 0 : slot + 1;
     const int bn = b + GW;
-    const int e0 = b * NEW, nel = min(NEW, prm.ne - e0);
-    const int32_t *cI = sI + slot * NEW * PS;
+    const int e0 = b * NEB, nel = NPART * min(NEB, prm.ne - e0);  // nel: valid slots of this batch
+    const int32_t *cI = sI + slot * NEB * PS;
     const double *cU = sU;
     (void)e0;
 
@@ -266,11 +306,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
 #pragma unroll
         for (int k = 0; k < n; k++)
         {
-          ux[k] = staged(cI, cU, ex * PS + tx + p * n * k, ex < nel);
-          uy[k] = staged(cI, cU, ex * PS + D3 + tx + n * p * k, ex < nel);
+          ux[k] = staged2(cI, (ex / NPART) * PS + tx + p * n * k, cU, ex * PS + tx + p * n * k, ex < nel);
+          uy[k] = staged2(cI, (ex / NPART) * PS + D3 + tx + n * p * k, cU, ex * PS + D3 + tx + n * p * k, ex < nel);
         }
 #pragma unroll
-        for (int k = 0; k < p; k++) uz[k] = staged(cI, cU, ez * PS + 2 * D3 + tz + n * n * k, ez < nel);
+        for (int k = 0; k < p; k++)
+          uz[k] = staged2(cI, (ez / NPART) * PS + 2 * D3 + tz + n * n * k, cU, ez * PS + 2 * D3 + tz + n * n * k, ez < nel);
         if (vx)
         {
           // x-directed dof tx = i + p*j ; y-directed dof tx = i + n*j
@@ -460,13 +501,51 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
           cc[qx][2] = dxuy - dyux;
         }
       }
-      const double *g = sG + e * GE + s;
-      const double *C = sC + e * 18;
+      const double *g = sG + (e / NPART) * GE + s;
+      const double *C = sC + (e / NPART) * CE;
 #pragma unroll
       for (int qx = 0; qx < q; qx++)
       {
         double v[3] = {0, 0, 0}, cw[3] = {0, 0, 0};
-        if (e < nel)
+        if constexpr (CPLX)
+        {
+          // z = (C_r + i C_i)(t_r + i t_i) with t = J^-T u (mass) or (J/detJ) curl u (curl): this slot owns one part
+          // of t; the partner slot (other part, same element, same point) sends its C_i t and gets ours.
+          const double *gq = g + QQ * qx;
+          const bool ok = e < nel;
+          double A[9], Jd[9], t[3], am[3] = {0, 0, 0}, bm[3] = {0, 0, 0}, ac[3] = {0, 0, 0}, bc[3] = {0, 0, 0};
+          const double wdetJ = ok ? alpha * gq[0] : 0.0;
+#pragma unroll
+          for (int i = 0; i < 9; i++) A[i] = ok ? gq[(1 + i) * Q] : 0.0;
+          if (MASS)
+          {
+            Ax33(A, uu[qx], t);
+            Ax33(C, t, am);
+            Ax33(C + 9, t, bm);
+          }
+          if (CURL)
+          {
+            cofactor33(A, Jd);
+            Ax33(Jd, cc[qx], t);
+            Ax33(C + 18, t, ac);
+            Ax33(C + 27, t, bc);
+          }
+          if (prm.has_imag)
+          {
+            constexpr unsigned xmask = (NEW * QQ >= 32) ? 0xffffffffu : ((1u << (NEW * QQ)) - 1u);
+            const int partner = (e ^ 1) * QQ + s;
+            const double sg = (e & 1) ? 1.0 : -1.0;  // real part: a_r - b_i ; imaginary part: a_i + b_r
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+            {
+              if (MASS) am[r] += sg * __shfl_sync(xmask, bm[r], partner);
+              if (CURL) ac[r] += sg * __shfl_sync(xmask, bc[r], partner);
+            }
+          }
+          if (MASS) Atx33(A, am, wdetJ, v);
+          if (CURL) Atx33(Jd, ac, wdetJ, cw);
+        }
+        else if (e < nel)
         {
           const double *gq = g + QQ * qx;
           if (ASM)
@@ -676,11 +755,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
 #pragma unroll
           for (int k = 0; k < n; k++)
           {
-            gx[k] = cI[ex * PS + tx + p * n * k];
-            gy[k] = cI[ex * PS + D3 + tx + n * p * k];
+            gx[k] = cI[(ex / NPART) * PS + tx + p * n * k];
+            gy[k] = cI[(ex / NPART) * PS + D3 + tx + n * p * k];
           }
 #pragma unroll
-          for (int k = 0; k < p; k++) gz[k] = cI[ez * PS + 2 * D3 + tz + n * n * k];
+          for (int k = 0; k < p; k++) gz[k] = cI[(ez / NPART) * PS + 2 * D3 + tz + n * n * k];
+        }
+        // output vector of this lane's slots (the imaginary part for odd slots of a fused complex apply)
+        double *yx = prm.y, *yz = prm.y;
+        if constexpr (CPLX)
+        {
+          yx = (ex % NPART) ? prm.yi : prm.y;
+          yz = (ez % NPART) ? prm.yi : prm.y;
         }
         if (vx)
         {
@@ -696,8 +782,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
               if (CURL) o += prm.Gc[qz * n + k] * xb[qz];
               if (CURL) o2 += prm.Gc[qz * n + k] * yb[qz];
             }
-            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gx[k], o); else scatter_fast(prm.y, gx[k], o);
-            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gy[k], o2); else scatter_fast(prm.y, gy[k], o2);
+            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gx[k], o); else scatter_fast(yx, gx[k], o);
+            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gy[k], o2); else scatter_fast(yx, gy[k], o2);
           }
         }
         if (vz)
@@ -708,7 +794,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
             double o = 0.0;
 #pragma unroll
             for (int qz = 0; qz < q; qz++) o += prm.Bo[qz * p + k] * za[qz];
-            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gz[k], o); else scatter_fast(prm.y, gz[k], o);
+            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gz[k], o); else scatter_fast(yz, gz[k], o);
           }
         }
       }
@@ -796,7 +882,102 @@ int launch4_kind(b2p_op *op, const int32_t *lidx, double alpha, const double *x,
   return B2P_ERR_UNSUPPORTED;
 }
 
+// Fused complex apply: one launch, geometry streamed once for both parts (see ND4ParamsZ).
+template <int P_, int Q_, int KIND>
+int launch4z(b2p_op *op, const int32_t *lidx, const double *zcoef, int has_imag, double alpha, const double *xr, const double *xi,
+             double *yr, double *yi, cudaStream_t s)
+{
+  using L = ND4Layout<P_, Q_, KIND, false, true>;
+  if constexpr (L::NEW < 2)
+  {
+    set_error(op->ctx, "fused complex apply: q1d=%d leaves one element slot per warp", Q_);
+    return B2P_ERR_UNSUPPORTED;
+  }
+  else
+  {
+    constexpr int SMEM_SM = 222 * 1024;
+    constexpr int WPS0 = (SMEM_SM / L::WS) < 1 ? 1 : SMEM_SM / L::WS;
+    constexpr int WPS = WPS0 > 8 ? 8 : WPS0;  // 8 warps per SM at up to 255 registers, as the real kernel (no spills)
+    constexpr int MINB = (WPS >= 8) ? 2 : 1;
+    constexpr int NW = (WPS / MINB) < 1 ? 1 : WPS / MINB;
+    const size_t shmem = (size_t)NW * L::WS;
+    auto kern = nd_hex_apply4_kernel<P_, Q_, KIND, false, false, NW, MINB, true>;
+    static bool configured = false;
+    if (!configured)
+    {
+      B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      configured = true;
+    }
+    if (op->ne <= 0) return B2P_SUCCESS;
+    ND4ParamsZ<P_, Q_> prm;
+    prm.lidx = lidx;
+    prm.qd = op->geom->qd;
+    prm.aq = nullptr;
+    prm.mat = op->mat;
+    prm.emat = op->emat;
+    prm.ecoef = nullptr;
+    prm.x = xr;
+    prm.y = yr;
+    prm.alpha = alpha;
+    prm.ne = op->ne;
+    prm.sp.n_owned = op->lsize;
+    prm.sp.xg = nullptr;
+    prm.sp.yg = nullptr;
+    prm.wait_flags = nullptr;
+    prm.wait_expect = nullptr;
+    prm.wait_n = 0;
+    prm.wait_from_elem = 0;
+    prm.iso = 0;
+    prm.xi = xi;
+    prm.yi = yi;
+    prm.zcoef = zcoef;
+    prm.has_imag = has_imag;
+    const int n = P_ + 1;
+    for (int i = 0; i < Q_ * P_; i++) prm.Bo[i] = op->h_tab[i];
+    for (int i = 0; i < Q_ * n; i++) prm.Bc[i] = op->h_tab[Q_ * P_ + i];
+    for (int i = 0; i < Q_ * n; i++) prm.Gc[i] = op->h_tab[Q_ * P_ + Q_ * n + i];
+    const int nb = (op->ne + L::NEB - 1) / L::NEB;
+    int grid = op->ctx->sm_count * MINB;
+    if (grid > (nb + NW - 1) / NW) grid = (nb + NW - 1) / NW;
+    B2P_LAUNCH(kern, grid, NW * 32, shmem, s, prm);
+    B2P_CUDA(op->ctx, cudaGetLastError());
+    return B2P_SUCCESS;
+  }
+}
+
+template <int P_, int Q_>
+int launch4z_kind(b2p_op *op, int kind, const int32_t *lidx, const double *zcoef, int has_imag, double alpha, const double *xr,
+                  const double *xi, double *yr, double *yi, cudaStream_t s)
+{
+  switch (kind)
+  {
+    case B2P_CURLCURL: return launch4z<P_, Q_, B2P_CURLCURL>(op, lidx, zcoef, has_imag, alpha, xr, xi, yr, yi, s);
+    case B2P_ND_MASS: return launch4z<P_, Q_, B2P_ND_MASS>(op, lidx, zcoef, has_imag, alpha, xr, xi, yr, yi, s);
+    case B2P_CURLCURL_MASS: return launch4z<P_, Q_, B2P_CURLCURL_MASS>(op, lidx, zcoef, has_imag, alpha, xr, xi, yr, yi, s);
+  }
+  set_error(op->ctx, "fused complex apply: unsupported kind %d", kind);
+  return B2P_ERR_UNSUPPORTED;
+}
+
 }  // namespace
+
+bool nd_hex_apply4z_eligible(const b2p_op *op)
+{
+  // two (element, part) slots per warp need q1d^2 <= 16; default quadrature (q1d = p + 1) only
+  return op && !op->dense && !op->assembled && op->kind != B2P_H1_DIFFUSION && op->q1d == op->p + 1 && op->q1d >= 2 && op->q1d <= 4;
+}
+
+// `op` supplies geometry, restriction and tables; `kind` says which parts of the complex coefficient block are used.
+int launch_nd_hex_apply4z(b2p_op *op, int kind, const int32_t *lidx, const double *zcoef, int has_imag, double alpha,
+                          const double *xr, const double *xi, double *yr, double *yi, cudaStream_t s)
+{
+#define B2P_CASE(PP, QQ) \
+  if (op->p == PP && op->q1d == QQ) return launch4z_kind<PP, QQ>(op, kind, lidx, zcoef, has_imag, alpha, xr, xi, yr, yi, s);
+  B2P_CASE(1, 2) B2P_CASE(2, 3) B2P_CASE(3, 4)
+#undef B2P_CASE
+  set_error(op->ctx, "fused complex apply: no kernel for p=%d q1d=%d", op->p, op->q1d);
+  return B2P_ERR_UNSUPPORTED;
+}
 
 int launch_nd_hex_apply4(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {

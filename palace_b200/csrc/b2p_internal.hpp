@@ -162,6 +162,10 @@ int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const dou
 int launch_nd_hex_apply4(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
 int launch_nd_hex_apply5(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
 bool nd_hex_apply5_eligible(b2p_op *op);
+// fused complex apply (b2p_hex_nd4.cu): both parts of a split complex vector in one pass over the geometry
+bool nd_hex_apply4z_eligible(const b2p_op *op);
+int launch_nd_hex_apply4z(b2p_op *op, int kind, const int32_t *lidx, const double *zcoef, int has_imag, double alpha, const double *xr,
+                          const double *xi, double *yr, double *yi, cudaStream_t s);
 int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, int flags,
                 cudaStream_t s);
 int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s);

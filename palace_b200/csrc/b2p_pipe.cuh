@@ -110,6 +110,16 @@ __device__ __forceinline__ double staged(const int32_t *cI, const double *cU, in
   const double r = __hiloint2double(hi, __double2loint(v));
   return valid ? r : 0.0;
 }
+// Same with the index row and the staged values at different positions (several vector parts of one element
+// share the element's index row).
+__device__ __forceinline__ double staged2(const int32_t *cI, int ipos, const double *cU, int upos, bool valid)
+{
+  const int32_t gi = cI[ipos];
+  const double v = cU[upos];
+  int hi = __double2hiint(v) ^ (gi & (int)0x80000000);
+  const double r = __hiloint2double(hi, __double2loint(v));
+  return valid ? r : 0.0;
+}
 // |index| of a signed restriction entry (-1 - gi == ~gi for negative entries)
 __device__ __forceinline__ int32_t abs_idx(int32_t gi) { return gi ^ (gi >> 31); }
 // Predicated RED.F64 of value (with the entry's sign) at y[|gi|]; masked entries are skipped.

@@ -34,6 +34,20 @@ __device__ __forceinline__ void AtAx(const double A[9], const double x[3], doubl
   y[2] = s * (A[6] * t0 + A[7] * t1 + A[8] * t2);
 }
 
+// t = A x ; y = s * A^T z   (the two halves of AtCAx, for coefficients applied in between)
+__device__ __forceinline__ void Ax33(const double A[9], const double x[3], double t[3])
+{
+  t[0] = A[0] * x[0] + A[3] * x[1] + A[6] * x[2];
+  t[1] = A[1] * x[0] + A[4] * x[1] + A[7] * x[2];
+  t[2] = A[2] * x[0] + A[5] * x[1] + A[8] * x[2];
+}
+__device__ __forceinline__ void Atx33(const double A[9], const double z[3], double s, double y[3])
+{
+  y[0] = s * (A[0] * z[0] + A[1] * z[1] + A[2] * z[2]);
+  y[1] = s * (A[3] * z[0] + A[4] * z[1] + A[5] * z[2]);
+  y[2] = s * (A[6] * z[0] + A[7] * z[1] + A[8] * z[2]);
+}
+
 // Cofactor matrix (adj^T) of a column-major 3x3: for A = J^-T this is J/detJ (utils_33_qf.h:20-37).
 __device__ __forceinline__ void cofactor33(const double J[9], double A[9])
 {

@@ -87,6 +87,17 @@ struct Warp
 {
   Bar bar;
   alignas(16) unsigned char mail[32][16];
+  std::vector<std::pair<unsigned, Bar>> sub;  // barriers of partial member masks (__shfl_sync with a subset of the lanes)
+  Bar &bar_for(unsigned mask)
+  {
+    if (mask == 0xffffffffu) return bar;
+    for (auto &m : sub)
+      if (m.first == mask) return m.second;
+    Bar b;
+    b.expected = __builtin_popcount(mask);
+    sub.emplace_back(mask, b);
+    return sub.back().second;
+  }
 };
 struct Copy
 {
@@ -279,16 +290,22 @@ void launch(dim3 grid, dim3 block, size_t shmem, const std::function<void()> &bo
 #endif
 
 template <typename T>
-inline T exchange(T v, int src_lane)
+inline T exchange(T v, int src_lane, unsigned mask = 0xffffffffu)
 {
   static_assert(sizeof(T) <= 16, "");
   Fiber *f = st().cur;
   Warp *w = f->warp;
+  if (!((mask >> f->lane) & 1u) || !((mask >> (src_lane & 31)) & 1u))
+  {
+    std::fprintf(stderr, "cuda_emu: shuffle with member mask %08x by lane %d from lane %d: both must be named in the mask\n", mask, f->lane,
+                 src_lane & 31);
+    std::abort();
+  }
   std::memcpy(w->mail[f->lane], &v, sizeof(T));
-  bar_wait(w->bar);
+  bar_wait(w->bar_for(mask));
   T r;
   std::memcpy(&r, w->mail[src_lane & 31], sizeof(T));
-  bar_wait(w->bar);
+  bar_wait(w->bar_for(mask));
   return r;
 }
 // mma.sync.m8n8k4 f64: A[8x4] row-major fragment a = A[lane/4][lane%4], B[4x8] b = B[lane%4][lane/4],
@@ -380,9 +397,9 @@ inline void cp_async_wait(int keep)
 inline void __syncthreads() { ::cuda_emu::bar_wait(::cuda_emu::st().blk->bar); }
 inline void __syncwarp(unsigned = 0xffffffffu) { ::cuda_emu::bar_wait(::cuda_emu::st().cur->warp->bar); }
 template <typename T>
-inline T __shfl_xor_sync(unsigned, T v, int m)
+inline T __shfl_xor_sync(unsigned mask, T v, int m)
 {
-  return ::cuda_emu::exchange(v, ::cuda_emu::st().cur->lane ^ m);
+  return ::cuda_emu::exchange(v, ::cuda_emu::st().cur->lane ^ m, mask);
 }
 template <typename T>
 inline T __shfl_xor(T v, int m)
@@ -390,9 +407,9 @@ inline T __shfl_xor(T v, int m)
   return ::cuda_emu::exchange(v, ::cuda_emu::st().cur->lane ^ m);
 }
 template <typename T>
-inline T __shfl_sync(unsigned, T v, int src)
+inline T __shfl_sync(unsigned mask, T v, int src)
 {
-  return ::cuda_emu::exchange(v, src);
+  return ::cuda_emu::exchange(v, src, mask);
 }
 template <typename T>
 inline T __ldg(const T *p)
