@@ -135,8 +135,9 @@ void cmulti_dot(b2p_ctx *c, int m, const CCPtr *V, CCPtr w, int64_t n, cplx *out
       L.re[j] = j < mm ? V[j0 + j].re : nullptr;
       L.im[j] = j < mm ? V[j0 + j].im : nullptr;
     }
-    B2P_LAUNCH(cmulti_dot_kernel, RED_BLOCKS, NT, 0, c->stream, L, w.re, w.im, n, mm, part);
-    B2P_LAUNCH(creduce_kernel, 2 * mm, 32, 0, c->stream, part, RED_BLOCKS, res);
+    const int rg = std::min(RED_BLOCKS, 2 * std::max(1, c->sm_count));  // two blocks per SM (296 on a B200)
+    B2P_LAUNCH(cmulti_dot_kernel, rg, NT, 0, c->stream, L, w.re, w.im, n, mm, part);
+    B2P_LAUNCH(creduce_kernel, 2 * mm, 32, 0, c->stream, part, rg, res);
     if (c->nranks > 1 && c->comm) b2p_allreduce_sum(c, res, 2 * mm);
     cudaMemcpyAsync(c->h_red, res, sizeof(double) * 2 * mm, cudaMemcpyDeviceToHost, c->stream);
     cudaStreamSynchronize(c->stream);

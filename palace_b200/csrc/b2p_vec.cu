@@ -5,6 +5,8 @@
 // Pure HBM streaming: 128-bit loads/stores, grid = a multiple of the SM count, grid-stride loops.
 #include <nccl.h>
 
+#include <algorithm>
+
 #include "b2p_linalg.hpp"
 
 namespace b2p
@@ -155,12 +157,14 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 }
 
 // Partial sums of m dot products live in ctx->d_red: [MAXM][RED_BLOCKS] partials then [MAXM] results.
+// Blocks of a reduction pass: two per SM (296 on a B200), fixed per device so the summation order is reproducible.
+int red_grid(b2p_ctx *c) { return std::min(RED_BLOCKS, 2 * std::max(1, c->sm_count)); }
 double *red_partials(b2p_ctx *c) { return c->d_red; }
 double *red_results(b2p_ctx *c) { return c->d_red + (size_t)MAXM * RED_BLOCKS; }
 
 void reduce_finish(b2p_ctx *c, int m, double *host_out)
 {
-  B2P_LAUNCH(final_reduce_kernel, m, 32, 0, c->stream, red_partials(c), m, RED_BLOCKS, red_results(c));
+  B2P_LAUNCH(final_reduce_kernel, m, 32, 0, c->stream, red_partials(c), m, red_grid(c), red_results(c));
   if (c->nranks > 1 && c->comm)
     ncclAllReduce(red_results(c), red_results(c), m, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
   cudaMemcpyAsync(c->h_red, red_results(c), sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
@@ -259,13 +263,13 @@ void multi_dot(b2p_ctx *c, int m, const double *const *V, const double *w, int64
     VecList L;
     for (int j = 0; j < MAXM; j++) L.v[j] = j < mm ? V[j0 + j] : nullptr;
     if (mm == 1)
-      B2P_LAUNCH(multi_dot_kernel<1>, RED_BLOCKS, NT, 0, c->stream, L, w, n, mm, red_partials(c));
+      B2P_LAUNCH(multi_dot_kernel<1>, red_grid(c), NT, 0, c->stream, L, w, n, mm, red_partials(c));
     else if (mm == 2)
-      B2P_LAUNCH(multi_dot_kernel<2>, RED_BLOCKS, NT, 0, c->stream, L, w, n, mm, red_partials(c));
+      B2P_LAUNCH(multi_dot_kernel<2>, red_grid(c), NT, 0, c->stream, L, w, n, mm, red_partials(c));
     else if (mm <= 4)
-      B2P_LAUNCH(multi_dot_kernel<4>, RED_BLOCKS, NT, 0, c->stream, L, w, n, mm, red_partials(c));
+      B2P_LAUNCH(multi_dot_kernel<4>, red_grid(c), NT, 0, c->stream, L, w, n, mm, red_partials(c));
     else
-      B2P_LAUNCH(multi_dot_kernel<8>, RED_BLOCKS, NT, 0, c->stream, L, w, n, mm, red_partials(c));
+      B2P_LAUNCH(multi_dot_kernel<8>, red_grid(c), NT, 0, c->stream, L, w, n, mm, red_partials(c));
     reduce_finish(c, mm, out + j0);
   }
 }
@@ -280,7 +284,7 @@ double dot(b2p_ctx *c, const double *x, const double *y, int64_t n)
 
 double sum(b2p_ctx *c, const double *x, int64_t n)
 {
-  B2P_LAUNCH(sum_kernel, RED_BLOCKS, NT, 0, c->stream, x, n, red_partials(c));
+  B2P_LAUNCH(sum_kernel, red_grid(c), NT, 0, c->stream, x, n, red_partials(c));
   double out = 0.0;
   reduce_finish(c, 1, &out);
   return out;

@@ -40,3 +40,9 @@ def test_element_kernels_under_emulation(order):
     different lane execution orders (a missing warp barrier shows up as stale data in at least one of them)."""
     n = _run(["tests/test_apply_gpu.py", "tests/test_dense_gpu.py", "tests/test_tet_gpu.py", "tests/test_zfused_gpu.py"], order)
     assert n >= 120
+
+
+def test_solver_layer_under_emulation():
+    """Vector kernels, smoothers, interpolators, V-cycle and Krylov solvers: the whole device-resident loop of
+    tests/test_solvers_gpu.py on the emulated machine (reductions use two blocks per emulated SM)."""
+    assert _run(["tests/test_solvers_gpu.py"], "fwd") >= 15
