@@ -719,6 +719,7 @@ void b2p_ctx_destroy(b2p_ctx *ctx)
   if (!ctx) return;
   cudaFree(ctx->d_red);
   cudaFreeHost(ctx->h_red);
+  if (ctx->graph_stream) cudaStreamDestroy(ctx->graph_stream);
   delete ctx;
 }
 

@@ -64,6 +64,7 @@ struct b2p_ctx
   int rank = 0, nranks = 1;
   ncclComm *comm = nullptr;
   cudaStream_t stream = 0;  // stream of the linear algebra / solver layer (b2p_ctx_set_stream)
+  cudaStream_t graph_stream = nullptr;  // internal BLOCKING stream for graph capture when `stream` is the legacy stream
   std::string last_error;
   // scratch for reductions (dot products): device partials + pinned host result
   double *d_red = nullptr;

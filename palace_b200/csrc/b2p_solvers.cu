@@ -106,7 +106,24 @@ void ParOperator::Mult(const double *x, double *y) const
     const auto key = std::make_pair(x, y);
     auto it = graphs_.find(key);
     static const bool no_graph = []() { const char *e = getenv("B2P_NO_GRAPH"); return e && e[0] == '1'; }();
-    if (no_graph)
+    // Stream capture is not allowed on the legacy default stream (what MFEM and b2p_ctx_set_stream(ctx, nullptr) use).
+    // B2P_GRAPH_STREAM=1: capture and replay on an internal BLOCKING stream instead -- it synchronises implicitly with
+    // the legacy stream in both directions, so the caller's ordering is preserved. (Opt-in until measured on 2+ GPUs;
+    // without it a legacy-stream context runs the eager sequence.)
+    static const bool graph_stream = []() { const char *e = getenv("B2P_GRAPH_STREAM"); return e && e[0] == '1'; }();
+    if (s == nullptr && graph_stream && !no_graph)
+    {
+      if (!ctx->graph_stream && cudaStreamCreate(&ctx->graph_stream) != cudaSuccess) ctx->graph_stream = nullptr;
+      if (ctx->graph_stream) s = ctx->graph_stream;
+    }
+    struct StreamSwap  // the body's vector kernels launch on ctx->stream: point it at the capture stream meanwhile
+    {
+      b2p_ctx *c;
+      cudaStream_t keep;
+      StreamSwap(b2p_ctx *c_, cudaStream_t s_) : c(c_), keep(c_->stream) { c->stream = s_; }
+      ~StreamSwap() { c->stream = keep; }
+    } swap(ctx, s);
+    if (no_graph || s == nullptr)
     {
       MultHaloBody(x, y, s);
     }

@@ -136,6 +136,11 @@ inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int)
   *s = nullptr;
   return cudaSuccess;
 }
+inline cudaError_t cudaStreamCreate(cudaStream_t *s)
+{
+  *s = nullptr;
+  return cudaSuccess;
+}
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned)
 {

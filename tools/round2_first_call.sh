@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU call of a round (run under gpurun from the repo root): parity, headline bench, the experiments prepared
+# on the CPU side, and the ncu evidence -- everything lands in gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+cd /root/repo; mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
+python bench.py --steps 200 --warmup 10 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_n1_reference.json 2>> gpurun_out/bench_n1.err
+# prepared experiments: fused complex matvec, tetrahedra through the dense DMMA operator
+timeout 300 python tools/zfused_bench.py > gpurun_out/zfused_p3.json 2> gpurun_out/zfused.err
+timeout 300 python tools/zfused_bench.py --order 1 --n 60 >> gpurun_out/zfused_p3.json 2>> gpurun_out/zfused.err
+timeout 300 python tools/tet_bench.py --order 3 --n 14 > gpurun_out/tet_p3.json 2> gpurun_out/tet.err
+timeout 300 python tools/tet_bench.py --order 6 --n 6 >> gpurun_out/tet_p3.json 2>> gpurun_out/tet.err
+# ncu: launch list of the bench command, then one full capture of the apply kernel and of the fused complex kernel
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:nd_hex_apply4 -s 5 -c 1 -o gpurun_out/nd4_full -f \
+    python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+B2P_COMPLEX_FUSED=1 ncu --set full --clock-control none --import-source on -k regex:nd_hex_apply4 -s 12 -c 1 -o gpurun_out/nd4z_full -f \
+    python tools/zfused_bench.py --steps 3 > /dev/null 2>&1
+ls -la gpurun_out
