@@ -45,6 +45,14 @@ def main():
     import bench
 
     bench.ClockSampler = lambda *a, **k: type("C", (), {"stop": lambda self, a, b: {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["dry run"]}})()
+    if len(sys.argv) > 1 and sys.argv[1].endswith(".py"):
+        # dry run of another GPU tool:  python tests/emu/bench_dryrun.py tools/zfused_bench.py --n 3 ...
+        import runpy
+
+        script = sys.argv[1]
+        sys.argv = [script] + sys.argv[2:]
+        runpy.run_path(script, run_name="__main__")
+        return
     sys.argv = ["bench.py", "--n", "3", "--steps", "3", "--warmup", "1", "--cpu-sample-elems", "27"] + sys.argv[1:]
     bench.main()
 
