@@ -211,6 +211,30 @@ int b2p_halo_p2p_export(b2p_halo *h, void *blob, size_t *bytes);
 int b2p_halo_p2p_import(b2p_halo *h, const void *blobs, size_t stride, int nranks);
 void b2p_halo_destroy(b2p_halo *h);
 
+/* ---- full assembly (coarse levels) ------------------------------------------------------------------------------
+ * Device-resident CSR matrix of a sum of local operators on the L-vector: what BilinearForm::FullAssemble /
+ * CeedOperatorFullAssemble (fem/libceed/operator.cpp:262-523) produce for ParOperator::ParallelAssemble
+ * (linalg/rap.cpp:84-152) -> HYPRE AMS/BoomerAMG or a sparse direct solver on the coarsest multigrid level.
+ * b2p_csr_create: symbolic phase from the restriction of `op` (host, once per space; the reference's
+ *   CeedOperatorLinearAssembleSymbolic + COO->CSR sort). Any operator on the same space can be assembled into it.
+ * b2p_csr_assemble: numeric phase on the device, values = sum_t coefs[t] * A_t (the reference's "set" = false
+ *   accumulation). The element matrices come from the operator kernels themselves (applied to local unit vectors
+ *   through an identity restriction), so hex / tet / assembled-D operators are all covered; no host work, no sort.
+ * b2p_csr_device_arrays: rowptr[n+1] / col[nnz] (int32, sorted columns) / val[nnz] device pointers, owned by the handle
+ *   (wrap them in a hypre_CSRMatrix). b2p_csr_eliminate: essential rows/columns as HypreParMatrix::EliminateBC with
+ *   the ParOperator diagonal policy (1 = DIAG_ONE, 0 = DIAG_ZERO), for callers that skip the P^T A P step.
+ * b2p_csr_mult: y = A x (verification / standalone coarse solves). */
+typedef struct b2p_csr b2p_csr;
+int b2p_csr_create(b2p_ctx *ctx, b2p_op *op, b2p_csr **out);
+int b2p_csr_assemble(b2p_csr *A, int n_terms, b2p_op *const *ops, const double *coefs, b2p_stream s);
+int64_t b2p_csr_rows(const b2p_csr *A);
+int64_t b2p_csr_nnz(const b2p_csr *A);
+int b2p_csr_device_arrays(b2p_csr *A, const int32_t **rowptr, const int32_t **col, const double **val);
+int b2p_csr_get_host(b2p_csr *A, int32_t *rowptr, int32_t *col, double *val, b2p_stream s);
+int b2p_csr_eliminate(b2p_csr *A, const int32_t *ess_dofs, int64_t n_ess, int diag_policy, b2p_stream s);
+int b2p_csr_mult(b2p_csr *A, const double *x, double *y, b2p_stream s);
+void b2p_csr_destroy(b2p_csr *A);
+
 /* ---- device-resident linear algebra (replaces linalg/vector.cpp kernels + MPI_Allreduce) ---- */
 int b2p_ctx_set_stream(b2p_ctx *ctx, b2p_stream s); /* stream used by everything below */
 int b2p_vec_axpby(b2p_ctx *ctx, int64_t n, double a, const double *x, double b, double *y);                 /* y = a x + b y  (vector.cpp:276-377) */

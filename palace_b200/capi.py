@@ -343,6 +343,45 @@ class Halo:
         _chk(lib().b2p_halo_reverse(self.h, _vp(lvec)), self.ctx.h)
 
 
+class Csr:
+    """Fully assembled device CSR matrix of a sum of local operators (coarse levels; BilinearForm::FullAssemble)."""
+
+    def __init__(self, ctx, op: Op):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _chk(lib().b2p_csr_create(ctx.h, op.h, C.byref(h)), ctx.h)
+        self.h = h
+        lib().b2p_csr_rows.restype = C.c_int64
+        lib().b2p_csr_nnz.restype = C.c_int64
+        self.n, self.nnz = int(lib().b2p_csr_rows(h)), int(lib().b2p_csr_nnz(h))
+
+    def assemble(self, ops, coefs=None, stream=None):
+        n = len(ops)
+        arr = (C.c_void_p * n)(*[o.h for o in ops])
+        cf = _np(coefs if coefs is not None else np.ones(n), np.float64)
+        _chk(lib().b2p_csr_assemble(self.h, n, arr, _ptr(cf), _stream(stream)), self.ctx.h)
+
+    def eliminate(self, ess_dofs, diag_policy=1, stream=None):
+        ess = _np(ess_dofs, np.int32)
+        _chk(lib().b2p_csr_eliminate(self.h, _ptr(ess), C.c_int64(ess.size), int(diag_policy), _stream(stream)), self.ctx.h)
+
+    def mult(self, x, y, stream=None):
+        _chk(lib().b2p_csr_mult(self.h, _vp(x), _vp(y), _stream(stream)), self.ctx.h)
+
+    def to_scipy(self, stream=None):
+        import scipy.sparse as sp
+
+        rowptr, col, val = np.empty(self.n + 1, np.int32), np.empty(self.nnz, np.int32), np.empty(self.nnz)
+        _chk(lib().b2p_csr_get_host(self.h, _ptr(rowptr), _ptr(col), _ptr(val), _stream(stream)), self.ctx.h)
+        return sp.csr_matrix((val, col, rowptr), shape=(self.n, self.n))
+
+    def close(self):
+        if self.h:
+            lib().b2p_csr_destroy.restype = None
+            lib().b2p_csr_destroy(self.h)
+            self.h = None
+
+
 def set_stream(ctx, stream=None):
     _chk(lib().b2p_ctx_set_stream(ctx.h, _stream(stream)), ctx.h)
 
