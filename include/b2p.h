@@ -193,6 +193,24 @@ typedef struct
 int b2p_interp_create(b2p_ctx *ctx, const b2p_interp_desc *desc, b2p_interp **out);
 /* y += alpha * (1/mult) .* I x   (transpose = 0, ceed::Operator::AddMult with dof multiplicity, operator.cpp:182-212)
  * y += alpha * I^T ((1/mult) .* x) (transpose = 1) */
+/* Element-dense interpolator for any element type (tetrahedra: p-prolongation / discrete gradient matrices from
+ * GetTransferMatrix / ProjectGrad, fem/libceed/basis.cpp:116-165): one [out_P][in_P] row-major matrix in native dof
+ * order for every element; restrictions with sign orientation (+1/-1) or with the int8 tridiagonal rows of
+ * restriction.cpp:301-329 -- domain side filled from InvTransformPrimal, range side from InvTransformDual. Same Mult /
+ * MultTranspose multiplicity scaling as b2p_interp_create (libceed/operator.cpp:182-235). */
+typedef struct
+{
+  int ne, in_P, out_P;
+  int64_t in_lsize, out_lsize;
+  const int32_t *in_idx;          /* [ne][in_P] */
+  const int8_t *in_orient;        /* [ne][in_P] or NULL */
+  const int8_t *in_curl_orient;   /* [ne][in_P][3] or NULL */
+  const int32_t *out_idx;         /* [ne][out_P] */
+  const int8_t *out_orient;       /* [ne][out_P] or NULL */
+  const int8_t *out_curl_orient;  /* [ne][out_P][3] (dual rows) or NULL */
+  const double *mat;              /* [out_P][in_P] */
+} b2p_dense_interp_desc;
+int b2p_interp_create_dense(b2p_ctx *ctx, const b2p_dense_interp_desc *desc, b2p_interp **out);
 int b2p_interp_apply_add(b2p_interp *it, int transpose, double alpha, const double *x, double *y, b2p_stream s);
 void b2p_interp_destroy(b2p_interp *it);
 

@@ -273,6 +273,14 @@ class InterpDesc(C.Structure):
     ]
 
 
+class DenseInterpDesc(C.Structure):
+    _fields_ = [
+        ("ne", C.c_int), ("in_P", C.c_int), ("out_P", C.c_int), ("in_lsize", C.c_int64), ("out_lsize", C.c_int64),
+        ("in_idx", C.c_void_p), ("in_orient", C.c_void_p), ("in_curl_orient", C.c_void_p), ("out_idx", C.c_void_p),
+        ("out_orient", C.c_void_p), ("out_curl_orient", C.c_void_p), ("mat", C.c_void_p),
+    ]
+
+
 class Interp:
     """Element-local tensor interpolator between two hex spaces (p-prolongation, discrete gradient)."""
 
@@ -309,6 +317,31 @@ class Interp:
         _chk(lib().b2p_interp_create(ctx.h, C.byref(d), C.byref(h)), ctx.h)
         self.ctx, self.h = ctx, h
         self.in_lsize, self.out_lsize = int(in_space["lsize"]), int(out_space["lsize"])
+
+    @classmethod
+    def dense(cls, ctx, mat, in_idx, in_lsize, out_idx, out_lsize, in_orient=None, in_curl_orient=None, out_orient=None,
+              out_curl_orient=None):
+        """Element-dense interpolator (any element type): one [out_P][in_P] matrix, native dof order."""
+        d = DenseInterpDesc()
+        keep = []
+        mat = _np(mat, np.float64)
+        in_idx, out_idx = _np(in_idx, np.int32), _np(out_idx, np.int32)
+        assert mat.shape == (out_idx.shape[1], in_idx.shape[1]) and in_idx.shape[0] == out_idx.shape[0]
+        d.ne, d.in_P, d.out_P = in_idx.shape[0], in_idx.shape[1], out_idx.shape[1]
+        d.in_lsize, d.out_lsize = int(in_lsize), int(out_lsize)
+        d.in_idx, d.out_idx, d.mat = _ptr(in_idx), _ptr(out_idx), _ptr(mat)
+        for name, arr in (("in_orient", in_orient), ("in_curl_orient", in_curl_orient), ("out_orient", out_orient),
+                          ("out_curl_orient", out_curl_orient)):
+            if arr is not None:
+                a = _np(arr, np.int8)
+                keep.append(a)
+                setattr(d, name, _ptr(a))
+        h = C.c_void_p()
+        _chk(lib().b2p_interp_create_dense(ctx.h, C.byref(d), C.byref(h)), ctx.h)
+        self = cls.__new__(cls)
+        self.ctx, self.h = ctx, h
+        self.in_lsize, self.out_lsize = int(in_lsize), int(out_lsize)
+        return self
 
     def apply_add(self, x, y, transpose=False, alpha=1.0, stream=None):
         _chk(lib().b2p_interp_apply_add(self.h, int(transpose), C.c_double(alpha), _vp(x), _vp(y), _stream(stream)), self.ctx.h)

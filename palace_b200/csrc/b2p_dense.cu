@@ -185,13 +185,16 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(DenseParams prm)
   }
 }
 
-// diag[g(i)] += sum_q T(:,q,i)^T D_q T(:,q,i)   (exact for sign orientation; for the tridiagonal
-// orientation this is libCEED's approximation the reference accepts, test-libceed.cpp:358-372)
+// diag[g(i)] += sum_q w(q)^T D w(q) with w = the i-th shape function as the global side sees it: for sign
+// orientation that is column i of the table (the sign squares away); for the tridiagonal orientation it is
+// sum_l T_e(l, i) * column l, which makes the diagonal of T^T A T exact (libCEED assembles it through the unsigned
+// restriction, an approximation the reference tolerates, test-libceed.cpp:358-372; the Chebyshev / Jacobi smoothers
+// converge visibly better with the exact one).
 __global__ void dense_diag_kernel(DenseParams prm)
 {
   const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= (size_t)prm.ne * prm.P) return;
-  const int e = (int)(w / prm.P), i = (int)(w % prm.P), Q = prm.Q;
+  const int e = (int)(w / prm.P), i = (int)(w % prm.P), Q = prm.Q, P = prm.P;
   const bool MASS = (prm.kind == B2P_ND_MASS || prm.kind == B2P_CURLCURL_MASS);
   const bool CURL = (prm.kind == B2P_CURLCURL || prm.kind == B2P_CURLCURL_MASS);
   const bool H1 = (prm.kind == B2P_H1_DIFFUSION);
@@ -202,6 +205,23 @@ __global__ void dense_diag_kernel(DenseParams prm)
     C0[t] = C[t];
     C1[t] = C[9 + t];
   }
+  // column combination: tc[l - i + 1] = T_e(l, i) for l = i-1, i, i+1
+  double tc[3] = {0.0, 1.0, 0.0};
+  if (prm.curl_orient)
+  {
+    const int8_t *co = prm.curl_orient + (size_t)e * P * 3;
+    tc[1] = (double)co[3 * i + 1];
+    tc[0] = i > 0 ? (double)co[3 * (i - 1) + 2] : 0.0;      // T(i-1, i)
+    tc[2] = i < P - 1 ? (double)co[3 * (i + 1) + 0] : 0.0;  // T(i+1, i)
+  }
+  auto col = [&](int row) -> double
+  {
+    const double *r = prm.T + (size_t)row * prm.Ppad;
+    double v = tc[1] * r[i];
+    if (tc[0] != 0.0) v += tc[0] * r[i - 1];
+    if (tc[2] != 0.0) v += tc[2] * r[i + 1];
+    return v;
+  };
   double s = 0.0;
   for (int iq = 0; iq < Q; iq++)
   {
@@ -211,16 +231,14 @@ __global__ void dense_diag_kernel(DenseParams prm)
     if (MASS || H1)
     {
       const int r0 = MASS ? prm.row_u : prm.row_c;
-      double u[3] = {prm.T[(size_t)(r0 + iq) * prm.Ppad + i], prm.T[(size_t)(r0 + Q + iq) * prm.Ppad + i],
-                     prm.T[(size_t)(r0 + 2 * Q + iq) * prm.Ppad + i]};
+      double u[3] = {col(r0 + iq), col(r0 + Q + iq), col(r0 + 2 * Q + iq)};
       AtCAx(A, C0, u, g[0], v);
       s += u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
     }
     if (CURL)
     {
       const int r0 = prm.row_c;
-      double c[3] = {prm.T[(size_t)(r0 + iq) * prm.Ppad + i], prm.T[(size_t)(r0 + Q + iq) * prm.Ppad + i],
-                     prm.T[(size_t)(r0 + 2 * Q + iq) * prm.Ppad + i]}, Jd[9];
+      double c[3] = {col(r0 + iq), col(r0 + Q + iq), col(r0 + 2 * Q + iq)}, Jd[9];
       cofactor33(A, Jd);
       AtCAx(Jd, C1, c, g[0], v);
       s += c[0] * v[0] + c[1] * v[1] + c[2] * v[2];

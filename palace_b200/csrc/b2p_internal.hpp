@@ -142,6 +142,11 @@ struct b2p_interp
   int ident[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   double *mats = nullptr;
   int n_mats = 0;
+  // element-dense variant (any element type, b2p_interp_create_dense): one [out_P][in_P] matrix, native dof order,
+  // optional tridiagonal transformations of the two restrictions
+  bool dense = false;
+  double *dmat = nullptr;
+  int8_t *in_co = nullptr, *out_co = nullptr;  // [ne][P][3] rows or null
 };
 
 namespace b2p

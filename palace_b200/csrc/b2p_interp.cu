@@ -7,6 +7,8 @@
 // by the inverse dof multiplicity on Mult and the input on MultTranspose
 // (/root/reference/palace/fem/libceed/operator.cpp:182-212). On hexes that dense matrix is a Kronecker
 // product of 1-D matrices per vector component; it is applied here in that factored form.
+#include <algorithm>
+
 #include "b2p_internal.hpp"
 #include "b2p_contract.cuh"
 
@@ -133,6 +135,124 @@ __global__ void interp_kernel(InterpParams prm, int neb)
   }
 }
 
+// Element-dense interpolator for any element type (tets: p-prolongation and discrete gradient from
+// GetTransferMatrix / ProjectGrad, basis.cpp:116-165): y_L += alpha * (1/mult) E_out^T ( M E_in x_L ), with the
+// restrictions' tridiagonal transformations when the spaces need them (domain side: InvTransformPrimal rows, range side:
+// InvTransformDual rows, restriction.cpp:301-329). Transposed: the input is scaled by 1/mult (operator.cpp:224-235).
+struct DenseInterpParams
+{
+  const int32_t *in_lidx, *out_lidx;
+  const int8_t *in_co, *out_co;
+  const double *inv_mult, *M, *x;
+  double *y;
+  double alpha;
+  int ne, in_P, out_P, in_PS, out_PS;
+};
+constexpr int DI_NEB = 8;
+
+// v <- T v (rows co[i] = {T(i,i-1), T(i,i), T(i,i+1)}) or v <- T^T v, for the element slots of one block
+__device__ __forceinline__ void tri_apply(const int8_t *co, int P, bool transpose, const double *src, double *dst, int ne_blk, int e0, int ne)
+{
+  for (int w = threadIdx.x; w < ne_blk * P; w += blockDim.x)
+  {
+    const int e = w / P, i = w % P;
+    double v = 0.0;
+    if (e0 + e < ne)
+    {
+      const int8_t *c = co + (size_t)(e0 + e) * P * 3;
+      const double *s = src + e * P;
+      if (!transpose)
+      {
+        v = (double)c[3 * i + 1] * s[i];
+        if (i > 0) v += (double)c[3 * i + 0] * s[i - 1];
+        if (i < P - 1) v += (double)c[3 * i + 2] * s[i + 1];
+      }
+      else
+      {
+        v = (double)c[3 * i + 1] * s[i];
+        if (i > 0) v += (double)c[3 * (i - 1) + 2] * s[i - 1];
+        if (i < P - 1) v += (double)c[3 * (i + 1) + 0] * s[i + 1];
+      }
+    }
+    dst[w] = v;
+  }
+}
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(256) dense_interp_kernel(DenseInterpParams prm)
+{
+  B2P_DYN_SMEM(double, sm);
+  const int src_P = TRANSPOSE ? prm.out_P : prm.in_P, dst_P = TRANSPOSE ? prm.in_P : prm.out_P;
+  const int src_PS = TRANSPOSE ? prm.out_PS : prm.in_PS, dst_PS = TRANSPOSE ? prm.in_PS : prm.out_PS;
+  const int32_t *src_lidx = TRANSPOSE ? prm.out_lidx : prm.in_lidx, *dst_lidx = TRANSPOSE ? prm.in_lidx : prm.out_lidx;
+  // the transformation that acts on the gathered values, and the one that acts before the scatter:
+  //   Mult:       u = T_in x_e            ...  z = D_out^T (M u)
+  //   Transpose:  u = D_out (x_e / mult)  ...  z = T_in^T (M^T u)
+  const int8_t *src_co = TRANSPOSE ? prm.out_co : prm.in_co, *dst_co = TRANSPOSE ? prm.in_co : prm.out_co;
+  const int PM = src_P > dst_P ? src_P : dst_P;
+  double *a = sm, *b = sm + DI_NEB * PM;  // two [NEB][PM] work vectors
+  const int e0 = blockIdx.x * DI_NEB;
+  for (int w = threadIdx.x; w < DI_NEB * src_P; w += blockDim.x)
+  {
+    const int e = w / src_P, l = w % src_P;
+    double v = 0.0;
+    if (e0 + e < prm.ne)
+    {
+      const int32_t gi = src_lidx[(size_t)(e0 + e) * src_PS + l];
+      v = gather1(prm.x, gi);
+      if (TRANSPOSE && gi != B2P_SKIP_IDX) v *= prm.inv_mult[gi >= 0 ? gi : -1 - gi];
+    }
+    a[w] = v;
+  }
+  __syncthreads();
+  const double *u = a;
+  if (src_co)
+  {
+    tri_apply(src_co, src_P, false, a, b, DI_NEB, e0, prm.ne);
+    __syncthreads();
+    u = b;
+  }
+  double *r = (u == a) ? b : a;  // result of the dense product
+  for (int w = threadIdx.x; w < DI_NEB * dst_P; w += blockDim.x)
+  {
+    const int e = w / dst_P, i = w % dst_P;
+    double s = 0.0;
+    if (e0 + e < prm.ne)
+    {
+      const double *ue = u + e * src_P;
+      if (!TRANSPOSE)
+      {
+        const double *row = prm.M + (size_t)i * prm.in_P;
+        for (int j = 0; j < src_P; j++) s += row[j] * ue[j];
+      }
+      else
+      {
+        const double *col = prm.M + i;
+        for (int j = 0; j < src_P; j++) s += col[(size_t)j * prm.in_P] * ue[j];
+      }
+    }
+    r[w] = s;
+  }
+  __syncthreads();
+  const double *z = r;
+  if (dst_co)
+  {
+    double *t = (r == a) ? b : a;
+    tri_apply(dst_co, dst_P, true, r, t, DI_NEB, e0, prm.ne);
+    __syncthreads();
+    z = t;
+  }
+  for (int w = threadIdx.x; w < DI_NEB * dst_P; w += blockDim.x)
+  {
+    const int e = w / dst_P, l = w % dst_P;
+    if (e0 + e >= prm.ne) continue;
+    const int32_t gi = dst_lidx[(size_t)(e0 + e) * dst_PS + l];
+    double v = prm.alpha * z[w];
+    if (!TRANSPOSE && gi != B2P_SKIP_IDX) v *= prm.inv_mult[gi >= 0 ? gi : -1 - gi];
+    scatter1(prm.y, gi, v);
+  }
+}
+
 InterpParams make_params(const b2p_interp *it, double alpha, const double *x, double *y)
 {
   InterpParams p;
@@ -196,6 +316,32 @@ int build_lidx(b2p_ctx *ctx, int ne, int P, int64_t lsize, const int32_t *idx, c
 
 int interp_apply(const b2p_interp *it, bool transpose, double alpha, const double *x, double *y, cudaStream_t s)
 {
+  if (it->dense)
+  {
+    DenseInterpParams dp;
+    dp.in_lidx = it->in_lidx;
+    dp.out_lidx = it->out_lidx;
+    dp.in_co = it->in_co;
+    dp.out_co = it->out_co;
+    dp.inv_mult = it->inv_mult;
+    dp.M = it->dmat;
+    dp.x = x;
+    dp.y = y;
+    dp.alpha = alpha;
+    dp.ne = it->ne;
+    dp.in_P = it->in_P;
+    dp.out_P = it->out_P;
+    dp.in_PS = it->in_PS;
+    dp.out_PS = it->out_PS;
+    const size_t shmem = sizeof(double) * 2 * DI_NEB * (size_t)std::max(it->in_P, it->out_P);
+    const int grid = (it->ne + DI_NEB - 1) / DI_NEB;
+    if (transpose)
+      B2P_LAUNCH(dense_interp_kernel<true>, grid, 256, shmem, s, dp);
+    else
+      B2P_LAUNCH(dense_interp_kernel<false>, grid, 256, shmem, s, dp);
+    B2P_CUDA(it->ctx, cudaGetLastError());
+    return B2P_SUCCESS;
+  }
   InterpParams prm = make_params(it, alpha, x, y);
   const int src_P = transpose ? it->out_P : it->in_P;
   // enough elements per block that every thread has at least two destination dofs
@@ -271,6 +417,51 @@ int b2p_interp_create(b2p_ctx *ctx, const b2p_interp_desc *d, b2p_interp **out)
   return B2P_SUCCESS;
 }
 
+int b2p_interp_create_dense(b2p_ctx *ctx, const b2p_dense_interp_desc *d, b2p_interp **out)
+{
+  B2P_CHECK(ctx, ctx && d && out && d->in_idx && d->out_idx && d->mat, B2P_ERR_ARG, "b2p_interp_create_dense: null argument");
+  B2P_CHECK(ctx, d->ne > 0 && d->in_P > 0 && d->out_P > 0, B2P_ERR_ARG, "b2p_interp_create_dense: empty");
+  B2P_CHECK(ctx, sizeof(double) * 2 * DI_NEB * (size_t)std::max(d->in_P, d->out_P) <= 48 * 1024, B2P_ERR_UNSUPPORTED,
+            "b2p_interp_create_dense: element too large (%d x %d)", d->out_P, d->in_P);
+  b2p_interp *it = new b2p_interp;
+  it->ctx = ctx;
+  it->dense = true;
+  it->ne = d->ne;
+  it->in_P = d->in_P;
+  it->out_P = d->out_P;
+  it->in_lsize = d->in_lsize;
+  it->out_lsize = d->out_lsize;
+  it->ncomp = 0;
+  int rc;
+  std::vector<int32_t> out_host;
+  // with a tridiagonal transformation the signs live in it (restriction.cpp:318-329): plain indices
+  if ((rc = build_lidx(ctx, d->ne, d->in_P, d->in_lsize, d->in_idx, d->in_curl_orient ? nullptr : d->in_orient, nullptr, &it->in_PS,
+                       &it->in_lidx, nullptr)) ||
+      (rc = build_lidx(ctx, d->ne, d->out_P, d->out_lsize, d->out_idx, d->out_curl_orient ? nullptr : d->out_orient, nullptr,
+                       &it->out_PS, &it->out_lidx, &out_host)))
+  {
+    b2p_interp_destroy(it);
+    return rc;
+  }
+  std::vector<double> mult((size_t)d->out_lsize, 0.0);
+  for (int32_t g : out_host)
+  {
+    if (g == (int32_t)B2P_SKIP_IDX) continue;
+    mult[g >= 0 ? g : -1 - g] += 1.0;
+  }
+  for (auto &m : mult) m = m > 0.0 ? 1.0 / m : 0.0;
+  if ((rc = upload(ctx, mult.data(), mult.size(), &it->inv_mult)) ||
+      (rc = upload(ctx, d->mat, (size_t)d->out_P * d->in_P, &it->dmat)) ||
+      (d->in_curl_orient && (rc = upload(ctx, d->in_curl_orient, (size_t)d->ne * d->in_P * 3, &it->in_co))) ||
+      (d->out_curl_orient && (rc = upload(ctx, d->out_curl_orient, (size_t)d->ne * d->out_P * 3, &it->out_co))))
+  {
+    b2p_interp_destroy(it);
+    return rc;
+  }
+  *out = it;
+  return B2P_SUCCESS;
+}
+
 int b2p_interp_apply_add(b2p_interp *it, int transpose, double alpha, const double *x, double *y, b2p_stream s)
 {
   if (!it || !x || !y) return B2P_ERR_ARG;
@@ -284,6 +475,9 @@ void b2p_interp_destroy(b2p_interp *it)
   cudaFree(it->out_lidx);
   cudaFree(it->inv_mult);
   cudaFree(it->mats);
+  cudaFree(it->dmat);
+  cudaFree(it->in_co);
+  cudaFree(it->out_co);
   delete it;
 }
 

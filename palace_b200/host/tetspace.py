@@ -491,3 +491,197 @@ def interpolate(mesh: TetMesh, space: TetSpace, field) -> np.ndarray:
                         x[int_base + nid * e + o] = Jm[:, d] @ E
                         o += 1
     return x
+
+
+# ------------------------------------------------------------------------------------------------
+# H1 tetrahedron (auxiliary space of the Hiptmair smoother) and the element-local transfer matrices
+# (discrete gradient G, p-prolongations): what Palace builds with ProjectGrad / GetTransferMatrix
+# (/root/reference/palace/fem/libceed/basis.cpp:116-165, fem/bilinearform.cpp:203-282)
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclasses.dataclass
+class H1TetElement:
+    p: int
+    P: int
+    nodes: np.ndarray   # [P][3] reference nodes: vertices, edge interiors, face interiors, interior
+    coef: np.ndarray    # [P][M] nodal basis in the modal (Legendre product) basis
+
+    def tabulate(self, pts):
+        """(values[n][P], grad[3][n][P]) of the nodal basis at pts."""
+        V, dV = _h1_modal(self.p, np.asarray(pts, dtype=np.float64))
+        return V @ self.coef.T, np.ascontiguousarray(np.einsum("nmd,pm->dnp", dV, self.coef))
+
+
+def _h1_modal(p, pts):
+    Lx, dLx = _leg01(p, pts[:, 0])
+    Ly, dLy = _leg01(p, pts[:, 1])
+    Lz, dLz = _leg01(p, pts[:, 2])
+    V, dV = [], []
+    for c in range(p + 1):
+        for b in range(p + 1 - c):
+            for a in range(p + 1 - b - c):
+                V.append(Lx[:, a] * Ly[:, b] * Lz[:, c])
+                dV.append(np.stack([dLx[:, a] * Ly[:, b] * Lz[:, c], Lx[:, a] * dLy[:, b] * Lz[:, c], Lx[:, a] * Ly[:, b] * dLz[:, c]], axis=1))
+    return np.stack(V, axis=1), np.stack(dV, axis=1)   # [n][M], [n][M][3]
+
+
+def _h1_nodes(p):
+    V = _REF_VERTS
+    nodes = [V[i] for i in range(4)]
+    for (a, b) in TET_EDGES:
+        for m in range(1, p):
+            nodes.append(V[a] + (m / p) * (V[b] - V[a]))
+    for (a, b, c) in TET_FACES:
+        for j in range(1, p):
+            for i in range(1, p - j):
+                nodes.append(((p - i - j) * V[a] + i * V[b] + j * V[c]) / p)
+    for k in range(1, p):
+        for j in range(1, p - k):
+            for i in range(1, p - k - j):
+                nodes.append(np.array([i, j, k]) / p)
+    return np.array(nodes)
+
+
+_H1_ELEMENTS = {}
+
+
+def h1_tet_element(p: int) -> H1TetElement:
+    if p not in _H1_ELEMENTS:
+        nodes = _h1_nodes(p)
+        P = (p + 1) * (p + 2) * (p + 3) // 6
+        assert nodes.shape[0] == P
+        V, _ = _h1_modal(p, nodes)
+        _H1_ELEMENTS[p] = H1TetElement(p, P, nodes, np.linalg.inv(V).T)
+    return _H1_ELEMENTS[p]
+
+
+@dataclasses.dataclass
+class H1TetSpace:
+    p: int
+    P: int
+    ndofs: int
+    idx: np.ndarray      # [ne][P] int32 (no orientation: nodal values)
+    ess_dofs: np.ndarray
+
+
+def face_interior_index(p):
+    out, o = {}, 0
+    for j in range(1, p):
+        for i in range(1, p - j):
+            out[(i, j)] = o
+            o += 1
+    return out
+
+
+def build_h1_tet_space(mesh: TetMesh, nd_space: TetSpace, p: int) -> H1TetSpace:
+    """Order-p nodal space on the same mesh (shares the edge / face numbering of the ND space)."""
+    el = h1_tet_element(p)
+    ne = mesh.ne
+    nv = mesh.verts.shape[0]
+    n_e, n_f = p - 1, (p - 1) * (p - 2) // 2
+    n_i = (p - 1) * (p - 2) * (p - 3) // 6
+    edge_base = nv
+    face_base = edge_base + n_e * nd_space.n_edges
+    int_base = face_base + n_f * nd_space.n_faces
+    ndofs = int_base + n_i * ne
+    fidx = face_interior_index(p)
+    idx = np.zeros((ne, el.P), dtype=np.int32)
+    face_count = {}
+    for e in range(ne):
+        v = mesh.elems[e]
+        idx[e, :4] = v
+        o = 4
+        for (a, b) in TET_EDGES:
+            ga, gb = int(v[a]), int(v[b])
+            base = edge_base + n_e * nd_space.edges[(min(ga, gb), max(ga, gb))]
+            for m in range(1, p):
+                idx[e, o] = base + ((m if ga < gb else p - m) - 1)
+                o += 1
+        for f in TET_FACES:
+            g = [int(v[t]) for t in f]
+            key = tuple(sorted(g))
+            face_count[key] = face_count.get(key, 0) + 1
+            base = face_base + n_f * nd_space.faces[key]
+            rank = [key.index(t) for t in g]
+            for j in range(1, p):
+                for i in range(1, p - j):
+                    trip = (p - i - j, i, j)
+                    gtrip = [0, 0, 0]
+                    for t in range(3):
+                        gtrip[rank[t]] = trip[t]
+                    idx[e, o] = base + fidx[(gtrip[1], gtrip[2])]
+                    o += 1
+        for t in range(n_i):
+            idx[e, o] = int_base + n_i * e + t
+            o += 1
+        assert o == el.P
+    ess = set()
+    for k, c in face_count.items():
+        if c != 1:
+            continue
+        ess.update(k)
+        base = face_base + n_f * nd_space.faces[k]
+        ess.update(range(base, base + n_f))
+        for (a, b) in ((0, 1), (0, 2), (1, 2)):
+            eb = edge_base + n_e * nd_space.edges[(k[a], k[b])]
+            ess.update(range(eb, eb + n_e))
+    return H1TetSpace(p, el.P, ndofs, idx, np.array(sorted(ess), dtype=np.int32))
+
+
+def nd_tet_prolongation(pc: int, pf: int) -> np.ndarray:
+    """[P_f][P_c]: fine functionals of the coarse shape functions (nested spaces: exact)."""
+    ec, ef = nd_tet_element(pc), nd_tet_element(pf)
+    interp, _ = ec.tabulate(ef.nodes)                       # [3][P_f nodes][P_c]
+    return np.einsum("cnd,nc->nd", interp, ef.tangents)
+
+
+def h1_tet_prolongation(pc: int, pf: int) -> np.ndarray:
+    vals, _ = h1_tet_element(pc).tabulate(h1_tet_element(pf).nodes)
+    return vals                                              # [P_f][P_c]
+
+
+def tet_discrete_gradient(p: int) -> np.ndarray:
+    """[P_nd][P_h1]: ND functionals of the gradients of the order-p nodal basis (grad H1_p is a subspace of ND_p)."""
+    nd = nd_tet_element(p)
+    _, grad = h1_tet_element(p).tabulate(nd.nodes)           # [3][P_nd nodes][P_h1]
+    return np.einsum("cnj,nc->nj", grad, nd.tangents)
+
+
+def dual_orient(space: TetSpace) -> np.ndarray:
+    """Range-side transformation of interpolators: int8 rows of T^-T, so that the transposed restriction applies T^-1
+    (the reference fills it from InvTransformDual, restriction.cpp:309-317). Blocks are 1x1 (signs) or unimodular 2x2."""
+    ne, P = space.curl_orient.shape[:2]
+    out = np.zeros_like(space.curl_orient)
+    for e in range(ne):
+        T = space.dense_T(e)
+        D = np.rint(np.linalg.inv(T).T).astype(np.int64)
+        assert np.abs(D).max() <= 1
+        out[e, :, 1] = np.diag(D)
+        out[e, 1:, 0] = np.diag(D, -1)
+        out[e, :-1, 2] = np.diag(D, 1)
+        chk = np.diag(np.diag(D)) + np.diag(np.diag(D, -1), -1) + np.diag(np.diag(D, 1), 1)
+        assert (chk == D).all()
+    return out
+
+
+def global_interp_matrix(I_loc, in_idx, in_T, out_idx, out_Tdual, n_in, n_out):
+    """Oracle-side assembled interpolator y = (1/mult) sum_e E_out^T (I_loc E_in x) with the curl-oriented
+    restrictions (dense T per element or None), as ceed::Operator::Mult does for interpolators
+    (/root/reference/palace/fem/libceed/operator.cpp:182-190)."""
+    import scipy.sparse as sp
+
+    ne = in_idx.shape[0]
+    rows, cols, vals = [], [], []
+    mult = np.zeros(n_out)
+    for e in range(ne):
+        M = I_loc if in_T is None else I_loc @ in_T(e)
+        if out_Tdual is not None:
+            M = out_Tdual(e).T @ M
+        r, c = np.meshgrid(out_idx[e], in_idx[e], indexing="ij")
+        rows.append(r.ravel())
+        cols.append(c.ravel())
+        vals.append(M.ravel())
+        np.add.at(mult, out_idx[e], 1.0)
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_out, n_in))
+    return sp.diags(1.0 / mult) @ A

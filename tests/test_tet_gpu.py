@@ -122,3 +122,125 @@ def test_tet_essential_rows_and_pec_box_energy(b2p_ctx):
     yd = torch.empty(sp.ndofs, dtype=torch.float64, device="cuda")
     A.mult(_dev(x), yd)
     assert _rel(yd.cpu().numpy(), y_ref) < RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# Transfer operators and the multigrid loop on tetrahedra
+# ------------------------------------------------------------------------------------------------
+
+
+def _dual_T(dual, e):
+    P = dual.shape[1]
+    co = dual[e]
+    T = np.zeros((P, P))
+    T[np.arange(P), np.arange(P)] = co[:, 1]
+    T[np.arange(1, P), np.arange(P - 1)] = co[1:, 0]
+    T[np.arange(P - 1), np.arange(1, P)] = co[:-1, 2]
+    return T
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_tet_interpolators_match_assembled_matrices(b2p_ctx, p):
+    """P_l (ND p-1 -> p), G (H1 p -> ND p) and the H1 prolongation as element-dense interpolators with curl-oriented
+    restrictions on both sides, Mult and MultTranspose, against the oracle-side assembled matrices."""
+    from palace_b200 import capi
+
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.25, scramble_seed=5)
+    ndf, ndc = ts.build_nd_tet_space(mesh, p), ts.build_nd_tet_space(mesh, p - 1)
+    h1f, h1c = ts.build_h1_tet_space(mesh, ndf, p), ts.build_h1_tet_space(mesh, ndf, p - 1)
+    dual = ts.dual_orient(ndf)
+    cases = [
+        ("P_l", ts.nd_tet_prolongation(p - 1, p), ndc.idx, ndc.ndofs, ndc.curl_orient, ndc.dense_T, ndf.idx, ndf.ndofs, dual),
+        ("G", ts.tet_discrete_gradient(p), h1f.idx, h1f.ndofs, None, None, ndf.idx, ndf.ndofs, dual),
+        ("P_h1", ts.h1_tet_prolongation(p - 1, p), h1c.idx, h1c.ndofs, None, None, h1f.idx, h1f.ndofs, None),
+    ]
+    rng = np.random.default_rng(11)
+    for name, M, iidx, nin, ico, iT, oidx, nout, oco in cases:
+        it = capi.Interp.dense(b2p_ctx, M, iidx, nin, oidx, nout, in_curl_orient=ico, out_curl_orient=oco)
+        ref = ts.global_interp_matrix(M, iidx, iT, oidx, (lambda e: _dual_T(oco, e)) if oco is not None else None, nin, nout)
+        x, z = rng.random(nin), rng.random(nout)
+        y = torch.zeros(nout, dtype=torch.float64, device="cuda")
+        it.apply_add(_dev(x), y)
+        assert _rel(y.cpu().numpy(), ref @ x) < RTOL, name
+        w = torch.zeros(nin, dtype=torch.float64, device="cuda")
+        it.apply_add(_dev(z), w, transpose=True, alpha=-2.0)
+        assert _rel(w.cpu().numpy(), -2.0 * (ref.T @ z)) < RTOL, name + "^T"
+
+
+def test_tet_multigrid_preconditioned_solve(b2p_ctx):
+    """FGMRES preconditioned by the p-multigrid V-cycle with Hiptmair auxiliary-space smoothing (Chebyshev on ND and on
+    the H1 space through the discrete gradient, distrelaxation.cpp:99-151; CG + Jacobi on the coarsest level) on a
+    scrambled tetrahedral mesh with PEC boundary: converges, and the answer solves the oracle's assembled system."""
+    from palace_b200 import capi
+
+    capi.set_stream(b2p_ctx)
+    mesh = ts.box_tet_mesh((2, 1, 2), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=3)
+    orders = [1, 2]
+    spaces = [ts.build_nd_tet_space(mesh, p) for p in orders]
+    h1s = [ts.build_h1_tet_space(mesh, sp, sp.p) for sp in spaces]
+    _, _, qpts, qw = ts.nd_tet_tables(orders[-1])           # every level integrates with the fine rule (shared q-data)
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    geom = capi.Geom.general(b2p_ctx, qd)
+    one = cf.coeff_ctx(a=1.0)
+    blob = cf.coeff_ctx_pair(one, one)
+    pars, auxs, grads = [], [], []
+    for sp, h1 in zip(spaces, h1s):
+        interp, curl = ts.nd_tet_element(sp.p).tabulate(qpts)
+        op = capi.Op.create_dense(b2p_ctx, geom, O.CURLCURL_MASS, sp.ndofs, sp.idx, None, interp, curl, blob, curl_orient=sp.curl_orient)
+        pars.append(capi.Operator.par(b2p_ctx, sp.ndofs, sp.ndofs, [op], None, sp.ess_dofs, diag_policy=1))
+        # auxiliary operator G^T (K + M) G = H1 diffusion with the mass coefficient
+        _, grad = ts.h1_tet_element(h1.p).tabulate(qpts)
+        aop = capi.Op.create_dense(b2p_ctx, geom, O.H1_DIFFUSION, h1.ndofs, h1.idx, None, None, grad, one)
+        auxs.append(capi.Operator.par(b2p_ctx, h1.ndofs, h1.ndofs, [aop], None, h1.ess_dofs, diag_policy=1))
+        git = capi.Interp.dense(b2p_ctx, ts.tet_discrete_gradient(sp.p), h1.idx, h1.ndofs, sp.idx, sp.ndofs, out_curl_orient=ts.dual_orient(sp))
+        grads.append(capi.Operator.interp(b2p_ctx, git))
+    prol = []
+    for c, f in zip(spaces[:-1], spaces[1:]):
+        it = capi.Interp.dense(b2p_ctx, ts.nd_tet_prolongation(c.p, f.p), c.idx, c.ndofs, f.idx, f.ndofs,
+                               in_curl_orient=c.curl_orient, out_curl_orient=ts.dual_orient(f))
+        prol.append(capi.Operator.interp(b2p_ctx, it))
+    coarse = capi.Solver.krylov(b2p_ctx, capi.CG, rel_tol=1e-12, max_it=500)
+    cj = capi.Solver.jacobi(b2p_ctx)
+    cj.set_operator(pars[0])
+    coarse.set_preconditioner(cj)
+    coarse.set_operator(pars[0])
+    gmg = capi.Solver.gmg(b2p_ctx, coarse, prol, grads, cycle_it=1, smooth_it=1, cheby_order=4)
+    gmg.gmg_set_operators(pars, auxs)
+    ksp = capi.Solver.krylov(b2p_ctx, capi.FGMRES, rel_tol=1e-10, max_it=60)
+    ksp.set_preconditioner(gmg)
+    ksp.set_operator(pars[-1])
+    fine = spaces[-1]
+    b = np.random.default_rng(2).random(fine.ndofs)
+    b[fine.ess_dofs] = 0.0
+    x = torch.zeros(fine.ndofs, dtype=torch.float64, device="cuda")
+    ksp.mult(_dev(b), x)
+    st = ksp.stats()
+    assert st["converged"] and st["its"] < 30, st
+    # oracle matrix with the essential rows/columns eliminated (DIAG_ONE)
+    interp, curl = ts.nd_tet_element(fine.p).tabulate(qpts)
+    Ae = O.element_matrices(O.CURLCURL_MASS, interp, curl, None, qd, blob, fine.P)
+    A = np.zeros((fine.ndofs, fine.ndofs))
+    for e in range(mesh.ne):
+        T = fine.dense_T(e)
+        A[np.ix_(fine.idx[e], fine.idx[e])] += T.T @ Ae[e] @ T
+    ess = fine.ess_dofs
+    A[ess, :] = 0
+    A[:, ess] = 0
+    A[ess, ess] = 1.0
+    xs = x.cpu().numpy()
+    assert np.linalg.norm(b - A @ xs) < 1e-9 * np.linalg.norm(b)      # true residual against the oracle matrix
+    assert _rel(xs, np.linalg.solve(A, b)) < 1e-9 * np.linalg.cond(A)  # error bound: residual x condition number
+
+
+def test_tet_diagonal_is_exact_with_curl_oriented_restriction(b2p_ctx):
+    mesh, sp, interp, curl, qd = _problem(2, (2, 1, 1), n_attr=1)
+    blob = cf.coeff_ctx_pair(cf.coeff_ctx(a=1.0), cf.coeff_ctx(a=2.0))
+    op = _op(b2p_ctx, O.CURLCURL_MASS, sp, interp, curl, qd, blob)
+    d = torch.zeros(sp.ndofs, dtype=torch.float64, device="cuda")
+    op.diag_add(d)
+    Ae = O.element_matrices(O.CURLCURL_MASS, interp, curl, None, qd, blob, sp.P)
+    ref = np.zeros(sp.ndofs)
+    for e in range(mesh.ne):
+        T = sp.dense_T(e)
+        np.add.at(ref, sp.idx[e], np.diag(T.T @ Ae[e] @ T))
+    assert _rel(d.cpu().numpy(), ref) < RTOL
