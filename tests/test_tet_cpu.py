@@ -192,3 +192,54 @@ def test_curl_oriented_oracle_equals_element_matrix_assembly():
         np.add.at(y_ref, sp.idx[e], T.T @ (Ae[e] @ (T @ x[sp.idx[e]])))
     y = _apply(O.CURLCURL_MASS, sp, interp, curl, qd, blob, x)
     assert np.linalg.norm(y - y_ref) < 1e-13 * np.linalg.norm(y_ref)
+
+
+def _assemble_dense(kind, mesh, interp, deriv, idx, Tfun, n, P, qd):
+    one = cf.coeff_ctx(a=1.0)
+    Ae = O.element_matrices(kind, interp, deriv, None, qd, one, P)
+    A = np.zeros((n, n))
+    for e in range(mesh.ne):
+        T = np.eye(P) if Tfun is None else Tfun(e)
+        A[np.ix_(idx[e], idx[e])] += T.T @ Ae[e] @ T
+    return A
+
+
+def _tri(co):
+    P = co.shape[0]
+    T = np.zeros((P, P))
+    T[np.arange(P), np.arange(P)] = co[:, 1]
+    T[np.arange(1, P), np.arange(P - 1)] = co[1:, 0]
+    T[np.arange(P - 1), np.arange(1, P)] = co[:-1, 2]
+    return T
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_transfer_operators_on_tets(p):
+    """Discrete gradient and p-prolongation on scrambled tets, with the range-side (dual) transformation of the
+    interpolators: K G = 0, G^T M G = H1 stiffness, P^T K P = K_coarse, P^T M P = M_coarse -- to round-off."""
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.25, scramble_seed=5)
+    nd = ts.build_nd_tet_space(mesh, p)
+    h1 = ts.build_h1_tet_space(mesh, nd, p)
+    assert sorted(np.unique(h1.idx)) == list(range(h1.ndofs))
+    interp, curl, qpts, qw = ts.nd_tet_tables(p)
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    K = _assemble_dense(O.CURLCURL, mesh, interp, curl, nd.idx, nd.dense_T, nd.ndofs, nd.P, qd)
+    M = _assemble_dense(O.ND_MASS, mesh, interp, curl, nd.idx, nd.dense_T, nd.ndofs, nd.P, qd)
+    vals, grad = ts.h1_tet_element(p).tabulate(qpts)
+    assert np.abs(vals.sum(axis=1) - 1.0).max() < 1e-12                      # partition of unity
+    A1 = _assemble_dense(O.H1_DIFFUSION, mesh, None, grad, h1.idx, None, h1.ndofs, h1.P, qd)
+    dual = ts.dual_orient(nd)
+    Td = lambda e: _tri(dual[e])
+    for e in range(mesh.ne):
+        assert np.abs(Td(e).T @ nd.dense_T(e) - np.eye(nd.P)).max() == 0      # dual rows are T^-T exactly
+    G = ts.global_interp_matrix(ts.tet_discrete_gradient(p), h1.idx, None, nd.idx, Td, h1.ndofs, nd.ndofs).toarray()
+    assert np.abs(K @ G).max() < 1e-12 * np.abs(K).max()
+    assert np.abs(G.T @ M @ G - A1).max() < 1e-12 * np.abs(A1).max()
+    if p > 1:
+        ndc = ts.build_nd_tet_space(mesh, p - 1)
+        Pg = ts.global_interp_matrix(ts.nd_tet_prolongation(p - 1, p), ndc.idx, ndc.dense_T, nd.idx, Td, ndc.ndofs, nd.ndofs).toarray()
+        ic, cc = ts.nd_tet_element(p - 1).tabulate(qpts)
+        Kc = _assemble_dense(O.CURLCURL, mesh, ic, cc, ndc.idx, ndc.dense_T, ndc.ndofs, ndc.P, qd)
+        Mc = _assemble_dense(O.ND_MASS, mesh, ic, cc, ndc.idx, ndc.dense_T, ndc.ndofs, ndc.P, qd)
+        assert np.abs(Pg.T @ K @ Pg - Kc).max() < 1e-12 * np.abs(Kc).max()
+        assert np.abs(Pg.T @ M @ Pg - Mc).max() < 1e-12 * np.abs(Mc).max()
