@@ -273,18 +273,21 @@ int b2p_solver_set_initial_guess(b2p_solver *s, int flag)
 int b2p_solver_mult(b2p_solver *s, const double *x, double *y)
 {
   if (!s || !s->s) return B2P_ERR_ARG;
+  B2P_CHECK(s->s->ctx, s->s->Height() > 0, B2P_ERR_ARG, "solver applied before SetOperator (a preconditioner needs its own set_operator call, as in Palace's KspSolver::SetOperators)");
   B2P_TRY(s->s->ctx, s->s->Mult(x, y));
   return B2P_SUCCESS;
 }
 int b2p_solver_mult2(b2p_solver *s, const double *x, double *y, double *r)
 {
   if (!s || !s->s) return B2P_ERR_ARG;
+  B2P_CHECK(s->s->ctx, s->s->Height() > 0, B2P_ERR_ARG, "solver applied before SetOperator (a preconditioner needs its own set_operator call, as in Palace's KspSolver::SetOperators)");
   B2P_TRY(s->s->ctx, s->s->Mult2(x, y, r));
   return B2P_SUCCESS;
 }
 int b2p_solver_mult_transpose2(b2p_solver *s, const double *x, double *y, double *r)
 {
   if (!s || !s->s) return B2P_ERR_ARG;
+  B2P_CHECK(s->s->ctx, s->s->Height() > 0, B2P_ERR_ARG, "solver applied before SetOperator (a preconditioner needs its own set_operator call, as in Palace's KspSolver::SetOperators)");
   B2P_TRY(s->s->ctx, s->s->MultTranspose2(x, y, r));
   return B2P_SUCCESS;
 }
