@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
 
   const double alpha = prm.alpha;
   int slot = 0;
+  bool y_ready = false;
   for (; b < nb; b += GW)
   {
     const int nslot = (slot == 2) ? 0 : slot + 1;
@@ -725,6 +726,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
     __syncwarp();
 
     // ------------------------------------------------------------------ phase Zt (transposed z-contraction + scatter)
+    // First write to y: under programmatic dependent launch the zero-fill of y that precedes this kernel in the stream
+    // may still be running -- everything above (index / geometry / x traffic and the arithmetic of the first batch) has
+    // overlapped with it.
+    if (!y_ready)
+    {
+      griddep_wait();
+      y_ready = true;
+    }
     {
       constexpr int IPX = p * n, IPZ = n * n, LSX = L::LSX, LSZ = L::LSZ;
       constexpr int LW = (NEW * LSX > NEW * LSZ) ? NEW * LSX : NEW * LSZ;
@@ -857,7 +866,10 @@ int launch4(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   const int nb = (e_cnt + L::NEW - 1) / L::NEW;
   int grid = op->ctx->sm_count * MINB;
   if (grid > (nb + NW - 1) / NW) grid = (nb + NW - 1) / NW;
-  B2P_LAUNCH(kern, grid, NW * 32, shmem, s, prm);
+  if (rg.pdl)
+    B2P_LAUNCH_PDL(kern, grid, NW * 32, shmem, s, prm);
+  else
+    B2P_LAUNCH(kern, grid, NW * 32, shmem, s, prm);
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

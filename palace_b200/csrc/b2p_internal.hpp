@@ -47,9 +47,27 @@ int upload(b2p_ctx *ctx, const T *host, size_t n, T **dptr);
 #ifdef B2P_EMU
 #define B2P_LAUNCH(kern, grid, block, shmem, stream, ...) \
   ::cuda_emu::launch(dim3(grid), dim3(block), (size_t)(shmem), [=]() { kern(__VA_ARGS__); })
+#define B2P_LAUNCH_PDL(kern, grid, block, shmem, stream, ...) B2P_LAUNCH(kern, grid, block, shmem, stream, __VA_ARGS__)
 #define B2P_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(::cuda_emu::dyn_smem())
 #define B2P_DYN_SMEM_ALIGNED16(type, name) B2P_DYN_SMEM(type, name)
 #else
+// launch that may overlap the tail of the previous kernel in the stream (the kernel must call griddep_wait() before it
+// touches anything the predecessor writes)
+#define B2P_LAUNCH_PDL(kern, grid, block, shmem, strm__, ...)                          \
+  do                                                                                   \
+  {                                                                                    \
+    cudaLaunchConfig_t cfg__ = {};                                                     \
+    cfg__.gridDim = dim3(grid);                                                        \
+    cfg__.blockDim = dim3(block);                                                      \
+    cfg__.dynamicSmemBytes = (shmem);                                                  \
+    cfg__.stream = (strm__);                                                           \
+    cudaLaunchAttribute attr__[1];                                                     \
+    attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                 \
+    attr__[0].val.programmaticStreamSerializationAllowed = 1;                          \
+    cfg__.attrs = attr__;                                                              \
+    cfg__.numAttrs = 1;                                                                \
+    cudaLaunchKernelEx(&cfg__, kern, __VA_ARGS__);                                     \
+  } while (0)
 #define B2P_LAUNCH(kern, grid, block, shmem, stream, ...) kern<<<(grid), (block), (shmem), (stream)>>>(__VA_ARGS__)
 #define B2P_DYN_SMEM(type, name) extern __shared__ type name[]
 #define B2P_DYN_SMEM_ALIGNED16(type, name) extern __shared__ __align__(16) type name[]
@@ -162,6 +180,7 @@ struct ApplyRange
   // waits until flags[k] >= expect[k] for k < wait_n (acquire at system scope)
   const unsigned long long *wait_flags = nullptr, *wait_expect = nullptr;
   int wait_n = 0, wait_from_elem = 0;
+  bool pdl = false;  // launch with programmatic stream serialisation (kernels that call griddep_wait() only)
 };
 // Kernel launchers (defined in the .cu files).
 int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);

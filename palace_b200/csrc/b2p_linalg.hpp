@@ -39,6 +39,7 @@ void b2p_allreduce_sum(b2p_ctx *c, double *dbuf, int n);  // in place, on ctx->s
 namespace vec
 {
 void set(b2p_ctx *c, double *y, int64_t n, double v);
+void zero_release(b2p_ctx *c, double *y, int64_t n);  // y = 0 by a kernel that lets a PDL-launched successor start early
 void copy(b2p_ctx *c, double *y, const double *x, int64_t n);
 void scale(b2p_ctx *c, double *y, int64_t n, double a);
 void axpy(b2p_ctx *c, double a, const double *x, double *y, int64_t n);                       // y += a x

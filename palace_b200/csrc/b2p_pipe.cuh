@@ -31,6 +31,8 @@ inline void st_release_sys_u64(unsigned long long *p, unsigned long long v)
   ::cuda_emu::st().events++;
 }
 inline void dmma884(double &c0, double &c1, double a, double b) { ::cuda_emu::dmma884(c0, c1, a, b); }
+inline void griddep_wait() {}               // launches are synchronous in the emulation
+inline void griddep_launch_dependents() {}
 inline void red_add_f64_if(double *addr, double v, bool pred)
 {
   if (pred) atomicAdd(addr, v);
@@ -92,6 +94,12 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsign
 {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream still runs; griddepcontrol.wait blocks until the predecessor has completed and its
+// writes are visible (returns at once when the kernel was launched normally); the predecessor releases its dependent
+// early with griddepcontrol.launch_dependents.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // FP64 tensor-core MMA, D(8x8) = A(8x4) B(4x8) + C: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
 // {c0, c1} = C[lane/4][2 (lane%4) + {0, 1}]  (SASS DMMA.8x8x4)
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)

@@ -98,8 +98,25 @@ void ParOperator::Mult(const double *x, double *y) const
   cudaStream_t s = ctx->stream;
   if (!halo)
   {
-    vec::set(ctx, y, height, 0.0);
-    for (auto &t : terms) b2p_op_apply_add_ex(t.op, t.coef, x, y, B2P_APPLY_MASKED, s);
+    // B2P_PDL=1: zero-fill by a kernel that releases its dependent at once, first element kernel launched with
+    // programmatic stream serialisation: its prologue and first batch overlap the zero-fill (it waits on the grid
+    // dependency just before its first scatter). Opt-in until measured.
+    static const bool pdl = []() { const char *e = getenv("B2P_PDL"); return e && e[0] == '1'; }();
+    const b2p_op *o0 = terms[0].op;
+    const bool pdl_ok = pdl && !o0->dense && o0->kind != B2P_H1_DIFFUSION && o0->lidx_bc != nullptr;
+    if (pdl_ok)
+    {
+      vec::zero_release(ctx, y, height);
+      ApplyRange rg;
+      rg.pdl = true;
+      apply_range(terms[0].op, o0->lidx_bc, terms[0].coef, x, y, rg, B2P_APPLY_MASKED, s);
+      for (size_t t = 1; t < terms.size(); t++) b2p_op_apply_add_ex(terms[t].op, terms[t].coef, x, y, B2P_APPLY_MASKED, s);
+    }
+    else
+    {
+      vec::set(ctx, y, height, 0.0);
+      for (auto &t : terms) b2p_op_apply_add_ex(t.op, t.coef, x, y, B2P_APPLY_MASKED, s);
+    }
   }
   else
   {

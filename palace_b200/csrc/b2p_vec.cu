@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "b2p_linalg.hpp"
+#include "b2p_pipe.cuh"
 
 namespace b2p
 {
@@ -182,6 +183,17 @@ void b2p_allreduce_sum(b2p_ctx *c, double *dbuf, int n)
 namespace vec
 {
 
+// Zero-fill as a kernel that releases its dependent launch at once (see griddep_wait in the element kernel).
+__global__ void zero_release_kernel(double *y, int64_t n)
+{
+  griddep_launch_dependents();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = 0.0;
+}
+void zero_release(b2p_ctx *c, double *y, int64_t n)
+{
+  if (n > 0) B2P_LAUNCH(zero_release_kernel, grid_for(c, n), NT, 0, c->stream, y, n);
+}
 void set(b2p_ctx *c, double *y, int64_t n, double v)
 {
   if (v == 0.0)
