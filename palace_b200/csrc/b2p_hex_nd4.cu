@@ -149,7 +149,10 @@ struct ND4Layout
 template <int P_, int Q_, bool CPLX>
 using ND4ParamsT = std::conditional_t<CPLX, ND4ParamsZ<P_, Q_>, ND4Params<P_, Q_>>;
 
-template <int P_, int Q_, int KIND, bool ASM, bool SPLIT, int NW, int MINB, bool CPLX = false>
+// FWD (experimental, B2P_ND_FWDCHAIN=1): the XDX phase consumes the Z region directly -- every lane does the y-contraction
+// of its own (qy, qz) line from broadcast reads -- so the forward Y-region round trip (write + read of 7 arrays) and
+// the Y phase disappear; same arithmetic, ~14 % fewer shared-memory wavefronts per element.
+template <int P_, int Q_, int KIND, bool ASM, bool SPLIT, int NW, int MINB, bool CPLX = false, bool FWD = false>
 __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __grid_constant__ ND4ParamsT<P_, Q_, CPLX> prm)
 {
   using L = ND4Layout<P_, Q_, KIND, ASM, CPLX>;
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
 
     // ------------------------------------------------------------------ phase Y (y-contraction)
     // item w = (e, t = qz + q*i): reads row j of the Z region at column w, writes row qy of the Y region at column w
+    if constexpr (!FWD)
     {
       constexpr int IX = NEW * p * q, IN = NEW * n * q;  // x-directed items; y- and z-directed items
       constexpr int ROUNDS = (IN + 31) / 32;
@@ -458,6 +462,54 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
       double uu[q][3], cc[q][3];
       {
         double x1[p], x2[p], x3[p], y1[n], y2[n], z1[n], z3[n];
+        if constexpr (FWD)
+        {
+          // y-contraction of this lane's own (qy, qz) line straight from the Z region: the four qy-lanes of a (e, qz)
+          // read the same words (broadcast), the table rows of qy are indexed loads from the constant bank
+          const int qy = s % q, qz = s / q;
+          const double *bo = prm.Bo + qy * p, *bc = prm.Bc + qy * n, *gc = prm.Gc + qy * n;
+          const double *ZX = sW + L::ZA0 + e * NXA + qz, *ZY = sW + L::ZB0 + e * NNA + qz, *ZZ = sW + L::ZA0 + L::A_ZA + e * NNA + qz;
+#pragma unroll
+          for (int i = 0; i < p; i++)
+          {
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < n; j++)
+            {
+              const double a = ZX[L::A_XA + RSA * j + q * i];
+              if (MASS) s1 += bc[j] * a;
+              if (CURL) s3 += gc[j] * a;
+              if (CURL) s2 += bc[j] * ZX[L::A_XB + RSA * j + q * i];
+            }
+            x1[i] = s1;
+            x2[i] = s2;
+            x3[i] = s3;
+          }
+#pragma unroll
+          for (int i = 0; i < n; i++)
+          {
+            double s1 = 0.0, s2 = 0.0, t1 = 0.0, t3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < p; j++)
+            {
+              s1 += bo[j] * ZY[L::B_YA + RSB * j + q * i];
+              if (CURL) s2 += bo[j] * ZY[L::B_YB + RSB * j + q * i];
+            }
+#pragma unroll
+            for (int j = 0; j < n; j++)
+            {
+              const double a = ZZ[RSA * j + q * i];
+              t1 += bc[j] * a;
+              if (CURL) t3 += gc[j] * a;
+            }
+            y1[i] = s1;
+            y2[i] = s2;
+            z1[i] = t1;
+            z3[i] = t3;
+          }
+        }
+        else
+        {
 #pragma unroll
         for (int i = 0; i < p; i++)
         {
@@ -472,6 +524,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
           if (CURL) y2[i] = WN[L::Y_Y2 + q * i];
           z1[i] = WN[L::Y_Z1 + q * i];
           if (CURL) z3[i] = WN[L::Y_Z3 + q * i];
+        }
         }
 #pragma unroll
         for (int qx = 0; qx < q; qx++)
@@ -832,11 +885,21 @@ int launch4(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   // SPLIT: the L-vector comes in two pieces (owned part in x / y, ghosts in separate buffers)
   const bool split = rg.xg || rg.yg || (rg.n_owned >= 0 && rg.n_owned < op->lsize);
   auto kern = split ? nd_hex_apply4_kernel<P_, Q_, KIND, ASM, true, NW, MINB> : nd_hex_apply4_kernel<P_, Q_, KIND, ASM, false, NW, MINB>;
-  static bool configured[2] = {false, false};
-  if (!configured[split])
+  int variant = split ? 1 : 0;
+  if constexpr (!ASM && Q_ == P_ + 1)
+  {
+    static const bool fwd = []() { const char *e = std::getenv("B2P_ND_FWDCHAIN"); return e && e[0] == '1'; }();
+    if (fwd && !split)
+    {
+      kern = nd_hex_apply4_kernel<P_, Q_, KIND, ASM, false, NW, MINB, false, true>;
+      variant = 2;
+    }
+  }
+  static bool configured[3] = {false, false, false};
+  if (!configured[variant])
   {
     B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    configured[split] = true;
+    configured[variant] = true;
   }
   ND4Params<P_, Q_> prm;
   const int e_off = rg.e_off, e_cnt = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;

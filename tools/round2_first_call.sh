@@ -9,6 +9,9 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_n1_refe
 # prepared experiments: PDL overlap of the zero-fill, graph replay on an internal stream, fused complex matvec, tets
 B2P_PDL=1 timeout 300 python -m pytest tests/test_apply_gpu.py tests/test_solvers_gpu.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_pdl.log
 B2P_PDL=1 python bench.py --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/bench_n1_pdl.json 2> gpurun_out/bench_n1_pdl.err
+B2P_ND_FWDCHAIN=1 timeout 300 python -m pytest tests/test_apply_gpu.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_fwdchain.log
+B2P_ND_FWDCHAIN=1 python bench.py --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/bench_n1_fwdchain.json 2> gpurun_out/bench_n1_fwdchain.err
+B2P_ND_FWDCHAIN=1 B2P_PDL=1 python bench.py --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/bench_n1_fwdchain_pdl.json 2>> gpurun_out/bench_n1_fwdchain.err
 timeout 300 python tools/zfused_bench.py > gpurun_out/zfused_p3.json 2> gpurun_out/zfused.err
 timeout 300 python tools/zfused_bench.py --order 1 --n 60 >> gpurun_out/zfused_p3.json 2>> gpurun_out/zfused.err
 timeout 300 python tools/tet_bench.py --order 3 --n 14 > gpurun_out/tet_p3.json 2> gpurun_out/tet.err
