@@ -2,6 +2,7 @@
 // QFunction headers where they lie under /root/reference (never copied into this repo):
 //   palace/fem/qfunctions/33/{geom,hdiv,hcurl,hdivmass,hdiv_build,hcurl_build,hdivmass_build}_33_qf.h
 //   palace/fem/qfunctions/apply/apply_33_qf.h
+//   palace/fem/qfunctions/32/{geom,hcurl}_32_qf.h   (boundary integrators)
 // behind the minimal libCEED macro shim below. Used only to pin oracle.cpp's restatement of the
 // pointwise arithmetic (tests/test_oracle_ref.py). The libCEED operator/basis/restriction layer and
 // MFEM are un-vendored, so this is the only part of the reference path that compiles here.
@@ -19,6 +20,9 @@ typedef int CeedInt;
 #include "fem/qfunctions/33/hdiv_build_33_qf.h"
 #include "fem/qfunctions/33/hdivmass_build_33_qf.h"
 #include "fem/qfunctions/apply/apply_33_qf.h"
+// boundary (2-D elements embedded in 3-D) geometry factors and the H(curl) mass QFunction
+#include "fem/qfunctions/32/geom_32_qf.h"
+#include "fem/qfunctions/32/hcurl_32_qf.h"
 
 extern "C"
 {
@@ -47,6 +51,19 @@ int ref_apply_hdivmass_33(void *ctx, int Q, const double *qdata, const double *u
   const double *in[3] = {qdata, u, curlu};
   double *out[2] = {v, curlv};
   return f_apply_hdivmass_33(ctx, Q, in, out);
+}
+// in = {attr[Q], qw[Q], J[6][Q]} (geom_32_qf.h:12): qdata[8][Q] = {attr, w |J|, (adj(J)^T / |J|)[6]}
+int ref_build_geom_factor_32(int Q, const double *attr, const double *qw, const double *J, double *qdata)
+{
+  const double *in[3] = {attr, qw, J};
+  double *out[1] = {qdata};
+  return f_build_geom_factor_32(nullptr, Q, in, out);
+}
+int ref_apply_hcurl_32(void *ctx, int Q, const double *qdata, const double *u, double *v)
+{
+  const double *in[2] = {qdata, u};
+  double *out[1] = {v};
+  return f_apply_hcurl_32(ctx, Q, in, out);
 }
 int ref_build_hcurl_33(void *ctx, int Q, const double *qdata, double *qd)
 {

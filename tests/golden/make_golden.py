@@ -63,5 +63,34 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+
+def main32():
+    """tests/golden/qf32_golden.npz: the reference's boundary (dim 2 in space_dim 3) geometry-factor and H(curl) mass
+    QFunctions (qfunctions/32/geom_32_qf.h, hcurl_32_qf.h) on seeded inputs."""
+    ref = O.ref()
+    assert ref is not None, "oracle/_ref not built (needs /root/reference)"
+    rng = np.random.default_rng(20260924)
+    Q = 64
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    J = np.ascontiguousarray(rng.random((6, Q)) - 0.5) + np.array([1.0, 0, 0, 0, 1.0, 0])[:, None]
+    n_attr = 4
+    attr = (1 + rng.integers(0, n_attr, size=Q)).astype(np.float64)
+    qw = 0.1 + rng.random(Q)
+    qd = np.empty((8, Q))
+    assert ref.ref_build_geom_factor_32(Q, p(attr), p(qw), p(J), p(qd)) == 0
+    am, mc = cf.test_suite_coefficient(n_attr, "matrix")
+    mc = mc + 0.05 * rng.random(mc.shape)
+    ctx = cf.coeff_ctx(am, mc, a=1.3)
+    u = np.ascontiguousarray(rng.random((2, Q)) - 0.5)
+    v = np.empty((2, Q))
+    assert ref.ref_apply_hcurl_32(p(ctx), Q, p(qd), p(u), p(v)) == 0
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "qf32_golden.npz")
+    np.savez_compressed(path, J=J, attr=attr, qw=qw, qdata=qd, ctx=ctx, u=u, v=v)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "32":
+        main32()
+    else:
+        main()

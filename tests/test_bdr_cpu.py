@@ -1,0 +1,90 @@
+"""CPU checks of the boundary-integrator path (quadrilateral Nedelec faces embedded in 3-D; Palace's dim = 2,
+space_dim = 3 QFunctions, /root/reference/palace/fem/qfunctions/32/{geom,hcurl}_32_qf.h): the embedding of the 3 x 2
+geometry factor and the 2-component field into the 3-D ND mass path is pinned against golden vectors produced by the
+reference's own headers (tests/golden/qf32_golden.npz, generator tests/golden/make_golden.py 32), and the assembled
+boundary mass against exact surface integrals."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from palace_b200.host import bdrspace as bs
+from palace_b200.host import coeff as cf
+from palace_b200.host import hexmesh as hm
+from palace_b200.host import hexspace as hs
+from tests import common
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qf32_golden.npz"))
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_geom32_restatement_matches_reference_golden():
+    assert _rel(bs.geom32_qdata(G["attr"], G["qw"], G["J"]), G["qdata"]) < 1e-13
+
+
+def test_padded_3d_mass_map_is_the_reference_hcurl_32():
+    """v = w|J| A^T C A u with A = adj(J)^T/|J| (3 x 2): the 3-D pointwise map on [A | 0] and (u, 0) returns (v, 0)."""
+    qd11 = bs.pad32_to_33(G["qdata"])
+    u3 = np.concatenate([G["u"], np.zeros((1, G["u"].shape[1]))], axis=0)
+    v, _ = O.apply_D(O.ND_MASS, np.ascontiguousarray(G["ctx"]), np.ascontiguousarray(qd11), np.ascontiguousarray(u3), None)
+    assert _rel(v[:2], G["v"]) < 2e-15 * 10 and np.abs(v[2]).max() == 0.0
+
+
+@pytest.mark.skipif(O.ref() is None, reason="oracle/_ref not built (no /root/reference on this box)")
+def test_against_compiled_reference_32_headers():
+    import ctypes as C
+
+    ref = O.ref()
+    rng = np.random.default_rng(3)
+    Q = 40
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    J = np.ascontiguousarray(rng.random((6, Q)) - 0.5) + np.array([0.8, 0, 0, 0, 1.2, 0])[:, None]
+    attr, qw = np.ones(Q), 0.2 + rng.random(Q)
+    qd = np.empty((8, Q))
+    assert ref.ref_build_geom_factor_32(Q, p(attr), p(qw), p(J), p(qd)) == 0
+    assert _rel(bs.geom32_qdata(attr, qw, J), qd) < 1e-13
+    # |J| is the area element and A the pseudo-inverse transposed: A^T Jm = I
+    for i in range(Q):
+        Jm = J[:, i].reshape(3, 2, order="F")
+        A = qd[2:, i].reshape(3, 2, order="F")
+        assert np.abs(A.T @ Jm - np.eye(2)).max() < 1e-12
+        assert abs(qd[1, i] / qw[i] - np.linalg.norm(np.cross(Jm[:, 0], Jm[:, 1]))) < 1e-12
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_boundary_mass_energy_of_a_constant_field(p):
+    """x = G phi with phi the nodal interpolant of a . x  (so E = a exactly) on a box mesh with scrambled element frames:
+    x^T M_bdr x = sum over boundary faces of area * |a - (a . n) n|^2."""
+    size = (1.0, 0.7, 0.9)
+    mesh = hm.box_mesh((3, 2, 2), size, warp_amp=0.0, scramble_seed=3, n_attr=1)
+    topo = hs.build_topology(mesh)
+    nd, h1 = hs.build_nd_space(mesh, topo, p), hs.build_h1_space(mesh, topo, p)
+    a = np.array([0.7, -1.1, 0.4])
+    nodes = hs.gauss_lobatto(p + 1)
+    xh = mesh.node_coords(p, nodes)                             # [ne][3][(p+1)^3] lexicographic
+    phi = np.zeros(h1.ndofs)
+    phi[h1.lex_gid] = np.einsum("c,ecn->en", a, xh)
+    Gm = common.oracle_interp(h1, nd, hs.discrete_gradient_matrix(p))
+    x = Gm @ phi
+    faces = bs.boundary_faces(topo)
+    assert faces.shape[0] == 2 * (3 * 2 + 3 * 2 + 2 * 2)
+    sp = bs.build_nd_bdr_space(nd, faces)
+    interp, qw2 = bs.nd_quad_tables(p)
+    q1d = p + 1
+    xe = mesh.node_coords(1, hs.gauss_lobatto(2))
+    qd = bs.pad32_to_33(bs.bdr_qdata(xe, faces, 1, q1d))
+    assert np.isclose(qd[:, 1, :].sum(), 2 * (size[0] * size[1] + size[0] * size[2] + size[1] * size[2]), rtol=1e-13)
+    y = O.apply_add(O.ND_MASS, interp, None, sp.idx, sp.orient, qd, cf.coeff_ctx(a=1.0), x, np.zeros(nd.ndofs))
+    want = 0.0
+    for n_ax, area in ((0, size[1] * size[2]), (1, size[0] * size[2]), (2, size[0] * size[1])):
+        want += 2 * area * (a @ a - a[n_ax] ** 2)
+    assert abs(x @ y - want) < 1e-12 * want
+    # a boundary mass with a material coefficient is symmetric positive semi-definite and touches boundary dofs only
+    z = np.random.default_rng(1).random(nd.ndofs)
+    yz = O.apply_add(O.ND_MASS, interp, None, sp.idx, sp.orient, qd, cf.coeff_ctx(a=2.0), z, np.zeros(nd.ndofs))
+    interior = np.setdiff1d(np.arange(nd.ndofs), nd.ess_dofs)
+    assert np.abs(yz[interior]).max() == 0.0 and z @ yz > 0
