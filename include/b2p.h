@@ -272,6 +272,7 @@ int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2
                      const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_halo *halo, b2p_operator **out);
 /* Elements [0, ne_interior) of every local operator touch no ghost dof: they are applied while the forward
  * shared-dof exchange is still in flight (element order chosen by the caller; 0 disables the overlap). */
+int b2p_operator_par_set_coefficients(b2p_operator *A, int n_terms, const double *coefs); /* same for a real sum operator */
 int b2p_operator_par_set_interior(b2p_operator *A, int ne_interior);
 /* Interpolator on true-dof vectors (ParOperator(..., use_R) semantics); halos/true sizes of the input
  * and output spaces, NULL / L-size for a single partition. */
@@ -328,6 +329,9 @@ int b2p_coperator_add_mult(b2p_coperator *A, const double *xr, const double *xi,
 int b2p_coperator_assemble_diagonal(b2p_coperator *A, double *dr, double *di);
 /* Number of Mult / MultHermitianTranspose calls served by the fused complex element kernel (one pass over the geometry
  * for all terms and both vector parts) instead of 2-4 real applies per term; -1 if A is not a sum operator. */
+/* New coefficients of the terms (next frequency of a driven sweep, spaceoperator.cpp:945-1153) without rebuilding the
+ * operator: the smoothers / solvers that hold A see the new matrix at their next SetOperator. */
+int b2p_coperator_set_coefficients(b2p_coperator *A, int n_terms, const double *coef_re, const double *coef_im);
 long b2p_coperator_fused_applies(b2p_coperator *A);
 void b2p_coperator_destroy(b2p_coperator *A);
 /* A real preconditioner (any b2p_solver, e.g. the multigrid) applied to the real and imaginary parts: the

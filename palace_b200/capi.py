@@ -467,6 +467,10 @@ class Operator:
         o._keep = list(ops)
         return o
 
+    def set_coefficients(self, coefs):
+        cf = _np(coefs, np.float64)
+        _chk(lib().b2p_operator_par_set_coefficients(self.h, int(cf.size), _ptr(cf)), self.ctx.h)
+
     def set_interior(self, ne_interior):
         _chk(lib().b2p_operator_par_set_interior(self.h, int(ne_interior)), self.ctx.h)
 
@@ -633,6 +637,11 @@ class ComplexOperator:
 
     def mult(self, xr, xi, yr, yi):
         _chk(lib().b2p_coperator_mult(self.h, _vp(xr), _vp(xi), _vp(yr), _vp(yi)), self.ctx.h)
+
+    def set_coefficients(self, coefs):
+        cr = _np([complex(c).real for c in coefs], np.float64)
+        ci = _np([complex(c).imag for c in coefs], np.float64)
+        _chk(lib().b2p_coperator_set_coefficients(self.h, int(cr.size), _ptr(cr), _ptr(ci)), self.ctx.h)
 
     def fused_applies(self):
         f = lib().b2p_coperator_fused_applies

@@ -119,6 +119,13 @@ int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2
   *out = h;
   return B2P_SUCCESS;
 }
+int b2p_operator_par_set_coefficients(b2p_operator *A, int n_terms, const double *coefs)
+{
+  auto *pa = A ? dynamic_cast<ParOperator *>(A->op.get()) : nullptr;
+  if (!pa || !coefs || n_terms != (int)pa->NumTerms()) return B2P_ERR_ARG;
+  pa->SetCoefficients(coefs);
+  return B2P_SUCCESS;
+}
 int b2p_operator_par_set_interior(b2p_operator *A, int ne_interior)
 {
   auto *pa = A ? dynamic_cast<ParOperator *>(A->op.get()) : nullptr;

@@ -252,12 +252,24 @@ public:
       if (a != b) return;  // different restriction or essential set
     }
     const int ne = o0->ne;
-    std::vector<double> z((size_t)36 * ne, 0.0), e18((size_t)18 * ne);
+    fused_e18.assign(terms.size(), std::vector<double>((size_t)18 * ne));
+    for (size_t i = 0; i < terms.size(); i++)
+      if (cudaMemcpy(fused_e18[i].data(), terms[i].op->ecoef, fused_e18[i].size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return;
+    fused = fill_fused();
+  }
+
+  // zcoef / zcoef_h from the cached per-term material tensors and the current scalar coefficients
+  bool fill_fused()
+  {
+    const int ne = terms[0].op->ne;
+    std::vector<double> z((size_t)36 * ne, 0.0);
     bool mass = false, curl = false;
     fused_imag = false;
-    for (auto &t : terms)
+    for (size_t ti = 0; ti < terms.size(); ti++)
     {
-      if (cudaMemcpy(e18.data(), t.op->ecoef, e18.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+      const Term &t = terms[ti];
+      const std::vector<double> &e18 = fused_e18[ti];
       const bool m = (t.op->kind == B2P_ND_MASS || t.op->kind == B2P_CURLCURL_MASS);
       const bool k = (t.op->kind == B2P_CURLCURL || t.op->kind == B2P_CURLCURL_MASS);
       mass = mass || m;
@@ -279,15 +291,31 @@ public:
         }
     }
     fused_kind = mass && curl ? B2P_CURLCURL_MASS : (mass ? B2P_ND_MASS : B2P_CURLCURL);
-    if (upload(ctx, z.data(), z.size(), &zcoef)) return;
+    cudaFree(zcoef);
+    cudaFree(zcoef_h);
+    zcoef = zcoef_h = nullptr;
+    if (upload(ctx, z.data(), z.size(), &zcoef)) return false;
     for (int e = 0; e < ne; e++)  // Hermitian transpose: conjugated coefficients (the A_i are real symmetric)
       for (int i = 0; i < 9; i++)
       {
         z[(size_t)36 * e + 9 + i] = -z[(size_t)36 * e + 9 + i];
         z[(size_t)36 * e + 27 + i] = -z[(size_t)36 * e + 27 + i];
       }
-    if (upload(ctx, z.data(), z.size(), &zcoef_h)) return;
-    fused = true;
+    if (upload(ctx, z.data(), z.size(), &zcoef_h)) return false;
+    return true;
+  }
+
+  // New complex coefficients of the terms (next frequency of a driven sweep): nothing is rebuilt; the fused kernel's
+  // per-element complex tensors are refilled from the cached material tensors (36 doubles per element uploaded).
+  size_t NumTerms() const { return terms.size(); }
+  void SetCoefficients(const double *cr, const double *ci)
+  {
+    for (size_t t = 0; t < terms.size(); t++)
+    {
+      terms[t].cr = cr[t];
+      terms[t].ci = ci[t];
+    }
+    if (fused) fused = fill_fused();
   }
 
   // operator.cpp:98-134 with A = sum_i c_i A_i: y_r = sum (c^r A x_r - c^i A x_i), y_i = sum (c^i A x_r + c^r A x_i);
@@ -359,6 +387,7 @@ private:
   bool fused = false, fused_imag = false;
   int fused_kind = 0;
   double *zcoef = nullptr, *zcoef_h = nullptr;
+  std::vector<std::vector<double>> fused_e18;  // host copies of the terms' per-element material tensors
 
 public:
   mutable long n_fused_applies = 0;
@@ -795,6 +824,13 @@ int b2p_coperator_assemble_diagonal(b2p_coperator *A, double *dr, double *di)
 {
   if (!A) return B2P_ERR_ARG;
   B2P_CTRY(A->op->ctx, A->op->AssembleDiagonal(CPtr{dr, di}));
+  return B2P_SUCCESS;
+}
+int b2p_coperator_set_coefficients(b2p_coperator *A, int n_terms, const double *coef_re, const double *coef_im)
+{
+  auto *p = A ? dynamic_cast<ComplexParOperator *>(A->op.get()) : nullptr;
+  if (!p || !coef_re || !coef_im || n_terms != (int)p->NumTerms()) return B2P_ERR_ARG;
+  p->SetCoefficients(coef_re, coef_im);
   return B2P_SUCCESS;
 }
 long b2p_coperator_fused_applies(b2p_coperator *A)

@@ -121,6 +121,10 @@ public:
   };
   ParOperator(b2p_ctx *c, int64_t tsize, int64_t lsize, const std::vector<Term> &terms, const int32_t *ess_tdofs,
               int64_t n_ess, int diag_policy, Halo *halo);
+  // New scalar coefficients of the terms (a0 K + a1 C + a2 M at the next frequency of a sweep, spaceoperator.cpp:945-1153)
+  // without rebuilding anything; cached CUDA graphs bake the coefficients in, so they are dropped.
+  void SetCoefficients(const double *coefs);
+  size_t NumTerms() const { return terms.size(); }
   ~ParOperator() override;
   void Mult(const double *x, double *y) const override;
   void AddMult(const double *x, double *y, double a = 1.0) const override;

@@ -51,6 +51,13 @@ ParOperator::~ParOperator()
   for (auto &g : graphs_) cudaGraphExecDestroy(g.second);
 }
 
+void ParOperator::SetCoefficients(const double *coefs)
+{
+  for (size_t t = 0; t < terms.size(); t++) terms[t].coef = coefs[t];
+  for (auto &g : graphs_) cudaGraphExecDestroy(g.second);
+  graphs_.clear();
+}
+
 void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
 {
   // Owned dofs are read from x and accumulated into y directly; ghosts live in the halo's buffers:

@@ -92,3 +92,35 @@ def test_fused_path_is_skipped_when_terms_differ(b2p_ctx, monkeypatch):
     ref = (1.0 + 0.5j) * (Ao @ x)
     ref[nd.ess_dofs] = x[nd.ess_dofs]
     assert _rel(yr.cpu().numpy() + 1j * yi.cpu().numpy(), ref) < RTOL
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_frequency_sweep_updates_coefficients_in_place(b2p_ctx, monkeypatch, fused):
+    """A(w) = K - w^2 (1 - i tan d) M + i w C: new coefficients per frequency without rebuilding the operator
+    (b2p_coperator_set_coefficients), term-by-term and fused."""
+    from palace_b200 import capi
+
+    prob = common.make_problem(n=(3, 2, 2), p=3, n_attr=2)
+    geom = common.gpu_geom(b2p_ctx, prob)
+    nd = prob.nd
+    specs = [(O.CURLCURL, common.coefficient(O.CURLCURL, 2, "const")), (O.ND_MASS, common.coefficient(O.ND_MASS, 2, "matrix")),
+             (O.ND_MASS, common.coefficient(O.ND_MASS, 2, "scalar", a_mass=0.3))]
+    ops = [common.gpu_op(b2p_ctx, geom, prob, k, b) for k, b in specs]
+    mats = [common.oracle_matrix(prob, k, b, eliminate=False) for k, b in specs]
+    coefs_of = lambda w: [1.0 + 0.0j, -w * w * (1 - 0.02j), 1j * w]
+    monkeypatch.setenv("B2P_COMPLEX_FUSED", fused)
+    A = capi.ComplexOperator.par(b2p_ctx, nd.ndofs, nd.ndofs, ops, coefs_of(1.0), nd.ess_dofs, 1)
+    rng = np.random.default_rng(3)
+    x = rng.random(nd.ndofs) + 1j * rng.random(nd.ndofs)
+    xr, xi = _dev(x.real), _dev(x.imag)
+    for w in (1.0, 2.5, 0.4):
+        A.set_coefficients(coefs_of(w))
+        yr, yi = torch.empty_like(xr), torch.empty_like(xr)
+        A.mult(xr, xi, yr, yi)
+        Ao = sum(c * M for c, M in zip(coefs_of(w), mats)).tolil()
+        ess = nd.ess_dofs
+        Ao[ess, :] = 0
+        Ao[:, ess] = 0
+        Ao[ess, ess] = 1.0
+        assert _rel(yr.cpu().numpy() + 1j * yi.cpu().numpy(), Ao.tocsr() @ x) < RTOL
+    assert A.fused_applies() == (3 if fused == "1" else 0)
