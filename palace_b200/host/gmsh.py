@@ -1,0 +1,96 @@
+"""Caller-side stand-in: reader for the reference's example meshes in Gmsh 2.2 binary format with second-order
+hexahedra (HEX27 volume elements + QUAD9 boundary elements, e.g. /root/reference/examples/cylinder/mesh/cylinder_hex.msh),
+converted to the lexicographic order-2 node layout the geometry entry points take (b2p_geom_create_hex with mesh_order 2:
+27 nodes per element, x fastest, nodes at 0, 1/2, 1 = the three Gauss-Lobatto points). MFEM does this conversion inside
+Palace (fem/mesh.cpp); here it only serves the end-to-end checks against the reference's stored regression outputs."""
+from __future__ import annotations
+
+import dataclasses
+import struct
+
+import numpy as np
+
+# Gmsh corner numbering of a hexahedron -> (x, y, z) in {0, 1}^3
+_GMSH_CORNERS = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+_GMSH_EDGES = [(0, 1), (0, 3), (0, 4), (1, 2), (1, 5), (2, 3), (2, 6), (3, 7), (4, 5), (4, 7), (5, 6), (6, 7)]
+_GMSH_FACES = [(0, 3, 2, 1), (0, 1, 5, 4), (0, 4, 7, 3), (1, 2, 6, 5), (2, 3, 7, 6), (4, 5, 6, 7)]
+_NODES_PER_TYPE = {1: 2, 2: 3, 3: 4, 4: 4, 5: 8, 8: 3, 9: 6, 10: 9, 11: 10, 12: 27, 15: 1}
+
+
+def hex27_reference_positions():
+    """Reference coordinates (multiples of 1/2) of Gmsh's 27 hexahedron nodes, in Gmsh order."""
+    c = np.array(_GMSH_CORNERS, dtype=np.float64)
+    pos = [c[i] for i in range(8)]
+    pos += [0.5 * (c[a] + c[b]) for a, b in _GMSH_EDGES]
+    pos += [0.25 * (c[a] + c[b] + c[d] + c[e]) for a, b, d, e in _GMSH_FACES]
+    pos.append(np.array([0.5, 0.5, 0.5]))
+    return np.array(pos)
+
+
+@dataclasses.dataclass
+class Hex27Mesh:
+    verts: np.ndarray     # [nv][3] corner vertices actually used (renumbered)
+    elems: np.ndarray     # [ne][8] corner vertex ids, corner = x + 2 y + 4 z
+    attr: np.ndarray      # [ne] volume attribute (Gmsh physical tag)
+    xe2: np.ndarray       # [ne][3][27] order-2 nodes, lexicographic (x fastest), component-major
+    bdr_attr: np.ndarray  # [nb] attribute of the QUAD9 boundary elements
+    bdr_verts: np.ndarray  # [nb][4] corner vertex ids of the boundary elements
+
+    @property
+    def ne(self):
+        return int(self.elems.shape[0])
+
+
+def read_gmsh22_binary(path: str):
+    """(nodes {id: xyz}, elements {type: (tags[n][ntags], conn[n][nn])}) of a Gmsh 2.2 binary file."""
+    f = open(path, "rb").read()
+    assert f[f.index(b"$MeshFormat\n") + 12:].split(b"\n", 1)[0].split()[:3] == [b"2.2", b"1", b"8"], "Gmsh 2.2 binary, 8-byte reals"
+    i = f.index(b"$Nodes\n") + 7
+    j = f.index(b"\n", i)
+    n = int(f[i:j])
+    rec = np.dtype([("id", "<i4"), ("x", "<f8", 3)])
+    nodes = np.frombuffer(f, dtype=rec, count=n, offset=j + 1)
+    off = j + 1 + n * rec.itemsize
+    k = f.index(b"$Elements\n", off) + 10
+    j = f.index(b"\n", k)
+    ne = int(f[k:j])
+    off = j + 1
+    out, cnt = {}, 0
+    while cnt < ne:
+        etype, nfollow, ntags = struct.unpack_from("<3i", f, off)
+        off += 12
+        nn = _NODES_PER_TYPE[etype]
+        w = 1 + ntags + nn
+        blk = np.frombuffer(f, dtype="<i4", count=w * nfollow, offset=off).reshape(nfollow, w)
+        off += 4 * w * nfollow
+        cnt += nfollow
+        tags, conn = out.setdefault(etype, ([], []))
+        tags.append(blk[:, 1:1 + ntags])
+        conn.append(blk[:, 1 + ntags:])
+    return {int(r["id"]): r["x"].copy() for r in nodes}, {t: (np.concatenate(a), np.concatenate(b)) for t, (a, b) in out.items()}
+
+
+def load_hex27(path: str) -> Hex27Mesh:
+    nodes, elems = read_gmsh22_binary(path)
+    tags, conn = elems[12]
+    ref = hex27_reference_positions()
+    lex = (np.rint(2 * ref[:, 0]) + 3 * np.rint(2 * ref[:, 1]) + 9 * np.rint(2 * ref[:, 2])).astype(int)  # Gmsh -> lexicographic
+    ne = conn.shape[0]
+    xe2 = np.zeros((ne, 3, 27))
+    for e in range(ne):
+        X = np.array([nodes[int(v)] for v in conn[e]])                      # Gmsh order
+        # sanity of the ordering table: every mid node sits near the mean of the corners it belongs to
+        c8 = X[:8]
+        w = np.array([[(1 - r[0] if cx == 0 else r[0]) * (1 - r[1] if cy == 0 else r[1]) * (1 - r[2] if cz == 0 else r[2])
+                       for (cx, cy, cz) in _GMSH_CORNERS] for r in ref])
+        size = np.linalg.norm(c8.max(axis=0) - c8.min(axis=0))
+        assert np.linalg.norm(w @ c8 - X, axis=1).max() < 0.2 * size, "HEX27 node ordering does not match the Gmsh convention"
+        xe2[e][:, lex] = X.T
+    corner_ids = np.unique(conn[:, :8])
+    renum = {int(v): i for i, v in enumerate(corner_ids)}
+    perm = [0, 1, 3, 2, 4, 5, 7, 6]  # ours (x + 2y + 4z) <- Gmsh corner number
+    el = np.array([[renum[int(conn[e, perm[c]])] for c in range(8)] for e in range(ne)], dtype=np.int64)
+    verts = np.array([nodes[int(v)] for v in corner_ids])
+    bt, bc = elems.get(10, (np.zeros((0, 2), dtype=int), np.zeros((0, 9), dtype=int)))
+    bverts = np.array([[renum[int(v)] for v in row[:4]] for row in bc], dtype=np.int64).reshape(-1, 4)
+    return Hex27Mesh(verts, el, tags[:, 0].astype(np.int32), xe2, bt[:, 0].astype(np.int32) if len(bt) else np.zeros(0, np.int32), bverts)
