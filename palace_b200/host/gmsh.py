@@ -94,3 +94,57 @@ def load_hex27(path: str) -> Hex27Mesh:
     bt, bc = elems.get(10, (np.zeros((0, 2), dtype=int), np.zeros((0, 9), dtype=int)))
     bverts = np.array([[renum[int(v)] for v in row[:4]] for row in bc], dtype=np.int64).reshape(-1, 4)
     return Hex27Mesh(verts, el, tags[:, 0].astype(np.int32), xe2, bt[:, 0].astype(np.int32) if len(bt) else np.zeros(0, np.int32), bverts)
+
+
+# ------------------------------------------------------------------------------------------------
+# High-order tetrahedra (TET10 / TET20 volume elements with TRI6 / TRI10 boundary elements)
+# ------------------------------------------------------------------------------------------------
+_NODES_PER_TYPE.update({21: 10, 29: 20, 26: 4})
+_TET_TYPES = {4: 1, 11: 2, 29: 3}
+_TRI_TYPES = {2: 1, 9: 2, 21: 3}
+
+
+@dataclasses.dataclass
+class HighOrderTetMesh:
+    order: int
+    verts: np.ndarray      # [nv][3] corner vertices (renumbered)
+    elems: np.ndarray      # [ne][4] corner vertex ids, positively oriented as stored
+    attr: np.ndarray       # [ne]
+    xe: np.ndarray         # [ne][3][Nn] element nodes on the equispaced lattice (a fastest, a + b + c <= order), component-major
+    bdr_attr: np.ndarray   # [nb]
+    bdr_verts: np.ndarray  # [nb][3] corner vertex ids of the boundary triangles
+
+    @property
+    def ne(self):
+        return int(self.elems.shape[0])
+
+
+def load_tets(path: str) -> HighOrderTetMesh:
+    """Order-k tetrahedral mesh; the high-order nodes of every element are matched to the lattice positions geometrically
+    (nearest node to the affine image of the lattice point), so no table of Gmsh's node ordering is involved."""
+    nodes, elems = read_gmsh22_binary(path)
+    (etype,) = [t for t in elems if t in _TET_TYPES]
+    order = _TET_TYPES[etype]
+    tags, conn = elems[etype]
+    lat = np.array([(a, b, c) for c in range(order + 1) for b in range(order + 1 - c) for a in range(order + 1 - b - c)], dtype=np.float64) / order
+    ids = np.array(sorted(nodes))
+    pos = np.zeros((ids.max() + 1, 3))
+    pos[ids] = np.array([nodes[int(i)] for i in ids])
+    X = pos[conn]                                                  # [ne][Nn][3] in Gmsh order
+    c0 = X[:, 0]
+    E = np.stack([X[:, 1] - c0, X[:, 2] - c0, X[:, 3] - c0], axis=1)   # [ne][3 edges][3]
+    img = c0[:, None, :] + np.einsum("nd,edc->enc", lat, E)        # affine images of the lattice points
+    d = np.linalg.norm(img[:, :, None, :] - X[:, None, :, :], axis=3)  # [ne][lattice][gmsh node]
+    pick = d.argmin(axis=2)
+    h = np.linalg.norm(E, axis=2).min(axis=1)
+    assert (np.sort(pick, axis=1) == np.arange(lat.shape[0])[None]).all(), "lattice matching is not a permutation"
+    # curved elements: a node may sit off its affine image, but never by as much as the lattice spacing
+    assert (np.take_along_axis(d, pick[:, :, None], axis=2)[:, :, 0].max(axis=1) < 0.45 * np.linalg.norm(E, axis=2).max(axis=1) / order).all()
+    xe = np.transpose(np.take_along_axis(X, pick[:, :, None], axis=1), (0, 2, 1))
+    corner_ids = np.unique(conn[:, :4])
+    renum = np.full(ids.max() + 1, -1, dtype=np.int64)
+    renum[corner_ids] = np.arange(corner_ids.size)
+    (btype,) = [t for t in elems if t in _TRI_TYPES] or [None]
+    bt, bc = elems[btype] if btype is not None else (np.zeros((0, 2), dtype=int), np.zeros((0, 3), dtype=int))
+    return HighOrderTetMesh(order, pos[corner_ids], renum[conn[:, :4]], tags[:, 0].astype(np.int32), np.ascontiguousarray(xe),
+                            bt[:, 0].astype(np.int32), renum[bc[:, :3]])

@@ -1,0 +1,71 @@
+"""END-TO-END pin of the TETRAHEDRAL geometry / space path against numbers produced by the reference itself: the
+capacitance matrix of the two-spheres electrostatics example (/root/reference/examples/spheres/spheres.json: 14,362
+curved cubic tetrahedra TET20, H1 order 3, 66,328 dofs) that Palace's regression suite stores in
+test/data/regression/ref/spheres/terminal-C.csv. The oracle-side path -- Gmsh reader (palace_b200/host/gmsh.py), order-3
+tet geometry q-data and the H1 tet space of palace_b200/host/tetspace.py, the reference QFunction arithmetic of the oracle,
+a sparse direct solve -- reproduces all four entries to better than 2e-7 relative (observed 4e-8 ... 7e-8: the reference
+solves to 1e-8 and integrates with another degree-6 rule). The mesh is read from the reference tree (3.4 MB, not copied
+into this repository), so the test runs only where /root/reference exists."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle import pyoracle as O
+from palace_b200.host import coeff as cf
+from palace_b200.host import gmsh
+from palace_b200.host import tetspace as ts
+
+MESH = "/root/reference/examples/spheres/mesh/spheres.msh"
+# test/data/regression/ref/spheres/terminal-C.csv (farads)
+C_REF = np.array([[+1.237445610357e-12, -4.770975738888e-13], [-4.770975738888e-13, +2.478413459856e-12]])
+
+
+@pytest.mark.skipif(not os.path.exists(MESH), reason="needs the reference's example mesh")
+def test_capacitance_matrix_of_the_spheres_example():
+    m = gmsh.load_tets(MESH)
+    assert m.order == 3 and m.ne == 14362
+    p = 3                                                            # spheres.json "Order": 3
+    mesh = ts.TetMesh(m.verts, m.elems, m.attr)
+    nd1 = ts.build_nd_tet_space(mesh, 1)                             # edge / face numbering
+    h1 = ts.build_h1_tet_space(mesh, nd1, p)
+    assert h1.ndofs == 66328                                         # = the node count of the order-3 mesh file
+    qpts, qw = ts.tet_quadrature(2 * p)
+    qd = ts.geom_qdata(m.xe, np.ones(m.ne, dtype=np.int32), m.order, qpts, qw)
+    assert (qd[:, 1, :] > 0).all()
+    _, grad = ts.h1_tet_element(p).tabulate(qpts)
+    Ae = O.element_matrices(O.H1_DIFFUSION, None, np.ascontiguousarray(grad), None, qd, cf.coeff_ctx(a=1.0), h1.P)
+    I = np.repeat(h1.idx, h1.P, axis=1).ravel()
+    J = np.tile(h1.idx, (1, h1.P)).ravel()
+    K = sp.csr_matrix((Ae.ravel(), (I, J)), shape=(h1.ndofs, h1.ndofs))
+    nv, n_e, n_f = m.verts.shape[0], p - 1, (p - 1) * (p - 2) // 2
+    edge_base, face_base = nv, nv + n_e * nd1.n_edges
+
+    def boundary_dofs(attr):
+        s = set()
+        for tri in m.bdr_verts[m.bdr_attr == attr]:
+            g = sorted(int(x) for x in tri)
+            s.update(g)
+            for a, b in ((0, 1), (0, 2), (1, 2)):
+                eb = edge_base + n_e * nd1.edges[(g[a], g[b])]
+                s.update(range(eb, eb + n_e))
+            fb = face_base + n_f * nd1.faces[tuple(g)]
+            s.update(range(fb, fb + n_f))
+        return np.array(sorted(s))
+
+    D = {a: boundary_dofs(a) for a in (2, 3, 4)}                     # ground (far field), sphere A, sphere B
+    free = np.setdiff1d(np.arange(h1.ndofs), np.concatenate(list(D.values())))
+    lu = spla.splu(K[free][:, free].tocsc())
+    V = []
+    for a in (3, 4):                                                  # unit potential on one terminal, zero on the rest
+        x = np.zeros(h1.ndofs)
+        x[D[a]] = 1.0
+        x[free] = lu.solve(-(K[free] @ x))
+        V.append(x)
+    mu0, c0, L0 = 1.25663706127e-6, 299792458.0, 1.0e-2              # palace/utils/constants.hpp:22-30, "L0": 1e-2
+    C = np.array([[V[i] @ (K @ V[j]) for j in range(2)] for i in range(2)]) * L0 / (mu0 * c0 * c0)
+    rel = np.abs(C - C_REF) / np.abs(C_REF)
+    print("capacitance matrix (F):", C, "rel. error vs the reference's terminal-C.csv:", rel)
+    assert rel.max() < 2e-7
