@@ -3,7 +3,7 @@ capacitance matrix of the two-spheres electrostatics example (/root/reference/ex
 curved cubic tetrahedra TET20, H1 order 3, 66,328 dofs) that Palace's regression suite stores in
 test/data/regression/ref/spheres/terminal-C.csv. The oracle-side path -- Gmsh reader (palace_b200/host/gmsh.py), order-3
 tet geometry q-data and the H1 tet space of palace_b200/host/tetspace.py, the reference QFunction arithmetic of the oracle,
-a sparse direct solve -- reproduces all four entries to better than 2e-7 relative (observed 4e-8 ... 7e-8: the reference
+a Jacobi-preconditioned CG solve to 1e-13 -- reproduces all four entries to better than 2e-7 relative (observed 4e-8 ... 7e-8: the reference
 solves to 1e-8 and integrates with another degree-6 rule). The mesh is read from the reference tree (3.4 MB, not copied
 into this repository), so the test runs only where /root/reference exists."""
 import os
@@ -57,12 +57,16 @@ def test_capacitance_matrix_of_the_spheres_example():
 
     D = {a: boundary_dofs(a) for a in (2, 3, 4)}                     # ground (far field), sphere A, sphere B
     free = np.setdiff1d(np.arange(h1.ndofs), np.concatenate(list(D.values())))
-    lu = spla.splu(K[free][:, free].tocsc())
+    Kff = K[free][:, free].tocsr()
+    dinv = 1.0 / Kff.diagonal()
+    prec = spla.LinearOperator(Kff.shape, matvec=lambda r: dinv * r, dtype=np.float64)
     V = []
     for a in (3, 4):                                                  # unit potential on one terminal, zero on the rest
         x = np.zeros(h1.ndofs)
         x[D[a]] = 1.0
-        x[free] = lu.solve(-(K[free] @ x))
+        sol, info = spla.cg(Kff, -(K[free] @ x), rtol=1e-13, atol=0.0, maxiter=20000, M=prec)
+        assert info == 0
+        x[free] = sol
         V.append(x)
     mu0, c0, L0 = 1.25663706127e-6, 299792458.0, 1.0e-2              # palace/utils/constants.hpp:22-30, "L0": 1e-2
     C = np.array([[V[i] @ (K @ V[j]) for j in range(2)] for i in range(2)]) * L0 / (mu0 * c0 * c0)
