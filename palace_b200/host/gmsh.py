@@ -148,3 +148,30 @@ def load_tets(path: str) -> HighOrderTetMesh:
     bt, bc = elems[btype] if btype is not None else (np.zeros((0, 2), dtype=int), np.zeros((0, 3), dtype=int))
     return HighOrderTetMesh(order, pos[corner_ids], renum[conn[:, :4]], tags[:, 0].astype(np.int32), np.ascontiguousarray(xe),
                             bt[:, 0].astype(np.int32), renum[bc[:, :3]])
+
+
+def refine_hex27(mesh: Hex27Mesh) -> Hex27Mesh:
+    """One uniform refinement (Model.Refinement.UniformLevels): every hexahedron becomes eight, the children's order-2 nodes
+    are the parent's triquadratic map evaluated at the child node positions (what refining MFEM's nodal grid function does)."""
+    t = np.array([0.0, 0.5, 1.0])
+
+    def lag(x):  # quadratic Lagrange basis on {0, 1/2, 1} at points x: [len(x)][3]
+        return np.stack([2 * (x - 0.5) * (x - 1), -4 * x * (x - 1), 2 * x * (x - 0.5)], axis=1)
+
+    ne = mesh.ne
+    X = mesh.xe2.reshape(ne, 3, 3, 3, 3)                        # [e][c][k][j][i]
+    kids, attr = [], []
+    for oz in (0, 1):
+        for oy in (0, 1):
+            for ox in (0, 1):
+                Lx, Ly, Lz = lag(0.5 * (t + ox)), lag(0.5 * (t + oy)), lag(0.5 * (t + oz))
+                kids.append(np.einsum("eckji,ai,bj,dk->ecdba", X, Lx, Ly, Lz).reshape(ne, 3, 27))
+                attr.append(mesh.attr)
+    xe2 = np.concatenate(kids, axis=0)
+    # corner vertices: unique points among the children's 8 corners
+    cidx = [0, 2, 6, 8, 18, 20, 24, 26]
+    corners = np.transpose(xe2[:, :, cidx], (0, 2, 1)).reshape(-1, 3)
+    scale = np.abs(corners).max()
+    key = np.rint(corners / scale * 2 ** 40).astype(np.int64)
+    _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    return Hex27Mesh(corners[first], inv.reshape(-1, 8), np.concatenate(attr), np.ascontiguousarray(xe2), mesh.bdr_attr[:0], np.zeros((0, 4), dtype=np.int64))
