@@ -301,6 +301,9 @@ int b2p_solver_gmg_set_operators(b2p_solver *s, b2p_operator *const *A, b2p_oper
 /* type 0 CG, 1 GMRES, 2 FGMRES (iterative.cpp) */
 int b2p_solver_krylov(b2p_ctx *ctx, int type, b2p_solver **out);
 int b2p_solver_krylov_config(b2p_solver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side);
+/* CG only: keep alpha / beta in device memory and read the residual back every `check_every` iterations (1 = the
+ * reference's iteration with two host-visible dot products per step, iterative.cpp:361-486). */
+int b2p_solver_krylov_set_check_interval(b2p_solver *s, int check_every);
 int b2p_solver_set_preconditioner(b2p_solver *s, b2p_solver *pc);
 int b2p_solver_set_operator(b2p_solver *s, b2p_operator *A);
 int b2p_solver_set_initial_guess(b2p_solver *s, int flag);

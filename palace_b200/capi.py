@@ -569,6 +569,9 @@ class Solver:
                                             int(pc_side)), ctx.h)
         return s
 
+    def set_check_interval(self, check_every):
+        _chk(lib().b2p_solver_krylov_set_check_interval(self.h, int(check_every)), self.ctx.h)
+
     def set_preconditioner(self, pc):
         self._keep.append(pc)
         _chk(lib().b2p_solver_set_preconditioner(self.h, pc.h if pc else None), self.ctx.h)

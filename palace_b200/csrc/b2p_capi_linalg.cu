@@ -258,6 +258,13 @@ int b2p_solver_krylov_config(b2p_solver *s, double rel_tol, double abs_tol, int 
   k->pc_side = (PcSide)pc_side;
   return B2P_SUCCESS;
 }
+int b2p_solver_krylov_set_check_interval(b2p_solver *s, int check_every)
+{
+  auto *k = s ? dynamic_cast<IterativeSolver *>(s->s.get()) : nullptr;
+  if (!k || check_every < 1) return B2P_ERR_ARG;
+  k->check_every = check_every;
+  return B2P_SUCCESS;
+}
 int b2p_solver_set_preconditioner(b2p_solver *s, b2p_solver *pc)
 {
   auto *k = s ? dynamic_cast<IterativeSolver *>(s->s.get()) : nullptr;

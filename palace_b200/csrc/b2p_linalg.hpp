@@ -39,6 +39,9 @@ void b2p_allreduce_sum(b2p_ctx *c, double *dbuf, int n);  // in place, on ctx->s
 namespace vec
 {
 void set(b2p_ctx *c, double *y, int64_t n, double v);
+void dot_dev(b2p_ctx *c, const double *x, const double *y, int64_t n, double *d_out);  // result stays on the device
+void xpay_ratio_dev(b2p_ctx *c, const double *z, const double *d_num, const double *d_den, double *p, int64_t n);
+void cg_update_dev(b2p_ctx *c, const double *d_num, const double *d_den, const double *p, const double *q, double *x, double *r, int64_t n);
 void zero_release(b2p_ctx *c, double *y, int64_t n);  // y = 0 by a kernel that lets a PDL-launched successor start early
 void copy(b2p_ctx *c, double *y, const double *x, int64_t n);
 void scale(b2p_ctx *c, double *y, int64_t n, double a);
@@ -283,6 +286,10 @@ public:
   const Solver *B = nullptr;
   double rel_tol = 1e-6, abs_tol = 0.0;
   int max_it = 100, max_dim = -1;
+  // CG only: > 1 keeps the recurrence scalars in device memory and looks at the residual every check_every iterations
+  // only (one host synchronisation per check instead of two per iteration); may run up to check_every - 1 iterations
+  // past convergence. 1 = the reference's iteration (iterative.cpp:361-486).
+  int check_every = 1;
   Orthog gs = Orthog::MGS;
   PcSide pc_side = PcSide::RIGHT;
   int print = 0;
@@ -294,6 +301,8 @@ public:
 
 private:
   void MultCG(const double *b, double *x) const;
+  void MultCGDeviceScalars(const double *b, double *x) const;
+  mutable DVec scal;  // device scalars of the sync-free CG
   void MultGMRES(const double *b, double *x, bool flexible) const;
   mutable std::vector<std::unique_ptr<DVec>> V, Z;
   mutable DVec r, z, p;

@@ -532,7 +532,7 @@ inline void ApplyPlaneRotation(double &dx, double &dy, const double cs, const do
 void IterativeSolver::Mult(const double *b, double *x) const
 {
   if (type == KspType::CG)
-    MultCG(b, x);
+    (check_every > 1 ? MultCGDeviceScalars(b, x) : MultCG(b, x));
   else
     MultGMRES(b, x, type == KspType::FGMRES);
 }
@@ -601,6 +601,83 @@ void IterativeSolver::MultCG(const double *b, double *x) const
     converged = (res < eps);
   }
   res_history.push_back(res);
+  final_res = res;
+  final_it = it;
+}
+
+// The same preconditioned CG recurrence with alpha, beta formed on the device: per iteration no host synchronisation;
+// the residual norm sqrt(|z.r|) is read back every check_every iterations.
+void IterativeSolver::MultCGDeviceScalars(const double *b, double *x) const
+{
+  const int64_t n = height;
+  r.resize(ctx, n);
+  z.resize(ctx, n);
+  p.resize(ctx, n);
+  if (scal.n != 4) scal.resize(ctx, 4);
+  double *d_beta = scal.p, *d_beta_prev = scal.p + 1, *d_denom = scal.p + 2;
+  res_history.clear();
+  auto read = [&](const double *d) -> double
+  {
+    double h = 0.0;
+    cudaMemcpyAsync(&h, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return h;
+  };
+  if (initial_guess)
+  {
+    A->Mult(x, r.p);
+    vec::axpby(ctx, 1.0, b, -1.0, r.p, n);
+  }
+  else
+  {
+    vec::copy(ctx, r.p, b, n);
+    vec::set(ctx, x, n, 0.0);
+  }
+  if (B)
+    B->Mult(r.p, z.p);
+  else
+    vec::copy(ctx, z.p, r.p, n);
+  vec::dot_dev(ctx, z.p, r.p, n, d_beta);
+  double res = std::sqrt(std::abs(read(d_beta)));
+  if (initial_guess)
+  {
+    double beta_rhs;
+    if (B)
+    {
+      B->Mult(b, p.p);
+      beta_rhs = vec::dot(ctx, p.p, b, n);
+    }
+    else
+      beta_rhs = vec::norml2(ctx, b, n);
+    initial_res = std::sqrt(std::abs(beta_rhs));
+  }
+  else
+    initial_res = res;
+  const double eps = std::max(rel_tol * initial_res, abs_tol);
+  converged = (res < eps);
+  int it = 0;
+  for (; it < max_it && !converged; it++)
+  {
+    if (!it)
+      vec::copy(ctx, p.p, z.p, n);
+    else
+      vec::xpay_ratio_dev(ctx, z.p, d_beta, d_beta_prev, p.p, n);  // p = z + (beta / beta_prev) p
+    A->Mult(p.p, z.p);
+    vec::dot_dev(ctx, z.p, p.p, n, d_denom);
+    vec::cg_update_dev(ctx, d_beta, d_denom, p.p, z.p, x, r.p, n);  // x += alpha p, r -= alpha A p
+    std::swap(d_beta, d_beta_prev);
+    if (B)
+      B->Mult(r.p, z.p);
+    else
+      vec::copy(ctx, z.p, r.p, n);
+    vec::dot_dev(ctx, z.p, r.p, n, d_beta);
+    if ((it + 1) % check_every == 0 || it + 1 == max_it)
+    {
+      res = std::sqrt(std::abs(read(d_beta)));
+      res_history.push_back(res);
+      converged = (res < eps);
+    }
+  }
   final_res = res;
   final_it = it;
 }

@@ -286,6 +286,36 @@ void multi_dot(b2p_ctx *c, int m, const double *const *V, const double *w, int64
   }
 }
 
+// Device-resident scalar variants (sync-free Krylov iterations): the dot product stays in device memory, the vector
+// updates read their scalar coefficients from there.
+void dot_dev(b2p_ctx *c, const double *x, const double *y, int64_t n, double *d_out)
+{
+  VecList L;
+  for (int j = 0; j < MAXM; j++) L.v[j] = j == 0 ? y : nullptr;
+  B2P_LAUNCH(multi_dot_kernel<1>, red_grid(c), NT, 0, c->stream, L, x, n, 1, red_partials(c));
+  B2P_LAUNCH(final_reduce_kernel, 1, 32, 0, c->stream, red_partials(c), 1, red_grid(c), d_out);
+  if (c->nranks > 1 && c->comm) ncclAllReduce(d_out, d_out, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
+}
+// p = z + (num / den) p
+void xpay_ratio_dev(b2p_ctx *c, const double *z, const double *d_num, const double *d_den, double *p, int64_t n)
+{
+  launch_ew(c, n, [=] __device__(int64_t i)
+            {
+              const double den = *d_den, b = den != 0.0 ? *d_num / den : 0.0;
+              p[i] = z[i] + b * p[i];
+            });
+}
+// a = num / den;  x += a p;  r -= a q
+void cg_update_dev(b2p_ctx *c, const double *d_num, const double *d_den, const double *p, const double *q, double *x, double *r, int64_t n)
+{
+  launch_ew(c, n, [=] __device__(int64_t i)
+            {
+              const double den = *d_den, a = den != 0.0 ? *d_num / den : 0.0;
+              x[i] += a * p[i];
+              r[i] -= a * q[i];
+            });
+}
+
 double dot(b2p_ctx *c, const double *x, const double *y, int64_t n)
 {
   double out = 0.0;

@@ -86,6 +86,7 @@ def main():
     cj = capi.Solver.jacobi(ctx)
     cj.set_operator(Pl[orders[0]])
     coarse.set_preconditioner(cj)
+    coarse.set_check_interval(int(os.environ.get("B2P_COARSE_CG_CHECK", "8")))  # device-resident CG scalars
     coarse.set_operator(Pl[orders[0]])
     mg = capi.Solver.gmg(ctx, coarse, P, G, cycle_it=1, smooth_it=1, cheby_order=6)
     mg.gmg_set_operators([Pl[q] for q in orders], [AG[q] for q in orders])
