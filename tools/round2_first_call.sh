@@ -16,6 +16,9 @@ timeout 300 python tools/zfused_bench.py > gpurun_out/zfused_p3.json 2> gpurun_o
 timeout 300 python tools/zfused_bench.py --order 1 --n 60 >> gpurun_out/zfused_p3.json 2>> gpurun_out/zfused.err
 timeout 300 python tools/tet_bench.py --order 3 --n 14 > gpurun_out/tet_p3.json 2> gpurun_out/tet.err
 timeout 300 python tools/tet_bench.py --order 6 --n 6 >> gpurun_out/tet_p3.json 2>> gpurun_out/tet.err
+# solver loop: reference CG vs device-scalar CG on the coarse level
+timeout 300 python tools/solver_bench.py > gpurun_out/solver_bench.json 2> gpurun_out/solver_bench.err
+B2P_COARSE_CG_CHECK=8 timeout 300 python tools/solver_bench.py > gpurun_out/solver_bench_devcg.json 2>> gpurun_out/solver_bench.err
 # BASELINE configs 0 / 2 on the reference's cylinder mesh (level 0 is compared with the reference's stored eig.csv)
 timeout 300 python tools/cylinder_bench.py --order 4 --refine 0 --nev 6 > gpurun_out/cylinder_p4_l0.json 2> gpurun_out/cylinder.err
 timeout 600 python tools/cylinder_bench.py --order 4 --refine 2 --nev 4 --tol 1e-8 > gpurun_out/cylinder_p4_l2.json 2>> gpurun_out/cylinder.err

@@ -2,6 +2,7 @@
 """Solver-loop benchmark on one GPU: FGMRES + p-multigrid (Chebyshev / Hiptmair smoothing, coarse PCG)
 for (K + M) x = b on the uniform hex mesh; reports set-up time, V-cycle time, iterations, time to solution
 and a per-kernel breakdown of one V-cycle (CUDA events)."""
+import os
 import argparse, json, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -39,6 +40,7 @@ def main():
     t0 = time.time()
     coarse = capi.Solver.krylov(ctx, capi.CG, rel_tol=a.coarse_tol, max_it=500); cj = capi.Solver.jacobi(ctx); cj.set_operator(A[orders[0]])
     coarse.set_preconditioner(cj); coarse.set_operator(A[orders[0]])
+    coarse.set_check_interval(int(os.environ.get("B2P_COARSE_CG_CHECK", "1")))  # > 1: CG scalars stay on the device
     mg = capi.Solver.gmg(ctx, coarse, P, G, cycle_it=1, smooth_it=1, cheby_order=corder)
     mg.gmg_set_operators([A[q] for q in orders], [AG[q] for q in orders])
     torch.cuda.synchronize(); t_setup = time.time() - t0
