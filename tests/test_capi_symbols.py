@@ -41,3 +41,15 @@ def test_no_cpu_fallback_without_gpu():
         assert "no CPU fallback" in str(e) or "CUDA" in str(e)
     else:
         raise AssertionError("context creation must fail loudly without a GPU")
+
+
+def test_palace_adapter_header_compiles_against_the_c_abi(tmp_path):
+    """include/b2p_palace.hpp (the reference-side binding) must stay type-correct against include/b2p.h: compiled here
+    against a mock <mfem.hpp> (tests/mock_mfem), since MFEM itself is not available in this container."""
+    import subprocess
+
+    tu = tmp_path / "adapter_tu.cpp"
+    tu.write_text('#include "b2p_palace.hpp"\nint main() { return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "mock_mfem"),
+                        "-I", os.path.join(ROOT, "include"), str(tu)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
