@@ -125,6 +125,13 @@ int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d
 /* p-coarsening that shares the fine operator's quadrature, geometry and coefficient
  * (ceed::CeedOperatorCoarsen, fem/libceed/operator.cpp:525-585): only space fields of desc are read
  * (p, lsize, idx, orient, dof_map, Bo/Bc/Gc evaluated at the FINE q1d points). */
+/* One operator for the real sum  sum_t coefs[t] * A_t  of sum-factorised ND operators over the same geometry, space and
+ * essential set (BuildParSumOperator(a0 K + a1 C + a2 M), linalg/rap.cpp:764-829): the terms differ only in their pointwise
+ * coefficient, so the sum runs as ONE element-kernel launch (one geometry stream) instead of one per term.
+ * b2p_operator_par does this by itself when its terms qualify. The result is independent of the terms afterwards, except
+ * that b2p_op_sum_set_coefficients re-reads their material tensors. */
+int b2p_op_create_sum(b2p_ctx *ctx, int n_terms, b2p_op *const *ops, const double *coefs, b2p_op **out);
+int b2p_op_sum_set_coefficients(b2p_op *sum, int n_terms, b2p_op *const *ops, const double *coefs);
 int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *coarse_space, b2p_op **out);
 /* y = A x  (ceed::Operator::Mult zero-fills first, operator.cpp:182-190) */
 int b2p_op_apply(b2p_op *op, const double *x, double *y, b2p_stream s);
@@ -272,6 +279,7 @@ int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2
                      const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_halo *halo, b2p_operator **out);
 /* Elements [0, ne_interior) of every local operator touch no ghost dof: they are applied while the forward
  * shared-dof exchange is still in flight (element order chosen by the caller; 0 disables the overlap). */
+int b2p_operator_par_is_fused(b2p_operator *A); /* 1: the terms run as one fused element operator (b2p_op_create_sum) */
 int b2p_operator_par_set_coefficients(b2p_operator *A, int n_terms, const double *coefs); /* same for a real sum operator */
 int b2p_operator_par_set_interior(b2p_operator *A, int ne_interior);
 /* Interpolator on true-dof vectors (ParOperator(..., use_R) semantics); halos/true sizes of the input

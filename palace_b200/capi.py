@@ -467,6 +467,9 @@ class Operator:
         o._keep = list(ops)
         return o
 
+    def is_fused(self):
+        return int(lib().b2p_operator_par_is_fused(self.h)) == 1
+
     def set_coefficients(self, coefs):
         cf = _np(coefs, np.float64)
         _chk(lib().b2p_operator_par_set_coefficients(self.h, int(cf.size), _ptr(cf)), self.ctx.h)

@@ -126,6 +126,11 @@ int b2p_operator_par_set_coefficients(b2p_operator *A, int n_terms, const double
   pa->SetCoefficients(coefs);
   return B2P_SUCCESS;
 }
+int b2p_operator_par_is_fused(b2p_operator *A)
+{
+  auto *pa = A ? dynamic_cast<ParOperator *>(A->op.get()) : nullptr;
+  return pa ? (pa->Fused() ? 1 : 0) : -1;
+}
 int b2p_operator_par_set_interior(b2p_operator *A, int ne_interior)
 {
   auto *pa = A ? dynamic_cast<ParOperator *>(A->op.get()) : nullptr;

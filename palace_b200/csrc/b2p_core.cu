@@ -3,6 +3,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <type_traits>
+
 #include "b2p_internal.hpp"
 #include "b2p_qf.cuh"
 
@@ -688,6 +690,127 @@ int64_t b2p_op_algorithmic_bytes(b2p_op *op)
     return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->PS + 80 * Q + 144) + 8 * (int64_t)op->dense_Rpad * op->dense_Ppad;
   const int64_t per_point = op->assembled ? op->aq_ncomp : 10;
   return 16 * op->lsize + (int64_t)op->ne * (4 * (int64_t)op->PS + 8 * per_point * Q + (op->assembled ? 0 : 144));  // +144: per-element coefficient block
+}
+
+// One operator for a real sum  sum_t c_t A_t  of sum-factorised ND operators over the same geometry, space and essential
+// set (BuildParSumOperator(a0 K + a1 C + a2 M), /root/reference/palace/linalg/rap.cpp:764-829, where every term is applied
+// separately and AXPY'd): the terms differ only in their pointwise coefficient, so the sum is the SAME element kernel with the
+// per-element tensors  mass = sum_t c_t * (mass tensor of term t),  curl = sum_t c_t * (curl tensor of term t)  -- one
+// launch and one geometry stream instead of one per term, in every smoother step that applies the system matrix.
+static int sum_fill_coefficients(b2p_op *sum, int n_terms, b2p_op *const *ops, const double *coefs)
+{
+  b2p_ctx *ctx = sum->ctx;
+  const int ne = sum->ne;
+  std::vector<double> e18((size_t)18 * ne), z((size_t)18 * ne, 0.0);
+  bool mass = false, curl = false;
+  for (int t = 0; t < n_terms; t++)
+  {
+    const b2p_op *o = ops[t];
+    B2P_CUDA(ctx, cudaMemcpy(e18.data(), o->ecoef, e18.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    const bool m = (o->kind == B2P_ND_MASS || o->kind == B2P_CURLCURL_MASS), k = (o->kind == B2P_CURLCURL || o->kind == B2P_CURLCURL_MASS);
+    mass = mass || m;
+    curl = curl || k;
+    for (int e = 0; e < ne; e++)
+      for (int i = 0; i < 9; i++)
+      {
+        if (m) z[(size_t)18 * e + i] += coefs[t] * e18[(size_t)18 * e + i];
+        if (k) z[(size_t)18 * e + 9 + i] += coefs[t] * e18[(size_t)18 * e + 9 + i];
+      }
+  }
+  sum->kind = mass && curl ? B2P_CURLCURL_MASS : (mass ? B2P_ND_MASS : B2P_CURLCURL);
+  if (!(mass && curl))  // single-part kinds read whichever part they use: keep both filled
+    for (int e = 0; e < ne; e++)
+      for (int i = 0; i < 9; i++)
+      {
+        if (!mass) z[(size_t)18 * e + i] = z[(size_t)18 * e + 9 + i];
+        if (!curl) z[(size_t)18 * e + 9 + i] = z[(size_t)18 * e + i];
+      }
+  sum->iso = true;
+  for (size_t m = 0; m < (size_t)2 * ne && sum->iso; m++)
+    for (int t = 0; t < 9; t++)
+    {
+      const double v = z[9 * m + t], d = z[9 * m];
+      if ((t % 4 == 0) ? (v != d) : (v != 0.0)) sum->iso = false;
+    }
+  std::vector<int32_t> emat((size_t)2 * ne);
+  for (int e = 0; e < ne; e++)
+  {
+    emat[2 * (size_t)e] = 2 * e;
+    emat[2 * (size_t)e + 1] = 2 * e + 1;
+  }
+  cudaFree(sum->mat);
+  cudaFree(sum->emat);
+  cudaFree(sum->ecoef);
+  sum->mat = nullptr;
+  sum->emat = nullptr;
+  sum->ecoef = nullptr;
+  sum->n_mat = 2 * ne;
+  int rc;
+  if ((rc = upload(ctx, z.data(), z.size(), &sum->mat)) || (rc = upload(ctx, emat.data(), emat.size(), &sum->emat)) ||
+      (rc = upload(ctx, z.data(), z.size(), &sum->ecoef)))
+    return rc;
+  return B2P_SUCCESS;
+}
+
+int b2p_op_create_sum(b2p_ctx *ctx, int n_terms, b2p_op *const *ops, const double *coefs, b2p_op **out)
+{
+  B2P_CHECK(ctx, ctx && ops && coefs && out && n_terms >= 1, B2P_ERR_ARG, "b2p_op_create_sum: bad argument");
+  const b2p_op *o0 = ops[0];
+  const size_t nidx = (size_t)o0->ne * o0->PS;
+  std::vector<int32_t> a(nidx), b(nidx);
+  for (int t = 0; t < n_terms; t++)
+  {
+    const b2p_op *o = ops[t];
+    B2P_CHECK(ctx, o && !o->dense && !o->assembled && o->kind != B2P_H1_DIFFUSION && o->ecoef, B2P_ERR_UNSUPPORTED,
+              "b2p_op_create_sum: term %d is not a sum-factorised ND operator with on-the-fly coefficients", t);
+    B2P_CHECK(ctx, o->geom == o0->geom && o->p == o0->p && o->q1d == o0->q1d && o->ne == o0->ne && o->lsize == o0->lsize && o->PS == o0->PS &&
+                       (o->lidx_bc != nullptr) == (o0->lidx_bc != nullptr),
+              B2P_ERR_UNSUPPORTED, "b2p_op_create_sum: term %d lives on another geometry / space", t);
+    for (int which = 0; which < 2; which++)
+    {
+      const int32_t *p0 = which ? o0->lidx_bc : o0->lidx, *pt = which ? o->lidx_bc : o->lidx;
+      if (!p0 || t == 0) continue;
+      B2P_CUDA(ctx, cudaMemcpy(a.data(), p0, nidx * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      B2P_CUDA(ctx, cudaMemcpy(b.data(), pt, nidx * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      B2P_CHECK(ctx, a == b, B2P_ERR_UNSUPPORTED, "b2p_op_create_sum: term %d has another restriction / essential set", t);
+    }
+  }
+  b2p_op *op = new b2p_op;
+  op->ctx = ctx;
+  op->geom = o0->geom;
+  o0->geom->refcount++;
+  op->p = o0->p;
+  op->q1d = o0->q1d;
+  op->ne = o0->ne;
+  op->P = o0->P;
+  op->PS = o0->PS;
+  op->lsize = o0->lsize;
+  op->h_tab = o0->h_tab;
+  op->tab_sym = o0->tab_sym;
+  int rc = 0;
+  auto dup = [&](const auto *src, size_t n, auto **dst) -> int
+  {
+    using T = std::remove_const_t<std::remove_pointer_t<decltype(src)>>;
+    if (!src) return B2P_SUCCESS;
+    if (cudaMalloc((void **)dst, n * sizeof(T)) != cudaSuccess) return B2P_ERR_CUDA;
+    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice) == cudaSuccess ? B2P_SUCCESS : B2P_ERR_CUDA;
+  };
+  if ((rc = dup(o0->lidx, nidx, &op->lidx)) || (rc = dup(o0->lidx_bc, nidx, &op->lidx_bc)) || (rc = dup(o0->tab, o0->h_tab.size(), &op->tab)) ||
+      (rc = sum_fill_coefficients(op, n_terms, ops, coefs)))
+  {
+    set_error(ctx, "b2p_op_create_sum: device allocation / copy failed");
+    b2p_op_destroy(op);
+    return rc;
+  }
+  *out = op;
+  return B2P_SUCCESS;
+}
+
+// New coefficients c_t (next frequency of a sweep) for an operator made by b2p_op_create_sum from the same terms.
+int b2p_op_sum_set_coefficients(b2p_op *sum, int n_terms, b2p_op *const *ops, const double *coefs)
+{
+  if (!sum || !ops || !coefs || n_terms < 1) return B2P_ERR_ARG;
+  return sum_fill_coefficients(sum, n_terms, ops, coefs);
 }
 
 void b2p_op_destroy(b2p_op *op)

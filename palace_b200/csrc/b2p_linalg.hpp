@@ -127,7 +127,8 @@ public:
   // New scalar coefficients of the terms (a0 K + a1 C + a2 M at the next frequency of a sweep, spaceoperator.cpp:945-1153)
   // without rebuilding anything; cached CUDA graphs bake the coefficients in, so they are dropped.
   void SetCoefficients(const double *coefs);
-  size_t NumTerms() const { return terms.size(); }
+  size_t NumTerms() const { return fused_sum ? orig_terms.size() : terms.size(); }
+  bool Fused() const { return fused_sum != nullptr; }
   ~ParOperator() override;
   void Mult(const double *x, double *y) const override;
   void AddMult(const double *x, double *y, double a = 1.0) const override;
@@ -139,6 +140,9 @@ public:
 
 private:
   std::vector<Term> terms;
+  // terms as given by the caller when `terms` has been replaced by their fused sum (b2p_op_create_sum)
+  std::vector<Term> orig_terms;
+  b2p_op *fused_sum = nullptr;
   int32_t *d_ess = nullptr;
   int64_t n_ess = 0;
   int diag_policy;  // 0 = DIAG_ZERO, 1 = DIAG_ONE

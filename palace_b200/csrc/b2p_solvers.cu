@@ -44,16 +44,48 @@ ParOperator::ParOperator(b2p_ctx *c, int64_t tsize, int64_t lsize_, const std::v
   // (multi-partition callers mask ghost copies too by calling b2p_op_set_essential with L indices first)
   for (auto &t : terms)
     if (!t.op->lidx_bc) b2p_op_set_essential(t.op, ess_tdofs, n_ess);
+  // Several ND terms on one space: apply their sum as one operator (one launch, one geometry stream per Mult).
+  // B2P_SUM_FUSED=0 keeps one apply per term.
+  const char *env = getenv("B2P_SUM_FUSED");
+  if (terms.size() >= 2 && !(env && env[0] == '0'))
+  {
+    std::vector<b2p_op *> ops;
+    std::vector<double> cf;
+    for (auto &t : terms)
+    {
+      ops.push_back(t.op);
+      cf.push_back(t.coef);
+    }
+    if (b2p_op_create_sum(c, (int)ops.size(), ops.data(), cf.data(), &fused_sum) == B2P_SUCCESS)
+    {
+      orig_terms = terms;
+      terms.assign(1, Term{fused_sum, 1.0});
+    }
+    else
+      fused_sum = nullptr;  // not eligible (mixed element types / spaces): term-by-term as before
+  }
 }
 ParOperator::~ParOperator()
 {
+  if (fused_sum) b2p_op_destroy(fused_sum);
   cudaFree(d_ess);
   for (auto &g : graphs_) cudaGraphExecDestroy(g.second);
 }
 
 void ParOperator::SetCoefficients(const double *coefs)
 {
-  for (size_t t = 0; t < terms.size(); t++) terms[t].coef = coefs[t];
+  if (fused_sum)
+  {
+    std::vector<b2p_op *> ops;
+    for (size_t t = 0; t < orig_terms.size(); t++)
+    {
+      orig_terms[t].coef = coefs[t];
+      ops.push_back(orig_terms[t].op);
+    }
+    b2p_op_sum_set_coefficients(fused_sum, (int)ops.size(), ops.data(), coefs);
+  }
+  else
+    for (size_t t = 0; t < terms.size(); t++) terms[t].coef = coefs[t];
   for (auto &g : graphs_) cudaGraphExecDestroy(g.second);
   graphs_.clear();
 }
