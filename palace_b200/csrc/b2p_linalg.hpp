@@ -155,6 +155,7 @@ private:
   void MultHaloBody(const double *x, double *y, cudaStream_t s) const;
   mutable std::map<std::pair<const double *, double *>, cudaGraphExec_t> graphs_;
   mutable bool warmed_ = false;
+  mutable bool capture_failed_ = false;  // stream capture is not possible on this stream: stay on the eager sequence
 };
 
 // Element-local tensor-product interpolation between two hex spaces on the same mesh: the

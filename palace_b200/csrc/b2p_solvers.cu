@@ -179,7 +179,7 @@ void ParOperator::Mult(const double *x, double *y) const
       StreamSwap(b2p_ctx *c_, cudaStream_t s_) : c(c_), keep(c_->stream) { c->stream = s_; }
       ~StreamSwap() { c->stream = keep; }
     } swap(ctx, s);
-    if (no_graph || s == nullptr)
+    if (no_graph || capture_failed_)
     {
       MultHaloBody(x, y, s);
     }
@@ -208,7 +208,8 @@ void ParOperator::Mult(const double *x, double *y) const
       if (it == graphs_.end())
       {
         cudaGetLastError();
-        set_error(ctx, "ParOperator::Mult: CUDA graph capture of the partitioned apply failed");
+        set_error(ctx, "ParOperator::Mult: CUDA graph capture of the partitioned apply failed (legacy default stream? set B2P_GRAPH_STREAM=1)");
+        capture_failed_ = true;  // do not try again on every call
         MultHaloBody(x, y, s);
       }
     }
