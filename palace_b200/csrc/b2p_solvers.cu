@@ -105,7 +105,8 @@ void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
   // checks the neighbours' flags just before it reaches the first interface element, so the forward exchange
   // costs nothing on the critical path. (H1 operators use the separate wait kernel.)
   bool in_kernel = h->p2p && ne_interior > 0;
-  for (auto &t : terms) in_kernel = in_kernel && t.op->kind != B2P_H1_DIFFUSION;
+  // only the sum-factorised ND kernel polls the flags itself; H1 and dense-basis (tet) operators need the separate wait kernel
+  for (auto &t : terms) in_kernel = in_kernel && t.op->kind != B2P_H1_DIFFUSION && !t.op->dense;
   if (h->p2p)
     halo_forward_p2p(h, x, in_kernel, s);
   else
