@@ -104,3 +104,81 @@ def partition_space(space: HexSpace, elem_rank: np.ndarray, rank: int, nranks: i
     send_idx = np.concatenate([send_lists[s] for s in nbr if s in send_lists]) if send_lists else np.zeros(0, dtype=np.int64)
     return LocalSpace(rank, elems, int(owned.size), int(ghosts.size), l2g, local, ess_t, ess_l, nbr, send_counts,
                       send_idx.astype(np.int32), recv_counts, n_interior)
+
+
+# ------------------------------------------------------------------------------------------------
+# Tetrahedral spaces (BASELINE configs 3 / 4 run on partitioned tet meshes): same layout and exchange lists, built from
+# the native element-dof array of a TetSpace / H1TetSpace.
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclasses.dataclass
+class LocalTetSpace:
+    rank: int
+    elems: np.ndarray            # global element ids of this rank, interior elements first
+    n_true: int
+    n_ghost: int
+    local_to_global: np.ndarray
+    idx: np.ndarray              # [ne_local][P] int32 local dof of every element dof (native order)
+    curl_orient: np.ndarray      # [ne_local][P][3] int8 rows (None for H1)
+    ess_tdofs: np.ndarray
+    ess_ldofs: np.ndarray
+    nbr: np.ndarray
+    send_counts: np.ndarray
+    send_idx: np.ndarray
+    recv_counts: np.ndarray
+    n_interior: int = 0
+
+    @property
+    def lsize(self):
+        return self.n_true + self.n_ghost
+
+
+def partition_tet_space(space, elem_rank: np.ndarray, rank: int, nranks: int) -> LocalTetSpace:
+    """`space`: tetspace.TetSpace or H1TetSpace (fields idx, ndofs, ess_dofs, optionally curl_orient)."""
+    gid = space.idx.astype(np.int64)
+    P = gid.shape[1]
+    owner = np.full(space.ndofs, nranks, dtype=np.int64)
+    np.minimum.at(owner, gid.ravel(), np.repeat(elem_rank.astype(np.int64), P))
+    elems = np.nonzero(elem_rank == rank)[0]
+    gids = np.unique(gid[elems])
+    own_mask = owner[gids] == rank
+    owned, ghosts = gids[own_mask], gids[~own_mask]
+    ghosts = ghosts[np.lexsort((ghosts, owner[ghosts]))]
+    l2g = np.concatenate([owned, ghosts])
+    g2l = np.full(space.ndofs, -1, dtype=np.int64)
+    g2l[l2g] = np.arange(l2g.size)
+    touches_ghost = (g2l[gid[elems]] >= owned.size).any(axis=1)
+    elems = np.concatenate([elems[~touches_ghost], elems[touches_ghost]])
+    ess_mask = np.zeros(space.ndofs, dtype=bool)
+    ess_mask[space.ess_dofs] = True
+    ess_l = np.nonzero(ess_mask[l2g])[0]
+    g_owner = owner[ghosts]
+    send_lists = {}
+    for s in range(nranks):
+        if s == rank:
+            continue
+        es = np.nonzero(elem_rank == s)[0]
+        if es.size == 0:
+            continue
+        touched = np.unique(gid[es])
+        mine = touched[owner[touched] == rank]
+        if mine.size:
+            send_lists[s] = g2l[mine]
+    nbr = np.array(sorted(set(np.unique(g_owner).tolist()) | set(send_lists.keys())), dtype=np.int32)
+    send_counts = np.array([send_lists[s].size if s in send_lists else 0 for s in nbr], dtype=np.int64)
+    recv_counts = np.array([(g_owner == s).sum() for s in nbr], dtype=np.int64)
+    send_idx = np.concatenate([send_lists[s] for s in nbr if s in send_lists]) if send_lists else np.zeros(0, dtype=np.int64)
+    co = getattr(space, "curl_orient", None)
+    return LocalTetSpace(rank, elems, int(owned.size), int(ghosts.size), l2g, g2l[gid[elems]].astype(np.int32),
+                         None if co is None else np.ascontiguousarray(co[elems]), ess_l[ess_l < owned.size], ess_l, nbr, send_counts,
+                         send_idx.astype(np.int32), recv_counts, int((~touches_ghost).sum()))
+
+
+def partition_tets_by_slabs(mesh_elems: np.ndarray, verts: np.ndarray, nranks: int, axis: int = 0) -> np.ndarray:
+    """Element -> rank by equal-count slabs of the centroid coordinate (stand-in for METIS, driver.cpp:66-70)."""
+    c = verts[mesh_elems].mean(axis=1)[:, axis]
+    order = np.argsort(c, kind="stable")
+    rank = np.empty(mesh_elems.shape[0], dtype=np.int64)
+    rank[order] = (np.arange(order.size) * nranks) // order.size
+    return rank
