@@ -156,6 +156,9 @@ int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, in
  * < n_owned in x / y (the true-dof vectors themselves), the rest in x_ghost / y_ghost. This is what lets
  * a partitioned ParOperator run its interior elements while the ghost values are still in flight and
  * never copy a T-vector into an L-vector (e_count < 0: to the end; n_owned < 0: everything owned). */
+/* Two right-hand sides in one pass over the geometry: y0 += alpha A x0, y1 += alpha A x1 (falls back to two applies when
+ * the operator has no two-slot kernel). flags as b2p_op_apply_add_ex. */
+int b2p_op_apply_add_pair(b2p_op *op, double alpha, const double *x0, const double *x1, double *y0, double *y1, int flags, b2p_stream s);
 int b2p_op_apply_add_split(b2p_op *op, double alpha, const double *x, const double *x_ghost, double *y, double *y_ghost,
                            int64_t n_owned, int e_begin, int e_count, int flags, b2p_stream s);
 /* Essential (Dirichlet / PEC) L-vector dofs for the masked apply. */

@@ -608,6 +608,44 @@ int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, in
   return b2p::apply_range(op, lidx, alpha, x, y, ApplyRange(), flags, (cudaStream_t)s);
 }
 
+// y0 += alpha A x0 and y1 += alpha A x1 in ONE pass over the geometry (two right-hand sides: the real and imaginary parts
+// under a real preconditioner, PCMatReal, spaceoperator.cpp:1098-1105; two Krylov vectors; ...): the two vectors ride in
+// adjacent element slots of the fused-complex kernel with a purely real coefficient block. Falls back to two applies when the
+// operator is not eligible (dense basis, H1, assembled D, q1d > 4).
+int b2p_op_apply_add_pair(b2p_op *op, double alpha, const double *x0, const double *x1, double *y0, double *y1, int flags, b2p_stream s)
+{
+  if (!op || !x0 || !x1 || !y0 || !y1) return B2P_ERR_ARG;
+  const int32_t *lidx = op->lidx;
+  if (flags & B2P_APPLY_MASKED)
+  {
+    B2P_CHECK(op->ctx, op->lidx_bc, B2P_ERR_ARG, "b2p_op_apply_add_pair: masked apply without b2p_op_set_essential");
+    lidx = op->lidx_bc;
+  }
+  if (!nd_hex_apply4z_eligible(op) || !op->ecoef)
+  {
+    int rc = b2p::apply_range(op, lidx, alpha, x0, y0, ApplyRange(), flags, (cudaStream_t)s);
+    return rc ? rc : b2p::apply_range(op, lidx, alpha, x1, y1, ApplyRange(), flags, (cudaStream_t)s);
+  }
+  const b2p_op *csrc = op->parent ? op->parent : op;  // coarsened operators share the fine operator's coefficients
+  if (!op->pair_zcoef || op->pair_version != csrc->coeff_version)
+  {
+    cudaFree(op->pair_zcoef);
+    op->pair_zcoef = nullptr;
+    std::vector<double> e18((size_t)18 * op->ne), z((size_t)36 * op->ne, 0.0);
+    B2P_CUDA(op->ctx, cudaMemcpy(e18.data(), op->ecoef, e18.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int e = 0; e < op->ne; e++)
+      for (int i = 0; i < 9; i++)
+      {
+        z[(size_t)36 * e + i] = e18[(size_t)18 * e + i];
+        z[(size_t)36 * e + 18 + i] = e18[(size_t)18 * e + 9 + i];
+      }
+    int rc = upload(op->ctx, z.data(), z.size(), &op->pair_zcoef);
+    if (rc) return rc;
+    op->pair_version = csrc->coeff_version;
+  }
+  return launch_nd_hex_apply4z(op, op->kind, lidx, op->pair_zcoef, 0, alpha, x0, x1, y0, y1, (cudaStream_t)s);
+}
+
 int b2p_op_apply_add_split(b2p_op *op, double alpha, const double *x, const double *x_ghost, double *y, double *y_ghost,
                            int64_t n_owned, int e_begin, int e_count, int flags, b2p_stream s)
 {
@@ -672,6 +710,7 @@ int b2p_op_diag_add(b2p_op *op, double *diag, b2p_stream s)
 int b2p_op_set_coeff(b2p_op *op, const void *blob, size_t bytes)
 {
   if (!op) return B2P_ERR_ARG;
+  op->coeff_version++;
   B2P_CHECK(op->ctx, op->parent == nullptr, B2P_ERR_ARG, "b2p_op_set_coeff: set the coefficient on the fine operator");
   int rc = set_coeff(op, blob, bytes);
   if (rc) return rc;
@@ -822,6 +861,7 @@ void b2p_op_destroy(b2p_op *op)
   cudaFree(op->tab);
   cudaFree(op->dense_T);
   cudaFree(op->curl_orient);
+  cudaFree(op->pair_zcoef);
   if (op->parent)
   {
     b2p_op_destroy(op->parent);

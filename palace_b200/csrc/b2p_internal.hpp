@@ -143,6 +143,8 @@ struct b2p_op
   double *dense_T = nullptr;   // [Rpad][Ppad] stacked interp/deriv tables, zero padded
   int dense_Ppad = 0, dense_Rpad = 0, dense_row_u = -1, dense_row_c = -1;
   int8_t *curl_orient = nullptr;  // [ne][P][3] tridiagonal orientation (ND tets/prisms p >= 2) or null
+  double *pair_zcoef = nullptr;  // [ne][36] {mass, 0, curl, 0}: coefficient block of the two-vector apply (built on first use)
+  int coeff_version = 0, pair_version = -1;  // b2p_op_set_coeff bumps coeff_version (coarsened operators follow their parent's)
   bool owns_coeff = true;  // coarsened operators share the fine operator's coefficient arrays
   b2p_op *parent = nullptr;
   int refcount = 1;

@@ -124,3 +124,25 @@ def test_frequency_sweep_updates_coefficients_in_place(b2p_ctx, monkeypatch, fus
         Ao[ess, ess] = 1.0
         assert _rel(yr.cpu().numpy() + 1j * yi.cpu().numpy(), Ao.tocsr() @ x) < RTOL
     assert A.fused_applies() == (3 if fused == "1" else 0)
+
+
+@pytest.mark.parametrize("kind", [O.CURLCURL, O.ND_MASS, O.CURLCURL_MASS])
+@pytest.mark.parametrize("p", [1, 3, 4])
+def test_two_vector_apply(b2p_ctx, p, kind):
+    """Two right-hand sides in one pass over the geometry (b2p_op_apply_add_pair; p = 4 takes the two-apply fallback)."""
+    prob = common.make_problem(n=(3, 2, 2), p=p, n_attr=3)
+    geom = common.gpu_geom(b2p_ctx, prob)
+    blob = common.coefficient(kind, 3, "matrix")
+    op = common.gpu_op(b2p_ctx, geom, prob, kind, blob)
+    op.set_essential(prob.nd.ess_dofs.astype(np.int32))
+    rng = np.random.default_rng(2)
+    x0, x1 = rng.random(prob.nd.ndofs), rng.random(prob.nd.ndofs)
+    for masked in (False, True):
+        y0, y1 = torch.full((prob.nd.ndofs,), 1.0, dtype=torch.float64, device="cuda"), torch.full((prob.nd.ndofs,), -2.0, dtype=torch.float64, device="cuda")
+        op.apply_add_pair(0.5, _dev(x0), _dev(x1), y0, y1, masked=masked)
+        r0, r1 = torch.full_like(y0, 1.0), torch.full_like(y1, -2.0)
+        op.apply_add_ex(0.5, _dev(x0), r0, masked=masked)
+        op.apply_add_ex(0.5, _dev(x1), r1, masked=masked)
+        assert _rel(y0.cpu().numpy(), r0.cpu().numpy()) < RTOL and _rel(y1.cpu().numpy(), r1.cpu().numpy()) < RTOL
+    assert _rel(r0.cpu().numpy() - 1.0, 0.5 * common.oracle_matrix(prob, kind, blob, eliminate=False).tolil()[:, :].tocsr().dot(
+        np.where(np.isin(np.arange(prob.nd.ndofs), prob.nd.ess_dofs), 0.0, x0)) * ~np.isin(np.arange(prob.nd.ndofs), prob.nd.ess_dofs)) < RTOL
