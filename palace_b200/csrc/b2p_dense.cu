@@ -14,6 +14,8 @@
 // dimension. tcgen05 has no FP64 kind, so DMMA is the tensor path for double precision on sm_100a.
 // The sum-factorised hex kernels (b2p_hex_nd3.cu) do the same operator in O(p^4) and are ~4x faster;
 // this kernel is the fallback that covers every other element type MFEM can describe by tables.
+#include <cstdlib>
+
 #include "b2p_internal.hpp"
 #include "b2p_qf.cuh"
 #include "b2p_contract.cuh"
@@ -40,10 +42,14 @@ struct DenseParams
   int kind;
 };
 
-constexpr int NEB = 8;
+constexpr int NEB0 = 8;  // elements per MMA n-tile
 
+// NT n-tiles (8 NT elements) per block: every table fragment fetched from L2 feeds NT MMAs (the tables, not HBM, are what the
+// NT = 1 kernel waits for); NT = 1 is the hardware-verified default, B2P_DENSE_NT = 2 / 4 opt in while shared memory allows.
+template <int NT>
 __global__ void __launch_bounds__(256) dense_apply_kernel(DenseParams prm)
 {
+  constexpr int NEB = NEB0 * NT;
   B2P_DYN_SMEM(double, sm);
   double *U = sm;                       // [Ppad][NEB]
   double *V = U + prm.Ppad * NEB;       // [Rpad][NEB]
@@ -89,13 +95,24 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(DenseParams prm)
   // ---- V = T U : m-tiles over table rows, k over dofs ----
   for (int mt = wid; mt < prm.Rpad / 8; mt += nw)
   {
-    double c0 = 0.0, c1 = 0.0;
+    double c[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) c[nt][0] = c[nt][1] = 0.0;
     const double *Arow = prm.T + (size_t)(mt * 8 + lane / 4) * prm.Ppad + (lane % 4);
     const double *Bcol = U + (lane % 4) * NEB + lane / 4;
-    for (int k0 = 0; k0 < prm.Ppad; k0 += 4) dmma884(c0, c1, __ldg(Arow + k0), Bcol[k0 * NEB]);
+    for (int k0 = 0; k0 < prm.Ppad; k0 += 4)
+    {
+      const double a = __ldg(Arow + k0);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(c[nt][0], c[nt][1], a, Bcol[k0 * NEB + 8 * nt]);
+    }
     double *o = V + (mt * 8 + lane / 4) * NEB + 2 * (lane % 4);
-    o[0] = c0;
-    o[1] = c1;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+    {
+      o[8 * nt] = c[nt][0];
+      o[8 * nt + 1] = c[nt][1];
+    }
   }
   __syncthreads();
 
@@ -142,13 +159,24 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(DenseParams prm)
   // ---- Y = T^T V : m-tiles over dofs, k over table rows; result overwrites U ----
   for (int mt = wid; mt < prm.Ppad / 8; mt += nw)
   {
-    double c0 = 0.0, c1 = 0.0;
+    double c[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) c[nt][0] = c[nt][1] = 0.0;
     const double *Acol = prm.T + (size_t)(lane % 4) * prm.Ppad + mt * 8 + lane / 4;
     const double *Bcol = V + (lane % 4) * NEB + lane / 4;
-    for (int k0 = 0; k0 < prm.Rpad; k0 += 4) dmma884(c0, c1, __ldg(Acol + (size_t)k0 * prm.Ppad), Bcol[k0 * NEB]);
+    for (int k0 = 0; k0 < prm.Rpad; k0 += 4)
+    {
+      const double a = __ldg(Acol + (size_t)k0 * prm.Ppad);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(c[nt][0], c[nt][1], a, Bcol[k0 * NEB + 8 * nt]);
+    }
     double *o = U + (mt * 8 + lane / 4) * NEB + 2 * (lane % 4);
-    o[0] = c0;
-    o[1] = c1;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+    {
+      o[8 * nt] = c[nt][0];
+      o[8 * nt + 1] = c[nt][1];
+    }
   }
   __syncthreads();
 
@@ -284,15 +312,27 @@ int launch_dense_apply(b2p_op *op, const int32_t *lidx, double alpha, const doub
 {
   DenseParams prm = make_params(op, lidx, alpha, x, y, rg);
   if (prm.ne <= 0) return B2P_SUCCESS;
-  const size_t shmem = sizeof(double) * NEB * ((size_t)prm.Ppad + prm.Rpad + (op->curl_orient ? prm.Ppad : 0));
-  static size_t configured = 0;
-  if (shmem > configured)
+  const size_t shmem1 = sizeof(double) * NEB0 * ((size_t)prm.Ppad + prm.Rpad + (op->curl_orient ? prm.Ppad : 0));
+  B2P_CHECK(op->ctx, shmem1 <= 227 * 1024, B2P_ERR_UNSUPPORTED, "dense operator: element too large for shared memory (%zu B)", shmem1);
+  static const int want_nt = []
   {
-    B2P_CHECK(op->ctx, shmem <= 227 * 1024, B2P_ERR_UNSUPPORTED, "dense operator: element too large for shared memory (%zu B)", shmem);
-    B2P_CUDA(op->ctx, cudaFuncSetAttribute(dense_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    configured = shmem;
+    const char *e = std::getenv("B2P_DENSE_NT");
+    const int v = e ? std::atoi(e) : 1;
+    return v >= 4 ? 4 : (v >= 2 ? 2 : 1);
+  }();
+  int nt = want_nt;
+  while (nt > 1 && (shmem1 * nt > 227 * 1024 || prm.ne < NEB0 * nt)) nt /= 2;
+  const size_t shmem = shmem1 * nt;
+  static size_t configured[3] = {0, 0, 0};
+  const int slot = nt == 4 ? 2 : (nt == 2 ? 1 : 0);
+  auto kern = nt == 4 ? dense_apply_kernel<4> : (nt == 2 ? dense_apply_kernel<2> : dense_apply_kernel<1>);
+  if (shmem > configured[slot])
+  {
+    B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    configured[slot] = shmem;
   }
-  B2P_LAUNCH(dense_apply_kernel, (prm.ne + NEB - 1) / NEB, 256, shmem, s, prm);
+  const int neb = NEB0 * nt;
+  B2P_LAUNCH(kern, (prm.ne + neb - 1) / neb, 256, shmem, s, prm);
   B2P_CUDA(op->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

@@ -16,6 +16,8 @@ timeout 300 python tools/zfused_bench.py > gpurun_out/zfused_p3.json 2> gpurun_o
 timeout 300 python tools/zfused_bench.py --order 1 --n 60 >> gpurun_out/zfused_p3.json 2>> gpurun_out/zfused.err
 timeout 300 python tools/tet_bench.py --order 3 --n 14 > gpurun_out/tet_p3.json 2> gpurun_out/tet.err
 timeout 300 python tools/tet_bench.py --order 6 --n 6 >> gpurun_out/tet_p3.json 2>> gpurun_out/tet.err
+for nt in 2 4; do B2P_DENSE_NT=$nt timeout 300 python tools/tet_bench.py --order 3 --n 14 >> gpurun_out/tet_p3.json 2>> gpurun_out/tet.err; done
+B2P_DENSE_NT=4 timeout 300 python -m pytest tests/test_dense_gpu.py tests/test_tet_gpu.py -m gpu -x -q 2>&1 | tail -2 > gpurun_out/pytest_dense_nt4.log
 # solver loop: reference CG vs device-scalar CG on the coarse level
 timeout 300 python tools/solver_bench.py > gpurun_out/solver_bench.json 2> gpurun_out/solver_bench.err
 B2P_COARSE_CG_CHECK=8 timeout 300 python tools/solver_bench.py > gpurun_out/solver_bench_devcg.json 2>> gpurun_out/solver_bench.err
