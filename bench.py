@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--warp", type=float, default=0.0)
     ap.add_argument("--cpu-sample-elems", type=int, default=0, help="elements in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-experiments", action="store_true", help="skip the opt-in kernel variants measured in subprocesses")
     return ap.parse_args()
 
 
@@ -182,6 +183,33 @@ def workload_config(args, prob, world):
         "partition": "1 block per GPU, shared dofs summed by NCCL send/recv" if world > 1 else "single partition",
         "vector": "true-dof (T) vector", "l2_policy": "L2 flushed (256 MiB write) between timed iterations",
     }
+
+
+def run_experiments(args):
+    """Opt-in variants of the hot path (parity-green on the CPU emulation build, not yet the default) measured in child
+    processes on the same workload, so that a failure of one of them cannot touch the headline numbers above. Each entry
+    repeats `value` (MDoF/s per ParOperator::Mult) and the kernel time / roofline fraction of that variant."""
+    variants = {
+        "pdl_zero_fill_overlap": {"B2P_PDL": "1"},
+        "xdx_consumes_z_region": {"B2P_ND_FWDCHAIN": "1"},
+        "both": {"B2P_PDL": "1", "B2P_ND_FWDCHAIN": "1"},
+    }
+    out = {"note": "opt-in kernel variants, each measured by a child process of this run; not part of value / roofline above"}
+    for name, env in variants.items():
+        try:
+            child = os.environ.get("B2P_BENCH_CHILD", os.path.abspath(__file__))  # (the CPU dry-run harness points this at itself)
+            r = subprocess.run([sys.executable, child, "--steps", str(args.steps), "--warmup", str(args.warmup), "--order",
+                                str(args.order), "--n", str(args.n), "--no-cpu-baseline", "--no-experiments"],
+                               env=dict(os.environ, B2P_BENCH_EXPERIMENTS="0", **env), capture_output=True, text=True, timeout=240)
+            last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+            if not last:
+                raise RuntimeError("no result line; stderr tail: " + r.stderr.strip()[-160:])
+            d = json.loads(last[-1])
+            out[name] = {"env": env, "value": d["value"], "ms_per_step": d["ms_per_step"], "kernel_ms": d["roofline"]["kernel_ms"],
+                         "roofline_frac": d["roofline"]["frac"]}
+        except Exception as exc:
+            out[name] = {"env": env, "failed": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    return out
 
 
 def main():
@@ -422,6 +450,8 @@ def main():
             line["cpu_baseline"] = {"value": ref.dofs_per_step / min(dts) / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{ref.ns} of {ref.ne} elements per apply, best of 5 ({min(dts):.3f} s); dense non-tensor basis apply (oracle port, "
                                               f"{'-march=native' if ref.native else 'x86-64-v3'} build)"}
+        if world == 1 and not args.no_experiments and os.environ.get("B2P_BENCH_EXPERIMENTS", "1") == "1":
+            line["experiments"] = run_experiments(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -53,7 +53,11 @@ def main():
         sys.argv = [script] + sys.argv[2:]
         runpy.run_path(script, run_name="__main__")
         return
-    sys.argv = ["bench.py", "--n", "3", "--steps", "3", "--warmup", "1", "--cpu-sample-elems", "27"] + sys.argv[1:]
+    os.environ.setdefault("B2P_BENCH_CHILD", os.path.abspath(__file__))   # experiments re-enter this harness
+    if "--no-experiments" in sys.argv:                                     # (child of an experiment: bench args come from the parent)
+        sys.argv = ["bench.py"] + sys.argv[1:]
+    else:
+        sys.argv = ["bench.py", "--n", "3", "--steps", "3", "--warmup", "1", "--cpu-sample-elems", "27"] + sys.argv[1:]
     bench.main()
 
 
