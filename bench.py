@@ -209,6 +209,27 @@ def run_experiments(args):
                          "roofline_frac": d["roofline"]["frac"]}
         except Exception as exc:
             out[name] = {"env": env, "failed": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    # other prepared measurements (tools/): one JSON line each
+    tools = {
+        "complex_fused_and_pair_apply": ["tools/zfused_bench.py", "--steps", "50"],
+        "tet_dense_p3": ["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"],
+    }
+    if os.environ.get("B2P_BENCH_CHILD"):  # CPU dry run: tiny sizes
+        tools = {"complex_fused_and_pair_apply": ["tools/zfused_bench.py", "--n", "3", "--steps", "2"],
+                 "tet_dense_p3": ["tools/tet_bench.py", "--order", "2", "--n", "2", "--steps", "2"]}
+    for name, cmd in tools.items():
+        try:
+            if os.environ.get("B2P_BENCH_CHILD"):
+                argv = [sys.executable, os.environ["B2P_BENCH_CHILD"], os.path.join(ROOT, cmd[0])] + cmd[1:]
+            else:
+                argv = [sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:]
+            r = subprocess.run(argv, env=dict(os.environ, B2P_BENCH_EXPERIMENTS="0"), capture_output=True, text=True, timeout=240, cwd=ROOT)
+            last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+            if not last:
+                raise RuntimeError("no result line; stderr tail: " + r.stderr.strip()[-160:])
+            out[name] = json.loads(last[-1])
+        except Exception as exc:
+            out[name] = {"failed": f"{type(exc).__name__}: {str(exc)[:200]}"}
     return out
 
 
