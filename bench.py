@@ -195,12 +195,16 @@ def run_experiments(args):
         "both": {"B2P_PDL": "1", "B2P_ND_FWDCHAIN": "1"},
     }
     out = {"note": "opt-in kernel variants, each measured by a child process of this run; not part of value / roofline above"}
+    t_start, budget_s = time.time(), float(os.environ.get("B2P_BENCH_EXPERIMENT_BUDGET_S", "330"))
     for name, env in variants.items():
+        if time.time() - t_start > budget_s:
+            out[name] = {"skipped": "experiment time budget used up"}
+            continue
         try:
             child = os.environ.get("B2P_BENCH_CHILD", os.path.abspath(__file__))  # (the CPU dry-run harness points this at itself)
             r = subprocess.run([sys.executable, child, "--steps", str(args.steps), "--warmup", str(args.warmup), "--order",
                                 str(args.order), "--n", str(args.n), "--no-cpu-baseline", "--no-experiments"],
-                               env=dict(os.environ, B2P_BENCH_EXPERIMENTS="0", **env), capture_output=True, text=True, timeout=240)
+                               env=dict(os.environ, B2P_BENCH_EXPERIMENTS="0", **env), capture_output=True, text=True, timeout=150)
             last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
             if not last:
                 raise RuntimeError("no result line; stderr tail: " + r.stderr.strip()[-160:])
@@ -211,19 +215,28 @@ def run_experiments(args):
             out[name] = {"env": env, "failed": f"{type(exc).__name__}: {str(exc)[:200]}"}
     # other prepared measurements (tools/): one JSON line each
     tools = {
-        "complex_fused_and_pair_apply": ["tools/zfused_bench.py", "--steps", "50"],
-        "tet_dense_p3": ["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"],
+        "cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "4", "--refine", "0", "--nev", "4"], {}),
+        "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--steps", "50"], {}),
+        "solver_loop_p3_2M": (["tools/solver_bench.py"], {}),
+        "solver_loop_p3_2M_device_scalar_cg": (["tools/solver_bench.py"], {"B2P_COARSE_CG_CHECK": "8"}),
+        "tet_dense_p3": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {}),
+        "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {"B2P_DENSE_NT": "4"}),
     }
     if os.environ.get("B2P_BENCH_CHILD"):  # CPU dry run: tiny sizes
-        tools = {"complex_fused_and_pair_apply": ["tools/zfused_bench.py", "--n", "3", "--steps", "2"],
-                 "tet_dense_p3": ["tools/tet_bench.py", "--order", "2", "--n", "2", "--steps", "2"]}
-    for name, cmd in tools.items():
+        tools = {"cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "1", "--nev", "1", "--tol", "1e-6"], {}),
+                 "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--n", "3", "--steps", "2"], {}),
+                 "solver_loop_p3_2M_device_scalar_cg": (["tools/solver_bench.py", "--n", "3"], {"B2P_COARSE_CG_CHECK": "8"}),
+                 "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "2", "--n", "2", "--steps", "2"], {"B2P_DENSE_NT": "4"})}
+    for name, (cmd, env) in tools.items():
+        if time.time() - t_start > budget_s:
+            out[name] = {"skipped": "experiment time budget used up"}
+            continue
         try:
             if os.environ.get("B2P_BENCH_CHILD"):
                 argv = [sys.executable, os.environ["B2P_BENCH_CHILD"], os.path.join(ROOT, cmd[0])] + cmd[1:]
             else:
                 argv = [sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:]
-            r = subprocess.run(argv, env=dict(os.environ, B2P_BENCH_EXPERIMENTS="0"), capture_output=True, text=True, timeout=240, cwd=ROOT)
+            r = subprocess.run(argv, env=dict(os.environ, B2P_BENCH_EXPERIMENTS="0", **env), capture_output=True, text=True, timeout=150, cwd=ROOT)
             last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
             if not last:
                 raise RuntimeError("no result line; stderr tail: " + r.stderr.strip()[-160:])
