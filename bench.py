@@ -218,14 +218,16 @@ def run_experiments(args):
         "cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "4", "--refine", "0", "--nev", "4"], {}),
         "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--steps", "50"], {}),
         "solver_loop_p3_2M": (["tools/solver_bench.py"], {}),
-        "solver_loop_p3_2M_device_scalar_cg": (["tools/solver_bench.py"], {"B2P_COARSE_CG_CHECK": "8"}),
+        "solver_loop_p3_2M_all_opt_ins": (["tools/solver_bench.py"], {"B2P_COARSE_CG_CHECK": "8", "B2P_INTERP_OWNER": "1", "B2P_PDL": "1",
+                                                                     "B2P_ND_FWDCHAIN": "1"}),
         "tet_dense_p3": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {}),
         "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {"B2P_DENSE_NT": "4"}),
     }
     if os.environ.get("B2P_BENCH_CHILD"):  # CPU dry run: tiny sizes
         tools = {"cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "1", "--nev", "1", "--tol", "1e-6"], {}),
                  "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--n", "3", "--steps", "2"], {}),
-                 "solver_loop_p3_2M_device_scalar_cg": (["tools/solver_bench.py", "--n", "3"], {"B2P_COARSE_CG_CHECK": "8"}),
+                 "solver_loop_p3_2M_all_opt_ins": (["tools/solver_bench.py", "--n", "3"], {"B2P_COARSE_CG_CHECK": "8", "B2P_INTERP_OWNER": "1",
+                                                                                          "B2P_PDL": "1", "B2P_ND_FWDCHAIN": "1"}),
                  "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "2", "--n", "2", "--steps", "2"], {"B2P_DENSE_NT": "4"})}
     for name, (cmd, env) in tools.items():
         if time.time() - t_start > budget_s:

@@ -156,6 +156,7 @@ struct b2p_interp
   int ne = 0, in_P = 0, out_P = 0, in_PS = 0, out_PS = 0, ncomp = 0;
   int64_t in_lsize = 0, out_lsize = 0;
   int32_t *in_lidx = nullptr, *out_lidx = nullptr;  // signed lexicographic restrictions [ne][PS]
+  int32_t *out_owner_lidx = nullptr;  // out_lidx with every dof kept in ONE element only (owner-computes Mult), or null
   double *inv_mult = nullptr;                       // [out_lsize] 1 / (local elements touching the dof)
   // per component: dims and matrix offsets into `mats`
   int in_off[3], in_n[3][3], out_off[3], out_n[3][3], mat_off[3][3];
