@@ -10,14 +10,19 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
-    # a wedged GPU test must end the run instead of hanging it (pytest-timeout, when installed)
-    if config.pluginmanager.hasplugin("timeout") and not getattr(config.option, "timeout", None):
-        config.option.timeout = 1500
     if os.environ.get("B2P_EMU_TESTS") == "1":
         # pre-GPU validation: the same tests against the host-thread SIMT emulation build of the kernel sources
         from tests.emu import emu_mode
 
         emu_mode.enable()
+
+
+def pytest_collection_modifyitems(config, items):
+    # a wedged test must end the run instead of hanging it (pytest-timeout, when installed and no --timeout given)
+    if config.pluginmanager.hasplugin("timeout") and not config.getoption("timeout", None):
+        for item in items:
+            if item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(1500))
 
 
 @pytest.fixture(scope="session")
