@@ -216,6 +216,16 @@ class Op:
         _chk(lib().b2p_op_create_dense(ctx.h, geom.h, C.byref(d), C.byref(h)), ctx.h)
         return cls(ctx, h, lsize)
 
+    @classmethod
+    def create_sum(cls, ctx, ops, coefs):
+        """One operator for sum_t coefs[t] * ops[t] (ND terms on one geometry / space): one launch per apply."""
+        n = len(ops)
+        arr = (C.c_void_p * n)(*[o.h for o in ops])
+        cf = _np(coefs, np.float64)
+        h = C.c_void_p()
+        _chk(lib().b2p_op_create_sum(ctx.h, n, arr, _ptr(cf), C.byref(h)), ctx.h)
+        return cls(ctx, h, ops[0].lsize)
+
     def coarsen(self, p, lsize, idx, orient, dof_map, Bo, Bc, Gc):
         d, keep = _desc(0, p, lsize, idx, orient, dof_map, Bo, Bc, Gc, None, False)
         h = C.c_void_p()

@@ -34,8 +34,8 @@ def _problem(p):
                           hs.tables_1d(p, q1d), (nB, nG), qd)
 
 
-@pytest.mark.parametrize("nev", [6])
-def test_cylinder_cavity_eigenfrequencies_match_the_reference(b2p_ctx, nev):
+@pytest.mark.parametrize("nev,as_sum", [(6, False), (3, True)])
+def test_cylinder_cavity_eigenfrequencies_match_the_reference(b2p_ctx, nev, as_sum):
     from palace_b200 import capi
 
     capi.set_stream(b2p_ctx)
@@ -50,10 +50,21 @@ def test_cylinder_cavity_eigenfrequencies_match_the_reference(b2p_ctx, nev):
     blob_A = cf.coeff_ctx_pair(cf.coeff_ctx(a=-sigma), cf.coeff_ctx(a=1.0))     # K - sigma M
     blob_P = cf.coeff_ctx_pair(cf.coeff_ctx(a=+sigma), cf.coeff_ctx(a=1.0))     # shifted positive preconditioner matrix
     blob_G = cf.coeff_ctx(a=sigma)
-    A = common.gpu_par_operator(b2p_ctx, geom, prob, O.CURLCURL_MASS, blob_A, space=nd[p])
     M = common.gpu_par_operator(b2p_ctx, geom, prob, O.ND_MASS, ident, space=nd[p])
     Pl, AG = {}, {}
-    Pl[p] = common.gpu_par_operator(b2p_ctx, geom, prob, O.CURLCURL_MASS, blob_P, space=nd[p])
+    if as_sum:
+        # the way Palace builds them: K and M assembled once, system / preconditioner matrices as sums a0 K + a2 M
+        # (BuildParSumOperator, rap.cpp:764-829) -- here each sum runs as one fused element operator
+        Kop = common.gpu_op(b2p_ctx, geom, prob, O.CURLCURL, ident)
+        Mop = common.gpu_op(b2p_ctx, geom, prob, O.ND_MASS, ident)
+        A = capi.Operator.par(b2p_ctx, nd[p].ndofs, nd[p].ndofs, [Kop, Mop], [1.0, -sigma], nd[p].ess_dofs, diag_policy=1)
+        assert A.is_fused()
+        Psum = capi.Op.create_sum(b2p_ctx, [Kop, Mop], [1.0, sigma])
+        Pl[p] = capi.Operator.par(b2p_ctx, nd[p].ndofs, nd[p].ndofs, [Psum], None, nd[p].ess_dofs, diag_policy=1)
+        Pl[p].local_op = Psum
+    else:
+        A = common.gpu_par_operator(b2p_ctx, geom, prob, O.CURLCURL_MASS, blob_A, space=nd[p])
+        Pl[p] = common.gpu_par_operator(b2p_ctx, geom, prob, O.CURLCURL_MASS, blob_P, space=nd[p])
     AG[p] = common.gpu_par_operator(b2p_ctx, geom, prob, O.H1_DIFFUSION, blob_G, space=h1[p])
     for q in orders[:-1]:
         Pl[q] = common.gpu_par_operator(b2p_ctx, geom, prob, O.CURLCURL_MASS, blob_P, space=nd[q], fine_op=Pl[p].local_op)

@@ -83,3 +83,32 @@ def test_mixed_element_types_keep_one_apply_per_term(b2p_ctx):
     A.mult(_dev(x), y)
     ref = common.oracle_apply(prob, O.ND_MASS, mb, x) + 0.7 * O.apply_add(O.ND_MASS, interp, None, sp.idx, sp.orient, qd, mb, x, np.zeros(nd.ndofs))
     assert _rel(y.cpu().numpy(), ref) < RTOL
+
+
+def test_sum_operator_can_be_coarsened(b2p_ctx):
+    """The fused sum is an ordinary local operator: p-coarsening it (CeedOperatorCoarsen semantics, fine quadrature and
+    coefficients shared) gives the sum of the coarsened terms."""
+    from palace_b200 import capi
+    from palace_b200.host import hexspace as hs
+
+    prob = common.make_problem(p=3, n_attr=2)
+    geom = common.gpu_geom(b2p_ctx, prob)
+    specs = [(O.CURLCURL, common.coefficient(O.CURLCURL, 2, "matrix")), (O.ND_MASS, common.coefficient(O.ND_MASS, 2, "matrix", a_mass=1.7))]
+    ops = [common.gpu_op(b2p_ctx, geom, prob, k, b) for k, b in specs]
+    coefs = [1.0, 7.5]
+    fine = capi.Op.create_sum(b2p_ctx, ops, coefs)
+    x = np.random.default_rng(8).random(prob.nd.ndofs)
+    y = torch.empty(prob.nd.ndofs, dtype=torch.float64, device="cuda")
+    fine.apply(_dev(x), y)
+    ref = sum(c * common.oracle_apply(prob, k, b, x) for c, (k, b) in zip(coefs, specs))
+    assert _rel(y.cpu().numpy(), ref) < RTOL
+    pc = 2
+    ndc = hs.build_nd_space(prob.mesh, prob.topo, pc)
+    t = hs.tables_1d(pc, prob.q1d)
+    idx, ori = ndc.native_restriction()
+    coarse = fine.coarsen(pc, ndc.ndofs, idx, ori, ndc.dof_map, t.Bo, t.Bc, t.Gc)
+    xc = np.random.default_rng(9).random(ndc.ndofs)
+    yc = torch.empty(ndc.ndofs, dtype=torch.float64, device="cuda")
+    coarse.apply(_dev(xc), yc)
+    refc = sum(c * common.oracle_apply(prob, k, b, xc, space=ndc, q1d=prob.q1d) for c, (k, b) in zip(coefs, specs))
+    assert _rel(yc.cpu().numpy(), refc) < RTOL
