@@ -125,6 +125,7 @@ int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d
 /* p-coarsening that shares the fine operator's quadrature, geometry and coefficient
  * (ceed::CeedOperatorCoarsen, fem/libceed/operator.cpp:525-585): only space fields of desc are read
  * (p, lsize, idx, orient, dof_map, Bo/Bc/Gc evaluated at the FINE q1d points). */
+int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *coarse_space, b2p_op **out);
 /* One operator for the real sum  sum_t coefs[t] * A_t  of sum-factorised ND operators over the same geometry, space and
  * essential set (BuildParSumOperator(a0 K + a1 C + a2 M), linalg/rap.cpp:764-829): the terms differ only in their pointwise
  * coefficient, so the sum runs as ONE element-kernel launch (one geometry stream) instead of one per term.
@@ -132,7 +133,6 @@ int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d
  * that b2p_op_sum_set_coefficients re-reads their material tensors. */
 int b2p_op_create_sum(b2p_ctx *ctx, int n_terms, b2p_op *const *ops, const double *coefs, b2p_op **out);
 int b2p_op_sum_set_coefficients(b2p_op *sum, int n_terms, b2p_op *const *ops, const double *coefs);
-int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *coarse_space, b2p_op **out);
 /* y = A x  (ceed::Operator::Mult zero-fills first, operator.cpp:182-190) */
 int b2p_op_apply(b2p_op *op, const double *x, double *y, b2p_stream s);
 /* y += A x (ceed::Operator::AddMult, a == 1 only, operator.cpp:192-212) */
