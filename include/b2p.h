@@ -261,6 +261,7 @@ int b2p_csr_device_arrays(b2p_csr *A, const int32_t **rowptr, const int32_t **co
 int b2p_csr_get_host(b2p_csr *A, int32_t *rowptr, int32_t *col, double *val, b2p_stream s);
 int b2p_csr_eliminate(b2p_csr *A, const int32_t *ess_dofs, int64_t n_ess, int diag_policy, b2p_stream s);
 int b2p_csr_mult(b2p_csr *A, const double *x, double *y, b2p_stream s);
+int b2p_csr_diag(b2p_csr *A, double *d, b2p_stream stream);   /* d = diag(A) */
 void b2p_csr_destroy(b2p_csr *A);
 
 /* ---- device-resident linear algebra (replaces linalg/vector.cpp kernels + MPI_Allreduce) ---- */
@@ -280,11 +281,14 @@ typedef struct b2p_operator b2p_operator;
  * diag_policy 0 = DIAG_ZERO, 1 = DIAG_ONE; halo may be NULL (single partition). */
 int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coefs,
                      const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_halo *halo, b2p_operator **out);
+int b2p_operator_par_is_fused(b2p_operator *A); /* 1: the terms run as one fused element operator (b2p_op_create_sum) */
+/* New coefficients of the sum without rebuilding the operator (frequency sweeps: a0 K + a1 C + a2 M with new a_i). */
+int b2p_operator_par_set_coefficients(b2p_operator *A, int n_terms, const double *coefs);
 /* Elements [0, ne_interior) of every local operator touch no ghost dof: they are applied while the forward
  * shared-dof exchange is still in flight (element order chosen by the caller; 0 disables the overlap). */
-int b2p_operator_par_is_fused(b2p_operator *A); /* 1: the terms run as one fused element operator (b2p_op_create_sum) */
-int b2p_operator_par_set_coefficients(b2p_operator *A, int n_terms, const double *coefs); /* same for a real sum operator */
 int b2p_operator_par_set_interior(b2p_operator *A, int ne_interior);
+/* The assembled matrix as an operator (symmetric; not owned): coarse-level Krylov / Jacobi / Chebyshev solvers run on it. */
+int b2p_operator_csr(b2p_ctx *ctx, b2p_csr *A, b2p_operator **out);
 /* Interpolator on true-dof vectors (ParOperator(..., use_R) semantics); halos/true sizes of the input
  * and output spaces, NULL / L-size for a single partition. */
 int b2p_operator_interp(b2p_ctx *ctx, b2p_interp *it, b2p_halo *in_halo, int64_t in_tsize, b2p_halo *out_halo,
@@ -310,6 +314,13 @@ int b2p_solver_gmg(b2p_ctx *ctx, b2p_solver *coarse, int n_levels, b2p_operator 
                    int smooth_it, int cheby_order, double sf_max, double sf_min, int fourth_kind, b2p_solver **out);  /* gmg.cpp */
 int b2p_solver_gmg_set_operators(b2p_solver *s, b2p_operator *const *A, b2p_operator *const *A_aux);
 /* type 0 CG, 1 GMRES, 2 FGMRES (iterative.cpp) */
+/* A solver that runs on the device-ASSEMBLED matrix of the ParOperator it is given at set_operator time
+ * (MfemWrapperSolver, linalg/solver.cpp:13-30; single partition): the multigrid's coarse solver. Takes over `inner` (a Krylov
+ * or smoother handle) and, optionally, its preconditioner `inner_pc`, which also gets the assembled matrix; the two handles
+ * only need b2p_solver_destroy afterwards. b2p_solver_assembled_nnz: entries of the current matrix (s: the solver, or the multigrid that took it over as its coarse
+ * solver), -1 before set_operator. */
+int b2p_solver_assembled(b2p_ctx *ctx, b2p_solver *inner, b2p_solver *inner_pc, b2p_solver **out);
+int64_t b2p_solver_assembled_nnz(b2p_solver *s);
 int b2p_solver_krylov(b2p_ctx *ctx, int type, b2p_solver **out);
 int b2p_solver_krylov_config(b2p_solver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side);
 /* CG only: keep alpha / beta in device memory and read the residual back every `check_every` iterations (1 = the

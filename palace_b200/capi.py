@@ -415,6 +415,9 @@ class Csr:
     def mult(self, x, y, stream=None):
         _chk(lib().b2p_csr_mult(self.h, _vp(x), _vp(y), _stream(stream)), self.ctx.h)
 
+    def diag(self, d, stream=None):
+        _chk(lib().b2p_csr_diag(self.h, _vp(d), _stream(stream)), self.ctx.h)
+
     def to_scipy(self, stream=None):
         import scipy.sparse as sp
 
@@ -479,6 +482,15 @@ class Operator:
                                     int(diag_policy), halo.h if halo else None, C.byref(h)), ctx.h)
         o = cls(ctx, h)
         o._keep = list(ops)
+        return o
+
+    @classmethod
+    def from_csr(cls, ctx, csr):
+        """The assembled matrix behind the operator interface (coarse-level solvers); csr must outlive it."""
+        h = C.c_void_p()
+        _chk(lib().b2p_operator_csr(ctx.h, csr.h, C.byref(h)), ctx.h)
+        o = cls(ctx, h)
+        o._csr = csr
         return o
 
     def is_fused(self):
@@ -585,6 +597,19 @@ class Solver:
         _chk(lib().b2p_solver_krylov_config(h, C.c_double(rel_tol), C.c_double(abs_tol), int(max_it), int(max_dim), int(orthog),
                                             int(pc_side)), ctx.h)
         return s
+
+    @classmethod
+    def assembled(cls, ctx, inner, inner_pc=None):
+        """Coarse solver on the device-assembled matrix of the ParOperator given to set_operator (MfemWrapperSolver)."""
+        h = C.c_void_p()
+        _chk(lib().b2p_solver_assembled(ctx.h, inner.h, inner_pc.h if inner_pc is not None else None, C.byref(h)), ctx.h)
+        s = cls(ctx, h)
+        s._keep += [inner, inner_pc]
+        return s
+
+    def assembled_nnz(self):
+        lib().b2p_solver_assembled_nnz.restype = C.c_int64
+        return int(lib().b2p_solver_assembled_nnz(self.h))
 
     def set_check_interval(self, check_every):
         _chk(lib().b2p_solver_krylov_set_check_interval(self.h, int(check_every)), self.ctx.h)

@@ -48,14 +48,31 @@ __global__ void scatter_column_kernel(const double *__restrict__ yE, const int32
   const double si = gidx[e * PS + i] < 0 ? -1.0 : 1.0, sj = gidx[e * PS + j] < 0 ? -1.0 : 1.0;
   atomicAdd(val + k, c * si * sj * yE[w]);
 }
+// y = A x, CSR_LANES lanes per row: the lanes stride over the row's entries (coalesced val / col reads; the coarse-level
+// rows hold 27-81 entries) and fold their partial sums with shuffles.
+constexpr int CSR_LANES = 8;
 __global__ void csr_mult_kernel(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                 const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = t / CSR_LANES;
+  const int sub = (int)(t % CSR_LANES);
+  double s = 0.0;
+  if (r < n)
+    for (int32_t k = rowptr[r] + sub; k < rowptr[r + 1]; k += CSR_LANES) s += val[k] * x[col[k]];
+#pragma unroll
+  for (int o = CSR_LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);  // stays inside the row's lane group
+  if (r < n && sub == 0) y[r] = s;
+}
+__global__ void csr_diag_kernel(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                const double *__restrict__ val, double *__restrict__ d)
 {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   double s = 0.0;
-  for (int32_t k = rowptr[r]; k < rowptr[r + 1]; k++) s += val[k] * x[col[k]];
-  y[r] = s;
+  for (int32_t k = rowptr[r]; k < rowptr[r + 1]; k++)
+    if (col[k] == r) s = val[k];
+  d[r] = s;
 }
 // mfem::HypreParMatrix::EliminateBC semantics on the local matrix: essential rows and columns zeroed, diagonal set to
 // one (DIAG_ONE) or zero (DIAG_ZERO)  (rap.cpp:141-146)
@@ -262,7 +279,15 @@ int b2p_csr_eliminate(b2p_csr *A, const int32_t *ess_dofs, int64_t n_ess, int di
 int b2p_csr_mult(b2p_csr *A, const double *x, double *y, b2p_stream stream)
 {
   if (!A || !x || !y) return B2P_ERR_ARG;
-  B2P_LAUNCH(csr_mult_kernel, blocks(A->n, 256), 256, 0, (cudaStream_t)stream, A->n, A->d_rowptr, A->d_col, A->d_val, x, y);
+  B2P_LAUNCH(csr_mult_kernel, blocks(A->n * CSR_LANES, 256), 256, 0, (cudaStream_t)stream, A->n, A->d_rowptr, A->d_col, A->d_val, x, y);
+  B2P_CUDA(A->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+
+int b2p_csr_diag(b2p_csr *A, double *d, b2p_stream stream)
+{
+  if (!A || !d) return B2P_ERR_ARG;
+  B2P_LAUNCH(csr_diag_kernel, blocks(A->n, 256), 256, 0, (cudaStream_t)stream, A->n, A->d_rowptr, A->d_col, A->d_val, d);
   B2P_CUDA(A->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

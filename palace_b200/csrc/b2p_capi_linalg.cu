@@ -119,6 +119,66 @@ int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2
   *out = h;
   return B2P_SUCCESS;
 }
+namespace
+{
+// The assembled coarse-level matrix behind the Operator interface, so that the Krylov solvers and smoothers can run on it
+// (the reference hands the assembled coarse matrix to its coarse solver, linalg/ksp.cpp:ConfigurePreconditionerSolver).
+class CsrOperator : public Operator
+{
+  b2p_csr *A;
+
+public:
+  CsrOperator(b2p_ctx *c, b2p_csr *a) : Operator(c, b2p_csr_rows(a), b2p_csr_rows(a)), A(a) {}
+  void Mult(const double *x, double *y) const override { b2p_csr_mult(A, x, y, (b2p_stream)ctx->stream); }
+  void AssembleDiagonal(double *d) const override { b2p_csr_diag(A, d, (b2p_stream)ctx->stream); }
+};
+// A solver that runs on the ASSEMBLED matrix of the ParOperator it is given (MfemWrapperSolver::SetOperator,
+// linalg/solver.cpp:13-30: "Operator is always assembled as a HypreParMatrix"): SetOperator assembles and eliminates the
+// sum on the device and hands the matrix to the inner solver and its preconditioner. This is how the multigrid's coarse
+// solver sees level 0.
+class AssembledSolver : public Solver
+{
+  std::unique_ptr<Solver> inner, pc;
+  b2p_csr *csr = nullptr;
+  std::unique_ptr<CsrOperator> Ac;
+
+public:
+  AssembledSolver(b2p_ctx *c, std::unique_ptr<Solver> &&in, std::unique_ptr<Solver> &&p) : Solver(c), inner(std::move(in)), pc(std::move(p)) {}
+  ~AssembledSolver() override { b2p_csr_destroy(csr); }
+  void SetOperator(const Operator &op) override
+  {
+    const auto *pa = dynamic_cast<const ParOperator *>(&op);
+    if (!pa)
+    {
+      set_error(ctx, "AssembledSolver must be able to assemble its operator: ParOperator required");
+      return;
+    }
+    b2p_csr *A = pa->FullAssemble();
+    if (!A) return;
+    b2p_csr_destroy(csr);
+    csr = A;
+    Ac = std::make_unique<CsrOperator>(ctx, csr);
+    if (pc) pc->SetOperator(*Ac);
+    inner->SetOperator(*Ac);
+    height = op.Height();
+    width = op.Width();
+  }
+  void Mult(const double *x, double *y) const override
+  {
+    inner->SetInitialGuess(initial_guess);
+    inner->Mult(x, y);
+  }
+  const b2p_csr *Matrix() const { return csr; }
+};
+}  // namespace
+int b2p_operator_csr(b2p_ctx *ctx, b2p_csr *A, b2p_operator **out)
+{
+  B2P_CHECK(ctx, ctx && A && out, B2P_ERR_ARG, "b2p_operator_csr: null argument");
+  auto *h = new b2p_operator;
+  h->op = std::make_unique<CsrOperator>(ctx, A);
+  *out = h;
+  return B2P_SUCCESS;
+}
 int b2p_operator_par_set_coefficients(b2p_operator *A, int n_terms, const double *coefs)
 {
   auto *pa = A ? dynamic_cast<ParOperator *>(A->op.get()) : nullptr;
@@ -242,6 +302,27 @@ int b2p_solver_gmg_set_operators(b2p_solver *s, b2p_operator *const *A, b2p_oper
   }
   B2P_TRY(g->ctx, g->SetOperators(Av, Gv));
   return B2P_SUCCESS;
+}
+int b2p_solver_assembled(b2p_ctx *ctx, b2p_solver *inner, b2p_solver *inner_pc, b2p_solver **out)
+{
+  B2P_CHECK(ctx, ctx && inner && inner->s && out, B2P_ERR_ARG, "b2p_solver_assembled: bad argument");
+  auto *k = dynamic_cast<IterativeSolver *>(inner->s.get());
+  if (inner_pc)
+  {
+    B2P_CHECK(ctx, inner_pc->s && k, B2P_ERR_ARG, "b2p_solver_assembled: a preconditioner needs a Krylov inner solver");
+    k->SetPreconditioner(inner_pc->s.get());
+  }
+  auto *h = new b2p_solver;
+  h->s = std::make_unique<AssembledSolver>(ctx, std::move(inner->s), inner_pc ? std::move(inner_pc->s) : nullptr);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int64_t b2p_solver_assembled_nnz(b2p_solver *s)
+{
+  const Solver *p = s ? s->s.get() : nullptr;
+  if (auto *g = dynamic_cast<const GeometricMultigridSolver *>(p)) p = g->B[0].get();  // the multigrid took the coarse solver over
+  auto *a = dynamic_cast<const AssembledSolver *>(p);
+  return a && a->Matrix() ? b2p_csr_nnz(a->Matrix()) : -1;
 }
 int b2p_solver_krylov(b2p_ctx *ctx, int type, b2p_solver **out)
 {

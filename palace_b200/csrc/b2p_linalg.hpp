@@ -134,6 +134,9 @@ public:
   void AddMult(const double *x, double *y, double a = 1.0) const override;
   void AssembleDiagonal(double *d) const override;
   void SetInteriorElements(int n) { ne_interior = n; }  // elements [0, n) touch no ghost dof
+  // The eliminated sum as one device CSR matrix (ParOperator::ParallelAssemble, rap.cpp:84-152; coarse levels, single
+  // partition); the caller owns the result (b2p_csr_destroy). Throws through set_error + nullptr on failure.
+  b2p_csr *FullAssemble() const;
   const int32_t *EssentialTrueDofs() const { return d_ess; }
   int64_t NumEssential() const { return n_ess; }
   int64_t lsize;

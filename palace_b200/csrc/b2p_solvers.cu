@@ -242,6 +242,36 @@ void ParOperator::AddMult(const double *x, double *y, double a) const
 }
 
 // rap.cpp:154-193: diag = |P|^T diag_L, essential rows per the diagonal policy
+b2p_csr *ParOperator::FullAssemble() const
+{
+  if (halo && halo->n_ghost > 0)
+  {
+    set_error(ctx, "ParOperator::FullAssemble: partitioned spaces are not assembled (the coarse matrix lives on one device)");
+    return nullptr;
+  }
+  b2p_csr *A = nullptr;
+  if (b2p_csr_create(ctx, terms[0].op, &A) != B2P_SUCCESS) return nullptr;
+  std::vector<b2p_op *> ops;
+  std::vector<double> cf;
+  for (auto &t : terms)
+  {
+    ops.push_back(t.op);
+    cf.push_back(t.coef);
+  }
+  std::vector<int32_t> ess((size_t)n_ess);
+  if (n_ess > 0)
+  {
+    cudaMemcpyAsync(ess.data(), d_ess, sizeof(int32_t) * n_ess, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (b2p_csr_assemble(A, (int)ops.size(), ops.data(), cf.data(), (b2p_stream)ctx->stream) != B2P_SUCCESS ||
+      b2p_csr_eliminate(A, ess.data(), n_ess, diag_policy, (b2p_stream)ctx->stream) != B2P_SUCCESS)
+  {
+    b2p_csr_destroy(A);
+    return nullptr;
+  }
+  return A;
+}
 void ParOperator::AssembleDiagonal(double *d) const
 {
   cudaStream_t s = ctx->stream;

@@ -325,6 +325,41 @@ def test_fgmres_with_multigrid_preconditioner_solves_the_system(b2p_ctx, capi_mo
     assert _rel(xd.cpu().numpy(), spla.spsolve(Ao.tocsc(), b)) < 1e-8
 
 
+def test_multigrid_with_the_coarse_level_assembled_on_the_device(b2p_ctx, capi_mod, hier):
+    """The reference's coarse-level flow (MfemWrapperSolver::SetOperator, linalg/solver.cpp:13-30): the multigrid hands its
+    level-0 ParOperator to a solver that assembles it; here a Jacobi-PCG on the device CSR matrix. Same V-cycle as with the
+    matrix-free coarse solve, and the FGMRES solve converges to the direct solution."""
+    orders = hier["orders"]
+    cg = capi_mod.Solver.krylov(b2p_ctx, 0, rel_tol=1e-13, max_it=2000)
+    coarse = capi_mod.Solver.assembled(b2p_ctx, cg, capi_mod.Solver.jacobi(b2p_ctx))
+    assert coarse.assembled_nnz() == -1
+    P = [hier["P"][(a, b)] for a, b in zip(orders[:-1], orders[1:])]
+    G = [hier["G"][p] for p in orders]
+    M = capi_mod.Solver.gmg(b2p_ctx, coarse, P, G, cycle_it=1, smooth_it=1, cheby_order=6, sf_max=1.0, sf_min=0.0, fourth_kind=True)
+    M.gmg_set_operators([hier["A"][p] for p in orders], [hier["AG"][p] for p in orders])
+    assert M.assembled_nnz() >= hier["Aor"][1].tocsr().nnz  # the symbolic pattern keeps structural zeros
+    Mref = _build_gmg(capi_mod, b2p_ctx, hier, True, 6)
+    n = hier["Aor"][3].shape[0]
+    x = np.random.default_rng(12).standard_normal(n)
+    x[hier["nd"][3].ess_dofs] = 0.0
+    y1, y2 = torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty(n, dtype=torch.float64, device="cuda")
+    M.mult(_dev(x), y1)
+    Mref.mult(_dev(x), y2)
+    assert _rel(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-9
+
+    A, Ao = hier["A"][3], hier["Aor"][3]
+    b = np.random.default_rng(11).standard_normal(n)
+    b[hier["nd"][3].ess_dofs] = 0.0
+    K = capi_mod.Solver.krylov(b2p_ctx, 2, rel_tol=1e-10, max_it=60, max_dim=60)
+    K.set_operator(A)
+    K.set_preconditioner(M)
+    xd = torch.zeros(n, dtype=torch.float64, device="cuda")
+    K.mult(_dev(b), xd)
+    st = K.stats()
+    assert st["converged"] and st["its"] <= 25, st
+    assert _rel(xd.cpu().numpy(), spla.spsolve(Ao.tocsc(), b)) < 1e-8
+
+
 def test_multi_gpu_partition_independence():
     """Runs tools/dist_check.py under torchrun on 2 GPUs when the box has them (gpurun --gpus 2)."""
     import os

@@ -93,3 +93,48 @@ def test_tetrahedron_operator_with_curl_oriented_restriction(b2p_ctx, p):
         T = sp.dense_T(e)
         ref[np.ix_(sp.idx[e], sp.idx[e])] += T.T @ Ae[e] @ T
     assert np.abs(got - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+def test_assembled_matrix_as_the_coarse_level_operator(b2p_ctx):
+    """The assembled, eliminated coarse matrix behind the operator interface (b2p_operator_csr): same action and diagonal
+    as the matrix-free ParOperator, and a Jacobi-PCG on it reproduces the sparse direct solution of the oracle matrix —
+    the reference's coarse-level flow (assembled matrix handed to the coarse solver)."""
+    import scipy.sparse.linalg as spla
+
+    from palace_b200 import capi
+
+    prob = common.make_problem(n=(3, 3, 2), p=1, n_attr=2)
+    geom = common.gpu_geom(b2p_ctx, prob)
+    kb = common.coefficient(O.CURLCURL, 2, "matrix")
+    mb = common.coefficient(O.ND_MASS, 2, "matrix", a_mass=1.3)
+    K, M = common.gpu_op(b2p_ctx, geom, prob, O.CURLCURL, kb), common.gpu_op(b2p_ctx, geom, prob, O.ND_MASS, mb)
+    n, ess = prob.nd.ndofs, prob.nd.ess_dofs
+    csr = capi.Csr(b2p_ctx, K)
+    csr.assemble([K, M], [1.0, 0.8])
+    csr.eliminate(ess, 1)
+    Ac = capi.Operator.from_csr(b2p_ctx, csr)
+    Amf = capi.Operator.par(b2p_ctx, n, n, [K, M], [1.0, 0.8], ess_tdofs=ess, diag_policy=1)
+    assert Ac.height == n
+
+    rng = np.random.default_rng(4)
+    x = rng.random(n)
+    y1, y2 = torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty(n, dtype=torch.float64, device="cuda")
+    Ac.mult(_dev(x), y1)
+    Amf.mult(_dev(x), y2)
+    assert np.linalg.norm(y1.cpu().numpy() - y2.cpu().numpy()) < 1e-12 * np.linalg.norm(y2.cpu().numpy())
+    d1, d2 = torch.empty_like(y1), torch.empty_like(y1)
+    Ac.assemble_diagonal(d1)
+    Amf.assemble_diagonal(d2)
+    assert np.abs(d1.cpu().numpy() - d2.cpu().numpy()).max() < 1e-12 * np.abs(d2.cpu().numpy()).max()
+
+    b = rng.random(n)
+    b[ess] = 0.0
+    J = capi.Solver.jacobi(b2p_ctx)
+    J.set_operator(Ac)
+    cg = capi.Solver.krylov(b2p_ctx, 0, rel_tol=1e-12, max_it=500)
+    cg.set_operator(Ac)
+    cg.set_preconditioner(J)
+    xd = torch.zeros(n, dtype=torch.float64, device="cuda")
+    cg.mult(_dev(b), xd)
+    want = spla.spsolve(csr.to_scipy().tocsc(), b)
+    assert np.linalg.norm(xd.cpu().numpy() - want) < 1e-9 * np.linalg.norm(want)
