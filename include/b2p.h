@@ -126,6 +126,9 @@ int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d
  * (ceed::CeedOperatorCoarsen, fem/libceed/operator.cpp:525-585): only space fields of desc are read
  * (p, lsize, idx, orient, dof_map, Bo/Bc/Gc evaluated at the FINE q1d points). */
 int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *coarse_space, b2p_op **out);
+/* The same for dense-basis operators: P, Q, ne, lsize, idx, orient / curl_orient, interp / deriv of the coarse space are
+ * read (tables at the fine operator's Q points); kind and coefficient come from `fine`. */
+int b2p_op_coarsen_dense(b2p_op *fine, const b2p_dense_op_desc *coarse_space, b2p_op **out);
 /* One operator for the real sum  sum_t coefs[t] * A_t  of sum-factorised ND operators over the same geometry, space and
  * essential set (BuildParSumOperator(a0 K + a1 C + a2 M), linalg/rap.cpp:764-829): the terms differ only in their pointwise
  * coefficient, so the sum runs as ONE element-kernel launch (one geometry stream) instead of one per term.

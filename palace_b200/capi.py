@@ -196,7 +196,7 @@ class Op:
         return cls(ctx, h, lsize)
 
     @classmethod
-    def create_dense(cls, ctx, geom, kind, lsize, idx, orient, interp, deriv, coeff, curl_orient=None):
+    def create_dense(cls, ctx, geom, kind, lsize, idx, orient, interp, deriv, coeff, curl_orient=None, fine=None):
         """Dense-basis operator from FULL DofToQuad tables (native dof order)."""
         keep = []
         d = DenseOpDesc()
@@ -210,11 +210,19 @@ class Op:
                 a = _np(arr, dt)
                 keep.append(a)
                 setattr(d, name, _ptr(a))
+        h = C.c_void_p()
+        if fine is not None:
+            _chk(lib().b2p_op_coarsen_dense(fine.h, C.byref(d), C.byref(h)), ctx.h)
+            return cls(ctx, h, lsize)
         c = _np(coeff, np.float64)
         d.coeff_ctx, d.coeff_ctx_bytes = _ptr(c), c.nbytes
-        h = C.c_void_p()
         _chk(lib().b2p_op_create_dense(ctx.h, geom.h, C.byref(d), C.byref(h)), ctx.h)
         return cls(ctx, h, lsize)
+
+    def coarsen_dense(self, lsize, idx, orient, interp, deriv, curl_orient=None):
+        """Coarse level of a dense-basis operator: geometry, kind and coefficient of self, tables and restriction of the coarse
+        space (tabulated at the same quadrature points)."""
+        return Op.create_dense(self.ctx, None, 0, lsize, idx, orient, interp, deriv, None, curl_orient=curl_orient, fine=self)
 
     @classmethod
     def create_sum(cls, ctx, ops, coefs):

@@ -493,10 +493,12 @@ int b2p_op_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_op_desc *d, b2p_op **o
   return B2P_SUCCESS;
 }
 
-// Dense-basis operator on any element type (see b2p_dense.cu).
-int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d, b2p_op **out)
+namespace
 {
-  B2P_CHECK(ctx, ctx && geom && d && out, B2P_ERR_ARG, "b2p_op_create_dense: null argument");
+// Dense-basis operator on any element type (see b2p_dense.cu). With `fine` set, the new operator shares the coefficient of
+// `fine` (the coarse level of a p-hierarchy) instead of reading desc->coeff_ctx.
+int create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d, b2p_op *fine, b2p_op **out)
+{
   B2P_CHECK(ctx, d->kind >= B2P_CURLCURL && d->kind <= B2P_H1_DIFFUSION, B2P_ERR_ARG, "b2p_op_create_dense: bad kind %d", d->kind);
   B2P_CHECK(ctx, geom->q1d == 0 && geom->Q == d->Q && geom->ne == d->ne, B2P_ERR_ARG,
             "b2p_op_create_dense: needs a general geometry (b2p_geom_create_qdata_general) with matching ne / Q");
@@ -541,8 +543,19 @@ int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d
   rd.orient = d->curl_orient ? nullptr : d->orient;  // the tridiagonal matrix already carries the signs
   rd.dof_map = nullptr;                              // native order
   int rc;
+  if (fine)
+  {
+    op->mat = fine->mat;
+    op->emat = fine->emat;
+    op->ecoef = fine->ecoef;
+    op->iso = fine->iso;
+    op->n_mat = fine->n_mat;
+    op->owns_coeff = false;
+    op->parent = fine;
+    fine->refcount++;
+  }
   if ((rc = build_restriction(op, &rd)) || (rc = upload(ctx, T.data(), T.size(), &op->dense_T)) ||
-      (rc = set_coeff(op, d->coeff_ctx, d->coeff_ctx_bytes)))
+      (!fine && (rc = set_coeff(op, d->coeff_ctx, d->coeff_ctx_bytes))))
   {
     b2p_op_destroy(op);
     return rc;
@@ -554,6 +567,26 @@ int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d
   }
   *out = op;
   return B2P_SUCCESS;
+}
+}  // namespace
+
+int b2p_op_create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d, b2p_op **out)
+{
+  B2P_CHECK(ctx, ctx && geom && d && out, B2P_ERR_ARG, "b2p_op_create_dense: null argument");
+  return create_dense(ctx, geom, d, nullptr, out);
+}
+
+// ceed::CeedOperatorCoarsen for dense-basis operators (fem/libceed/operator.cpp:525-585): same quadrature, geometry and
+// coefficient as `fine`, the coarse space's tables (evaluated at the same Q points) and restriction from the descriptor.
+int b2p_op_coarsen_dense(b2p_op *fine, const b2p_dense_op_desc *d, b2p_op **out)
+{
+  B2P_CHECK(fine ? fine->ctx : nullptr, fine && d && out, B2P_ERR_ARG, "b2p_op_coarsen_dense: null argument");
+  b2p_ctx *ctx = fine->ctx;
+  B2P_CHECK(ctx, fine->dense, B2P_ERR_ARG, "b2p_op_coarsen_dense: the fine operator is sum-factorised: use b2p_op_coarsen");
+  B2P_CHECK(ctx, d->P <= fine->P, B2P_ERR_ARG, "b2p_op_coarsen_dense: %d coarse element dofs > %d fine ones", d->P, fine->P);
+  b2p_dense_op_desc dd = *d;
+  dd.kind = fine->kind;
+  return create_dense(ctx, fine->geom, &dd, fine, out);
 }
 
 int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *d, b2p_op **out)

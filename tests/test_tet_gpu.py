@@ -244,3 +244,36 @@ def test_tet_diagonal_is_exact_with_curl_oriented_restriction(b2p_ctx):
         T = sp.dense_T(e)
         np.add.at(ref, sp.idx[e], np.diag(T.T @ Ae[e] @ T))
     assert _rel(d.cpu().numpy(), ref) < RTOL
+
+
+def test_dense_operator_coarsening_shares_the_fine_coefficient(b2p_ctx):
+    """b2p_op_coarsen_dense (ceed::CeedOperatorCoarsen, fem/libceed/operator.cpp:525-585): the p = 1 level built from the p = 2
+    operator acts exactly like a p = 1 operator created with the same geometry and coefficient blob."""
+    from palace_b200 import capi
+
+    mesh = ts.box_tet_mesh((2, 1, 2), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=5, n_attr=2)
+    fine_sp, coarse_sp = ts.build_nd_tet_space(mesh, 2), ts.build_nd_tet_space(mesh, 1)
+    _, _, qpts, qw = ts.nd_tet_tables(2)
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    geom = capi.Geom.general(b2p_ctx, qd)
+    blob = _blob(O.CURLCURL_MASS, 2)
+    fi, fc = ts.nd_tet_element(2).tabulate(qpts)
+    ci, cc = ts.nd_tet_element(1).tabulate(qpts)
+    fine = capi.Op.create_dense(b2p_ctx, geom, O.CURLCURL_MASS, fine_sp.ndofs, fine_sp.idx, None, fi, fc, blob, curl_orient=fine_sp.curl_orient)
+    direct = capi.Op.create_dense(b2p_ctx, geom, O.CURLCURL_MASS, coarse_sp.ndofs, coarse_sp.idx, None, ci, cc, blob,
+                                  curl_orient=coarse_sp.curl_orient)
+    coarse = fine.coarsen_dense(coarse_sp.ndofs, coarse_sp.idx, None, ci, cc, curl_orient=coarse_sp.curl_orient)
+    x = np.random.default_rng(2).random(coarse_sp.ndofs)
+    y1 = torch.empty(coarse_sp.ndofs, dtype=torch.float64, device="cuda")
+    y2 = torch.empty_like(y1)
+    coarse.apply(_dev(x), y1)
+    direct.apply(_dev(x), y2)
+    assert np.linalg.norm(y1.cpu().numpy()) > 0
+    assert np.abs(y1.cpu().numpy() - y2.cpu().numpy()).max() <= 1e-14 * np.abs(y2.cpu().numpy()).max()
+    d1, d2 = torch.zeros_like(y1), torch.zeros_like(y1)
+    coarse.diag_add(d1)
+    direct.diag_add(d2)
+    assert np.abs(d1.cpu().numpy() - d2.cpu().numpy()).max() <= 1e-14 * np.abs(d2.cpu().numpy()).max()
+    fine.close()   # the coarse level keeps the shared coefficient alive
+    coarse.apply(_dev(x), y1)
+    assert np.abs(y1.cpu().numpy() - y2.cpu().numpy()).max() <= 1e-14 * np.abs(y2.cpu().numpy()).max()
