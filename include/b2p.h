@@ -348,9 +348,13 @@ int b2p_vec_cdot(b2p_ctx *ctx, int64_t n, const double *xr, const double *xi, co
 int b2p_vec_caxpy(b2p_ctx *ctx, int64_t n, double ar, double ai, const double *xr, const double *xi, double *yr, double *yi);
 /* A = sum_i (coef_re[i] + i coef_im[i]) * op_i with real partially assembled op_i: ComplexParOperator over
  * BuildParSumOperator / ComplexWrapperOperator (linalg/rap.cpp:481-517,843-919, linalg/operator.cpp:98-134).
- * Single partition only in this round (tsize == lsize). */
+ * Single partition (tsize == lsize); on partitioned spaces use b2p_coperator_wrap over two b2p_operator_par. */
 int b2p_coperator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coef_re,
                       const double *coef_im, const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_coperator **out);
+/* A = Ar + i Ai from two real true-dof operators (either may be NULL, not owned): ComplexWrapperOperator,
+ * linalg/operator.cpp:98-134 — the parts can be ParOperators on PARTITIONED spaces (each with its halo), assembled matrices
+ * (b2p_operator_csr), ... For the complex DIAG_ONE rows give Ar DIAG_ONE and Ai DIAG_ZERO (rap.cpp:481-517). */
+int b2p_coperator_wrap(b2p_ctx *ctx, b2p_operator *Ar, b2p_operator *Ai, b2p_coperator **out);
 int b2p_coperator_mult(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi);
 int b2p_coperator_mult_hermitian_transpose(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi);
 int b2p_coperator_add_mult(b2p_coperator *A, const double *xr, const double *xi, double *yr, double *yi, double ar, double ai);

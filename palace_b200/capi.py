@@ -688,6 +688,15 @@ class ComplexOperator:
         o._keep = list(ops)
         return o
 
+    @classmethod
+    def wrap(cls, ctx, Ar=None, Ai=None):
+        """A = Ar + i Ai from two real true-dof operators (ComplexWrapperOperator): partitioned spaces, assembled matrices, ..."""
+        h = C.c_void_p()
+        _chk(lib().b2p_coperator_wrap(ctx.h, Ar.h if Ar is not None else None, Ai.h if Ai is not None else None, C.byref(h)), ctx.h)
+        o = cls(ctx, h)
+        o._keep = [Ar, Ai]
+        return o
+
     def mult(self, xr, xi, yr, yi):
         _chk(lib().b2p_coperator_mult(self.h, _vp(xr), _vp(xi), _vp(yr), _vp(yi)), self.ctx.h)
 

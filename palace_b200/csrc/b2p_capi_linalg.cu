@@ -22,6 +22,7 @@ struct b2p_solver
 namespace b2p
 {
 Solver *solver_of(b2p_solver *s) { return s ? s->s.get() : nullptr; }
+Operator *operator_of(b2p_operator *A) { return A ? A->op.get() : nullptr; }
 }  // namespace b2p
 
 #define B2P_TRY(ctx, stmt)                                   \

@@ -395,6 +395,66 @@ public:
   int diag_policy;
 };
 
+// ComplexWrapperOperator (linalg/operator.cpp:98-134): A = Ar + i Ai from two REAL true-dof operators, either may be
+// absent. This is the form the reference uses everywhere (ComplexParOperator holds two ParOperators, rap.cpp:481-517): the
+// parts may live on partitioned spaces (their own halo exchange), be assembled matrices, or anything else behind Operator.
+// Essential dofs: give Ar DIAG_ONE and Ai DIAG_ZERO to get the complex DIAG_ONE rows.
+class ComplexWrapperOperator : public ComplexOperator
+{
+  const Operator *Ar, *Ai;
+
+public:
+  ComplexWrapperOperator(b2p_ctx *c, const Operator *ar, const Operator *ai) : ComplexOperator(c, (ar ? ar : ai)->Height()), Ar(ar), Ai(ai) {}
+  void apply(CCPtr x, CPtr y, bool herm) const
+  {
+    const double si = herm ? -1.0 : 1.0;  // A^H = Ar^T - i Ai^T
+    if (Ar)
+    {
+      if (herm)
+      {
+        Ar->MultTranspose(x.re, y.re);
+        Ar->MultTranspose(x.im, y.im);
+      }
+      else
+      {
+        Ar->Mult(x.re, y.re);
+        Ar->Mult(x.im, y.im);
+      }
+    }
+    else
+    {
+      vec::set(ctx, y.re, n, 0.0);
+      vec::set(ctx, y.im, n, 0.0);
+    }
+    if (Ai)
+    {
+      if (herm)
+      {
+        Ai->AddMultTranspose(x.im, y.re, -si);
+        Ai->AddMultTranspose(x.re, y.im, si);
+      }
+      else
+      {
+        Ai->AddMult(x.im, y.re, -si);
+        Ai->AddMult(x.re, y.im, si);
+      }
+    }
+  }
+  void Mult(CCPtr x, CPtr y) const override { apply(x, y, false); }
+  void MultHermitianTranspose(CCPtr x, CPtr y) const override { apply(x, y, true); }
+  void AssembleDiagonal(CPtr d) const override
+  {
+    if (Ar)
+      Ar->AssembleDiagonal(d.re);
+    else
+      vec::set(ctx, d.re, n, 0.0);
+    if (Ai)
+      Ai->AssembleDiagonal(d.im);
+    else
+      vec::set(ctx, d.im, n, 0.0);
+  }
+};
+
 // ------------------------------------------------------------------------------------ complex solvers
 class ComplexSolver
 {
@@ -746,6 +806,7 @@ struct b2p_solver;
 namespace b2p
 {
 Solver *solver_of(b2p_solver *s);
+Operator *operator_of(b2p_operator *A);
 }
 
 struct b2p_coperator
@@ -786,11 +847,23 @@ int b2p_vec_caxpy(b2p_ctx *ctx, int64_t n, double ar, double ai, const double *x
   return B2P_SUCCESS;
 }
 
+int b2p_coperator_wrap(b2p_ctx *ctx, b2p_operator *Ar, b2p_operator *Ai, b2p_coperator **out)
+{
+  B2P_CHECK(ctx, ctx && out && (Ar || Ai), B2P_ERR_ARG, "b2p_coperator_wrap: Empty ComplexOperator");
+  const Operator *ar = operator_of(Ar), *ai = operator_of(Ai);
+  B2P_CHECK(ctx, !ar || !ai || (ar->Height() == ai->Height() && ar->Width() == ai->Width()), B2P_ERR_ARG,
+            "b2p_coperator_wrap: mismatch in dimension of real and imaginary matrix parts");
+  B2P_CHECK(ctx, (ar ? ar : ai)->Height() == (ar ? ar : ai)->Width(), B2P_ERR_ARG, "b2p_coperator_wrap: square operators only");
+  auto *h = new b2p_coperator;
+  h->op = std::make_unique<ComplexWrapperOperator>(ctx, ar, ai);
+  *out = h;
+  return B2P_SUCCESS;
+}
 int b2p_coperator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coef_re,
                       const double *coef_im, const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_coperator **out)
 {
   B2P_CHECK(ctx, ctx && out && n_terms > 0 && ops && coef_re && coef_im, B2P_ERR_ARG, "b2p_coperator_par: bad argument");
-  B2P_CHECK(ctx, tsize == lsize, B2P_ERR_UNSUPPORTED, "b2p_coperator_par: partitioned complex operators are not implemented yet");
+  B2P_CHECK(ctx, tsize == lsize, B2P_ERR_UNSUPPORTED, "b2p_coperator_par: single partition only; on partitioned spaces wrap two b2p_operator_par with b2p_coperator_wrap");
   std::vector<ComplexParOperator::Term> terms;
   for (int i = 0; i < n_terms; i++)
   {

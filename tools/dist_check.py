@@ -101,6 +101,20 @@ def main():
     dot = capi.vec_dot(ctx, xd, yd)
     err_dot = abs(dot - float(x @ y_ref)) / abs(float(x @ y_ref))
 
+    # ---- complex operator on the partitioned space: A + 0.3i A0 as a wrapper of two real ParOperators ----
+    Ai = capi.Operator.par(ctx, lnd[p].n_true, lnd[p].lsize, [A[p].local_op], [0.3], lnd[p].ess_tdofs, 0, hnd[p])
+    W = capi.ComplexOperator.wrap(ctx, A[p], Ai)
+    A0 = common.oracle_matrix(prob, O.CURLCURL_MASS, blob, space=nd[p], eliminate=False).tolil()
+    A0[nd[p].ess_dofs, :] = 0
+    A0[:, nd[p].ess_dofs] = 0
+    xi = np.random.default_rng(2).standard_normal(nd[p].ndofs)
+    xid = torch.from_numpy(xi[own]).cuda()
+    zr, zi = torch.empty_like(xd), torch.empty_like(xd)
+    W.mult(xd, xid, zr, zi)
+    torch.cuda.synchronize()
+    z_ref = Ao @ (x + 1j * xi) + 0.3j * (A0.tocsr() @ (x + 1j * xi))
+    err_cplx = float(np.abs(zr.cpu().numpy() + 1j * zi.cpu().numpy() - z_ref[own]).max() / np.abs(z_ref).max())
+
     # ---- FGMRES + GMG, distributed ----
     def interp(in_ls, in_h, out_ls, out_h, comps):
         it = capi.Interp(ctx, asm.space_dict(in_ls.space), asm.space_dict(out_ls.space), comps)
@@ -128,13 +142,13 @@ def main():
 
     x_ref = spla.spsolve(Ao.tocsc(), b)
     err_solve = float(np.linalg.norm(sol.cpu().numpy() - x_ref[own]) / np.linalg.norm(x_ref))
-    errs = torch.tensor([err_apply, err_dot, err_solve], dtype=torch.float64, device="cuda")
+    errs = torch.tensor([err_apply, err_dot, err_solve, err_cplx], dtype=torch.float64, device="cuda")
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     errs = errs.cpu().numpy()
     if rank == 0:
         print(f"DIST_CHECK world={world} apply_err={errs[0]:.2e} dot_err={errs[1]:.2e} solve_err={errs[2]:.2e} "
-              f"fgmres_its={st['its']} converged={st['converged']}", flush=True)
-    assert errs[0] < 1e-12 and errs[1] < 1e-12 and errs[2] < 1e-8 and st["converged"], errs
+              f"fgmres_its={st['its']} converged={st['converged']} complex_apply_err={errs[3]:.2e}", flush=True)
+    assert errs[0] < 1e-12 and errs[1] < 1e-12 and errs[2] < 1e-8 and errs[3] < 1e-12 and st["converged"], errs
     if rank == 0:
         print("DIST_CHECK OK", flush=True)
     dist.destroy_process_group()
