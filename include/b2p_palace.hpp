@@ -139,6 +139,18 @@ public:
   }
 };
 
+// The multigrid's coarse solver on the device-assembled level-0 matrix: MfemWrapperSolver<Operator> (palace/linalg/solver.hpp:
+// 67-110, solver.cpp:13-30) with a Krylov method (and its preconditioner) from this library inside instead of HYPRE. The
+// handles `krylov` and `pc` are consumed; SetOperator assembles the ParOperator it is given.
+inline std::unique_ptr<SolverAdapter> MakeAssembledCoarseSolver(b2p_ctx *ctx, b2p_solver *krylov, b2p_solver *pc)
+{
+  b2p_solver *S = nullptr;
+  Check(b2p_solver_assembled(ctx, krylov, pc, &S), ctx);
+  b2p_solver_destroy(krylov);
+  if (pc) b2p_solver_destroy(pc);
+  return std::make_unique<SolverAdapter>(ctx, S);
+}
+
 // palace::ComplexOperator interface (palace/linalg/operator.hpp:24-68) on two mfem::Vectors per complex vector
 // (palace/linalg/vector.hpp:23-27).
 class ComplexParOperatorAdapter
@@ -155,6 +167,13 @@ public:
     Check(b2p_coperator_par(ctx, tsize, lsize, (int)ops.size(), ops.data(), coef_re.data(), coef_im.data(), dbc.HostRead(), dbc.Size(),
                             diag_policy, &A),
           ctx);
+  }
+  // The reference's own ComplexParOperator(Ar, Ai) form over two real adapters (rap.hpp:123-150): this is the one for
+  // PARTITIONED spaces (each part runs its halo exchange); give Ar DIAG_ONE and Ai DIAG_ZERO. Either part may be null.
+  ComplexParOperatorAdapter(b2p_ctx *ctx, const ParOperatorAdapter *Ar, const ParOperatorAdapter *Ai)
+    : ctx(ctx), n((Ar ? Ar : Ai)->Height())
+  {
+    Check(b2p_coperator_wrap(ctx, Ar ? Ar->Handle() : nullptr, Ai ? Ai->Handle() : nullptr, &A), ctx);
   }
   ~ComplexParOperatorAdapter() { b2p_coperator_destroy(A); }
   b2p_coperator *Handle() const { return A; }
