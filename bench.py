@@ -220,6 +220,7 @@ def run_experiments(args):
         "solver_loop_p3_2M": (["tools/solver_bench.py"], {}),
         "solver_loop_p3_2M_all_opt_ins": (["tools/solver_bench.py"], {"B2P_COARSE_CG_CHECK": "8", "B2P_INTERP_OWNER": "1", "B2P_PDL": "1",
                                                                      "B2P_ND_FWDCHAIN": "1"}),
+        "solver_loop_p3_2M_assembled_coarse_level": (["tools/solver_bench.py"], {"B2P_COARSE_ASSEMBLED": "1"}),
         "tet_dense_p3": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {}),
         "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {"B2P_DENSE_NT": "4"}),
     }
@@ -228,6 +229,7 @@ def run_experiments(args):
                  "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--n", "3", "--steps", "2"], {}),
                  "solver_loop_p3_2M_all_opt_ins": (["tools/solver_bench.py", "--n", "3"], {"B2P_COARSE_CG_CHECK": "8", "B2P_INTERP_OWNER": "1",
                                                                                           "B2P_PDL": "1", "B2P_ND_FWDCHAIN": "1"}),
+                 "solver_loop_p3_2M_assembled_coarse_level": (["tools/solver_bench.py", "--n", "3"], {"B2P_COARSE_ASSEMBLED": "1"}),
                  "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "2", "--n", "2", "--steps", "2"], {"B2P_DENSE_NT": "4"})}
     for name, (cmd, env) in tools.items():
         if time.time() - t_start > budget_s:

@@ -38,9 +38,13 @@ def main():
     P = [capi.Operator.interp(ctx, capi.Interp(ctx, asm.space_dict(nd[x]), asm.space_dict(nd[y]), asm.nd_prolongation_comps(x, y))) for x, y in zip(orders[:-1], orders[1:])]
     torch.cuda.synchronize(); t_ops = time.time() - t0
     t0 = time.time()
-    coarse = capi.Solver.krylov(ctx, capi.CG, rel_tol=a.coarse_tol, max_it=500); cj = capi.Solver.jacobi(ctx); cj.set_operator(A[orders[0]])
-    coarse.set_preconditioner(cj); coarse.set_operator(A[orders[0]])
+    coarse = capi.Solver.krylov(ctx, capi.CG, rel_tol=a.coarse_tol, max_it=500); cj = capi.Solver.jacobi(ctx)
     coarse.set_check_interval(int(os.environ.get("B2P_COARSE_CG_CHECK", "1")))  # > 1: CG scalars stay on the device
+    assembled = os.environ.get("B2P_COARSE_ASSEMBLED", "0") == "1"
+    if assembled:  # PCG on the device-assembled p = 1 matrix (MfemWrapperSolver flow) instead of the matrix-free coarse operator
+        coarse = capi.Solver.assembled(ctx, coarse, cj)
+    else:
+        cj.set_operator(A[orders[0]]); coarse.set_preconditioner(cj); coarse.set_operator(A[orders[0]])
     mg = capi.Solver.gmg(ctx, coarse, P, G, cycle_it=1, smooth_it=1, cheby_order=corder)
     mg.gmg_set_operators([A[q] for q in orders], [AG[q] for q in orders])
     torch.cuda.synchronize(); t_setup = time.time() - t0
@@ -64,5 +68,5 @@ def main():
     A[p].mult(x, y); res = float(torch.linalg.norm(y - b) / torch.linalg.norm(b))
     print(json.dumps({"dofs": n, "orders": orders, "cheby_order": corder, "host_mesh_space_s": t_host, "operator_create_s": t_ops, "smoother_setup_s": t_setup,
                       "nd_apply_ms": t_apply, "h1_apply_ms": t_h1, "G_ms": t_G, "Gt_ms": t_Gt, "P_ms": t_P, "Pt_ms": t_Pt, "dot_ms": t_dot, "axpby_ms": t_axpy,
-                      "vcycle_ms": t_vc, "fgmres_its": st["its"], "solve_s": t_solve, "true_rel_residual": res, "converged": st["converged"]}))
+                      "vcycle_ms": t_vc, "coarse_level": ("assembled_csr nnz=%d" % mg.assembled_nnz()) if assembled else "matrix_free", "fgmres_its": st["its"], "solve_s": t_solve, "true_rel_residual": res, "converged": st["converged"]}))
 main()
