@@ -21,6 +21,7 @@ B2P_DENSE_NT=4 timeout 300 python -m pytest tests/test_dense_gpu.py tests/test_t
 # solver loop: reference CG vs device-scalar CG on the coarse level
 timeout 300 python tools/solver_bench.py > gpurun_out/solver_bench.json 2> gpurun_out/solver_bench.err
 B2P_COARSE_CG_CHECK=8 timeout 300 python tools/solver_bench.py > gpurun_out/solver_bench_devcg.json 2>> gpurun_out/solver_bench.err
+B2P_COARSE_ASSEMBLED=1 timeout 300 python tools/solver_bench.py > gpurun_out/solver_bench_assembled_coarse.json 2>> gpurun_out/solver_bench.err
 # BASELINE configs 0 / 2 on the reference's cylinder mesh (level 0 is compared with the reference's stored eig.csv)
 timeout 300 python tools/cylinder_bench.py --order 4 --refine 0 --nev 6 > gpurun_out/cylinder_p4_l0.json 2> gpurun_out/cylinder.err
 timeout 600 python tools/cylinder_bench.py --order 4 --refine 2 --nev 4 --tol 1e-8 > gpurun_out/cylinder_p4_l2.json 2>> gpurun_out/cylinder.err
