@@ -223,6 +223,8 @@ def run_experiments(args):
         "solver_loop_p3_2M_assembled_coarse_level": (["tools/solver_bench.py"], {"B2P_COARSE_ASSEMBLED": "1"}),
         "tet_dense_p3": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {}),
         "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {"B2P_DENSE_NT": "4"}),
+        "cylinder_cavity_p4_assembled_coarse_level": (["tools/cylinder_bench.py", "--order", "4", "--refine", "0", "--nev", "4"],
+                                                      {"B2P_COARSE_ASSEMBLED": "1"}),
     }
     if os.environ.get("B2P_BENCH_CHILD"):  # CPU dry run: tiny sizes
         tools = {"cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "1", "--nev", "1", "--tol", "1e-6"], {}),

@@ -84,10 +84,13 @@ def main():
     P = [common.gpu_interp(ctx, nd[a], nd[b], asm.nd_prolongation_comps(a, b)) for a, b in zip(orders[:-1], orders[1:])]
     coarse = capi.Solver.krylov(ctx, capi.CG, rel_tol=1e-10, max_it=5000)
     cj = capi.Solver.jacobi(ctx)
-    cj.set_operator(Pl[orders[0]])
-    coarse.set_preconditioner(cj)
     coarse.set_check_interval(int(os.environ.get("B2P_COARSE_CG_CHECK", "8")))  # device-resident CG scalars
-    coarse.set_operator(Pl[orders[0]])
+    if os.environ.get("B2P_COARSE_ASSEMBLED", "0") == "1":  # PCG on the device-assembled p = 1 matrix (MfemWrapperSolver flow)
+        coarse = capi.Solver.assembled(ctx, coarse, cj)
+    else:
+        cj.set_operator(Pl[orders[0]])
+        coarse.set_preconditioner(cj)
+        coarse.set_operator(Pl[orders[0]])
     mg = capi.Solver.gmg(ctx, coarse, P, G, cycle_it=1, smooth_it=1, cheby_order=6)
     mg.gmg_set_operators([Pl[q] for q in orders], [AG[q] for q in orders])
     ksp = capi.Solver.krylov(ctx, capi.FGMRES, rel_tol=args.tol, max_it=300, max_dim=300)
