@@ -57,6 +57,8 @@ void set_random(b2p_ctx *c, double *y, int64_t n, uint64_t seed);               
 // Chebyshev fused updates (chebyshev.cpp:70-156 plus the y += d the reference does separately)
 void cheb_first(b2p_ctx *c, double sr, const double *dinv, const double *r, double *d, int64_t n);
 void cheb_next(b2p_ctx *c, double sd, double sr, const double *dinv, const double *r, double *d, int64_t n);
+void cheb_first_y(b2p_ctx *c, double sr, const double *dinv, const double *r, double *d, double *y, bool assign, int64_t n);
+void cheb_next_y(b2p_ctx *c, double sd, double sr, const double *dinv, const double *r, double *d, double *y, int64_t n);
 // Global reductions: local device reduction (deterministic order) + NCCL all-reduce + one host sync.
 double dot(b2p_ctx *c, const double *x, const double *y, int64_t n);
 double sum(b2p_ctx *c, const double *x, int64_t n);
@@ -78,6 +80,8 @@ public:
   virtual void AddMult(const double *x, double *y, double a = 1.0) const;           // default: temp + axpy
   virtual void AddMultTranspose(const double *x, double *y, double a = 1.0) const;
   virtual void AssembleDiagonal(double *d) const;
+  // true: AddMult accumulates straight into y (no temporary): r = x - A y is then a copy plus one AddMult
+  virtual bool NativeAddMult() const { return false; }
   int64_t Height() const { return height; }
   int64_t Width() const { return width; }
 
@@ -132,6 +136,7 @@ public:
   ~ParOperator() override;
   void Mult(const double *x, double *y) const override;
   void AddMult(const double *x, double *y, double a = 1.0) const override;
+  bool NativeAddMult() const override { return halo == nullptr; }
   void AssembleDiagonal(double *d) const override;
   void SetInteriorElements(int n) { ne_interior = n; }  // elements [0, n) touch no ghost dof
   // The eliminated sum as one device CSR matrix (ParOperator::ParallelAssemble, rap.cpp:84-152; coarse levels, single

@@ -368,50 +368,64 @@ void ChebyshevSmoother::SetOperator(const Operator &op)
   }
 }
 
+namespace
+{
+// r = x - A y. With a native AddMult this is a copy and one accumulating apply (no zero fill of r, no separate subtraction
+// pass); otherwise Mult followed by r = x - r.
+inline void Residual(b2p_ctx *ctx, const Operator &A, const double *x, const double *y, double *r, int64_t n)
+{
+  if (A.NativeAddMult())
+  {
+    vec::copy(ctx, r, x, n);
+    A.AddMult(y, r, -1.0);
+  }
+  else
+  {
+    A.Mult(y, r);
+    vec::axpby(ctx, 1.0, x, -1.0, r, n);
+  }
+}
+}  // namespace
+
 // chebyshev.cpp:191-220 and :261-293: y = y + p(D^-1 A) D^-1 (x - A y)
 void ChebyshevSmoother::Mult2(const double *x, double *y, double *r) const
 {
+  // chebyshev.cpp:190-220 (4th kind) / :260-293 (1st kind). Same recurrences; the vector work is arranged so that every
+  // step is ONE operator apply and ONE pass over the vectors: r = x - A y accumulates into a copy of x (no zero fill, no
+  // separate subtraction), and y += d is folded into the kernel that produces d.
   const int64_t n = height;
   for (int it = 0; it < pc_it; it++)
   {
-    if (initial_guess || it > 0)
-    {
-      A->Mult(y, r);
-      vec::axpby(ctx, 1.0, x, -1.0, r, n);
-    }
-    else
-    {
+    const bool fresh = !(initial_guess || it > 0);  // y == 0: r = x, and the first update assigns y
+    if (fresh)
       vec::copy(ctx, r, x, n);
-      vec::set(ctx, y, n, 0.0);
-    }
+    else
+      Residual(ctx, *A, x, y, r, n);
     if (fourth_kind)
     {
-      vec::cheb_first(ctx, 4.0 / (3.0 * lambda_max), dinv.p, r, d.p, n);
+      vec::cheb_first_y(ctx, 4.0 / (3.0 * lambda_max), dinv.p, r, d.p, y, fresh, n);
       for (int k = 1; k < order; k++)
       {
-        vec::axpy(ctx, 1.0, d.p, y, n);
         A->AddMult(d.p, r, -1.0);
         const double sd = (2.0 * k - 1.0) / (2.0 * k + 3.0);
         const double sr = (8.0 * k + 4.0) / ((2.0 * k + 3.0) * lambda_max);
-        vec::cheb_next(ctx, sd, sr, dinv.p, r, d.p, n);
+        vec::cheb_next_y(ctx, sd, sr, dinv.p, r, d.p, y, n);
       }
     }
     else
     {
-      vec::cheb_first(ctx, 1.0 / theta, dinv.p, r, d.p, n);
+      vec::cheb_first_y(ctx, 1.0 / theta, dinv.p, r, d.p, y, fresh, n);
       double rhop = delta / theta;
       for (int k = 1; k < order; k++)
       {
-        vec::axpy(ctx, 1.0, d.p, y, n);
         A->AddMult(d.p, r, -1.0);
         const double rho = 1.0 / (2.0 * theta / delta - rhop);
         const double sd = rho * rhop;
         const double sr = 2.0 * rho / delta;
-        vec::cheb_next(ctx, sd, sr, dinv.p, r, d.p, n);
+        vec::cheb_next_y(ctx, sd, sr, dinv.p, r, d.p, y, n);
         rhop = rho;
       }
     }
-    vec::axpy(ctx, 1.0, d.p, y, n);
   }
 }
 
@@ -451,8 +465,7 @@ void DistRelaxationSmoother::Mult2(const double *x, double *y, double *r) const
   {
     B->SetInitialGuess(initial_guess || it > 0);
     B->Mult2(x, y, r);
-    A->Mult(y, r);
-    vec::axpby(ctx, 1.0, x, -1.0, r, height);
+    Residual(ctx, *A, x, y, r, height);
     G->MultTranspose(r, x_G.p);
     if (A_G->NumEssential() > 0) vec::set_sub(ctx, x_G.p, A_G->EssentialTrueDofs(), A_G->NumEssential(), 0.0);
     B_G->Mult2(x_G.p, y_G.p, r_G.p);
@@ -467,8 +480,7 @@ void DistRelaxationSmoother::MultTranspose2(const double *x, double *y, double *
   {
     if (initial_guess || it > 0)
     {
-      A->Mult(y, r);
-      vec::axpby(ctx, 1.0, x, -1.0, r, height);
+      Residual(ctx, *A, x, y, r, height);
       G->MultTranspose(r, x_G.p);
     }
     else
@@ -538,13 +550,11 @@ void GeometricMultigridSolver::VCycle(int l, bool initial_guess_) const
     return;
   }
   B[l]->Mult2(X[l].p, Y[l].p, R[l].p);
-  A[l]->Mult(Y[l].p, R[l].p);
-  vec::axpby(ctx, 1.0, X[l].p, -1.0, R[l].p, A[l]->Height());
+  Residual(ctx, *A[l], X[l].p, Y[l].p, R[l].p, A[l]->Height());
   P[l - 1]->MultTranspose(R[l].p, X[l - 1].p);
   if (A[l - 1]->NumEssential() > 0) vec::set_sub(ctx, X[l - 1].p, A[l - 1]->EssentialTrueDofs(), A[l - 1]->NumEssential(), 0.0);
   VCycle(l - 1, false);
-  P[l - 1]->Mult(Y[l - 1].p, R[l].p);
-  vec::axpy(ctx, 1.0, R[l].p, Y[l].p, A[l]->Height());
+  P[l - 1]->AddMult(Y[l - 1].p, Y[l].p, 1.0);  // y += P y_c in one pass (no temporary, no zero fill)
   B[l]->SetInitialGuess(true);
   B[l]->MultTranspose2(X[l].p, Y[l].p, R[l].p);
 }

@@ -267,6 +267,31 @@ void cheb_next(b2p_ctx *c, double sd, double sr, const double *dinv, const doubl
   launch_ew(c, n, [=] __device__(int64_t i) { d[i] = sd * d[i] + sr * dinv[i] * r[i]; });
 }
 
+// The same with the solution update folded in (one pass instead of cheb_* followed by y += d): y = d or y += d.
+void cheb_first_y(b2p_ctx *c, double sr, const double *dinv, const double *r, double *d, double *y, bool assign, int64_t n)
+{
+  if (assign)
+    launch_ew(c, n, [=] __device__(int64_t i) {
+      const double di = sr * dinv[i] * r[i];
+      d[i] = di;
+      y[i] = di;
+    });
+  else
+    launch_ew(c, n, [=] __device__(int64_t i) {
+      const double di = sr * dinv[i] * r[i];
+      d[i] = di;
+      y[i] += di;
+    });
+}
+void cheb_next_y(b2p_ctx *c, double sd, double sr, const double *dinv, const double *r, double *d, double *y, int64_t n)
+{
+  launch_ew(c, n, [=] __device__(int64_t i) {
+    const double di = sd * d[i] + sr * dinv[i] * r[i];
+    d[i] = di;
+    y[i] += di;
+  });
+}
+
 void multi_dot(b2p_ctx *c, int m, const double *const *V, const double *w, int64_t n, double *out)
 {
   for (int j0 = 0; j0 < m; j0 += MAXM)

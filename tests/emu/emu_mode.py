@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "libb2p_emu.so")
+LIB = os.environ.get("B2P_EMU_LIB") or os.path.join(HERE, "libb2p_emu.so")
 
 
 def build():
