@@ -276,6 +276,11 @@ public:
 
 private:
   void VCycle(int l, bool initial_guess) const;
+  // the finest level works on the caller's vectors directly (x is only read there, y is the iterate): no copies in / out
+  mutable const double *x_top = nullptr;
+  mutable double *y_top = nullptr;
+  const double *Xp(int l) const { return l + 1 == (int)A.size() ? x_top : X[l].p; }
+  double *Yp(int l) const { return l + 1 == (int)A.size() ? y_top : Y[l].p; }
 };
 
 enum class KspType { CG = 0, GMRES = 1, FGMRES = 2 };

@@ -536,9 +536,9 @@ void GeometricMultigridSolver::SetOperators(const std::vector<const ParOperator 
 void GeometricMultigridSolver::Mult(const double *x, double *y) const
 {
   const int n_levels = (int)A.size();
-  vec::copy(ctx, X.back().p, x, height);
+  x_top = x;
+  y_top = y;
   for (int it = 0; it < pc_it; it++) VCycle(n_levels - 1, it > 0);
-  vec::copy(ctx, y, Y.back().p, height);
 }
 // gmg.cpp:172-205
 void GeometricMultigridSolver::VCycle(int l, bool initial_guess_) const
@@ -546,17 +546,17 @@ void GeometricMultigridSolver::VCycle(int l, bool initial_guess_) const
   B[l]->SetInitialGuess(initial_guess_);
   if (l == 0)
   {
-    B[l]->Mult(X[l].p, Y[l].p);
+    B[l]->Mult(Xp(l), Yp(l));
     return;
   }
-  B[l]->Mult2(X[l].p, Y[l].p, R[l].p);
-  Residual(ctx, *A[l], X[l].p, Y[l].p, R[l].p, A[l]->Height());
+  B[l]->Mult2(Xp(l), Yp(l), R[l].p);
+  Residual(ctx, *A[l], Xp(l), Yp(l), R[l].p, A[l]->Height());
   P[l - 1]->MultTranspose(R[l].p, X[l - 1].p);
   if (A[l - 1]->NumEssential() > 0) vec::set_sub(ctx, X[l - 1].p, A[l - 1]->EssentialTrueDofs(), A[l - 1]->NumEssential(), 0.0);
   VCycle(l - 1, false);
-  P[l - 1]->AddMult(Y[l - 1].p, Y[l].p, 1.0);  // y += P y_c in one pass (no temporary, no zero fill)
+  P[l - 1]->AddMult(Y[l - 1].p, Yp(l), 1.0);  // y += P y_c in one pass (no temporary, no zero fill)
   B[l]->SetInitialGuess(true);
-  B[l]->MultTranspose2(X[l].p, Y[l].p, R[l].p);
+  B[l]->MultTranspose2(Xp(l), Yp(l), R[l].p);
 }
 
 // ------------------------------------------------------------------------------------ Krylov (iterative.cpp)
