@@ -269,11 +269,11 @@ def test_dense_operator_coarsening_shares_the_fine_coefficient(b2p_ctx):
     coarse.apply(_dev(x), y1)
     direct.apply(_dev(x), y2)
     assert np.linalg.norm(y1.cpu().numpy()) > 0
-    assert np.abs(y1.cpu().numpy() - y2.cpu().numpy()).max() <= 1e-14 * np.abs(y2.cpu().numpy()).max()
+    assert np.abs(y1.cpu().numpy() - y2.cpu().numpy()).max() <= 1e-13 * np.abs(y2.cpu().numpy()).max()
     d1, d2 = torch.zeros_like(y1), torch.zeros_like(y1)
     coarse.diag_add(d1)
     direct.diag_add(d2)
-    assert np.abs(d1.cpu().numpy() - d2.cpu().numpy()).max() <= 1e-14 * np.abs(d2.cpu().numpy()).max()
+    assert np.abs(d1.cpu().numpy() - d2.cpu().numpy()).max() <= 1e-13 * np.abs(d2.cpu().numpy()).max()
     fine.close()   # the coarse level keeps the shared coefficient alive
     coarse.apply(_dev(x), y1)
-    assert np.abs(y1.cpu().numpy() - y2.cpu().numpy()).max() <= 1e-14 * np.abs(y2.cpu().numpy()).max()
+    assert np.abs(y1.cpu().numpy() - y2.cpu().numpy()).max() <= 1e-13 * np.abs(y2.cpu().numpy()).max()
