@@ -370,6 +370,9 @@ void b2p_coperator_destroy(b2p_coperator *A);
  * "PCMatReal" configuration (models/spaceoperator.cpp:1098-1105, utils/configfile.hpp:1051). */
 int b2p_csolver_real_pc(b2p_ctx *ctx, b2p_solver *real_pc, b2p_csolver **out);
 /* CgSolver / GmresSolver / FgmresSolver<ComplexOperator> (linalg/iterative.cpp:361-871; type 0/1/2) */
+/* JacobiSmoother<ComplexOperator> (linalg/jacobi.cpp:75-105): y = omega D^-1 x with the complex diagonal of the operator given to
+ * b2p_csolver_set_operator; omega != 0. The preconditioner of the complex-valued (PCMatReal = false) path. */
+int b2p_csolver_jacobi(b2p_ctx *ctx, double omega, b2p_csolver **out);
 int b2p_csolver_krylov(b2p_ctx *ctx, int type, b2p_csolver **out);
 int b2p_csolver_krylov_config(b2p_csolver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side);
 int b2p_csolver_set_operator(b2p_csolver *s, b2p_coperator *A);

@@ -735,6 +735,12 @@ class ComplexSolver:
         return s
 
     @classmethod
+    def jacobi(cls, ctx, omega=1.0):
+        h = C.c_void_p()
+        _chk(lib().b2p_csolver_jacobi(ctx.h, C.c_double(omega), C.byref(h)), ctx.h)
+        return cls(ctx, h)
+
+    @classmethod
     def krylov(cls, ctx, kind, rel_tol=1e-6, abs_tol=0.0, max_it=100, max_dim=-1, orthog=MGS, pc_side=PC_RIGHT):
         h = C.c_void_p()
         _chk(lib().b2p_csolver_krylov(ctx.h, int(kind), C.byref(h)), ctx.h)

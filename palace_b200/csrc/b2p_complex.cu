@@ -105,6 +105,28 @@ __global__ void cmulti_axpy_kernel(CVecList V, const double *__restrict__ coef, 
   }
 }
 
+// dinv = omega / d (complex reciprocal of the assembled diagonal, jacobi.cpp:75-96)
+__global__ void creciprocal_kernel(double *__restrict__ dr, double *__restrict__ di, double omega, int64_t n)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+  {
+    const double a = dr[i], b = di[i], m = a * a + b * b;
+    dr[i] = omega * a / m;
+    di[i] = -omega * b / m;
+  }
+}
+// y = dinv * x (jacobi.cpp:47-63) or y = conj(dinv) * x (transpose branch, :64-72)
+__global__ void cdiag_mult_kernel(const double *__restrict__ dr, const double *__restrict__ di, const double *__restrict__ xr,
+                                  const double *__restrict__ xi, double *__restrict__ yr, double *__restrict__ yi, double sgn, int64_t n)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+  {
+    const double a = dr[i], b = sgn * di[i], u = xr[i], v = xi[i];
+    yr[i] = a * u - b * v;
+    yi[i] = b * u + a * v;
+  }
+}
+
 inline int grid_for(b2p_ctx *c, int64_t n)
 {
   const int64_t want = (n + 2 * NT - 1) / (2 * NT), cap = (int64_t)c->sm_count * 8;
@@ -464,6 +486,32 @@ public:
   ComplexSolver(b2p_ctx *c) : ctx(c) {}
   virtual ~ComplexSolver() = default;
   virtual void Mult(CCPtr x, CPtr y) const = 0;
+  virtual bool SetOperator(const ComplexOperator &) { return false; }  // false: this solver takes no operator
+};
+
+// JacobiSmoother<ComplexOperator> (jacobi.cpp:75-105): y = omega D^-1 x with the COMPLEX assembled diagonal; the smoother and
+// simplest preconditioner of the complex-valued (PCMatReal = false, the reference's default) path.
+class ComplexJacobiSmoother : public ComplexSolver
+{
+  double omega;
+  mutable DVec dinv;
+  int64_t n = 0;
+
+public:
+  ComplexJacobiSmoother(b2p_ctx *c, double omega_) : ComplexSolver(c), omega(omega_) {}
+  bool SetOperator(const ComplexOperator &op) override
+  {
+    n = op.n;
+    dinv.resize(ctx, 2 * n);
+    op.AssembleDiagonal(CPtr{dinv.p, dinv.p + n});
+    B2P_LAUNCH(creciprocal_kernel, grid_for(ctx, n), NT, 0, ctx->stream, dinv.p, dinv.p + n, omega, n);
+    return true;
+  }
+  void Mult(CCPtr x, CPtr y) const override
+  {
+    B2P_LAUNCH(cdiag_mult_kernel, grid_for(ctx, n), NT, 0, ctx->stream, (const double *)dinv.p, (const double *)(dinv.p + n), x.re, x.im,
+               y.re, y.im, 1.0, n);
+  }
 };
 
 // PCMatReal: the (real) preconditioner acts on real and imaginary parts separately.
@@ -921,6 +969,15 @@ int b2p_csolver_real_pc(b2p_ctx *ctx, b2p_solver *real_pc, b2p_csolver **out)
   *out = h;
   return B2P_SUCCESS;
 }
+int b2p_csolver_jacobi(b2p_ctx *ctx, double omega, b2p_csolver **out)
+{
+  B2P_CHECK(ctx, ctx && out, B2P_ERR_ARG, "b2p_csolver_jacobi: bad argument");
+  B2P_CHECK(ctx, omega != 0.0, B2P_ERR_UNSUPPORTED, "b2p_csolver_jacobi: give the damping factor (the estimated optimum, omega == 0, is not built)");
+  auto *h = new b2p_csolver;
+  h->s = std::make_unique<ComplexJacobiSmoother>(ctx, omega);
+  *out = h;
+  return B2P_SUCCESS;
+}
 int b2p_csolver_krylov(b2p_ctx *ctx, int type, b2p_csolver **out)
 {
   B2P_CHECK(ctx, type >= 0 && type <= 2 && out, B2P_ERR_ARG, "b2p_csolver_krylov: type must be 0 (CG), 1 (GMRES) or 2 (FGMRES)");
@@ -943,10 +1000,16 @@ int b2p_csolver_krylov_config(b2p_csolver *s, double rel_tol, double abs_tol, in
 }
 int b2p_csolver_set_operator(b2p_csolver *s, b2p_coperator *A)
 {
-  auto *k = s ? dynamic_cast<ComplexIterativeSolver *>(s->s.get()) : nullptr;
-  if (!k || !A) return B2P_ERR_ARG;
-  k->A = A->op.get();
-  return B2P_SUCCESS;
+  if (!s || !s->s || !A) return B2P_ERR_ARG;
+  if (auto *k = dynamic_cast<ComplexIterativeSolver *>(s->s.get()))
+  {
+    k->A = A->op.get();
+    return B2P_SUCCESS;
+  }
+  b2p_ctx *ctx = s->s->ctx;
+  bool ok = false;
+  B2P_CTRY(ctx, ok = s->s->SetOperator(*A->op));
+  return ok ? B2P_SUCCESS : B2P_ERR_ARG;
 }
 int b2p_csolver_set_preconditioner(b2p_csolver *s, b2p_csolver *pc)
 {
