@@ -373,6 +373,11 @@ int b2p_csolver_real_pc(b2p_ctx *ctx, b2p_solver *real_pc, b2p_csolver **out);
 /* JacobiSmoother<ComplexOperator> (linalg/jacobi.cpp:75-105): y = omega D^-1 x with the complex diagonal of the operator given to
  * b2p_csolver_set_operator; omega != 0. The preconditioner of the complex-valued (PCMatReal = false) path. */
 int b2p_csolver_jacobi(b2p_ctx *ctx, double omega, b2p_csolver **out);
+/* ChebyshevSmoother<ComplexOperator>, 4th kind (linalg/chebyshev.cpp:160-220) on the operator given to b2p_csolver_set_operator:
+ * complex inverse diagonal, lambda_max = sf_max * ||D^-1 A||_2 (power iteration, linalg/operator.cpp:583-631). mult applies
+ * y = y + p(D^-1 A) D^-1 (x - A y) (y = 0 unless b2p_csolver_set_initial_guess). */
+int b2p_csolver_chebyshev(b2p_ctx *ctx, int smooth_it, int order, double sf_max, b2p_csolver **out);
+int b2p_csolver_lambda_max(b2p_csolver *s, double *out);
 int b2p_csolver_krylov(b2p_ctx *ctx, int type, b2p_csolver **out);
 int b2p_csolver_krylov_config(b2p_csolver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side);
 int b2p_csolver_set_operator(b2p_csolver *s, b2p_coperator *A);

@@ -735,6 +735,17 @@ class ComplexSolver:
         return s
 
     @classmethod
+    def chebyshev(cls, ctx, smooth_it=1, order=4, sf_max=1.0):
+        h = C.c_void_p()
+        _chk(lib().b2p_csolver_chebyshev(ctx.h, int(smooth_it), int(order), C.c_double(sf_max), C.byref(h)), ctx.h)
+        return cls(ctx, h)
+
+    def lambda_max(self):
+        out = C.c_double()
+        _chk(lib().b2p_csolver_lambda_max(self.h, C.byref(out)), self.ctx.h)
+        return out.value
+
+    @classmethod
     def jacobi(cls, ctx, omega=1.0):
         h = C.c_void_p()
         _chk(lib().b2p_csolver_jacobi(ctx.h, C.c_double(omega), C.byref(h)), ctx.h)

@@ -127,6 +127,36 @@ __global__ void cdiag_mult_kernel(const double *__restrict__ dr, const double *_
   }
 }
 
+// Chebyshev update with the complex inverse diagonal and the solution update folded in (chebyshev.cpp:81-156):
+// d = sd d + sr dinv r, then y = d (assign) or y += d
+__global__ void ccheb_kernel(double sd, double sr, const double *__restrict__ ir, const double *__restrict__ ii, const double *__restrict__ rr,
+                             const double *__restrict__ ri, double *__restrict__ dr, double *__restrict__ di, double *__restrict__ yr,
+                             double *__restrict__ yi, int first, int assign, int64_t n)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+  {
+    const double a = ir[i], b = ii[i], u = rr[i], v = ri[i];
+    double er = sr * (a * u - b * v), ei = sr * (b * u + a * v);
+    if (!first)
+    {
+      er += sd * dr[i];
+      ei += sd * di[i];
+    }
+    dr[i] = er;
+    di[i] = ei;
+    if (assign)
+    {
+      yr[i] = er;
+      yi[i] = ei;
+    }
+    else
+    {
+      yr[i] += er;
+      yi[i] += ei;
+    }
+  }
+}
+
 inline int grid_for(b2p_ctx *c, int64_t n)
 {
   const int64_t want = (n + 2 * NT - 1) / (2 * NT), cap = (int64_t)c->sm_count * 8;
@@ -211,6 +241,7 @@ public:
   virtual void Mult(CCPtr x, CPtr y) const = 0;
   virtual void MultHermitianTranspose(CCPtr x, CPtr y) const = 0;
   virtual void AssembleDiagonal(CPtr d) const = 0;
+  virtual bool IsReal() const { return false; }  // no imaginary part (operator.hpp:47)
   void AddMult(CCPtr x, CPtr y, cplx a) const
   {
     if (tmp_.n != 2 * n) tmp_.resize(ctx, 2 * n);
@@ -380,6 +411,12 @@ public:
       }
     }
   }
+  bool IsReal() const override
+  {
+    for (auto &t : terms)
+      if (t.ci != 0.0) return false;
+    return true;
+  }
   void Mult(CCPtr x, CPtr y) const override { apply(x, y, false); }
   void MultHermitianTranspose(CCPtr x, CPtr y) const override { apply(x, y, true); }
   void AssembleDiagonal(CPtr d) const override
@@ -462,6 +499,7 @@ public:
       }
     }
   }
+  bool IsReal() const override { return Ai == nullptr; }
   void Mult(CCPtr x, CPtr y) const override { apply(x, y, false); }
   void MultHermitianTranspose(CCPtr x, CPtr y) const override { apply(x, y, true); }
   void AssembleDiagonal(CPtr d) const override
@@ -511,6 +549,100 @@ public:
   {
     B2P_LAUNCH(cdiag_mult_kernel, grid_for(ctx, n), NT, 0, ctx->stream, (const double *)dinv.p, (const double *)(dinv.p + n), x.re, x.im,
                y.re, y.im, 1.0, n);
+  }
+};
+
+// ChebyshevSmoother<ComplexOperator>, 4th kind (chebyshev.cpp:160-220): complex inverse diagonal, lambda_max =
+// sf_max * ||D^-1 A||_2 by the reference's power iteration (operator.cpp:583-631; on (D^-1 A)^H (D^-1 A) unless A is real).
+class ComplexChebyshevSmoother : public ComplexSolver
+{
+  int pc_it, order;
+  double sf_max;
+  const ComplexOperator *A = nullptr;
+  int64_t n = 0;
+  mutable DVec d, dinv, r_;
+
+  double SpectralNormDinvA(double tol = 1e-4, int max_it = 1000) const
+  {
+    const bool herm = A->IsReal();
+    DVec u(ctx, 2 * n), v(ctx, 2 * n);
+    vec::set_random(ctx, u.p, 2 * n, 0);
+    double l = cnorm(ctx, CCPtr{u.p, u.p + n}, n), l0 = 0.0;
+    vec::scale(ctx, u.p, 2 * n, 1.0 / l);
+    int it = 0;
+    for (; it < max_it; it++)
+    {
+      // w = D^-1 A u  (w is u itself in the Hermitian case, else the work vector d)
+      const double *ir = dinv.p, *ii = dinv.p + n;
+      double *up = u.p, *vp = v.p;
+      A->Mult(CCPtr{up, up + n}, CPtr{vp, vp + n});
+      double *w = herm ? up : d.p;
+      B2P_LAUNCH(cdiag_mult_kernel, grid_for(ctx, n), NT, 0, ctx->stream, ir, ii, (const double *)vp, (const double *)(vp + n), w, w + n, 1.0,
+                 n);
+      if (!herm)
+      {
+        // u = (D^-1 A)^H w = A^H (conj(D^-1) w)
+        B2P_LAUNCH(cdiag_mult_kernel, grid_for(ctx, n), NT, 0, ctx->stream, ir, ii, (const double *)w, (const double *)(w + n), vp, vp + n,
+                   -1.0, n);
+        A->MultHermitianTranspose(CCPtr{vp, vp + n}, CPtr{up, up + n});
+      }
+      l = cnorm(ctx, CCPtr{u.p, u.p + n}, n);
+      vec::scale(ctx, u.p, 2 * n, 1.0 / l);
+      if (it > 0 && std::abs(l - l0) / l0 < tol) break;
+      l0 = l;
+    }
+    return herm ? l : std::sqrt(l);
+  }
+
+public:
+  double lambda_max = 0.0;
+  ComplexChebyshevSmoother(b2p_ctx *c, int smooth_it, int poly_order, double sf_max_)
+    : ComplexSolver(c), pc_it(smooth_it), order(poly_order), sf_max(sf_max_)
+  {
+  }
+  bool SetOperator(const ComplexOperator &op) override
+  {
+    A = &op;
+    n = op.n;
+    d.resize(ctx, 2 * n);
+    dinv.resize(ctx, 2 * n);
+    r_.resize(ctx, 2 * n);
+    op.AssembleDiagonal(CPtr{dinv.p, dinv.p + n});
+    B2P_LAUNCH(creciprocal_kernel, grid_for(ctx, n), NT, 0, ctx->stream, dinv.p, dinv.p + n, 1.0, n);
+    lambda_max = sf_max * SpectralNormDinvA();
+    if (!(lambda_max > 0.0)) set_error(ctx, "Encountered zero maximum eigenvalue in Chebyshev smoother!");
+    return lambda_max > 0.0;
+  }
+  // y = y + p(D^-1 A) D^-1 (x - A y), chebyshev.cpp:190-220
+  void Mult(CCPtr x, CPtr y) const override
+  {
+    CPtr r{r_.p, r_.p + n}, dd{d.p, d.p + n};
+    const double *ir = dinv.p, *ii = dinv.p + n;
+    for (int it = 0; it < pc_it; it++)
+    {
+      const bool fresh = !(initial_guess || it > 0);
+      if (fresh)
+      {
+        vec::copy(ctx, r.re, x.re, n);
+        vec::copy(ctx, r.im, x.im, n);
+      }
+      else
+      {
+        A->Mult(CCPtr{y.re, y.im}, r);
+        vec::axpby(ctx, 1.0, x.re, -1.0, r.re, n);
+        vec::axpby(ctx, 1.0, x.im, -1.0, r.im, n);
+      }
+      B2P_LAUNCH(ccheb_kernel, grid_for(ctx, n), NT, 0, ctx->stream, 0.0, 4.0 / (3.0 * lambda_max), ir, ii, (const double *)r.re,
+                 (const double *)r.im, dd.re, dd.im, y.re, y.im, 1, fresh ? 1 : 0, n);
+      for (int k = 1; k < order; k++)
+      {
+        A->AddMult(CCPtr{dd.re, dd.im}, r, cplx(-1.0, 0.0));
+        const double sd = (2.0 * k - 1.0) / (2.0 * k + 3.0);
+        const double sr = (8.0 * k + 4.0) / ((2.0 * k + 3.0) * lambda_max);
+        B2P_LAUNCH(ccheb_kernel, grid_for(ctx, n), NT, 0, ctx->stream, sd, sr, ir, ii, (const double *)r.re, (const double *)r.im, dd.re,
+                   dd.im, y.re, y.im, 0, 0, n);
+      }
+    }
   }
 };
 
@@ -976,6 +1108,22 @@ int b2p_csolver_jacobi(b2p_ctx *ctx, double omega, b2p_csolver **out)
   auto *h = new b2p_csolver;
   h->s = std::make_unique<ComplexJacobiSmoother>(ctx, omega);
   *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_csolver_chebyshev(b2p_ctx *ctx, int smooth_it, int order, double sf_max, b2p_csolver **out)
+{
+  B2P_CHECK(ctx, ctx && out && smooth_it > 0, B2P_ERR_ARG, "b2p_csolver_chebyshev: bad argument");
+  B2P_CHECK(ctx, order > 0, B2P_ERR_ARG, "Polynomial order for Chebyshev smoothing must be positive!");
+  auto *h = new b2p_csolver;
+  h->s = std::make_unique<ComplexChebyshevSmoother>(ctx, smooth_it, order, sf_max);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_csolver_lambda_max(b2p_csolver *s, double *out)
+{
+  auto *c = s ? dynamic_cast<ComplexChebyshevSmoother *>(s->s.get()) : nullptr;
+  if (!c || !out) return B2P_ERR_ARG;
+  *out = c->lambda_max;
   return B2P_SUCCESS;
 }
 int b2p_csolver_krylov(b2p_ctx *ctx, int type, b2p_csolver **out)

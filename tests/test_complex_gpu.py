@@ -176,6 +176,48 @@ def test_complex_jacobi_smoother(b2p_ctx, setup):
     assert its[1] <= its[0], its
 
 
+def test_complex_chebyshev_smoother(b2p_ctx, setup):
+    """ChebyshevSmoother<ComplexOperator>, 4th kind (linalg/chebyshev.cpp:160-220): lambda_max against the exact
+    ||D^-1 A||_2 (the power iteration stops at 1e-4), the polynomial against the NumPy restatement of the recurrence run in
+    complex arithmetic with the device's lambda_max, with and without an initial guess, and as a GMRES preconditioner."""
+    from oracle import solvers as S
+
+    capi, A, Ao = setup["capi"], setup["A"], setup["Ao"]
+    n = Ao.shape[0]
+    order = 4
+    Cb = capi.ComplexSolver.chebyshev(b2p_ctx, smooth_it=1, order=order, sf_max=1.0)
+    Cb.set_operator(A)
+    lam = Cb.lambda_max()
+    dinv = 1.0 / Ao.diagonal()
+    exact = np.linalg.norm(dinv[:, None] * Ao.toarray(), 2)
+    assert abs(lam - exact) < 5e-3 * exact, (lam, exact)
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    xr, xi = _cvec(x)
+    yr, yi = torch.empty_like(xr), torch.empty_like(xi)
+    Cb.mult(xr, xi, yr, yi)
+    assert _rel(_host(yr, yi), S.chebyshev(Ao, dinv, lam, order, x, np.zeros(n, complex), False)) < 1e-11
+    y0 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    yr, yi = _cvec(y0)
+    Cb.set_initial_guess(True)
+    Cb.mult(xr, xi, yr, yi)
+    assert _rel(_host(yr, yi), S.chebyshev(Ao, dinv, lam, order, x, y0, True)) < 1e-11
+    Cb.set_initial_guess(False)
+    # flexible GMRES with the polynomial as preconditioner
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    b[setup["prob"].nd.ess_dofs] = 0.0
+    br, bi = _cvec(b)
+    Sv = capi.ComplexSolver.krylov(b2p_ctx, 2, rel_tol=1e-10, max_it=300, max_dim=300)
+    Sv.set_operator(A)
+    Sv.set_preconditioner(Cb)
+    zr, zi = torch.zeros_like(br), torch.zeros_like(bi)
+    Sv.mult(br, bi, zr, zi)
+    import scipy.sparse.linalg as spla
+
+    assert Sv.stats()["converged"]
+    assert _rel(_host(zr, zi), spla.spsolve(Ao.tocsc(), b)) < 1e-7
+
+
 @pytest.mark.parametrize("kind,orth,side", [(1, 0, 0), (1, 2, 1), (2, 1, 0)])
 def test_complex_gmres_matches_reference_recurrence(b2p_ctx, setup, kind, orth, side):
     """Complex (F)GMRES with a Jacobi-like real preconditioner applied to both parts."""
