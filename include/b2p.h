@@ -378,6 +378,13 @@ int b2p_csolver_jacobi(b2p_ctx *ctx, double omega, b2p_csolver **out);
  * y = y + p(D^-1 A) D^-1 (x - A y) (y = 0 unless b2p_csolver_set_initial_guess). */
 int b2p_csolver_chebyshev(b2p_ctx *ctx, int smooth_it, int order, double sf_max, b2p_csolver **out);
 int b2p_csolver_lambda_max(b2p_csolver *s, double *out);
+/* GeometricMultigridSolver<ComplexOperator> (linalg/gmg.cpp:16-205), the reference's default (PCMatReal = false) preconditioner
+ * of complex systems: complex level operators A[l] (and auxiliary H1 operators A_aux[l] when the discrete gradients G are given:
+ * DistRelaxationSmoother<ComplexOperator>, distrelaxation.cpp:39-151), 4th-kind complex Chebyshev smoothing, REAL prolongations P
+ * and gradients G applied to both parts. Takes over `coarse` (it is handed A[0] by ..._set_operators). */
+int b2p_csolver_gmg(b2p_ctx *ctx, b2p_csolver *coarse, int n_levels, b2p_operator *const *P, b2p_operator *const *G, int cycle_it,
+                    int smooth_it, int cheby_order, double sf_max, b2p_csolver **out);
+int b2p_csolver_gmg_set_operators(b2p_csolver *s, b2p_coperator *const *A, b2p_coperator *const *A_aux);
 int b2p_csolver_krylov(b2p_ctx *ctx, int type, b2p_csolver **out);
 int b2p_csolver_krylov_config(b2p_csolver *s, double rel_tol, double abs_tol, int max_it, int max_dim, int orthog, int pc_side);
 int b2p_csolver_set_operator(b2p_csolver *s, b2p_coperator *A);

@@ -735,6 +735,30 @@ class ComplexSolver:
         return s
 
     @classmethod
+    def gmg(cls, ctx, coarse, P, G=None, cycle_it=1, smooth_it=1, cheby_order=4, sf_max=1.0):
+        """Complex-valued p-multigrid (PCMatReal = false): real prolongations / gradients, complex level operators."""
+        n_levels = len(P) + 1
+        Parr = (C.c_void_p * max(1, len(P)))(*[p.h for p in P])
+        Garr = None
+        if G is not None:
+            Garr = (C.c_void_p * n_levels)(*[(g.h if g is not None else None) for g in G])
+        h = C.c_void_p()
+        _chk(lib().b2p_csolver_gmg(ctx.h, coarse.h, n_levels, Parr, Garr, int(cycle_it), int(smooth_it), int(cheby_order),
+                                   C.c_double(sf_max), C.byref(h)), ctx.h)
+        s = cls(ctx, h)
+        s._keep += [coarse, list(P), G]
+        return s
+
+    def gmg_set_operators(self, A, A_aux=None):
+        n = len(A)
+        Aarr = (C.c_void_p * n)(*[a.h for a in A])
+        Garr = None
+        if A_aux is not None:
+            Garr = (C.c_void_p * n)(*[(a.h if a is not None else None) for a in A_aux])
+        self._keep += [list(A), A_aux]
+        _chk(lib().b2p_csolver_gmg_set_operators(self.h, Aarr, Garr), self.ctx.h)
+
+    @classmethod
     def chebyshev(cls, ctx, smooth_it=1, order=4, sf_max=1.0):
         h = C.c_void_p()
         _chk(lib().b2p_csolver_chebyshev(ctx.h, int(smooth_it), int(order), C.c_double(sf_max), C.byref(h)), ctx.h)

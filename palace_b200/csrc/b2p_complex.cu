@@ -242,6 +242,8 @@ public:
   virtual void MultHermitianTranspose(CCPtr x, CPtr y) const = 0;
   virtual void AssembleDiagonal(CPtr d) const = 0;
   virtual bool IsReal() const { return false; }  // no imaginary part (operator.hpp:47)
+  virtual const int32_t *EssentialTrueDofs() const { return nullptr; }  // device list
+  virtual int64_t NumEssential() const { return 0; }
   void AddMult(CCPtr x, CPtr y, cplx a) const
   {
     if (tmp_.n != 2 * n) tmp_.resize(ctx, 2 * n);
@@ -417,6 +419,8 @@ public:
       if (t.ci != 0.0) return false;
     return true;
   }
+  const int32_t *EssentialTrueDofs() const override { return d_ess; }
+  int64_t NumEssential() const override { return n_ess; }
   void Mult(CCPtr x, CPtr y) const override { apply(x, y, false); }
   void MultHermitianTranspose(CCPtr x, CPtr y) const override { apply(x, y, true); }
   void AssembleDiagonal(CPtr d) const override
@@ -500,6 +504,16 @@ public:
     }
   }
   bool IsReal() const override { return Ai == nullptr; }
+  const int32_t *EssentialTrueDofs() const override
+  {
+    const auto *p = dynamic_cast<const ParOperator *>(Ar ? Ar : Ai);
+    return p ? p->EssentialTrueDofs() : nullptr;
+  }
+  int64_t NumEssential() const override
+  {
+    const auto *p = dynamic_cast<const ParOperator *>(Ar ? Ar : Ai);
+    return p ? p->NumEssential() : 0;
+  }
   void Mult(CCPtr x, CPtr y) const override { apply(x, y, false); }
   void MultHermitianTranspose(CCPtr x, CPtr y) const override { apply(x, y, true); }
   void AssembleDiagonal(CPtr d) const override
@@ -525,6 +539,7 @@ public:
   virtual ~ComplexSolver() = default;
   virtual void Mult(CCPtr x, CPtr y) const = 0;
   virtual bool SetOperator(const ComplexOperator &) { return false; }  // false: this solver takes no operator
+  virtual void MultTranspose(CCPtr x, CPtr y) const { Mult(x, y); }  // smoothers of symmetric operators: the same
 };
 
 // JacobiSmoother<ComplexOperator> (jacobi.cpp:75-105): y = omega D^-1 x with the COMPLEX assembled diagonal; the smoother and
@@ -646,6 +661,181 @@ public:
   }
 };
 
+// DistRelaxationSmoother<ComplexOperator> (distrelaxation.cpp:39-151): Hiptmair smoothing of the complex ND operator with the
+// complex auxiliary (H1) operator; the discrete gradient G is real and acts on both parts.
+class ComplexDistRelaxationSmoother : public ComplexSolver
+{
+  int pc_it;
+  const Operator *G;
+  const ComplexOperator *A = nullptr, *A_G = nullptr;
+  std::unique_ptr<ComplexChebyshevSmoother> B, B_G;
+  int64_t n = 0, nG = 0;
+  mutable DVec r_, x_G, y_G;
+
+  void Residual(CCPtr x, CPtr y, CPtr r) const
+  {
+    A->Mult(CCPtr{y.re, y.im}, r);
+    vec::axpby(ctx, 1.0, x.re, -1.0, r.re, n);
+    vec::axpby(ctx, 1.0, x.im, -1.0, r.im, n);
+  }
+  void AuxCorrection(CCPtr r, CPtr y, bool transpose) const
+  {
+    CPtr xg{x_G.p, x_G.p + nG}, yg{y_G.p, y_G.p + nG};
+    G->MultTranspose(r.re, xg.re);
+    G->MultTranspose(r.im, xg.im);
+    if (A_G->NumEssential() > 0)
+    {
+      vec::set_sub(ctx, xg.re, A_G->EssentialTrueDofs(), A_G->NumEssential(), 0.0);
+      vec::set_sub(ctx, xg.im, A_G->EssentialTrueDofs(), A_G->NumEssential(), 0.0);
+    }
+    B_G->initial_guess = false;
+    if (transpose)
+      B_G->MultTranspose(CCPtr{xg.re, xg.im}, yg);
+    else
+      B_G->Mult(CCPtr{xg.re, xg.im}, yg);
+    G->AddMult(yg.re, y.re, 1.0);
+    G->AddMult(yg.im, y.im, 1.0);
+  }
+
+public:
+  ComplexDistRelaxationSmoother(b2p_ctx *c, const Operator &G_, int smooth_it, int cheby_smooth_it, int cheby_order, double sf_max)
+    : ComplexSolver(c), pc_it(smooth_it), G(&G_)
+  {
+    B = std::make_unique<ComplexChebyshevSmoother>(c, cheby_smooth_it, cheby_order, sf_max);
+    B_G = std::make_unique<ComplexChebyshevSmoother>(c, cheby_smooth_it, cheby_order, sf_max);
+  }
+  bool SetOperators(const ComplexOperator &op, const ComplexOperator &op_G)
+  {
+    A = &op;
+    A_G = &op_G;
+    n = op.n;
+    nG = op_G.n;
+    r_.resize(ctx, 2 * n);
+    x_G.resize(ctx, 2 * nG);
+    y_G.resize(ctx, 2 * nG);
+    return B->SetOperator(op) && B_G->SetOperator(op_G);
+  }
+  // distrelaxation.cpp:99-119
+  void Mult(CCPtr x, CPtr y) const override
+  {
+    CPtr r{r_.p, r_.p + n};
+    for (int it = 0; it < pc_it; it++)
+    {
+      B->initial_guess = initial_guess || it > 0;
+      B->Mult(x, y);
+      Residual(x, y, r);
+      AuxCorrection(CCPtr{r.re, r.im}, y, false);
+    }
+  }
+  // distrelaxation.cpp:121-151
+  void MultTranspose(CCPtr x, CPtr y) const override
+  {
+    CPtr r{r_.p, r_.p + n};
+    for (int it = 0; it < pc_it; it++)
+    {
+      if (initial_guess || it > 0)
+      {
+        Residual(x, y, r);
+        AuxCorrection(CCPtr{r.re, r.im}, y, true);
+      }
+      else
+      {
+        vec::set(ctx, y.re, n, 0.0);
+        vec::set(ctx, y.im, n, 0.0);
+        AuxCorrection(x, y, true);
+      }
+      B->initial_guess = true;
+      B->MultTranspose(x, y);
+    }
+  }
+};
+
+// GeometricMultigridSolver<ComplexOperator> (gmg.cpp:16-205): complex level operators and smoothers, REAL prolongations and
+// discrete gradients applied to both parts.
+class ComplexGeometricMultigridSolver : public ComplexSolver
+{
+public:
+  int pc_it;
+  std::vector<const Operator *> P;
+  std::vector<const ComplexOperator *> A;
+  std::vector<std::unique_ptr<ComplexSolver>> B;
+  mutable std::vector<DVec> X, Y, R;
+  ComplexGeometricMultigridSolver(b2p_ctx *c, std::unique_ptr<ComplexSolver> &&coarse, const std::vector<const Operator *> &P_,
+                                  const std::vector<const Operator *> &G, int cycle_it, int smooth_it, int cheby_order, double sf_max)
+    : ComplexSolver(c), pc_it(cycle_it), P(P_), A(P_.size() + 1), B(P_.size() + 1), X(P_.size() + 1), Y(P_.size() + 1), R(P_.size() + 1)
+  {
+    B[0] = std::move(coarse);
+    for (size_t l = 1; l < B.size(); l++)
+    {
+      if (!G.empty())
+        B[l] = std::make_unique<ComplexDistRelaxationSmoother>(c, *G[l], smooth_it, 1, cheby_order, sf_max);  // gmg.cpp:45-50
+      else
+        B[l] = std::make_unique<ComplexChebyshevSmoother>(c, smooth_it, cheby_order, sf_max);  // gmg.cpp:52-63
+    }
+  }
+  // gmg.cpp:66-123
+  bool SetOperators(const std::vector<const ComplexOperator *> &A_, const std::vector<const ComplexOperator *> &A_aux)
+  {
+    bool ok = true;
+    for (size_t l = 0; l < A.size(); l++)
+    {
+      A[l] = A_[l];
+      auto *dist = dynamic_cast<ComplexDistRelaxationSmoother *>(B[l].get());
+      if (dist)
+        ok = ok && !A_aux.empty() && A_aux[l] && dist->SetOperators(*A_[l], *A_aux[l]);
+      else
+        ok = B[l]->SetOperator(*A_[l]) && ok;
+      const int64_t n = A[l]->n;
+      X[l].resize(ctx, 2 * n);
+      Y[l].resize(ctx, 2 * n);
+      R[l].resize(ctx, 2 * n);
+    }
+    return ok;
+  }
+  void Mult(CCPtr x, CPtr y) const override
+  {
+    const int top = (int)A.size() - 1;
+    const int64_t n = A[top]->n;
+    vec::copy(ctx, X[top].p, x.re, n);
+    vec::copy(ctx, X[top].p + n, x.im, n);
+    for (int it = 0; it < pc_it; it++) VCycle(top, it > 0);
+    vec::copy(ctx, y.re, Y[top].p, n);
+    vec::copy(ctx, y.im, Y[top].p + n, n);
+  }
+
+private:
+  // gmg.cpp:172-205
+  void VCycle(int l, bool initial_guess_) const
+  {
+    const int64_t n = A[l]->n;
+    CPtr x{X[l].p, X[l].p + n}, y{Y[l].p, Y[l].p + n}, r{R[l].p, R[l].p + n};
+    B[l]->initial_guess = initial_guess_;
+    if (l == 0)
+    {
+      B[l]->Mult(CCPtr{x.re, x.im}, y);
+      return;
+    }
+    const int64_t nc = A[l - 1]->n;
+    CPtr xc{X[l - 1].p, X[l - 1].p + nc}, yc{Y[l - 1].p, Y[l - 1].p + nc};
+    B[l]->Mult(CCPtr{x.re, x.im}, y);
+    A[l]->Mult(CCPtr{y.re, y.im}, r);
+    vec::axpby(ctx, 1.0, x.re, -1.0, r.re, n);
+    vec::axpby(ctx, 1.0, x.im, -1.0, r.im, n);
+    P[l - 1]->MultTranspose(r.re, xc.re);
+    P[l - 1]->MultTranspose(r.im, xc.im);
+    if (A[l - 1]->NumEssential() > 0)
+    {
+      vec::set_sub(ctx, xc.re, A[l - 1]->EssentialTrueDofs(), A[l - 1]->NumEssential(), 0.0);
+      vec::set_sub(ctx, xc.im, A[l - 1]->EssentialTrueDofs(), A[l - 1]->NumEssential(), 0.0);
+    }
+    VCycle(l - 1, false);
+    P[l - 1]->AddMult(yc.re, y.re, 1.0);
+    P[l - 1]->AddMult(yc.im, y.im, 1.0);
+    B[l]->initial_guess = true;
+    B[l]->MultTranspose(CCPtr{x.re, x.im}, y);
+  }
+};
+
 // PCMatReal: the (real) preconditioner acts on real and imaginary parts separately.
 class RealPcSolver : public ComplexSolver
 {
@@ -694,6 +884,11 @@ public:
   ComplexIterativeSolver(b2p_ctx *c, KspType type_) : ComplexSolver(c), type(type_) {}
   KspType type;
   const ComplexOperator *A = nullptr;
+  bool SetOperator(const ComplexOperator &op) override
+  {
+    A = &op;
+    return true;
+  }
   const ComplexSolver *B = nullptr;
   double rel_tol = 1e-6, abs_tol = 0.0;
   int max_it = 100, max_dim = -1;
@@ -1125,6 +1320,34 @@ int b2p_csolver_lambda_max(b2p_csolver *s, double *out)
   if (!c || !out) return B2P_ERR_ARG;
   *out = c->lambda_max;
   return B2P_SUCCESS;
+}
+int b2p_csolver_gmg(b2p_ctx *ctx, b2p_csolver *coarse, int n_levels, b2p_operator *const *P, b2p_operator *const *G, int cycle_it,
+                    int smooth_it, int cheby_order, double sf_max, b2p_csolver **out)
+{
+  B2P_CHECK(ctx, ctx && coarse && coarse->s && n_levels >= 1 && out && (n_levels == 1 || P), B2P_ERR_ARG, "b2p_csolver_gmg: bad argument");
+  std::vector<const Operator *> Pv, Gv;
+  for (int l = 0; l + 1 < n_levels; l++) Pv.push_back(operator_of(P[l]));
+  if (G)
+    for (int l = 0; l < n_levels; l++) Gv.push_back(G[l] ? operator_of(G[l]) : nullptr);
+  auto *h = new b2p_csolver;
+  h->s = std::make_unique<ComplexGeometricMultigridSolver>(ctx, std::move(coarse->s), Pv, Gv, cycle_it, smooth_it, cheby_order, sf_max);
+  *out = h;
+  return B2P_SUCCESS;
+}
+int b2p_csolver_gmg_set_operators(b2p_csolver *s, b2p_coperator *const *A, b2p_coperator *const *A_aux)
+{
+  auto *g = s ? dynamic_cast<ComplexGeometricMultigridSolver *>(s->s.get()) : nullptr;
+  if (!g || !A) return B2P_ERR_ARG;
+  std::vector<const ComplexOperator *> Av, Gv;
+  for (size_t l = 0; l < g->A.size(); l++)
+  {
+    B2P_CHECK(g->ctx, A[l], B2P_ERR_ARG, "b2p_csolver_gmg_set_operators: level %d has no operator", (int)l);
+    Av.push_back(A[l]->op.get());
+    if (A_aux) Gv.push_back(A_aux[l] ? A_aux[l]->op.get() : nullptr);
+  }
+  bool ok = false;
+  B2P_CTRY(g->ctx, ok = g->SetOperators(Av, Gv));
+  return ok ? B2P_SUCCESS : B2P_ERR_ARG;
 }
 int b2p_csolver_krylov(b2p_ctx *ctx, int type, b2p_csolver **out)
 {
