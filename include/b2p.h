@@ -281,7 +281,12 @@ int b2p_vec_orthogonalize(b2p_ctx *ctx, int type, int64_t n, int m, const double
 /* ---- operators on true-dof vectors ---- */
 typedef struct b2p_operator b2p_operator;
 /* ParOperator over sum_i coef_i * op_i (BuildParSumOperator, rap.cpp:764-829) with essential true dofs;
- * diag_policy 0 = DIAG_ZERO, 1 = DIAG_ONE; halo may be NULL (single partition). */
+ * diag_policy 0 = DIAG_ZERO, 1 = DIAG_ONE; halo may be NULL (single partition).
+ * Op sharing: essential dofs are eliminated through the b2p_op's masked restriction (b2p_op_set_essential), one mask per
+ * b2p_op. The first single-partition operator built on an op installs the mask from ess_tdofs; building another operator on
+ * the same op with a DIFFERENT essential set (including empty vs non-empty) fails with B2P_ERR_ARG -- create a second b2p_op
+ * (geometry and tables are shared, refcounted) or re-install the mask. Partitioned callers (halo != NULL) install the mask
+ * in L-vector indices, ghost copies included, before this call. */
 int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2p_op *const *ops, const double *coefs,
                      const int32_t *ess_tdofs, int64_t n_ess, int diag_policy, b2p_halo *halo, b2p_operator **out);
 int b2p_operator_par_is_fused(b2p_operator *A); /* 1: the terms run as one fused element operator (b2p_op_create_sum) */

@@ -113,6 +113,12 @@ int b2p_operator_par(b2p_ctx *ctx, int64_t tsize, int64_t lsize, int n_terms, b2
   for (int i = 0; i < n_terms; i++)
   {
     B2P_CHECK(ctx, ops[i] && b2p_op_lsize(ops[i]) == lsize, B2P_ERR_ARG, "b2p_operator_par: term %d has the wrong L-size", i);
+    // Operators built on one b2p_op share its masked restriction. On a single partition the mask is installed from
+    // ess_tdofs by the first operator; a later one with another essential set would silently reuse it (wrong columns
+    // eliminated), so it is refused. (Partitioned callers install the mask themselves, with ghost copies, in L indices.)
+    B2P_CHECK(ctx, halo || !ops[i]->lidx_bc || op_essential_matches(ops[i], ess_tdofs, n_ess), B2P_ERR_ARG,
+              "b2p_operator_par: term %d already carries a different essential-dof mask (one b2p_op = one essential set; "
+              "create a second b2p_op or call b2p_op_set_essential again)", i);
     terms.push_back({ops[i], coefs ? coefs[i] : 1.0});
   }
   auto *h = new b2p_operator;
@@ -274,11 +280,20 @@ int b2p_solver_distrelax_set_operators(b2p_solver *s, b2p_operator *A, b2p_opera
 int b2p_solver_gmg(b2p_ctx *ctx, b2p_solver *coarse, int n_levels, b2p_operator *const *P, b2p_operator *const *G, int cycle_it,
                    int smooth_it, int cheby_order, double sf_max, double sf_min, int fourth_kind, b2p_solver **out)
 {
-  B2P_CHECK(ctx, coarse && coarse->s && n_levels >= 1 && out, B2P_ERR_ARG, "b2p_solver_gmg: bad argument");
+  B2P_CHECK(ctx, coarse && coarse->s && n_levels >= 1 && out && (P || n_levels == 1), B2P_ERR_ARG, "b2p_solver_gmg: bad argument");
   std::vector<const Operator *> Pv, Gv;
-  for (int l = 0; l + 1 < n_levels; l++) Pv.push_back(P[l]->op.get());
+  for (int l = 0; l + 1 < n_levels; l++)
+  {
+    B2P_CHECK(ctx, P[l] && P[l]->op, B2P_ERR_ARG, "b2p_solver_gmg: no prolongation between levels %d and %d", l, l + 1);
+    Pv.push_back(P[l]->op.get());
+  }
   if (G)
-    for (int l = 0; l < n_levels; l++) Gv.push_back(G[l] ? G[l]->op.get() : nullptr);
+    for (int l = 0; l < n_levels; l++)
+    {
+      // every level above the coarsest gets a DistRelaxationSmoother built on G[l] (gmg.cpp:45-50); G[0] is unused
+      B2P_CHECK(ctx, l == 0 || (G[l] && G[l]->op), B2P_ERR_ARG, "b2p_solver_gmg: level %d has no discrete gradient", l);
+      Gv.push_back(G[l] ? G[l]->op.get() : nullptr);
+    }
   auto *h = new b2p_solver;
   h->s = std::make_unique<GeometricMultigridSolver>(ctx, std::move(coarse->s), Pv, Gv, cycle_it, smooth_it, cheby_order, sf_max,
                                                     sf_min, fourth_kind != 0);
@@ -288,18 +303,19 @@ int b2p_solver_gmg(b2p_ctx *ctx, b2p_solver *coarse, int n_levels, b2p_operator 
 int b2p_solver_gmg_set_operators(b2p_solver *s, b2p_operator *const *A, b2p_operator *const *A_aux)
 {
   auto *g = s ? dynamic_cast<GeometricMultigridSolver *>(s->s.get()) : nullptr;
-  if (!g) return B2P_ERR_ARG;
+  if (!g || !A) return B2P_ERR_ARG;
   std::vector<const ParOperator *> Av, Gv;
   for (size_t l = 0; l < g->A.size(); l++)
   {
+    B2P_CHECK(g->ctx, A[l] && A[l]->op, B2P_ERR_ARG, "b2p_solver_gmg_set_operators: level %d has no operator", (int)l);
     auto *pa = dynamic_cast<ParOperator *>(A[l]->op.get());
     B2P_CHECK(g->ctx, pa, B2P_ERR_ARG, "GeometricMultigridSolver requires ParOperator operators!");
     Av.push_back(pa);
-    if (A_aux)
-    {
-      auto *pg = A_aux[l] ? dynamic_cast<ParOperator *>(A_aux[l]->op.get()) : nullptr;
-      Gv.push_back(pg);
-    }
+    auto *pg = (A_aux && A_aux[l]) ? dynamic_cast<ParOperator *>(A_aux[l]->op.get()) : nullptr;
+    // a level smoothed by DistRelaxationSmoother (the multigrid was built with discrete gradients) needs its auxiliary-space operator
+    const bool dist = dynamic_cast<DistRelaxationSmoother *>(g->B[l].get()) != nullptr;
+    B2P_CHECK(g->ctx, !dist || pg, B2P_ERR_ARG, "b2p_solver_gmg_set_operators: level %d needs an auxiliary-space ParOperator", (int)l);
+    Gv.push_back(pg);
   }
   B2P_TRY(g->ctx, g->SetOperators(Av, Gv));
   return B2P_SUCCESS;

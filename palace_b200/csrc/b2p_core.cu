@@ -5,6 +5,8 @@
 
 #include <type_traits>
 
+#include <algorithm>
+
 #include "b2p_internal.hpp"
 #include "b2p_qf.cuh"
 
@@ -109,11 +111,40 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   }();
   if (((flags & B2P_APPLY_HALFWARP_KERNEL) || nd_kernel == 5) && nd_hex_apply5_eligible(op))
     return launch_nd_hex_apply5(op, lidx, alpha, x, y, rg, s);
+  // Register-staged pipeline (b2p_hex_nd6.cu): B2P_ND_KERNEL=6
+  if (nd_kernel == 6 && nd_hex_apply6_eligible(op))
+  {
+    static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
+    if (trace) fprintf(stderr, "[b2p] nd_hex_apply6 p=%d q1d=%d kind=%d ne=%d\n", op->p, op->q1d, op->kind, op->ne);
+    return launch_nd_hex_apply6(op, lidx, alpha, x, y, rg, s);
+  }
   return launch_nd_hex_apply4(op, lidx, alpha, x, y, rg, s);
 }
 }  // namespace b2p
 
 using namespace b2p;
+
+namespace b2p
+{
+// order-free fingerprint of a dof set (splitmix64 finaliser per dof, summed)
+inline uint64_t ess_mix(uint64_t z)
+{
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+bool op_essential_matches(const b2p_op *op, const int32_t *ess_ldofs, int64_t n)
+{
+  std::vector<int32_t> v(ess_ldofs, ess_ldofs + (n > 0 ? n : 0));
+  std::sort(v.begin(), v.end());
+  v.erase(std::unique(v.begin(), v.end()), v.end());
+  uint64_t h = 0;
+  for (int32_t d : v) h += ess_mix((uint64_t)d);
+  if (!op->lidx_bc) return v.empty();
+  return op->ess_n == (int64_t)v.size() && op->ess_hash == h;
+}
+}  // namespace b2p
 
 extern "C"
 {
@@ -729,6 +760,14 @@ int b2p_op_set_essential(b2p_op *op, const int32_t *ess_ldofs, int64_t n)
   }
   cudaFree(op->lidx_bc);
   op->lidx_bc = nullptr;
+  op->ess_n = 0;
+  op->ess_hash = 0;
+  for (int64_t d = 0; d < op->lsize; d++)
+    if (mark[d])
+    {
+      op->ess_n++;
+      op->ess_hash += b2p::ess_mix((uint64_t)d);
+    }
   return upload(op->ctx, lidx.data(), lidx.size(), &op->lidx_bc);
 }
 
@@ -859,6 +898,8 @@ int b2p_op_create_sum(b2p_ctx *ctx, int n_terms, b2p_op *const *ops, const doubl
   op->lsize = o0->lsize;
   op->h_tab = o0->h_tab;
   op->tab_sym = o0->tab_sym;
+  op->ess_n = o0->ess_n;  // the masked restriction is copied below: same essential set
+  op->ess_hash = o0->ess_hash;
   int rc = 0;
   auto dup = [&](const auto *src, size_t n, auto **dst) -> int
   {

@@ -98,11 +98,14 @@ __global__ void p2p_wait_add_kernel(const long long *seg_off, const unsigned lon
 }
 __global__ void p2p_wait_kernel(int nseg, const long long *seg_off, const unsigned long long *flags, unsigned long long *expect)
 {
+  // Same epoch semantics as the in-kernel wait (p2p_push_kernel bumps expect[k] only where recv_has[k]): a neighbour that
+  // sends this rank nothing never raises flag k, so its expected epoch must not advance either -- otherwise a later Mult
+  // that waits inside the element kernel would spin on it forever.
   const int k = threadIdx.x;
   if (k >= nseg) return;
-  const unsigned long long ep = ++expect[k];
   if (seg_off[k + 1] > seg_off[k])
   {
+    const unsigned long long ep = ++expect[k];
     unsigned long long v;
     do
     {
@@ -110,7 +113,120 @@ __global__ void p2p_wait_kernel(int nseg, const long long *seg_off, const unsign
     } while (v < ep);
   }
 }
+
+// ---- fused variants used by ParOperator::Mult (one launch before and one after the element kernel) ----
+// PRE: forward exchange + every zero-fill of the step. Blocks [0, nn*GX) copy column k = block / GX of the send list into
+// the peer's mailbox exactly as p2p_push_kernel does (the last block of a column publishes the epoch); then ALL blocks
+// zero y (the output T-vector) and the ghost accumulation buffer. Thread k of block 0 also advances the expected epoch of
+// this step's reverse exchange, so that every block of the POST kernel can read it without a race.
+__global__ void p2p_pre_kernel(const double *__restrict__ src, const int32_t *__restrict__ idx, const long long *seg_off, int nn, int GX,
+                               double *const *dst_ptr, unsigned long long *const *flag_ptr, unsigned long long *epoch,
+                               unsigned int *done, unsigned long long *bump_expect, const int *recv_has, unsigned long long *expect_rev,
+                               double *__restrict__ y, long long ny, double *__restrict__ yg, long long nyg)
+{
+  if (blockIdx.x == 0 && (int)threadIdx.x < nn) ++expect_rev[threadIdx.x];
+  if ((int)blockIdx.x < nn * GX)
+  {
+    const int k = blockIdx.x / GX, bx = blockIdx.x % GX;
+    const long long b = seg_off[k], e = seg_off[k + 1];
+    double *dst = dst_ptr[k];
+    for (long long i = b + (long long)bx * blockDim.x + threadIdx.x; i < e; i += (long long)GX * blockDim.x) dst[i - b] = src[idx[i]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      const unsigned int prev = atomicAdd(done + k, 1u);
+      if (prev == (unsigned)GX - 1)
+      {
+        done[k] = 0;
+        if (bump_expect && recv_has[k]) ++bump_expect[k];
+        const unsigned long long ep = ++epoch[k];
+        if (e > b)
+        {
+          __threadfence_system();
+          st_release_sys_u64(flag_ptr[k], ep);
+        }
+      }
+    }
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = t0; i < nyg; i += stride) yg[i] = 0.0;
+  for (long long i = t0; i < ny; i += stride) y[i] = 0.0;
+}
+// POST: reverse exchange in one launch. Block (k, bx) copies its slice of ghost segment k into the peer's receive block
+// (last block of the column publishes the epoch), then waits for the peer's flag and adds its slice of the values received
+// from neighbour k into y. Waiting blocks only depend on the PEER's copies, never on blocks of this grid that have not
+// started, so the grid need not be co-resident.
+__global__ void p2p_post_kernel(const double *__restrict__ yg, const long long *recv_off, const long long *send_off, int GX,
+                                double *const *dst_ptr, unsigned long long *const *flag_ptr, unsigned long long *epoch, unsigned int *done,
+                                const unsigned long long *flags, const unsigned long long *expect, double *__restrict__ y,
+                                const int32_t *__restrict__ idx, const double *__restrict__ buf)
+{
+  const int k = blockIdx.x / GX, bx = blockIdx.x % GX;
+  {
+    const long long b = recv_off[k], e = recv_off[k + 1];
+    double *dst = dst_ptr[k];
+    for (long long i = b + (long long)bx * blockDim.x + threadIdx.x; i < e; i += (long long)GX * blockDim.x) dst[i - b] = yg[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      const unsigned int prev = atomicAdd(done + k, 1u);
+      if (prev == (unsigned)GX - 1)
+      {
+        done[k] = 0;
+        const unsigned long long ep = ++epoch[k];
+        if (e > b)
+        {
+          __threadfence_system();
+          st_release_sys_u64(flag_ptr[k], ep);
+        }
+      }
+    }
+  }
+  const long long b = send_off[k], e = send_off[k + 1];
+  if (e <= b) return;
+  if (threadIdx.x == 0)
+  {
+    const unsigned long long want = expect[k];
+    unsigned long long v;
+    do
+    {
+      v = ld_acquire_sys_u64(flags + k);
+    } while (v < want);
+  }
+  __syncthreads();
+  for (long long i = b + (long long)bx * blockDim.x + threadIdx.x; i < e; i += (long long)GX * blockDim.x) atomicAdd(y + idx[i], __ldcv(buf + i));
+}
 }  // namespace
+
+// Forward exchange + zero-fill of y and of the ghost accumulators in one launch (ParOperator::Mult). `in_kernel_wait`: the
+// element kernel polls the flags itself; otherwise a separate one-warp wait kernel follows.
+int halo_pre_p2p(Halo *h, const double *x, double *y, long long ny, bool in_kernel_wait, cudaStream_t s)
+{
+  const int nn = (int)h->nbr.size();
+  const long long ns = nn ? h->send_off.back() : 0;
+  const int GX = nn ? (int)std::min<long long>((ns / nn + 255) / 256 + 1, 16) : 1;
+  int grid = h->ctx->sm_count * 4;
+  if (grid < nn * GX) grid = nn * GX;
+  B2P_LAUNCH(p2p_pre_kernel, grid, 256, 0, s, x, h->d_send_idx, h->d_send_off, nn, GX, h->d_peer_fwd, h->d_peer_flag_fwd, h->d_epoch, h->d_done,
+             in_kernel_wait ? h->d_epoch + 2 * 32 : nullptr, h->d_recv_has, h->d_epoch + 3 * 32, y, ny, h->d_yg, (long long)h->n_ghost);
+  if (!in_kernel_wait && nn > 0) B2P_LAUNCH(p2p_wait_kernel, 1, 32, 0, s, nn, h->d_recv_off, h->d_flags, h->d_epoch + 2 * 32);
+  B2P_CUDA(h->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+// Reverse exchange of the step opened by halo_pre_p2p: ghost contributions -> owners, summed into y, in one launch.
+int halo_post_p2p(Halo *h, double *y, cudaStream_t s)
+{
+  const int nn = (int)h->nbr.size();
+  if (nn == 0) return B2P_SUCCESS;
+  const long long nr = h->recv_off.back(), ns = h->send_off.back();
+  const int GX = (int)std::min<long long>((std::max(nr, ns) / nn + 255) / 256 + 1, 16);
+  B2P_LAUNCH(p2p_post_kernel, nn * GX, 256, 0, s, h->d_yg, h->d_recv_off, h->d_send_off, GX, h->d_peer_rev, h->d_peer_flag_rev, h->d_epoch + 32,
+             h->d_done + 32, h->d_flags + 32, h->d_epoch + 3 * 32, y, h->d_send_idx, h->d_mail_rev);
+  B2P_CUDA(h->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
 
 int halo_forward_p2p(Halo *h, const double *x, bool in_kernel_wait, cudaStream_t s)
 {

@@ -124,6 +124,8 @@ struct b2p_op
   // lidx[e][l] >= 0 -> +x[lidx], < 0 -> -x[-1-lidx]   (layout [ne][P])
   int32_t *lidx = nullptr;
   int32_t *lidx_bc = nullptr;  // same with essential dofs replaced by B2P_SKIP_IDX (optional)
+  int64_t ess_n = -1;          // fingerprint of the essential set behind lidx_bc: number of distinct dofs, order-free hash
+  uint64_t ess_hash = 0;
   std::vector<double> h_tab;   // host copy of the packed 1-D tables (kernel parameter block)
   // 1-D tables (device): Bo[q1d][p], Bc[q1d][p+1], Gc[q1d][p+1]
   double *tab = nullptr;  // packed Bo | Bc | Gc
@@ -190,10 +192,14 @@ int launch_nd_hex_apply(b2p_op *op, const int32_t *lidx, double alpha, const dou
 int launch_nd_hex_apply4(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
 int launch_nd_hex_apply5(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
 bool nd_hex_apply5_eligible(b2p_op *op);
+int launch_nd_hex_apply6(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
+bool nd_hex_apply6_eligible(const b2p_op *op);
 // fused complex apply (b2p_hex_nd4.cu): both parts of a split complex vector in one pass over the geometry
 bool nd_hex_apply4z_eligible(const b2p_op *op);
 int launch_nd_hex_apply4z(b2p_op *op, int kind, const int32_t *lidx, const double *zcoef, int has_imag, double alpha, const double *xr,
                           const double *xi, double *yr, double *yi, cudaStream_t s);
+// Does the op's masked restriction (b2p_op_set_essential) eliminate exactly this set of L dofs?  (No mask <=> empty set.)
+bool op_essential_matches(const b2p_op *op, const int32_t *ess_ldofs, int64_t n);
 int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, int flags,
                 cudaStream_t s);
 int launch_nd_hex_diag(b2p_op *op, double *diag, cudaStream_t s);

@@ -138,7 +138,15 @@ public:
   void AddMult(const double *x, double *y, double a = 1.0) const override;
   bool NativeAddMult() const override { return halo == nullptr; }
   void AssembleDiagonal(double *d) const override;
-  void SetInteriorElements(int n) { ne_interior = n; }  // elements [0, n) touch no ghost dof
+  // elements [0, n) touch no ghost dof. A captured graph bakes in the wait mode that follows from it: drop the cache.
+  void SetInteriorElements(int n)
+  {
+    if (n == ne_interior) return;
+    ne_interior = n;
+    for (auto &g : graphs_) cudaGraphExecDestroy(g.second);
+    graphs_.clear();
+    capture_failed_ = false;
+  }
   // The eliminated sum as one device CSR matrix (ParOperator::ParallelAssemble, rap.cpp:84-152; coarse levels, single
   // partition); the caller owns the result (b2p_csr_destroy). Throws through set_error + nullptr on failure.
   b2p_csr *FullAssemble() const;

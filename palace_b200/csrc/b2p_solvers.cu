@@ -14,6 +14,8 @@ int halo_forward_split(Halo *h, const double *x, cudaStream_t s);
 int halo_reverse_split(Halo *h, double *y, cudaStream_t s);
 int halo_forward_p2p(Halo *h, const double *x, bool in_kernel_wait, cudaStream_t s);
 int halo_reverse_p2p(Halo *h, double *y, cudaStream_t s);
+int halo_pre_p2p(Halo *h, const double *x, double *y, long long ny, bool in_kernel_wait, cudaStream_t s);
+int halo_post_p2p(Halo *h, double *y, cudaStream_t s);
 int interp_apply(const b2p_interp *it, bool transpose, double alpha, const double *x, double *y, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------ Operator
@@ -99,15 +101,23 @@ void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
   // the collectives with the element kernel was measured to give nothing on B200: the persistent element
   // kernel fills every SM, so a collective kernel launched beside it only starts when it retires.)
   Halo *h = halo;
-  vec::set(ctx, y, height, 0.0);
-  if (h->n_ghost > 0 && !h->p2p) cudaMemsetAsync(h->d_yg, 0, sizeof(double) * h->n_ghost, s);  // (the p2p push kernel clears it)
+  // B2P_HALO_FUSED=0 keeps the round-1 sequence (zero-fill, push, element kernel, push, wait+add: five launches)
+  static const bool fused_halo = []() { const char *e = getenv("B2P_HALO_FUSED"); return !(e && e[0] == '0'); }();
+  const bool fused = h->p2p && fused_halo;
+  if (!fused)
+  {
+    vec::set(ctx, y, height, 0.0);
+    if (h->n_ghost > 0 && !h->p2p) cudaMemsetAsync(h->d_yg, 0, sizeof(double) * h->n_ghost, s);  // (the p2p push kernel clears it)
+  }
   // In-kernel wait: with elements ordered interior-first (SetInteriorElements) the ND element kernel itself
   // checks the neighbours' flags just before it reaches the first interface element, so the forward exchange
   // costs nothing on the critical path. (H1 operators use the separate wait kernel.)
   bool in_kernel = h->p2p && ne_interior > 0;
   // only the sum-factorised ND kernel polls the flags itself; H1 and dense-basis (tet) operators need the separate wait kernel
   for (auto &t : terms) in_kernel = in_kernel && t.op->kind != B2P_H1_DIFFUSION && !t.op->dense;
-  if (h->p2p)
+  if (fused)
+    halo_pre_p2p(h, x, y, height, in_kernel, s);  // forward exchange and both zero-fills: one launch
+  else if (h->p2p)
     halo_forward_p2p(h, x, in_kernel, s);
   else
     halo_forward_split(h, x, s);
@@ -126,7 +136,9 @@ void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
     }
     apply_range(t.op, t.op->lidx_bc ? t.op->lidx_bc : t.op->lidx, t.coef, x, y, rg, 0, s);
   }
-  if (h->p2p)
+  if (fused)
+    halo_post_p2p(h, y, s);  // push, wait and add: one launch
+  else if (h->p2p)
     halo_reverse_p2p(h, y, s);
   else
     halo_reverse_split(h, y, s);
@@ -164,10 +176,10 @@ void ParOperator::Mult(const double *x, double *y) const
     auto it = graphs_.find(key);
     static const bool no_graph = []() { const char *e = getenv("B2P_NO_GRAPH"); return e && e[0] == '1'; }();
     // Stream capture is not allowed on the legacy default stream (what MFEM and b2p_ctx_set_stream(ctx, nullptr) use).
-    // B2P_GRAPH_STREAM=1: capture and replay on an internal BLOCKING stream instead -- it synchronises implicitly with
-    // the legacy stream in both directions, so the caller's ordering is preserved. (Opt-in until measured on 2+ GPUs;
-    // without it a legacy-stream context runs the eager sequence.)
-    static const bool graph_stream = []() { const char *e = getenv("B2P_GRAPH_STREAM"); return e && e[0] == '1'; }();
+    // Capture and replay on an internal BLOCKING stream instead -- it synchronises implicitly with the legacy stream in
+    // both directions, so the caller's ordering is preserved. (B2P_GRAPH_STREAM=0: a legacy-stream context runs the eager
+    // sequence, as in round 1.)
+    static const bool graph_stream = []() { const char *e = getenv("B2P_GRAPH_STREAM"); return !(e && e[0] == '0'); }();
     if (s == nullptr && graph_stream && !no_graph)
     {
       if (!ctx->graph_stream && cudaStreamCreate(&ctx->graph_stream) != cudaSuccess) ctx->graph_stream = nullptr;
