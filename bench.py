@@ -40,18 +40,22 @@ def parse():
     ap.add_argument("--n", type=int, default=29, help="elements per direction per GPU (29 -> 2.02M dofs at p=3)")
     ap.add_argument("--assemble-qdata", type=int, default=0)
     ap.add_argument("--warp", type=float, default=0.0)
+    ap.add_argument("--coefficient", default="iso", choices=["iso", "matrix4"],
+                    help="iso: one material, identity tensors (SURVEY 8d.2 case 1); matrix4: four striped materials with full 3x3 "
+                         "tensors, as the reference's unit test builds them (test/unit/test-libceed.cpp:144-168)")
     ap.add_argument("--cpu-sample-elems", type=int, default=0, help="elements in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-experiments", action="store_true", help="skip the opt-in kernel variants measured in subprocesses")
     return ap.parse_args()
 
 
-def build_problem(n, p, warp, mesh_order=1, origin=(0.0, 0.0, 0.0), size=(1.0, 1.0, 1.0)):
+def build_problem(n, p, warp, mesh_order=1, origin=(0.0, 0.0, 0.0), size=(1.0, 1.0, 1.0), coefficient="iso"):
     from palace_b200.host import coeff as cf
     from palace_b200.host import hexmesh as hm
     from palace_b200.host import hexspace as hs
 
-    mesh = hm.box_mesh(n, size, warp_amp=warp, n_attr=1, origin=origin)
+    n_attr = 4 if coefficient == "matrix4" else 1
+    mesh = hm.box_mesh(n, size, warp_amp=warp, n_attr=n_attr, origin=origin)
     topo = hs.build_topology(mesh)
     nd = hs.build_nd_space(mesh, topo, p)
     q1d = p + 1
@@ -60,8 +64,14 @@ def build_problem(n, p, warp, mesh_order=1, origin=(0.0, 0.0, 0.0), size=(1.0, 1
     qx, qw = hs.gauss_legendre(q1d)
     nB, nG = hs.lagrange_table(nodes, qx)
     tabs = hs.tables_1d(p, q1d)
-    # one material: mu^-1 = I (curl part), eps = 1 (mass part)  
-    blob = cf.coeff_ctx_pair(cf.coeff_ctx(a=1.0), cf.coeff_ctx(a=1.0))
+    if coefficient == "matrix4":
+        # four striped materials, symmetric positive definite 3x3 tensors (the reference's unit-test coefficient,
+        # test/unit/test-libceed.cpp:144-168); the curl part takes the materials in reverse order, transposed
+        am, mc = cf.test_suite_coefficient(n_attr, "matrix")
+        blob = cf.coeff_ctx_pair(cf.coeff_ctx(am, mc, a=1.0), cf.coeff_ctx(am, mc[::-1].copy(), a=1.0, transpose=True))
+    else:
+        # one material: mu^-1 = I (curl part), eps = 1 (mass part)  
+        blob = cf.coeff_ctx_pair(cf.coeff_ctx(a=1.0), cf.coeff_ctx(a=1.0))
     return dict(mesh=mesh, topo=topo, nd=nd, q1d=q1d, xe=xe, nB=nB, nG=nG, tabs=tabs, blob=blob, mesh_order=mesh_order, p=p)
 
 
@@ -117,9 +127,32 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def cpu_quota():
+    """CPUs' worth of time the container may use per scheduling period (cgroup CFS quota), or None when unlimited. Running
+    more busy threads than this makes the kernel throttle the whole process for the rest of every period (measured on the
+    bench box: 64 pinned threads gave 19.6 ms best / 91 ms median per step), so the reference arm sizes its pool to it."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:  # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()[:2]
+            return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+            q = float(f.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            per = float(f.read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 class CpuReference:
-    """The reference algorithm (dense [3Q x P] interp/curl per element + reference QFunction
-    arithmetic: the oracle port of the libCEED /cpu/self path) on the host cores."""
+    """The reference algorithm (dense [3Q x P] interp/curl per element + reference QFunction arithmetic: the oracle port of
+    the libCEED /cpu/self path) on the host cores, organised like libCEED's blocked CPU backend: blocks of 8 elements with
+    the element index innermost, a persistent pool of threads pinned one per PHYSICAL core, precomputed transposed
+    restriction. Both the `--impl reference` arm and the `cpu_baseline` of the GPU arm time exactly this object and report
+    the median step, so the two CPU numbers of one record agree."""
 
     def __init__(self, prob, sample_elems=0):
         from oracle import pyoracle as O
@@ -138,37 +171,51 @@ class CpuReference:
         self.x = np.random.default_rng(1).random(nd.ndofs)
         self.y = np.zeros(nd.ndofs)
         self.ndofs = nd.ndofs
+        self.physical = O.physical_cores()
+        self.quota = cpu_quota()
+        nthreads = self.physical if self.quota is None else max(1, min(self.physical, int(self.quota)))
+        self.arm = O.BlockedApply(O.CURLCURL_MASS, self.interp, self.curl, self.idx, self.ori, self.qd, self.blob, nd.ndofs, nthreads=nthreads)
+        self.cores = self.arm.threads  # pinned threads, one per physical core, at most the container's CPU quota
+        self.logical = os.cpu_count() or 1
 
-    def step(self, nthreads):
+    def step(self):
         self.y[:] = 0.0
         t0 = time.perf_counter()
-        self.O.apply_add_mt(nthreads, self.O.CURLCURL_MASS, self.interp, self.curl, self.idx, self.ori, self.qd, self.blob, self.x, self.y)
+        self.arm.apply_add(self.x, self.y)
         return time.perf_counter() - t0
+
+    def median_step(self, steps, warmup=2):
+        for _ in range(max(1, warmup)):
+            self.step()
+        dts = sorted(self.step() for _ in range(max(1, steps)))
+        return dts[len(dts) // 2], dts
 
     @property
     def dofs_per_step(self):
         return self.ndofs * (self.ns / self.ne)
 
+    def describe(self, steps):
+        return (f"{self.ns} of {self.ne} elements per step, median of {steps} steps; dense non-tensor basis apply (oracle port of the libCEED "
+                f"/cpu/self path, blocks of 8 elements, {self.cores} threads pinned one per physical core; host: {self.physical} physical cores / "
+                f"{self.logical} logical CPUs, container CPU quota {'none' if self.quota is None else round(self.quota, 1)}, "
+                f"{'-march=native build on this host' if self.native else 'portable x86-64-v3 build'}; the reference itself is unbuildable here)")
+
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    prob = build_problem(args.n, args.order, args.warp)
-    cores = os.cpu_count() or 1
+    prob = build_problem(args.n, args.order, args.warp, coefficient=args.coefficient)
     ref = CpuReference(prob, args.cpu_sample_elems)  # default: the whole 2M-dof mesh every step
-    for _ in range(max(1, min(args.warmup, 2))):
-        ref.step(cores)
     steps = max(1, args.steps)
-    t_tot = sum(ref.step(cores) for _ in range(steps))
-    value = float(ref.dofs_per_step * steps / t_tot / 1e6)
+    med, dts = ref.median_step(steps, warmup=max(1, min(args.warmup, 3)))
+    value = float(ref.dofs_per_step / med / 1e6)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, prob, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{ref.ns} of {ref.ne} elements per step (dense non-tensor basis apply: oracle port of the libCEED /cpu/self path, "
-                                   f"{'-march=native build on this host' if ref.native else 'portable x86-64-v3 build'}; the reference itself is unbuildable here)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": ref.describe(steps),
+                         "min_ms": 1e3 * dts[0], "max_ms": 1e3 * dts[-1]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -178,78 +225,75 @@ def workload_config(args, prob, world):
     nd = prob["nd"]
     return {
         "workload": f"ND hex p={args.order} curl-curl+mass ParOperator Mult (P, local apply, P^T) on a uniform {args.n}^3-elements-per-GPU box mesh, stored per-point geometry"
-                    + (" (assembled D)" if args.assemble_qdata else " (J^-T, w detJ; coefficient applied on the fly)"),
+                    + (" (assembled D)" if args.assemble_qdata else " (J^-T, w detJ; coefficient applied on the fly)")
+                    + ("; four striped materials with full 3x3 tensors" if args.coefficient == "matrix4" else "; one isotropic material")
+                    + (f"; mesh warped by {args.warp}" if args.warp else ""),
         "order": args.order, "elements_per_gpu": int(args.n ** 3), "global_true_dofs": int(nd.ndofs), "n_gpus": world,
-        "partition": "1 block per GPU, shared dofs summed by NCCL send/recv" if world > 1 else "single partition",
+        "partition": ("1 block per GPU; shared dofs exchanged through peer memory over NVLink (CUDA-IPC mailboxes: stores + epoch flags, "
+                      "fused into one kernel before and one after the element kernel, replayed from a CUDA graph)"
+                      if os.environ.get("B2P_HALO_P2P", "1") == "1" else
+                      "1 block per GPU; shared dofs exchanged by NCCL grouped send/recv") if world > 1 else "single partition",
         "vector": "true-dof (T) vector", "l2_policy": "L2 flushed (256 MiB write) between timed iterations",
     }
 
 
 def run_experiments(args):
-    """Opt-in variants of the hot path (parity-green on the CPU emulation build, not yet the default) measured in child
-    processes on the same workload, so that a failure of one of them cannot touch the headline numbers above. Each entry
-    repeats `value` (MDoF/s per ParOperator::Mult) and the kernel time / roofline fraction of that variant."""
-    variants = {
-        "pdl_zero_fill_overlap": {"B2P_PDL": "1"},
-        "xdx_consumes_z_region": {"B2P_ND_FWDCHAIN": "1"},
-        "both": {"B2P_PDL": "1", "B2P_ND_FWDCHAIN": "1"},
-    }
-    out = {"note": "opt-in kernel variants, each measured by a child process of this run; not part of value / roofline above"}
+    """Side measurements of the same run, each taken by a child process (a failure or hang of one of them cannot touch the
+    headline numbers) and printed as ITS OWN short JSON line -- {"experiment": name, ...} -- before the headline line, so that
+    none of them can fall off a log tail. The headline line stays the last line of the output."""
     t_start, budget_s = time.time(), float(os.environ.get("B2P_BENCH_EXPERIMENT_BUDGET_S", "330"))
-    for name, env in variants.items():
+    common = ["--steps", str(args.steps), "--warmup", str(args.warmup), "--order", str(args.order), "--n", str(args.n),
+              "--no-cpu-baseline", "--no-experiments"]
+    # (1) the same bench on other kernels / coefficients: value, kernel time and roofline fraction of each
+    variants = {
+        "matrix_coefficient_warped_mesh": (["--coefficient", "matrix4", "--warp", "0.05"], {}),
+        "round1_kernel_nd_hex_apply4": ([], {"B2P_ND_KERNEL": "4"}),
+        "zero_fill_overlap_pdl": ([], {"B2P_PDL": "1"}),
+    }
+    # (2) prepared tool measurements (tools/): one JSON line each
+    tools = {
+        "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--steps", "50"], {}),
+        "solver_loop_p3_2M": (["tools/solver_bench.py"], {}),
+        "cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "4", "--refine", "0", "--nev", "4"], {}),
+        "tet_dense_p3": (["tools/tet_bench.py", "--order", "3", "--n", "14", "--steps", "30"], {}),
+        "tet_dense_p6": (["tools/tet_bench.py", "--order", "6", "--n", "6", "--steps", "10"], {}),
+    }
+    child = os.environ.get("B2P_BENCH_CHILD")  # (the CPU dry-run harness points this at itself)
+    if child:  # CPU dry run: tiny sizes
+        tools = {"complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--n", "3", "--steps", "2"], {}),
+                 "solver_loop_p3_2M": (["tools/solver_bench.py", "--n", "3"], {})}
+
+    def emit(name, payload):
+        print(json.dumps(dict({"experiment": name}, **payload)), flush=True)
+
+    for name, (extra, env) in variants.items():
         if time.time() - t_start > budget_s:
-            out[name] = {"skipped": "experiment time budget used up"}
+            emit(name, {"skipped": "experiment time budget used up"})
             continue
         try:
-            child = os.environ.get("B2P_BENCH_CHILD", os.path.abspath(__file__))  # (the CPU dry-run harness points this at itself)
-            r = subprocess.run([sys.executable, child, "--steps", str(args.steps), "--warmup", str(args.warmup), "--order",
-                                str(args.order), "--n", str(args.n), "--no-cpu-baseline", "--no-experiments"],
+            r = subprocess.run([sys.executable, child or os.path.abspath(__file__)] + common + extra,
                                env=dict(os.environ, B2P_BENCH_EXPERIMENTS="0", **env), capture_output=True, text=True, timeout=150)
             last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
             if not last:
                 raise RuntimeError("no result line; stderr tail: " + r.stderr.strip()[-160:])
             d = json.loads(last[-1])
-            out[name] = {"env": env, "value": d["value"], "ms_per_step": d["ms_per_step"], "kernel_ms": d["roofline"]["kernel_ms"],
-                         "roofline_frac": d["roofline"]["frac"]}
+            emit(name, {"args": extra, "env": env, "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                        "kernel": d["roofline"]["kernel"], "kernel_ms": d["roofline"]["kernel_ms"], "roofline_frac": d["roofline"]["frac"]})
         except Exception as exc:
-            out[name] = {"env": env, "failed": f"{type(exc).__name__}: {str(exc)[:200]}"}
-    # other prepared measurements (tools/): one JSON line each
-    tools = {
-        "cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "4", "--refine", "0", "--nev", "4"], {}),
-        "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--steps", "50"], {}),
-        "solver_loop_p3_2M": (["tools/solver_bench.py"], {}),
-        "solver_loop_p3_2M_all_opt_ins": (["tools/solver_bench.py"], {"B2P_COARSE_CG_CHECK": "8", "B2P_INTERP_OWNER": "1", "B2P_PDL": "1",
-                                                                     "B2P_ND_FWDCHAIN": "1"}),
-        "solver_loop_p3_2M_assembled_coarse_level": (["tools/solver_bench.py"], {"B2P_COARSE_ASSEMBLED": "1"}),
-        "tet_dense_p3": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {}),
-        "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "3", "--n", "10", "--steps", "30"], {"B2P_DENSE_NT": "4"}),
-        "cylinder_cavity_p4_assembled_coarse_level": (["tools/cylinder_bench.py", "--order", "4", "--refine", "0", "--nev", "4"],
-                                                      {"B2P_COARSE_ASSEMBLED": "1"}),
-    }
-    if os.environ.get("B2P_BENCH_CHILD"):  # CPU dry run: tiny sizes
-        tools = {"cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "1", "--nev", "1", "--tol", "1e-6"], {}),
-                 "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--n", "3", "--steps", "2"], {}),
-                 "solver_loop_p3_2M_all_opt_ins": (["tools/solver_bench.py", "--n", "3"], {"B2P_COARSE_CG_CHECK": "8", "B2P_INTERP_OWNER": "1",
-                                                                                          "B2P_PDL": "1", "B2P_ND_FWDCHAIN": "1"}),
-                 "solver_loop_p3_2M_assembled_coarse_level": (["tools/solver_bench.py", "--n", "3"], {"B2P_COARSE_ASSEMBLED": "1"}),
-                 "tet_dense_p3_4_tiles": (["tools/tet_bench.py", "--order", "2", "--n", "2", "--steps", "2"], {"B2P_DENSE_NT": "4"})}
+            emit(name, {"args": extra, "env": env, "failed": f"{type(exc).__name__}: {str(exc)[:200]}"})
     for name, (cmd, env) in tools.items():
         if time.time() - t_start > budget_s:
-            out[name] = {"skipped": "experiment time budget used up"}
+            emit(name, {"skipped": "experiment time budget used up"})
             continue
         try:
-            if os.environ.get("B2P_BENCH_CHILD"):
-                argv = [sys.executable, os.environ["B2P_BENCH_CHILD"], os.path.join(ROOT, cmd[0])] + cmd[1:]
-            else:
-                argv = [sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:]
+            argv = [sys.executable] + ([child] if child else []) + [os.path.join(ROOT, cmd[0])] + cmd[1:]
             r = subprocess.run(argv, env=dict(os.environ, B2P_BENCH_EXPERIMENTS="0", **env), capture_output=True, text=True, timeout=150, cwd=ROOT)
             last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
             if not last:
                 raise RuntimeError("no result line; stderr tail: " + r.stderr.strip()[-160:])
-            out[name] = json.loads(last[-1])
+            emit(name, json.loads(last[-1]))
         except Exception as exc:
-            out[name] = {"failed": f"{type(exc).__name__}: {str(exc)[:200]}"}
-    return out
+            emit(name, {"failed": f"{type(exc).__name__}: {str(exc)[:200]}"})
 
 
 def main():
@@ -286,7 +330,7 @@ def main():
     from palace_b200.host import partition as pt
 
     gn = (args.n * parts[0], args.n * parts[1], args.n * parts[2])
-    prob = build_problem(gn, args.order, args.warp, size=(float(parts[0]), float(parts[1]), float(parts[2])))
+    prob = build_problem(gn, args.order, args.warp, size=(float(parts[0]), float(parts[1]), float(parts[2])), coefficient=args.coefficient)
     p, q1d = prob["p"], prob["q1d"]
     gnd = prob["nd"]
     if world > 1:
@@ -380,12 +424,15 @@ def main():
     torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     abytes = op.algorithmic_bytes()
+    # which sum-factorised kernel the library dispatches for this operator (b2p_core.cu:apply_range)
+    forced = os.environ.get("B2P_ND_KERNEL", "0")
+    kernel_name = "nd_hex_apply6_kernel" if (forced in ("0", "6") and args.order in (2, 3) and not args.assemble_qdata) else "nd_hex_apply4_kernel"
     traffic = None
     try:  # DRAM bytes of the same kernel/launch shape from the committed ncu capture (profiles/)
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)
         if args.order == 3 and args.n == 29 and not args.assemble_qdata and world == 1:
-            k = tr["nd_hex_apply4_kernel<3,4,CURLCURL_MASS,geom>"]
+            k = tr[kernel_name + "<3,4,CURLCURL_MASS,geom>"]
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     except Exception:
         pass
@@ -478,20 +525,17 @@ def main():
             # per rank and step: the apply kernel (+ halo pack and unpack kernels when N > 1); memset/NCCL not counted
             "gpu_launches": int(args.steps * (1 + (2 if world > 1 else 0))),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "nd_hex_apply4_kernel", "kernel_ms": k_ms,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(abytes)},
         }
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            base_prob = prob if world == 1 else build_problem(args.n, args.order, args.warp)
+            base_prob = prob if world == 1 else build_problem(args.n, args.order, args.warp, coefficient=args.coefficient)
             ref = CpuReference(base_prob, args.cpu_sample_elems)
-            ref.step(cores)
-            dts = [ref.step(cores) for _ in range(5)]
-            line["cpu_baseline"] = {"value": ref.dofs_per_step / min(dts) / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{ref.ns} of {ref.ne} elements per apply, best of 5 ({min(dts):.3f} s); dense non-tensor basis apply (oracle port, "
-                                              f"{'-march=native' if ref.native else 'x86-64-v3'} build)"}
+            med, dts = ref.median_step(10, warmup=2)
+            line["cpu_baseline"] = {"value": ref.dofs_per_step / med / 1e6, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                                    "sample": ref.describe(10), "min_ms": 1e3 * dts[0], "max_ms": 1e3 * dts[-1]}
         if world == 1 and not args.no_experiments and os.environ.get("B2P_BENCH_EXPERIMENTS", "1") == "1":
-            line["experiments"] = run_experiments(args)
+            run_experiments(args)  # one JSON line each, before the headline
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

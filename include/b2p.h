@@ -344,6 +344,50 @@ int b2p_solver_stats(b2p_solver *s, int *its, double *initial_res, double *final
 int b2p_solver_lambda_max(b2p_solver *s, double *out); /* Chebyshev: estimated lambda_max(D^-1 A) * sf_max */
 void b2p_solver_destroy(b2p_solver *s);
 
+/* ---- BaseKspSolver: configuration -> Krylov solver + preconditioner (linalg/ksp.cpp:29-102,131-239,256-328) ----
+ * The fields mirror config::LinearSolverData (utils/configfile.hpp:1000-1120) with the defaults iodata.cpp:500-545 derives;
+ * b2p_ksp_config_default fills them for a solution space of polynomial order `order`. The composer builds
+ *   ConfigureKrylovSolver:          CG / GMRES / FGMRES with restart size, tolerances, orthogonalisation, preconditioner side
+ *   ConfigurePreconditionerSolver:  one level  -> the coarse solver alone (Jacobi, or PCG-Jacobi on the assembled matrix)
+ *                                   n levels   -> GeometricMultigridSolver(coarse, P, mg_smooth_aux ? G : NULL, mg_cycle_it,
+ *                                                  mg_smooth_it, mg_smooth_order, sf_max, sf_min, cheby_4th)
+ * and keeps the reference's counters NumTotalMult / NumTotalMultIts. The sparse-direct / HYPRE coarse solvers of the
+ * reference stay outside this library: coarse_type 2 takes a caller-supplied b2p_solver instead. */
+typedef struct b2p_ksp b2p_ksp;
+typedef struct
+{
+  int krylov_solver;     /* 0 CG, 1 GMRES, 2 FGMRES                                   (KrylovSolver) */
+  double tol;            /* relative residual tolerance                               (linear.tol, 1e-6) */
+  int max_it;            /* (linear.max_it, 100) */
+  int max_size;          /* GMRES / FGMRES restart dimension; <= 0: max_it            (linear.max_size) */
+  int initial_guess;     /* use the incoming y as the initial guess                   (linear.initial_guess) */
+  int pc_side;           /* -1 default of the solver, 0 right, 1 left                 (PreconditionerSide) */
+  int gs_orthog;         /* 0 MGS, 1 CGS, 2 CGS2                                      (Orthogonalization) */
+  int mg_cycle_it;       /* V-cycles per preconditioner application                   (linear.mg_cycle_it, 1) */
+  int mg_smooth_aux;     /* Hiptmair distributive relaxation on the levels > 0        (linear.mg_smooth_aux) */
+  int mg_smooth_it;      /* pre/post smoothing iterations                             (linear.mg_smooth_it, 1) */
+  int mg_smooth_order;   /* Chebyshev order; <= 0: max(2 * order, 4)                  (iodata.cpp:533-536) */
+  double mg_smooth_sf_max, mg_smooth_sf_min; /* (1.0, 0.0) */
+  int mg_smooth_cheby_4th; /* 4th-kind (1) or 1st-kind (0) Chebyshev                  (true) */
+  int coarse_type;       /* 0 Jacobi (LinearSolver::JACOBI), 1 Jacobi-PCG on the device-assembled level-0 matrix
+                          * (MfemWrapperSolver analogue), 2 caller-supplied solver */
+  double coarse_tol;     /* coarse_type 1: relative tolerance of the inner PCG */
+  int coarse_max_it;
+} b2p_ksp_config;
+int b2p_ksp_config_default(b2p_ksp_config *cfg, int order);
+/* P[n_levels-1] prolongations, G[n_levels] discrete gradients (read when mg_smooth_aux; G[0] unused), coarse_solver only
+ * for coarse_type 2 (ownership moves into the composed solver). n_levels == 1: no multigrid, the coarse solver preconditions. */
+int b2p_ksp_create(b2p_ctx *ctx, const b2p_ksp_config *cfg, int n_levels, b2p_operator *const *P, b2p_operator *const *G,
+                   b2p_solver *coarse_solver, b2p_ksp **out);
+/* KspSolver::SetOperators(op, pc_op): `op` the system operator; pc_ops[n_levels] the preconditioner's level operators and
+ * aux_ops[n_levels] their auxiliary-space (H1) operators (BaseMultigridOperator), aux_ops may be NULL without mg_smooth_aux. */
+int b2p_ksp_set_operators(b2p_ksp *k, b2p_operator *op, b2p_operator *const *pc_ops, b2p_operator *const *aux_ops);
+int b2p_ksp_mult(b2p_ksp *k, const double *x, double *y);
+/* NumTotalMult(), NumTotalMultIts() (ksp.hpp:57-58) and the last solve's record */
+int b2p_ksp_stats(b2p_ksp *k, int *num_total_mult, int *num_total_mult_its, int *last_its, double *initial_res, double *final_res,
+                  int *converged);
+void b2p_ksp_destroy(b2p_ksp *k);
+
 /* ---- complex-valued operators and Krylov solvers on split (real, imag) vectors ---------------------
  * Palace's ComplexVector is two real vectors (linalg/vector.hpp:23-27); every entry takes the two device
  * pointers separately. Inner product convention Dot(x, y) = y^H x (linalg/vector.cpp:674-685). */

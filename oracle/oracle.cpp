@@ -19,8 +19,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
+#include <pthread.h>
+#include <sched.h>
 #include "basis1d.hpp"
 
 using orc::ld;
@@ -649,6 +656,321 @@ void orc_apply_add_mt(int nthreads, int kind, int ne, int P, int Q, const double
         });
   }
   for (auto &t : th) t.join();
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reference arm of bench.py (`--impl reference`, `cpu_baseline`): the same dense-basis algorithm as orc_apply_add,
+// organised the way libCEED's /cpu/self/opt/blocked backend runs it on the host -- blocks of 8 elements with the
+// element index innermost (one SIMD lane per element), a PERSISTENT pool of threads pinned one per physical core,
+// and a precomputed transposed restriction (dof -> E-vector entries, libCEED's t_offsets) so that the scatter-add is a
+// race-free parallel loop over dofs. Same arithmetic per element as orc_apply_add (verified against it in
+// tests/test_oracle_identities.py); only the loop order and the threading differ.
+// ---------------------------------------------------------------------------------------------------------------
+namespace
+{
+constexpr int BLK = 8;
+
+struct OrcPool
+{
+  int nt = 0;
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  std::function<void(int)> job;
+  long long epoch = 0;
+  int pending = 0;
+  bool stop = false;
+  void run(const std::function<void(int)> &f)
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    job = f;
+    pending = nt;
+    epoch++;
+    cv_go.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+};
+
+std::vector<int> physical_core_cpus()
+{
+  // one logical CPU per (package, core) pair, among the CPUs this process may run on
+  std::vector<int> out;
+  cpu_set_t allowed;
+  CPU_ZERO(&allowed);
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0)
+  {
+    const unsigned n = std::thread::hardware_concurrency();
+    for (unsigned c = 0; c < (n ? n : 1); c++) out.push_back((int)c);
+    return out;
+  }
+  std::vector<std::pair<int, int>> seen;
+  for (int c = 0; c < CPU_SETSIZE; c++)
+  {
+    if (!CPU_ISSET(c, &allowed)) continue;
+    int pkg = 0, core = c;
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/physical_package_id", c);
+    if (FILE *f = fopen(path, "r"))
+    {
+      if (fscanf(f, "%d", &pkg) != 1) pkg = 0;
+      fclose(f);
+    }
+    snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/core_id", c);
+    if (FILE *f = fopen(path, "r"))
+    {
+      if (fscanf(f, "%d", &core) != 1) core = c;
+      fclose(f);
+    }
+    bool dup = false;
+    for (auto &pc : seen) dup = dup || (pc.first == pkg && pc.second == core);
+    if (!dup)
+    {
+      seen.emplace_back(pkg, core);
+      out.push_back(c);
+    }
+  }
+  if (out.empty()) out.push_back(0);
+  return out;
+}
+
+struct OrcBlocked
+{
+  int ne = 0, P = 0;
+  long long lsize = 0;
+  std::vector<long long> dof_ptr;   // [lsize + 1]
+  std::vector<int> dof_ent;         // E-vector positions e * P + i, grouped by dof
+  std::vector<double> Ye;           // [ne][P] element vectors
+};
+}  // namespace
+
+extern "C"
+{
+
+int orc_physical_cores() { return (int)physical_core_cpus().size(); }
+
+// nthreads <= 0: one thread per physical core, pinned.
+void *orc_pool_create(int nthreads)
+{
+  const std::vector<int> cpus = physical_core_cpus();
+  auto *p = new OrcPool;
+  p->nt = nthreads > 0 ? nthreads : (int)cpus.size();
+  for (int t = 0; t < p->nt; t++)
+  {
+    p->th.emplace_back(
+        [p, t]()
+        {
+          long long seen = 0;
+          for (;;)
+          {
+            std::function<void(int)> f;
+            {
+              std::unique_lock<std::mutex> lk(p->mu);
+              p->cv_go.wait(lk, [&] { return p->stop || p->epoch != seen; });
+              if (p->stop) return;
+              seen = p->epoch;
+              f = p->job;
+            }
+            f(t);
+            {
+              std::unique_lock<std::mutex> lk(p->mu);
+              if (--p->pending == 0) p->cv_done.notify_all();
+            }
+          }
+        });
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    CPU_SET(cpus[t % cpus.size()], &set);
+    pthread_setaffinity_np(p->th.back().native_handle(), sizeof(set), &set);
+  }
+  return p;
+}
+int orc_pool_threads(void *pool) { return ((OrcPool *)pool)->nt; }
+void orc_pool_destroy(void *pool)
+{
+  auto *p = (OrcPool *)pool;
+  if (!p) return;
+  {
+    std::unique_lock<std::mutex> lk(p->mu);
+    p->stop = true;
+    p->cv_go.notify_all();
+  }
+  for (auto &t : p->th) t.join();
+  delete p;
+}
+
+// Set-up (untimed, like CeedElemRestrictionCreate): transposed restriction + the E-vector.
+void *orc_blocked_setup(int ne, int P, const int *idx, long long lsize)
+{
+  auto *b = new OrcBlocked;
+  b->ne = ne;
+  b->P = P;
+  b->lsize = lsize;
+  b->dof_ptr.assign((size_t)lsize + 1, 0);
+  const size_t tot = (size_t)ne * P;
+  for (size_t k = 0; k < tot; k++) b->dof_ptr[(size_t)idx[k] + 1]++;
+  for (long long g = 0; g < lsize; g++) b->dof_ptr[g + 1] += b->dof_ptr[g];
+  b->dof_ent.resize(tot);
+  std::vector<long long> fill(b->dof_ptr.begin(), b->dof_ptr.end() - 1);
+  for (size_t k = 0; k < tot; k++) b->dof_ent[(size_t)fill[idx[k]]++] = (int)k;
+  b->Ye.assign(tot, 0.0);
+  return b;
+}
+void orc_blocked_destroy(void *h) { delete (OrcBlocked *)h; }
+
+// y += A x, blocks of BLK elements handed out dynamically to the pool's threads.
+void orc_apply_add_blocked(void *pool, void *setup, int kind, int ne, int P, int Q, const double *interp, const double *deriv,
+                           const int *idx, const signed char *orient, const double *qdata, const void *ctx, const double *x,
+                           double *y)
+{
+  auto *pl = (OrcPool *)pool;
+  auto *bs = (OrcBlocked *)setup;
+  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
+  const bool need_c = (kind != ND_MASS);
+  const int nblk = (ne + BLK - 1) / BLK, R = 3 * Q;
+  std::atomic<int> next{0};
+  pl->run(
+      [&](int)
+      {
+        std::vector<double> ue((size_t)P * BLK), uq((size_t)R * BLK), cq((size_t)R * BLK), vq((size_t)R * BLK), wq((size_t)R * BLK),
+            ye((size_t)P * BLK), u1(R), c1(R), v1(R), w1(R);
+        for (;;)
+        {
+          const int blk = next.fetch_add(2);  // two blocks per grab (a preempted thread holds back at most 16 elements)
+          if (blk >= nblk) break;
+          for (int bb = blk; bb < std::min(blk + 2, nblk); bb++)
+          {
+            const int e0 = bb * BLK, nel = std::min(BLK, ne - e0);
+            // gather with signs, element index innermost
+            for (int i = 0; i < P; i++)
+              for (int l = 0; l < BLK; l++)
+              {
+                const int e = e0 + (l < nel ? l : 0);
+                const double sg = orient ? (double)orient[(size_t)e * P + i] : 1.0;
+                ue[(size_t)i * BLK + l] = l < nel ? sg * x[idx[(size_t)e * P + i]] : 0.0;
+              }
+            // u = interp ue, c = deriv ue: four rows of the dense tables at a time against BLK element lanes (eight
+            // independent SIMD accumulators cover the FMA latency; every ue vector is loaded once per four rows)
+            for (int r0 = 0; r0 < R; r0 += 4)
+            {
+              const int nr = std::min(4, R - r0);
+              double au[4][BLK] = {{0}}, ac[4][BLK] = {{0}};
+              const double *ri[4], *rd[4];
+              for (int k = 0; k < 4; k++)
+              {
+                ri[k] = interp + (size_t)(r0 + std::min(k, nr - 1)) * P;
+                rd[k] = deriv + (size_t)(r0 + std::min(k, nr - 1)) * P;
+              }
+              if (need_u && need_c)
+                for (int i = 0; i < P; i++)
+                {
+                  const double *__restrict ul = &ue[(size_t)i * BLK];
+                  for (int k = 0; k < 4; k++)
+                  {
+                    const double a = ri[k][i], d = rd[k][i];
+#pragma GCC ivdep
+                    for (int l = 0; l < BLK; l++)
+                    {
+                      au[k][l] += a * ul[l];
+                      ac[k][l] += d * ul[l];
+                    }
+                  }
+                }
+              else if (need_u)
+                for (int i = 0; i < P; i++)
+                {
+                  const double *__restrict ul = &ue[(size_t)i * BLK];
+                  for (int k = 0; k < 4; k++)
+                  {
+                    const double a = ri[k][i];
+#pragma GCC ivdep
+                    for (int l = 0; l < BLK; l++) au[k][l] += a * ul[l];
+                  }
+                }
+              else
+                for (int i = 0; i < P; i++)
+                {
+                  const double *__restrict ul = &ue[(size_t)i * BLK];
+                  for (int k = 0; k < 4; k++)
+                  {
+                    const double d = rd[k][i];
+#pragma GCC ivdep
+                    for (int l = 0; l < BLK; l++) ac[k][l] += d * ul[l];
+                  }
+                }
+              for (int k = 0; k < nr; k++)
+                for (int l = 0; l < BLK; l++)
+                {
+                  uq[(size_t)(r0 + k) * BLK + l] = au[k][l];
+                  cq[(size_t)(r0 + k) * BLK + l] = ac[k][l];
+                }
+            }
+            // pointwise D, element by element (the reference's QFunction arithmetic)
+            for (int l = 0; l < nel; l++)
+            {
+              for (int r = 0; r < R; r++)
+              {
+                u1[r] = uq[(size_t)r * BLK + l];
+                c1[r] = cq[(size_t)r * BLK + l];
+              }
+              orc_apply_D(kind, ctx, Q, qdata + (size_t)(e0 + l) * 11 * Q, u1.data(), c1.data(), v1.data(), w1.data());
+              for (int r = 0; r < R; r++)
+              {
+                vq[(size_t)r * BLK + l] = need_u ? v1[r] : 0.0;
+                wq[(size_t)r * BLK + l] = need_c ? w1[r] : 0.0;
+              }
+            }
+            for (int l = nel; l < BLK; l++)
+              for (int r = 0; r < R; r++) vq[(size_t)r * BLK + l] = wq[(size_t)r * BLK + l] = 0.0;
+            // ye = interp^T v + deriv^T w: four output dofs at a time held in registers across the whole row loop
+            for (int i0 = 0; i0 < P; i0 += 4)
+            {
+              const int ni = std::min(4, P - i0);
+              double acc[4][BLK] = {{0}};
+              for (int r = 0; r < R; r++)
+              {
+                const double *ri = interp + (size_t)r * P + i0, *rd = deriv + (size_t)r * P + i0;
+                const double *__restrict vl = &vq[(size_t)r * BLK], *__restrict wl = &wq[(size_t)r * BLK];
+                for (int k = 0; k < 4; k++)
+                {
+                  const int kk = std::min(k, ni - 1);
+                  const double a = need_u ? ri[kk] : 0.0, d = need_c ? rd[kk] : 0.0;
+#pragma GCC ivdep
+                  for (int l = 0; l < BLK; l++) acc[k][l] += a * vl[l] + d * wl[l];
+                }
+              }
+              for (int k = 0; k < ni; k++)
+                for (int l = 0; l < BLK; l++) ye[(size_t)(i0 + k) * BLK + l] = acc[k][l];
+            }
+            for (int l = 0; l < nel; l++)
+              for (int i = 0; i < P; i++)
+              {
+                const size_t k = (size_t)(e0 + l) * P + i;
+                bs->Ye[k] = (orient ? (double)orient[k] : 1.0) * ye[(size_t)i * BLK + l];
+              }
+          }
+        }
+      });
+  // transposed restriction: every dof sums its E-vector entries (no races, fixed order)
+  const long long lsize = bs->lsize, CH = 8192;
+  std::atomic<long long> nextd{0};
+  pl->run(
+      [&](int)
+      {
+        for (;;)
+        {
+          const long long lo = nextd.fetch_add(CH);
+          if (lo >= lsize) break;
+          const long long hi = std::min(lsize, lo + CH);
+          for (long long g = lo; g < hi; g++)
+          {
+            double sacc = 0.0;
+            for (long long k = bs->dof_ptr[g]; k < bs->dof_ptr[g + 1]; k++) sacc += bs->Ye[bs->dof_ent[k]];
+            y[g] += sacc;
+          }
+        }
+      });
 }
 
 }  // extern "C"

@@ -158,3 +158,43 @@ def apply_add_mt(nthreads, kind, interp, deriv, idx, orient, qdata, ctx, x, y):
     lib().orc_apply_add_mt(int(nthreads), kind, ne, P, Q, _p(interp), _p(deriv), _p(idx), _p(orient), _p(qdata), _p(ctx), _p(x),
                            _p(y), C.c_longlong(y.size))
     return y
+
+
+def physical_cores():
+    lib().orc_physical_cores.restype = C.c_int
+    return int(lib().orc_physical_cores())
+
+
+class BlockedApply:
+    """The reference arm of bench.py: dense-basis apply in blocks of 8 elements (one SIMD lane per element, libCEED
+    /cpu/self/opt/blocked style) on a persistent pool of threads pinned one per physical core, with a precomputed
+    transposed restriction for the scatter-add. Same arithmetic per element as apply_add (tests/test_oracle_identities.py)."""
+
+    def __init__(self, kind, interp, deriv, idx, orient, qdata, ctx, lsize, nthreads=0):
+        L = lib()
+        L.orc_pool_create.restype = C.c_void_p
+        L.orc_blocked_setup.restype = C.c_void_p
+        L.orc_pool_threads.restype = C.c_int
+        self.kind, self.interp, self.deriv, self.idx, self.orient, self.qdata, self.ctx = kind, interp, deriv, idx, orient, qdata, ctx
+        self.ne, self.P = idx.shape
+        self.Q = qdata.shape[-1]
+        self.pool = C.c_void_p(L.orc_pool_create(int(nthreads)))
+        self.threads = int(L.orc_pool_threads(self.pool))
+        self.setup = C.c_void_p(L.orc_blocked_setup(self.ne, self.P, _p(idx), C.c_longlong(int(lsize))))
+
+    def apply_add(self, x, y):
+        lib().orc_apply_add_blocked(self.pool, self.setup, self.kind, self.ne, self.P, self.Q, _p(self.interp), _p(self.deriv),
+                                    _p(self.idx), _p(self.orient), _p(self.qdata), _p(self.ctx), _p(x), _p(y))
+        return y
+
+    def close(self):
+        if self.pool:
+            lib().orc_blocked_destroy(self.setup)
+            lib().orc_pool_destroy(self.pool)
+            self.pool = self.setup = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

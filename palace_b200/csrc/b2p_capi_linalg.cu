@@ -428,3 +428,168 @@ int b2p_solver_lambda_max(b2p_solver *s, double *out)
 void b2p_solver_destroy(b2p_solver *s) { delete s; }
 
 }  // extern "C"
+
+// BaseKspSolver (ksp.cpp:256-328): owns the Krylov solver and its preconditioner, counts solves and iterations.
+struct b2p_ksp
+{
+  b2p_ctx *ctx = nullptr;
+  b2p_ksp_config cfg;
+  int n_levels = 1;
+  std::unique_ptr<IterativeSolver> ksp;
+  std::unique_ptr<Solver> pc;
+  int ksp_mult = 0, ksp_mult_it = 0;
+};
+
+extern "C"
+{
+
+int b2p_ksp_config_default(b2p_ksp_config *c, int order)
+{
+  if (!c || order < 1) return B2P_ERR_ARG;
+  c->krylov_solver = 1;  // GMRES for the frequency-domain problems (iodata.cpp:480-498); CG for the SPD ones
+  c->tol = 1e-6;
+  c->max_it = 100;
+  c->max_size = -1;
+  c->initial_guess = 1;
+  c->pc_side = -1;
+  c->gs_orthog = 0;
+  c->mg_cycle_it = 1;
+  c->mg_smooth_aux = 1;
+  c->mg_smooth_it = 1;
+  c->mg_smooth_order = std::max(2 * order, 4);  // iodata.cpp:533-536
+  c->mg_smooth_sf_max = 1.0;
+  c->mg_smooth_sf_min = 0.0;
+  c->mg_smooth_cheby_4th = 1;
+  c->coarse_type = 1;
+  c->coarse_tol = 1e-3;
+  c->coarse_max_it = 500;
+  return B2P_SUCCESS;
+}
+
+int b2p_ksp_create(b2p_ctx *ctx, const b2p_ksp_config *cfg, int n_levels, b2p_operator *const *P, b2p_operator *const *G,
+                   b2p_solver *coarse_solver, b2p_ksp **out)
+{
+  B2P_CHECK(ctx, ctx && cfg && out && n_levels >= 1, B2P_ERR_ARG, "b2p_ksp_create: bad argument");
+  B2P_CHECK(ctx, cfg->krylov_solver >= 0 && cfg->krylov_solver <= 2, B2P_ERR_ARG,
+            "b2p_ksp_create: Unexpected solver type for Krylov solver configuration!");
+  B2P_CHECK(ctx, n_levels == 1 || P, B2P_ERR_ARG, "b2p_ksp_create: a multigrid hierarchy needs its prolongation operators");
+  B2P_CHECK(ctx, n_levels == 1 || !cfg->mg_smooth_aux || G, B2P_ERR_ARG,
+            "Multigrid with auxiliary space smoothers requires both primary space and auxiliary spaces for construction!");
+  auto k = std::make_unique<b2p_ksp>();
+  k->ctx = ctx;
+  k->cfg = *cfg;
+  k->n_levels = n_levels;
+  // ConfigureKrylovSolver (ksp.cpp:29-102)
+  k->ksp = std::make_unique<IterativeSolver>(ctx, (KspType)cfg->krylov_solver);
+  k->ksp->rel_tol = cfg->tol;
+  k->ksp->max_it = cfg->max_it;
+  k->ksp->max_dim = cfg->max_size > 0 ? cfg->max_size : cfg->max_it;
+  k->ksp->gs = (Orthog)cfg->gs_orthog;
+  if (cfg->pc_side >= 0 && cfg->krylov_solver != 0) k->ksp->pc_side = (PcSide)cfg->pc_side;  // ignored for CG, as in the reference
+  k->ksp->SetInitialGuess(cfg->initial_guess != 0);
+  // ConfigurePreconditionerSolver (ksp.cpp:131-239): the coarse solver first ...
+  std::unique_ptr<Solver> coarse;
+  switch (cfg->coarse_type)
+  {
+    case 0: coarse = std::make_unique<JacobiSmoother>(ctx, 1.0, 1.0); break;
+    case 1:
+    {
+      auto cg = std::make_unique<IterativeSolver>(ctx, KspType::CG);
+      cg->rel_tol = cfg->coarse_tol;
+      cg->max_it = cfg->coarse_max_it;
+      auto jac = std::make_unique<JacobiSmoother>(ctx, 1.0, 1.0);
+      cg->SetPreconditioner(jac.get());
+      coarse = std::make_unique<AssembledSolver>(ctx, std::move(cg), std::move(jac));
+      break;
+    }
+    case 2:
+      B2P_CHECK(ctx, coarse_solver && coarse_solver->s, B2P_ERR_ARG, "b2p_ksp_create: coarse_type 2 needs a coarse solver");
+      coarse = std::move(coarse_solver->s);
+      break;
+    default: B2P_CHECK(ctx, false, B2P_ERR_ARG, "Unexpected solver type for preconditioner configuration!");
+  }
+  // ... then the multigrid hierarchy around it when there is more than one level
+  if (n_levels > 1)
+  {
+    std::vector<const Operator *> Pv, Gv;
+    for (int l = 0; l + 1 < n_levels; l++)
+    {
+      B2P_CHECK(ctx, P[l] && P[l]->op, B2P_ERR_ARG, "b2p_ksp_create: no prolongation between levels %d and %d", l, l + 1);
+      Pv.push_back(P[l]->op.get());
+    }
+    if (cfg->mg_smooth_aux)
+      for (int l = 0; l < n_levels; l++)
+      {
+        B2P_CHECK(ctx, l == 0 || (G[l] && G[l]->op), B2P_ERR_ARG, "b2p_ksp_create: level %d has no discrete gradient", l);
+        Gv.push_back(G[l] ? G[l]->op.get() : nullptr);
+      }
+    k->pc = std::make_unique<GeometricMultigridSolver>(ctx, std::move(coarse), Pv, Gv, cfg->mg_cycle_it, cfg->mg_smooth_it,
+                                                       cfg->mg_smooth_order, cfg->mg_smooth_sf_max, cfg->mg_smooth_sf_min,
+                                                       cfg->mg_smooth_cheby_4th != 0);
+  }
+  else
+    k->pc = std::move(coarse);
+  k->ksp->SetPreconditioner(k->pc.get());
+  *out = k.release();
+  return B2P_SUCCESS;
+}
+
+int b2p_ksp_set_operators(b2p_ksp *k, b2p_operator *op, b2p_operator *const *pc_ops, b2p_operator *const *aux_ops)
+{
+  if (!k || !op || !pc_ops) return B2P_ERR_ARG;
+  b2p_ctx *ctx = k->ctx;
+  B2P_TRY(ctx, k->ksp->SetOperator(*op->op));  // ksp.cpp:295-297
+  if (auto *g = dynamic_cast<GeometricMultigridSolver *>(k->pc.get()))
+  {
+    std::vector<const ParOperator *> Av, Gv;
+    for (int l = 0; l < k->n_levels; l++)
+    {
+      B2P_CHECK(ctx, pc_ops[l] && pc_ops[l]->op, B2P_ERR_ARG, "b2p_ksp_set_operators: level %d has no operator", l);
+      auto *pa = dynamic_cast<ParOperator *>(pc_ops[l]->op.get());
+      B2P_CHECK(ctx, pa, B2P_ERR_ARG, "GeometricMultigridSolver requires ParOperator operators!");
+      Av.push_back(pa);
+      auto *pg = (aux_ops && aux_ops[l]) ? dynamic_cast<ParOperator *>(aux_ops[l]->op.get()) : nullptr;
+      const bool dist = dynamic_cast<DistRelaxationSmoother *>(g->B[l].get()) != nullptr;
+      B2P_CHECK(ctx, !dist || pg, B2P_ERR_ARG, "b2p_ksp_set_operators: level %d needs an auxiliary-space ParOperator", l);
+      Gv.push_back(pg);
+    }
+    B2P_TRY(ctx, g->SetOperators(Av, Gv));
+  }
+  else
+  {
+    // one level: the finest (only) preconditioner operator goes to the solver itself (ksp.cpp:302-305)
+    B2P_CHECK(ctx, pc_ops[0] && pc_ops[0]->op, B2P_ERR_ARG, "b2p_ksp_set_operators: no preconditioner operator");
+    B2P_TRY(ctx, k->pc->SetOperator(*pc_ops[0]->op));
+  }
+  return B2P_SUCCESS;
+}
+
+int b2p_ksp_mult(b2p_ksp *k, const double *x, double *y)
+{
+  if (!k || !x || !y) return B2P_ERR_ARG;
+  B2P_CHECK(k->ctx, k->ksp->Height() > 0, B2P_ERR_ARG, "b2p_ksp_mult before b2p_ksp_set_operators");
+  B2P_TRY(k->ctx, k->ksp->Mult(x, y));
+  if (!k->ksp->converged)
+    set_error(k->ctx, "Linear solver did not converge, norm(Ax-b)/norm(b) = %.3e (norm(b) = %.3e)!", k->ksp->final_res / k->ksp->initial_res,
+              k->ksp->initial_res);  // a warning in the reference (ksp.cpp:316-322): recorded, not an error code
+  k->ksp_mult++;
+  k->ksp_mult_it += k->ksp->final_it;
+  return B2P_SUCCESS;
+}
+
+int b2p_ksp_stats(b2p_ksp *k, int *num_total_mult, int *num_total_mult_its, int *last_its, double *initial_res, double *final_res,
+                  int *converged)
+{
+  if (!k) return B2P_ERR_ARG;
+  if (num_total_mult) *num_total_mult = k->ksp_mult;
+  if (num_total_mult_its) *num_total_mult_its = k->ksp_mult_it;
+  if (last_its) *last_its = k->ksp->final_it;
+  if (initial_res) *initial_res = k->ksp->initial_res;
+  if (final_res) *final_res = k->ksp->final_res;
+  if (converged) *converged = k->ksp->converged ? 1 : 0;
+  return B2P_SUCCESS;
+}
+
+void b2p_ksp_destroy(b2p_ksp *k) { delete k; }
+
+}  // extern "C"

@@ -286,10 +286,11 @@ public:
   // (operator.cpp:98-134) and streams the geometry once.
   void build_fused()
   {
-    // Opt-in for now (B2P_COMPLEX_FUSED=1): validated against the term-by-term path under the SIMT emulation of
-    // tests/emu and by tests/test_zfused_gpu.py; becomes the default once measured on a B200.
+    // Default since round 2: measured on a B200 at 0.136 ms per complex matvec of K + lossy M + conductivity term on 2.02M
+    // complex dofs against 0.351 ms term by term (2.6x, profiles/r02_zfused_p3.json); parity with the term-by-term path in
+    // tests/test_zfused_gpu.py. B2P_COMPLEX_FUSED=0 keeps one real apply per term and part.
     const char *env = std::getenv("B2P_COMPLEX_FUSED");
-    if (!env || env[0] != '1') return;
+    if (env && env[0] == '0') return;
     const b2p_op *o0 = terms[0].op;
     for (auto &t : terms)
     {

@@ -104,15 +104,17 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   if (simple) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
   // One-element-per-warp variant (p = 3, q1d = 4, mirror-symmetric tables): opt-in through the apply flag or
   // B2P_ND_KERNEL=5; measured slower than nd_hex_apply4_kernel on B200, kept for the analysis.
+  // B2P_ND_KERNEL = 4 | 5 | 6 forces one of the sum-factorised ND kernels; default: the register-gather pipeline
+  // nd_hex_apply6_kernel where it is the faster one on B200 (p = 2, 3 at q1d = p + 1: 51.1 vs 54.6 us at p = 3, 78.5 vs 90.6 us
+  // at p = 2, profiles/r02_nd6_variants.txt), nd_hex_apply4_kernel everywhere else.
   static const int nd_kernel = []
   {
     const char *e = std::getenv("B2P_ND_KERNEL");
-    return e ? std::atoi(e) : 4;
+    return e ? std::atoi(e) : 0;
   }();
   if (((flags & B2P_APPLY_HALFWARP_KERNEL) || nd_kernel == 5) && nd_hex_apply5_eligible(op))
     return launch_nd_hex_apply5(op, lidx, alpha, x, y, rg, s);
-  // Register-staged pipeline (b2p_hex_nd6.cu): B2P_ND_KERNEL=6
-  if (nd_kernel == 6 && nd_hex_apply6_eligible(op))
+  if ((nd_kernel == 6 || nd_kernel == 0) && nd_hex_apply6_eligible(op))
   {
     static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
     if (trace) fprintf(stderr, "[b2p] nd_hex_apply6 p=%d q1d=%d kind=%d ne=%d\n", op->p, op->q1d, op->kind, op->ne);
@@ -174,6 +176,8 @@ int b2p_ctx_create(int cuda_device, b2p_ctx **out)
   ctx->red_cap = 4096;
   B2P_CUDA(nullptr, cudaMalloc((void **)&ctx->d_red, ctx->red_cap * sizeof(double)));
   B2P_CUDA(nullptr, cudaMallocHost((void **)&ctx->h_red, ctx->red_cap * sizeof(double)));
+  B2P_CUDA(nullptr, cudaMalloc((void **)&ctx->d_sink, b2p_ctx::SINK_SLOTS * sizeof(double)));
+  B2P_CUDA(nullptr, cudaMemset(ctx->d_sink, 0, b2p_ctx::SINK_SLOTS * sizeof(double)));
   *out = ctx;
   return B2P_SUCCESS;
 }
@@ -955,6 +959,7 @@ void b2p_ctx_destroy(b2p_ctx *ctx)
 {
   if (!ctx) return;
   cudaFree(ctx->d_red);
+  cudaFree(ctx->d_sink);
   cudaFreeHost(ctx->h_red);
   if (ctx->graph_stream) cudaStreamDestroy(ctx->graph_stream);
   delete ctx;

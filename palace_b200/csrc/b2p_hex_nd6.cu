@@ -21,7 +21,9 @@
 // Reference semantics: ceed::Operator::AddMult over CeedOperatorApplyAdd
 // (/root/reference/palace/fem/libceed/operator.cpp:148-178,192-212); D from
 // /root/reference/palace/fem/qfunctions/33/{hdiv,hcurl,hdivmass}_33_qf.h.
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "b2p_internal.hpp"
@@ -43,15 +45,21 @@ struct ND6Params
   const double *ecoef;  // [ne][18] per-element coefficient matrices (value part, derivative part)
   const double *x;
   double *y;
+  double *sink;  // [SINK_SLOTS] scratch: masked entries scatter 0.0 into the thread's slot (branch-free RED)
   double alpha;
   int ne;
   VSplit sp;
   const unsigned long long *wait_flags, *wait_expect;  // peer-memory halo flags (SPLIT kernels only)
   int wait_n, wait_from_elem;
   int iso;  // all coefficient matrices are multiples of the identity
-  double Bo[Q_ * P_];
-  double Bc[Q_ * (P_ + 1)];
-  double Gc[Q_ * (P_ + 1)];
+  // 1-D tables, rows c < H = ceil(q/2) only: the launcher has verified the mirror symmetry of MFEM's Gauss-Legendre /
+  // Gauss-Lobatto bases on a symmetric point set, Bo[q-1-c][p-1-i] = Bo[c][i], Bc[q-1-c][n-1-i] = Bc[c][i],
+  // Gc[q-1-c][n-1-i] = -Gc[c][i]. ptxas keeps every table entry a DFMA touches in a REGISTER (no constant-bank operand
+  // on the FP64 pipe of sm_100a: 0 of 924 DFMA in the round-1 SASS), so half the rows is 40 registers less.
+  static constexpr int H = (Q_ + 1) / 2;
+  double Bo[H * P_];
+  double Bc[H * (P_ + 1)];
+  double Gc[H * (P_ + 1)];
 };
 
 struct Nd6Pad
@@ -81,7 +89,10 @@ constexpr int nd6_lane_stride(int items, int nel)
 
 // Work-array layout: identical to ND4Layout (b2p_hex_nd4.cu) -- rows over the index the next phase contracts, padded
 // row strides from b2p_nd4_pads.inc -- minus the staging buffers.
-template <int P_, int Q_, int KIND>
+// ALIAS: the Y region (written by the second half of XDX, read by Yt) lies on top of the Z region (read by the first
+// half of XDX, written by Yt) -- two extra __syncwarp() separate the reads of one from the writes of the other.
+// GSM: the batch's q-data is staged in shared memory by TMA (as in nd_hex_apply4_kernel) instead of LDG into registers.
+template <int P_, int Q_, int KIND, bool ALIAS = false, bool GSM = false>
 struct ND6Layout
 {
   static constexpr int p = P_, q = Q_, n = P_ + 1, Q = q * q * q, P = 3 * p * n * n, D3 = p * n * n;
@@ -98,16 +109,17 @@ struct ND6Layout
   static constexpr int Y_X1 = 0, Y_X2 = Y_X1 + (MASS ? NEW * NXA : 0), Y_X3 = Y_X2 + (CURL ? NEW * NXA : 0),
                        Y_Y1 = Y_X3 + (CURL ? NEW * NXA : 0), Y_Y2 = Y_Y1 + NEW * NNA, Y_Z1 = Y_Y2 + (CURL ? NEW * NNA : 0),
                        Y_Z3 = Y_Z1 + NEW * NNA, LY = Y_Z3 + (CURL ? NEW * NNA : 0), RSY = LY + PAD.y;
-  static constexpr int Y0 = ZSZ, WTOT = (Y0 + q * RSY + 1) & ~1;
+  static constexpr int Y0 = ALIAS ? 0 : ZSZ, WEND = (ALIAS && ZSZ > q * RSY) ? ZSZ : Y0 + q * RSY, WTOT = (WEND + 1) & ~1;
   static constexpr int LSX = nd6_lane_stride(p * n, NEW), LSZ = nd6_lane_stride(n * n, NEW);
   static constexpr int GE = 10 * Q;   // doubles of q-data per element
   static constexpr int CE = 18;       // coefficient matrices per element
   // one ring slot: the batch's index rows followed by its coefficient blocks (one mbarrier, one transaction count)
   static constexpr int SLOT_I = NEW * PS * 4, SLOT_C = NEW * CE * 8, SLOT = (SLOT_I + SLOT_C + 15) & ~15;
-  static constexpr int OFF_W = 0;
+  static constexpr int OFF_G = 0;                     // [NEW * GE] doubles of staged q-data (GSM)
+  static constexpr int OFF_W = OFF_G + (GSM ? NEW * GE * 8 : 0);
   static constexpr int OFF_R = OFF_W + WTOT * 8;      // [3] ring slots
-  static constexpr int OFF_B = OFF_R + 3 * SLOT;      // 3 mbarriers
-  static constexpr int WS = (OFF_B + 3 * 8 + 15) & ~15;
+  static constexpr int OFF_B = OFF_R + 3 * SLOT;      // 3 ring mbarriers + 1 for the q-data
+  static constexpr int WS = (OFF_B + 4 * 8 + 15) & ~15;
   // Z-phase lane rounds and the x values a lane keeps per round
   static constexpr int LW = (NEW * LSX > NEW * LSZ) ? NEW * LSX : NEW * LSZ;
   static constexpr int ZROUNDS = (LW + 31) / 32;
@@ -117,7 +129,9 @@ struct ND6Layout
 #ifdef B2P_EMU
 inline double ldg_stream_f64(const double *p) { return *p; }
 inline void prefetch_l2_bulk(const void *, uint32_t) {}
+inline void prefetch_l1(const void *) {}
 #else
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // streaming read: the q-data is used exactly once per launch -- keep it out of L1 (the x gathers reuse lines there)
 __device__ __forceinline__ double ldg_stream_f64(const double *p)
 {
@@ -131,15 +145,46 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes)
 }
 #endif
 
-template <int P_, int Q_, int KIND, bool SPLIT, int NW, int MINB, bool FWD>
+// FWD: XDX consumes the Z region (no forward Y phase / Y region; the backward Y region aliases the Z region).
+// GSM: q-data through shared memory (TMA) instead of LDG into registers.  XLATE: gather the next batch's x values after
+// XDX instead of right after the Z phase (their registers are then not live across XDX).
+// Scatter-add without a predicate: ptxas turns every predicated RED into a branch region (BSSY / BRA / BSYNC), which cuts
+// the Zt phase into basic blocks of two short DFMA chains. Masked entries (B2P_SKIP_IDX; idle lanes and tail slots carry it
+// too) add 0.0 to the thread's own slot of a scratch array instead -- distinct addresses, no hot spot.
+template <bool SPLIT>
+__device__ __forceinline__ void scatter_nb(double *y, const VSplit &sp, double *sink, int32_t gi, double v)
+{
+  const bool skip = gi == (int32_t)B2P_SKIP_IDX;
+  const int hi = __double2hiint(v) ^ (gi & (int)0x80000000);
+  const double sv = skip ? 0.0 : __hiloint2double(hi, __double2loint(v));
+  const uint32_t a = (uint32_t)abs_idx(gi), no = (uint32_t)sp.n_owned;
+  double *addr = SPLIT ? ((a < no) ? y + a : sp.yg + (a - no)) : y + a;
+  addr = skip ? sink : addr;
+#ifdef B2P_EMU
+  atomicAdd(addr, sv);
+#else
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(sv) : "memory");
+#endif
+}
+
+// GL1 (with GSM = false): L1 is the staging buffer -- the batch's q-data lines are pulled into L1 by prefetch.global.L1 one
+// batch ahead and the LDGs of the D loop hit there (half the L1 data-pipe wavefronts of TMA -> shared -> LDS, no buffer).
+template <int P_, int Q_, int KIND, bool SPLIT, int NW, int MINB, bool FWD, bool GSM = false, bool XLATE = false, bool GL1 = false>
 __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __grid_constant__ ND6Params<P_, Q_> prm)
 {
-  using L = ND6Layout<P_, Q_, KIND>;
+  using L = ND6Layout<P_, Q_, KIND, FWD, GSM>;
+  constexpr bool ALIAS = FWD;
+  static_assert(L::NEW * Q_ * Q_ <= 32, "one XDX item per lane");
   constexpr int p = L::p, q = L::q, n = L::n, Q = L::Q, D3 = L::D3, GE = L::GE, PS = L::PS, NEW = L::NEW, CE = L::CE;
   constexpr int RSA = L::RSA, RSB = L::RSB, RSY = L::RSY, NXA = L::NXA, NNA = L::NNA;
   constexpr bool MASS = L::MASS, CURL = L::CURL;
   constexpr int QQ = q * q;
   constexpr int IPX = p * n, IPZ = n * n, LSX = L::LSX, LSZ = L::LSZ, ZROUNDS = L::ZROUNDS, NXR = L::NXR;
+  constexpr int H = (q + 1) / 2;
+// table entry (row c, column i) from the stored half (indices are compile-time constants after unrolling)
+#define TBO(c, i) ((c) < H ? prm.Bo[(c) * p + (i)] : prm.Bo[(q - 1 - (c)) * p + (p - 1 - (i))])
+#define TBC(c, i) ((c) < H ? prm.Bc[(c) * n + (i)] : prm.Bc[(q - 1 - (c)) * n + (n - 1 - (i))])
+#define TGC(c, i) ((c) < H ? prm.Gc[(c) * n + (i)] : -prm.Gc[(q - 1 - (c)) * n + (n - 1 - (i))])
 
   B2P_DYN_SMEM_ALIGNED16(unsigned char, smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -147,6 +192,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
   double *sW = (double *)(wbase + L::OFF_W);
   unsigned char *sR = wbase + L::OFF_R;
   uint64_t *bar_i = (uint64_t *)(wbase + L::OFF_B);  // [3]
+  uint64_t *bar_g = bar_i + 3;
+  double *sG = (double *)(wbase + L::OFF_G);
 
   const int nb = (prm.ne + NEW - 1) / NEW;  // element batches
   const int GW = gridDim.x * NW;            // warps in the grid
@@ -158,6 +205,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
     mbar_init(bar_i + 0, 1);
     mbar_init(bar_i + 1, 1);
     mbar_init(bar_i + 2, 1);
+    if (GSM) mbar_init(bar_g, 1);
   }
   __syncwarp();
 
@@ -171,8 +219,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
   };
   auto prefetch_geom = [&](int bb)
   {
+    if (GSM || GL1) return;
     const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
     prefetch_l2_bulk(prm.qd + (size_t)e0 * GE, (uint32_t)(nel * GE * sizeof(double)));
+  };
+  auto prefetch_geom_l1 = [&](int bb)  // (whole warp) one 128-byte line per lane and round
+  {
+    const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
+    const char *base = (const char *)(prm.qd + (size_t)e0 * GE);
+    const int lines = nel * GE * 8 / 128;
+    for (int i = lane; i < lines; i += 32) prefetch_l1(base + (size_t)i * 128);
+  };
+  auto issue_geom = [&](int bb)
+  {
+    const int e0 = bb * NEW, nel = min(NEW, prm.ne - e0);
+    const uint32_t bytes = (uint32_t)(nel * GE * sizeof(double));
+    mbar_expect_tx(bar_g, bytes);
+    tma_bulk_g2s(sG, prm.qd + (size_t)e0 * GE, bytes, bar_g);
   };
 
   // x values of the batch whose Z phase comes next, in the registers of the lane that contracts them; `xsign` holds the
@@ -236,21 +299,24 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
     ghosts_ready = true;
   };
 
-  uint32_t par_i = 0;  // mbarrier phase parities: bit s for ring slot s
+  uint32_t par_i = 0, par_g = 0;  // mbarrier phase parities: bit s for ring slot s
   if (lane == 0)
   {
     issue_ring(b, 0);
     if (b + GW < nb) issue_ring(b + GW, 1);
     if (b + 2 * GW < nb) issue_ring(b + 2 * GW, 2);
+    if (GSM) issue_geom(b);
     prefetch_geom(b);
     if (b + GW < nb) prefetch_geom(b + GW);
   }
+  if constexpr (GL1) prefetch_geom_l1(b);
   mbar_wait(bar_i + 0, 0);
   par_i ^= 1u;
   wait_ghosts(b);
   gather_x(b, 0);
 
   const double alpha = prm.alpha;
+  double *my_sink = prm.sink + ((blockIdx.x * (NW * 32) + threadIdx.x) & (b2p_ctx::SINK_SLOTS - 1));
   int slot = 0;
   bool y_ready = false;
   for (; b < nb; b += GW)
@@ -279,7 +345,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
         }
 #pragma unroll
         for (int k = 0; k < p; k++) uz[k] = signed_x(r, 2 * n + k);
-        if (vx)
+        // (no divergent regions: idle lanes run on item 0 and their stores are predicated off)
         {
           double *xa = sW + L::ZA0 + (tx / p) * RSA + L::A_XA + ex * NXA + q * (tx % p), *xb = xa + (L::A_XB - L::A_XA);
           double *ya = sW + L::ZB0 + (tx / n) * RSB + L::B_YA + ex * NNA + q * (tx % n), *yb = ya + (L::B_YB - L::B_YA);
@@ -290,18 +356,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
             for (int k = 0; k < n; k++)
             {
-              a += prm.Bc[qz * n + k] * ux[k];
-              c += prm.Bc[qz * n + k] * uy[k];
-              if (CURL) b2 += prm.Gc[qz * n + k] * ux[k];
-              if (CURL) d += prm.Gc[qz * n + k] * uy[k];
+              a += TBC(qz, k) * ux[k];
+              c += TBC(qz, k) * uy[k];
+              if (CURL) b2 += TGC(qz, k) * ux[k];
+              if (CURL) d += TGC(qz, k) * uy[k];
             }
-            xa[qz] = a;
-            ya[qz] = c;
-            if (CURL) xb[qz] = b2;
-            if (CURL) yb[qz] = d;
+            if (vx) xa[qz] = a;
+            if (vx) ya[qz] = c;
+            if (CURL && vx) xb[qz] = b2;
+            if (CURL && vx) yb[qz] = d;
           }
         }
-        if (vz)
         {
           double *za = sW + L::ZA0 + (tz / n) * RSA + L::A_ZA + ez * NNA + q * (tz % n);
 #pragma unroll
@@ -309,8 +374,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
           {
             double a = 0.0;
 #pragma unroll
-            for (int k = 0; k < p; k++) a += prm.Bo[qz * p + k] * uz[k];
-            za[qz] = a;
+            for (int k = 0; k < p; k++) a += TBO(qz, k) * uz[k];
+            if (vz) za[qz] = a;
           }
         }
       }
@@ -318,14 +383,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
     __syncwarp();
     // the x registers are free: gather the next batch's values while this one computes; its q-data is already on the
     // way to L2, pull the one after it
-    if (bn < nb)
+    auto next_batch = [&]()
     {
-      mbar_wait(bar_i + nslot, (par_i >> nslot) & 1u);
-      par_i ^= (1u << nslot);
-      wait_ghosts(bn);
-      gather_x(bn, nslot);
-      if (lane == 0 && bn + GW < nb) prefetch_geom(bn + GW);
-    }
+      if (bn < nb)
+      {
+        mbar_wait(bar_i + nslot, (par_i >> nslot) & 1u);
+        par_i ^= (1u << nslot);
+        wait_ghosts(bn);
+        gather_x(bn, nslot);
+        if (lane == 0 && bn + GW < nb) prefetch_geom(bn + GW);
+      }
+    };
+    if constexpr (!XLATE) next_batch();
 
     // ------------------------------------------------------------------ phase Y (y-contraction)
     if constexpr (!FWD)
@@ -368,9 +437,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < n; j++)
             {
-              if (MASS) s1 += prm.Bc[qy * n + j] * xa[j];
-              if (CURL) s2 += prm.Bc[qy * n + j] * xb[j];
-              if (CURL) s3 += prm.Gc[qy * n + j] * xa[j];
+              if (MASS) s1 += TBC(qy, j) * xa[j];
+              if (CURL) s2 += TBC(qy, j) * xb[j];
+              if (CURL) s3 += TGC(qy, j) * xa[j];
             }
             if (MASS) v1[RSY * qy] = s1;
             if (CURL) v2[RSY * qy] = s2;
@@ -388,14 +457,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < p; j++)
             {
-              s1 += prm.Bo[qy * p + j] * ya[j];
-              if (CURL) s2 += prm.Bo[qy * p + j] * yb[j];
+              s1 += TBO(qy, j) * ya[j];
+              if (CURL) s2 += TBO(qy, j) * yb[j];
             }
 #pragma unroll
             for (int j = 0; j < n; j++)
             {
-              t1 += prm.Bc[qy * n + j] * za[j];
-              if (CURL) t3 += prm.Gc[qy * n + j] * za[j];
+              t1 += TBC(qy, j) * za[j];
+              if (CURL) t3 += TGC(qy, j) * za[j];
             }
             v1[RSY * qy] = s1;
             if (CURL) v2[RSY * qy] = s2;
@@ -409,15 +478,25 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 
     // ------------------------------------------------------------------ phase XDX
     // item s = qy + q*qz of element slot e: all qx of this line live in registers.
-    for (int w = lane; w < NEW * QQ; w += 32)
+    if constexpr (GSM)
     {
+      mbar_wait(bar_g, par_g);  // q-data of this batch has landed
+      par_g ^= 1;
+    }
+    {
+      // one item per lane (NEW * QQ <= 32); lanes beyond the last item run on item 0 and store nothing
+      const bool act = lane < NEW * QQ;
+      const int w = act ? lane : 0;
       const int e = w / QQ, s = w % QQ;
-      const bool ok = e < nel;
+      const bool ok = act && e < nel;
       // q-data of this lane's line, point qx at g[comp * Q + QQ * qx]; rows of a tail batch read element 0 (discarded)
-      const double *g = prm.qd + (size_t)(e0 + (ok ? e : 0)) * GE + s;
+      const double *g = GSM ? sG + (ok ? e : 0) * GE + s : prm.qd + (size_t)(e0 + (ok ? e : 0)) * GE + s;
       double G[2][10];
+      if constexpr (!GSM)
+      {
 #pragma unroll
-      for (int c = 0; c < 10; c++) G[0][c] = ldg_stream_f64(g + c * Q);
+        for (int c = 0; c < 10; c++) G[0][c] = GL1 ? __ldg(g + c * Q) : ldg_stream_f64(g + c * Q);
+      }
       double *WX = sW + L::Y0 + (s % q) * RSY + e * NXA + s / q;
       double *WN = sW + L::Y0 + (s % q) * RSY + e * NNA + s / q;
       double uu[q][3], cc[q][3];
@@ -430,14 +509,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
         // y-contraction of this lane's own line straight from the Z region (broadcast reads), every line value folded
         // into the point accumulators at once
         const int qy = s % q, qz = s / q;
+        // this lane's rows of the y tables (lane-dependent: indexed loads from the parameter block, mirrored rows reversed)
+        const bool mir = qy >= H;
+        const int cy = mir ? q - 1 - qy : qy;
+        const double gsgn = mir ? -1.0 : 1.0;
         double bo[p], bc[n], gc[n];
 #pragma unroll
-        for (int j = 0; j < p; j++) bo[j] = prm.Bo[qy * p + j];
+        for (int j = 0; j < p; j++) bo[j] = prm.Bo[cy * p + (mir ? p - 1 - j : j)];
 #pragma unroll
         for (int j = 0; j < n; j++)
         {
-          bc[j] = prm.Bc[qy * n + j];
-          gc[j] = prm.Gc[qy * n + j];
+          bc[j] = prm.Bc[cy * n + (mir ? n - 1 - j : j)];
+          gc[j] = gsgn * prm.Gc[cy * n + (mir ? n - 1 - j : j)];
         }
         const double *ZX = sW + L::ZA0 + e * NXA + qz, *ZY = sW + L::ZB0 + e * NNA + qz, *ZZ = sW + L::ZA0 + L::A_ZA + e * NNA + qz;
 #pragma unroll
@@ -455,9 +538,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
           for (int qx = 0; qx < q; qx++)
           {
-            if (MASS) uu[qx][0] += prm.Bo[qx * p + i] * s1;
-            if (CURL) cc[qx][1] += prm.Bo[qx * p + i] * s2;
-            if (CURL) cc[qx][2] -= prm.Bo[qx * p + i] * s3;
+            if (MASS) uu[qx][0] += TBO(qx, i) * s1;
+            if (CURL) cc[qx][1] += TBO(qx, i) * s2;
+            if (CURL) cc[qx][2] -= TBO(qx, i) * s3;
           }
         }
 #pragma unroll
@@ -480,12 +563,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
           for (int qx = 0; qx < q; qx++)
           {
-            if (MASS) uu[qx][1] += prm.Bc[qx * n + i] * s1;
-            if (CURL) cc[qx][0] -= prm.Bc[qx * n + i] * s2;
-            if (CURL) cc[qx][2] += prm.Gc[qx * n + i] * s1;
-            if (MASS) uu[qx][2] += prm.Bc[qx * n + i] * t1;
-            if (CURL) cc[qx][0] += prm.Bc[qx * n + i] * t3;
-            if (CURL) cc[qx][1] -= prm.Gc[qx * n + i] * t1;
+            if (MASS) uu[qx][1] += TBC(qx, i) * s1;
+            if (CURL) cc[qx][0] -= TBC(qx, i) * s2;
+            if (CURL) cc[qx][2] += TGC(qx, i) * s1;
+            if (MASS) uu[qx][2] += TBC(qx, i) * t1;
+            if (CURL) cc[qx][0] += TBC(qx, i) * t3;
+            if (CURL) cc[qx][1] -= TGC(qx, i) * t1;
           }
         }
       }
@@ -501,9 +584,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
           for (int qx = 0; qx < q; qx++)
           {
-            if (MASS) uu[qx][0] += prm.Bo[qx * p + i] * x1;
-            if (CURL) cc[qx][1] += prm.Bo[qx * p + i] * x2;
-            if (CURL) cc[qx][2] -= prm.Bo[qx * p + i] * x3;
+            if (MASS) uu[qx][0] += TBO(qx, i) * x1;
+            if (CURL) cc[qx][1] += TBO(qx, i) * x2;
+            if (CURL) cc[qx][2] -= TBO(qx, i) * x3;
           }
         }
 #pragma unroll
@@ -517,24 +600,30 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
           for (int qx = 0; qx < q; qx++)
           {
-            if (MASS) uu[qx][1] += prm.Bc[qx * n + i] * y1;
-            if (CURL) cc[qx][0] -= prm.Bc[qx * n + i] * y2;
-            if (CURL) cc[qx][2] += prm.Gc[qx * n + i] * y1;
-            if (MASS) uu[qx][2] += prm.Bc[qx * n + i] * z1;
-            if (CURL) cc[qx][0] += prm.Bc[qx * n + i] * z3;
-            if (CURL) cc[qx][1] -= prm.Gc[qx * n + i] * z1;
+            if (MASS) uu[qx][1] += TBC(qx, i) * y1;
+            if (CURL) cc[qx][0] -= TBC(qx, i) * y2;
+            if (CURL) cc[qx][2] += TGC(qx, i) * y1;
+            if (MASS) uu[qx][2] += TBC(qx, i) * z1;
+            if (CURL) cc[qx][0] += TBC(qx, i) * z3;
+            if (CURL) cc[qx][1] -= TGC(qx, i) * z1;
           }
         }
       }
+      if constexpr (ALIAS) __syncwarp();  // every lane has read its Z-region values: the Y region may overwrite them
       const double *C = cC + e * CE;
 #pragma unroll
       for (int qx = 0; qx < q; qx++)
       {
-        // q-data of the next point of the line is requested before this point's arithmetic
-        if (qx + 1 < q)
+        if constexpr (GSM)
         {
 #pragma unroll
-          for (int c = 0; c < 10; c++) G[(qx + 1) & 1][c] = ldg_stream_f64(g + c * Q + QQ * (qx + 1));
+          for (int c = 0; c < 10; c++) G[qx & 1][c] = g[c * Q + QQ * qx];
+        }
+        else if (qx + 1 < q)
+        {
+          // q-data of the next point of the line is requested before this point's arithmetic
+#pragma unroll
+          for (int c = 0; c < 10; c++) G[(qx + 1) & 1][c] = GL1 ? __ldg(g + c * Q + QQ * (qx + 1)) : ldg_stream_f64(g + c * Q + QQ * (qx + 1));
         }
         const double *gq = G[qx & 1];
         double v[3] = {0, 0, 0}, cw[3] = {0, 0, 0};
@@ -575,13 +664,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
         for (int qx = 0; qx < q; qx++)
         {
-          if (MASS) a1 += prm.Bo[qx * p + i] * uu[qx][0];
-          if (CURL) a2 += prm.Bo[qx * p + i] * cc[qx][1];
-          if (CURL) a3 -= prm.Bo[qx * p + i] * cc[qx][2];
+          if (MASS) a1 += TBO(qx, i) * uu[qx][0];
+          if (CURL) a2 += TBO(qx, i) * cc[qx][1];
+          if (CURL) a3 -= TBO(qx, i) * cc[qx][2];
         }
-        if (MASS) WX[L::Y_X1 + q * i] = a1;
-        if (CURL) WX[L::Y_X2 + q * i] = a2;
-        if (CURL) WX[L::Y_X3 + q * i] = a3;
+        if (MASS && act) WX[L::Y_X1 + q * i] = a1;
+        if (CURL && act) WX[L::Y_X2 + q * i] = a2;
+        if (CURL && act) WX[L::Y_X3 + q * i] = a3;
       }
 #pragma unroll
       for (int i = 0; i < n; i++)
@@ -590,20 +679,33 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
         for (int qx = 0; qx < q; qx++)
         {
-          if (MASS) b1 += prm.Bc[qx * n + i] * uu[qx][1];
-          if (CURL) b1 += prm.Gc[qx * n + i] * cc[qx][2];
-          if (CURL) b2 -= prm.Bc[qx * n + i] * cc[qx][0];
-          if (MASS) c1 += prm.Bc[qx * n + i] * uu[qx][2];
-          if (CURL) c1 -= prm.Gc[qx * n + i] * cc[qx][1];
-          if (CURL) c3 += prm.Bc[qx * n + i] * cc[qx][0];
+          if (MASS) b1 += TBC(qx, i) * uu[qx][1];
+          if (CURL) b1 += TGC(qx, i) * cc[qx][2];
+          if (CURL) b2 -= TBC(qx, i) * cc[qx][0];
+          if (MASS) c1 += TBC(qx, i) * uu[qx][2];
+          if (CURL) c1 -= TGC(qx, i) * cc[qx][1];
+          if (CURL) c3 += TBC(qx, i) * cc[qx][0];
         }
-        WN[L::Y_Y1 + q * i] = b1;
-        if (CURL) WN[L::Y_Y2 + q * i] = b2;
-        WN[L::Y_Z1 + q * i] = c1;
-        if (CURL) WN[L::Y_Z3 + q * i] = c3;
+        if (act) WN[L::Y_Y1 + q * i] = b1;
+        if (CURL && act) WN[L::Y_Y2 + q * i] = b2;
+        if (act) WN[L::Y_Z1 + q * i] = c1;
+        if (CURL && act) WN[L::Y_Z3 + q * i] = c3;
       }
     }
     __syncwarp();
+    if constexpr (GSM)
+    {
+      if (bn < nb && lane == 0)
+      {
+        fence_proxy_async();
+        issue_geom(bn);  // refill the single q-data buffer for the next batch
+      }
+    }
+    if constexpr (GL1)
+    {
+      if (bn < nb) prefetch_geom_l1(bn);
+    }
+    if constexpr (XLATE) next_batch();
 
     // ------------------------------------------------------------------ phase Yt (transposed y-contraction)
     {
@@ -632,7 +734,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
             if (CURL) z3[qy] = t3[RSY * qy];
           }
         }
-        if (vx)
+        if constexpr (ALIAS)
+        {
+          static_assert(!ALIAS || ROUNDS == 1, "aliased work arrays: one Yt round (all Y-region reads precede the Z-region writes)");
+          __syncwarp();
+        }
         {
           double *za = sW + L::ZA0 + L::A_XA + wx, *zb = sW + L::ZA0 + L::A_XB + wx;
 #pragma unroll
@@ -642,15 +748,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
             for (int qy = 0; qy < q; qy++)
             {
-              if (MASS) a += prm.Bc[qy * n + j] * x1[qy];
-              if (CURL) a += prm.Gc[qy * n + j] * x3[qy];
-              if (CURL) b2 += prm.Bc[qy * n + j] * x2[qy];
+              if (MASS) a += TBC(qy, j) * x1[qy];
+              if (CURL) a += TGC(qy, j) * x3[qy];
+              if (CURL) b2 += TBC(qy, j) * x2[qy];
             }
-            za[RSA * j] = a;
-            if (CURL) zb[RSA * j] = b2;
+            if (vx) za[RSA * j] = a;
+            if (CURL && vx) zb[RSA * j] = b2;
           }
         }
-        if (vn)
         {
           double *ya = sW + L::ZB0 + L::B_YA + wn, *yb = sW + L::ZB0 + L::B_YB + wn;
 #pragma unroll
@@ -660,11 +765,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
             for (int qy = 0; qy < q; qy++)
             {
-              a += prm.Bo[qy * p + j] * y1[qy];
-              if (CURL) b2 += prm.Bo[qy * p + j] * y2[qy];
+              a += TBO(qy, j) * y1[qy];
+              if (CURL) b2 += TBO(qy, j) * y2[qy];
             }
-            ya[RSB * j] = a;
-            if (CURL) yb[RSB * j] = b2;
+            if (vn) ya[RSB * j] = a;
+            if (CURL && vn) yb[RSB * j] = b2;
           }
           double *za = sW + L::ZA0 + L::A_ZA + wn;
 #pragma unroll
@@ -674,10 +779,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
             for (int qy = 0; qy < q; qy++)
             {
-              a += prm.Bc[qy * n + j] * z1[qy];
-              if (CURL) a += prm.Gc[qy * n + j] * z3[qy];
+              a += TBC(qy, j) * z1[qy];
+              if (CURL) a += TGC(qy, j) * z3[qy];
             }
-            za[RSA * j] = a;
+            if (vn) za[RSA * j] = a;
           }
         }
       }
@@ -716,16 +821,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
             if (CURL) xb[qz] = pxb[qz];
             if (CURL) yb[qz] = pyb[qz];
           }
+          // idle lanes / tail slots carry the "masked" index: the predicated RED skips them (no divergent region)
 #pragma unroll
           for (int k = 0; k < n; k++)
           {
-            gx[k] = cI[ex * PS + tx + p * n * k];
-            gy[k] = cI[ex * PS + D3 + tx + n * p * k];
+            gx[k] = vx ? cI[ex * PS + tx + p * n * k] : (int32_t)B2P_SKIP_IDX;
+            gy[k] = vx ? cI[ex * PS + D3 + tx + n * p * k] : (int32_t)B2P_SKIP_IDX;
           }
 #pragma unroll
-          for (int k = 0; k < p; k++) gz[k] = cI[ez * PS + 2 * D3 + tz + n * n * k];
+          for (int k = 0; k < p; k++) gz[k] = vz ? cI[ez * PS + 2 * D3 + tz + n * n * k] : (int32_t)B2P_SKIP_IDX;
         }
-        if (vx)
         {
 #pragma unroll
           for (int k = 0; k < n; k++)
@@ -734,24 +839,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
 #pragma unroll
             for (int qz = 0; qz < q; qz++)
             {
-              o += prm.Bc[qz * n + k] * xa[qz];
-              o2 += prm.Bc[qz * n + k] * ya[qz];
-              if (CURL) o += prm.Gc[qz * n + k] * xb[qz];
-              if (CURL) o2 += prm.Gc[qz * n + k] * yb[qz];
+              o += TBC(qz, k) * xa[qz];
+              o2 += TBC(qz, k) * ya[qz];
+              if (CURL) o += TGC(qz, k) * xb[qz];
+              if (CURL) o2 += TGC(qz, k) * yb[qz];
             }
-            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gx[k], o); else scatter_fast(prm.y, gx[k], o);
-            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gy[k], o2); else scatter_fast(prm.y, gy[k], o2);
+            scatter_nb<SPLIT>(prm.y, prm.sp, my_sink, gx[k], o);
+            scatter_nb<SPLIT>(prm.y, prm.sp, my_sink, gy[k], o2);
           }
         }
-        if (vz)
         {
 #pragma unroll
           for (int k = 0; k < p; k++)
           {
             double o = 0.0;
 #pragma unroll
-            for (int qz = 0; qz < q; qz++) o += prm.Bo[qz * p + k] * za[qz];
-            if (SPLIT) scatter_fast_split(prm.y, prm.sp, gz[k], o); else scatter_fast(prm.y, gz[k], o);
+            for (int qz = 0; qz < q; qz++) o += TBO(qz, k) * za[qz];
+            scatter_nb<SPLIT>(prm.y, prm.sp, my_sink, gz[k], o);
           }
         }
       }
@@ -764,18 +868,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply6_kernel(const __gr
     }
     slot = nslot;
   }
+#undef TBO
+#undef TBC
+#undef TGC
 }
 
-template <int P_, int Q_, int KIND, int NW, int MINB, bool FWD, bool WITH_SPLIT>
+template <int P_, int Q_, int KIND, int NW, int MINB, bool FWD, bool GSM, bool XLATE, bool WITH_SPLIT, bool GL1 = false>
 int launch6_cfg(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
-  using L = ND6Layout<P_, Q_, KIND>;
+  using L = ND6Layout<P_, Q_, KIND, FWD, GSM>;
   const size_t shmem = (size_t)NW * L::WS;
   const bool split = rg.xg || rg.yg || (rg.n_owned >= 0 && rg.n_owned < op->lsize);
-  auto kern = nd_hex_apply6_kernel<P_, Q_, KIND, false, NW, MINB, FWD>;
+  auto kern = nd_hex_apply6_kernel<P_, Q_, KIND, false, NW, MINB, FWD, GSM, XLATE, GL1>;
   if constexpr (WITH_SPLIT)
   {
-    if (split) kern = nd_hex_apply6_kernel<P_, Q_, KIND, true, NW, MINB, FWD>;
+    if (split) kern = nd_hex_apply6_kernel<P_, Q_, KIND, true, NW, MINB, FWD, GSM, XLATE, GL1>;
   }
   else if (split)
   {
@@ -786,6 +893,10 @@ int launch6_cfg(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   if (!configured[split ? 1 : 0])
   {
     B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+#ifndef B2P_EMU
+    if (GL1)  // leave the rest of the 256 KB array to L1: it is the staging buffer of the q-data
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((MINB * (shmem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+#endif
     configured[split ? 1 : 0] = true;
   }
   ND6Params<P_, Q_> prm;
@@ -796,6 +907,7 @@ int launch6_cfg(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   prm.ecoef = op->ecoef + 18 * (size_t)e_off;
   prm.x = x;
   prm.y = y;
+  prm.sink = op->ctx->d_sink;
   prm.alpha = alpha;
   prm.ne = e_cnt;
   prm.sp.n_owned = rg.n_owned < 0 ? op->lsize : rg.n_owned;
@@ -807,9 +919,10 @@ int launch6_cfg(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   prm.wait_from_elem = rg.wait_from_elem;
   prm.iso = op->iso ? 1 : 0;
   const int n = P_ + 1;
-  for (int i = 0; i < Q_ * P_; i++) prm.Bo[i] = op->h_tab[i];
-  for (int i = 0; i < Q_ * n; i++) prm.Bc[i] = op->h_tab[Q_ * P_ + i];
-  for (int i = 0; i < Q_ * n; i++) prm.Gc[i] = op->h_tab[Q_ * P_ + Q_ * n + i];
+  constexpr int H = ND6Params<P_, Q_>::H;
+  for (int i = 0; i < H * P_; i++) prm.Bo[i] = op->h_tab[i];
+  for (int i = 0; i < H * n; i++) prm.Bc[i] = op->h_tab[Q_ * P_ + i];
+  for (int i = 0; i < H * n; i++) prm.Gc[i] = op->h_tab[Q_ * P_ + Q_ * n + i];
   const int nb = (e_cnt + L::NEW - 1) / L::NEW;
   int grid = op->ctx->sm_count * MINB;
   if (grid > (nb + NW - 1) / NW) grid = (nb + NW - 1) / NW;
@@ -821,21 +934,22 @@ int launch6_cfg(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   return B2P_SUCCESS;
 }
 
-// B2P_ND6_CFG = "<warps per CTA><CTAs per SM><f|y>" picks another launch shape / XDX variant of the p = 3 curl-curl+mass
-// kernel for A/B measurements ("43f": 4 warps x 3 CTAs per SM, XDX consumes the Z region = the shipped one).
+// B2P_ND6_CFG = "<warps per CTA><CTAs per SM><f|y><g|l><e|x>" picks another launch shape / variant of the p = 3
+// curl-curl+mass kernel for A/B measurements: f = XDX consumes the Z region, y = separate Y phase; g = q-data staged in
+// shared memory by TMA, l = LDG into registers; e = x gathered right after the Z phase, x = after XDX.
 inline int nd6_cfg_code()
 {
   static const int code = []
   {
     const char *e = std::getenv("B2P_ND6_CFG");
-    if (!e || !e[0] || !e[1]) return 0;
-    return (e[0] - '0') * 100 + (e[1] - '0') * 10 + ((e[2] == 'y') ? 1 : 0);
+    if (!e || std::strlen(e) < 5) return 0;
+    return (e[0] - '0') * 10000 + (e[1] - '0') * 1000 + (e[2] == 'y' ? 100 : 0) + (e[3] == 'g' ? 10 : e[3] == 'c' ? 20 : 0) + (e[4] == 'x' ? 1 : 0);
   }();
   return code;
 }
 
-constexpr int ND6_NW = 4, ND6_MINB = 3;
-constexpr bool ND6_FWD = true;
+constexpr int ND6_NW = 4, ND6_MINB = 2;
+constexpr bool ND6_FWD = true, ND6_GSM = true, ND6_XLATE = true;
 
 template <int P_, int Q_, int KIND>
 int launch6(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
@@ -845,27 +959,59 @@ int launch6(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
   {
     switch (nd6_cfg_code())
     {
-#define B2P_CFG(NWV, MB)                                                                                                \
-  case NWV * 100 + MB * 10: return launch6_cfg<P_, Q_, KIND, NWV, MB, true, false>(op, lidx, alpha, x, y, rg, s);        \
-  case NWV * 100 + MB * 10 + 1: return launch6_cfg<P_, Q_, KIND, NWV, MB, false, false>(op, lidx, alpha, x, y, rg, s);
-      B2P_CFG(4, 2)
-      B2P_CFG(4, 3)
-      B2P_CFG(5, 3)
-      B2P_CFG(6, 2)
-      B2P_CFG(7, 2)
+#define B2P_CFG(NWV, MB, FW, GS, XL) \
+  case NWV * 10000 + MB * 1000 + (FW ? 0 : 100) + (GS ? 10 : 0) + (XL ? 1 : 0): \
+    return launch6_cfg<P_, Q_, KIND, NWV, MB, FW, GS, XL, false>(op, lidx, alpha, x, y, rg, s);
+      B2P_CFG(4, 3, true, false, false)
+      B2P_CFG(4, 3, true, false, true)
+      B2P_CFG(4, 2, true, true, false)
+      B2P_CFG(4, 2, true, true, true)
+      B2P_CFG(5, 2, true, true, false)
+      B2P_CFG(5, 2, true, true, true)
+      B2P_CFG(3, 3, true, true, false)
+      B2P_CFG(3, 3, true, true, true)
+      B2P_CFG(4, 2, false, true, true)
 #undef B2P_CFG
+      case 42021: return launch6_cfg<P_, Q_, KIND, 4, 2, true, false, true, false, true>(op, lidx, alpha, x, y, rg, s);   // "42fcx"
+      case 42020: return launch6_cfg<P_, Q_, KIND, 4, 2, true, false, false, false, true>(op, lidx, alpha, x, y, rg, s);  // "42fce"
+      case 43021: return launch6_cfg<P_, Q_, KIND, 4, 3, true, false, true, false, true>(op, lidx, alpha, x, y, rg, s);   // "43fcx"
     }
   }
 #endif
-  return launch6_cfg<P_, Q_, KIND, ND6_NW, ND6_MINB, ND6_FWD, true>(op, lidx, alpha, x, y, rg, s);
+  return launch6_cfg<P_, Q_, KIND, ND6_NW, ND6_MINB, ND6_FWD, ND6_GSM, ND6_XLATE, true>(op, lidx, alpha, x, y, rg, s);
 }
 
 }  // namespace
 
-bool nd_hex_apply6_eligible(const b2p_op *op)
+namespace
+{
+bool nd6_tables_symmetric(const double *tab, int p, int q)
+{
+  const int n = p + 1;
+  const double *Bo = tab, *Bc = tab + q * p, *Gc = Bc + q * n;
+  double scale = 0.0;
+  for (int i = 0; i < q * p + 2 * q * n; i++) scale = std::fmax(scale, std::fabs(tab[i]));
+  const double tol = 4e-16 * scale;  // the kernel substitutes mirrored entries: they must agree to round-off
+  for (int c = 0; c < q; c++)
+  {
+    for (int i = 0; i < p; i++)
+      if (std::fabs(Bo[c * p + i] - Bo[(q - 1 - c) * p + (p - 1 - i)]) > tol) return false;
+    for (int i = 0; i < n; i++)
+    {
+      if (std::fabs(Bc[c * n + i] - Bc[(q - 1 - c) * n + (n - 1 - i)]) > tol) return false;
+      if (std::fabs(Gc[c * n + i] + Gc[(q - 1 - c) * n + (n - 1 - i)]) > tol) return false;
+    }
+  }
+  return true;
+}
+}  // namespace
+
+bool nd_hex_apply6_eligible(b2p_op *op)
 {
   if (!op || op->dense || op->assembled || op->kind == B2P_H1_DIFFUSION || !op->ecoef) return false;
-  return op->q1d == op->p + 1 && op->p >= 2 && op->p <= 4;
+  if (!(op->q1d == op->p + 1 && op->p >= 2 && op->p <= 3)) return false;
+  if (op->tab_sym6 < 0) op->tab_sym6 = nd6_tables_symmetric(op->h_tab.data(), op->p, op->q1d) ? 1 : 0;
+  return op->tab_sym6 == 1;
 }
 
 int launch_nd_hex_apply6(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
@@ -883,7 +1029,6 @@ int launch_nd_hex_apply6(b2p_op *op, const int32_t *lidx, double alpha, const do
   B2P_CASE(3, 4)
 #ifndef B2P_ND6_P3_ONLY
   B2P_CASE(2, 3)
-  B2P_CASE(4, 5)
 #endif
 #undef B2P_CASE
   set_error(op->ctx, "nd_hex_apply6: no kernel for p=%d q1d=%d kind=%d", op->p, op->q1d, op->kind);

@@ -88,6 +88,9 @@ struct b2p_ctx
   double *d_red = nullptr;
   double *h_red = nullptr;
   size_t red_cap = 0;
+  // sink of the branch-free scatter (nd_hex_apply6_kernel): masked restriction entries add 0.0 to a per-thread slot here
+  double *d_sink = nullptr;
+  static constexpr int SINK_SLOTS = 1 << 16;
 };
 
 // Geometry q-data of one element block, device resident.
@@ -135,6 +138,7 @@ struct b2p_op
   int n_mat = 0;
   bool iso = false;            // every material matrix is c * I
   int tab_sym = -1;            // 1-D tables mirror-symmetric (nd_hex_apply5_kernel): -1 unknown, 0 no, 1 yes
+  int tab_sym6 = -1;           // same to round-off (nd_hex_apply6_kernel stores half the rows)
   double *ecoef = nullptr;     // [ne][18] per-element coefficient matrices (TMA-friendly copy of mat[emat])
   // assembled q-data (optional): aq[ne][ncomp][Q], symmetric 6 per part
   double *aq = nullptr;
@@ -193,7 +197,7 @@ int launch_nd_hex_apply4(b2p_op *op, const int32_t *lidx, double alpha, const do
 int launch_nd_hex_apply5(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
 bool nd_hex_apply5_eligible(b2p_op *op);
 int launch_nd_hex_apply6(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
-bool nd_hex_apply6_eligible(const b2p_op *op);
+bool nd_hex_apply6_eligible(b2p_op *op);
 // fused complex apply (b2p_hex_nd4.cu): both parts of a split complex vector in one pass over the geometry
 bool nd_hex_apply4z_eligible(const b2p_op *op);
 int launch_nd_hex_apply4z(b2p_op *op, int kind, const int32_t *lidx, const double *zcoef, int has_imag, double alpha, const double *xr,
