@@ -248,7 +248,7 @@ def run_experiments(args):
     variants = {
         "matrix_coefficient_warped_mesh": (["--coefficient", "matrix4", "--warp", "0.05"], {}),
         "round1_kernel_nd_hex_apply4": ([], {"B2P_ND_KERNEL": "4"}),
-        "zero_fill_overlap_pdl": ([], {"B2P_PDL": "1"}),
+        "without_pdl_zero_fill_overlap": ([], {"B2P_PDL": "0"}),
     }
     # (2) prepared tool measurements (tools/): one JSON line each
     tools = {

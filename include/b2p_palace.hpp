@@ -11,6 +11,8 @@
 //   b2p::palace::ComplexParOperatorAdapter  replaces palace::ComplexParOperator over ComplexWrapperOperator
 //                                    (palace/linalg/rap.hpp:123-220, operator.cpp:98-134): sum_i (a_i^r + i a_i^i) A_i on split
 //                                    real / imaginary vectors, one fused element-kernel launch per matvec when eligible.
+//   b2p::palace::KspSolverAdapter    replaces palace::BaseKspSolver<Operator> (palace/linalg/ksp.hpp:24-75): one configuration
+//                                    record -> Krylov solver + p-multigrid preconditioner, NumTotalMult / NumTotalMultIterations.
 //   b2p::palace::FullAssembly        replaces BilinearForm::FullAssemble / CeedOperatorFullAssemble for the coarse level
 //                                    (palace/fem/bilinearform.hpp:72-84, libceed/operator.cpp:262-523): device CSR arrays
 //                                    to wrap in a hypre::HypreCSRMatrix.
@@ -20,6 +22,7 @@
 #if defined(MFEM_VERSION) || __has_include(<mfem.hpp>)
 #include <mfem.hpp>
 
+#include <cstdint>
 #include <memory>
 #include <vector>
 
@@ -34,6 +37,126 @@ inline void Check(int rc, b2p_ctx *ctx)
   {
     MFEM_ABORT("b2p error " << rc << ": " << b2p_last_error(ctx));  // PalaceCeedCall semantics, ceed.hpp:13-33
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Integrator glue: MFEM objects -> the descriptors of b2p.h. This is what BilinearForm::PartialAssemble
+// (palace/fem/bilinearform.cpp:27-107) does through InitBasis / InitRestriction / Mesh::GetCeedGeomFactorData for libCEED:
+//   1-D tables       fem/libceed/basis.cpp:15-38    (fe.GetDofToQuad(ir, TENSOR) of the closed and open bases)
+//   dof map          fem/libceed/restriction.cpp:134-136,413-426 (TensorBasisElement::GetDofMap())
+//   element dofs     fem/libceed/restriction.cpp:207-297 (GetElementDofs: index + sign from the -1-d encoding)
+//   node coordinates fem/mesh.cpp:146-209           (E-vector of mesh.GetNodes(), attributes)
+// tests/mock_mfem/glue_exec.cpp runs these functions on a one-element mesh through the C ABI against the oracle.
+// ------------------------------------------------------------------------------------------------------------------
+// Host arrays a b2p_op_desc points into (they must outlive b2p_op_create only).
+struct HexNDSpaceInputs
+{
+  int p = 0, q1d = 0, ne = 0;
+  long long lsize = 0;
+  std::vector<int32_t> idx, dof_map;
+  std::vector<int8_t> orient;
+  std::vector<double> Bo, Bc, Gc;
+};
+
+// DofToQuad tables are column-major [nqpt x ndof] (B[q + nqpt * d]); b2p wants [q1d][ndof] row-major.
+inline std::vector<double> RowMajorTable(const std::vector<double> &colmajor, int nqpt, int ndof)
+{
+  std::vector<double> t((size_t)nqpt * ndof);
+  for (int q = 0; q < nqpt; q++)
+    for (int d = 0; d < ndof; d++) t[(size_t)q * ndof + d] = colmajor[q + (size_t)nqpt * d];
+  return t;
+}
+
+inline HexNDSpaceInputs GatherHexNDSpace(const mfem::FiniteElementSpace &fes, const mfem::IntegrationRule &ir1d)
+{
+  HexNDSpaceInputs in;
+  const auto *fe = dynamic_cast<const mfem::VectorTensorFiniteElement *>(fes.GetFE(0));
+  MFEM_VERIFY(fe, "GatherHexNDSpace: a tensor-product vector element (ND hexahedron) is required!");
+  in.p = fe->GetOrder();
+  in.q1d = ir1d.GetNPoints();
+  in.ne = fes.GetNE();
+  in.lsize = fes.GetVSize();
+  const mfem::DofToQuad &mc = fe->GetDofToQuad(ir1d, mfem::DofToQuad::TENSOR);      // closed (Gauss-Lobatto) basis
+  const mfem::DofToQuad &mo = fe->GetDofToQuadOpen(ir1d, mfem::DofToQuad::TENSOR);  // open (Gauss-Legendre) basis
+  MFEM_VERIFY(mc.ndof == in.p + 1 && mo.ndof == in.p && mc.nqpt == in.q1d && mo.nqpt == in.q1d, "unexpected 1-D table sizes!");
+  in.Bc = RowMajorTable(mc.B, in.q1d, in.p + 1);
+  in.Gc = RowMajorTable(mc.G, in.q1d, in.p + 1);
+  in.Bo = RowMajorTable(mo.B, in.q1d, in.p);
+  const mfem::Array<int> &dm = fe->GetDofMap();
+  in.dof_map.assign(dm.HostRead(), dm.HostRead() + dm.Size());
+  const int P = dm.Size();
+  in.idx.resize((size_t)in.ne * P);
+  in.orient.resize((size_t)in.ne * P);
+  mfem::Array<int> dofs;
+  for (int e = 0; e < in.ne; e++)
+  {
+    fes.GetElementDofs(e, dofs);  // native element order; d < 0 encodes -(d + 1) with a sign flip (restriction.cpp:281-297)
+    MFEM_VERIFY(dofs.Size() == P, "element dof count differs from the dof map!");
+    for (int i = 0; i < P; i++)
+    {
+      const int d = dofs[i];
+      in.idx[(size_t)e * P + i] = d >= 0 ? d : -1 - d;
+      in.orient[(size_t)e * P + i] = d >= 0 ? 1 : -1;
+    }
+  }
+  return in;
+}
+
+// Geometry handle of a hexahedral mesh block (Mesh::GetCeedGeomFactorData -> b2p_geom_create_hex): the element node
+// coordinates in LEXICOGRAPHIC tensor order, component-major, through the nodal element's dof map; 1-D nodal tables and
+// weights of the rule.
+inline b2p_geom *CreateHexGeometry(b2p_ctx *ctx, const mfem::Mesh &mesh, const mfem::IntegrationRule &ir1d)
+{
+  const mfem::GridFunction *nodes = mesh.GetNodes();
+  MFEM_VERIFY(nodes, "CreateHexGeometry: the mesh needs a nodal grid function (Mesh::EnsureNodes)!");
+  const mfem::FiniteElementSpace *nfes = nodes->FESpace();
+  const auto *nfe = dynamic_cast<const mfem::NodalTensorFiniteElement *>(nfes->GetFE(0));
+  MFEM_VERIFY(nfe && nfes->GetVDim() == 3, "CreateHexGeometry: H1 tensor-product nodes in 3-D are required!");
+  const int k = nfe->GetOrder(), nn = (k + 1) * (k + 1) * (k + 1), ne = mesh.GetNE(), q1d = ir1d.GetNPoints();
+  const mfem::DofToQuad &mn = nfe->GetDofToQuad(ir1d, mfem::DofToQuad::TENSOR);
+  const std::vector<double> nB = RowMajorTable(mn.B, q1d, k + 1), nG = RowMajorTable(mn.G, q1d, k + 1);
+  const mfem::Array<int> &dm = nfe->GetDofMap();  // lexicographic -> native node
+  std::vector<double> xe((size_t)ne * 3 * nn);
+  std::vector<int32_t> attr(ne);
+  mfem::Array<int> vdofs;
+  mfem::Vector xv;
+  for (int e = 0; e < ne; e++)
+  {
+    nfes->GetElementVDofs(e, vdofs);  // byNODES: [x of all nodes | y ... | z ...] in native node order
+    nodes->GetSubVector(vdofs, xv);
+    for (int c = 0; c < 3; c++)
+      for (int l = 0; l < nn; l++) xe[((size_t)e * 3 + c) * nn + l] = xv.HostRead()[c * nn + (dm.Size() ? dm[l] : l)];
+    attr[e] = mesh.GetAttribute(e);
+  }
+  std::vector<double> qw(q1d);
+  for (int i = 0; i < q1d; i++) qw[i] = ir1d.IntPoint(i).weight;
+  b2p_geom *geom = nullptr;
+  Check(b2p_geom_create_hex(ctx, ne, k, q1d, xe.data(), nB.data(), nG.data(), qw.data(), attr.data(), &geom), ctx);
+  return geom;
+}
+
+// One integrator of the form on one hexahedral block: kind from fem/integ/{curlcurl,vecfemass,curlcurlmass}.cpp, the
+// coefficient context bytes exactly as PopulateCoefficientContext builds them (fem/libceed/coefficient.cpp:51-130).
+inline b2p_op *CreateHexNDIntegrator(b2p_ctx *ctx, b2p_geom *geom, int kind, const HexNDSpaceInputs &in, const void *coeff_ctx,
+                                     size_t coeff_ctx_bytes, bool assemble_q_data = false)
+{
+  b2p_op_desc d = {};
+  d.kind = kind;
+  d.p = in.p;
+  d.ne = in.ne;
+  d.lsize = in.lsize;
+  d.idx = in.idx.data();
+  d.orient = in.orient.data();
+  d.dof_map = in.dof_map.data();
+  d.Bo = in.Bo.data();
+  d.Bc = in.Bc.data();
+  d.Gc = in.Gc.data();
+  d.coeff_ctx = coeff_ctx;
+  d.coeff_ctx_bytes = coeff_ctx_bytes;
+  d.assemble_qdata = assemble_q_data ? 1 : 0;
+  b2p_op *op = nullptr;
+  Check(b2p_op_create(ctx, geom, &d, &op), ctx);
+  return op;
 }
 
 // Same five methods as ceed::Operator; sub-operators are b2p_op handles created by the integrator glue.
@@ -218,6 +341,49 @@ public:
   long long Rows() const { return b2p_csr_rows(csr); }
   long long NNZ() const { return b2p_csr_nnz(csr); }
   void DeviceArrays(const int **I, const int **J, const double **data) const { Check(b2p_csr_device_arrays(csr, I, J, data), ctx); }
+};
+
+// palace::BaseKspSolver<Operator> (palace/linalg/ksp.hpp:24-75, ksp.cpp:256-328): the configured Krylov solver together
+// with its (multigrid) preconditioner, built from one b2p_ksp_config -- see INTEGRATION.md section 5 for the field mapping
+// from config::LinearSolverData. P / G: prolongation and discrete-gradient operators of the space hierarchy
+// (fespaces.GetProlongationOperators(), GetDiscreteInterpolators(aux_fespaces)), already wrapped as b2p_operator handles.
+class KspSolverAdapter
+{
+  b2p_ctx *ctx;
+  b2p_ksp *K = nullptr;
+  int n_levels;
+
+public:
+  KspSolverAdapter(b2p_ctx *ctx, const b2p_ksp_config &cfg, const std::vector<b2p_operator *> &P, const std::vector<b2p_operator *> &G,
+                   b2p_solver *coarse_plugin = nullptr)
+    : ctx(ctx), n_levels((int)P.size() + 1)
+  {
+    Check(b2p_ksp_create(ctx, &cfg, n_levels, P.data(), G.empty() ? nullptr : G.data(), coarse_plugin, &K), ctx);
+  }
+  ~KspSolverAdapter() { b2p_ksp_destroy(K); }
+  // SetOperators(op, pc_op): pc_levels / aux_levels are the ParOperators of the MultigridOperator, coarsest first
+  void SetOperators(const ParOperatorAdapter &op, const std::vector<const ParOperatorAdapter *> &pc_levels,
+                    const std::vector<const ParOperatorAdapter *> &aux_levels)
+  {
+    MFEM_VERIFY((int)pc_levels.size() == n_levels, "one preconditioner operator per multigrid level!");
+    std::vector<b2p_operator *> A, Ax;
+    for (auto *a : pc_levels) A.push_back(a->Handle());
+    for (auto *a : aux_levels) Ax.push_back(a ? a->Handle() : nullptr);
+    Check(b2p_ksp_set_operators(K, op.Handle(), A.data(), Ax.empty() ? nullptr : Ax.data()), ctx);
+  }
+  void Mult(const mfem::Vector &x, mfem::Vector &y) const { Check(b2p_ksp_mult(K, x.Read(true), y.ReadWrite(true)), ctx); }
+  int NumTotalMult() const
+  {
+    int n = 0;
+    Check(b2p_ksp_stats(K, &n, nullptr, nullptr, nullptr, nullptr, nullptr), ctx);
+    return n;
+  }
+  int NumTotalMultIterations() const
+  {
+    int n = 0;
+    Check(b2p_ksp_stats(K, nullptr, &n, nullptr, nullptr, nullptr, nullptr), ctx);
+    return n;
+  }
 };
 
 }  // namespace b2p::palace

@@ -802,3 +802,61 @@ class ComplexSolver:
         r0, r1 = C.c_double(), C.c_double()
         _chk(lib().b2p_csolver_stats(self.h, C.byref(its), C.byref(r0), C.byref(r1), C.byref(conv)), self.ctx.h)
         return dict(its=its.value, initial_res=r0.value, final_res=r1.value, converged=bool(conv.value))
+
+
+class KspConfig(C.Structure):
+    """b2p_ksp_config (include/b2p.h): config::LinearSolverData as the composer reads it."""
+    _fields_ = [("krylov_solver", C.c_int), ("tol", C.c_double), ("max_it", C.c_int), ("max_size", C.c_int), ("initial_guess", C.c_int),
+                ("pc_side", C.c_int), ("gs_orthog", C.c_int), ("mg_cycle_it", C.c_int), ("mg_smooth_aux", C.c_int),
+                ("mg_smooth_it", C.c_int), ("mg_smooth_order", C.c_int), ("mg_smooth_sf_max", C.c_double),
+                ("mg_smooth_sf_min", C.c_double), ("mg_smooth_cheby_4th", C.c_int), ("coarse_type", C.c_int),
+                ("coarse_tol", C.c_double), ("coarse_max_it", C.c_int)]
+
+
+class Ksp:
+    """BaseKspSolver (linalg/ksp.cpp): configuration -> Krylov solver + (multigrid) preconditioner, with the reference's
+    NumTotalMult / NumTotalMultIts counters."""
+
+    def __init__(self, ctx, order, P=(), G=None, coarse_solver=None, **overrides):
+        self.ctx = ctx
+        self.cfg = KspConfig()
+        _chk(lib().b2p_ksp_config_default(C.byref(self.cfg), int(order)), ctx.h)
+        for k, v in overrides.items():
+            assert hasattr(self.cfg, k), k
+            setattr(self.cfg, k, v)
+        n_levels = len(P) + 1
+        Parr = (C.c_void_p * max(1, len(P)))(*[p.h for p in P])
+        Garr = None
+        if G is not None:
+            Garr = (C.c_void_p * n_levels)(*[(g.h if g is not None else None) for g in G])
+        self.h = C.c_void_p()
+        _chk(lib().b2p_ksp_create(ctx.h, C.byref(self.cfg), n_levels, Parr, Garr, coarse_solver.h if coarse_solver else None,
+                                  C.byref(self.h)), ctx.h)
+        self.n_levels = n_levels
+        self._keep = [list(P), G, coarse_solver]
+
+    def set_operators(self, op, pc_ops, aux_ops=None):
+        A = (C.c_void_p * self.n_levels)(*[a.h for a in pc_ops])
+        Ax = None
+        if aux_ops is not None:
+            Ax = (C.c_void_p * self.n_levels)(*[(a.h if a is not None else None) for a in aux_ops])
+        _chk(lib().b2p_ksp_set_operators(self.h, op.h, A, Ax), self.ctx.h)
+        self._keep += [op, list(pc_ops), aux_ops]
+
+    def mult(self, x, y):
+        _chk(lib().b2p_ksp_mult(self.h, _vp(x), _vp(y)), self.ctx.h)
+
+    def stats(self):
+        nm, nit, its, conv = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        r0, r1 = C.c_double(), C.c_double()
+        _chk(lib().b2p_ksp_stats(self.h, C.byref(nm), C.byref(nit), C.byref(its), C.byref(r0), C.byref(r1), C.byref(conv)), self.ctx.h)
+        return {"num_total_mult": nm.value, "num_total_mult_its": nit.value, "its": its.value, "initial_res": r0.value,
+                "final_res": r1.value, "converged": bool(conv.value)}
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b2p_ksp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

@@ -213,6 +213,238 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(DenseParams prm)
   }
 }
 
+// Round-2 kernel: the two GEMMs of an element batch are fused over chunks of QC quadrature points, so that
+//   * the [6Q x NEB] array of point values never exists -- only a [6 QC x NEB] chunk does, which leaves room for NT = 4
+//     n-tiles (32 elements per CTA): every table fragment fetched from L2 / L1 feeds four MMAs (the round-1 kernel streamed
+//     the whole table twice per 8 elements and was bound by those loads: 4.4 TFLOP/s, 12 % of the DMMA peak);
+//   * the output accumulators Y[Ppad x NEB] stay in registers across the chunks (each warp owns its dof tiles);
+//   * table fragments are prefetched four k-steps ahead into registers.
+// Chunk rows are ordered [block c][point j], block c < 3: interp component c, c >= 3: deriv component c - 3 (blocks of absent
+// parts are skipped); QC is a multiple of 8, so an m-tile never straddles two blocks.
+template <int NT, int QC, int MTB>
+__global__ void __launch_bounds__(256) dense_apply2_kernel(DenseParams prm)
+{
+  constexpr int NEB = NEB0 * NT, LS = NEB + 4;  // row stride of the shared arrays: +4 doubles makes the B-fragment reads conflict free
+  B2P_DYN_SMEM(double, sm);
+  const int P = prm.P, Q = prm.Q, Ppad = prm.Ppad;
+  const bool MASS = (prm.kind == B2P_ND_MASS || prm.kind == B2P_CURLCURL_MASS);
+  const bool CURL = (prm.kind == B2P_CURLCURL || prm.kind == B2P_CURLCURL_MASS);
+  const bool H1 = (prm.kind == B2P_H1_DIFFUSION);
+  const int nblk = ((MASS ? 3 : 0) + ((CURL || H1) ? 3 : 0));  // row blocks per chunk
+  const int CR = nblk * QC;                                    // chunk rows
+  double *U = sm;                 // [Ppad][LS]
+  double *V = U + Ppad * LS;      // [6 QC][LS]
+  double *X = V + 6 * QC * LS;    // [Ppad][LS] raw gathered values (curl-oriented restriction only)
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int e0 = blockIdx.x * NEB;
+  // table row of chunk row r (block c = r / QC, point q0 + r % QC); rows of points >= Q are clamped (their V entries are zeroed)
+  auto table_row = [&](int r, int q0) -> int
+  {
+    const int c = r / QC, iq = min(q0 + r % QC, Q - 1);
+    const int base = (MASS && c < 3) ? prm.row_u + c * Q : prm.row_c + (c - (MASS ? 3 : 0)) * Q;
+    return base + iq;
+  };
+
+  // ---- restriction (E): native order, sign or tridiagonal orientation ----
+  for (int w = tid; w < Ppad * NEB; w += blockDim.x)
+  {
+    const int i = w / NEB, e = w % NEB;
+    double v = 0.0;
+    if (i < P && e0 + e < prm.ne)
+    {
+      const int32_t gi = prm.lidx[(size_t)(e0 + e) * prm.PS + i];
+      if (prm.curl_orient)
+        v = (gi == B2P_SKIP_IDX) ? 0.0 : __ldg(split_src(prm.x, prm.sp, gi >= 0 ? gi : -1 - gi));
+      else
+        v = gather2(prm.x, prm.sp, gi);
+    }
+    (prm.curl_orient ? X : U)[i * LS + e] = v;
+  }
+  if (prm.curl_orient)
+  {
+    __syncthreads();
+    for (int w = tid; w < Ppad * NEB; w += blockDim.x)
+    {
+      const int i = w / NEB, e = w % NEB;
+      double v = 0.0;
+      if (i < P && e0 + e < prm.ne)
+      {
+        const int8_t *co = prm.curl_orient + ((size_t)(e0 + e) * P + i) * 3;
+        v = (double)co[1] * X[i * LS + e];
+        if (i > 0) v += (double)co[0] * X[(i - 1) * LS + e];
+        if (i < P - 1) v += (double)co[2] * X[(i + 1) * LS + e];
+      }
+      U[i * LS + e] = v;
+    }
+  }
+  __syncthreads();
+
+  // output accumulators: dof tiles wid, wid + nw, ... of this warp, NT n-tiles each
+  double acc[MTB][NT][2];
+#pragma unroll
+  for (int t = 0; t < MTB; t++)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+
+  const int KF = Ppad / 4;  // k-steps of the forward GEMM
+  for (int q0 = 0; q0 < Q; q0 += QC)
+  {
+    // ---- V_chunk = T_chunk U : m-tiles over chunk rows, k over dofs ----
+    for (int mt = wid; mt < CR / 8; mt += nw)
+    {
+      double c[NT][2];
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) c[nt][0] = c[nt][1] = 0.0;
+      const double *Arow = prm.T + (size_t)table_row(mt * 8 + lane / 4, q0) * Ppad + (lane % 4);
+      const double *Bcol = U + (lane % 4) * LS + lane / 4;
+      double a[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) a[j] = (j < KF) ? __ldg(Arow + 4 * j) : 0.0;
+      for (int kk = 0; kk < KF; kk += 4)
+      {
+        double an[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) an[j] = (kk + 4 + j < KF) ? __ldg(Arow + 4 * (kk + 4 + j)) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (kk + j < KF)
+          {
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) dmma884(c[nt][0], c[nt][1], a[j], Bcol[(size_t)(kk + j) * 4 * LS + 8 * nt]);
+          }
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = an[j];
+      }
+      double *o = V + (mt * 8 + lane / 4) * LS + 2 * (lane % 4);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++)
+      {
+        o[8 * nt] = c[nt][0];
+        o[8 * nt + 1] = c[nt][1];
+      }
+    }
+    __syncthreads();
+
+    // ---- D at the chunk's quadrature points (in place); points beyond Q and elements beyond ne become zero rows ----
+    for (int w = tid; w < QC * NEB; w += blockDim.x)
+    {
+      const int j = w / NEB, e = w % NEB, iq = q0 + j;
+      const bool ok = iq < Q && e0 + e < prm.ne;
+      const double *g = prm.qd + (size_t)(e0 + (ok ? e : 0)) * 10 * Q + (ok ? iq : 0);
+      const double *C = prm.ecoef + (size_t)(e0 + (ok ? e : 0)) * 18;
+      const double wdetJ = ok ? prm.alpha * g[0] : 0.0;
+      double A[9], Cm[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) A[i] = g[(1 + i) * Q];
+      if (MASS || H1)
+      {
+        double *r = V + j * LS + e;  // blocks 0, 1, 2
+        double u[3] = {r[0], r[QC * LS], r[2 * QC * LS]}, v[3];
+#pragma unroll
+        for (int i = 0; i < 9; i++) Cm[i] = C[i];
+        AtCAx(A, Cm, u, wdetJ, v);
+        r[0] = v[0];
+        r[QC * LS] = v[1];
+        r[2 * QC * LS] = v[2];
+      }
+      if (CURL)
+      {
+        double *r = V + ((MASS ? 3 : 0) * QC + j) * LS + e;
+        double c[3] = {r[0], r[QC * LS], r[2 * QC * LS]}, v[3], Jd[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) Cm[i] = C[9 + i];
+        cofactor33(A, Jd);
+        AtCAx(Jd, Cm, c, wdetJ, v);
+        r[0] = v[0];
+        r[QC * LS] = v[1];
+        r[2 * QC * LS] = v[2];
+      }
+    }
+    __syncthreads();
+
+    // ---- Y += T_chunk^T V_chunk : this warp's dof tiles, k over chunk rows ----
+#pragma unroll
+    for (int t = 0; t < MTB; t++)
+    {
+      const int mt = wid + t * nw;
+      if (mt < Ppad / 8)
+      {
+        const double *Bcol = V + (lane % 4) * LS + lane / 4;
+        const int KB = CR / 4;
+        // A[m = dof][k = chunk row]: lane reads T[table_row(4 k + lane % 4)][8 mt + lane / 4]
+        auto lda = [&](int k) -> double { return __ldg(prm.T + (size_t)table_row(4 * k + lane % 4, q0) * Ppad + mt * 8 + lane / 4); };
+        double a[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = (j < KB) ? lda(j) : 0.0;
+        for (int kk = 0; kk < KB; kk += 4)
+        {
+          double an[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) an[j] = (kk + 4 + j < KB) ? lda(kk + 4 + j) : 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (kk + j < KB)
+            {
+#pragma unroll
+              for (int nt = 0; nt < NT; nt++) dmma884(acc[t][nt][0], acc[t][nt][1], a[j], Bcol[(size_t)(kk + j) * 4 * LS + 8 * nt]);
+            }
+#pragma unroll
+          for (int j = 0; j < 4; j++) a[j] = an[j];
+        }
+      }
+    }
+    __syncthreads();  // the next chunk's forward GEMM overwrites V
+  }
+
+  // ---- accumulators -> U (as Y), then E^T ----
+#pragma unroll
+  for (int t = 0; t < MTB; t++)
+  {
+    const int mt = wid + t * nw;
+    if (mt < Ppad / 8)
+    {
+      double *o = U + (mt * 8 + lane / 4) * LS + 2 * (lane % 4);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++)
+      {
+        o[8 * nt] = acc[t][nt][0];
+        o[8 * nt + 1] = acc[t][nt][1];
+      }
+    }
+  }
+  __syncthreads();
+  if (prm.curl_orient)
+  {
+    for (int w = tid; w < Ppad * NEB; w += blockDim.x)
+    {
+      const int i = w / NEB, e = w % NEB;
+      double v = 0.0;
+      if (i < P && e0 + e < prm.ne)
+      {
+        const int8_t *co = prm.curl_orient + ((size_t)(e0 + e) * P) * 3;
+        v = (double)co[3 * i + 1] * U[i * LS + e];
+        if (i > 0) v += (double)co[3 * (i - 1) + 2] * U[(i - 1) * LS + e];
+        if (i < P - 1) v += (double)co[3 * (i + 1) + 0] * U[(i + 1) * LS + e];
+      }
+      X[i * LS + e] = v;
+    }
+    __syncthreads();
+  }
+  const double *src = prm.curl_orient ? X : U;
+  for (int w = tid; w < P * NEB; w += blockDim.x)
+  {
+    const int i = w / NEB, e = w % NEB;
+    if (e0 + e >= prm.ne) continue;
+    const int32_t gi = prm.lidx[(size_t)(e0 + e) * prm.PS + i];
+    if (prm.curl_orient)
+    {
+      if (gi != B2P_SKIP_IDX) scatter2(prm.y, prm.sp, gi >= 0 ? gi : -1 - gi, src[i * LS + e]);
+    }
+    else
+      scatter2(prm.y, prm.sp, gi, src[i * LS + e]);
+  }
+}
+
 // diag[g(i)] += sum_q w(q)^T D w(q) with w = the i-th shape function as the global side sees it: for sign
 // orientation that is column i of the table (the sign squares away); for the tridiagonal orientation it is
 // sum_l T_e(l, i) * column l, which makes the diagonal of T^T A T exact (libCEED assembles it through the unsigned
@@ -307,11 +539,54 @@ DenseParams make_params(b2p_op *op, const int32_t *lidx, double alpha, const dou
 
 }  // namespace
 
+namespace
+{
+// The fused, chunked kernel: NT n-tiles per CTA, QC points per chunk, up to MTB dof tiles per warp.
+template <int NT, int QC, int MTB>
+int launch_dense2(b2p_op *op, const DenseParams &prm, int nwarps, cudaStream_t s)
+{
+  constexpr int NEB = NEB0 * NT, LS = NEB + 4;
+  const size_t shmem = sizeof(double) * LS * ((size_t)prm.Ppad + 6 * QC + (op->curl_orient ? prm.Ppad : 0));
+  auto kern = dense_apply2_kernel<NT, QC, MTB>;
+  static size_t configured = 0;
+  if (shmem > configured)
+  {
+    B2P_CUDA(op->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    configured = shmem;
+  }
+  B2P_LAUNCH(kern, (prm.ne + NEB - 1) / NEB, nwarps * 32, shmem, s, prm);
+  B2P_CUDA(op->ctx, cudaGetLastError());
+  return B2P_SUCCESS;
+}
+}  // namespace
+
 int launch_dense_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg,
                        cudaStream_t s)
 {
   DenseParams prm = make_params(op, lidx, alpha, x, y, rg);
   if (prm.ne <= 0) return B2P_SUCCESS;
+  // B2P_DENSE_KERNEL=1: the round-1 kernel (whole [6Q x 8] point array in shared memory, table streamed per 8 elements)
+  static const int which = []
+  {
+    const char *e = std::getenv("B2P_DENSE_KERNEL");
+    return e ? std::atoi(e) : 2;
+  }();
+  if (which == 2 && prm.ne >= 32)
+  {
+    constexpr int QC = 32;
+    const int tiles = prm.Ppad / 8;  // dof tiles of the backward GEMM: one warp per tile up to 8 warps, then several per warp
+    const int nwarps = tiles < 8 ? (tiles < 4 ? 4 : tiles) : 8;
+    const int mtb = (tiles + nwarps - 1) / nwarps;
+    const size_t need = sizeof(double) * 36 * ((size_t)prm.Ppad + 6 * QC + (op->curl_orient ? prm.Ppad : 0));
+    if (need <= 227 * 1024 && mtb <= 4)
+    {
+      static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
+      if (trace) fprintf(stderr, "[b2p] dense_apply2 P=%d Q=%d ne=%d warps=%d tiles/warp=%d\n", prm.P, prm.Q, prm.ne, nwarps, mtb);
+      if (mtb <= 1) return launch_dense2<4, QC, 1>(op, prm, nwarps, s);
+      if (mtb <= 2) return launch_dense2<4, QC, 2>(op, prm, nwarps, s);
+      return launch_dense2<4, QC, 4>(op, prm, nwarps, s);
+    }
+  }
   const size_t shmem1 = sizeof(double) * NEB0 * ((size_t)prm.Ppad + prm.Rpad + (op->curl_orient ? prm.Ppad : 0));
   B2P_CHECK(op->ctx, shmem1 <= 227 * 1024, B2P_ERR_UNSUPPORTED, "dense operator: element too large for shared memory (%zu B)", shmem1);
   static const int want_nt = []

@@ -124,20 +124,27 @@ __global__ void p2p_pre_kernel(const double *__restrict__ src, const int32_t *__
                                unsigned int *done, unsigned long long *bump_expect, const int *recv_has, unsigned long long *expect_rev,
                                double *__restrict__ y, long long ny, double *__restrict__ yg, long long nyg)
 {
+  griddep_launch_dependents();  // the element kernel may start its prologue now (it waits on this grid before its first scatter / ghost read)
   if (blockIdx.x == 0 && (int)threadIdx.x < nn) ++expect_rev[threadIdx.x];
   if ((int)blockIdx.x < nn * GX)
   {
     const int k = blockIdx.x / GX, bx = blockIdx.x % GX;
     const long long b = seg_off[k], e = seg_off[k + 1];
-    double *dst = dst_ptr[k];
-    for (long long i = b + (long long)bx * blockDim.x + threadIdx.x; i < e; i += (long long)GX * blockDim.x) dst[i - b] = src[idx[i]];
-    __threadfence_system();
+    double *__restrict__ dst = dst_ptr[k];
+    // (GX is sized so that this is a single pass: a short kernel of dependent idx -> x -> remote store chains is bound by
+    // their latency, 8 us for 15k values on 16 blocks -- measured with B2P_HALO_TIMING)
+    for (long long i = b + (long long)bx * blockDim.x + threadIdx.x; i < e; i += (long long)GX * blockDim.x) dst[i - b] = __ldg(src + __ldg(idx + i));
+    // Device-scope fence + block barrier + device-scope counter: the ONE system-scope release by the publishing thread below is
+    // cumulative over everything ordered before it (a system-scope fence per thread costs ~10 us per kernel on NVSwitch
+    // systems -- measured with B2P_HALO_TIMING: 12.6 us for a PRE kernel that pushes nothing).
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
     {
       const unsigned int prev = atomicAdd(done + k, 1u);
       if (prev == (unsigned)GX - 1)
       {
+        __threadfence();  // acquire side of the counter: every block's stores are ordered before the release below
         done[k] = 0;
         if (bump_expect && recv_has[k]) ++bump_expect[k];
         const unsigned long long ep = ++epoch[k];
@@ -151,7 +158,15 @@ __global__ void p2p_pre_kernel(const double *__restrict__ src, const int32_t *__
   }
   const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long i = t0; i < nyg; i += stride) yg[i] = 0.0;
-  for (long long i = t0; i < ny; i += stride) y[i] = 0.0;
+  if ((reinterpret_cast<uintptr_t>(y) & 15) == 0)
+  {
+    double2 *y2 = reinterpret_cast<double2 *>(y);
+    const long long n2 = ny / 2;
+    for (long long i = t0; i < n2; i += stride) y2[i] = make_double2(0.0, 0.0);
+    if (t0 == 0 && (ny & 1)) y[ny - 1] = 0.0;
+  }
+  else
+    for (long long i = t0; i < ny; i += stride) y[i] = 0.0;
 }
 // POST: reverse exchange in one launch. Block (k, bx) copies its slice of ghost segment k into the peer's receive block
 // (last block of the column publishes the epoch), then waits for the peer's flag and adds its slice of the values received
@@ -163,17 +178,22 @@ __global__ void p2p_post_kernel(const double *__restrict__ yg, const long long *
                                 const int32_t *__restrict__ idx, const double *__restrict__ buf)
 {
   const int k = blockIdx.x / GX, bx = blockIdx.x % GX;
+  griddep_wait();  // launched with programmatic stream serialisation: the element kernel has completed from here on
   {
     const long long b = recv_off[k], e = recv_off[k + 1];
-    double *dst = dst_ptr[k];
-    for (long long i = b + (long long)bx * blockDim.x + threadIdx.x; i < e; i += (long long)GX * blockDim.x) dst[i - b] = yg[i];
-    __threadfence_system();
+    double *__restrict__ dst = dst_ptr[k];
+    for (long long i = b + (long long)bx * blockDim.x + threadIdx.x; i < e; i += (long long)GX * blockDim.x) dst[i - b] = __ldcv(yg + i);
+    // Device-scope fence + block barrier + device-scope counter: the ONE system-scope release by the publishing thread below is
+    // cumulative over everything ordered before it (a system-scope fence per thread costs ~10 us per kernel on NVSwitch
+    // systems -- measured with B2P_HALO_TIMING: 12.6 us for a PRE kernel that pushes nothing).
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
     {
       const unsigned int prev = atomicAdd(done + k, 1u);
       if (prev == (unsigned)GX - 1)
       {
+        __threadfence();  // acquire side of the counter: every block's stores are ordered before the release below
         done[k] = 0;
         const unsigned long long ep = ++epoch[k];
         if (e > b)
@@ -206,7 +226,9 @@ int halo_pre_p2p(Halo *h, const double *x, double *y, long long ny, bool in_kern
 {
   const int nn = (int)h->nbr.size();
   const long long ns = nn ? h->send_off.back() : 0;
-  const int GX = nn ? (int)std::min<long long>((ns / nn + 255) / 256 + 1, 16) : 1;
+  long long seg = 0;  // largest segment: one value per thread up to 16k values per neighbour
+  for (int k = 0; k < nn; k++) seg = std::max<long long>(seg, h->send_off[k + 1] - h->send_off[k]);
+  const int GX = nn ? (int)std::min<long long>((seg + 255) / 256 + 1, 64) : 1;
   int grid = h->ctx->sm_count * 4;
   if (grid < nn * GX) grid = nn * GX;
   B2P_LAUNCH(p2p_pre_kernel, grid, 256, 0, s, x, h->d_send_idx, h->d_send_off, nn, GX, h->d_peer_fwd, h->d_peer_flag_fwd, h->d_epoch, h->d_done,
@@ -216,14 +238,25 @@ int halo_pre_p2p(Halo *h, const double *x, double *y, long long ny, bool in_kern
   return B2P_SUCCESS;
 }
 // Reverse exchange of the step opened by halo_pre_p2p: ghost contributions -> owners, summed into y, in one launch.
-int halo_post_p2p(Halo *h, double *y, cudaStream_t s)
+int halo_post_p2p(Halo *h, double *y, cudaStream_t s, bool pdl)
 {
   const int nn = (int)h->nbr.size();
   if (nn == 0) return B2P_SUCCESS;
   const long long nr = h->recv_off.back(), ns = h->send_off.back();
-  const int GX = (int)std::min<long long>((std::max(nr, ns) / nn + 255) / 256 + 1, 16);
-  B2P_LAUNCH(p2p_post_kernel, nn * GX, 256, 0, s, h->d_yg, h->d_recv_off, h->d_send_off, GX, h->d_peer_rev, h->d_peer_flag_rev, h->d_epoch + 32,
-             h->d_done + 32, h->d_flags + 32, h->d_epoch + 3 * 32, y, h->d_send_idx, h->d_mail_rev);
+  long long seg = 0;
+  for (int k = 0; k < nn; k++)
+    seg = std::max<long long>(seg, std::max<long long>(h->send_off[k + 1] - h->send_off[k], h->recv_off[k + 1] - h->recv_off[k]));
+  (void)nr;
+  (void)ns;
+  const int GX = (int)std::min<long long>((seg + 255) / 256 + 1, 64);
+  if (pdl)
+    B2P_LAUNCH_PDL(p2p_post_kernel, nn * GX, 256, 0, s, (const double *)h->d_yg, (const long long *)h->d_recv_off, (const long long *)h->d_send_off, GX,
+                   (double *const *)h->d_peer_rev, (unsigned long long *const *)h->d_peer_flag_rev, h->d_epoch + 32, h->d_done + 32,
+                   (const unsigned long long *)(h->d_flags + 32), (const unsigned long long *)(h->d_epoch + 3 * 32), y,
+                   (const int32_t *)h->d_send_idx, (const double *)h->d_mail_rev);
+  else
+    B2P_LAUNCH(p2p_post_kernel, nn * GX, 256, 0, s, h->d_yg, h->d_recv_off, h->d_send_off, GX, h->d_peer_rev, h->d_peer_flag_rev, h->d_epoch + 32,
+               h->d_done + 32, h->d_flags + 32, h->d_epoch + 3 * 32, y, h->d_send_idx, h->d_mail_rev);
   B2P_CUDA(h->ctx, cudaGetLastError());
   return B2P_SUCCESS;
 }

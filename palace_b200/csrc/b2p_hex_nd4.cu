@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
   const int nb = (prm.ne + NEB - 1) / NEB;  // element batches
   const int GW = gridDim.x * NW;            // warps in the grid
   int b = blockIdx.x * NW + wid;
+  griddep_launch_dependents();              // a dependent launched programmatically (the halo POST kernel) may be scheduled as CTAs retire
   if (b >= nb) return;                      // (whole warp)
 
   if (lane == 0)
@@ -245,10 +246,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
   };
 
   // Peer-memory halo: ghost values of this step are complete once every neighbour's flag reached the expected epoch.
+  bool y_ready = false;  // the grid dependency (zero-fill of y / the halo PRE kernel under programmatic dependent launch) is resolved
   bool ghosts_ready = !(SPLIT && prm.wait_n > 0);
   auto wait_ghosts = [&](int bb)
   {
     if (ghosts_ready || (bb + 1) * NEB <= prm.wait_from_elem) return;
+    if (!y_ready)
+    {
+      griddep_wait();  // the expected epochs are advanced by the PRE kernel this grid may be overlapping
+      y_ready = true;
+    }
     if (lane < prm.wait_n)
     {
       const unsigned long long want = prm.wait_expect[lane];
@@ -278,7 +285,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) nd_hex_apply4_kernel(const __gr
 
   const double alpha = prm.alpha;
   int slot = 0;
-  bool y_ready = false;
   for (; b < nb; b += GW)
   {
     const int nslot = (slot == 2) ? 0 : slot + 1;

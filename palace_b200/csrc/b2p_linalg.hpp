@@ -170,6 +170,8 @@ private:
   // CUDA graph and replayed (solver loops reuse a handful of vector pairs).
   void MultHaloBody(const double *x, double *y, cudaStream_t s) const;
   mutable std::map<std::pair<const double *, double *>, cudaGraphExec_t> graphs_;
+  mutable double halo_ms_[3] = {0.0, 0.0, 0.0};  // B2P_HALO_TIMING: accumulated event times of pre / element / post
+  mutable long halo_calls_ = 0;
   mutable bool warmed_ = false;
   mutable bool capture_failed_ = false;  // stream capture is not possible on this stream: stay on the eager sequence
 };

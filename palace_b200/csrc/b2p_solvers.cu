@@ -15,7 +15,7 @@ int halo_reverse_split(Halo *h, double *y, cudaStream_t s);
 int halo_forward_p2p(Halo *h, const double *x, bool in_kernel_wait, cudaStream_t s);
 int halo_reverse_p2p(Halo *h, double *y, cudaStream_t s);
 int halo_pre_p2p(Halo *h, const double *x, double *y, long long ny, bool in_kernel_wait, cudaStream_t s);
-int halo_post_p2p(Halo *h, double *y, cudaStream_t s);
+int halo_post_p2p(Halo *h, double *y, cudaStream_t s, bool pdl);
 int interp_apply(const b2p_interp *it, bool transpose, double alpha, const double *x, double *y, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------ Operator
@@ -101,6 +101,16 @@ void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
   // the collectives with the element kernel was measured to give nothing on B200: the persistent element
   // kernel fills every SM, so a collective kernel launched beside it only starts when it retires.)
   Halo *h = halo;
+  // B2P_HALO_TIMING=1 (diagnostic): CUDA events between the three launches, accumulated per operator and printed by the
+  // destructor -- where the time of a partitioned Mult goes on this rank (the events serialise nothing: same stream).
+  static const bool timing = []() { const char *e = getenv("B2P_HALO_TIMING"); return e && e[0] == '1'; }();
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (timing)
+    for (auto &e : ev)
+    {
+      cudaEventCreate(&e);
+    }
+  if (timing) cudaEventRecord(ev[0], s);
   // B2P_HALO_FUSED=0 keeps the round-1 sequence (zero-fill, push, element kernel, push, wait+add: five launches)
   static const bool fused_halo = []() { const char *e = getenv("B2P_HALO_FUSED"); return !(e && e[0] == '0'); }();
   const bool fused = h->p2p && fused_halo;
@@ -121,12 +131,22 @@ void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
     halo_forward_p2p(h, x, in_kernel, s);
   else
     halo_forward_split(h, x, s);
+  // Eager launches of the fused sequence are chained by programmatic dependent launch: the element kernel starts while the
+  // PRE kernel still zero-fills (it waits on the grid dependency before its first scatter or ghost read), the POST kernel
+  // is scheduled as the element kernel's CTAs retire. (Not inside a stream capture.)
+  if (timing) cudaEventRecord(ev[1], s);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  static const bool pdl_env = []() { const char *e = getenv("B2P_PDL"); return !(e && e[0] == '0'); }();
+  bool pdl = fused && pdl_env && cap == cudaStreamCaptureStatusNone && terms.size() == 1;
+  for (auto &t : terms) pdl = pdl && t.op->kind != B2P_H1_DIFFUSION && !t.op->dense && in_kernel;
   for (auto &t : terms)
   {
     ApplyRange rg;
     rg.n_owned = height;
     rg.xg = h->d_xg;
     rg.yg = h->d_yg;
+    rg.pdl = pdl;
     if (in_kernel)
     {
       rg.wait_flags = h->d_flags;
@@ -136,12 +156,32 @@ void ParOperator::MultHaloBody(const double *x, double *y, cudaStream_t s) const
     }
     apply_range(t.op, t.op->lidx_bc ? t.op->lidx_bc : t.op->lidx, t.coef, x, y, rg, 0, s);
   }
+  if (timing) cudaEventRecord(ev[2], s);
   if (fused)
-    halo_post_p2p(h, y, s);  // push, wait and add: one launch
+    halo_post_p2p(h, y, s, pdl);  // push, wait and add: one launch
   else if (h->p2p)
     halo_reverse_p2p(h, y, s);
   else
     halo_reverse_split(h, y, s);
+  if (timing)
+  {
+    cudaEventRecord(ev[3], s);
+    cudaEventSynchronize(ev[3]);
+    for (int i = 0; i < 3; i++)
+    {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      halo_ms_[i] += ms;
+    }
+    halo_calls_++;
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (halo_calls_ % 100 == 0)
+    {
+      fprintf(stderr, "[b2p] rank %d ParOperator halo timing, last 100 Mults: pre %.2f us, element kernel(s) %.2f us, post %.2f us\n", ctx->rank,
+              10.0 * halo_ms_[0], 10.0 * halo_ms_[1], 10.0 * halo_ms_[2]);
+      halo_ms_[0] = halo_ms_[1] = halo_ms_[2] = 0.0;
+    }
+  }
 }
 
 // rap.cpp:195-234
@@ -180,7 +220,9 @@ void ParOperator::Mult(const double *x, double *y) const
     // Capture and replay on an internal BLOCKING stream instead -- it synchronises implicitly with the legacy stream in
     // both directions, so the caller's ordering is preserved. (B2P_GRAPH_STREAM=0: a legacy-stream context runs the eager
     // sequence, as in round 1.)
-    static const bool graph_stream = []() { const char *e = getenv("B2P_GRAPH_STREAM"); return !(e && e[0] == '0'); }();
+    // Measured on 2 B200s (profiles/r02_bench_2gpu_halo_variants.json): replay on the internal blocking stream costs more in
+    // legacy-stream synchronisation than it saves in launches (81.4 vs 78.4 us per Mult) -- opt-in, B2P_GRAPH_STREAM=1.
+    static const bool graph_stream = []() { const char *e = getenv("B2P_GRAPH_STREAM"); return e && e[0] == '1'; }();
     if (s == nullptr && graph_stream && !no_graph)
     {
       if (!ctx->graph_stream && cudaStreamCreate(&ctx->graph_stream) != cudaSuccess) ctx->graph_stream = nullptr;

@@ -49,6 +49,11 @@ struct dim3
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
+struct alignas(16) double2
+{
+  double x, y;
+};
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 extern "C" void b2p_emu_switch(void **save_sp, void *new_sp);
 #ifdef B2P_EMU_DEFINE_SWITCH

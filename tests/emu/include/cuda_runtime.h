@@ -147,9 +147,26 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned)
   *e = nullptr;
   return cudaSuccess;
 }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { return cudaEventCreateWithFlags(e, 0); }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t)
+{
+  *ms = 0.f;
+  return cudaSuccess;
+}
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+enum cudaStreamCaptureStatus
+{
+  cudaStreamCaptureStatusNone = 0,
+  cudaStreamCaptureStatusActive = 1
+};
+inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus *st)
+{
+  *st = cudaStreamCaptureStatusNone;
+  return cudaSuccess;
+}
 inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
 inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *) { return cudaErrorNotSupported; }
 inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long = 0) { return cudaErrorNotSupported; }

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdlib>
 #include <iostream>
+#include <vector>
 #define MFEM_VERSION 40700
 #define MFEM_ABORT(msg)                  \
   do                                     \
@@ -34,6 +35,16 @@ public:
     for (int i = 0; i < n; i++) d[i] = v;
     return *this;
   }
+  void SetSize(int n_)
+  {
+    delete[] d;
+    d = new double[n_]();
+    n = n_;
+  }
+  double *HostWrite() { return d; }
+  const double *HostRead() const { return d; }
+  double &operator[](int i) { return d[i]; }
+  const double &operator[](int i) const { return d[i]; }
 };
 template <typename T>
 class Array
@@ -49,7 +60,117 @@ public:
   }
   int Size() const { return n; }
   const T *HostRead() const { return d; }
+  const T &operator[](int i) const { return d[i]; }
+  void Assign(const std::vector<T> &v)
+  {
+    delete[] d;
+    n = (int)v.size();
+    d = n ? new T[n] : nullptr;
+    for (int i = 0; i < n; i++) d[i] = v[i];
+  }
 };
+// ---- the MFEM objects the integrator glue of b2p_palace.hpp reads (fem/libceed/basis.cpp:15-85, restriction.cpp:113-297,
+// fem/mesh.cpp:146-209). The mock holds plain arrays that the test driver fills; the member functions have MFEM's
+// signatures and conventions (column-major DofToQuad tables, -1-d encoding of flipped dofs, byNODES vdofs). ----
+struct IntegrationPoint
+{
+  double x = 0.0, weight = 0.0;
+};
+class IntegrationRule
+{
+public:
+  std::vector<IntegrationPoint> pts;
+  int GetNPoints() const { return (int)pts.size(); }
+  const IntegrationPoint &IntPoint(int i) const { return pts[i]; }
+};
+struct DofToQuad
+{
+  enum Mode
+  {
+    FULL,
+    TENSOR
+  };
+  int ndof = 0, nqpt = 0;
+  std::vector<double> B, G;  // B[q + nqpt * d]
+};
+class FiniteElement
+{
+protected:
+  int order;
+
+public:
+  explicit FiniteElement(int p) : order(p) {}
+  virtual ~FiniteElement() = default;
+  int GetOrder() const { return order; }
+};
+class TensorBasisElement
+{
+public:
+  Array<int> dof_map;  // lexicographic -> native (-1 - native for a sign flip)
+  virtual ~TensorBasisElement() = default;
+  const Array<int> &GetDofMap() const { return dof_map; }
+};
+// H1 hexahedron (nodal tensor element): one 1-D basis
+class NodalTensorFiniteElement : public FiniteElement, public TensorBasisElement
+{
+public:
+  DofToQuad maps;
+  explicit NodalTensorFiniteElement(int p) : FiniteElement(p) {}
+  const DofToQuad &GetDofToQuad(const IntegrationRule &, DofToQuad::Mode) const { return maps; }
+};
+// ND hexahedron: closed and open 1-D bases
+class VectorTensorFiniteElement : public FiniteElement, public TensorBasisElement
+{
+public:
+  DofToQuad closed_maps, open_maps;
+  explicit VectorTensorFiniteElement(int p) : FiniteElement(p) {}
+  const DofToQuad &GetDofToQuad(const IntegrationRule &, DofToQuad::Mode) const { return closed_maps; }
+  const DofToQuad &GetDofToQuadOpen(const IntegrationRule &, DofToQuad::Mode) const { return open_maps; }
+};
+class FiniteElementSpace
+{
+public:
+  const FiniteElement *fe = nullptr;
+  int ne = 0, vsize = 0, vdim = 1;
+  std::vector<std::vector<int>> elem_dofs;  // scalar dofs, -1 - d for a flipped one
+  int GetNE() const { return ne; }
+  int GetVSize() const { return vsize; }
+  int GetVDim() const { return vdim; }
+  const FiniteElement *GetFE(int) const { return fe; }
+  void GetElementDofs(int e, Array<int> &dofs) const { dofs.Assign(elem_dofs[e]); }
+  void GetElementVDofs(int e, Array<int> &vdofs) const  // Ordering::byNODES
+  {
+    std::vector<int> v;
+    const int nd = vsize / vdim;
+    for (int c = 0; c < vdim; c++)
+      for (int d : elem_dofs[e]) v.push_back(d + c * nd);
+    vdofs.Assign(v);
+  }
+};
+class GridFunction : public Vector
+{
+  const FiniteElementSpace *fes;
+
+public:
+  GridFunction(const FiniteElementSpace *f, int n) : Vector(n), fes(f) {}
+  const FiniteElementSpace *FESpace() const { return fes; }
+  void GetSubVector(const Array<int> &dofs, Vector &out) const
+  {
+    out.SetSize(dofs.Size());
+    for (int i = 0; i < dofs.Size(); i++) out.HostWrite()[i] = Read()[dofs[i]];
+  }
+};
+class Mesh
+{
+public:
+  int ne = 0;
+  std::vector<int> attributes;
+  const GridFunction *nodes = nullptr;
+  int GetNE() const { return ne; }
+  int GetAttribute(int e) const { return attributes[e]; }
+  const GridFunction *GetNodes() const { return nodes; }
+};
+
 class Operator
 {
 protected:

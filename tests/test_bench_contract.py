@@ -37,3 +37,19 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["unit"] == "MDoF/s" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_experiment_lines_precede_the_headline_line():
+    """Every side measurement is its own short JSON line {"experiment": ...} and the headline is the LAST line, so that no
+    experiment can fall off a log tail and no headline key can be pushed out by them (VERDICT r01, weak #9)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dryrun.py")], capture_output=True, text=True, timeout=1500,
+                       env=dict(os.environ, B2P_BENCH_EXPERIMENTS="1", B2P_BENCH_EXPERIMENT_BUDGET_S="600"), cwd=ROOT)
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) >= 4, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "metric" in lines[-1] and "experiment" not in lines[-1] and "experiments" not in lines[-1]
+    names = [ln["experiment"] for ln in lines[:-1]]
+    assert all("experiment" in ln for ln in lines[:-1])
+    assert "matrix_coefficient_warped_mesh" in names and "round1_kernel_nd_hex_apply4" in names
+    ok = [ln for ln in lines[:-1] if ln["experiment"] == "matrix_coefficient_warped_mesh"][0]
+    assert "failed" not in ok and ok["kernel"] == "nd_hex_apply6_kernel", ok
+    assert max(len(json.dumps(ln)) for ln in lines) < 4000

@@ -360,6 +360,41 @@ def test_multigrid_with_the_coarse_level_assembled_on_the_device(b2p_ctx, capi_m
     assert _rel(xd.cpu().numpy(), spla.spsolve(Ao.tocsc(), b)) < 1e-8
 
 
+def test_ksp_composer_builds_the_reference_configuration(b2p_ctx, capi_mod, hier):
+    """BaseKspSolver (linalg/ksp.cpp:29-239,256-328): one configuration record -> FGMRES + p-multigrid (Chebyshev order
+    max(2p, 4) + Hiptmair smoothing, coarse level assembled on the device) -- the same solve as the hand-composed objects, and
+    the reference's counters NumTotalMult / NumTotalMultIts across two solves."""
+    orders = hier["orders"]
+    P = [hier["P"][(a, b)] for a, b in zip(orders[:-1], orders[1:])]
+    G = [hier["G"][p] for p in orders]
+    ksp = capi_mod.Ksp(b2p_ctx, order=3, P=P, G=G, krylov_solver=2, tol=1e-10, max_it=60, coarse_tol=1e-12, coarse_max_it=2000)
+    assert ksp.cfg.mg_smooth_order == 6 and ksp.cfg.mg_smooth_aux == 1 and ksp.cfg.mg_cycle_it == 1  # iodata.cpp:519-536
+    ksp.set_operators(hier["A"][3], [hier["A"][p] for p in orders], [hier["AG"][p] for p in orders])
+    Ao = hier["Aor"][3]
+    n = Ao.shape[0]
+    sol = spla.splu(Ao.tocsc())
+    its = 0
+    for seed in (11, 12):
+        b = np.random.default_rng(seed).standard_normal(n)
+        b[hier["nd"][3].ess_dofs] = 0.0
+        xd = torch.zeros(n, dtype=torch.float64, device="cuda")
+        ksp.mult(_dev(b), xd)
+        st = ksp.stats()
+        assert st["converged"] and st["its"] <= 25, st
+        its += st["its"]
+        assert _rel(xd.cpu().numpy(), sol.solve(b)) < 1e-8
+    assert st["num_total_mult"] == 2 and st["num_total_mult_its"] == its
+    # one level: the coarse solver alone preconditions (ksp.cpp:232-237); Jacobi-PCG through the same record
+    k1 = capi_mod.Ksp(b2p_ctx, order=1, krylov_solver=0, tol=1e-10, max_it=2000, coarse_type=0)
+    k1.set_operators(hier["A"][1], [hier["A"][1]])
+    A1 = hier["Aor"][1]
+    b = np.random.default_rng(13).standard_normal(A1.shape[0])
+    b[hier["nd"][1].ess_dofs] = 0.0
+    xd = torch.zeros(A1.shape[0], dtype=torch.float64, device="cuda")
+    k1.mult(_dev(b), xd)
+    assert k1.stats()["converged"] and _rel(xd.cpu().numpy(), spla.spsolve(A1.tocsc(), b)) < 1e-7
+
+
 def test_multi_gpu_partition_independence():
     """Runs tools/dist_check.py under torchrun on 2 GPUs when the box has them (gpurun --gpus 2)."""
     import os

@@ -62,6 +62,27 @@ def test_tet_apply_matches_oracle(b2p_ctx, p, kind):
     assert _rel(yd.cpu().numpy(), 0.75 * y_ref) < RTOL
 
 
+@pytest.mark.parametrize("p,kind", [(1, O.CURLCURL_MASS), (2, O.CURLCURL), (3, O.ND_MASS), (3, O.CURLCURL_MASS), (6, O.CURLCURL_MASS)])
+def test_fused_chunked_dense_kernel_matches_oracle_and_the_round1_kernel(b2p_ctx, p, kind):
+    """dense_apply2_kernel (32 elements per CTA, the two GEMMs fused over chunks of 32 points, output tiles in registers)
+    takes every batch of >= 32 elements: 54 tets = one full CTA + a ragged one of 22, rules of 4 ... 343 points (ragged
+    last chunk), 1 ... 27 dof tiles (one to four per warp), all three kinds (3 or 6 row blocks per chunk)."""
+    mesh, sp, interp, curl, qd = _problem(p, (3, 3, 1))       # 54 tets
+    blob = _blob(kind, 3)
+    op = _op(b2p_ctx, kind, sp, interp, curl, qd, blob)
+    x = np.random.default_rng(7).random(sp.ndofs)
+    y_ref = O.apply_add_co(kind, interp, curl, sp.idx, sp.curl_orient, qd, blob, x, np.zeros(sp.ndofs))
+    yd = torch.full((sp.ndofs,), -3.0, dtype=torch.float64, device="cuda")
+    op.apply(_dev(x), yd)
+    assert _rel(yd.cpu().numpy(), y_ref) < RTOL
+    # the same operator through the element range API in pieces of < 32 elements runs the round-1 kernel
+    n_owned = sp.ndofs
+    y2 = torch.zeros(sp.ndofs, dtype=torch.float64, device="cuda")
+    for e0 in range(0, mesh.ne, 18):
+        op.apply_add_split(1.0, _dev(x), None, y2, None, n_owned, e0, min(18, mesh.ne - e0))
+    assert _rel(y2.cpu().numpy(), y_ref) < RTOL
+
+
 def test_tet_p1_sign_orientation_equals_curl_orientation(b2p_ctx):
     mesh, sp, interp, curl, qd = _problem(1, (2, 1, 1))       # 12 tets: ragged last batch
     kind, blob = O.CURLCURL_MASS, _blob(O.CURLCURL_MASS, 3)
