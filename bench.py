@@ -233,7 +233,8 @@ def workload_config(args, prob, world):
                       "fused into one kernel before and one after the element kernel, replayed from a CUDA graph)"
                       if os.environ.get("B2P_HALO_P2P", "1") == "1" else
                       "1 block per GPU; shared dofs exchanged by NCCL grouped send/recv") if world > 1 else "single partition",
-        "vector": "true-dof (T) vector", "l2_policy": "L2 flushed (256 MiB write) between timed iterations",
+        "vector": "true-dof (T) vector",
+        "l2_policy": "L2 flushed (256 MiB write" + (", then read back" if os.environ.get("B2P_BENCH_FLUSH", "write") == "write_read" else "") + ") between timed iterations",
     }
 
 
@@ -249,6 +250,7 @@ def run_experiments(args):
         "matrix_coefficient_warped_mesh": (["--coefficient", "matrix4", "--warp", "0.05"], {}),
         "round1_kernel_nd_hex_apply4": ([], {"B2P_ND_KERNEL": "4"}),
         "without_pdl_zero_fill_overlap": ([], {"B2P_PDL": "0"}),
+        "l2_flush_written_then_read_back": ([], {"B2P_BENCH_FLUSH": "write_read"}),
     }
     # (2) prepared tool measurements (tools/): one JSON line each
     tools = {
@@ -372,6 +374,14 @@ def main():
 
     qbytes = prob["local_ne"] * 10 * q1d ** 3 * 8
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2
+    # B2P_BENCH_FLUSH=write_read (side experiment only): read the buffer back after writing it, so the 126 MB the flush
+    # leaves in L2 are CLEAN lines -- a plain write leaves them dirty and the timed kernels pay their write-back.
+    flush_read = os.environ.get("B2P_BENCH_FLUSH", "write") == "write_read"
+
+    def do_flush():
+        flush.zero_()
+        if flush_read:
+            torch.sum(flush)
 
     def step_device():
         A.mult(xd, yd)  # ParOperator::Mult: P (halo), zero-fill, local apply, P^T (halo)
@@ -397,7 +407,7 @@ def main():
     barrier()
     for a, b in evs:
         if flush is not None:
-            flush.zero_()
+            do_flush()
         a.record(stream)
         step_device()
         b.record(stream)
@@ -417,7 +427,7 @@ def main():
     for a, b in kev:
         yl.zero_()
         if flush is not None:
-            flush.zero_()
+            do_flush()
         a.record(stream)
         op.apply_add(xl, yl)  # the local element kernel alone, all elements of this rank
         b.record(stream)

@@ -3,8 +3,8 @@
 dense-basis curl-curl+mass operator on a slab-partitioned box of tets, n^3 * 6 tets per GPU, shared dofs exchanged through
 the peer-memory halo. One JSON line on rank 0: MDoF/s over all GPUs, TFLOP/s of the two element GEMMs, time per Mult
 (max over ranks, CUDA events, L2 flushed between steps).
-  python tools/tet_scale_bench.py --order 3 --n 21                                   (1 GPU)
-  torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/tet_scale_bench.py --order 6 --n 11"""
+  python tools/tet_scale_bench.py --order 3 --cells 21                                  (1 GPU)
+  torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/tet_scale_bench.py --order 6 --cells 11"""
 import argparse
 import json
 import os
@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--order", type=int, default=3)
-    ap.add_argument("--n", type=int, default=21, help="cells per direction per GPU (6 n^3 tets per GPU)")
+    ap.add_argument("--cells", dest="n", type=int, default=21, help="cells per direction per GPU (6 n^3 tets per GPU); (not --n: torchrun claims that prefix)")
     ap.add_argument("--geom-order", type=int, default=1, help="2: curved (quadratic) tets, as the spheres example")
     ap.add_argument("--warp", type=float, default=0.0)
     ap.add_argument("--steps", type=int, default=20)
