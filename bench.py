@@ -532,8 +532,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N_global * 8), "d2h_bytes_per_step": int(N_global * 8),
                     "mode": e2e_mode, "serial_value": e2e_serial},
-            # per rank and step: the apply kernel (+ halo pack and unpack kernels when N > 1); memset/NCCL not counted
-            "gpu_launches": int(args.steps * (1 + (2 if world > 1 else 0))),
+            # kernels of this library per rank and timed step: N = 1: zero_release_kernel + the element kernel (the zero-fill is a
+            # cudaMemset, not a kernel of ours, with B2P_PDL=0); N > 1: p2p_pre_kernel + element kernel + p2p_post_kernel
+            "gpu_launches": int(args.steps * (3 if world > 1 else (1 if os.environ.get("B2P_PDL", "1") == "0" else 2))),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(abytes)},

@@ -671,6 +671,7 @@ void orc_apply_add_mt(int nthreads, int kind, int ne, int P, int Q, const double
 namespace
 {
 constexpr int BLK = 8;
+typedef double vblk __attribute__((vector_size(BLK * sizeof(double)), aligned(8)));  // one element lane per SIMD lane
 
 struct OrcPool
 {
@@ -850,61 +851,48 @@ void orc_apply_add_blocked(void *pool, void *setup, int kind, int ne, int P, int
                 const double sg = orient ? (double)orient[(size_t)e * P + i] : 1.0;
                 ue[(size_t)i * BLK + l] = l < nel ? sg * x[idx[(size_t)e * P + i]] : 0.0;
               }
-            // u = interp ue, c = deriv ue: four rows of the dense tables at a time against BLK element lanes (eight
-            // independent SIMD accumulators cover the FMA latency; every ue vector is loaded once per four rows)
+            // u = interp ue, c = deriv ue: four rows of the dense tables at a time against the BLK element lanes held as ONE
+            // SIMD vector (GCC vector extension: eight independent register accumulators cover the FMA latency; every ue
+            // vector is loaded once per four rows)
             for (int r0 = 0; r0 < R; r0 += 4)
             {
               const int nr = std::min(4, R - r0);
-              double au[4][BLK] = {{0}}, ac[4][BLK] = {{0}};
+              vblk au[4], ac[4];
+              for (int k = 0; k < 4; k++) au[k] = ac[k] = vblk{};
               const double *ri[4], *rd[4];
               for (int k = 0; k < 4; k++)
               {
                 ri[k] = interp + (size_t)(r0 + std::min(k, nr - 1)) * P;
                 rd[k] = deriv + (size_t)(r0 + std::min(k, nr - 1)) * P;
               }
+              const vblk *uev = reinterpret_cast<const vblk *>(ue.data());
               if (need_u && need_c)
                 for (int i = 0; i < P; i++)
                 {
-                  const double *__restrict ul = &ue[(size_t)i * BLK];
+                  const vblk ul = uev[i];
                   for (int k = 0; k < 4; k++)
                   {
-                    const double a = ri[k][i], d = rd[k][i];
-#pragma GCC ivdep
-                    for (int l = 0; l < BLK; l++)
-                    {
-                      au[k][l] += a * ul[l];
-                      ac[k][l] += d * ul[l];
-                    }
+                    au[k] += ri[k][i] * ul;
+                    ac[k] += rd[k][i] * ul;
                   }
                 }
               else if (need_u)
                 for (int i = 0; i < P; i++)
                 {
-                  const double *__restrict ul = &ue[(size_t)i * BLK];
-                  for (int k = 0; k < 4; k++)
-                  {
-                    const double a = ri[k][i];
-#pragma GCC ivdep
-                    for (int l = 0; l < BLK; l++) au[k][l] += a * ul[l];
-                  }
+                  const vblk ul = uev[i];
+                  for (int k = 0; k < 4; k++) au[k] += ri[k][i] * ul;
                 }
               else
                 for (int i = 0; i < P; i++)
                 {
-                  const double *__restrict ul = &ue[(size_t)i * BLK];
-                  for (int k = 0; k < 4; k++)
-                  {
-                    const double d = rd[k][i];
-#pragma GCC ivdep
-                    for (int l = 0; l < BLK; l++) ac[k][l] += d * ul[l];
-                  }
+                  const vblk ul = uev[i];
+                  for (int k = 0; k < 4; k++) ac[k] += rd[k][i] * ul;
                 }
               for (int k = 0; k < nr; k++)
-                for (int l = 0; l < BLK; l++)
-                {
-                  uq[(size_t)(r0 + k) * BLK + l] = au[k][l];
-                  cq[(size_t)(r0 + k) * BLK + l] = ac[k][l];
-                }
+              {
+                *reinterpret_cast<vblk *>(&uq[(size_t)(r0 + k) * BLK]) = au[k];
+                *reinterpret_cast<vblk *>(&cq[(size_t)(r0 + k) * BLK]) = ac[k];
+              }
             }
             // pointwise D, element by element (the reference's QFunction arithmetic)
             for (int l = 0; l < nel; l++)
@@ -923,25 +911,31 @@ void orc_apply_add_blocked(void *pool, void *setup, int kind, int ne, int P, int
             }
             for (int l = nel; l < BLK; l++)
               for (int r = 0; r < R; r++) vq[(size_t)r * BLK + l] = wq[(size_t)r * BLK + l] = 0.0;
-            // ye = interp^T v + deriv^T w: four output dofs at a time held in registers across the whole row loop
-            for (int i0 = 0; i0 < P; i0 += 4)
+            // ye = interp^T v + deriv^T w: eight output dofs at a time held in registers across the whole row loop
             {
-              const int ni = std::min(4, P - i0);
-              double acc[4][BLK] = {{0}};
-              for (int r = 0; r < R; r++)
+              const vblk *vv = reinterpret_cast<const vblk *>(vq.data()), *wv = reinterpret_cast<const vblk *>(wq.data());
+              for (int i0 = 0; i0 < P; i0 += 8)
               {
-                const double *ri = interp + (size_t)r * P + i0, *rd = deriv + (size_t)r * P + i0;
-                const double *__restrict vl = &vq[(size_t)r * BLK], *__restrict wl = &wq[(size_t)r * BLK];
-                for (int k = 0; k < 4; k++)
+                const int ni = std::min(8, P - i0);
+                vblk acc[8];
+                for (int k = 0; k < 8; k++) acc[k] = vblk{};
+                for (int r = 0; r < R; r++)
                 {
-                  const int kk = std::min(k, ni - 1);
-                  const double a = need_u ? ri[kk] : 0.0, d = need_c ? rd[kk] : 0.0;
-#pragma GCC ivdep
-                  for (int l = 0; l < BLK; l++) acc[k][l] += a * vl[l] + d * wl[l];
+                  const double *ri = interp + (size_t)r * P + i0, *rd = deriv + (size_t)r * P + i0;
+                  const vblk vl = vv[r], wl = wv[r];
+                  if (need_u && need_c)
+                    for (int k = 0; k < 8; k++)
+                    {
+                      const int kk = std::min(k, ni - 1);
+                      acc[k] += ri[kk] * vl + rd[kk] * wl;
+                    }
+                  else if (need_u)
+                    for (int k = 0; k < 8; k++) acc[k] += ri[std::min(k, ni - 1)] * vl;
+                  else
+                    for (int k = 0; k < 8; k++) acc[k] += rd[std::min(k, ni - 1)] * wl;
                 }
+                for (int k = 0; k < ni; k++) *reinterpret_cast<vblk *>(&ye[(size_t)(i0 + k) * BLK]) = acc[k];
               }
-              for (int k = 0; k < ni; k++)
-                for (int l = 0; l < BLK; l++) ye[(size_t)(i0 + k) * BLK + l] = acc[k][l];
             }
             for (int l = 0; l < nel; l++)
               for (int i = 0; i < P; i++)

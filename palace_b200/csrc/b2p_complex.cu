@@ -10,7 +10,9 @@
 //                          (/root/reference/palace/linalg/iterative.cpp:361-871, complex Givens :112-226)
 // Inner product convention: Dot(x, y) = y^H x (vector.cpp:674-685); Gram-Schmidt calls dot(w, V_j) (orthog.hpp:48-49).
 #include <complex>
+#include <limits>
 
+#include "b2p_givens.hpp"
 #include "b2p_linalg.hpp"
 
 namespace b2p
@@ -852,25 +854,6 @@ public:
 
 namespace
 {
-// iterative.cpp:112-226, well-scaled branches
-inline void GeneratePlaneRotation(const cplx dx, const cplx dy, double &cs, cplx &sn)
-{
-  if (dy == 0.0)
-  {
-    cs = 1.0;
-    sn = 0.0;
-    return;
-  }
-  if (dx == 0.0)
-  {
-    cs = 0.0;
-    sn = std::conj(dy) / std::abs(dy);
-    return;
-  }
-  const double dx2 = std::norm(dx), dy2 = std::norm(dy), dz2 = dx2 + dy2;
-  cs = std::sqrt(dx2 / dz2);
-  sn = std::conj(dy) * (dx / std::sqrt(dx2 * dz2));
-}
 inline void ApplyPlaneRotation(cplx &dx, cplx &dy, const double cs, const cplx sn)
 {
   const cplx t = cs * dx + sn * dy;

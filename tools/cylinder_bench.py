@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--refine", type=int, default=0)
     ap.add_argument("--nev", type=int, default=4)
     ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--coarse-tol", type=float, default=1e-10, help="relative tolerance of the coarse-level PCG (the reference's coarse solve is one AMS V-cycle)")
     ap.add_argument("--cheby-order", type=int, default=0, help="Chebyshev smoother order; 0 = the reference's default max(2p, 4) (iodata.cpp:533-536)")
     args = ap.parse_args()
     import torch
@@ -83,7 +84,7 @@ def main():
         AG[q] = common.gpu_par_operator(ctx, geom, prob, O.H1_DIFFUSION, cf.coeff_ctx(a=sigma), space=h1[q], fine_op=AG[p].local_op)
     G = [common.gpu_interp(ctx, h1[q], nd[q], asm.gradient_comps(q)) for q in orders]
     P = [common.gpu_interp(ctx, nd[a], nd[b], asm.nd_prolongation_comps(a, b)) for a, b in zip(orders[:-1], orders[1:])]
-    coarse = capi.Solver.krylov(ctx, capi.CG, rel_tol=1e-10, max_it=5000)
+    coarse = capi.Solver.krylov(ctx, capi.CG, rel_tol=args.coarse_tol, max_it=5000)
     cj = capi.Solver.jacobi(ctx)
     coarse.set_check_interval(int(os.environ.get("B2P_COARSE_CG_CHECK", "8")))  # device-resident CG scalars
     if os.environ.get("B2P_COARSE_ASSEMBLED", "0") == "1":  # PCG on the device-assembled p = 1 matrix (MfemWrapperSolver flow)
@@ -132,6 +133,15 @@ def main():
         level_ms[f"P_p{a}_p{b}"] = timeit(lambda: Pab.mult(va, vb))
     xd.copy_(torch.rand(n, dtype=torch.float64))
     vcycle_ms = timeit(lambda: mg.mult(xd, yd), reps=5)
+    q0 = orders[0]
+    c_in = torch.rand(nd[q0].ndofs, dtype=torch.float64, device="cuda")
+    c_in[torch.from_numpy(np.asarray(nd[q0].ess_dofs, dtype=np.int64)).cuda()] = 0.0
+    c_out = torch.zeros_like(c_in)
+    try:
+        level_ms["coarse_solve"] = timeit(lambda: coarse.mult(c_in, c_out), reps=3)
+        level_ms["coarse_solve_its"] = coarse.stats()["its"]
+    except Exception:
+        pass  # (the assembled coarse solver is owned by the multigrid once handed over)
     its, t_solve = [], [0.0]
 
     def to_full(v):
@@ -162,7 +172,8 @@ def main():
     t_eig = time.time() - t0
     f = frequencies_ghz(np.sort(lam)).real
     out = {"workload": f"cylinder cavity eigenmodes, ND order {p}, {m.ne} HEX27 elements (refine {args.refine})", "dofs": int(n),
-           "levels": orders, "cheby_order": cheby_order, "level_dofs": {f"nd_p{q}": int(nd[q].ndofs) for q in orders},
+           "levels": orders, "cheby_order": cheby_order, "coarse_tol": args.coarse_tol,
+           "coarse_level": "Jacobi-PCG on the device-assembled p=1 matrix" if os.environ.get("B2P_COARSE_ASSEMBLED", "0") == "1" else "Jacobi-PCG, matrix-free p=1 operator", "level_dofs": {f"nd_p{q}": int(nd[q].ndofs) for q in orders},
            "piece_ms": level_ms, "host_build_s": t_host, "device_setup_s": t_setup, "apply_ms": apply_ms, "apply_MDoF_s": n / apply_ms / 1e3,
            "vcycle_ms": vcycle_ms, "eigensolve_s": t_eig, "linear_solves": len(its), "fgmres_its_per_solve": float(np.mean(its)),
            "time_in_linear_solves_s": t_solve[0], "f_ghz": f.tolist(), "analytic_ghz": analytic_ghz(args.nev).tolist()}
