@@ -443,6 +443,20 @@ int b2p_csolver_mult(b2p_csolver *s, const double *br, const double *bi, double 
 int b2p_csolver_stats(b2p_csolver *s, int *its, double *initial_res, double *final_res, int *converged);
 void b2p_csolver_destroy(b2p_csolver *s);
 
+/* ---- outer eigen-solver interface: the operator applications of ArpackEPSSolver (linalg/arpack.cpp:631-674) --------
+ * ARPACK's reverse communication (and SLEPc's shell matrices, slepc.cpp) run on the HOST and hand over host pointers to
+ * interleaved complex vectors; the vectors of the applications live on the device. One handle keeps the device work
+ * vectors and pinned staging:   apply_op   : y = (1/gamma) opInv (K x)            without spectral transformation
+ *                                            y = gamma opInv (M x)                shift-and-invert (opInv = (K - sigma M)^-1)
+ *                               apply_op_b : y = delta B x                        weighted inner product
+ * K may be NULL with sinvert, B may be NULL (apply_op_b then fails). x, y: n std::complex<double> on the host. */
+typedef struct b2p_eps b2p_eps;
+int b2p_eps_create(b2p_ctx *ctx, int64_t n, b2p_coperator *K, b2p_coperator *M, b2p_csolver *opInv, b2p_coperator *B, int sinvert,
+                   double gamma, double delta, b2p_eps **out);
+int b2p_eps_apply_op(b2p_eps *e, const double *x_host_interleaved, double *y_host_interleaved);
+int b2p_eps_apply_op_b(b2p_eps *e, const double *x_host_interleaved, double *y_host_interleaved);
+void b2p_eps_destroy(b2p_eps *e);
+
 #ifdef __cplusplus
 }
 #endif

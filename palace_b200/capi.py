@@ -860,3 +860,38 @@ class Ksp:
                 self.h = None
         except Exception:
             pass
+
+
+class Eps:
+    """The operator applications an outer eigen-solver asks for (ArpackEPSSolver::ApplyOp / ApplyOpB, linalg/arpack.cpp:631-674):
+    host complex vectors in, host complex vectors out; operators, linear solve and work vectors stay on the device."""
+
+    def __init__(self, ctx, n, K, M, op_inv, B=None, sinvert=True, gamma=1.0, delta=1.0):
+        self.ctx, self.n = ctx, int(n)
+        self.h = C.c_void_p()
+        _chk(lib().b2p_eps_create(ctx.h, C.c_int64(self.n), K.h if K is not None else None, M.h if M is not None else None, op_inv.h,
+                                  B.h if B is not None else None, int(bool(sinvert)), C.c_double(gamma), C.c_double(delta),
+                                  C.byref(self.h)), ctx.h)
+        self._keep = [K, M, op_inv, B]
+
+    def _run(self, fn, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        assert x.size == self.n
+        y = np.empty(self.n, dtype=np.complex128)
+        _chk(fn(self.h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)), self.ctx.h)
+        return y
+
+    def apply_op(self, x):
+        return self._run(lib().b2p_eps_apply_op, x)
+
+    def apply_op_b(self, x):
+        return self._run(lib().b2p_eps_apply_op_b, x)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b2p_eps_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+

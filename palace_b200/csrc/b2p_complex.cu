@@ -10,6 +10,7 @@
 //                          (/root/reference/palace/linalg/iterative.cpp:361-871, complex Givens :112-226)
 // Inner product convention: Dot(x, y) = y^H x (vector.cpp:674-685); Gram-Schmidt calls dot(w, V_j) (orthog.hpp:48-49).
 #include <complex>
+#include <cstring>
 #include <limits>
 
 #include "b2p_givens.hpp"
@@ -1398,5 +1399,119 @@ int b2p_csolver_stats(b2p_csolver *s, int *its, double *initial_res, double *fin
   return B2P_SUCCESS;
 }
 void b2p_csolver_destroy(b2p_csolver *s) { delete s; }
+
+}  // extern "C"
+
+// ---- outer eigen-solver interface (ArpackEPSSolver::ApplyOp / ApplyOpB, arpack.cpp:631-674) ----
+namespace
+{
+// interleaved complex (the host layout, staged in z[2n]) <-> split real / imaginary device vectors
+__global__ void csplit_kernel(const double *__restrict__ z, double *__restrict__ re, double *__restrict__ im, int64_t n)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    re[i] = z[2 * i];
+    im[i] = z[2 * i + 1];
+  }
+}
+__global__ void cjoin_scaled_kernel(const double *__restrict__ re, const double *__restrict__ im, double s, double *__restrict__ z, int64_t n)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    z[2 * i] = s * re[i];
+    z[2 * i + 1] = s * im[i];
+  }
+}
+}  // namespace
+
+struct b2p_eps
+{
+  b2p_ctx *ctx = nullptr;
+  int64_t n = 0;
+  const ComplexOperator *K = nullptr, *M = nullptr, *B = nullptr;
+  const ComplexSolver *opInv = nullptr;
+  bool sinvert = true;
+  double gamma = 1.0, delta = 1.0;
+  DVec xr, xi, zr, zi, yr, yi, stage;  // x1, z1, y1 of the reference + the interleaved staging vector
+  double *h_pin = nullptr;             // pinned host staging [2n]
+};
+
+namespace
+{
+int eps_run(b2p_eps *e, const double *px, double *py, bool op_b)
+{
+  b2p_ctx *ctx = e->ctx;
+  cudaStream_t s = ctx->stream;
+  const int64_t n = e->n;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+  std::memcpy(e->h_pin, px, sizeof(double) * 2 * n);  // x1.Set(px, n): the caller's buffer need not be pinned
+  B2P_CUDA(ctx, cudaMemcpyAsync(e->stage.p, e->h_pin, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s));
+  B2P_LAUNCH(csplit_kernel, grid, 256, 0, s, (const double *)e->stage.p, e->xr.p, e->xi.p, n);
+  double scale;
+  if (op_b)
+  {
+    B2P_CTRY(ctx, e->B->Mult(CCPtr{e->xr.p, e->xi.p}, CPtr{e->yr.p, e->yi.p}));
+    scale = e->delta;
+  }
+  else
+  {
+    const ComplexOperator *first = e->sinvert ? e->M : e->K;  // y = gamma opInv (M x)  |  y = opInv (K x) / gamma
+    B2P_CTRY(ctx, first->Mult(CCPtr{e->xr.p, e->xi.p}, CPtr{e->zr.p, e->zi.p}));
+    B2P_CTRY(ctx, e->opInv->Mult(CCPtr{e->zr.p, e->zi.p}, CPtr{e->yr.p, e->yi.p}));
+    scale = e->sinvert ? e->gamma : 1.0 / e->gamma;
+  }
+  B2P_LAUNCH(cjoin_scaled_kernel, grid, 256, 0, s, (const double *)e->yr.p, (const double *)e->yi.p, scale, e->stage.p, n);
+  B2P_CUDA(ctx, cudaMemcpyAsync(e->h_pin, e->stage.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, s));
+  B2P_CUDA(ctx, cudaStreamSynchronize(s));
+  std::memcpy(py, e->h_pin, sizeof(double) * 2 * n);  // y1.Get(py, n)
+  return B2P_SUCCESS;
+}
+}  // namespace
+
+extern "C"
+{
+
+int b2p_eps_create(b2p_ctx *ctx, int64_t n, b2p_coperator *K, b2p_coperator *M, b2p_csolver *opInv, b2p_coperator *B, int sinvert,
+                   double gamma, double delta, b2p_eps **out)
+{
+  B2P_CHECK(ctx, ctx && out && n > 0 && opInv && opInv->s, B2P_ERR_ARG, "b2p_eps_create: bad argument");
+  B2P_CHECK(ctx, sinvert ? (M && M->op) : (K && K->op), B2P_ERR_ARG,
+            "b2p_eps_create: shift-and-invert applies M first, the untransformed problem K");
+  B2P_CHECK(ctx, gamma != 0.0, B2P_ERR_ARG, "b2p_eps_create: gamma = 0");
+  auto e = std::make_unique<b2p_eps>();
+  e->ctx = ctx;
+  e->n = n;
+  e->K = K ? K->op.get() : nullptr;
+  e->M = M ? M->op.get() : nullptr;
+  e->B = B ? B->op.get() : nullptr;
+  e->opInv = opInv->s.get();
+  e->sinvert = sinvert != 0;
+  e->gamma = gamma;
+  e->delta = delta;
+  for (DVec *v : {&e->xr, &e->xi, &e->zr, &e->zi, &e->yr, &e->yi}) v->resize(ctx, n);
+  e->stage.resize(ctx, 2 * n);
+  B2P_CUDA(ctx, cudaMallocHost((void **)&e->h_pin, sizeof(double) * 2 * n));
+  *out = e.release();
+  return B2P_SUCCESS;
+}
+int b2p_eps_apply_op(b2p_eps *e, const double *x, double *y)
+{
+  if (!e || !x || !y) return B2P_ERR_ARG;
+  return eps_run(e, x, y, false);
+}
+int b2p_eps_apply_op_b(b2p_eps *e, const double *x, double *y)
+{
+  if (!e || !x || !y) return B2P_ERR_ARG;
+  B2P_CHECK(e->ctx, e->B, B2P_ERR_ARG, "No B operator for weighted inner product in the eigen-solver interface!");
+  return eps_run(e, x, y, true);
+}
+void b2p_eps_destroy(b2p_eps *e)
+{
+  if (!e) return;
+  cudaFreeHost(e->h_pin);
+  delete e;
+}
 
 }  // extern "C"

@@ -246,9 +246,12 @@ __global__ void __launch_bounds__(256) dense_apply2_kernel(DenseParams prm)
   };
 
   // ---- restriction (E): native order, sign or tridiagonal orientation ----
+  // (dof index fastest across threads: the index rows and the int8 orientation rows are read coalesced -- element-fastest
+  // threads touched one 32-byte sector per 4-byte index, 8x the restriction's bytes; the shared-memory stores take the
+  // bank conflicts instead)
   for (int w = tid; w < Ppad * NEB; w += blockDim.x)
   {
-    const int i = w / NEB, e = w % NEB;
+    const int e = w / Ppad, i = w % Ppad;
     double v = 0.0;
     if (i < P && e0 + e < prm.ne)
     {
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(256) dense_apply2_kernel(DenseParams prm)
     __syncthreads();
     for (int w = tid; w < Ppad * NEB; w += blockDim.x)
     {
-      const int i = w / NEB, e = w % NEB;
+      const int e = w / Ppad, i = w % Ppad;
       double v = 0.0;
       if (i < P && e0 + e < prm.ne)
       {
@@ -326,9 +329,13 @@ __global__ void __launch_bounds__(256) dense_apply2_kernel(DenseParams prm)
     __syncthreads();
 
     // ---- D at the chunk's quadrature points (in place); points beyond Q and elements beyond ne become zero rows ----
+    // item -> (point, element): a warp covers 4 consecutive points x 8 elements, so every 32-byte sector of the q-data is
+    // used whole (element-fastest threads fetched a sector per 8-byte value: 4x the geometry stream, the largest HBM term)
+    // and the shared-memory accesses are at most 2-way conflicted
     for (int w = tid; w < QC * NEB; w += blockDim.x)
     {
-      const int j = w / NEB, e = w % NEB, iq = q0 + j;
+      const int rest = w >> 5;
+      const int j = (rest % (QC / 4)) * 4 + (w & 3), e = (rest / (QC / 4)) * 8 + ((w >> 2) & 7), iq = q0 + j;
       const bool ok = iq < Q && e0 + e < prm.ne;
       const double *g = prm.qd + (size_t)(e0 + (ok ? e : 0)) * 10 * Q + (ok ? iq : 0);
       const double *C = prm.ecoef + (size_t)(e0 + (ok ? e : 0)) * 18;
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(256) dense_apply2_kernel(DenseParams prm)
   {
     for (int w = tid; w < Ppad * NEB; w += blockDim.x)
     {
-      const int i = w / NEB, e = w % NEB;
+      const int e = w / Ppad, i = w % Ppad;
       double v = 0.0;
       if (i < P && e0 + e < prm.ne)
       {
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(256) dense_apply2_kernel(DenseParams prm)
   const double *src = prm.curl_orient ? X : U;
   for (int w = tid; w < P * NEB; w += blockDim.x)
   {
-    const int i = w / NEB, e = w % NEB;
+    const int e = w / P, i = w % P;
     if (e0 + e >= prm.ne) continue;
     const int32_t gi = prm.lidx[(size_t)(e0 + e) * prm.PS + i];
     if (prm.curl_orient)

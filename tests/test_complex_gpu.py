@@ -360,6 +360,64 @@ def test_complex_gmres_is_scale_invariant_far_outside_the_squarable_range(b2p_ct
     assert np.isfinite(sols[1]).all() and _rel(sols[1], sols[0]) < 1e-9
 
 
+def test_outer_eigen_solver_interface_shift_invert_on_host_vectors(b2p_ctx):
+    """ArpackEPSSolver::ApplyOp / ApplyOpB (linalg/arpack.cpp:631-674): the eigen-solver's reverse communication hands over
+    HOST pointers to interleaved complex vectors; y = gamma (K - sigma M)^-1 M x and y = delta B x are formed on the device.
+    Checked against SciPy on the oracle matrices, and driven by ARPACK (scipy eigs) to the eigenvalues of the lossy pencil.
+    (A small problem: the inner GMRES runs unpreconditioned to 1e-12.)"""
+    from palace_b200 import capi
+
+    capi.set_stream(b2p_ctx)
+    prob = common.make_problem(n=(3, 2, 2), p=1, n_attr=2)
+    geom = common.gpu_geom(b2p_ctx, prob)
+    nd = prob.nd
+    n = nd.ndofs
+    ident = cf.coeff_ctx()
+    mblob = common.coefficient(O.ND_MASS, 2, "matrix")
+    Kop = common.gpu_op(b2p_ctx, geom, prob, O.CURLCURL, ident)
+    Mop = common.gpu_op(b2p_ctx, geom, prob, O.ND_MASS, mblob)
+    sigma, loss = 5.0 + 0.3j, 1.0 - 0.05j
+    Kc = capi.ComplexOperator.par(b2p_ctx, n, n, [Kop], [1.0 + 0.0j], nd.ess_dofs, 1)
+    Mc = capi.ComplexOperator.par(b2p_ctx, n, n, [Mop], [loss], nd.ess_dofs, 0)                      # lossy mass, DIAG_ZERO rows
+    Sh = capi.ComplexOperator.par(b2p_ctx, n, n, [Kop, Mop], [1.0 + 0.0j, -sigma * loss], nd.ess_dofs, 1)
+    ksp = capi.ComplexSolver.krylov(b2p_ctx, 1, rel_tol=1e-12, max_it=200, max_dim=200)
+    ksp.set_operator(Sh)
+    gamma, delta = 0.7, 1.3
+    eps = capi.Eps(b2p_ctx, n, Kc, Mc, ksp, B=Mc, sinvert=True, gamma=gamma, delta=delta)
+    ess = nd.ess_dofs
+    Ko = common.oracle_matrix(prob, O.CURLCURL, ident, eliminate=False).tolil()
+    Mo = (loss * common.oracle_matrix(prob, O.ND_MASS, mblob, eliminate=False)).tolil()
+    for A_, d in ((Ko, 1.0), (Mo, 0.0)):
+        A_[ess, :] = 0
+        A_[:, ess] = 0
+        A_[ess, ess] = d
+    Ko, Mo = Ko.tocsc(), Mo.tocsc()
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    x[ess] = 0.0
+    y = eps.apply_op(x)
+    y_ref = gamma * spla.spsolve((Ko - sigma * Mo).tocsc(), Mo @ x)
+    assert _rel(y, y_ref) < 1e-8
+    assert _rel(eps.apply_op_b(x), delta * (Mo @ x)) < 1e-12
+    # ARPACK in shift-invert mode on the free dofs: eigenvalues of (K, M) nearest sigma
+    free = np.setdiff1d(np.arange(n), ess)
+
+    def opinv(v):
+        f = np.zeros(n, dtype=np.complex128)
+        f[free] = v
+        return eps.apply_op(f)[free] / gamma
+
+    nf = free.size
+    lam = spla.eigs(spla.LinearOperator((nf, nf), matvec=opinv, dtype=np.complex128), k=2, which="LM", tol=1e-10,
+                    v0=np.random.default_rng(1).standard_normal(nf) + 0j, return_eigenvectors=False)
+    lam = np.sort_complex(sigma + 1.0 / lam)
+    import scipy.linalg as sla
+
+    all_lam = sla.eigvals(Ko[free][:, free].toarray(), Mo[free][:, free].toarray())
+    ref = all_lam[np.argsort(np.abs(all_lam - sigma))[:2]]
+    assert np.abs(lam - np.sort_complex(ref)).max() < 1e-7 * np.abs(ref).max()
+
+
 def test_lossy_system_with_real_multigrid_preconditioner(b2p_ctx, setup):
     """FGMRES on the complex lossy system, preconditioned by the real p-multigrid of K + omega^2 M applied
     to real and imaginary parts (PCMatReal + PCMatShifted)."""
