@@ -1403,7 +1403,9 @@ void b2p_csolver_destroy(b2p_csolver *s) { delete s; }
 }  // extern "C"
 
 // ---- outer eigen-solver interface (ArpackEPSSolver::ApplyOp / ApplyOpB, arpack.cpp:631-674) ----
-namespace
+namespace b2p
+{
+namespace eps_detail
 {
 // interleaved complex (the host layout, staged in z[2n]) <-> split real / imaginary device vectors
 __global__ void csplit_kernel(const double *__restrict__ z, double *__restrict__ re, double *__restrict__ im, int64_t n)
@@ -1424,7 +1426,8 @@ __global__ void cjoin_scaled_kernel(const double *__restrict__ re, const double 
     z[2 * i + 1] = s * im[i];
   }
 }
-}  // namespace
+}  // namespace eps_detail
+}  // namespace b2p
 
 struct b2p_eps
 {
@@ -1438,10 +1441,9 @@ struct b2p_eps
   double *h_pin = nullptr;             // pinned host staging [2n]
 };
 
-namespace
+static int eps_run(b2p_eps *e, const double *px, double *py, bool op_b)
 {
-int eps_run(b2p_eps *e, const double *px, double *py, bool op_b)
-{
+  using namespace b2p::eps_detail;
   b2p_ctx *ctx = e->ctx;
   cudaStream_t s = ctx->stream;
   const int64_t n = e->n;
@@ -1468,7 +1470,6 @@ int eps_run(b2p_eps *e, const double *px, double *py, bool op_b)
   std::memcpy(py, e->h_pin, sizeof(double) * 2 * n);  // y1.Get(py, n)
   return B2P_SUCCESS;
 }
-}  // namespace
 
 extern "C"
 {
