@@ -147,12 +147,15 @@ int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s);
  *                            the overwrite of y at those rows after P^T (rap.cpp:207-233)
  *   B2P_APPLY_SIMPLE_KERNEL  run the simple cross-check kernel instead of the production one
  *   B2P_APPLY_HALFWARP_KERNEL  run the one-element-per-warp ND kernel where it applies (p = 3, q1d = 4,
- *                            mirror-symmetric 1-D tables; ignored otherwise) */
+ *                            mirror-symmetric 1-D tables; ignored otherwise)
+ *   B2P_APPLY_ROUND1_KERNEL  run nd_hex_apply4_kernel (the round-1 production kernel) where the default is
+ *                            nd_hex_apply6_kernel (p = 2, 3 at q1d = p + 1); same as B2P_ND_KERNEL=4 for one call */
 enum
 {
   B2P_APPLY_MASKED = 1,
   B2P_APPLY_SIMPLE_KERNEL = 2,
-  B2P_APPLY_HALFWARP_KERNEL = 4
+  B2P_APPLY_HALFWARP_KERNEL = 4,
+  B2P_APPLY_ROUND1_KERNEL = 8
 };
 int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, int flags, b2p_stream s);
 /* Same over the element sub-range [e_begin, e_begin + e_count) with the L-vector in two pieces: dofs

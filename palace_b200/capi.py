@@ -246,17 +246,18 @@ class Op:
     def apply_add(self, x, y, stream=None):
         _chk(lib().b2p_op_apply_add(self.h, _vp(x), _vp(y), _stream(stream)), self.ctx.h)
 
-    def apply_add_ex(self, alpha, x, y, masked=False, simple_kernel=False, halfwarp_kernel=False, stream=None):
-        flags = (1 if masked else 0) | (2 if simple_kernel else 0) | (4 if halfwarp_kernel else 0)
+    def apply_add_ex(self, alpha, x, y, masked=False, simple_kernel=False, halfwarp_kernel=False, round1_kernel=False, stream=None):
+        flags = (1 if masked else 0) | (2 if simple_kernel else 0) | (4 if halfwarp_kernel else 0) | (8 if round1_kernel else 0)
         _chk(lib().b2p_op_apply_add_ex(self.h, C.c_double(alpha), _vp(x), _vp(y), flags, _stream(stream)), self.ctx.h)
 
     def apply_add_pair(self, alpha, x0, x1, y0, y1, masked=False, stream=None):
         _chk(lib().b2p_op_apply_add_pair(self.h, C.c_double(alpha), _vp(x0), _vp(x1), _vp(y0), _vp(y1), 1 if masked else 0,
                                          _stream(stream)), self.ctx.h)
 
-    def apply_add_split(self, alpha, x, xg, y, yg, n_owned, e_begin, e_count, masked=False, halfwarp_kernel=False, stream=None):
+    def apply_add_split(self, alpha, x, xg, y, yg, n_owned, e_begin, e_count, masked=False, halfwarp_kernel=False, round1_kernel=False, stream=None):
         _chk(lib().b2p_op_apply_add_split(self.h, C.c_double(alpha), _vp(x), _vp(xg), _vp(y), _vp(yg), C.c_int64(n_owned), int(e_begin),
-                                          int(e_count), (1 if masked else 0) | (4 if halfwarp_kernel else 0), _stream(stream)), self.ctx.h)
+                                          int(e_count), (1 if masked else 0) | (4 if halfwarp_kernel else 0) | (8 if round1_kernel else 0),
+                                          _stream(stream)), self.ctx.h)
 
     def set_essential(self, ess_ldofs):
         e = _np(ess_ldofs, np.int32)

@@ -114,7 +114,7 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   }();
   if (((flags & B2P_APPLY_HALFWARP_KERNEL) || nd_kernel == 5) && nd_hex_apply5_eligible(op))
     return launch_nd_hex_apply5(op, lidx, alpha, x, y, rg, s);
-  if ((nd_kernel == 6 || nd_kernel == 0) && nd_hex_apply6_eligible(op))
+  if ((nd_kernel == 6 || nd_kernel == 0) && !(flags & B2P_APPLY_ROUND1_KERNEL) && nd_hex_apply6_eligible(op))
   {
     static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
     if (trace) fprintf(stderr, "[b2p] nd_hex_apply6 p=%d q1d=%d kind=%d ne=%d\n", op->p, op->q1d, op->kind, op->ne);

@@ -206,6 +206,42 @@ def test_h1_production_and_simple_kernels_agree_with_alpha_and_mask(b2p_ctx, p):
         assert _rel(yd.cpu().numpy(), y0 + 1.25 * y_ref) < RTOL
 
 
+@pytest.mark.parametrize("p", [2, 3])
+@pytest.mark.parametrize("kind", [O.CURLCURL, O.ND_MASS, O.CURLCURL_MASS])
+def test_both_production_nd_kernels_match_the_oracle(b2p_ctx, kind, p):
+    """p = 2, 3 run nd_hex_apply6_kernel by default (register x-gather, XDX on the Z region, aliased work arrays, half tables,
+    branch-free scatter); B2P_APPLY_ROUND1_KERNEL selects nd_hex_apply4_kernel for the same call. Both against the oracle: plain,
+    scaled + masked, and over element sub-ranges with the owned | ghost split (a ragged last batch in each piece)."""
+    prob = common.make_problem(n=(3, 3, 2), p=p)
+    blob = common.coefficient(kind, 3, "matrix", a_mass=0.9, a_curl=1.1)
+    g = common.gpu_geom(b2p_ctx, prob)
+    op = common.gpu_op(b2p_ctx, g, prob, kind, blob)
+    ess = prob.nd.ess_dofs
+    op.set_essential(ess)
+    rng = np.random.default_rng(23)
+    x, y0 = rng.standard_normal(prob.nd.ndofs), rng.standard_normal(prob.nd.ndofs)
+    y_ref = common.oracle_apply(prob, kind, blob, x)
+    xm = x.copy()
+    xm[ess] = 0.0
+    ym = common.oracle_apply(prob, kind, blob, xm)
+    ym[ess] = 0.0
+    n_owned = prob.nd.ndofs // 2
+    ne = prob.nd.lex_gid.shape[0]
+    for r1 in (False, True):
+        yd = _dev(y0)
+        op.apply_add_ex(1.5, _dev(x), yd, round1_kernel=r1)
+        assert _rel(yd.cpu().numpy(), y0 + 1.5 * y_ref) < RTOL
+        yd = _dev(y0)
+        op.apply_add_ex(-0.5, _dev(x), yd, masked=True, round1_kernel=r1)
+        assert _rel(yd.cpu().numpy(), y0 - 0.5 * ym) < RTOL
+        xd = _dev(x)
+        yo = torch.zeros(n_owned, dtype=torch.float64, device="cuda")
+        yg = torch.zeros(prob.nd.ndofs - n_owned, dtype=torch.float64, device="cuda")
+        for e0, ec in ((0, ne // 3), (ne // 3, ne - ne // 3)):
+            op.apply_add_split(1.0, xd[:n_owned].contiguous(), xd[n_owned:].contiguous(), yo, yg, n_owned, e0, ec, round1_kernel=r1)
+        assert _rel(np.concatenate([yo.cpu().numpy(), yg.cpu().numpy()]), y_ref) < RTOL
+
+
 @pytest.mark.parametrize("assemble", [False, True])
 @pytest.mark.parametrize("kind", [O.CURLCURL, O.ND_MASS, O.CURLCURL_MASS])
 def test_halfwarp_kernel_matches_oracle(b2p_ctx, kind, assemble):
