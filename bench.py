@@ -526,6 +526,40 @@ def main():
                 pass
             e2e_value, e2e_mode = e2e_serial, f"serial: H2D, Mult, D2H on one stream (pipelined leg failed: {type(exc).__name__}: {exc})"
 
+    # ---- N > 1: parity of the partitioned Mult inside the recorded run (outside every timed region) ----
+    # Every rank applies the distributed operator to its slice of ONE global vector; rank 0 applies the single-partition
+    # operator of the whole mesh to the same vector and compares on each rank's owned dofs (the reference checks partition
+    # independence by running its regression suite at several rank counts).
+    partition_parity = None
+    if world > 1:
+        xg = np.random.default_rng(12345).standard_normal(N_global)
+        own = ls.local_to_global[: ls.n_true]
+        xp = torch.from_numpy(np.ascontiguousarray(xg[own])).cuda()
+        yp = torch.empty_like(xp)
+        A.mult(xp, yp)
+        torch.cuda.synchronize()
+        pieces = [None] * world if rank == 0 else None
+        dist.gather_object((np.asarray(own), yp.cpu().numpy()), pieces, dst=0)
+        if rank == 0:
+            try:
+                geom_g = capi.Geom.hex(ctx, prob["xe"], prob["mesh"].attr, prob["mesh_order"], q1d, prob["nB"], prob["nG"], prob["tabs"].qw)
+                gi, go = gnd.native_restriction()
+                op_g = capi.Op.create(ctx, geom_g, capi.CURLCURL_MASS, p, gnd.ndofs, gi, go, gnd.dof_map, t.Bo, t.Bc, t.Gc, prob["blob"],
+                                      assemble=bool(args.assemble_qdata))
+                A_g = capi.Operator.par(ctx, gnd.ndofs, gnd.ndofs, [op_g], None, None, diag_policy=1, halo=None)
+                xgd = torch.from_numpy(xg).cuda()
+                ygd = torch.empty_like(xgd)
+                A_g.mult(xgd, ygd)
+                torch.cuda.synchronize()
+                y_ref = ygd.cpu().numpy()
+                err = max(float(np.abs(yv - y_ref[o]).max()) for o, yv in pieces) / float(np.abs(y_ref).max())
+                covered = int(sum(o.size for o, _ in pieces))
+                partition_parity = {"max_rel_err": err, "dofs_checked": covered, "ok": bool(err < 1e-12 and covered == N_global),
+                                    "against": "single-partition ParOperator::Mult of the whole mesh on rank 0, same global vector"}
+                del A_g, op_g, geom_g, xgd, ygd
+            except Exception as exc:
+                partition_parity = {"failed": f"{type(exc).__name__}: {str(exc)[:200]}"}
+
     line = None
     if rank == 0:
         line = {
@@ -542,6 +576,8 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(abytes)},
         }
+        if partition_parity is not None:
+            line["partition_parity"] = partition_parity
         if not args.no_cpu_baseline:
             base_prob = prob if world == 1 else build_problem(args.n, args.order, args.warp, coefficient=args.coefficient)
             ref = CpuReference(base_prob, args.cpu_sample_elems)

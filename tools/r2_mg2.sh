@@ -2,9 +2,9 @@
 N=${1:-2}
 cd /root/repo; mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $TR tools/dist_check.py > gpurun_out/dist_check_${N}gpu.log 2>&1; tail -n 1 gpurun_out/dist_check_${N}gpu.log
-B2P_HALO_TIMING=1 B2P_PDL=0 timeout 300 $TR bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/bench_${N}gpu_timing_nopdl.json 2> gpurun_out/bench_${N}gpu_timing_nopdl.err
-grep "halo timing" gpurun_out/bench_${N}gpu_timing_nopdl.err | tail -2
 timeout 300 $TR bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err
-python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-experiments > gpurun_out/bench_1gpu_same_box.json 2>> gpurun_out/bench_${N}gpu.err
-for f in gpurun_out/bench_${N}gpu.json gpurun_out/bench_1gpu_same_box.json; do grep '^{' $f | cut -c1-230; done
+grep '^{' gpurun_out/bench_${N}gpu.json | python -c "
+import sys,json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['n_gpus'], d['value'], d['ms_per_step'], d.get('partition_parity'), d['config']['partition'][:80])"
+tail -n 3 gpurun_out/bench_${N}gpu.err | cut -c1-300
+timeout 300 python -m pytest tests/test_solvers_gpu.py -m gpu -x -q -k "multi_gpu" 2>&1 | tail -2
