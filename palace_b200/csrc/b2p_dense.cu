@@ -584,10 +584,26 @@ int launch_dense_apply(b2p_op *op, const int32_t *lidx, double alpha, const doub
     const int tiles = prm.Ppad / 8;  // dof tiles of the backward GEMM: one warp per tile up to 8 warps, then several per warp
     const int nwarps = tiles < 8 ? (tiles < 4 ? 4 : tiles) : 8;
     const int mtb = (tiles + nwarps - 1) / nwarps;
-    const size_t need = sizeof(double) * 36 * ((size_t)prm.Ppad + 6 * QC + (op->curl_orient ? prm.Ppad : 0));
-    if (need <= 227 * 1024 && mtb <= 4)
+    const size_t rows = (size_t)prm.Ppad + 6 * QC + (op->curl_orient ? prm.Ppad : 0);
+    const size_t need4 = sizeof(double) * 36 * rows, need2 = sizeof(double) * 20 * rows;
+    // Two CTAs per SM need <= 113 KB each: large elements (p = 6: 180 KB with four n-tiles) run two n-tiles per CTA instead,
+    // 16 elements per CTA, so that 16 warps per SM hide the table-fragment latency (B2P_DENSE_NT=4 forces four).
+    static const int force_nt = []
     {
-      static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
+      const char *e = std::getenv("B2P_DENSE_NT");
+      return e ? std::atoi(e) : 0;
+    }();
+    const bool two = force_nt == 2 || (force_nt != 4 && need4 > 113 * 1024 && need2 <= 113 * 1024);
+    static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
+    if (two && need2 <= 227 * 1024 && mtb <= 4 && prm.ne >= 16)
+    {
+      if (trace) fprintf(stderr, "[b2p] dense_apply2 (2 n-tiles) P=%d Q=%d ne=%d warps=%d tiles/warp=%d\n", prm.P, prm.Q, prm.ne, nwarps, mtb);
+      if (mtb <= 1) return launch_dense2<2, QC, 1>(op, prm, nwarps, s);
+      if (mtb <= 2) return launch_dense2<2, QC, 2>(op, prm, nwarps, s);
+      return launch_dense2<2, QC, 4>(op, prm, nwarps, s);
+    }
+    if (need4 <= 227 * 1024 && mtb <= 4)
+    {
       if (trace) fprintf(stderr, "[b2p] dense_apply2 P=%d Q=%d ne=%d warps=%d tiles/warp=%d\n", prm.P, prm.Q, prm.ne, nwarps, mtb);
       if (mtb <= 1) return launch_dense2<4, QC, 1>(op, prm, nwarps, s);
       if (mtb <= 2) return launch_dense2<4, QC, 2>(op, prm, nwarps, s);
