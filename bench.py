@@ -439,7 +439,11 @@ def main():
     abytes = op.algorithmic_bytes()
     # which sum-factorised kernel the library dispatches for this operator (b2p_core.cu:apply_range)
     forced = os.environ.get("B2P_ND_KERNEL", "0")
-    kernel_name = "nd_hex_apply6_kernel" if (forced in ("0", "6") and args.order in (2, 3) and not args.assemble_qdata) else "nd_hex_apply4_kernel"
+    kernel_name = "nd_hex_apply4_kernel"
+    if forced in ("0", "6") and args.order in (2, 3) and not args.assemble_qdata:
+        kernel_name = "nd_hex_apply6_kernel"
+    elif forced in ("0", "7") and args.order in (4, 5, 6) and not args.assemble_qdata:
+        kernel_name = "nd_hex_apply7_kernel"
     traffic = None
     try:  # DRAM bytes of the same kernel/launch shape from the committed ncu capture (profiles/)
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:

@@ -149,13 +149,17 @@ int b2p_op_apply_add(b2p_op *op, const double *x, double *y, b2p_stream s);
  *   B2P_APPLY_HALFWARP_KERNEL  run the one-element-per-warp ND kernel where it applies (p = 3, q1d = 4,
  *                            mirror-symmetric 1-D tables; ignored otherwise)
  *   B2P_APPLY_ROUND1_KERNEL  run nd_hex_apply4_kernel (the round-1 production kernel) where the default is
- *                            nd_hex_apply6_kernel (p = 2, 3 at q1d = p + 1); same as B2P_ND_KERNEL=4 for one call */
+ *                            nd_hex_apply6_kernel (p = 2, 3 at q1d = p + 1); same as B2P_ND_KERNEL=4 for one call
+ *   B2P_APPLY_CTA_KERNEL     run nd_hex_apply7_kernel (one CTA per element batch, one 1-D line per thread) where it
+ *                            applies (p = 4, 5, 6 at q1d = p + 1, mirror-symmetric tables; ignored otherwise); same as
+ *                            B2P_ND_KERNEL=7 for one call */
 enum
 {
   B2P_APPLY_MASKED = 1,
   B2P_APPLY_SIMPLE_KERNEL = 2,
   B2P_APPLY_HALFWARP_KERNEL = 4,
-  B2P_APPLY_ROUND1_KERNEL = 8
+  B2P_APPLY_ROUND1_KERNEL = 8,
+  B2P_APPLY_CTA_KERNEL = 16
 };
 int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, int flags, b2p_stream s);
 /* Same over the element sub-range [e_begin, e_begin + e_count) with the L-vector in two pieces: dofs
@@ -459,6 +463,28 @@ int b2p_eps_create(b2p_ctx *ctx, int64_t n, b2p_coperator *K, b2p_coperator *M, 
 int b2p_eps_apply_op(b2p_eps *e, const double *x_host_interleaved, double *y_host_interleaved);
 int b2p_eps_apply_op_b(b2p_eps *e, const double *x_host_interleaved, double *y_host_interleaved);
 void b2p_eps_destroy(b2p_eps *e);
+
+/* ---- DivFreeSolver (linalg/divfree.cpp:42-186): projection of an ND field onto the discretely divergence-free fields ----
+ *        rhs = WeakDiv y ;  rhs[h1 essential dofs] = 0 ;  M psi = rhs  (PCG) ;  y += G psi
+ * with M the H1 diffusion operator with the permittivity (essential dofs DIAG_ONE), G the discrete gradient and WeakDiv the
+ * weak divergence -(eps u, grad v). The reference partially assembles WeakDiv from MixedVectorWeakDivergenceIntegrator
+ * (fem/integ/mixedvecgrad.cpp:148-208): the ND mass quadrature function between the ND interpolation and the H1 gradient, negated.
+ * grad v_h IS G v for an H1 function, so WeakDiv = -G^T M_eps with M_eps the ND mass operator: `nd_mass` is that operator as a
+ * b2p_operator_par WITHOUT essential dofs (one element kernel launch), and no separate mixed operator is set up.
+ * Solver as the reference builds it: CG, no initial guess, relative tolerance tol, absolute tolerance epsilon; one level ->
+ * the coarse solver alone, n levels -> GeometricMultigridSolver(coarse, h1_P, no auxiliary space, 1 cycle, 1 smoothing
+ * iteration, Chebyshev 4th kind of order max(h1_order, 2)). coarse_type / coarse_tol / coarse_max_it / coarse_solver as in
+ * b2p_ksp_config (the reference's BoomerAMG stays outside this library). h1_ops[n_levels] carry the essential dofs; when the
+ * mesh has no marked boundary the caller constrains one dof (true dof 0 of the first rank) on every level as divfree.cpp:50-81
+ * does. Complex fields: one CG iteration on both parts together (ComplexParOperator(M, nullptr)). */
+typedef struct b2p_divfree b2p_divfree;
+int b2p_divfree_create(b2p_ctx *ctx, b2p_operator *nd_mass, b2p_operator *grad, int n_levels, b2p_operator *const *h1_ops,
+                       b2p_operator *const *h1_P, const int32_t *h1_ess_tdofs, int64_t n_ess, int h1_order, double tol, int max_it,
+                       int coarse_type, double coarse_tol, int coarse_max_it, b2p_solver *coarse_solver, b2p_divfree **out);
+int b2p_divfree_mult(b2p_divfree *d, double *y);                         /* DivFreeSolver<Vector>::Mult, in place */
+int b2p_divfree_mult_complex(b2p_divfree *d, double *y_re, double *y_im); /* DivFreeSolver<ComplexVector>::Mult */
+int b2p_divfree_stats(b2p_divfree *d, int *num_mult, int *num_mult_its, int *last_its, int *converged);
+void b2p_divfree_destroy(b2p_divfree *d);
 
 #ifdef __cplusplus
 }

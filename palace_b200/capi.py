@@ -246,17 +246,20 @@ class Op:
     def apply_add(self, x, y, stream=None):
         _chk(lib().b2p_op_apply_add(self.h, _vp(x), _vp(y), _stream(stream)), self.ctx.h)
 
-    def apply_add_ex(self, alpha, x, y, masked=False, simple_kernel=False, halfwarp_kernel=False, round1_kernel=False, stream=None):
-        flags = (1 if masked else 0) | (2 if simple_kernel else 0) | (4 if halfwarp_kernel else 0) | (8 if round1_kernel else 0)
+    def apply_add_ex(self, alpha, x, y, masked=False, simple_kernel=False, halfwarp_kernel=False, round1_kernel=False, cta_kernel=False,
+                     stream=None):
+        flags = ((1 if masked else 0) | (2 if simple_kernel else 0) | (4 if halfwarp_kernel else 0) | (8 if round1_kernel else 0)
+                 | (16 if cta_kernel else 0))
         _chk(lib().b2p_op_apply_add_ex(self.h, C.c_double(alpha), _vp(x), _vp(y), flags, _stream(stream)), self.ctx.h)
 
     def apply_add_pair(self, alpha, x0, x1, y0, y1, masked=False, stream=None):
         _chk(lib().b2p_op_apply_add_pair(self.h, C.c_double(alpha), _vp(x0), _vp(x1), _vp(y0), _vp(y1), 1 if masked else 0,
                                          _stream(stream)), self.ctx.h)
 
-    def apply_add_split(self, alpha, x, xg, y, yg, n_owned, e_begin, e_count, masked=False, halfwarp_kernel=False, round1_kernel=False, stream=None):
+    def apply_add_split(self, alpha, x, xg, y, yg, n_owned, e_begin, e_count, masked=False, halfwarp_kernel=False, round1_kernel=False,
+                        cta_kernel=False, stream=None):
         _chk(lib().b2p_op_apply_add_split(self.h, C.c_double(alpha), _vp(x), _vp(xg), _vp(y), _vp(yg), C.c_int64(n_owned), int(e_begin),
-                                          int(e_count), (1 if masked else 0) | (4 if halfwarp_kernel else 0) | (8 if round1_kernel else 0),
+                                          int(e_count), (1 if masked else 0) | (4 if halfwarp_kernel else 0) | (8 if round1_kernel else 0) | (16 if cta_kernel else 0),
                                           _stream(stream)), self.ctx.h)
 
     def set_essential(self, ess_ldofs):
@@ -858,6 +861,43 @@ class Ksp:
         try:
             if self.h:
                 lib().b2p_ksp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class DivFree:
+    """DivFreeSolver (linalg/divfree.cpp): y <- y + G psi with (G^T M_eps G) psi = -G^T M_eps y on the H1 hierarchy."""
+
+    def __init__(self, ctx, nd_mass, grad, h1_ops, h1_P, h1_ess, h1_order, tol=1e-6, max_it=1000, coarse_type=1, coarse_tol=1e-3,
+                 coarse_max_it=500, coarse_solver=None):
+        self.ctx = ctx
+        n_levels = len(h1_ops)
+        assert len(h1_P) == n_levels - 1
+        A = (C.c_void_p * n_levels)(*[a.h for a in h1_ops])
+        Parr = (C.c_void_p * max(1, len(h1_P)))(*[p.h for p in h1_P])
+        ess = np.ascontiguousarray(h1_ess, dtype=np.int32)
+        self.h = C.c_void_p()
+        _chk(lib().b2p_divfree_create(ctx.h, nd_mass.h, grad.h, n_levels, A, Parr, _ptr(ess), C.c_int64(ess.size), int(h1_order),
+                                      C.c_double(tol), int(max_it), int(coarse_type), C.c_double(coarse_tol), int(coarse_max_it),
+                                      coarse_solver.h if coarse_solver else None, C.byref(self.h)), ctx.h)
+        self._keep = [nd_mass, grad, list(h1_ops), list(h1_P), coarse_solver]
+
+    def mult(self, y):
+        _chk(lib().b2p_divfree_mult(self.h, _vp(y)), self.ctx.h)
+
+    def mult_complex(self, yr, yi):
+        _chk(lib().b2p_divfree_mult_complex(self.h, _vp(yr), _vp(yi)), self.ctx.h)
+
+    def stats(self):
+        nm, nit, its, conv = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().b2p_divfree_stats(self.h, C.byref(nm), C.byref(nit), C.byref(its), C.byref(conv)), self.ctx.h)
+        return {"num_mult": nm.value, "num_mult_its": nit.value, "its": its.value, "converged": bool(conv.value)}
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b2p_divfree_destroy(self.h)
                 self.h = None
         except Exception:
             pass

@@ -593,3 +593,186 @@ int b2p_ksp_stats(b2p_ksp *k, int *num_total_mult, int *num_total_mult_its, int 
 void b2p_ksp_destroy(b2p_ksp *k) { delete k; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- DivFreeSolver (linalg/divfree.cpp)
+namespace b2p
+{
+// The complex instantiation of the reference runs ONE Krylov iteration on the complex vector with the real operators applied to
+// both parts (ComplexParOperator(M, nullptr), divfree.cpp:36-41): the same recurrence as real CG on the stacked vector
+// [re; im] with diag(M, M) and diag(B, B) (the operator is Hermitian, so every inner product is real).
+class TwoPartOperator : public Operator
+{
+public:
+  TwoPartOperator(b2p_ctx *c, const Operator *A_) : Operator(c, 2 * A_->Height(), 2 * A_->Width()), A(A_) {}
+  void Mult(const double *x, double *y) const override
+  {
+    A->Mult(x, y);
+    A->Mult(x + A->Width(), y + A->Height());
+  }
+  const Operator *A;
+};
+class TwoPartSolver : public Solver
+{
+public:
+  TwoPartSolver(b2p_ctx *c, const Solver *B_, int64_t n_) : Solver(c), B(B_), n(n_) { height = width = 2 * n_; }
+  void SetOperator(const Operator &) override {}
+  void Mult(const double *x, double *y) const override
+  {
+    B->Mult(x, y);
+    B->Mult(x + n, y + n);
+  }
+  const Solver *B;
+  int64_t n;
+};
+}  // namespace b2p
+
+struct b2p_divfree
+{
+  b2p_ctx *ctx = nullptr;
+  const Operator *Mnd = nullptr, *Grad = nullptr;
+  b2p_ksp *ksp = nullptr;
+  std::unique_ptr<TwoPartOperator> A2;
+  std::unique_ptr<TwoPartSolver> B2;
+  std::unique_ptr<IterativeSolver> ksp2;
+  int32_t *d_ess = nullptr;
+  int64_t n_ess = 0, n_h1 = 0, n_nd = 0;
+  DVec t_nd, rhs, psi;
+  int mult = 0, mult_it = 0, last_it = 0;
+  bool last_converged = true;
+  ~b2p_divfree()
+  {
+    b2p_ksp_destroy(ksp);
+    cudaFree(d_ess);
+  }
+};
+
+extern "C"
+{
+
+int b2p_divfree_create(b2p_ctx *ctx, b2p_operator *nd_mass, b2p_operator *grad, int n_levels, b2p_operator *const *h1_ops,
+                       b2p_operator *const *h1_P, const int32_t *h1_ess_tdofs, int64_t n_ess, int h1_order, double tol, int max_it,
+                       int coarse_type, double coarse_tol, int coarse_max_it, b2p_solver *coarse_solver, b2p_divfree **out)
+{
+  B2P_CHECK(ctx, ctx && nd_mass && nd_mass->op && grad && grad->op && h1_ops && out && n_levels >= 1 && h1_order >= 1, B2P_ERR_ARG,
+            "b2p_divfree_create: bad argument");
+  B2P_CHECK(ctx, n_ess == 0 || h1_ess_tdofs, B2P_ERR_ARG, "b2p_divfree_create: essential dof list missing");
+  b2p_operator *fine = h1_ops[n_levels - 1];
+  B2P_CHECK(ctx, fine && fine->op, B2P_ERR_ARG, "b2p_divfree_create: no operator on the finest H1 level");
+  B2P_CHECK(ctx, grad->op->Width() == fine->op->Height() && grad->op->Height() == nd_mass->op->Height() &&
+                     nd_mass->op->Height() == nd_mass->op->Width(),
+            B2P_ERR_ARG, "b2p_divfree_create: sizes of the mass operator (%lld), the gradient (%lld x %lld) and the H1 operator (%lld) do not match",
+            (long long)nd_mass->op->Height(), (long long)grad->op->Height(), (long long)grad->op->Width(), (long long)fine->op->Height());
+  auto d = std::make_unique<b2p_divfree>();
+  d->ctx = ctx;
+  d->Mnd = nd_mass->op.get();
+  d->Grad = grad->op.get();
+  d->n_h1 = fine->op->Height();
+  d->n_nd = nd_mass->op->Height();
+  // PCG, no initial guess, relative tolerance `tol`, absolute tolerance epsilon (divfree.cpp:137-143); preconditioner: the coarse
+  // solver alone on one level, else GeometricMultigridSolver(coarse, P, no auxiliary space, 1 cycle, 1 smoothing iteration,
+  // Chebyshev order max(p, 2), sf_max 1, sf_min 0, 4th kind) (divfree.cpp:121-135)
+  b2p_ksp_config cfg;
+  b2p_ksp_config_default(&cfg, h1_order);
+  cfg.krylov_solver = 0;
+  cfg.tol = tol;
+  cfg.max_it = max_it;
+  cfg.initial_guess = 0;
+  cfg.mg_cycle_it = 1;
+  cfg.mg_smooth_aux = 0;
+  cfg.mg_smooth_it = 1;
+  cfg.mg_smooth_order = std::max(h1_order, 2);
+  cfg.mg_smooth_sf_max = 1.0;
+  cfg.mg_smooth_sf_min = 0.0;
+  cfg.mg_smooth_cheby_4th = 1;
+  cfg.coarse_type = coarse_type;
+  cfg.coarse_tol = coarse_tol;
+  cfg.coarse_max_it = coarse_max_it;
+  int rc = b2p_ksp_create(ctx, &cfg, n_levels, h1_P, nullptr, coarse_solver, &d->ksp);
+  if (rc) return rc;
+  d->ksp->ksp->abs_tol = 2.220446049250313e-16;
+  if ((rc = b2p_ksp_set_operators(d->ksp, fine, h1_ops, nullptr))) return rc;  // ksp->SetOperators(*M, *M)
+  if (n_ess > 0)
+  {
+    if ((rc = upload(ctx, h1_ess_tdofs, (size_t)n_ess, &d->d_ess))) return rc;
+    d->n_ess = n_ess;
+  }
+  *out = d.release();
+  return B2P_SUCCESS;
+}
+
+// rhs = WeakDiv y = -G^T (M_eps y): MixedVectorWeakDivergenceIntegrator is the ND mass quadrature function between the ND
+// interpolation and the H1 gradient with the coefficient negated (fem/integ/mixedvecgrad.cpp:148-208), and the gradient of an H1
+// function is exactly G applied to its dofs, so the partially assembled weak divergence equals -G^T M_eps to round-off.
+static void divfree_rhs(b2p_divfree *d, const double *y, double *rhs)
+{
+  if (d->t_nd.n != d->n_nd) d->t_nd.resize(d->ctx, d->n_nd);
+  d->Mnd->Mult(y, d->t_nd.p);
+  d->Grad->MultTranspose(d->t_nd.p, rhs);
+  vec::scale(d->ctx, rhs, d->n_h1, -1.0);
+  if (d->n_ess > 0) vec::set_sub(d->ctx, rhs, d->d_ess, d->n_ess, 0.0);  // divfree.cpp:168-171
+}
+
+int b2p_divfree_mult(b2p_divfree *d, double *y)
+{
+  if (!d || !y) return B2P_ERR_ARG;
+  b2p_ctx *ctx = d->ctx;
+  if (d->rhs.n < d->n_h1) d->rhs.resize(ctx, 2 * d->n_h1);
+  if (d->psi.n < d->n_h1) d->psi.resize(ctx, 2 * d->n_h1);
+  B2P_TRY(ctx, divfree_rhs(d, y, d->rhs.p));
+  int rc = b2p_ksp_mult(d->ksp, d->rhs.p, d->psi.p);
+  if (rc) return rc;
+  B2P_TRY(ctx, d->Grad->AddMult(d->psi.p, y, 1.0));  // divfree.cpp:174-183
+  d->mult++;
+  d->last_it = d->ksp->ksp->final_it;
+  d->mult_it += d->last_it;
+  d->last_converged = d->ksp->ksp->converged;
+  return B2P_SUCCESS;
+}
+
+int b2p_divfree_mult_complex(b2p_divfree *d, double *yr, double *yi)
+{
+  if (!d || !yr || !yi) return B2P_ERR_ARG;
+  b2p_ctx *ctx = d->ctx;
+  const int64_t n = d->n_h1;
+  if (d->rhs.n < 2 * n) d->rhs.resize(ctx, 2 * n);
+  if (d->psi.n < 2 * n) d->psi.resize(ctx, 2 * n);
+  if (!d->ksp2)
+  {
+    d->A2 = std::make_unique<TwoPartOperator>(ctx, d->ksp->ksp->A);
+    d->B2 = std::make_unique<TwoPartSolver>(ctx, d->ksp->pc.get(), n);
+    d->ksp2 = std::make_unique<IterativeSolver>(ctx, KspType::CG);
+    d->ksp2->rel_tol = d->ksp->ksp->rel_tol;
+    d->ksp2->abs_tol = d->ksp->ksp->abs_tol;
+    d->ksp2->max_it = d->ksp->ksp->max_it;
+    d->ksp2->SetInitialGuess(false);
+    d->ksp2->SetOperator(*d->A2);
+    d->ksp2->SetPreconditioner(d->B2.get());
+  }
+  B2P_TRY(ctx, divfree_rhs(d, yr, d->rhs.p));
+  B2P_TRY(ctx, divfree_rhs(d, yi, d->rhs.p + n));
+  B2P_TRY(ctx, d->ksp2->Mult(d->rhs.p, d->psi.p));
+  if (!d->ksp2->converged)
+    set_error(ctx, "Linear solver did not converge, norm(Ax-b)/norm(b) = %.3e (norm(b) = %.3e)!", d->ksp2->final_res / d->ksp2->initial_res,
+              d->ksp2->initial_res);
+  B2P_TRY(ctx, d->Grad->AddMult(d->psi.p, yr, 1.0));
+  B2P_TRY(ctx, d->Grad->AddMult(d->psi.p + n, yi, 1.0));
+  d->mult++;
+  d->last_it = d->ksp2->final_it;
+  d->mult_it += d->last_it;
+  d->last_converged = d->ksp2->converged;
+  return B2P_SUCCESS;
+}
+
+int b2p_divfree_stats(b2p_divfree *d, int *num_mult, int *num_mult_its, int *last_its, int *converged)
+{
+  if (!d) return B2P_ERR_ARG;
+  if (num_mult) *num_mult = d->mult;
+  if (num_mult_its) *num_mult_its = d->mult_it;
+  if (last_its) *last_its = d->last_it;
+  if (converged) *converged = d->last_converged ? 1 : 0;
+  return B2P_SUCCESS;
+}
+
+void b2p_divfree_destroy(b2p_divfree *d) { delete d; }
+
+}  // extern "C"

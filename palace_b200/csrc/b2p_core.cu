@@ -104,7 +104,7 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   if (simple) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
   // One-element-per-warp variant (p = 3, q1d = 4, mirror-symmetric tables): opt-in through the apply flag or
   // B2P_ND_KERNEL=5; measured slower than nd_hex_apply4_kernel on B200, kept for the analysis.
-  // B2P_ND_KERNEL = 4 | 5 | 6 forces one of the sum-factorised ND kernels; default: the register-gather pipeline
+  // B2P_ND_KERNEL = 4 | 5 | 6 | 7 forces one of the sum-factorised ND kernels; default: the register-gather pipeline
   // nd_hex_apply6_kernel where it is the faster one on B200 (p = 2, 3 at q1d = p + 1: 51.1 vs 54.6 us at p = 3, 78.5 vs 90.6 us
   // at p = 2, profiles/r02_nd6_variants.txt), nd_hex_apply4_kernel everywhere else.
   static const int nd_kernel = []
@@ -119,6 +119,15 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
     static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
     if (trace) fprintf(stderr, "[b2p] nd_hex_apply6 p=%d q1d=%d kind=%d ne=%d\n", op->p, op->q1d, op->kind, op->ne);
     return launch_nd_hex_apply6(op, lidx, alpha, x, y, rg, s);
+  }
+  // p = 4, 5, 6 at q1d = p + 1: nd_hex_apply7_kernel (one CTA per element batch, warps specialised by vector component, one 1-D
+  // line per thread): 63.7 / 65.9 / 69.5 us against 73.8 / 116.1 / 233.1 us of nd_hex_apply4_kernel at 2.2-2.4M dofs
+  // (profiles/r02_nd7_shapes_ab.jsonl). B2P_ND_KERNEL=4 or B2P_APPLY_ROUND1_KERNEL select the round-1 kernel.
+  if (((flags & B2P_APPLY_CTA_KERNEL) || nd_kernel == 7 || nd_kernel == 0) && !(flags & B2P_APPLY_ROUND1_KERNEL) && nd_hex_apply7_eligible(op))
+  {
+    static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
+    if (trace) fprintf(stderr, "[b2p] nd_hex_apply7 p=%d q1d=%d kind=%d ne=%d\n", op->p, op->q1d, op->kind, op->ne);
+    return launch_nd_hex_apply7(op, lidx, alpha, x, y, rg, s);
   }
   return launch_nd_hex_apply4(op, lidx, alpha, x, y, rg, s);
 }

@@ -989,15 +989,14 @@ int launch6(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
 
 }  // namespace
 
-namespace
-{
-bool nd6_tables_symmetric(const double *tab, int p, int q)
+// Mirror symmetry of the 1-D tables to round-off (the half-table kernels substitute mirrored entries).
+bool nd_tables_symmetric(const double *tab, int p, int q, double rel_tol)
 {
   const int n = p + 1;
   const double *Bo = tab, *Bc = tab + q * p, *Gc = Bc + q * n;
   double scale = 0.0;
   for (int i = 0; i < q * p + 2 * q * n; i++) scale = std::fmax(scale, std::fabs(tab[i]));
-  const double tol = 4e-16 * scale;  // the kernel substitutes mirrored entries: they must agree to round-off
+  const double tol = rel_tol * scale;  // the kernels substitute mirrored entries: they must agree to round-off
   for (int c = 0; c < q; c++)
   {
     for (int i = 0; i < p; i++)
@@ -1010,13 +1009,12 @@ bool nd6_tables_symmetric(const double *tab, int p, int q)
   }
   return true;
 }
-}  // namespace
 
 bool nd_hex_apply6_eligible(b2p_op *op)
 {
   if (!op || op->dense || op->assembled || op->kind == B2P_H1_DIFFUSION || !op->ecoef) return false;
   if (!(op->q1d == op->p + 1 && op->p >= 2 && op->p <= 3)) return false;
-  if (op->tab_sym6 < 0) op->tab_sym6 = nd6_tables_symmetric(op->h_tab.data(), op->p, op->q1d) ? 1 : 0;
+  if (op->tab_sym6 < 0) op->tab_sym6 = nd_tables_symmetric(op->h_tab.data(), op->p, op->q1d, 4e-16) ? 1 : 0;
   return op->tab_sym6 == 1;
 }
 

@@ -139,6 +139,7 @@ struct b2p_op
   bool iso = false;            // every material matrix is c * I
   int tab_sym = -1;            // 1-D tables mirror-symmetric (nd_hex_apply5_kernel): -1 unknown, 0 no, 1 yes
   int tab_sym6 = -1;           // same to round-off (nd_hex_apply6_kernel stores half the rows)
+  int tab_sym7 = -1;           // same within 8e-15 of the largest entry (nd_hex_apply7_kernel, p = 4, 5, 6)
   double *ecoef = nullptr;     // [ne][18] per-element coefficient matrices (TMA-friendly copy of mat[emat])
   // assembled q-data (optional): aq[ne][ncomp][Q], symmetric 6 per part
   double *aq = nullptr;
@@ -198,6 +199,9 @@ int launch_nd_hex_apply5(b2p_op *op, const int32_t *lidx, double alpha, const do
 bool nd_hex_apply5_eligible(b2p_op *op);
 int launch_nd_hex_apply6(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
 bool nd_hex_apply6_eligible(b2p_op *op);
+bool nd_tables_symmetric(const double *tab, int p, int q, double rel_tol);
+int launch_nd_hex_apply7(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s);
+bool nd_hex_apply7_eligible(b2p_op *op);
 // fused complex apply (b2p_hex_nd4.cu): both parts of a split complex vector in one pass over the geometry
 bool nd_hex_apply4z_eligible(const b2p_op *op);
 int launch_nd_hex_apply4z(b2p_op *op, int kind, const int32_t *lidx, const double *zcoef, int has_imag, double alpha, const double *xr,

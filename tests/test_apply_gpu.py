@@ -242,6 +242,65 @@ def test_both_production_nd_kernels_match_the_oracle(b2p_ctx, kind, p):
         assert _rel(np.concatenate([yo.cpu().numpy(), yg.cpu().numpy()]), y_ref) < RTOL
 
 
+@pytest.mark.parametrize("p", [4, 5, 6])
+@pytest.mark.parametrize("kind", [O.CURLCURL, O.ND_MASS, O.CURLCURL_MASS])
+def test_cta_per_batch_kernel_matches_the_oracle(b2p_ctx, kind, p):
+    """nd_hex_apply7_kernel (p = 4, 5, 6: one CTA per element batch, warps specialised by vector component, one 1-D line per
+    thread) against the oracle and against nd_hex_apply4_kernel on the same call: plain, scaled + masked, and over element
+    sub-ranges with the owned | ghost split. 3 x 3 x 1 + 2 elements per piece leave a ragged last batch at p = 5 (two elements
+    per batch)."""
+    prob = common.make_problem(n=(3, 3, 1) if p == 6 else (3, 2, 2), p=p)
+    blob = common.coefficient(kind, 3, "matrix", a_mass=0.9, a_curl=1.1)
+    g = common.gpu_geom(b2p_ctx, prob)
+    op = common.gpu_op(b2p_ctx, g, prob, kind, blob)
+    ess = prob.nd.ess_dofs
+    op.set_essential(ess)
+    rng = np.random.default_rng(29)
+    x, y0 = rng.standard_normal(prob.nd.ndofs), rng.standard_normal(prob.nd.ndofs)
+    y_ref = common.oracle_apply(prob, kind, blob, x)
+    xm = x.copy()
+    xm[ess] = 0.0
+    ym = common.oracle_apply(prob, kind, blob, xm)
+    ym[ess] = 0.0
+    n_owned = prob.nd.ndofs // 2
+    ne = prob.nd.lex_gid.shape[0]
+    for cta in (True, False):
+        yd = _dev(y0)
+        op.apply_add_ex(1.5, _dev(x), yd, cta_kernel=cta, round1_kernel=not cta)
+        assert _rel(yd.cpu().numpy(), y0 + 1.5 * y_ref) < RTOL
+        yd = _dev(y0)
+        op.apply_add_ex(-0.5, _dev(x), yd, masked=True, cta_kernel=cta, round1_kernel=not cta)
+        assert _rel(yd.cpu().numpy(), y0 - 0.5 * ym) < RTOL
+        xd = _dev(x)
+        yo = torch.zeros(n_owned, dtype=torch.float64, device="cuda")
+        yg = torch.zeros(prob.nd.ndofs - n_owned, dtype=torch.float64, device="cuda")
+        for e0, ec in ((0, ne // 3 + 1), (ne // 3 + 1, ne - ne // 3 - 1)):
+            op.apply_add_split(1.0, xd[:n_owned].contiguous(), xd[n_owned:].contiguous(), yo, yg, n_owned, e0, ec, cta_kernel=cta,
+                               round1_kernel=not cta)
+        assert _rel(np.concatenate([yo.cpu().numpy(), yg.cpu().numpy()]), y_ref) < RTOL
+
+
+@pytest.mark.parametrize("p,cfgs", [(4, ["116d", "118g", "223d", "224g", "541d", "542g"]), (5, ["231d", "232g", "233d", "341g", "342d"]),
+                                    (6, ["122g", "123d", "124g", "241d", "242g"])])
+def test_cta_per_batch_kernel_launch_shapes(b2p_ctx, monkeypatch, p, cfgs):
+    """The other launch shapes of nd_hex_apply7_kernel (B2P_ND7_CFG = elements per batch, warps per component, CTAs per SM,
+    q-data by LDG or staged by TMA) compute the same operator: 14 elements leave ragged last batches for 3 and 5 elements
+    per batch."""
+    prob = common.make_problem(n=(7, 2, 1), p=p)
+    kind = O.CURLCURL_MASS
+    blob = common.coefficient(kind, 3, "matrix", a_mass=0.9, a_curl=1.1)
+    g = common.gpu_geom(b2p_ctx, prob)
+    op = common.gpu_op(b2p_ctx, g, prob, kind, blob)
+    rng = np.random.default_rng(31)
+    x, y0 = rng.standard_normal(prob.nd.ndofs), rng.standard_normal(prob.nd.ndofs)
+    y_ref = common.oracle_apply(prob, kind, blob, x)
+    for cfg in cfgs:
+        monkeypatch.setenv("B2P_ND7_CFG", cfg)
+        yd = _dev(y0)
+        op.apply_add_ex(0.75, _dev(x), yd, cta_kernel=True)
+        assert _rel(yd.cpu().numpy(), y0 + 0.75 * y_ref) < RTOL, cfg
+
+
 @pytest.mark.parametrize("assemble", [False, True])
 @pytest.mark.parametrize("kind", [O.CURLCURL, O.ND_MASS, O.CURLCURL_MASS])
 def test_halfwarp_kernel_matches_oracle(b2p_ctx, kind, assemble):
