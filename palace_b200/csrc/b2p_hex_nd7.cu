@@ -20,7 +20,8 @@
 //     6 out); the point order inside a batch is x-slowest, the order of the q-data in HBM, so its loads coalesce;
 //   * persistent grid; the signed restriction indices of the NEXT batch are fetched into registers behind the Z phase,
 //     its x values behind the X phase (both land while the transposed phases run).
-// Phases per batch (one __syncthreads() between them): Z, Y, X, D, Xt, Yt, Zt + scatter (RED.F64).
+// Phases per batch (a barrier between them, component-wide where the hand-off stays inside a component): Z, Y, X, D, Xt, Yt,
+// Zt + scatter (RED.F64).
 //
 // Reference semantics: ceed::Operator::AddMult over CeedOperatorApplyAdd
 // (/root/reference/palace/fem/libceed/operator.cpp:148-178,192-212); D from
@@ -114,7 +115,11 @@ __device__ __forceinline__ void scatter7(double *y, const VSplit &sp, double *si
 // NE elements per batch, WPC warps per component (3 WPC warps per CTA), MINB CTAs per SM.
 // GSM: the batch's q-data and coefficient blocks are staged in shared memory by TMA bulk copies issued one batch ahead (as
 // soon as the D phase of the previous batch has read the buffer); otherwise the D phase loads them with LDG.
-template <int P_, int KIND, bool SPLIT, int NE, int WPC, int MINB, bool GSM>
+// CBAR: the three hand-offs that stay inside one vector component (Z -> Y, Yt -> Zt, Zt -> next Z: producer and consumer lines
+// belong to the same component's warps and its own work arrays) synchronise only that component's WPC warps (named barrier,
+// __syncwarp() for one warp) instead of the CTA; the components may drift apart by a phase. The other four hand-offs cross
+// components (X reads all three, the point arrays alias the Z -> Y arrays) and stay __syncthreads().
+template <int P_, int KIND, bool SPLIT, int NE, int WPC, int MINB, bool GSM, bool CBAR>
 __global__ void __launch_bounds__(3 * WPC * 32, MINB) nd_hex_apply7_kernel(const __grid_constant__ ND7Params<P_> prm)
 {
   using L = ND7Layout<P_, KIND, NE>;
@@ -149,6 +154,19 @@ __global__ void __launch_bounds__(3 * WPC * 32, MINB) nd_hex_apply7_kernel(const
   griddep_launch_dependents();  // a dependent launched programmatically (the halo POST kernel) may be scheduled as CTAs retire
   if (b >= nb) return;
   double *my_sink = prm.sink + ((blockIdx.x * NT + tid) & (b2p_ctx::SINK_SLOTS - 1));
+  auto comp_sync = [&]()
+  {
+#ifdef B2P_EMU
+    __syncthreads();  // (the emulation has CTA barriers only: stricter, same results)
+#else
+    if (!CBAR)
+      __syncthreads();
+    else if (WPC == 1)
+      __syncwarp();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(comp + 1), "r"(WPC * 32) : "memory");
+#endif
+  };
 
   auto load_idx = [&](int bb, int32_t(&g)[n])
   {
@@ -270,7 +288,7 @@ __global__ void __launch_bounds__(3 * WPC * 32, MINB) nd_hex_apply7_kernel(const
       }
     }
     if (has_next) load_idx(bn, ngi);
-    __syncthreads();
+    comp_sync();
 
     // ------------------------------------------------------------------ phase Y (contract j -> qy)
     if (yv)
@@ -649,7 +667,7 @@ __global__ void __launch_bounds__(3 * WPC * 32, MINB) nd_hex_apply7_kernel(const
         }
       }
     }
-    __syncthreads();
+    comp_sync();
 
     // ------------------------------------------------------------------ phase Zt (transposed z-contraction) + scatter
     if (!y_ready)
@@ -700,7 +718,7 @@ __global__ void __launch_bounds__(3 * WPC * 32, MINB) nd_hex_apply7_kernel(const
     }
 #pragma unroll
     for (int k = 0; k < n; k++) gi[k] = ngi[k];
-    __syncthreads();  // the next batch's Z phase overwrites the arrays Zt has just read
+    comp_sync();  // the next batch's Z phase overwrites the arrays Zt has just read
   }
 #undef TBO
 #undef TBC
@@ -715,29 +733,29 @@ template <>
 struct ND7Shape<4>
 {
   static constexpr int NE = 1, WPC = 1, MINB = 8;  // 25 of 32 lanes, 96 threads: 63.7 us (LDG q-data 69.2, nd_hex_apply4_kernel 73.8)
-  static constexpr bool GSM = true;
+  static constexpr bool GSM = true, CBAR = true;
 };
 template <>
 struct ND7Shape<5>
 {
   static constexpr int NE = 2, WPC = 3, MINB = 2;  // 72 of 96 lanes, 288 threads: 65.9 us (LDG q-data 75.8, nd_hex_apply4_kernel 116.1)
-  static constexpr bool GSM = true;
+  static constexpr bool GSM = true, CBAR = true;
 };
 template <>
 struct ND7Shape<6>
 {
   static constexpr int NE = 1, WPC = 2, MINB = 3;  // 49 of 64 lanes, 192 threads: 69.5 us (LDG q-data 73.8, nd_hex_apply4_kernel 233.1)
-  static constexpr bool GSM = true;
+  static constexpr bool GSM = true, CBAR = true;
 };
 
-template <int P_, int KIND, int NE, int WPC, int MINB, bool GSM>
+template <int P_, int KIND, int NE, int WPC, int MINB, bool GSM, bool CBAR>
 int launch7_cfg(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, cudaStream_t s)
 {
   using L = ND7Layout<P_, KIND, NE>;
   constexpr int NT = 3 * WPC * 32;
   const size_t shmem = GSM ? L::SMEM_BYTES_GSM : L::SMEM_BYTES_LDG;
   const bool split = rg.xg || rg.yg || (rg.n_owned >= 0 && rg.n_owned < op->lsize);
-  auto kern = split ? nd_hex_apply7_kernel<P_, KIND, true, NE, WPC, MINB, GSM> : nd_hex_apply7_kernel<P_, KIND, false, NE, WPC, MINB, GSM>;
+  auto kern = split ? nd_hex_apply7_kernel<P_, KIND, true, NE, WPC, MINB, GSM, CBAR> : nd_hex_apply7_kernel<P_, KIND, false, NE, WPC, MINB, GSM, CBAR>;
   static bool configured[2] = {false, false};
   if (!configured[split ? 1 : 0])
   {
@@ -778,14 +796,15 @@ int launch7_cfg(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
   return B2P_SUCCESS;
 }
 
-// B2P_ND7_CFG = "<elements per batch><warps per component><CTAs per SM><d | g>" picks another launch shape of the
-// curl-curl + mass kernel without owned | ghost split (d: q-data by LDG in the D phase, g: staged by TMA): A/B measurements
+// B2P_ND7_CFG = "<elements per batch><warps per component><CTAs per SM><d | g | c>" picks another launch shape of the
+// curl-curl + mass kernel without owned | ghost split (d: q-data by LDG in the D phase, g: staged by TMA, c: staged by TMA and
+// component-wide barriers): A/B measurements
 // (tools/nd7_ab.py switches it inside one process, so it is read per launch).
 inline int nd7_cfg_code()
 {
   const char *e = std::getenv("B2P_ND7_CFG");
   if (!e || !e[0] || !e[1] || !e[2] || !e[3]) return -1;
-  return (e[0] - '0') * 1000 + (e[1] - '0') * 100 + (e[2] - '0') * 10 + (e[3] == 'g' ? 1 : 0);
+  return (e[0] - '0') * 1000 + (e[1] - '0') * 100 + (e[2] - '0') * 10 + (e[3] == 'c' ? 2 : e[3] == 'g' ? 1 : 0);
 }
 
 template <int P_, int KIND>
@@ -798,23 +817,24 @@ int launch7(b2p_op *op, const int32_t *lidx, double alpha, const double *x, doub
     const int code = split ? -1 : nd7_cfg_code();
 #define B2P_CFG(PP, NEV, WPCV, MB)                                                                                       \
   if (P_ == PP && code / 10 == NEV * 100 + WPCV * 10 + MB)                                                               \
-    return (code % 10) ? launch7_cfg<P_, KIND, NEV, (P_ == PP ? WPCV : S::WPC), MB, true>(op, lidx, alpha, x, y, rg, s)   \
-                       : launch7_cfg<P_, KIND, NEV, (P_ == PP ? WPCV : S::WPC), MB, false>(op, lidx, alpha, x, y, rg, s);
+    return (code % 10) == 2   ? launch7_cfg<P_, KIND, NEV, (P_ == PP ? WPCV : S::WPC), MB, true, true>(op, lidx, alpha, x, y, rg, s)   \
+           : (code % 10) == 1 ? launch7_cfg<P_, KIND, NEV, (P_ == PP ? WPCV : S::WPC), MB, true, false>(op, lidx, alpha, x, y, rg, s)  \
+                              : launch7_cfg<P_, KIND, NEV, (P_ == PP ? WPCV : S::WPC), MB, false, false>(op, lidx, alpha, x, y, rg, s);
     if constexpr (P_ == 4)
     {
-      B2P_CFG(4, 1, 1, 6) B2P_CFG(4, 1, 1, 8) B2P_CFG(4, 2, 2, 3) B2P_CFG(4, 2, 2, 4) B2P_CFG(4, 5, 4, 1) B2P_CFG(4, 5, 4, 2)
+      B2P_CFG(4, 1, 1, 6) B2P_CFG(4, 1, 1, 8) B2P_CFG(4, 2, 2, 4) B2P_CFG(4, 5, 4, 2)
     }
     if constexpr (P_ == 5)
     {
-      B2P_CFG(5, 2, 3, 1) B2P_CFG(5, 2, 3, 2) B2P_CFG(5, 2, 3, 3) B2P_CFG(5, 3, 4, 1) B2P_CFG(5, 3, 4, 2)
+      B2P_CFG(5, 2, 3, 1) B2P_CFG(5, 2, 3, 2) B2P_CFG(5, 3, 4, 1) B2P_CFG(5, 3, 4, 2)
     }
     if constexpr (P_ == 6)
     {
-      B2P_CFG(6, 1, 2, 2) B2P_CFG(6, 1, 2, 3) B2P_CFG(6, 1, 2, 4) B2P_CFG(6, 2, 4, 1) B2P_CFG(6, 2, 4, 2)
+      B2P_CFG(6, 1, 2, 2) B2P_CFG(6, 1, 2, 3) B2P_CFG(6, 2, 4, 1) B2P_CFG(6, 2, 4, 2)
     }
 #undef B2P_CFG
   }
-  return launch7_cfg<P_, KIND, S::NE, S::WPC, S::MINB, S::GSM>(op, lidx, alpha, x, y, rg, s);
+  return launch7_cfg<P_, KIND, S::NE, S::WPC, S::MINB, S::GSM, S::CBAR>(op, lidx, alpha, x, y, rg, s);
 }
 
 }  // namespace

@@ -280,11 +280,11 @@ def test_cta_per_batch_kernel_matches_the_oracle(b2p_ctx, kind, p):
         assert _rel(np.concatenate([yo.cpu().numpy(), yg.cpu().numpy()]), y_ref) < RTOL
 
 
-@pytest.mark.parametrize("p,cfgs", [(4, ["116d", "118g", "223d", "224g", "541d", "542g"]), (5, ["231d", "232g", "233d", "341g", "342d"]),
-                                    (6, ["122g", "123d", "124g", "241d", "242g"])])
+@pytest.mark.parametrize("p,cfgs", [(4, ["116d", "118g", "118c", "224g", "542c"]), (5, ["231d", "232g", "232c", "341g", "342c"]),
+                                    (6, ["122g", "123d", "123c", "241c", "242g"])])
 def test_cta_per_batch_kernel_launch_shapes(b2p_ctx, monkeypatch, p, cfgs):
     """The other launch shapes of nd_hex_apply7_kernel (B2P_ND7_CFG = elements per batch, warps per component, CTAs per SM,
-    q-data by LDG or staged by TMA) compute the same operator: 14 elements leave ragged last batches for 3 and 5 elements
+    q-data by LDG (d), staged by TMA (g), staged by TMA with component-wide barriers (c)) compute the same operator: 14 elements leave ragged last batches for 3 and 5 elements
     per batch."""
     prob = common.make_problem(n=(7, 2, 1), p=p)
     kind = O.CURLCURL_MASS

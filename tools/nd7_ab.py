@@ -19,9 +19,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--orders", default="4,5,6")
     ap.add_argument("--reps", type=int, default=30)
-    ap.add_argument("--configs", default="4:116d,118d,118g,223d,224d,224g,542d,542g,541g;5:232d,232g,231d,231g,233g,342d,342g,341g;"
-                    "6:123d,123g,122d,122g,124g,242d,242g,241g",
-                    help="B2P_ND7_CFG values per order: <elements per batch><warps per component><CTAs per SM><d|g>")
+    ap.add_argument("--configs", default="4:118g,118c,542c;5:232g,232c,341c;6:123g,123c,122c",
+                    help="B2P_ND7_CFG values per order: <elements per batch><warps per component><CTAs per SM><d|g|c>")
     ap.add_argument("--skip-round1", action="store_true")
     ap.add_argument("--warp", type=float, default=0.0)
     ap.add_argument("--coefficient", default="iso")
