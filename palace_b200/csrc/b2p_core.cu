@@ -121,8 +121,8 @@ int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, 
     return launch_nd_hex_apply6(op, lidx, alpha, x, y, rg, s);
   }
   // p = 4, 5, 6 at q1d = p + 1: nd_hex_apply7_kernel (one CTA per element batch, warps specialised by vector component, one 1-D
-  // line per thread): 63.7 / 65.9 / 69.5 us against 73.8 / 116.1 / 233.1 us of nd_hex_apply4_kernel at 2.2-2.4M dofs
-  // (profiles/r02_nd7_shapes_ab.jsonl). B2P_ND_KERNEL=4 or B2P_APPLY_ROUND1_KERNEL select the round-1 kernel.
+  // line per thread): 62.8 / 65.2 / 67.0 us against 73.6 / 114.9 / 232.6 us of nd_hex_apply4_kernel at 2.2-2.4M dofs
+  // (profiles/r02_nd7_component_barriers_ab.jsonl). B2P_ND_KERNEL=4 or B2P_APPLY_ROUND1_KERNEL select the round-1 kernel.
   if (((flags & B2P_APPLY_CTA_KERNEL) || nd_kernel == 7 || nd_kernel == 0) && !(flags & B2P_APPLY_ROUND1_KERNEL) && nd_hex_apply7_eligible(op))
   {
     static const bool trace = std::getenv("B2P_TRACE_KERNEL") != nullptr;
