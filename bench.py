@@ -252,6 +252,13 @@ def run_experiments(args):
         "without_pdl_zero_fill_overlap": ([], {"B2P_PDL": "0"}),
         "l2_flush_written_then_read_back": ([], {"B2P_BENCH_FLUSH": "write_read"}),
     }
+    if args.order == 3:
+        # the high-order kernel (nd_hex_apply7_kernel: CTA per element batch) at about the same number of dofs
+        variants.update({
+            "hex_order4_2p4M_dofs": (["--order", "4", "--n", "23"], {}),
+            "hex_order5_2p2M_dofs": (["--order", "5", "--n", "18"], {}),
+            "hex_order6_2p2M_dofs": (["--order", "6", "--n", "15"], {}),
+        })
     # (2) prepared tool measurements (tools/): one JSON line each
     tools = {
         "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--steps", "50"], {}),

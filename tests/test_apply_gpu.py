@@ -280,6 +280,30 @@ def test_cta_per_batch_kernel_matches_the_oracle(b2p_ctx, kind, p):
         assert _rel(np.concatenate([yo.cpu().numpy(), yg.cpu().numpy()]), y_ref) < RTOL
 
 
+@pytest.mark.parametrize("p", [4, 5, 6])
+def test_cta_per_batch_kernel_on_a_single_element_and_empty_ranges(b2p_ctx, p):
+    """One element (a lone, partly filled batch at p = 5), an empty element range, and alpha = 0."""
+    prob = common.make_problem(n=(1, 1, 1), p=p)
+    kind = O.CURLCURL_MASS
+    blob = common.coefficient(kind, 3, "matrix", a_mass=0.9, a_curl=1.1)
+    g = common.gpu_geom(b2p_ctx, prob)
+    op = common.gpu_op(b2p_ctx, g, prob, kind, blob)
+    rng = np.random.default_rng(37)
+    n = prob.nd.ndofs
+    x, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    y_ref = common.oracle_apply(prob, kind, blob, x)
+    yd = _dev(y0)
+    op.apply_add_ex(2.0, _dev(x), yd, cta_kernel=True)
+    assert _rel(yd.cpu().numpy(), y0 + 2.0 * y_ref) < RTOL
+    yd = _dev(y0)
+    op.apply_add_ex(0.0, _dev(x), yd, cta_kernel=True)
+    assert np.array_equal(yd.cpu().numpy(), y0)
+    yo = torch.zeros(n, dtype=torch.float64, device="cuda")
+    yg = torch.zeros(1, dtype=torch.float64, device="cuda")
+    op.apply_add_split(1.0, _dev(x), yg, yo, yg, n, 1, 0, cta_kernel=True)  # no elements: nothing launched, nothing written
+    assert not yo.cpu().numpy().any()
+
+
 @pytest.mark.parametrize("p,cfgs", [(4, ["116d", "118g", "118c", "224g", "542c"]), (5, ["231d", "232g", "232c", "341g", "342c"]),
                                     (6, ["122g", "123d", "123c", "241c", "242g"])])
 def test_cta_per_batch_kernel_launch_shapes(b2p_ctx, monkeypatch, p, cfgs):
