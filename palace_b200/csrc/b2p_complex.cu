@@ -247,12 +247,30 @@ public:
   virtual bool IsReal() const { return false; }  // no imaginary part (operator.hpp:47)
   virtual const int32_t *EssentialTrueDofs() const { return nullptr; }  // device list
   virtual int64_t NumEssential() const { return 0; }
-  void AddMult(CCPtr x, CPtr y, cplx a) const
+  // y += a A x; the default goes through a temporary, operators that can accumulate straight into y override it
+  virtual void AddMult(CCPtr x, CPtr y, cplx a) const
   {
     if (tmp_.n != 2 * n) tmp_.resize(ctx, 2 * n);
     CPtr t{tmp_.p, tmp_.p + n};
     Mult(x, t);
     caxpy(ctx, a, CCPtr{t.re, t.im}, y, n);
+  }
+  virtual bool NativeAddMult() const { return false; }  // AddMult with a real scalar accumulates into y (no temporary)
+  // r = b - A y: with a native AddMult a copy plus one accumulating apply (no zero fill, no AXPBY pass)
+  void Residual(CCPtr b, CCPtr y, CPtr r) const
+  {
+    if (NativeAddMult())
+    {
+      vec::copy(ctx, r.re, b.re, n);
+      vec::copy(ctx, r.im, b.im, n);
+      AddMult(y, r, cplx(-1.0, 0.0));
+    }
+    else
+    {
+      Mult(y, r);
+      vec::axpby(ctx, 1.0, b.re, -1.0, r.re, n);
+      vec::axpby(ctx, 1.0, b.im, -1.0, r.im, n);
+    }
   }
 
 protected:
@@ -381,28 +399,9 @@ public:
   // essential rows as in ComplexParOperator::Mult (rap.cpp:481-517)
   void apply(CCPtr x, CPtr y, bool herm) const
   {
-    cudaStream_t s = ctx->stream;
     vec::set(ctx, y.re, n, 0.0);
     vec::set(ctx, y.im, n, 0.0);
-    b2p_op *o0 = terms[0].op;
-    if (fused && launch_nd_hex_apply4z(o0, fused_kind, o0->lidx_bc, herm ? zcoef_h : zcoef, fused_imag ? 1 : 0, 1.0, x.re, x.im, y.re,
-                                       y.im, s) == B2P_SUCCESS)
-      n_fused_applies++;
-    else
-    for (auto &t : terms)
-    {
-      const double ci = herm ? -t.ci : t.ci;
-      if (t.cr != 0.0)
-      {
-        b2p_op_apply_add_ex(t.op, t.cr, x.re, y.re, B2P_APPLY_MASKED, s);
-        b2p_op_apply_add_ex(t.op, t.cr, x.im, y.im, B2P_APPLY_MASKED, s);
-      }
-      if (ci != 0.0)
-      {
-        b2p_op_apply_add_ex(t.op, -ci, x.im, y.re, B2P_APPLY_MASKED, s);
-        b2p_op_apply_add_ex(t.op, ci, x.re, y.im, B2P_APPLY_MASKED, s);
-      }
-    }
+    apply_terms(x, y, 1.0, herm);
     if (n_ess > 0)
     {
       if (diag_policy == 1)
@@ -415,6 +414,46 @@ public:
         vec::set_sub(ctx, y.re, d_ess, n_ess, 0.0);
         vec::set_sub(ctx, y.im, d_ess, n_ess, 0.0);
       }
+    }
+  }
+  // y += alpha * (masked element operators) x: the essential rows of y are not touched
+  void apply_terms(CCPtr x, CPtr y, double alpha, bool herm) const
+  {
+    cudaStream_t s = ctx->stream;
+    b2p_op *o0 = terms[0].op;
+    if (fused && launch_nd_hex_apply4z(o0, fused_kind, o0->lidx_bc, herm ? zcoef_h : zcoef, fused_imag ? 1 : 0, alpha, x.re, x.im, y.re,
+                                       y.im, s) == B2P_SUCCESS)
+      n_fused_applies++;
+    else
+    for (auto &t : terms)
+    {
+      const double ci = herm ? -t.ci : t.ci;
+      if (t.cr != 0.0)
+      {
+        b2p_op_apply_add_ex(t.op, alpha * t.cr, x.re, y.re, B2P_APPLY_MASKED, s);
+        b2p_op_apply_add_ex(t.op, alpha * t.cr, x.im, y.im, B2P_APPLY_MASKED, s);
+      }
+      if (ci != 0.0)
+      {
+        b2p_op_apply_add_ex(t.op, -alpha * ci, x.im, y.re, B2P_APPLY_MASKED, s);
+        b2p_op_apply_add_ex(t.op, alpha * ci, x.re, y.im, B2P_APPLY_MASKED, s);
+      }
+    }
+  }
+  // y += a A x with a real: the element kernels accumulate straight into y; essential rows: (A x)[ess] = x[ess] (DIAG_ONE) or 0
+  bool NativeAddMult() const override { return true; }
+  void AddMult(CCPtr x, CPtr y, cplx a) const override
+  {
+    if (a.imag() != 0.0)
+    {
+      ComplexOperator::AddMult(x, y, a);
+      return;
+    }
+    apply_terms(x, y, a.real(), false);
+    if (n_ess > 0 && diag_policy == 1)
+    {
+      vec::axpy_sub(ctx, a.real(), x.re, d_ess, n_ess, y.re);
+      vec::axpy_sub(ctx, a.real(), x.im, d_ess, n_ess, y.im);
     }
   }
   bool IsReal() const override
@@ -647,9 +686,7 @@ public:
       }
       else
       {
-        A->Mult(CCPtr{y.re, y.im}, r);
-        vec::axpby(ctx, 1.0, x.re, -1.0, r.re, n);
-        vec::axpby(ctx, 1.0, x.im, -1.0, r.im, n);
+        A->Residual(x, CCPtr{y.re, y.im}, r);
       }
       B2P_LAUNCH(ccheb_kernel, grid_for(ctx, n), NT, 0, ctx->stream, 0.0, 4.0 / (3.0 * lambda_max), ir, ii, (const double *)r.re,
                  (const double *)r.im, dd.re, dd.im, y.re, y.im, 1, fresh ? 1 : 0, n);
@@ -676,12 +713,7 @@ class ComplexDistRelaxationSmoother : public ComplexSolver
   int64_t n = 0, nG = 0;
   mutable DVec r_, x_G, y_G;
 
-  void Residual(CCPtr x, CPtr y, CPtr r) const
-  {
-    A->Mult(CCPtr{y.re, y.im}, r);
-    vec::axpby(ctx, 1.0, x.re, -1.0, r.re, n);
-    vec::axpby(ctx, 1.0, x.im, -1.0, r.im, n);
-  }
+  void Residual(CCPtr x, CPtr y, CPtr r) const { A->Residual(x, CCPtr{y.re, y.im}, r); }
   void AuxCorrection(CCPtr r, CPtr y, bool transpose) const
   {
     CPtr xg{x_G.p, x_G.p + nG}, yg{y_G.p, y_G.p + nG};
@@ -790,8 +822,11 @@ public:
       else
         ok = B[l]->SetOperator(*A_[l]) && ok;
       const int64_t n = A[l]->n;
-      X[l].resize(ctx, 2 * n);
-      Y[l].resize(ctx, 2 * n);
+      if (l + 1 < A.size())  // the finest level works on the caller's vectors (x is only read there, y is the iterate)
+      {
+        X[l].resize(ctx, 2 * n);
+        Y[l].resize(ctx, 2 * n);
+      }
       R[l].resize(ctx, 2 * n);
     }
     return ok;
@@ -799,32 +834,31 @@ public:
   void Mult(CCPtr x, CPtr y) const override
   {
     const int top = (int)A.size() - 1;
-    const int64_t n = A[top]->n;
-    vec::copy(ctx, X[top].p, x.re, n);
-    vec::copy(ctx, X[top].p + n, x.im, n);
+    x_top = x;
+    y_top = y;
     for (int it = 0; it < pc_it; it++) VCycle(top, it > 0);
-    vec::copy(ctx, y.re, Y[top].p, n);
-    vec::copy(ctx, y.im, Y[top].p + n, n);
   }
 
 private:
+  mutable CCPtr x_top{nullptr, nullptr};
+  mutable CPtr y_top{nullptr, nullptr};
   // gmg.cpp:172-205
   void VCycle(int l, bool initial_guess_) const
   {
     const int64_t n = A[l]->n;
-    CPtr x{X[l].p, X[l].p + n}, y{Y[l].p, Y[l].p + n}, r{R[l].p, R[l].p + n};
+    const bool top = l + 1 == (int)A.size();
+    const CCPtr x = top ? x_top : CCPtr{X[l].p, X[l].p + n};
+    const CPtr y = top ? y_top : CPtr{Y[l].p, Y[l].p + n}, r{R[l].p, R[l].p + n};
     B[l]->initial_guess = initial_guess_;
     if (l == 0)
     {
-      B[l]->Mult(CCPtr{x.re, x.im}, y);
+      B[l]->Mult(x, y);
       return;
     }
     const int64_t nc = A[l - 1]->n;
     CPtr xc{X[l - 1].p, X[l - 1].p + nc}, yc{Y[l - 1].p, Y[l - 1].p + nc};
-    B[l]->Mult(CCPtr{x.re, x.im}, y);
-    A[l]->Mult(CCPtr{y.re, y.im}, r);
-    vec::axpby(ctx, 1.0, x.re, -1.0, r.re, n);
-    vec::axpby(ctx, 1.0, x.im, -1.0, r.im, n);
+    B[l]->Mult(x, y);
+    A[l]->Residual(x, CCPtr{y.re, y.im}, r);
     P[l - 1]->MultTranspose(r.re, xc.re);
     P[l - 1]->MultTranspose(r.im, xc.im);
     if (A[l - 1]->NumEssential() > 0)
@@ -836,7 +870,7 @@ private:
     P[l - 1]->AddMult(yc.re, y.re, 1.0);
     P[l - 1]->AddMult(yc.im, y.im, 1.0);
     B[l]->initial_guess = true;
-    B[l]->MultTranspose(CCPtr{x.re, x.im}, y);
+    B[l]->MultTranspose(x, y);
   }
 };
 
