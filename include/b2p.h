@@ -486,6 +486,44 @@ int b2p_divfree_mult_complex(b2p_divfree *d, double *y_re, double *y_im); /* Div
 int b2p_divfree_stats(b2p_divfree *d, int *num_mult, int *num_mult_its, int *last_its, int *converged);
 void b2p_divfree_destroy(b2p_divfree *d);
 
+/* ---- Flux error estimator for H(curl) problems (linalg/errorestimator.cpp:112-270,400-513) ------------------------------------
+ * CurlFluxErrorEstimator: the discontinuous flux mu^-1 B (B = curl E, dofs in the RT space) is projected onto the ND space,
+ *        M H = Flux B    (FluxProjector: mixed H(div) -> H(curl) mass operator with mu^-1, ND mass matrix, PCG + damped Jacobi),
+ * and eta_K^2 = int_K |(mu^-1)^(-1/2) H - (mu^-1)^(1/2) B|^2 is integrated element by element (f_apply_hdivhcurl_error_33); complex
+ * fields add the two parts; eta_K = sqrt(s eta_K^2) with s = 0.5 / Et (or 1 when Et <= 0).
+ * A space is what libCEED sees of a non-tensor basis (fem/libceed/basis.cpp:40-85, restriction.cpp:281-297): reference-space
+ * values interp[3][Q][P] at the quadrature points of `geom` (x fastest for tensor rules), native restriction idx[ne][P] with
+ * orient[ne][P] in {+1, -1} (NULL: all +1), and the reference-to-physical map of the values. The three coefficient tables are
+ * per ATTRIBUTE, [n_attr][9] column-major: mu^-1, its matrix square root and its inverse square root (linalg::MatrixSqrt /
+ * MatrixPow of the reference, computed by the caller). `smooth_mass`: ParOperator of the ND mass integrator (no coefficient, no
+ * essential dofs). Single partition only for now (T-vectors = L-vectors); the estimator is post-processing, not hot path. */
+enum
+{
+  B2P_MAP_HCURL = 1, /* u = J^-T u^      (mfem::FiniteElement::H_CURL) */
+  B2P_MAP_HDIV = 2   /* u = J u^ / detJ  (mfem::FiniteElement::H_DIV) */
+};
+typedef struct
+{
+  int P;                /* dofs per element */
+  int map_type;         /* B2P_MAP_HCURL | B2P_MAP_HDIV */
+  const double *interp; /* [3][Q][P] */
+  const int32_t *idx;   /* [ne][P] */
+  const int8_t *orient; /* [ne][P] or NULL */
+  int64_t lsize;
+} b2p_vecfe_space_desc;
+typedef struct b2p_flux_estimator b2p_flux_estimator;
+int b2p_flux_estimator_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_vecfe_space_desc *flux_space,
+                              const b2p_vecfe_space_desc *smooth_space, int n_attr, const double *coef_flux, const double *coef_disc,
+                              const double *coef_smooth, b2p_operator *smooth_mass, double tol, int max_it, b2p_flux_estimator **out);
+/* FluxProjector::Mult: smooth_dofs = M^-1 Flux flux_dofs */
+int b2p_flux_estimator_project(b2p_flux_estimator *e, const double *flux_dofs, double *smooth_dofs);
+/* estimates[ne] += eta_K^2 of one part (device array) */
+int b2p_flux_estimator_integrate(b2p_flux_estimator *e, const double *flux_dofs, const double *smooth_dofs, double *estimates);
+/* CurlFluxErrorEstimator::AddErrorIndicator: estimates[ne] = sqrt(s (eta_K^2(re) + eta_K^2(im))); flux_im may be NULL */
+int b2p_flux_estimator_indicator(b2p_flux_estimator *e, const double *flux_re, const double *flux_im, double Et, double *estimates);
+int b2p_flux_estimator_stats(b2p_flux_estimator *e, int *num_mult, int *num_mult_its, int *last_its, int *converged);
+void b2p_flux_estimator_destroy(b2p_flux_estimator *e);
+
 #ifdef __cplusplus
 }
 #endif

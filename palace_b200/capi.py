@@ -903,6 +903,64 @@ class DivFree:
             pass
 
 
+class VecFESpaceDesc(C.Structure):
+    """b2p_vecfe_space_desc (include/b2p.h): a vector finite element space as libCEED sees a non-tensor basis."""
+    _fields_ = [("P", C.c_int), ("map_type", C.c_int), ("interp", C.c_void_p), ("idx", C.c_void_p), ("orient", C.c_void_p),
+                ("lsize", C.c_int64)]
+
+
+MAP_HCURL, MAP_HDIV = 1, 2
+
+
+class FluxEstimator:
+    """CurlFluxErrorEstimator (linalg/errorestimator.cpp): flux projection M H = Flux B and the element-wise error integrals."""
+
+    def __init__(self, ctx, geom, flux_space, smooth_space, coef_flux, coef_disc, coef_smooth, smooth_mass, tol=1e-6, max_it=500):
+        self.ctx = ctx
+        keep = []
+
+        def desc(sp):
+            interp = np.ascontiguousarray(sp["interp"], dtype=np.float64)
+            idx = np.ascontiguousarray(sp["idx"], dtype=np.int32)
+            ori = None if sp.get("orient") is None else np.ascontiguousarray(sp["orient"], dtype=np.int8)
+            keep.extend([interp, idx, ori])
+            return VecFESpaceDesc(int(sp["P"]), int(sp["map_type"]), interp.ctypes.data, idx.ctypes.data,
+                                  None if ori is None else ori.ctypes.data, int(sp["lsize"]))
+
+        d1, d2 = desc(flux_space), desc(smooth_space)
+        cf = np.ascontiguousarray(coef_flux, dtype=np.float64).reshape(-1, 9)
+        cd = np.ascontiguousarray(coef_disc, dtype=np.float64).reshape(-1, 9)
+        cs = np.ascontiguousarray(coef_smooth, dtype=np.float64).reshape(-1, 9)
+        assert cf.shape == cd.shape == cs.shape
+        self.h = C.c_void_p()
+        _chk(lib().b2p_flux_estimator_create(ctx.h, geom.h, C.byref(d1), C.byref(d2), int(cf.shape[0]), _ptr(cf), _ptr(cd), _ptr(cs),
+                                             smooth_mass.h, C.c_double(tol), int(max_it), C.byref(self.h)), ctx.h)
+        self._keep = [geom, smooth_mass, keep]
+
+    def project(self, flux_dofs, smooth_dofs):
+        _chk(lib().b2p_flux_estimator_project(self.h, _vp(flux_dofs), _vp(smooth_dofs)), self.ctx.h)
+
+    def integrate(self, flux_dofs, smooth_dofs, estimates):
+        _chk(lib().b2p_flux_estimator_integrate(self.h, _vp(flux_dofs), _vp(smooth_dofs), _vp(estimates)), self.ctx.h)
+
+    def indicator(self, flux_re, flux_im, Et, estimates):
+        _chk(lib().b2p_flux_estimator_indicator(self.h, _vp(flux_re), _vp(flux_im) if flux_im is not None else None, C.c_double(Et),
+                                                _vp(estimates)), self.ctx.h)
+
+    def stats(self):
+        nm, nit, its, conv = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().b2p_flux_estimator_stats(self.h, C.byref(nm), C.byref(nit), C.byref(its), C.byref(conv)), self.ctx.h)
+        return {"num_mult": nm.value, "num_mult_its": nit.value, "its": its.value, "converged": bool(conv.value)}
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b2p_flux_estimator_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class Eps:
     """The operator applications an outer eigen-solver asks for (ArpackEPSSolver::ApplyOp / ApplyOpB, linalg/arpack.cpp:631-674):
     host complex vectors in, host complex vectors out; operators, linear solve and work vectors stay on the device."""

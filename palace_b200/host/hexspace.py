@@ -467,3 +467,126 @@ def discrete_gradient_matrix(p: int) -> np.ndarray:
             m[c] = t
             G[l, m[0] + n * (m[1] + n * m[2])] = dC[ix[c], t]
     return G
+
+
+# --------------------------------------------------------------------------------------------
+# Raviart-Thomas space RT_{p-1} on hexahedra (the H(div) partner of ND_p: curl ND_p is contained in RT_{p-1}); used by the
+# flux error estimator (/root/reference/palace/linalg/errorestimator.cpp: B = curl E lives in the RT space of
+# RT_FECollection(p - 1)). Component c is CLOSED (p + 1 Gauss-Lobatto nodes) along axis c and OPEN (p Gauss-Legendre nodes) along
+# the other two; reference-to-physical map u = J u^ / det J.
+# --------------------------------------------------------------------------------------------
+
+
+def _rt_lex_layout(p):
+    """Lexicographic element dofs: list of (comp, i, j, k) in storage order (i fastest)."""
+    out = []
+    for c in range(3):
+        n = [p, p, p]
+        n[c] = p + 1
+        for k in range(n[2]):
+            for j in range(n[1]):
+                for i in range(n[0]):
+                    out.append((c, i, j, k))
+    return out
+
+
+def _perm_sign(t1, t2, n):
+    """+1 if (t1, t2, n) is an even permutation of (0, 1, 2)."""
+    return 1 if (t1, t2, n) in ((0, 1, 2), (1, 2, 0), (2, 0, 1)) else -1
+
+
+def build_rt_space(mesh: HexMesh, topo: HexTopology, p: int) -> HexSpace:
+    """Face dofs: p^2 normal-flux dofs per face in the face's canonical frame (origin = smallest vertex id, first axis towards
+    its smaller neighbour), positive along first x second; an element sees them with the sign of its local +n axis against
+    that normal (elements are positively oriented). Interior dofs: 3 p^2 (p - 1) per element."""
+    ne = mesh.ne
+    lay = _rt_lex_layout(p)
+    P = len(lay)
+    n_f, n_i = p * p, 3 * p * p * (p - 1)
+    off_i = topo.nface * n_f
+    ndofs = off_i + ne * n_i
+    gid = np.empty((ne, P), dtype=np.int64)
+    sgn = np.ones((ne, P), dtype=np.int8)
+    earange = np.arange(ne)
+    int_count = 0
+    ess = np.zeros(ndofs, dtype=bool)
+    bfaces = topo.face_nelem == 1
+    for l, (c, i, j, k) in enumerate(lay):
+        ix = [i, j, k]
+        if ix[c] in (0, p):
+            side = ix[c] // p
+            t1, t2 = _others(c)
+            a0 = topo.face_a0[:, c, side]
+            b0 = topo.face_b0[:, c, side]
+            sw = topo.face_swap[:, c, side]
+            u = np.where(a0 == 1, p - 1 - ix[t1], ix[t1])
+            v = np.where(b0 == 1, p - 1 - ix[t2], ix[t2])
+            s = np.where(sw, v, u)
+            t = np.where(sw, u, v)
+            gid[:, l] = topo.face_id[:, c, side] * n_f + s + p * t
+            # canonical normal = (+-e_t1) x (+-e_t2), exchanged under swap; e_t1 x e_t2 = perm(t1, t2, c) e_c
+            sg = _perm_sign(t1, t2, c) * np.where(a0 == 1, -1, 1) * np.where(b0 == 1, -1, 1) * np.where(sw, -1, 1)
+            sgn[:, l] = sg
+            onb = bfaces[topo.face_id[:, c, side]]
+            ess[gid[onb, l]] = True
+        else:
+            gid[:, l] = off_i + earange * n_i + int_count
+            int_count += 1
+    assert int_count == n_i
+    mult = np.bincount(gid.ravel(), minlength=ndofs)
+    return HexSpace("rt", p, ndofs, P, gid, sgn, np.arange(P, dtype=np.int64), np.nonzero(ess)[0], mult)
+
+
+def rt_hex_dense_interp(p: int, q1d: int) -> np.ndarray:
+    """interp[3][Q][P]: reference-space values of the lexicographic RT basis at the tensor Gauss-Legendre points (x fastest),
+    the layout of libCEED non-tensor bases (fem/libceed/basis.cpp:40-85)."""
+    t = tables_1d(p, q1d)
+    lay = _rt_lex_layout(p)
+    Q = q1d ** 3
+    out = np.zeros((3, Q, len(lay)))
+    for l, (c, i, j, k) in enumerate(lay):
+        tx = t.Bc[:, i] if c == 0 else t.Bo[:, i]
+        ty = t.Bc[:, j] if c == 1 else t.Bo[:, j]
+        tz = t.Bc[:, k] if c == 2 else t.Bo[:, k]
+        out[c, :, l] = np.einsum("c,b,a->cba", tz, ty, tx).ravel()
+    return out
+
+
+def nd_hex_dense_interp(p: int, q1d: int) -> np.ndarray:
+    """interp[3][Q][P] of the LEXICOGRAPHIC ND basis (open along the component's axis, closed along the others)."""
+    t = tables_1d(p, q1d)
+    lay = _nd_lex_layout(p)
+    Q = q1d ** 3
+    out = np.zeros((3, Q, len(lay)))
+    for l, (c, i, j, k) in enumerate(lay):
+        tx = t.Bo[:, i] if c == 0 else t.Bc[:, i]
+        ty = t.Bo[:, j] if c == 1 else t.Bc[:, j]
+        tz = t.Bo[:, k] if c == 2 else t.Bc[:, k]
+        out[c, :, l] = np.einsum("c,b,a->cba", tz, ty, tx).ravel()
+    return out
+
+
+def discrete_curl_matrix(p: int) -> np.ndarray:
+    """C[l_rt, m_nd]: the curl of ND shape function m expanded in the RT basis (both lexicographic), mfem ProjectCurl
+    semantics: (curl u)_c = d_a u_b - d_b u_a for (c, a, b) cyclic; the derivative of the closed basis along an axis is exactly
+    representable in the open basis of that axis (values at the Gauss-Legendre nodes)."""
+    op, _ = gauss_legendre(p)
+    cp = gauss_lobatto(p + 1)
+    _, dC = lagrange_table(cp, op)  # [p, p+1] closed-basis derivative at the open points
+    lay_nd = _nd_lex_layout(p)
+    rt_index = {key: l for l, key in enumerate(_rt_lex_layout(p))}
+    C = np.zeros((len(rt_index), len(lay_nd)))
+    for m, (b, i, j, k) in enumerate(lay_nd):          # ND function with component b
+        ix = [i, j, k]
+        for a in range(3):                             # derivative direction a != b
+            if a == b:
+                continue
+            c = 3 - a - b                              # the curl component that receives d_a u_b
+            sign = 1.0 if (c, a, b) in ((0, 1, 2), (1, 2, 0), (2, 0, 1)) else -1.0
+            # u_b is closed along a (a != b): d_a maps the closed index ix[a] onto the open indices along a; it stays open
+            # along b and closed along c -- exactly the RT component c layout
+            for t in range(p):
+                tgt = list(ix)
+                tgt[a] = t
+                C[rt_index[(c, tgt[0], tgt[1], tgt[2])], m] += sign * dC[t, ix[a]]
+    return C
