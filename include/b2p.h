@@ -512,6 +512,12 @@ typedef struct
   int64_t lsize;
 } b2p_vecfe_space_desc;
 typedef struct b2p_flux_estimator b2p_flux_estimator;
+/* VectorFEMassIntegrator on ONE table-described space: y = sum_e E^T B^T (w detJ P^T C P) B E x with the space's map P; coef
+ * [n_attr][9] per attribute or NULL (identity). The mass matrix `smooth_mass` of a FluxProjector whose smooth space has no
+ * sum-factorised operator here (Raviart-Thomas: GradFluxErrorEstimator, errorestimator.cpp:272-398, with the H(curl) space as
+ * the flux space and sqrt(eps), eps^(-1/2) as coef_disc, coef_smooth). Mult and AssembleDiagonal; single partition. */
+int b2p_operator_vecfe_mass(b2p_ctx *ctx, b2p_geom *geom, const b2p_vecfe_space_desc *space, int n_attr, const double *coef,
+                            b2p_operator **out);
 int b2p_flux_estimator_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_vecfe_space_desc *flux_space,
                               const b2p_vecfe_space_desc *smooth_space, int n_attr, const double *coef_flux, const double *coef_disc,
                               const double *coef_smooth, b2p_operator *smooth_mass, double tol, int max_it, b2p_flux_estimator **out);
@@ -521,6 +527,9 @@ int b2p_flux_estimator_project(b2p_flux_estimator *e, const double *flux_dofs, d
 int b2p_flux_estimator_integrate(b2p_flux_estimator *e, const double *flux_dofs, const double *smooth_dofs, double *estimates);
 /* CurlFluxErrorEstimator::AddErrorIndicator: estimates[ne] = sqrt(s (eta_K^2(re) + eta_K^2(im))); flux_im may be NULL */
 int b2p_flux_estimator_indicator(b2p_flux_estimator *e, const double *flux_re, const double *flux_im, double Et, double *estimates);
+/* estimates[i] = sqrt(s estimates[i]): last step when several flux terms are added before the square root
+ * (TimeDependentFluxErrorEstimator: project + integrate of both estimators into one array, errorestimator.cpp:531-545) */
+int b2p_flux_estimator_sqrt_scale(b2p_ctx *ctx, int64_t n, double s, double *estimates);
 int b2p_flux_estimator_stats(b2p_flux_estimator *e, int *num_mult, int *num_mult_its, int *last_its, int *converged);
 void b2p_flux_estimator_destroy(b2p_flux_estimator *e);
 

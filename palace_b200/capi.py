@@ -912,22 +912,42 @@ class VecFESpaceDesc(C.Structure):
 MAP_HCURL, MAP_HDIV = 1, 2
 
 
+def _vecfe_desc(sp, keep):
+    interp = np.ascontiguousarray(sp["interp"], dtype=np.float64)
+    idx = np.ascontiguousarray(sp["idx"], dtype=np.int32)
+    ori = None if sp.get("orient") is None else np.ascontiguousarray(sp["orient"], dtype=np.int8)
+    keep.extend([interp, idx, ori])
+    return VecFESpaceDesc(int(sp["P"]), int(sp["map_type"]), interp.ctypes.data, idx.ctypes.data, None if ori is None else ori.ctypes.data,
+                          int(sp["lsize"]))
+
+
+def vecfe_mass_operator(ctx, geom, space, coef=None):
+    """b2p_operator_vecfe_mass: the mass operator of a table-described vector finite element space (e.g. Raviart-Thomas)."""
+    keep = []
+    d = _vecfe_desc(space, keep)
+    n_attr, cptr = 0, None
+    if coef is not None:
+        c = np.ascontiguousarray(coef, dtype=np.float64).reshape(-1, 9)
+        keep.append(c)
+        n_attr, cptr = int(c.shape[0]), _ptr(c)
+    h = C.c_void_p()
+    _chk(lib().b2p_operator_vecfe_mass(ctx.h, geom.h, C.byref(d), n_attr, cptr, C.byref(h)), ctx.h)
+    A = Operator(ctx, h)
+    A._keep_vecfe = [geom, keep]
+    return A
+
+
+def flux_sqrt_scale(ctx, n, s, estimates):
+    _chk(lib().b2p_flux_estimator_sqrt_scale(ctx.h, C.c_int64(n), C.c_double(s), _vp(estimates)), ctx.h)
+
+
 class FluxEstimator:
     """CurlFluxErrorEstimator (linalg/errorestimator.cpp): flux projection M H = Flux B and the element-wise error integrals."""
 
     def __init__(self, ctx, geom, flux_space, smooth_space, coef_flux, coef_disc, coef_smooth, smooth_mass, tol=1e-6, max_it=500):
         self.ctx = ctx
         keep = []
-
-        def desc(sp):
-            interp = np.ascontiguousarray(sp["interp"], dtype=np.float64)
-            idx = np.ascontiguousarray(sp["idx"], dtype=np.int32)
-            ori = None if sp.get("orient") is None else np.ascontiguousarray(sp["orient"], dtype=np.int8)
-            keep.extend([interp, idx, ori])
-            return VecFESpaceDesc(int(sp["P"]), int(sp["map_type"]), interp.ctypes.data, idx.ctypes.data,
-                                  None if ori is None else ori.ctypes.data, int(sp["lsize"]))
-
-        d1, d2 = desc(flux_space), desc(smooth_space)
+        d1, d2 = _vecfe_desc(flux_space, keep), _vecfe_desc(smooth_space, keep)
         cf = np.ascontiguousarray(coef_flux, dtype=np.float64).reshape(-1, 9)
         cd = np.ascontiguousarray(coef_disc, dtype=np.float64).reshape(-1, 9)
         cs = np.ascontiguousarray(coef_smooth, dtype=np.float64).reshape(-1, 9)

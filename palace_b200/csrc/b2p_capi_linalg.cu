@@ -23,6 +23,12 @@ namespace b2p
 {
 Solver *solver_of(b2p_solver *s) { return s ? s->s.get() : nullptr; }
 Operator *operator_of(b2p_operator *A) { return A ? A->op.get() : nullptr; }
+b2p_operator *wrap_operator(std::unique_ptr<Operator> &&op)  // (handles of operators built in other translation units)
+{
+  auto *h = new b2p_operator;
+  h->op = std::move(op);
+  return h;
+}
 }  // namespace b2p
 
 #define B2P_TRY(ctx, stmt)                                   \

@@ -28,6 +28,7 @@ struct b2p_operator;
 namespace b2p
 {
 Operator *operator_of(b2p_operator *A);
+b2p_operator *wrap_operator(std::unique_ptr<Operator> &&op);
 }
 
 namespace b2p
@@ -183,6 +184,7 @@ public:
   {
     vec::set(ctx, y, height, 0.0);
     const size_t shmem = (size_t)(std::max(trial.P, test.P) + 3 * geom->Q) * sizeof(double);
+    if (shmem > 48 * 1024) cudaFuncSetAttribute(mixed_mass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
     B2P_LAUNCH(mixed_mass_kernel, geom->ne, FLUX_NT, shmem, ctx->stream, geom->ne, geom->Q, geom->q1d, trial, test,
                (const double *)geom->qd, d_coef, x, y);
   }
@@ -190,6 +192,87 @@ public:
   VecFESpace trial, test;
   const double *d_coef;
 };
+
+// diag[|i|] += sum_q phi_i^T D phi_i (the signs of the restriction cancel)
+__global__ void vecfe_mass_diag_kernel(int ne, int Q, int q1d, VecFESpace sp, const double *__restrict__ qd, const double *__restrict__ coef,
+                                       double *diag)
+{
+  const int e = blockIdx.x;
+  if (e >= ne) return;
+  const double *C = coef + (size_t)e * 9;
+  for (int i = threadIdx.x; i < sp.P; i += blockDim.x)
+  {
+    double s = 0.0;
+    for (int q = 0; q < Q; q++)
+    {
+      const int slot = q1d > 0 ? qslot_of(q1d, q) : q;
+      const double *g = qd + (size_t)e * 10 * Q + slot;
+      double A[9], M[9], Cm[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++)
+      {
+        A[k] = g[(1 + k) * Q];
+        Cm[k] = C[k];
+      }
+      piola_matrix(sp.map, A, M);
+      const double u[3] = {sp.interp[(size_t)(0 * Q + q) * sp.P + i], sp.interp[(size_t)(1 * Q + q) * sp.P + i],
+                           sp.interp[(size_t)(2 * Q + q) * sp.P + i]};
+      double t[3], z[3];
+      Ax33(M, u, t);
+      Ax33(Cm, t, z);
+      s += g[0] * (t[0] * z[0] + t[1] * z[1] + t[2] * z[2]);
+    }
+    const int32_t gi = sp.sidx[(size_t)e * sp.P + i];
+    atomicAdd(diag + (gi >= 0 ? gi : -1 - gi), s);
+  }
+}
+
+// VectorFEMassIntegrator on ONE table-described space (the mass matrix of a FluxProjector's smooth space when that space has no
+// sum-factorised operator in this library, e.g. Raviart-Thomas); owns its device arrays
+class VecFEMassOperator : public MixedMassOperator
+{
+public:
+  VecFEMassOperator(b2p_ctx *c, b2p_geom *g, const VecFESpace &sp, double *d_coef_owned)
+    : MixedMassOperator(c, g, sp, sp, d_coef_owned), owned_geom(g), owned_coef(d_coef_owned)
+  {
+    g->refcount++;
+  }
+  ~VecFEMassOperator() override
+  {
+    cudaFree(trial.interp);
+    cudaFree(trial.sidx);
+    cudaFree(owned_coef);
+    b2p_geom_destroy(owned_geom);
+  }
+  void AssembleDiagonal(double *d) const override
+  {
+    vec::set(ctx, d, height, 0.0);
+    B2P_LAUNCH(vecfe_mass_diag_kernel, geom->ne, FLUX_NT, 0, ctx->stream, geom->ne, geom->Q, geom->q1d, trial, (const double *)geom->qd,
+               d_coef, d);
+  }
+  b2p_geom *owned_geom;
+  double *owned_coef;
+};
+
+int upload_coef(b2p_ctx *ctx, const b2p_geom *geom, int n_attr, const double *coef, double **out)
+{
+  const int ne = geom->ne;
+  std::vector<double> c((size_t)ne * 9, 0.0);
+  if (!coef)
+    for (int el = 0; el < ne; el++) c[(size_t)el * 9] = c[(size_t)el * 9 + 4] = c[(size_t)el * 9 + 8] = 1.0;
+  else
+  {
+    std::vector<int32_t> attr(ne);
+    B2P_CUDA(ctx, cudaMemcpy(attr.data(), geom->attr, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost));
+    for (int el = 0; el < ne; el++)
+    {
+      const int a = attr[el] - 1;  // attributes are 1-based
+      B2P_CHECK(ctx, a >= 0 && a < n_attr, B2P_ERR_ARG, "element %d has attribute %d outside 1..%d", el, a + 1, n_attr);
+      for (int i = 0; i < 9; i++) c[(size_t)el * 9 + i] = coef[(size_t)a * 9 + i];
+    }
+  }
+  return upload(ctx, c.data(), c.size(), out);
+}
 
 int upload_space(b2p_ctx *ctx, const b2p_vecfe_space_desc *d, int ne, int Q, VecFESpace *out)
 {
@@ -245,6 +328,32 @@ struct b2p_flux_estimator
 extern "C"
 {
 
+int b2p_operator_vecfe_mass(b2p_ctx *ctx, b2p_geom *geom, const b2p_vecfe_space_desc *space, int n_attr, const double *coef,
+                            b2p_operator **out)
+{
+  B2P_CHECK(ctx, ctx && geom && space && out && (!coef || n_attr > 0), B2P_ERR_ARG, "b2p_operator_vecfe_mass: bad argument");
+  B2P_CHECK(ctx, ctx->nranks == 1, B2P_ERR_UNSUPPORTED, "b2p_operator_vecfe_mass: partitioned spaces are not supported yet");
+  VecFESpace sp;
+  int rc = upload_space(ctx, space, geom->ne, geom->Q, &sp);
+  if (rc) return rc;
+  double *d_coef = nullptr;
+  if ((rc = upload_coef(ctx, geom, n_attr, coef, &d_coef))) return rc;
+  *out = wrap_operator(std::make_unique<VecFEMassOperator>(ctx, geom, sp, d_coef));
+  return B2P_SUCCESS;
+}
+
+// estimates[i] = sqrt(s * estimates[i]): the last step of the estimators that add several flux terms before the square root
+// (TimeDependentFluxErrorEstimator, errorestimator.cpp:531-545)
+int b2p_flux_estimator_sqrt_scale(b2p_ctx *ctx, int64_t n, double s, double *estimates)
+{
+  if (!ctx || !estimates || n < 0) return B2P_ERR_ARG;
+  if (n == 0) return B2P_SUCCESS;
+  B2P_LAUNCH(sqrt_scale_kernel, (unsigned)((n + 255) / 256), 256, 0, ctx->stream, n, s, estimates);
+  cudaError_t err = cudaPeekAtLastError();
+  B2P_CHECK(ctx, err == cudaSuccess, B2P_ERR_CUDA, "b2p_flux_estimator_sqrt_scale: %s", cudaGetErrorString(err));
+  return B2P_SUCCESS;
+}
+
 int b2p_flux_estimator_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_vecfe_space_desc *flux_space,
                               const b2p_vecfe_space_desc *smooth_space, int n_attr, const double *coef_flux, const double *coef_disc,
                               const double *coef_smooth, b2p_operator *smooth_mass, double tol, int max_it, b2p_flux_estimator **out)
@@ -265,23 +374,9 @@ int b2p_flux_estimator_create(b2p_ctx *ctx, b2p_geom *geom, const b2p_vecfe_spac
   if ((rc = upload_space(ctx, flux_space, ne, Q, &e->flux))) return rc;
   if ((rc = upload_space(ctx, smooth_space, ne, Q, &e->smooth))) return rc;
   // per-element coefficient matrices from the per-attribute tables (coeff/coeff_qf.h: attribute -> material -> matrix)
-  std::vector<int32_t> attr(ne);
-  B2P_CUDA(ctx, cudaMemcpy(attr.data(), geom->attr, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost));
-  std::vector<double> cf((size_t)ne * 9), cd((size_t)ne * 9), cs((size_t)ne * 9);
-  for (int el = 0; el < ne; el++)
-  {
-    const int a = attr[el] - 1;  // attributes are 1-based
-    B2P_CHECK(ctx, a >= 0 && a < n_attr, B2P_ERR_ARG, "b2p_flux_estimator_create: element %d has attribute %d outside 1..%d", el, a + 1, n_attr);
-    for (int i = 0; i < 9; i++)
-    {
-      cf[(size_t)el * 9 + i] = coef_flux[(size_t)a * 9 + i];
-      cd[(size_t)el * 9 + i] = coef_disc[(size_t)a * 9 + i];
-      cs[(size_t)el * 9 + i] = coef_smooth[(size_t)a * 9 + i];
-    }
-  }
-  if ((rc = upload(ctx, cf.data(), cf.size(), &e->d_coef_flux))) return rc;
-  if ((rc = upload(ctx, cd.data(), cd.size(), &e->d_coef_disc))) return rc;
-  if ((rc = upload(ctx, cs.data(), cs.size(), &e->d_coef_smooth))) return rc;
+  if ((rc = upload_coef(ctx, geom, n_attr, coef_flux, &e->d_coef_flux))) return rc;
+  if ((rc = upload_coef(ctx, geom, n_attr, coef_disc, &e->d_coef_disc))) return rc;
+  if ((rc = upload_coef(ctx, geom, n_attr, coef_smooth, &e->d_coef_smooth))) return rc;
   e->Flux = std::make_unique<MixedMassOperator>(ctx, geom, e->flux, e->smooth, e->d_coef_flux);
   e->M = M;
   // ConfigureLinearSolver(use_mg = false) (errorestimator.cpp:63-109)
@@ -325,6 +420,7 @@ int b2p_flux_estimator_integrate(b2p_flux_estimator *e, const double *flux_dofs,
   b2p_ctx *ctx = e->ctx;
   const b2p_geom *g = e->geom;
   const size_t shmem = (size_t)(e->flux.P + e->smooth.P + 6 * g->Q + FLUX_NT) * sizeof(double);
+  if (shmem > 48 * 1024) cudaFuncSetAttribute(flux_error_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
   B2P_LAUNCH(flux_error_kernel, g->ne, FLUX_NT, shmem, ctx->stream, g->ne, g->Q, g->q1d, e->flux, e->smooth, (const double *)g->qd,
              (const double *)e->d_coef_disc, (const double *)e->d_coef_smooth, flux_dofs, smooth_dofs, estimates);
   cudaError_t err = cudaPeekAtLastError();
@@ -347,10 +443,7 @@ int b2p_flux_estimator_indicator(b2p_flux_estimator *e, const double *flux_re, c
     if ((rc = b2p_flux_estimator_project(e, part, e->H.p))) return rc;
     if ((rc = b2p_flux_estimator_integrate(e, part, e->H.p, estimates))) return rc;
   }
-  B2P_LAUNCH(sqrt_scale_kernel, (ne + 255) / 256, 256, 0, ctx->stream, (int64_t)ne, Et > 0.0 ? 0.5 / Et : 1.0, estimates);
-  cudaError_t err = cudaPeekAtLastError();
-  B2P_CHECK(ctx, err == cudaSuccess, B2P_ERR_CUDA, "b2p_flux_estimator_indicator: %s", cudaGetErrorString(err));
-  return B2P_SUCCESS;
+  return b2p_flux_estimator_sqrt_scale(ctx, ne, Et > 0.0 ? 0.5 / Et : 1.0, estimates);
 }
 
 int b2p_flux_estimator_stats(b2p_flux_estimator *e, int *num_mult, int *num_mult_its, int *last_its, int *converged)

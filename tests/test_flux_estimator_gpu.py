@@ -147,6 +147,68 @@ def test_smooth_flux_has_no_error_on_an_affine_mesh(b2p_ctx, setup):
     assert (ed.cpu().numpy() < 1e-9 * np.sqrt(vol * (c @ c))).all()
 
 
+def test_table_described_mass_operator_and_grad_flux_configuration(b2p_ctx, setup):
+    """b2p_operator_vecfe_mass on the Raviart-Thomas space (Mult, diagonal) against the oracle matrix, and the estimator with the
+    roles of GradFluxErrorEstimator (errorestimator.cpp:272-398): discontinuous flux eps E with E in the ND space, smooth flux D in
+    the RT space, M = RT mass matrix, integrand |eps^(-1/2) D - eps^(1/2) E|^2 (f_apply_hcurlhdiv_error_33)."""
+    from palace_b200 import capi
+
+    s = setup
+    prob, nd, rt, p, o = s["prob"], s["nd"], s["rt"], s["p"], s["o"]
+    geom = s["keep"][2]
+    sp_rt = dict(P=rt.P, map_type=capi.MAP_HDIV, interp=hs.rt_hex_dense_interp(p, prob.q1d), idx=rt.lex_gid, orient=rt.lex_sign, lsize=rt.ndofs)
+    sp_nd = dict(P=nd.P, map_type=capi.MAP_HCURL, interp=hs.nd_hex_dense_interp(p, prob.q1d), idx=nd.lex_gid, orient=nd.lex_sign, lsize=nd.ndofs)
+    Mrt = capi.vecfe_mass_operator(b2p_ctx, geom, sp_rt)
+    ident = [np.eye(3)] * prob.mesh.ne
+    Mo = E.mixed_mass_matrix(o["qd"], o["rt_interp"], E.HDIV, o["idx_r"], o["ori_r"], rt.ndofs, o["rt_interp"], E.HDIV, o["idx_r"], o["ori_r"],
+                             rt.ndofs, ident)
+    rng = np.random.default_rng(57)
+    x = rng.standard_normal(rt.ndofs)
+    yd = torch.empty(rt.ndofs, dtype=torch.float64, device="cuda")
+    Mrt.mult(_dev(x), yd)
+    assert _rel(yd.cpu().numpy(), Mo @ x) < 1e-12
+    dd = torch.empty(rt.ndofs, dtype=torch.float64, device="cuda")
+    Mrt.assemble_diagonal(dd)
+    assert _rel(dd.cpu().numpy(), Mo.diagonal()) < 1e-12
+    # the same operator with a coefficient table agrees with the oracle's coefficient version
+    n_attr = 3
+    am, mc = cf.test_suite_coefficient(n_attr, "matrix")
+    eps = np.stack([mc[am[a]] for a in range(n_attr)])
+    c_eps = np.stack([m.ravel(order="F") for m in eps])
+    attr = prob.mesh.attr - 1
+    Mo_eps = E.mixed_mass_matrix(o["qd"], o["rt_interp"], E.HDIV, o["idx_r"], o["ori_r"], rt.ndofs, o["rt_interp"], E.HDIV, o["idx_r"], o["ori_r"],
+                                 rt.ndofs, [E._mat33(c_eps[a]) for a in attr])
+    Mrt_eps = capi.vecfe_mass_operator(b2p_ctx, geom, sp_rt, c_eps)
+    Mrt_eps.mult(_dev(x), yd)
+    assert _rel(yd.cpu().numpy(), Mo_eps @ x) < 1e-12
+    # GradFlux roles: flux space ND with eps, smooth space RT
+    c_disc = np.stack([E.spd_power(m, 0.5).ravel(order="F") for m in eps])
+    c_smooth = np.stack([E.spd_power(m, -0.5).ravel(order="F") for m in eps])
+    est = capi.FluxEstimator(b2p_ctx, geom, sp_nd, sp_rt, c_eps, c_disc, c_smooth, Mrt, tol=1e-13, max_it=4000)
+    Ev = rng.standard_normal(nd.ndofs)
+    celem = lambda tab: [E._mat33(tab[a]) for a in attr]
+    F = E.mixed_mass_matrix(o["qd"], o["nd_interp"], E.HCURL, o["idx_n"], o["ori_n"], nd.ndofs, o["rt_interp"], E.HDIV, o["idx_r"], o["ori_r"],
+                            rt.ndofs, celem(c_eps))
+    D_ref = spla.spsolve(Mo.tocsc(), F @ Ev)
+    eta2 = E.element_errors(o["qd"], o["nd_interp"], E.HCURL, o["idx_n"], o["ori_n"], Ev, celem(c_disc), o["rt_interp"], E.HDIV, o["idx_r"],
+                            o["ori_r"], D_ref, celem(c_smooth))
+    Dd = torch.zeros(rt.ndofs, dtype=torch.float64, device="cuda")
+    est.project(_dev(Ev), Dd)
+    assert est.stats()["converged"]
+    assert _rel(Dd.cpu().numpy(), D_ref) < 1e-9
+    ed = torch.zeros(prob.mesh.ne, dtype=torch.float64, device="cuda")
+    est.integrate(_dev(Ev), Dd, ed)
+    assert _rel(ed.cpu().numpy(), eta2) < 1e-8
+    # TimeDependentFluxErrorEstimator: both flux terms in one array, then one square root
+    B = curl_dofs(nd, rt, rng.standard_normal(nd.ndofs))
+    Hd = torch.zeros(nd.ndofs, dtype=torch.float64, device="cuda")
+    s["est"].project(_dev(B), Hd)
+    s["est"].integrate(_dev(B), Hd, ed)
+    _, e2c = oracle_estimates(s, B)
+    capi.flux_sqrt_scale(b2p_ctx, prob.mesh.ne, 0.25, ed)
+    assert _rel(ed.cpu().numpy(), np.sqrt(0.25 * (eta2 + e2c))) < 1e-8
+
+
 def test_argument_checks(b2p_ctx, setup):
     from palace_b200 import capi
 
