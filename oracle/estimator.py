@@ -8,8 +8,11 @@ assembled matrices (no product code is used here; only tests import this module)
   element error integrand               /root/reference/palace/fem/qfunctions/33/hcurlhdiv_error_33_qf.h:46-76
   summation over the element            /root/reference/palace/fem/libceed/integrator.cpp:560-574 (all-ones basis)
 
-Parity unpinned: the reference has no stored vectors for the estimator (the regression suite compares error-indicator statistics
-of whole solves); this module follows the reference's formulas term by term."""
+Parity: the pointwise arithmetic (mixed mass D, both element error integrands) is pinned to the reference's own QFunction headers
+compiled in place (oracle/_ref, oracle/ref_qf.cpp) through tests/golden/qf_mixed_golden.npz
+(tests/test_oracle_golden.py::test_estimator_oracle_matches_reference_golden, 1e-14). The reference stores no vectors for whole
+estimator runs (its regression suite compares error-indicator statistics of full solves), so the projection + summation around that
+arithmetic follows errorestimator.cpp term by term without a stored golden."""
 import numpy as np
 import scipy.sparse as sp
 

@@ -162,8 +162,13 @@ enum Kind
   CURLCURL = 0,       // hdiv_33 on curl           (integ/curlcurl.cpp:47-52)
   ND_MASS = 1,        // hcurl_33 on interp        (integ/vecfemass.cpp:72-105)
   CURLCURL_MASS = 2,  // hdivmass_33 (pair ctx)    (integ/curlcurlmass.cpp:37-44)
-  H1_DIFFUSION = 3    // hcurl_33 on grad          (integ/diffusion.cpp:37-42)
+  H1_DIFFUSION = 3,   // hcurl_33 on grad          (integ/diffusion.cpp:37-42)
+  ND_WEAKCURL = 4,    // hcurlhdiv_33: interp -> curl test values   (integ/mixedveccurl.cpp:68-117, MixedVectorWeakCurlIntegrator)
+  ND_MIXEDCURL = 5    // hdivhcurl_33: curl -> interp test values   (integ/mixedveccurl.cpp:23-66, MixedVectorCurlIntegrator)
 };
+// which reference-space fields a kind evaluates (trial) and tests with: value part u / v, derivative part c / w
+inline bool needs_u(int kind) { return kind == ND_MASS || kind == CURLCURL_MASS || kind == ND_WEAKCURL || kind == ND_MIXEDCURL; }
+inline bool needs_c(int kind) { return kind != ND_MASS; }
 
 // One quadrature point of D. qd = {attr, wdetJ, adjJt[9]}; u = value part, c = derivative part.
 inline void apply_D(int kind, const IntScalar *ctx, const double qd[11], const double u[3], const double c[3],
@@ -194,6 +199,22 @@ inline void apply_D(int kind, const IntScalar *ctx, const double qd[11], const d
     adjJt33(adjJt, J);                     // J/detJ = adj(adjJt/detJ)^T   (hdiv_33_qf.h:24)
     multAtBCx(J, coeff, J, c, w);
     for (int d = 0; d < 3; d++) w[d] *= wdetJ;
+  }
+  if (kind == ND_WEAKCURL || kind == ND_MIXEDCURL)
+  {
+    // the two spaces meet at the point: an H(curl) value maps with adjJt / detJ = J^-T, a curl (H(div)) with J / detJ
+    double J[9];
+    coeff_unpack3(ctx, attr, coeff);
+    adjJt33(adjJt, J);
+    if (kind == ND_WEAKCURL)
+      multAtBCx(J, coeff, adjJt, u, w);  // hcurlhdiv_33_qf.h:24 (f_apply_hcurlhdiv_33): trial value -> test curl
+    else
+      multAtBCx(adjJt, coeff, J, c, v);  // hcurlhdiv_33_qf.h:48 (f_apply_hdivhcurl_33): trial curl -> test value
+    for (int d = 0; d < 3; d++)
+    {
+      v[d] *= wdetJ;
+      w[d] *= wdetJ;
+    }
   }
 }
 
@@ -390,8 +411,8 @@ void orc_apply_D(int kind, const void *ctx, int Q, const double *qdata, const do
 void orc_apply_add(int kind, int ne, int P, int Q, const double *interp, const double *deriv, const int *idx,
                    const signed char *orient, const double *qdata, const void *ctx, const double *x, double *y)
 {
-  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
-  const bool need_c = (kind != ND_MASS);
+  const bool need_u = needs_u(kind);
+  const bool need_c = needs_c(kind);
   std::vector<double> ue(P), ye(P), u(3 * Q), c(3 * Q), v(3 * Q), w(3 * Q);
   for (int e = 0; e < ne; e++)
   {
@@ -444,8 +465,8 @@ void orc_apply_add(int kind, int ne, int P, int Q, const double *interp, const d
 void orc_apply_add_co(int kind, int ne, int P, int Q, const double *interp, const double *deriv, const int *idx,
                       const signed char *co, const double *qdata, const void *ctx, const double *x, double *y)
 {
-  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
-  const bool need_c = (kind != ND_MASS);
+  const bool need_u = needs_u(kind);
+  const bool need_c = needs_c(kind);
   std::vector<double> xe(P), ue(P), ye(P), u(3 * Q), c(3 * Q), v(3 * Q), w(3 * Q);
   for (int e = 0; e < ne; e++)
   {
@@ -510,8 +531,8 @@ void orc_apply_add_co(int kind, int ne, int P, int Q, const double *interp, cons
 void orc_element_matrices(int kind, int ne, int P, int Q, const double *interp, const double *deriv,
                           const signed char *orient, const double *qdata, const void *ctx, double *Ae)
 {
-  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
-  const bool need_c = (kind != ND_MASS);
+  const bool need_u = needs_u(kind);
+  const bool need_c = needs_c(kind);
   std::vector<double> u(3 * Q), c(3 * Q), v(3 * Q), w(3 * Q);
   for (int e = 0; e < ne; e++)
   {
@@ -545,8 +566,8 @@ void orc_element_matrices(int kind, int ne, int P, int Q, const double *interp, 
 void orc_diag_add(int kind, int ne, int P, int Q, const double *interp, const double *deriv, const int *idx,
                   const double *qdata, const void *ctx, double *diag)
 {
-  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
-  const bool need_c = (kind != ND_MASS);
+  const bool need_u = needs_u(kind);
+  const bool need_c = needs_c(kind);
   for (int e = 0; e < ne; e++)
     for (int i = 0; i < P; i++)
     {
@@ -580,8 +601,8 @@ void orc_apply_add_mt(int nthreads, int kind, int ne, int P, int Q, const double
     orc_apply_add(kind, ne, P, Q, interp, deriv, idx, orient, qdata, ctx, x, y);
     return;
   }
-  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
-  const bool need_c = (kind != ND_MASS);
+  const bool need_u = needs_u(kind);
+  const bool need_c = needs_c(kind);
   std::vector<double> Ye((size_t)ne * P);
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; t++)
@@ -827,8 +848,8 @@ void orc_apply_add_blocked(void *pool, void *setup, int kind, int ne, int P, int
 {
   auto *pl = (OrcPool *)pool;
   auto *bs = (OrcBlocked *)setup;
-  const bool need_u = (kind == ND_MASS || kind == CURLCURL_MASS);
-  const bool need_c = (kind != ND_MASS);
+  const bool need_u = needs_u(kind);
+  const bool need_c = needs_c(kind);
   const int nblk = (ne + BLK - 1) / BLK, R = 3 * Q;
   std::atomic<int> next{0};
   pl->run(

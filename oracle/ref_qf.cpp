@@ -3,6 +3,7 @@
 //   palace/fem/qfunctions/33/{geom,hdiv,hcurl,hdivmass,hdiv_build,hcurl_build,hdivmass_build}_33_qf.h
 //   palace/fem/qfunctions/apply/apply_33_qf.h
 //   palace/fem/qfunctions/32/{geom,hcurl}_32_qf.h   (boundary integrators)
+//   palace/fem/qfunctions/33/{hcurlhdiv,hcurlhdiv_error}_33_qf.h   (mixed curl / weak curl integrators, flux error estimators)
 // behind the minimal libCEED macro shim below. Used only to pin oracle.cpp's restatement of the
 // pointwise arithmetic (tests/test_oracle_ref.py). The libCEED operator/basis/restriction layer and
 // MFEM are un-vendored, so this is the only part of the reference path that compiles here.
@@ -23,6 +24,9 @@ typedef int CeedInt;
 // boundary (2-D elements embedded in 3-D) geometry factors and the H(curl) mass QFunction
 #include "fem/qfunctions/32/geom_32_qf.h"
 #include "fem/qfunctions/32/hcurl_32_qf.h"
+// mixed H(curl) / H(div) mass (MixedVectorCurl / MixedVectorWeakCurl integrators, FluxProjector) and the element error integrands
+#include "fem/qfunctions/33/hcurlhdiv_33_qf.h"
+#include "fem/qfunctions/33/hcurlhdiv_error_33_qf.h"
 
 extern "C"
 {
@@ -82,5 +86,32 @@ int ref_build_hdivmass_33(void *ctx, int Q, const double *qdata, double *qd)
   const double *in[1] = {qdata};
   double *out[1] = {qd};
   return f_build_hdivmass_33(ctx, Q, in, out);
+}
+// v = w detJ (J / detJ)^T C (J^-T) u: H(curl) trial values, H(div) test values (hcurlhdiv_33_qf.h:10-31)
+int ref_apply_hcurlhdiv_33(void *ctx, int Q, const double *qdata, const double *u, double *v)
+{
+  const double *in[2] = {qdata, u};
+  double *out[1] = {v};
+  return f_apply_hcurlhdiv_33(ctx, Q, in, out);
+}
+// v = w detJ (J^-T)^T C (J / detJ) u: H(div) trial values, H(curl) test values (hcurlhdiv_33_qf.h:33-55)
+int ref_apply_hdivhcurl_33(void *ctx, int Q, const double *qdata, const double *u, double *v)
+{
+  const double *in[2] = {qdata, u};
+  double *out[1] = {v};
+  return f_apply_hdivhcurl_33(ctx, Q, in, out);
+}
+// v[Q] = w detJ |C2 P2 u2 - C1 P1 u1|^2 with a pair context (hcurlhdiv_error_33_qf.h): u1 H(curl) / u2 H(div) and the reverse
+int ref_apply_hcurlhdiv_error_33(void *ctx, int Q, const double *qdata, const double *u1, const double *u2, double *v)
+{
+  const double *in[3] = {qdata, u1, u2};
+  double *out[1] = {v};
+  return f_apply_hcurlhdiv_error_33(ctx, Q, in, out);
+}
+int ref_apply_hdivhcurl_error_33(void *ctx, int Q, const double *qdata, const double *u1, const double *u2, double *v)
+{
+  const double *in[3] = {qdata, u1, u2};
+  double *out[1] = {v};
+  return f_apply_hdivhcurl_error_33(ctx, Q, in, out);
 }
 }

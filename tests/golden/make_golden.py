@@ -89,8 +89,44 @@ def main32():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main_mixed():
+    """tests/golden/qf_mixed_golden.npz: the reference's mixed H(curl) / H(div) QFunctions (qfunctions/33/hcurlhdiv_33_qf.h:
+    MixedVectorWeakCurl / MixedVectorCurl integrators and the FluxProjector's mixed mass) and the element error integrands of
+    the flux error estimators (hcurlhdiv_error_33_qf.h, pair context) on the seeded q-data of qf_golden.npz."""
+    ref = O.ref()
+    assert ref is not None, "oracle/_ref not built (needs /root/reference)"
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "qf_golden.npz"))
+    rng = np.random.default_rng(20260925)
+    qdata = np.ascontiguousarray(G["qdata"])
+    Q = qdata.shape[1]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_attr = 5
+    am, mc = cf.test_suite_coefficient(n_attr, "matrix")
+    mc = mc + 0.05 * rng.random(mc.shape)  # non-symmetric: the two QFunctions place the coefficient differently
+    ctx_weak = cf.coeff_ctx(am, mc, a=-1.0)                                # MixedVectorWeakCurlIntegrator scales by -1
+    ctx_curl = cf.coeff_ctx(am, mc, a=1.0, transpose=True)                 # MixedVectorCurlIntegrator(Q, transpose = true)
+    ctx_err = cf.coeff_ctx_pair(cf.coeff_ctx(am, mc, a=1.0), cf.coeff_ctx(am, mc[::-1].copy(), a=0.8))
+    u1 = np.ascontiguousarray(rng.random((3, Q)) - 0.5)
+    u2 = np.ascontiguousarray(rng.random((3, Q)) - 0.5)
+    v = np.empty((3, Q)); s = np.empty(Q)
+    out = dict(ctx_weak=ctx_weak, ctx_curl=ctx_curl, ctx_err=ctx_err, u1=u1, u2=u2)
+    assert ref.ref_apply_hcurlhdiv_33(p(ctx_weak), Q, p(qdata), p(u1), p(v)) == 0
+    out["hcurlhdiv_v"] = v.copy()
+    assert ref.ref_apply_hdivhcurl_33(p(ctx_curl), Q, p(qdata), p(u2), p(v)) == 0
+    out["hdivhcurl_v"] = v.copy()
+    assert ref.ref_apply_hcurlhdiv_error_33(p(ctx_err), Q, p(qdata), p(u1), p(u2), p(s)) == 0
+    out["hcurlhdiv_error"] = s.copy()
+    assert ref.ref_apply_hdivhcurl_error_33(p(ctx_err), Q, p(qdata), p(u1), p(u2), p(s)) == 0
+    out["hdivhcurl_error"] = s.copy()
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "qf_mixed_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "32":
         main32()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mixed":
+        main_mixed()
     else:
         main()
