@@ -44,7 +44,12 @@ enum
   B2P_CURLCURL = 0,      /* CurlCurlIntegrator        -> f_apply_hdiv_33      (integ/curlcurl.cpp:47-52)     */
   B2P_ND_MASS = 1,       /* VectorFEMassIntegrator    -> f_apply_hcurl_33     (integ/vecfemass.cpp:72-105)   */
   B2P_CURLCURL_MASS = 2, /* CurlCurlMassIntegrator    -> f_apply_hdivmass_33  (integ/curlcurlmass.cpp:37-44) */
-  B2P_H1_DIFFUSION = 3   /* DiffusionIntegrator       -> f_apply_hcurl_33 on grad (integ/diffusion.cpp:37-42) */
+  B2P_H1_DIFFUSION = 3,  /* DiffusionIntegrator       -> f_apply_hcurl_33 on grad (integ/diffusion.cpp:37-42) */
+  /* The Floquet-periodic terms on one ND space (models/spaceoperator.cpp:305-309); NOT symmetric; dense-basis operators only
+   * (b2p_op_create_dense with both tables; hexahedra enter with their dense tables). One coefficient context each, built by the
+   * caller as the reference's integrators do (PopulateCoefficientContext with a = -1 for the weak curl, transpose for the curl): */
+  B2P_ND_WEAKCURL = 4,   /* MixedVectorWeakCurlIntegrator: values -> curls,  f_apply_hcurlhdiv_33 (integ/mixedveccurl.cpp:68-117) */
+  B2P_ND_MIXEDCURL = 5   /* MixedVectorCurlIntegrator:     curls  -> values, f_apply_hdivhcurl_33 (integ/mixedveccurl.cpp:23-66)  */
 };
 
 /* ---- context -------------------------------------------------------------------------------- */
@@ -159,7 +164,8 @@ enum
   B2P_APPLY_SIMPLE_KERNEL = 2,
   B2P_APPLY_HALFWARP_KERNEL = 4,
   B2P_APPLY_ROUND1_KERNEL = 8,
-  B2P_APPLY_CTA_KERNEL = 16
+  B2P_APPLY_CTA_KERNEL = 16,
+  B2P_APPLY_TRANSPOSE = 32 /* y += alpha A^T x; only the non-symmetric kinds (B2P_ND_WEAKCURL / B2P_ND_MIXEDCURL) look at it */
 };
 int b2p_op_apply_add_ex(b2p_op *op, double alpha, const double *x, double *y, int flags, b2p_stream s);
 /* Same over the element sub-range [e_begin, e_begin + e_count) with the L-vector in two pieces: dofs

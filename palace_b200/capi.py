@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2p.so")
 
-CURLCURL, ND_MASS, CURLCURL_MASS, H1_DIFFUSION = 0, 1, 2, 3
+CURLCURL, ND_MASS, CURLCURL_MASS, H1_DIFFUSION, ND_WEAKCURL, ND_MIXEDCURL = 0, 1, 2, 3, 4, 5
 
 _lib = None
 
@@ -247,9 +247,9 @@ class Op:
         _chk(lib().b2p_op_apply_add(self.h, _vp(x), _vp(y), _stream(stream)), self.ctx.h)
 
     def apply_add_ex(self, alpha, x, y, masked=False, simple_kernel=False, halfwarp_kernel=False, round1_kernel=False, cta_kernel=False,
-                     stream=None):
+                     transpose=False, stream=None):
         flags = ((1 if masked else 0) | (2 if simple_kernel else 0) | (4 if halfwarp_kernel else 0) | (8 if round1_kernel else 0)
-                 | (16 if cta_kernel else 0))
+                 | (16 if cta_kernel else 0) | (32 if transpose else 0))
         _chk(lib().b2p_op_apply_add_ex(self.h, C.c_double(alpha), _vp(x), _vp(y), flags, _stream(stream)), self.ctx.h)
 
     def apply_add_pair(self, alpha, x0, x1, y0, y1, masked=False, stream=None):

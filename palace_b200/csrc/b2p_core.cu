@@ -98,7 +98,7 @@ namespace b2p
 int apply_range(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg, int flags,
                 cudaStream_t s)
 {
-  if (op->dense) return launch_dense_apply(op, lidx, alpha, x, y, rg, s);
+  if (op->dense) return launch_dense_apply(op, lidx, alpha, x, y, rg, s, (flags & B2P_APPLY_TRANSPOSE) != 0);
   const bool simple = flags & B2P_APPLY_SIMPLE_KERNEL;
   if (op->kind == B2P_H1_DIFFUSION) return simple ? launch_h1_hex_apply(op, lidx, alpha, x, y, rg, s) : launch_h1_hex_apply3(op, lidx, alpha, x, y, rg, s);
   if (simple) return launch_nd_hex_apply(op, lidx, alpha, x, y, rg, s);
@@ -543,10 +543,11 @@ namespace
 // `fine` (the coarse level of a p-hierarchy) instead of reading desc->coeff_ctx.
 int create_dense(b2p_ctx *ctx, b2p_geom *geom, const b2p_dense_op_desc *d, b2p_op *fine, b2p_op **out)
 {
-  B2P_CHECK(ctx, d->kind >= B2P_CURLCURL && d->kind <= B2P_H1_DIFFUSION, B2P_ERR_ARG, "b2p_op_create_dense: bad kind %d", d->kind);
+  B2P_CHECK(ctx, d->kind >= B2P_CURLCURL && d->kind <= B2P_ND_MIXEDCURL, B2P_ERR_ARG, "b2p_op_create_dense: bad kind %d", d->kind);
   B2P_CHECK(ctx, geom->q1d == 0 && geom->Q == d->Q && geom->ne == d->ne, B2P_ERR_ARG,
             "b2p_op_create_dense: needs a general geometry (b2p_geom_create_qdata_general) with matching ne / Q");
-  const bool need_u = (d->kind == B2P_ND_MASS || d->kind == B2P_CURLCURL_MASS), need_c = (d->kind != B2P_ND_MASS);
+  const bool mixed = (d->kind == B2P_ND_WEAKCURL || d->kind == B2P_ND_MIXEDCURL);  // value and curl tables, one coefficient
+  const bool need_u = (d->kind == B2P_ND_MASS || d->kind == B2P_CURLCURL_MASS || mixed), need_c = (d->kind != B2P_ND_MASS);
   B2P_CHECK(ctx, (!need_u || d->interp) && (!need_c || d->deriv) && d->idx && d->lsize > 0 && d->P > 0, B2P_ERR_ARG,
             "b2p_op_create_dense: missing tables / restriction");
   b2p_op *op = new b2p_op;

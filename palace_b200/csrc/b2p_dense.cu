@@ -40,6 +40,7 @@ struct DenseParams
   VSplit sp;
   int ne, P, PS, Ppad, Q, Rpad, row_u, row_c;  // row_u / row_c: first row of the interp / deriv block (-1: absent)
   int kind;
+  int transpose;  // mixed kinds only: apply A^T (the symmetric kinds ignore it)
 };
 
 constexpr int NEB0 = 8;  // elements per MMA n-tile
@@ -452,6 +453,158 @@ __global__ void __launch_bounds__(256) dense_apply2_kernel(DenseParams prm)
   }
 }
 
+// Mixed kinds on one ND space (the Floquet-periodic terms, models/spaceoperator.cpp:305-309):
+//   B2P_ND_WEAKCURL   y = E^T Bc^T [w detJ Jd^T C A ] Bu E x   trial VALUES (H(curl) map A = J^-T) tested with CURLS (H(div) map Jd = J / detJ)
+//                     MixedVectorWeakCurlIntegrator -> f_apply_hcurlhdiv_33 (integ/mixedveccurl.cpp:68-117, qfunctions/33/hcurlhdiv_33_qf.h:10-31)
+//   B2P_ND_MIXEDCURL  y = E^T Bu^T [w detJ A^T C Jd ] Bc E x   trial CURLS tested with VALUES
+//                     MixedVectorCurlIntegrator     -> f_apply_hdivhcurl_33 (integ/mixedveccurl.cpp:23-66, hcurlhdiv_33_qf.h:33-55)
+// The forward GEMM runs over the trial block of the stacked table only, D maps the three point values in place, the backward GEMM
+// runs over the test block: same two DMMA GEMMs per batch of 8 elements as dense_apply_kernel, half the rows each. The transpose
+// of one kind is the other kind with C^T (prm.transpose). Not on the hot path (one extra term of periodic models): the whole
+// [3Q x 8] point array stays in shared memory, tables stream from L2.
+__global__ void __launch_bounds__(256) dense_mixed_kernel(DenseParams prm)
+{
+  constexpr int NEB = NEB0;
+  B2P_DYN_SMEM(double, sm);
+  const int P = prm.P, Q = prm.Q, R3 = 3 * Q, R3pad = (R3 + 7) & ~7;
+  double *U = sm;                   // [Ppad][NEB]
+  double *V = U + prm.Ppad * NEB;   // [R3pad][NEB]
+  double *X = V + R3pad * NEB;      // [Ppad][NEB] raw gathered values (curl-oriented restriction only)
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int e0 = blockIdx.x * NEB;
+  const bool trial_curl = (prm.kind == B2P_ND_MIXEDCURL) != (prm.transpose != 0);
+  const int trial_row = trial_curl ? prm.row_c : prm.row_u, test_row = trial_curl ? prm.row_u : prm.row_c;
+
+  // ---- restriction (E): native order, sign or tridiagonal orientation ----
+  for (int w = tid; w < prm.Ppad * NEB; w += blockDim.x)
+  {
+    const int i = w / NEB, e = w % NEB;
+    double v = 0.0;
+    if (i < P && e0 + e < prm.ne)
+    {
+      const int32_t gi = prm.lidx[(size_t)(e0 + e) * prm.PS + i];
+      if (prm.curl_orient)
+        v = (gi == B2P_SKIP_IDX) ? 0.0 : __ldg(split_src(prm.x, prm.sp, gi >= 0 ? gi : -1 - gi));
+      else
+        v = gather2(prm.x, prm.sp, gi);
+    }
+    (prm.curl_orient ? X : U)[w] = v;
+  }
+  if (prm.curl_orient)
+  {
+    __syncthreads();
+    for (int w = tid; w < prm.Ppad * NEB; w += blockDim.x)
+    {
+      const int i = w / NEB, e = w % NEB;
+      double v = 0.0;
+      if (i < P && e0 + e < prm.ne)
+      {
+        const int8_t *co = prm.curl_orient + ((size_t)(e0 + e) * P + i) * 3;
+        v = (double)co[1] * X[i * NEB + e];
+        if (i > 0) v += (double)co[0] * X[(i - 1) * NEB + e];
+        if (i < P - 1) v += (double)co[2] * X[(i + 1) * NEB + e];
+      }
+      U[w] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- V = T_trial U : m-tiles over the trial block's rows (rows past the block read as zero), k over dofs ----
+  for (int mt = wid; mt < R3pad / 8; mt += nw)
+  {
+    double c0 = 0.0, c1 = 0.0;
+    const int r = mt * 8 + lane / 4;
+    const bool live = r < R3;
+    const double *Arow = prm.T + (size_t)(trial_row + (live ? r : 0)) * prm.Ppad + (lane % 4);
+    const double *Bcol = U + (lane % 4) * NEB + lane / 4;
+    for (int k0 = 0; k0 < prm.Ppad; k0 += 4)
+    {
+      const double a = live ? __ldg(Arow + k0) : 0.0;
+      dmma884(c0, c1, a, Bcol[k0 * NEB]);
+    }
+    double *o = V + r * NEB + 2 * (lane % 4);
+    o[0] = c0;
+    o[1] = c1;
+  }
+  __syncthreads();
+
+  // ---- D at the quadrature points (in place): out = w detJ M2^T C' M1 t ----
+  for (int w = tid; w < Q * NEB; w += blockDim.x)
+  {
+    const int iq = w / NEB, e = w % NEB;
+    if (e0 + e >= prm.ne) continue;  // (their U columns are zero, so their V entries already are)
+    const double *g = prm.qd + (size_t)(e0 + e) * 10 * Q + iq;
+    const double *C = prm.ecoef + (size_t)(e0 + e) * 18;
+    const double wdetJ = prm.alpha * g[0];
+    double A[9], Jd[9], Cm[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) A[i] = g[(1 + i) * Q];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Cm[i + 3 * j] = prm.transpose ? C[j + 3 * i] : C[i + 3 * j];
+    cofactor33(A, Jd);
+    const double t[3] = {V[iq * NEB + e], V[(Q + iq) * NEB + e], V[(2 * Q + iq) * NEB + e]};
+    double t1[3], z[3], v[3];
+    Ax33(trial_curl ? Jd : A, t, t1);
+    Ax33(Cm, t1, z);
+    Atx33(trial_curl ? A : Jd, z, wdetJ, v);
+    V[iq * NEB + e] = v[0];
+    V[(Q + iq) * NEB + e] = v[1];
+    V[(2 * Q + iq) * NEB + e] = v[2];
+  }
+  __syncthreads();
+
+  // ---- Y = T_test^T V : m-tiles over dofs, k over the test block's rows; result overwrites U ----
+  for (int mt = wid; mt < prm.Ppad / 8; mt += nw)
+  {
+    double c0 = 0.0, c1 = 0.0;
+    const double *Bcol = V + (lane % 4) * NEB + lane / 4;
+    for (int k0 = 0; k0 < R3pad; k0 += 4)
+    {
+      const int r = k0 + lane % 4;
+      const double a = r < R3 ? __ldg(prm.T + (size_t)(test_row + r) * prm.Ppad + mt * 8 + lane / 4) : 0.0;
+      dmma884(c0, c1, a, Bcol[k0 * NEB]);
+    }
+    double *o = U + (mt * 8 + lane / 4) * NEB + 2 * (lane % 4);
+    o[0] = c0;
+    o[1] = c1;
+  }
+  __syncthreads();
+
+  // ---- E^T ----
+  if (prm.curl_orient)
+  {
+    for (int w = tid; w < prm.Ppad * NEB; w += blockDim.x)
+    {
+      const int i = w / NEB, e = w % NEB;
+      double v = 0.0;
+      if (i < P && e0 + e < prm.ne)
+      {
+        const int8_t *co = prm.curl_orient + ((size_t)(e0 + e) * P) * 3;
+        v = (double)co[3 * i + 1] * U[i * NEB + e];
+        if (i > 0) v += (double)co[3 * (i - 1) + 2] * U[(i - 1) * NEB + e];
+        if (i < P - 1) v += (double)co[3 * (i + 1) + 0] * U[(i + 1) * NEB + e];
+      }
+      X[w] = v;
+    }
+    __syncthreads();
+  }
+  const double *src = prm.curl_orient ? X : U;
+  for (int w = tid; w < P * NEB; w += blockDim.x)
+  {
+    const int i = w / NEB, e = w % NEB;
+    if (e0 + e >= prm.ne) continue;
+    const int32_t gi = prm.lidx[(size_t)(e0 + e) * prm.PS + i];
+    if (prm.curl_orient)
+    {
+      if (gi != B2P_SKIP_IDX) scatter2(prm.y, prm.sp, gi >= 0 ? gi : -1 - gi, src[w]);
+    }
+    else
+      scatter2(prm.y, prm.sp, gi, src[w]);
+  }
+}
+
 // diag[g(i)] += sum_q w(q)^T D w(q) with w = the i-th shape function as the global side sees it: for sign
 // orientation that is column i of the table (the sign squares away); for the tridiagonal orientation it is
 // sum_l T_e(l, i) * column l, which makes the diagonal of T^T A T exact (libCEED assembles it through the unsigned
@@ -465,6 +618,7 @@ __global__ void dense_diag_kernel(DenseParams prm)
   const bool MASS = (prm.kind == B2P_ND_MASS || prm.kind == B2P_CURLCURL_MASS);
   const bool CURL = (prm.kind == B2P_CURLCURL || prm.kind == B2P_CURLCURL_MASS);
   const bool H1 = (prm.kind == B2P_H1_DIFFUSION);
+  const bool MIXED = (prm.kind == B2P_ND_WEAKCURL || prm.kind == B2P_ND_MIXEDCURL);
   const double *C = prm.ecoef + (size_t)e * 18;
   double C0[9], C1[9];
   for (int t = 0; t < 9; t++)
@@ -510,6 +664,27 @@ __global__ void dense_diag_kernel(DenseParams prm)
       AtCAx(Jd, C1, c, g[0], v);
       s += c[0] * v[0] + c[1] * v[1] + c[2] * v[2];
     }
+    if (MIXED)
+    {
+      // value and curl of the same shape function meet through C: c^T (w detJ Jd^T C A) u (weak curl), u^T (w detJ A^T C Jd) c
+      double u[3] = {col(prm.row_u + iq), col(prm.row_u + Q + iq), col(prm.row_u + 2 * Q + iq)};
+      double c[3] = {col(prm.row_c + iq), col(prm.row_c + Q + iq), col(prm.row_c + 2 * Q + iq)}, Jd[9], t1[3], z[3];
+      cofactor33(A, Jd);
+      if (prm.kind == B2P_ND_WEAKCURL)
+      {
+        Ax33(A, u, t1);
+        Ax33(C0, t1, z);
+        Atx33(Jd, z, g[0], v);
+        s += c[0] * v[0] + c[1] * v[1] + c[2] * v[2];
+      }
+      else
+      {
+        Ax33(Jd, c, t1);
+        Ax33(C0, t1, z);
+        Atx33(A, z, g[0], v);
+        s += u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
+      }
+    }
   }
   int gi = prm.lidx[(size_t)e * prm.PS + i];
   if (gi == B2P_SKIP_IDX) return;
@@ -520,6 +695,7 @@ __global__ void dense_diag_kernel(DenseParams prm)
 DenseParams make_params(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg)
 {
   DenseParams p;
+  p.transpose = 0;
   const int e_off = rg.e_off, e_cnt = rg.e_cnt < 0 ? op->ne - rg.e_off : rg.e_cnt;
   p.lidx = lidx + (size_t)e_off * op->PS;
   p.curl_orient = op->curl_orient ? op->curl_orient + (size_t)e_off * op->P * 3 : nullptr;
@@ -568,10 +744,26 @@ int launch_dense2(b2p_op *op, const DenseParams &prm, int nwarps, cudaStream_t s
 }  // namespace
 
 int launch_dense_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg,
-                       cudaStream_t s)
+                       cudaStream_t s, bool transpose)
 {
   DenseParams prm = make_params(op, lidx, alpha, x, y, rg);
   if (prm.ne <= 0) return B2P_SUCCESS;
+  if (op->kind == B2P_ND_WEAKCURL || op->kind == B2P_ND_MIXEDCURL)
+  {
+    prm.transpose = transpose ? 1 : 0;
+    const int R3pad = (3 * prm.Q + 7) & ~7;
+    const size_t shmem = sizeof(double) * NEB0 * ((size_t)prm.Ppad + R3pad + (op->curl_orient ? prm.Ppad : 0));
+    B2P_CHECK(op->ctx, shmem <= 227 * 1024, B2P_ERR_UNSUPPORTED, "dense mixed operator: element too large for shared memory (%zu B)", shmem);
+    static size_t configured = 0;
+    if (shmem > configured)
+    {
+      B2P_CUDA(op->ctx, cudaFuncSetAttribute(dense_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      configured = shmem;
+    }
+    B2P_LAUNCH(dense_mixed_kernel, (prm.ne + NEB0 - 1) / NEB0, 256, shmem, s, prm);
+    B2P_CUDA(op->ctx, cudaGetLastError());
+    return B2P_SUCCESS;
+  }
   // B2P_DENSE_KERNEL=1: the round-1 kernel (whole [6Q x 8] point array in shared memory, table streamed per 8 elements)
   static const int which = []
   {

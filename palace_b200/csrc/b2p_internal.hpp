@@ -217,7 +217,7 @@ int launch_h1_hex_apply3(b2p_op *op, const int32_t *lidx, double alpha, const do
 int launch_h1_hex_diag(b2p_op *op, double *diag, cudaStream_t s);
 int launch_assemble_qdata(b2p_op *op, cudaStream_t s);
 int launch_dense_apply(b2p_op *op, const int32_t *lidx, double alpha, const double *x, double *y, const ApplyRange &rg,
-                       cudaStream_t s);
+                       cudaStream_t s, bool transpose = false);
 int launch_dense_diag(b2p_op *op, double *diag, cudaStream_t s);
 int launch_geom_hex(b2p_ctx *ctx, int ne, int k, int q1d, const double *d_xe, const double *d_B, const double *d_G,
                     const double *d_qw, double *d_qd, cudaStream_t s);

@@ -135,6 +135,9 @@ public:
   bool Fused() const { return fused_sum != nullptr; }
   ~ParOperator() override;
   void Mult(const double *x, double *y) const override;
+  // Symmetric terms: Mult. With a non-symmetric term (B2P_ND_WEAKCURL / B2P_ND_MIXEDCURL) the local operators are applied
+  // transposed (single partition; the reference has no transpose of its BilinearForm operators at all, libceed/operator.cpp:60-99).
+  void MultTranspose(const double *x, double *y) const override;
   void AddMult(const double *x, double *y, double a = 1.0) const override;
   bool NativeAddMult() const override { return halo == nullptr; }
   void AssembleDiagonal(double *d) const override;

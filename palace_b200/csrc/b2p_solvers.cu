@@ -280,6 +280,33 @@ void ParOperator::Mult(const double *x, double *y) const
   }
 }
 
+// rap.cpp:236-275
+void ParOperator::MultTranspose(const double *x, double *y) const
+{
+  bool nonsym = false;
+  for (auto &t : terms) nonsym = nonsym || t.op->kind == B2P_ND_WEAKCURL || t.op->kind == B2P_ND_MIXEDCURL;
+  if (!nonsym)
+  {
+    Mult(x, y);
+    return;
+  }
+  cudaStream_t s = ctx->stream;
+  vec::set(ctx, y, height, 0.0);
+  if (halo)
+  {
+    set_error(ctx, "ParOperator::MultTranspose: non-symmetric terms on a partitioned space are not supported");
+    return;
+  }
+  for (auto &t : terms) b2p_op_apply_add_ex(t.op, t.coef, x, y, B2P_APPLY_MASKED | B2P_APPLY_TRANSPOSE, s);
+  if (n_ess > 0)
+  {
+    if (diag_policy == 1)
+      vec::set_sub_from(ctx, y, d_ess, n_ess, x);
+    else
+      vec::set_sub(ctx, y, d_ess, n_ess, 0.0);
+  }
+}
+
 // rap.cpp:277-318 (y += a * (P^T A P x with the essential rows replaced))
 void ParOperator::AddMult(const double *x, double *y, double a) const
 {
