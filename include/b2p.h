@@ -322,6 +322,23 @@ int64_t b2p_operator_height(b2p_operator *A);
 int64_t b2p_operator_width(b2p_operator *A);
 void b2p_operator_destroy(b2p_operator *A);
 
+/* ---- ParOperator with a general conforming prolongation (non-conforming / AMR meshes; linalg/rap.cpp:154-275) ----
+ * On a non-conforming mesh the prolongation of a space is a sparse matrix P [lsize x tsize] whose slave rows interpolate from
+ * master dofs (mfem::ParFiniteElementSpace::GetProlongationMatrix(), a HypreParMatrix); the reference applies y = P^T A P x with
+ * the essential TRUE dofs zeroed before P and overwritten after P^T (rap.cpp:195-234), and assembles the diagonal as |P|^T d_L
+ * with entry-wise absolute values (rap.cpp:162-178, HypreParMatrix::AbsMultTranspose).
+ * b2p_spmat: device CSR matrix from host arrays (int32 rowptr[rows+1] / col[nnz], double val[nnz]; copied), kept with its
+ * transpose. b2p_operator_rap: A_local is the operator on the L-vector (a b2p_operator_par over the local operators with
+ * tsize == lsize and NO essential dofs; not owned), P the space's prolongation (shared: reference counted, the caller may destroy
+ * its handle), ess_tdofs in TRUE-dof numbering; Mult, MultTranspose, AddMult and AssembleDiagonal as above. Single partition. */
+typedef struct b2p_spmat b2p_spmat;
+int b2p_spmat_create(b2p_ctx *ctx, int64_t rows, int64_t cols, const int32_t *rowptr, const int32_t *col, const double *val,
+                     b2p_spmat **out);
+int b2p_spmat_mult(b2p_spmat *m, int transpose, const double *x, double *y); /* y = A x or A^T x on the context's stream */
+void b2p_spmat_destroy(b2p_spmat *m);
+int b2p_operator_rap(b2p_ctx *ctx, b2p_operator *A_local, b2p_spmat *P, const int32_t *ess_tdofs, int64_t n_ess, int diag_policy,
+                     b2p_operator **out);
+
 /* ---- solvers (palace::Solver<Operator>, linalg/solver.hpp:21-65) ---- */
 typedef struct b2p_solver b2p_solver;
 int b2p_solver_jacobi(b2p_ctx *ctx, double omega, double sf_max, b2p_solver **out);                                  /* jacobi.cpp */

@@ -542,6 +542,40 @@ class Operator:
         return int(lib().b2p_operator_height(self.h))
 
 
+class SpMat:
+    """Device CSR matrix with its transpose (b2p_spmat): the prolongation of a non-conforming space."""
+
+    def __init__(self, ctx, A):
+        import scipy.sparse as sp
+
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        self.ctx, self.shape = ctx, A.shape
+        rp, cl, vl = _np(A.indptr, np.int32), _np(A.indices, np.int32), _np(A.data, np.float64)
+        self.h = C.c_void_p()
+        _chk(lib().b2p_spmat_create(ctx.h, C.c_int64(A.shape[0]), C.c_int64(A.shape[1]), _ptr(rp), _ptr(cl), _ptr(vl), C.byref(self.h)),
+             ctx.h)
+
+    def mult(self, x, y, transpose=False):
+        _chk(lib().b2p_spmat_mult(self.h, 1 if transpose else 0, _vp(x), _vp(y)), self.ctx.h)
+
+    def __del__(self):
+        try:
+            lib().b2p_spmat_destroy(self.h)
+        except Exception:
+            pass
+
+
+def operator_rap(ctx, A_local, P: SpMat, ess_tdofs=None, diag_policy=1):
+    """ParOperator with a general prolongation: P^T A_local P with essential true dofs (b2p_operator_rap)."""
+    ess = _np(ess_tdofs if ess_tdofs is not None else np.zeros(0), np.int32)
+    h = C.c_void_p()
+    _chk(lib().b2p_operator_rap(ctx.h, A_local.h, P.h, _ptr(ess), C.c_int64(ess.size), int(diag_policy), C.byref(h)), ctx.h)
+    o = Operator(ctx, h)
+    o._keep = [A_local, P]
+    return o
+
+
 CG, GMRES, FGMRES = 0, 1, 2
 MGS, CGS, CGS2 = 0, 1, 2
 PC_RIGHT, PC_LEFT = 0, 1

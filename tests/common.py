@@ -29,6 +29,11 @@ class Problem:
 
 def make_problem(n=(3, 2, 2), p=2, q1d=None, mesh_order=2, warp=0.04, scramble=3, n_attr=3, size=(1.0, 0.7, 0.9)) -> Problem:
     mesh = hm.box_mesh(n, size, warp_amp=warp, scramble_seed=scramble, n_attr=n_attr)
+    return problem_on_mesh(mesh, p, q1d, mesh_order)
+
+
+def problem_on_mesh(mesh, p=2, q1d=None, mesh_order=2) -> Problem:
+    """Spaces, tables and oracle q-data on a given hexahedral mesh (conforming numbering of every entity the mesh has)."""
     topo = hs.build_topology(mesh)
     q1d = p + 1 if q1d is None else q1d
     nodes = hs.gauss_lobatto(mesh_order + 1)
