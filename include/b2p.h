@@ -338,6 +338,11 @@ int b2p_spmat_mult(b2p_spmat *m, int transpose, const double *x, double *y); /* 
 void b2p_spmat_destroy(b2p_spmat *m);
 int b2p_operator_rap(b2p_ctx *ctx, b2p_operator *A_local, b2p_spmat *P, const int32_t *ess_tdofs, int64_t n_ess, int diag_policy,
                      b2p_operator **out);
+/* y = L A R x with sparse L and / or R (NULL: absent), transpose R^T A^T L^T: the level prolongations and discrete gradients of
+ * non-conforming spaces, ParOperator(interpolator, trial, test, use_R = true) = R_test I P_trial (rap.cpp:195-275,320-345), with
+ * A_mid the interpolator on L-vectors (b2p_operator_interp without halos), L the test space's restriction (true-dof selection)
+ * and R the trial space's prolongation. A_mid is not owned; the matrices are shared. */
+int b2p_operator_triple(b2p_ctx *ctx, b2p_spmat *L, b2p_operator *A_mid, b2p_spmat *R, b2p_operator **out);
 
 /* ---- solvers (palace::Solver<Operator>, linalg/solver.hpp:21-65) ---- */
 typedef struct b2p_solver b2p_solver;

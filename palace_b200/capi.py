@@ -576,6 +576,15 @@ def operator_rap(ctx, A_local, P: SpMat, ess_tdofs=None, diag_policy=1):
     return o
 
 
+def operator_triple(ctx, L, A_mid, R):
+    """y = L A_mid R x with sparse L / R (SpMat or None): b2p_operator_triple."""
+    h = C.c_void_p()
+    _chk(lib().b2p_operator_triple(ctx.h, L.h if L is not None else None, A_mid.h, R.h if R is not None else None, C.byref(h)), ctx.h)
+    o = Operator(ctx, h)
+    o._keep = [L, A_mid, R]
+    return o
+
+
 CG, GMRES, FGMRES = 0, 1, 2
 MGS, CGS, CGS2 = 0, 1, 2
 PC_RIGHT, PC_LEFT = 0, 1

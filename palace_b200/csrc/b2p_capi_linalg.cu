@@ -277,8 +277,7 @@ int b2p_solver_distrelax(b2p_ctx *ctx, b2p_operator *G, int smooth_it, int cheby
 int b2p_solver_distrelax_set_operators(b2p_solver *s, b2p_operator *A, b2p_operator *A_G)
 {
   auto *d = s ? dynamic_cast<DistRelaxationSmoother *>(s->s.get()) : nullptr;
-  auto *pa = A ? dynamic_cast<ParOperator *>(A->op.get()) : nullptr;
-  auto *pg = A_G ? dynamic_cast<ParOperator *>(A_G->op.get()) : nullptr;
+  Operator *pa = A ? A->op.get() : nullptr, *pg = A_G ? A_G->op.get() : nullptr;  // ParOperator or its general-prolongation form
   if (!d || !pa || !pg) return B2P_ERR_ARG;
   B2P_TRY(d->ctx, d->SetOperators(*pa, *pg));
   return B2P_SUCCESS;
@@ -310,14 +309,12 @@ int b2p_solver_gmg_set_operators(b2p_solver *s, b2p_operator *const *A, b2p_oper
 {
   auto *g = s ? dynamic_cast<GeometricMultigridSolver *>(s->s.get()) : nullptr;
   if (!g || !A) return B2P_ERR_ARG;
-  std::vector<const ParOperator *> Av, Gv;
+  std::vector<const Operator *> Av, Gv;
   for (size_t l = 0; l < g->A.size(); l++)
   {
     B2P_CHECK(g->ctx, A[l] && A[l]->op, B2P_ERR_ARG, "b2p_solver_gmg_set_operators: level %d has no operator", (int)l);
-    auto *pa = dynamic_cast<ParOperator *>(A[l]->op.get());
-    B2P_CHECK(g->ctx, pa, B2P_ERR_ARG, "GeometricMultigridSolver requires ParOperator operators!");
-    Av.push_back(pa);
-    auto *pg = (A_aux && A_aux[l]) ? dynamic_cast<ParOperator *>(A_aux[l]->op.get()) : nullptr;
+    Av.push_back(A[l]->op.get());  // a ParOperator (b2p_operator_par) or its general-prolongation form (b2p_operator_rap)
+    Operator *pg = (A_aux && A_aux[l]) ? A_aux[l]->op.get() : nullptr;
     // a level smoothed by DistRelaxationSmoother (the multigrid was built with discrete gradients) needs its auxiliary-space operator
     const bool dist = dynamic_cast<DistRelaxationSmoother *>(g->B[l].get()) != nullptr;
     B2P_CHECK(g->ctx, !dist || pg, B2P_ERR_ARG, "b2p_solver_gmg_set_operators: level %d needs an auxiliary-space ParOperator", (int)l);
@@ -547,14 +544,12 @@ int b2p_ksp_set_operators(b2p_ksp *k, b2p_operator *op, b2p_operator *const *pc_
   B2P_TRY(ctx, k->ksp->SetOperator(*op->op));  // ksp.cpp:295-297
   if (auto *g = dynamic_cast<GeometricMultigridSolver *>(k->pc.get()))
   {
-    std::vector<const ParOperator *> Av, Gv;
+    std::vector<const Operator *> Av, Gv;
     for (int l = 0; l < k->n_levels; l++)
     {
       B2P_CHECK(ctx, pc_ops[l] && pc_ops[l]->op, B2P_ERR_ARG, "b2p_ksp_set_operators: level %d has no operator", l);
-      auto *pa = dynamic_cast<ParOperator *>(pc_ops[l]->op.get());
-      B2P_CHECK(ctx, pa, B2P_ERR_ARG, "GeometricMultigridSolver requires ParOperator operators!");
-      Av.push_back(pa);
-      auto *pg = (aux_ops && aux_ops[l]) ? dynamic_cast<ParOperator *>(aux_ops[l]->op.get()) : nullptr;
+      Av.push_back(pc_ops[l]->op.get());
+      Operator *pg = (aux_ops && aux_ops[l]) ? aux_ops[l]->op.get() : nullptr;
       const bool dist = dynamic_cast<DistRelaxationSmoother *>(g->B[l].get()) != nullptr;
       B2P_CHECK(ctx, !dist || pg, B2P_ERR_ARG, "b2p_ksp_set_operators: level %d needs an auxiliary-space ParOperator", l);
       Gv.push_back(pg);

@@ -82,6 +82,10 @@ public:
   virtual void AssembleDiagonal(double *d) const;
   // true: AddMult accumulates straight into y (no temporary): r = x - A y is then a copy plus one AddMult
   virtual bool NativeAddMult() const { return false; }
+  // essential (Dirichlet) true dofs of operators that eliminate them (ParOperator and its general-prolongation form): the
+  // multigrid zeroes them in restricted residuals (gmg.cpp:190-194)
+  virtual const int32_t *EssentialTrueDofs() const { return nullptr; }
+  virtual int64_t NumEssential() const { return 0; }
   int64_t Height() const { return height; }
   int64_t Width() const { return width; }
 
@@ -153,8 +157,8 @@ public:
   // The eliminated sum as one device CSR matrix (ParOperator::ParallelAssemble, rap.cpp:84-152; coarse levels, single
   // partition); the caller owns the result (b2p_csr_destroy). Throws through set_error + nullptr on failure.
   b2p_csr *FullAssemble() const;
-  const int32_t *EssentialTrueDofs() const { return d_ess; }
-  int64_t NumEssential() const { return n_ess; }
+  const int32_t *EssentialTrueDofs() const override { return d_ess; }
+  int64_t NumEssential() const override { return n_ess; }
   int64_t lsize;
 
 private:
@@ -260,13 +264,13 @@ public:
   DistRelaxationSmoother(b2p_ctx *c, const Operator &G, int smooth_it, int cheby_smooth_it, int cheby_order, double sf_max,
                          double sf_min, bool fourth_kind);
   void SetOperator(const Operator &) override;  // not used: needs both operators
-  void SetOperators(const ParOperator &op, const ParOperator &op_G);
+  void SetOperators(const Operator &op, const Operator &op_G);
   void Mult(const double *x, double *y) const override;
   void Mult2(const double *x, double *y, double *r) const override;
   void MultTranspose2(const double *x, double *y, double *r) const override;
   int pc_it;
   const Operator *G;
-  const ParOperator *A = nullptr, *A_G = nullptr;
+  const Operator *A = nullptr, *A_G = nullptr;
   std::unique_ptr<ChebyshevSmoother> B, B_G;
   mutable DVec x_G, y_G, r_G;
 };
@@ -279,11 +283,11 @@ public:
                            const std::vector<const Operator *> &G, int cycle_it, int smooth_it, int cheby_order, double sf_max,
                            double sf_min, bool fourth_kind);
   void SetOperator(const Operator &) override;
-  void SetOperators(const std::vector<const ParOperator *> &A, const std::vector<const ParOperator *> &A_aux);
+  void SetOperators(const std::vector<const Operator *> &A, const std::vector<const Operator *> &A_aux);
   void Mult(const double *x, double *y) const override;
   int pc_it;
   std::vector<const Operator *> P;
-  std::vector<const ParOperator *> A;
+  std::vector<const Operator *> A;
   std::vector<std::unique_ptr<Solver>> B;
   mutable std::vector<DVec> X, Y, R;
 

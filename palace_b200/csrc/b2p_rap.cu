@@ -104,6 +104,8 @@ public:
   }
   void Mult(const double *x, double *y) const override { Apply(x, y, false); }
   void MultTranspose(const double *x, double *y) const override { Apply(x, y, true); }
+  const int32_t *EssentialTrueDofs() const override { return d_ess; }
+  int64_t NumEssential() const override { return n_ess; }
   void AssembleDiagonal(double *d) const override
   {
     A->AssembleDiagonal(lx.p);
@@ -142,6 +144,55 @@ private:
   int64_t n_ess;
   int diag_policy;
   mutable DVec lx, ly, tx;
+};
+
+// y = L A R x with sparse L, R (either may be absent): level prolongations of non-conforming spaces are
+// ParOperator(interpolator, trial space, test space, use_R = true) = R_fine I P_coarse (rap.cpp:195-234 with RestrictionMatrixMult,
+// rap.cpp:320-345), the transpose P_coarse^T I^T R_fine^T (rap.cpp:236-275).
+class TripleOperator : public Operator
+{
+public:
+  TripleOperator(b2p_ctx *c, b2p_spmat *L_, Operator *A_, b2p_spmat *R_)
+    : Operator(c, L_ ? L_->rows : A_->height, R_ ? R_->cols : A_->width), L(L_), A(A_), R(R_)
+  {
+    if (L) L->refcount++;
+    if (R) R->refcount++;
+    if (R) in.resize(c, A->width);
+    if (L) out.resize(c, A->height);
+  }
+  ~TripleOperator() override
+  {
+    spmat_release(L);
+    spmat_release(R);
+  }
+  void Mult(const double *x, double *y) const override
+  {
+    const double *src = x;
+    if (R)
+    {
+      spmat_apply(R, false, false, x, in.p, ctx->stream);
+      src = in.p;
+    }
+    A->Mult(src, L ? out.p : y);
+    if (L) spmat_apply(L, false, false, out.p, y, ctx->stream);
+  }
+  void MultTranspose(const double *x, double *y) const override
+  {
+    const double *src = x;
+    if (L)
+    {
+      spmat_apply(L, true, false, x, out.p, ctx->stream);
+      src = out.p;
+    }
+    A->MultTranspose(src, R ? in.p : y);
+    if (R) spmat_apply(R, true, false, in.p, y, ctx->stream);
+  }
+
+private:
+  b2p_spmat *L;
+  Operator *A;  // not owned
+  b2p_spmat *R;
+  mutable DVec in, out;
 };
 }  // namespace
 }  // namespace b2p
@@ -214,6 +265,17 @@ int b2p_operator_rap(b2p_ctx *ctx, b2p_operator *A_local, b2p_spmat *P, const in
     B2P_CHECK(ctx, ess_tdofs[i] >= 0 && ess_tdofs[i] < P->cols, B2P_ERR_ARG, "b2p_operator_rap: essential true dof %d outside [0, %lld)",
               ess_tdofs[i], (long long)P->cols);
   *out = wrap_operator(std::make_unique<RapOperator>(ctx, A, P, ess_tdofs, n_ess, diag_policy));
+  return B2P_SUCCESS;
+}
+
+int b2p_operator_triple(b2p_ctx *ctx, b2p_spmat *L, b2p_operator *A_mid, b2p_spmat *R, b2p_operator **out)
+{
+  B2P_CHECK(ctx, ctx && A_mid && out, B2P_ERR_ARG, "b2p_operator_triple: bad argument");
+  Operator *A = operator_of(A_mid);
+  B2P_CHECK(ctx, (!L || L->cols == A->height) && (!R || R->rows == A->width), B2P_ERR_ARG,
+            "b2p_operator_triple: sizes do not chain (L %lld x %lld, A %lld x %lld, R %lld x %lld)", (long long)(L ? L->rows : 0),
+            (long long)(L ? L->cols : 0), (long long)A->height, (long long)A->width, (long long)(R ? R->rows : 0), (long long)(R ? R->cols : 0));
+  *out = wrap_operator(std::make_unique<TripleOperator>(ctx, L, A, R));
   return B2P_SUCCESS;
 }
 }

@@ -523,7 +523,7 @@ DistRelaxationSmoother::DistRelaxationSmoother(b2p_ctx *c, const Operator &G_, i
 }
 void DistRelaxationSmoother::SetOperator(const Operator &) { set_error(ctx, "DistRelaxationSmoother needs SetOperators(A, A_G)"); }
 // distrelaxation.cpp:39-69
-void DistRelaxationSmoother::SetOperators(const ParOperator &op, const ParOperator &op_G)
+void DistRelaxationSmoother::SetOperators(const Operator &op, const Operator &op_G)
 {
   A = &op;
   A_G = &op_G;
@@ -596,7 +596,7 @@ GeometricMultigridSolver::GeometricMultigridSolver(b2p_ctx *c, std::unique_ptr<S
 }
 void GeometricMultigridSolver::SetOperator(const Operator &) { set_error(ctx, "GeometricMultigridSolver needs SetOperators"); }
 // gmg.cpp:66-123
-void GeometricMultigridSolver::SetOperators(const std::vector<const ParOperator *> &A_, const std::vector<const ParOperator *> &A_aux)
+void GeometricMultigridSolver::SetOperators(const std::vector<const Operator *> &A_, const std::vector<const Operator *> &A_aux)
 {
   const size_t n_levels = A.size();
   for (size_t l = 0; l < n_levels; l++)
