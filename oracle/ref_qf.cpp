@@ -24,6 +24,8 @@ typedef int CeedInt;
 // boundary (2-D elements embedded in 3-D) geometry factors and the H(curl) mass QFunction
 #include "fem/qfunctions/32/geom_32_qf.h"
 #include "fem/qfunctions/32/hcurl_32_qf.h"
+// scalar curl of a 2-D element (boundary curl-curl: integ/curlcurl.cpp:54-60, case 32 -> f_apply_l2_1)
+#include "fem/qfunctions/1/l2_1_qf.h"
 // mixed H(curl) / H(div) mass (MixedVectorCurl / MixedVectorWeakCurl integrators, FluxProjector) and the element error integrands
 #include "fem/qfunctions/33/hcurlhdiv_33_qf.h"
 #include "fem/qfunctions/33/hcurlhdiv_error_33_qf.h"
@@ -113,5 +115,12 @@ int ref_apply_hdivhcurl_error_33(void *ctx, int Q, const double *qdata, const do
   const double *in[3] = {qdata, u1, u2};
   double *out[1] = {v};
   return f_apply_hdivhcurl_error_33(ctx, Q, in, out);
+}
+// v[Q] = coeff qw^2 / (w |J|) u: in = {qdata (attr, w |J|, ...), qw, u} (l2_1_qf.h:9-22; EvalMode::Weight is an active input)
+int ref_apply_l2_1(void *ctx, int Q, const double *qdata, const double *qw, const double *u, double *v)
+{
+  const double *in[3] = {qdata, qw, u};
+  double *out[1] = {v};
+  return f_apply_l2_1(ctx, Q, in, out);
 }
 }

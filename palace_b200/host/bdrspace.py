@@ -137,3 +137,43 @@ def bdr_qdata(xe: np.ndarray, faces: np.ndarray, mesh_order: int, q1d: int, attr
         a = np.full(Q2, 1.0 if attr is None else float(attr[f]))
         out[f] = geom32_qdata(a, qw2, J)
     return out
+
+
+# ---- boundary curl-curl: CurlCurlIntegrator on boundary elements (second-order absorbing boundaries, wave ports;
+# /root/reference/palace/models/spaceoperator.cpp:290-300). For dim = 2 in space_dim = 3 the curl has ONE component and the
+# integrator selects f_apply_l2_1 with the quadrature weight as an extra input (integ/curlcurl.cpp:54-68):
+#     v = coeff qw^2 / (w |J|) curl^ u        (qfunctions/1/l2_1_qf.h:9-22; coefficient context of dimension 1)
+# since the reference-space scalar curl is |J| times the physical surface curl. Again no new device kernel: the 3-D curl-curl
+# map w detJ Jd^T C Jd c with the geometry factor replaced by the identity (Jd = cofactor(I) = I), the weight slot holding
+# qw^2 / (w |J|), the scalar curl padded to (curl, 0, 0) and the scalar coefficient as a diagonal 3 x 3 IS that QFunction. ----
+def nd_quad_curl_tables(p: int, q1d: int | None = None):
+    """deriv[3][Q2][P2]: component 0 = reference scalar curl d(u_t2)/d(t1) - d(u_t1)/d(t2) of the quadrilateral Nedelec element
+    (dof order of build_nd_bdr_space / nd_quad_tables), components 1, 2 zero."""
+    t = hs.tables_1d(p, q1d)
+    q = t.Bo.shape[0]
+    P2, Q2 = 2 * p * (p + 1), q * q
+    deriv = np.zeros((3, Q2, P2))
+    for qb in range(q):
+        for qa in range(q):
+            iq = qa + q * qb
+            o = 0
+            for m in range(p + 1):          # u_t1 = Bo_i(a) Bc_m(b)
+                for i in range(p):
+                    deriv[0, iq, o] = -t.Bo[qa, i] * t.Gc[qb, m]
+                    o += 1
+            for m in range(p):              # u_t2 = Bc_i(a) Bo_m(b)
+                for i in range(p + 1):
+                    deriv[0, iq, o] = t.Gc[qa, i] * t.Bo[qb, m]
+                    o += 1
+    return deriv
+
+
+def curl32_qdata(qd8, qw2):
+    """[..., 8, Q] boundary q-data + the rule's weights -> the [..., 11, Q] layout the 3-D curl-curl operator reads:
+    {attr, qw^2 / (w |J|), identity}."""
+    qd8 = np.asarray(qd8)
+    out = np.zeros(qd8.shape[:-2] + (11, qd8.shape[-1]))
+    out[..., 0, :] = qd8[..., 0, :]
+    out[..., 1, :] = np.asarray(qw2) ** 2 / qd8[..., 1, :]
+    out[..., 2, :] = out[..., 6, :] = out[..., 10, :] = 1.0
+    return out

@@ -64,3 +64,17 @@ def test_suite_coefficient(n_attr_global: int, kind: str = "matrix"):
             for d in range(3):
                 mc[k, d, d] = 10.0 * k + (d + 1.0)
     return attr_mat, mc
+
+
+def widen_scalar_ctx(blob1: np.ndarray) -> np.ndarray:
+    """A coefficient context of dimension 1 (what PopulateCoefficientContext(1, Q) builds for the scalar curl of 2-D elements,
+    integ/curlcurl.cpp:70) as the dimension-3 context of the same attribute -> material map with c * I materials."""
+    ints = np.ascontiguousarray(blob1).view(np.int32)[::2]
+    n_attr = int(ints[0])
+    n_mat = int(ints[1 + n_attr])
+    base = 2 + n_attr
+    out = np.zeros(base + 9 * n_mat, dtype=np.float64)
+    out[:base] = blob1[:base]
+    for k in range(n_mat):
+        out[base + 9 * k: base + 9 * (k + 1)] = (float(blob1[base + k]) * np.eye(3)).ravel(order="F")
+    return out

@@ -123,9 +123,33 @@ def main_mixed():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main32curl():
+    """tests/golden/qf32_curl_golden.npz: the reference's boundary curl-curl QFunction (scalar curl of a 2-D element in 3-D:
+    integ/curlcurl.cpp case 32 -> f_apply_l2_1, qfunctions/1/l2_1_qf.h, coefficient context of dimension 1) on the q-data of
+    qf32_golden.npz."""
+    ref = O.ref()
+    assert ref is not None, "oracle/_ref not built (needs /root/reference)"
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "qf32_golden.npz"))
+    rng = np.random.default_rng(20260926)
+    qd, qw = np.ascontiguousarray(G["qdata"]), np.ascontiguousarray(G["qw"])
+    Q = qd.shape[1]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_attr = 4
+    am = np.arange(n_attr) % 3
+    ctx1 = cf.coeff_ctx(am, np.array([1.5, 0.25, 7.0]), a=0.9, dim=1)
+    u = np.ascontiguousarray(rng.random(Q) - 0.5)
+    v = np.empty(Q)
+    assert ref.ref_apply_l2_1(p(ctx1), Q, p(qd), p(qw), p(u), p(v)) == 0
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "qf32_curl_golden.npz")
+    np.savez_compressed(path, ctx1=ctx1, u=u, v=v)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "32":
         main32()
+    elif len(sys.argv) > 1 and sys.argv[1] == "32curl":
+        main32curl()
     elif len(sys.argv) > 1 and sys.argv[1] == "mixed":
         main_mixed()
     else:

@@ -88,3 +88,49 @@ def test_boundary_mass_energy_of_a_constant_field(p):
     yz = O.apply_add(O.ND_MASS, interp, None, sp.idx, sp.orient, qd, cf.coeff_ctx(a=2.0), z, np.zeros(nd.ndofs))
     interior = np.setdiff1d(np.arange(nd.ndofs), nd.ess_dofs)
     assert np.abs(yz[interior]).max() == 0.0 and z @ yz > 0
+
+
+# ---- boundary curl-curl (scalar curl of the face element; integ/curlcurl.cpp case 32 -> f_apply_l2_1) ----
+GC = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qf32_curl_golden.npz"))
+
+
+def test_padded_3d_curlcurl_map_is_the_reference_l2_1():
+    """w = w' Jd^T C Jd c with the identity geometry factor, w' = qw^2 / (w |J|), C = coeff I and c = (curl, 0, 0)."""
+    qd11 = bs.curl32_qdata(G["qdata"], G["qw"])
+    c3 = np.zeros((3, GC["u"].size))
+    c3[0] = GC["u"]
+    ctx3 = cf.widen_scalar_ctx(GC["ctx1"])
+    _, w = O.apply_D(O.CURLCURL, np.ascontiguousarray(ctx3), np.ascontiguousarray(qd11), None, np.ascontiguousarray(c3))
+    assert _rel(w[0], GC["v"]) < 1e-14 and np.abs(w[1:]).max() == 0.0
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_boundary_curlcurl_energy_of_a_rigid_rotation(p):
+    """E = omega x r (in ND_p for p >= 2, curl E = 2 omega): x^T K_bdr x = sum over boundary faces of area (2 omega . n)^2."""
+    size = (1.0, 0.7, 0.9)
+    mesh = hm.box_mesh((3, 2, 2), size, warp_amp=0.0, scramble_seed=4, n_attr=1)
+    topo = hs.build_topology(mesh)
+    nd = hs.build_nd_space(mesh, topo, p)
+    om = np.array([0.3, -0.8, 0.5])
+    # ND dofs of E: tangential reference component at the dof's node (interpolatory tensor basis): u^_c = (J^T E)_c
+    op_, _ = hs.gauss_legendre(p)
+    cp_ = hs.gauss_lobatto(p + 1)
+    x = np.zeros(nd.ndofs)
+    for e in range(mesh.ne):
+        v = mesh.verts[mesh.elems[e]]
+        J = np.stack([v[1] - v[0], v[2] - v[0], v[4] - v[0]], axis=1)
+        for l, (c, i, j, k) in enumerate(hs._nd_lex_layout(p)):
+            ix = (i, j, k)
+            xi = np.array([op_[ix[d]] if d == c else cp_[ix[d]] for d in range(3)])
+            E = np.cross(om, v[0] + J @ xi)
+            x[nd.lex_gid[e, l]] = nd.lex_sign[e, l] * (J[:, c] @ E)
+    faces = bs.boundary_faces(topo)
+    sp = bs.build_nd_bdr_space(nd, faces)
+    deriv = bs.nd_quad_curl_tables(p)
+    _, qw2 = bs.nd_quad_tables(p)
+    xe = mesh.node_coords(1, hs.gauss_lobatto(2))
+    qd = bs.curl32_qdata(bs.bdr_qdata(xe, faces, 1, p + 1), qw2)
+    ctx3 = cf.widen_scalar_ctx(cf.coeff_ctx(np.array([0]), np.array([1.0]), a=1.0, dim=1))
+    y = O.apply_add(O.CURLCURL, None, deriv, sp.idx, sp.orient, qd, ctx3, x, np.zeros(nd.ndofs))
+    want = sum(2 * area * (2 * om[n_ax]) ** 2 for n_ax, area in ((0, size[1] * size[2]), (1, size[0] * size[2]), (2, size[0] * size[1])))
+    assert abs(x @ y - want) < 1e-11 * want
