@@ -264,7 +264,7 @@ def run_experiments(args):
         "complex_fused_and_pair_apply": (["tools/zfused_bench.py", "--steps", "50"], {}),
         "solver_loop_p3_2M": (["tools/solver_bench.py"], {}),
         "cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "4", "--refine", "0", "--nev", "4"], {}),
-        "tet_dense_p3_1M_dofs": (["tools/tet_bench.py", "--order", "3", "--n", "21", "--steps", "20"], {}),
+        "tet_dense_p3_1M_dofs": (["tools/tet_bench.py", "--order", "3", "--n", "21", "--steps", "20", "--terms"], {}),
         "tet_dense_p6_1M_dofs": (["tools/tet_bench.py", "--order", "6", "--n", "11", "--steps", "10"], {}),
         # BASELINE config 2 at size: cylinder cavity, ND order 4, p-multigrid {1, 2, 4}, Chebyshev order 8 + Hiptmair, 7.94M dofs
         "cylinder_cavity_p4_7p9M_dofs": (["tools/cylinder_bench.py", "--order", "4", "--refine", "3", "--nev", "2", "--tol", "1e-8",

@@ -134,7 +134,9 @@ int b2p_op_coarsen(b2p_op *fine, const b2p_op_desc *coarse_space, b2p_op **out);
 /* The same for dense-basis operators: P, Q, ne, lsize, idx, orient / curl_orient, interp / deriv of the coarse space are
  * read (tables at the fine operator's Q points); kind and coefficient come from `fine`. */
 int b2p_op_coarsen_dense(b2p_op *fine, const b2p_dense_op_desc *coarse_space, b2p_op **out);
-/* One operator for the real sum  sum_t coefs[t] * A_t  of sum-factorised ND operators over the same geometry, space and
+/* (Dense-basis terms -- b2p_op_create_dense with kinds CURLCURL / ND_MASS / CURLCURL_MASS on one geometry handle, space and
+ * orientation -- fuse the same way: one stacked table, summed per-element tensors.)
+ * One operator for the real sum  sum_t coefs[t] * A_t  of sum-factorised ND operators over the same geometry, space and
  * essential set (BuildParSumOperator(a0 K + a1 C + a2 M), linalg/rap.cpp:764-829): the terms differ only in their pointwise
  * coefficient, so the sum runs as ONE element-kernel launch (one geometry stream) instead of one per term.
  * b2p_operator_par does this by itself when its terms qualify. The result is independent of the terms afterwards, except

@@ -298,6 +298,8 @@ public:
     cudaFree(d_ess);
     cudaFree(zcoef);
     cudaFree(zcoef_h);
+    if (sum_re) b2p_op_destroy(sum_re);
+    if (sum_im) b2p_op_destroy(sum_im);
   }
 
   // Fused path: when every term is a sum-factorised ND operator over the same geometry, space and essential set,
@@ -313,6 +315,27 @@ public:
     const char *env = std::getenv("B2P_COMPLEX_FUSED");
     if (env && env[0] == '0') return;
     const b2p_op *o0 = terms[0].op;
+    if (o0->dense && terms.size() >= 2)
+    {
+      // Dense-basis terms (tets, prisms) have no complex element kernel; their sum still collapses to TWO real dense operators,
+      // S_re = sum_t c_t^r A_t and S_im = sum_t c_t^i A_t (b2p_op_create_sum: stacked tables, summed per-element tensors), so a
+      // complex matvec costs 4 dense applies (2 when every c_t^i = 0) instead of 2-4 per term.
+      std::vector<b2p_op *> ops;
+      std::vector<double> cr, ci;
+      for (auto &t : terms)
+      {
+        ops.push_back(t.op);
+        cr.push_back(t.cr);
+        ci.push_back(t.ci);
+      }
+      if (b2p_op_create_sum(ctx, (int)ops.size(), ops.data(), cr.data(), &sum_re) == B2P_SUCCESS &&
+          b2p_op_create_sum(ctx, (int)ops.size(), ops.data(), ci.data(), &sum_im) == B2P_SUCCESS)
+        return;
+      if (sum_re) b2p_op_destroy(sum_re);
+      if (sum_im) b2p_op_destroy(sum_im);
+      sum_re = sum_im = nullptr;  // not fusable (mixed kinds / spaces): term by term
+      return;
+    }
     for (auto &t : terms)
     {
       const b2p_op *o = t.op;
@@ -393,6 +416,13 @@ public:
       terms[t].ci = ci[t];
     }
     if (fused) fused = fill_fused();
+    if (sum_re)
+    {
+      std::vector<b2p_op *> ops;
+      for (auto &t : terms) ops.push_back(t.op);
+      b2p_op_sum_set_coefficients(sum_re, (int)ops.size(), ops.data(), cr);
+      b2p_op_sum_set_coefficients(sum_im, (int)ops.size(), ops.data(), ci);
+    }
   }
 
   // operator.cpp:98-134 with A = sum_i c_i A_i: y_r = sum (c^r A x_r - c^i A x_i), y_i = sum (c^i A x_r + c^r A x_i);
@@ -424,6 +454,27 @@ public:
     if (fused && launch_nd_hex_apply4z(o0, fused_kind, o0->lidx_bc, herm ? zcoef_h : zcoef, fused_imag ? 1 : 0, alpha, x.re, x.im, y.re,
                                        y.im, s) == B2P_SUCCESS)
       n_fused_applies++;
+    else if (sum_re)
+    {
+      bool any_re = false, any_im = false;
+      for (auto &t : terms)
+      {
+        any_re = any_re || t.cr != 0.0;
+        any_im = any_im || t.ci != 0.0;
+      }
+      const double si = herm ? -alpha : alpha;
+      if (any_re)
+      {
+        b2p_op_apply_add_ex(sum_re, alpha, x.re, y.re, B2P_APPLY_MASKED, s);
+        b2p_op_apply_add_ex(sum_re, alpha, x.im, y.im, B2P_APPLY_MASKED, s);
+      }
+      if (any_im)
+      {
+        b2p_op_apply_add_ex(sum_im, -si, x.im, y.re, B2P_APPLY_MASKED, s);
+        b2p_op_apply_add_ex(sum_im, si, x.re, y.im, B2P_APPLY_MASKED, s);
+      }
+      n_fused_applies++;
+    }
     else
     for (auto &t : terms)
     {
@@ -491,6 +542,7 @@ private:
   int32_t *d_ess = nullptr;
   // fused complex element operator (build_fused)
   bool fused = false, fused_imag = false;
+  b2p_op *sum_re = nullptr, *sum_im = nullptr;  // dense-basis terms: the real and imaginary coefficient sums as two dense operators
   int fused_kind = 0;
   double *zcoef = nullptr, *zcoef_h = nullptr;
   std::vector<std::vector<double>> fused_e18;  // host copies of the terms' per-element material tensors

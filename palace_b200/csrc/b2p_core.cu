@@ -883,14 +883,24 @@ int b2p_op_create_sum(b2p_ctx *ctx, int n_terms, b2p_op *const *ops, const doubl
   const b2p_op *o0 = ops[0];
   const size_t nidx = (size_t)o0->ne * o0->PS;
   std::vector<int32_t> a(nidx), b(nidx);
+  const bool dense = o0 && o0->dense;  // dense-basis terms (tets, prisms, faces) fuse the same way: one stacked table, summed tensors
   for (int t = 0; t < n_terms; t++)
   {
     const b2p_op *o = ops[t];
-    B2P_CHECK(ctx, o && !o->dense && !o->assembled && o->kind != B2P_H1_DIFFUSION && o->ecoef, B2P_ERR_UNSUPPORTED,
-              "b2p_op_create_sum: term %d is not a sum-factorised ND operator with on-the-fly coefficients", t);
+    B2P_CHECK(ctx, o && o->dense == dense && !o->assembled && o->kind >= B2P_CURLCURL && o->kind <= B2P_CURLCURL_MASS && o->ecoef,
+              B2P_ERR_UNSUPPORTED, "b2p_op_create_sum: term %d is not an ND curl-curl / mass operator with on-the-fly coefficients", t);
     B2P_CHECK(ctx, o->geom == o0->geom && o->p == o0->p && o->q1d == o0->q1d && o->ne == o0->ne && o->lsize == o0->lsize && o->PS == o0->PS &&
+                       o->P == o0->P && o->dense_Ppad == o0->dense_Ppad && (o->curl_orient != nullptr) == (o0->curl_orient != nullptr) &&
                        (o->lidx_bc != nullptr) == (o0->lidx_bc != nullptr),
               B2P_ERR_UNSUPPORTED, "b2p_op_create_sum: term %d lives on another geometry / space", t);
+    if (dense && o->curl_orient && t > 0)
+    {
+      const size_t nco = (size_t)o0->ne * o0->P * 3;
+      std::vector<int8_t> c0(nco), ct(nco);
+      B2P_CUDA(ctx, cudaMemcpy(c0.data(), o0->curl_orient, nco, cudaMemcpyDeviceToHost));
+      B2P_CUDA(ctx, cudaMemcpy(ct.data(), o->curl_orient, nco, cudaMemcpyDeviceToHost));
+      B2P_CHECK(ctx, c0 == ct, B2P_ERR_UNSUPPORTED, "b2p_op_create_sum: term %d has another orientation of its element dofs", t);
+    }
     for (int which = 0; which < 2; which++)
     {
       const int32_t *p0 = which ? o0->lidx_bc : o0->lidx, *pt = which ? o->lidx_bc : o->lidx;
@@ -922,8 +932,34 @@ int b2p_op_create_sum(b2p_ctx *ctx, int n_terms, b2p_op *const *ops, const doubl
     if (cudaMalloc((void **)dst, n * sizeof(T)) != cudaSuccess) return B2P_ERR_CUDA;
     return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice) == cudaSuccess ? B2P_SUCCESS : B2P_ERR_CUDA;
   };
-  if ((rc = dup(o0->lidx, nidx, &op->lidx)) || (rc = dup(o0->lidx_bc, nidx, &op->lidx_bc)) || (rc = dup(o0->tab, o0->h_tab.size(), &op->tab)) ||
-      (rc = sum_fill_coefficients(op, n_terms, ops, coefs)))
+  if (dense)
+  {
+    // stacked table of the sum: the value block of a term that has one, then the curl block of a term that has one (the
+    // terms tabulate the same element at the same points, so whichever term supplies a block supplies the same numbers)
+    const b2p_op *tu = nullptr, *tc = nullptr;
+    for (int t = 0; t < n_terms; t++)
+    {
+      if (!tu && ops[t]->dense_row_u >= 0 && ops[t]->kind != B2P_CURLCURL) tu = ops[t];
+      if (!tc && ops[t]->dense_row_c >= 0 && ops[t]->kind != B2P_ND_MASS) tc = ops[t];
+    }
+    const int Q = o0->geom->Q, Ppad = o0->dense_Ppad, blk = 3 * Q;
+    op->dense = true;
+    op->dense_Ppad = Ppad;
+    op->dense_row_u = tu ? 0 : -1;
+    op->dense_row_c = tc ? (tu ? blk : 0) : -1;
+    op->dense_Rpad = (((tu ? blk : 0) + (tc ? blk : 0)) + 7) & ~7;
+    std::vector<double> T((size_t)op->dense_Rpad * Ppad, 0.0);
+    if (tu && cudaMemcpy(T.data(), tu->dense_T + (size_t)tu->dense_row_u * Ppad, sizeof(double) * blk * Ppad, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = B2P_ERR_CUDA;
+    if (!rc && tc &&
+        cudaMemcpy(T.data() + (size_t)op->dense_row_c * Ppad, tc->dense_T + (size_t)tc->dense_row_c * Ppad, sizeof(double) * blk * Ppad,
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = B2P_ERR_CUDA;
+    if (!rc) rc = upload(ctx, T.data(), T.size(), &op->dense_T);
+    if (!rc) rc = dup(o0->curl_orient, (size_t)o0->ne * o0->P * 3, &op->curl_orient);
+  }
+  if (rc || (rc = dup(o0->lidx, nidx, &op->lidx)) || (rc = dup(o0->lidx_bc, nidx, &op->lidx_bc)) ||
+      (rc = dup(o0->tab, o0->h_tab.size(), &op->tab)) || (rc = sum_fill_coefficients(op, n_terms, ops, coefs)))
   {
     set_error(ctx, "b2p_op_create_sum: device allocation / copy failed");
     b2p_op_destroy(op);
