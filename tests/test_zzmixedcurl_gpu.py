@@ -162,3 +162,32 @@ def test_floquet_terms_in_a_complex_operator(b2p_ctx):
     A.mult(_dev(x.real), _dev(x.imag), yr, yi)
     y = yr.cpu().numpy() + 1j * yi.cpu().numpy()
     assert _rel(y, Z @ x) < RTOL
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_mixed_curl_kinds_on_scrambled_tetrahedra(b2p_ctx, p):
+    """Real simplex tables, the tridiagonal curl-oriented restriction of scrambled ND tets (restriction.cpp:301-368), curved
+    (quadratic) geometry: both kinds against the oracle, and the integration-by-parts identity the Floquet terms rest on --
+    with F constant and u, v vanishing tangentially on the boundary, (F^T curl u, v) = (curl u, F v) and -(F u, curl v) are
+    transposes of each other up to sign: x^T (A_weak(F) + A_curl(F^T-context)) x = 0 for every x."""
+    from palace_b200 import capi
+    from palace_b200.host import tetspace as ts
+
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.25, scramble_seed=5, n_attr=2, warp_amp=0.03)
+    sp = ts.build_nd_tet_space(mesh, p)
+    interp, curl, qpts, qw = ts.nd_tet_tables(p)
+    qd = ts.geom_qdata(mesh.node_coords(2), mesh.attr, 2, qpts, qw)
+    geom = capi.Geom.general(b2p_ctx, qd)
+    rng = np.random.default_rng(8)
+    x = rng.random(sp.ndofs) - 0.5
+    ys = {}
+    for kind in (O.ND_WEAKCURL, O.ND_MIXEDCURL):
+        blob = periodic_ctx(kind, 2)
+        op = capi.Op.create_dense(b2p_ctx, geom, kind, sp.ndofs, sp.idx, None, interp, curl, blob, curl_orient=sp.curl_orient)
+        y_ref = O.apply_add_co(kind, interp, curl, sp.idx, sp.curl_orient, qd, blob, x, np.zeros(sp.ndofs))
+        yd = torch.empty(sp.ndofs, dtype=torch.float64, device="cuda")
+        op.apply(_dev(x), yd)
+        assert _rel(yd.cpu().numpy(), y_ref) < RTOL
+        ys[kind] = yd.cpu().numpy()
+    # the two contexts of periodic_ctx hold -F and F^T of the SAME F: the pair is skew-symmetric
+    assert abs(x @ (ys[O.ND_WEAKCURL] + ys[O.ND_MIXEDCURL])) < 1e-12 * np.linalg.norm(x) * np.linalg.norm(ys[O.ND_WEAKCURL])
