@@ -162,3 +162,62 @@ def build_constrained_nd_space(hb: HangingBox, p: int, tol=1e-10) -> Constrained
     Pm.sum_duplicates()
     ess = true_of[np.nonzero(on_bdr & ~is_slave)[0]]
     return ConstrainedSpace(space, Pm, true_of, np.sort(ess), slaves)
+
+
+def build_constrained_h1_space(hb: HangingBox, p: int, tol=1e-10) -> ConstrainedSpace:
+    """The auxiliary (H1) space of the same mesh: a fine-side node in the interface plane that is not a coarse node takes the value
+    of the master's nodal interpolant there (continuity of the scalar potential; the discrete gradients of such functions are the
+    constrained ND fields' gradients, so R_nd G P_h1 maps true dofs to true dofs)."""
+    mesh = hb.mesh
+    topo = hs.build_topology(mesh)
+    space = hs.build_h1_space(mesh, topo, p)
+    ne, P = space.lex_gid.shape
+    n = p + 1
+    cp = hs.gauss_lobatto(n)
+    xI = hb.x_interface
+    aff = [_affine(mesh, e) for e in range(ne)]
+    ref_node = np.array([[cp[i], cp[j], cp[k]] for k in range(n) for j in range(n) for i in range(n)])
+    masters = [e for e in range(ne) if hb.coarse[e] and np.any(np.abs(mesh.verts[mesh.elems[e], 0] - xI) < tol)]
+    boxes = {e: (mesh.verts[mesh.elems[e]].min(axis=0), mesh.verts[mesh.elems[e]].max(axis=0)) for e in masters}
+    coarse_gids = set(int(g) for e in range(ne) if hb.coarse[e] for g in space.lex_gid[e])
+    rows = {}
+    on_bdr = np.zeros(space.ndofs, dtype=bool)
+    L = np.array(hb.size)
+    for e in range(ne):
+        x0, J = aff[e]
+        for l in range(P):
+            xp = x0 + J @ ref_node[l]
+            if any(abs(xp[d]) < tol or abs(xp[d] - L[d]) < tol for d in range(3)):
+                on_bdr[space.lex_gid[e, l]] = True
+            s = int(space.lex_gid[e, l])
+            if hb.coarse[e] or abs(xp[0] - xI) > tol or s in coarse_gids or s in rows:
+                continue
+            C = next(m for m in masters if np.all(xp >= boxes[m][0] - tol) and np.all(xp <= boxes[m][1] + tol))
+            xc0, JC = aff[C]
+            xiC = np.linalg.solve(JC, xp - xc0)
+            B = [hs.lagrange_table(cp, [xiC[d]])[0][0] for d in range(3)]
+            w = np.array([B[0][i] * B[1][j] * B[2][k] for k in range(n) for j in range(n) for i in range(n)])
+            keep = np.abs(w) > 1e-14
+            rows[s] = (space.lex_gid[C][keep], w[keep])
+    slaves = np.array(sorted(rows), dtype=np.int64)
+    is_slave = np.zeros(space.ndofs, dtype=bool)
+    is_slave[slaves] = True
+    n_true = int((~is_slave).sum())
+    true_of = -np.ones(space.ndofs, dtype=np.int64)
+    true_of[~is_slave] = np.arange(n_true)
+    ri, ci, vi = [np.nonzero(~is_slave)[0]], [true_of[~is_slave]], [np.ones(n_true)]
+    for s, (g, w) in rows.items():
+        assert not is_slave[g].any()
+        ri.append(np.full(len(g), s))
+        ci.append(true_of[g])
+        vi.append(w)
+    Pm = sp.coo_matrix((np.concatenate(vi), (np.concatenate(ri), np.concatenate(ci))), shape=(space.ndofs, n_true)).tocsr()
+    Pm.sum_duplicates()
+    ess = true_of[np.nonzero(on_bdr & ~is_slave)[0]]
+    return ConstrainedSpace(space, Pm, true_of, np.sort(ess), slaves)
+
+
+def restriction_matrix(cs: ConstrainedSpace) -> sp.csr_matrix:
+    """R [n_true x ndofs_L]: selects the true dofs of an L-vector (FiniteElementSpace::GetRestrictionMatrix on conforming dofs)."""
+    tr = np.nonzero(cs.true_of >= 0)[0]
+    return sp.csr_matrix((np.ones(tr.size), (cs.true_of[tr], tr)), shape=(cs.P.shape[1], cs.space.ndofs))

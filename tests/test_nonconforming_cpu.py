@@ -70,3 +70,22 @@ def test_constrained_cavity_eigenvalues_match_the_closed_form():
     assert np.allclose(w[:6], exact, rtol=5e-5), (w[:6], exact)
     # no spurious modes between the null space and the first cavity mode
     assert w[0] > 0.9999 * exact[0]
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_constrained_gradients_are_constrained_fields(p):
+    """The discrete de Rham property the Hiptmair smoother relies on survives the constraints: G (P_h1 phi) = P_nd (R_nd G P_h1 phi)
+    for every true-dof potential, i.e. gradients of continuous potentials are tangentially continuous ND fields, and the
+    constrained curl-curl matrix annihilates them."""
+    hb = nc.hanging_box_mesh(nc=(1, 2, 1), nfx=2, h=1.0, scramble_seed=p)
+    cn, ch = nc.build_constrained_nd_space(hb, p), nc.build_constrained_h1_space(hb, p)
+    assert np.array_equal(ch.P.sum(axis=1).A1.round(12), np.ones(ch.space.ndofs))  # partition of unity: constants are reproduced
+    G = common.oracle_interp(ch.space, cn.space, hs.discrete_gradient_matrix(p))
+    R = nc.restriction_matrix(cn)
+    phi = np.random.default_rng(0).random(ch.P.shape[1])
+    gL = G @ (ch.P @ phi)
+    assert np.abs(cn.P @ (R @ gL) - gL).max() < 1e-12 * np.abs(gL).max()
+    prob = common.problem_on_mesh(hb.mesh, p)
+    K = common.oracle_matrix(prob, O.CURLCURL, common.coefficient(O.CURLCURL, 1, "const"), eliminate=False)
+    Kt = cn.P.T @ K @ cn.P
+    assert np.abs(Kt @ (R @ gL)).max() < 1e-11 * abs(Kt).max() * np.abs(gL).max()

@@ -186,3 +186,91 @@ def test_p_multigrid_on_the_non_conforming_mesh(b2p_ctx):
     st = K.stats()
     assert st["converged"], st  # (57 iterations: Chebyshev alone, without the auxiliary-space correction, smooths ND operators poorly)
     assert _rel(xd.cpu().numpy(), spla.spsolve(At[2].tocsc(), b)) < 1e-8
+
+
+def test_hiptmair_multigrid_on_the_non_conforming_mesh(b2p_ctx):
+    """The reference's production preconditioner on the mesh with hanging faces: p-multigrid {1, 2} with Chebyshev + auxiliary-space
+    (Hiptmair) smoothing (distrelaxation.cpp:99-151) -- ND and H1 level operators from b2p_operator_rap, discrete gradients
+    R_nd G P_h1 and the level prolongation R I P from b2p_operator_triple -- one V-cycle against oracle/solvers.py, and FGMRES
+    converging in a handful of iterations where plain Chebyshev smoothing needed 57."""
+    from palace_b200 import capi
+    from palace_b200.host import assemble as asm
+    from palace_b200.host import hexspace as hs
+
+    hb = nc.hanging_box_mesh(nc=(1, 2, 1), nfx=2, h=1.0, scramble_seed=9, n_attr=2)
+    prob = common.problem_on_mesh(hb.mesh, 2)
+    kind = O.CURLCURL_MASS
+    blob = common.coefficient(kind, 2, "matrix", a_mass=1.0, a_curl=0.5)
+    blob_h1 = common.coefficient(O.H1_DIFFUSION, 2, "matrix", a_mass=1.0)
+    geom = common.gpu_geom(b2p_ctx, prob)
+    orders = (1, 2)
+    nd = {1: hs.build_nd_space(hb.mesh, prob.topo, 1), 2: prob.nd}
+    h1 = {1: hs.build_h1_space(hb.mesh, prob.topo, 1), 2: prob.h1}
+    cn = {p: nc.build_constrained_nd_space(hb, p) for p in orders}
+    ch = {p: nc.build_constrained_h1_space(hb, p) for p in orders}
+    op = {2: common.gpu_op(b2p_ctx, geom, prob, kind, blob)}
+    oph = {2: common.gpu_op(b2p_ctx, geom, prob, O.H1_DIFFUSION, blob_h1)}
+    t = hs.tables_1d(1, prob.q1d)
+    idx, ori = nd[1].native_restriction()
+    op[1] = op[2].coarsen(1, nd[1].ndofs, idx, ori, nd[1].dof_map, t.Bo, t.Bc, t.Gc)
+    oph[1] = oph[2].coarsen(1, h1[1].ndofs, h1[1].lex_gid.astype(np.int32), None, None, None, t.Bc, t.Gc)
+    A, AG, G, At, AGt, Gt, dA, dG, keep = {}, {}, {}, {}, {}, {}, {}, {}, []
+
+    def rap(local_op, cs, nL, AL):
+        Aloc = capi.Operator.par(b2p_ctx, nL, nL, [local_op], None, None, diag_policy=1)
+        Pm = capi.SpMat(b2p_ctx, cs.P)
+        keep.extend([Aloc, Pm])
+        d = abs(cs.P).T @ AL.diagonal()
+        d[cs.ess_tdofs] = 1.0
+        return capi.operator_rap(b2p_ctx, Aloc, Pm, cs.ess_tdofs, diag_policy=1), Pm, S.eliminate((cs.P.T @ AL @ cs.P).tocsr(), cs.ess_tdofs), d
+
+    Pnd, Ph1 = {}, {}
+    for p in orders:
+        A[p], Pnd[p], At[p], dA[p] = rap(op[p], cn[p], nd[p].ndofs, common.oracle_matrix(prob, kind, blob, space=nd[p], eliminate=False))
+        AG[p], Ph1[p], AGt[p], dG[p] = rap(oph[p], ch[p], h1[p].ndofs, common.oracle_matrix(prob, O.H1_DIFFUSION, blob_h1, space=h1[p], eliminate=False))
+        Gloc = common.gpu_interp(b2p_ctx, h1[p], nd[p], asm.gradient_comps(p))
+        Rn = nc.restriction_matrix(cn[p])
+        G[p] = capi.operator_triple(b2p_ctx, capi.SpMat(b2p_ctx, Rn), Gloc, Ph1[p])
+        Gt[p] = (Rn @ common.oracle_interp(h1[p], nd[p], hs.discrete_gradient_matrix(p)) @ ch[p].P).tocsr()
+        keep.append(Gloc)
+    I_loc = common.gpu_interp(b2p_ctx, nd[1], nd[2], asm.nd_prolongation_comps(1, 2))
+    R2 = nc.restriction_matrix(cn[2])
+    Plev = capi.operator_triple(b2p_ctx, capi.SpMat(b2p_ctx, R2), I_loc, Pnd[1])
+    Por = (R2 @ common.oracle_interp(nd[1], nd[2], hs.nd_prolongation_matrix(1, 2)) @ cn[1].P).tocsr()
+    rng = np.random.default_rng(5)
+    xg = rng.standard_normal(Gt[2].shape[1])
+    yg = torch.empty(Gt[2].shape[0], dtype=torch.float64, device="cuda")
+    G[2].mult(_dev(xg), yg)
+    assert _rel(yg.cpu().numpy(), Gt[2] @ xg) < 1e-13
+    order = 4
+    coarse = capi.Solver.krylov(b2p_ctx, 0, rel_tol=1e-13, max_it=2000)
+    cj = capi.Solver.jacobi(b2p_ctx)
+    cj.set_operator(A[1])
+    coarse.set_preconditioner(cj)
+    coarse.set_operator(A[1])
+    M = capi.Solver.gmg(b2p_ctx, coarse, [Plev], [G[1], G[2]], cycle_it=1, smooth_it=1, cheby_order=order, sf_max=1.0, sf_min=0.0,
+                        fourth_kind=True)
+    M.gmg_set_operators([A[1], A[2]], [AG[1], AG[2]])
+    c1, c2 = capi.Solver.chebyshev(b2p_ctx, 1, order), capi.Solver.chebyshev(b2p_ctx, 1, order)
+    c1.set_operator(A[2])
+    c2.set_operator(AG[2])
+    sm = S.DistRelax(At[2], AGt[2], Gt[2], ch[2].ess_tdofs, c1.lambda_max(), c2.lambda_max(), order)
+    sm.dinv, sm.dinv_G = 1.0 / dA[2], 1.0 / dG[2]
+    lu = spla.splu(At[1].tocsc())
+    ref = S.Gmg([At[1], At[2]], [Por], [None, sm], lambda v: lu.solve(v), [cn[1].ess_tdofs, cn[2].ess_tdofs])
+    n = At[2].shape[0]
+    x = rng.standard_normal(n)
+    x[cn[2].ess_tdofs] = 0.0
+    yd = torch.empty(n, dtype=torch.float64, device="cuda")
+    M.mult(_dev(x), yd)
+    assert _rel(yd.cpu().numpy(), ref.mult(x)) < 5e-3
+    K = capi.Solver.krylov(b2p_ctx, 2, rel_tol=1e-10, max_it=60, max_dim=60)
+    K.set_operator(A[2])
+    K.set_preconditioner(M)
+    b = rng.standard_normal(n)
+    b[cn[2].ess_tdofs] = 0.0
+    xd = torch.zeros(n, dtype=torch.float64, device="cuda")
+    K.mult(_dev(b), xd)
+    st = K.stats()
+    assert st["converged"] and st["its"] <= 25, st
+    assert _rel(xd.cpu().numpy(), spla.spsolve(At[2].tocsc(), b)) < 1e-8
