@@ -159,6 +159,123 @@ inline b2p_op *CreateHexNDIntegrator(b2p_ctx *ctx, b2p_geom *geom, int kind, con
   return op;
 }
 
+// ---- non-tensor elements (tetrahedra, prisms, pyramids; any vector element libCEED sees through dense tables) --------------
+// What InitNonTensorBasis (fem/libceed/basis.cpp:40-85) and InitNativeRestr (fem/libceed/restriction.cpp:207-385) gather, as the
+// arrays of a b2p_dense_op_desc: the FULL DofToQuad tables Bt / Gt ARE interp[3][Q][P] / deriv[3][Q][P]; element dofs with the
+// -1-d sign encoding; with a DofTransformation (ND tets / prisms of order >= 2) the int8 tridiagonal rows, filled column by
+// column from InvTransformPrimal exactly as restriction.cpp:301-329 does.
+struct DenseNDSpaceInputs
+{
+  int P = 0, Q = 0, ne = 0;
+  long long lsize = 0;
+  std::vector<int32_t> idx;
+  std::vector<int8_t> orient, curl_orient;  // one of the two is filled
+  std::vector<double> interp, deriv;
+};
+
+inline DenseNDSpaceInputs GatherDenseNDSpace(const mfem::FiniteElementSpace &fes, const mfem::IntegrationRule &ir)
+{
+  DenseNDSpaceInputs in;
+  const auto *fe = dynamic_cast<const mfem::VectorFiniteElement *>(fes.GetFE(0));
+  MFEM_VERIFY(fe && fe->GetDim() == 3, "GatherDenseNDSpace: a 3-D vector finite element is required!");
+  const mfem::DofToQuad &maps = fe->GetDofToQuad(ir, mfem::DofToQuad::FULL);
+  in.P = maps.ndof;
+  in.Q = maps.nqpt;
+  in.ne = fes.GetNE();
+  in.lsize = fes.GetVSize();
+  MFEM_VERIFY((int)maps.Bt.size() == 3 * in.Q * in.P && (int)maps.Gt.size() == 3 * in.Q * in.P, "unexpected FULL table sizes!");
+  in.interp = maps.Bt;
+  in.deriv = maps.Gt;
+  const int P = in.P;
+  in.idx.resize((size_t)in.ne * P);
+  mfem::Array<int> dofs;
+  mfem::Vector col(P);
+  bool any_trans = false;
+  for (int e = 0; e < in.ne && !any_trans; e++) any_trans = fes.GetElementDofs(e, dofs, 0) != nullptr;
+  if (any_trans)
+    in.curl_orient.assign((size_t)in.ne * P * 3, 0);
+  else
+    in.orient.resize((size_t)in.ne * P);
+  for (int e = 0; e < in.ne; e++)
+  {
+    const mfem::DofTransformation *dt = fes.GetElementDofs(e, dofs, 0);
+    MFEM_VERIFY(dofs.Size() == P, "element dof count differs from the table!");
+    for (int j = 0; j < P; j++)
+    {
+      const int d = dofs[j];
+      in.idx[(size_t)e * P + j] = d >= 0 ? d : -1 - d;
+      if (!any_trans)
+      {
+        in.orient[(size_t)e * P + j] = d >= 0 ? 1 : -1;
+        continue;
+      }
+      // column j of the element's transformation, scaled by the sign of dof j (restriction.cpp:301-329)
+      col = 0.0;
+      col[j] = 1.0;
+      if (dt) dt->InvTransformPrimal(col);
+      const double sj = d >= 0 ? 1.0 : -1.0;
+      int8_t *co = in.curl_orient.data() + (size_t)e * P * 3;
+      co[3 * j + 1] = (int8_t)(sj * col[j]);
+      if (j > 0) co[3 * (j - 1) + 2] = (int8_t)(sj * col[j - 1]);
+      if (j < P - 1) co[3 * (j + 1) + 0] = (int8_t)(sj * col[j + 1]);
+    }
+  }
+  return in;
+}
+
+// q-data of any element type at the points of `ir` (Mesh::GetCeedGeomFactorData + f_build_geom_factor_33, fem/mesh.cpp:146-209,
+// qfunctions/33/geom_33_qf.h:9-34): {attr, w detJ, adj(J)^T / detJ = J^-T column-major} from the element transformations.
+inline b2p_geom *CreateGeneralGeometry(b2p_ctx *ctx, const mfem::Mesh &mesh, const mfem::IntegrationRule &ir)
+{
+  const int ne = mesh.GetNE(), Q = ir.GetNPoints();
+  std::vector<double> qd((size_t)ne * 11 * Q);
+  for (int e = 0; e < ne; e++)
+  {
+    mfem::ElementTransformation *T = mesh.GetElementTransformation(e);
+    for (int q = 0; q < Q; q++)
+    {
+      const mfem::IntegrationPoint &ip = ir.IntPoint(q);
+      T->SetIntPoint(&ip);
+      const mfem::DenseMatrix &J = T->Jacobian();
+      const double det = T->Weight();
+      double *o = qd.data() + (size_t)e * 11 * Q + q;
+      o[0] = mesh.GetAttribute(e);
+      o[(size_t)Q] = ip.weight * det;
+      // J^-T = cofactor(J) / det, stored column-major: entry (r, c) at 2 + r + 3 c
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++)
+        {
+          const int r1 = (r + 1) % 3, r2 = (r + 2) % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+          o[(size_t)(2 + r + 3 * c) * Q] = (J(r1, c1) * J(r2, c2) - J(r1, c2) * J(r2, c1)) / det;
+        }
+    }
+  }
+  b2p_geom *geom = nullptr;
+  Check(b2p_geom_create_qdata_general(ctx, ne, Q, qd.data(), &geom), ctx);
+  return geom;
+}
+
+inline b2p_op *CreateDenseNDIntegrator(b2p_ctx *ctx, b2p_geom *geom, int kind, const DenseNDSpaceInputs &in, const void *coeff_ctx,
+                                       size_t coeff_ctx_bytes)
+{
+  b2p_dense_op_desc d = {};
+  d.kind = kind;
+  d.P = in.P;
+  d.Q = in.Q;
+  d.ne = in.ne;
+  d.lsize = in.lsize;
+  d.idx = in.idx.data();
+  d.orient = in.orient.empty() ? nullptr : in.orient.data();
+  d.curl_orient = in.curl_orient.empty() ? nullptr : in.curl_orient.data();
+  d.interp = in.interp.data();
+  d.deriv = in.deriv.data();
+  d.coeff_ctx = coeff_ctx;
+  d.coeff_ctx_bytes = coeff_ctx_bytes;
+  b2p_op *op = nullptr;
+  Check(b2p_op_create_dense(ctx, geom, &d, &op), ctx);
+  return op;
+}
+
 // Same five methods as ceed::Operator; sub-operators are b2p_op handles created by the integrator glue.
 class Operator : public mfem::Operator
 {

@@ -230,6 +230,9 @@ int b2p_operator_mult(b2p_operator *A, const double *x, double *y)
 int b2p_operator_mult_transpose(b2p_operator *A, const double *x, double *y)
 {
   if (!A) return B2P_ERR_ARG;
+  if (auto *pa = dynamic_cast<ParOperator *>(A->op.get()))
+    B2P_CHECK(pa->ctx, pa->TransposeAvailable(), B2P_ERR_UNSUPPORTED,
+              "b2p_operator_mult_transpose: non-symmetric terms (B2P_ND_WEAKCURL / B2P_ND_MIXEDCURL) on a partitioned space are not supported");
   B2P_TRY(A->op->ctx, A->op->MultTranspose(x, y));
   return B2P_SUCCESS;
 }

@@ -142,6 +142,14 @@ public:
   // Symmetric terms: Mult. With a non-symmetric term (B2P_ND_WEAKCURL / B2P_ND_MIXEDCURL) the local operators are applied
   // transposed (single partition; the reference has no transpose of its BilinearForm operators at all, libceed/operator.cpp:60-99).
   void MultTranspose(const double *x, double *y) const override;
+  // false: a non-symmetric term on a partitioned space (the transposed local apply is not plumbed through the halo path)
+  bool TransposeAvailable() const
+  {
+    if (!halo) return true;
+    for (auto &t : terms)
+      if (t.op->kind == B2P_ND_WEAKCURL || t.op->kind == B2P_ND_MIXEDCURL) return false;
+    return true;
+  }
   void AddMult(const double *x, double *y, double a = 1.0) const override;
   bool NativeAddMult() const override { return halo == nullptr; }
   void AssembleDiagonal(double *d) const override;

@@ -3,12 +3,15 @@
 // the emulation build of the kernels on a CPU box, against libb2p.so on a GPU box -- and compares with the oracle's dense
 // reference-style apply (liboracle.so). The "MFEM" is tests/mock_mfem/mfem.hpp, filled with what MFEM would hold for the mesh:
 // native ND dof numbering with sign flips (-1-d), H1 nodes in MFEM's native (vertex) order, column-major DofToQuad tables.
-//   glue_exec <coeff_ctx.bin> <order>      prints "GLUE_EXEC OK apply_err=... diag_err=..."
+//   glue_exec <coeff_ctx.bin> <order> [hex | dense | dense_co]     prints "GLUE_EXEC OK apply_err=... diag_err=..."
+// "dense": the same mesh through the non-tensor glue (GatherDenseNDSpace, CreateGeneralGeometry, CreateDenseNDIntegrator: FULL
+// DofToQuad tables, element transformations); "dense_co": with element DofTransformations (tridiagonal curl orientation).
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <random>
+#include <string>
 #include <vector>
 
 #include "b2p_palace.hpp"
@@ -22,6 +25,8 @@ void orc_gauss_legendre(int n, double *x, double *w);
 void orc_geom_hex_qdata(int ne, int k, int q1d, const double *xe, const int *attr, double *qdata);
 void orc_apply_add(int kind, int ne, int P, int Q, const double *interp, const double *deriv, const int *idx, const signed char *orient,
                    const double *qdata, const void *ctx, const double *x, double *y);
+void orc_apply_add_co(int kind, int ne, int P, int Q, const double *interp, const double *deriv, const int *idx, const signed char *co,
+                      const double *qdata, const void *ctx, const double *x, double *y);
 void orc_diag_add(int kind, int ne, int P, int Q, const double *interp, const double *deriv, const int *idx, const double *qdata,
                   const void *ctx, double *diag);
 }
@@ -41,6 +46,7 @@ int main(int argc, char **argv)
   std::vector<char> blob((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
   const int p = std::atoi(argv[2]), q1d = p + 1, n = p + 1, P = 3 * p * n * n, Q = q1d * q1d * q1d;
   const int kind = B2P_CURLCURL_MASS;
+  const std::string mode = argc > 3 ? argv[3] : "hex";
 
   // ---- what MFEM holds: two hexahedra side by side, trilinear nodes (slightly distorted), ND space of order p ----
   const int ne = 2;
@@ -129,10 +135,72 @@ int main(int argc, char **argv)
     std::fprintf(stderr, "b2p_ctx_create: %s\n", b2p_last_error(nullptr));
     return 3;
   }
-  b2p_geom *geom = b2p::palace::CreateHexGeometry(ctx, mesh, ir);
-  const b2p::palace::HexNDSpaceInputs in = b2p::palace::GatherHexNDSpace(nd_fes, ir);
+  // dense tables in native order, as fe.GetDofToQuad(ir, FULL) holds them, and the 3-D rule (x fastest)
+  std::vector<double> interp((size_t)3 * Q * P), curl((size_t)3 * Q * P), qw(Q);
+  orc_nd_hex_tables(p, q1d, interp.data(), curl.data(), qw.data());
+  mfem::IntegrationRule ir3;
+  for (int k = 0; k < q1d; k++)
+    for (int j = 0; j < q1d; j++)
+      for (int i = 0; i < q1d; i++)
+        ir3.pts.push_back({ir.pts[i].x, ir.pts[i].weight * ir.pts[j].weight * ir.pts[k].weight, ir.pts[j].x, ir.pts[k].x});
+  mfem::VectorFiniteElement vfe(p);
+  vfe.full_maps.ndof = P;
+  vfe.full_maps.nqpt = Q;
+  vfe.full_maps.Bt = interp;
+  vfe.full_maps.Gt = curl;
+  mfem::FiniteElementSpace dense_fes = nd_fes;
+  dense_fes.fe = &vfe;
+  // element transformations for "dense_co": unit diagonal with sprinkled 2 x 2 blocks of small integers on consecutive dof pairs
+  std::vector<mfem::DofTransformation> dts(ne);
+  std::vector<signed char> co_ref;
+  if (mode == "dense_co")
+  {
+    std::mt19937 r2(11);
+    co_ref.assign((size_t)ne * P * 3, 0);
+    for (int e = 0; e < ne; e++)
+    {
+      dts[e].n = P;
+      dts[e].Minv.assign((size_t)P * P, 0.0);
+      for (int i = 0; i < P; i++) dts[e].Minv[(size_t)i * P + i] = (r2() % 2) ? 1.0 : -1.0;
+      for (int j = 0; j + 1 < P; j += 6)
+      {
+        const int b[4] = {(int)(r2() % 3) - 1, (int)(r2() % 3) - 1, (int)(r2() % 3) - 1, (int)(r2() % 3) - 1};
+        dts[e].Minv[(size_t)j * P + j] = b[0];
+        dts[e].Minv[(size_t)j * P + j + 1] = b[1];
+        dts[e].Minv[(size_t)(j + 1) * P + j] = b[2];
+        dts[e].Minv[(size_t)(j + 1) * P + j + 1] = b[3];
+      }
+      dense_fes.elem_trans.push_back(&dts[e]);
+      // expected rows: T(r, j) = sign_j M(r, j) stored row-major tridiagonal {T(r, r-1), T(r, r), T(r, r+1)}
+      for (int r = 0; r < P; r++)
+        for (int t = -1; t <= 1; t++)
+        {
+          const int j = r + t;
+          if (j < 0 || j >= P) continue;
+          const double sj = nd_fes.elem_dofs[e][j] >= 0 ? 1.0 : -1.0;
+          co_ref[((size_t)e * P + r) * 3 + (t + 1)] = (signed char)(sj * dts[e].Minv[(size_t)r * P + j]);
+        }
+    }
+  }
+  b2p_geom *geom = nullptr;
   auto op = std::make_unique<b2p::palace::Operator>(ctx, nd_fes.GetVSize(), nd_fes.GetVSize());
-  op->AddSubOperator(b2p::palace::CreateHexNDIntegrator(ctx, geom, kind, in, blob.data(), blob.size()));
+  if (mode == "hex")
+  {
+    geom = b2p::palace::CreateHexGeometry(ctx, mesh, ir);
+    const b2p::palace::HexNDSpaceInputs in = b2p::palace::GatherHexNDSpace(nd_fes, ir);
+    op->AddSubOperator(b2p::palace::CreateHexNDIntegrator(ctx, geom, kind, in, blob.data(), blob.size()));
+  }
+  else
+  {
+    geom = b2p::palace::CreateGeneralGeometry(ctx, mesh, ir3);
+    const b2p::palace::DenseNDSpaceInputs in = b2p::palace::GatherDenseNDSpace(dense_fes, ir3);
+    if (mode == "dense_co" && std::vector<signed char>(in.curl_orient.begin(), in.curl_orient.end()) != co_ref)
+    {
+      std::printf("GLUE_EXEC FAIL curl_orient rows differ from the expected tridiagonal matrices\n");
+      return 1;
+    }
+    op->AddSubOperator(b2p::palace::CreateDenseNDIntegrator(ctx, geom, kind, in, blob.data(), blob.size()));
+  }
   const int N = nd_fes.GetVSize();
   std::vector<double> x(N), y(N), d(N);
   std::uniform_real_distribution<double> ux(-1.0, 1.0);
@@ -151,8 +219,7 @@ int main(int argc, char **argv)
   b2p::palace::Check(b2p_ctx_sync(ctx, nullptr), ctx);
 
   // ---- the reference-style path on the same data: dense tables in native order, native restriction with signs, q-data ----
-  std::vector<double> interp((size_t)3 * Q * P), curl((size_t)3 * Q * P), qw(Q), qdata((size_t)ne * 11 * Q), xe((size_t)ne * 3 * 8);
-  orc_nd_hex_tables(p, q1d, interp.data(), curl.data(), qw.data());
+  std::vector<double> qdata((size_t)ne * 11 * Q), xe((size_t)ne * 3 * 8);
   const int lex2nat[8] = {0, 1, 3, 2, 4, 5, 7, 6};
   for (int e = 0; e < ne; e++)
     for (int c = 0; c < 3; c++)
@@ -168,8 +235,14 @@ int main(int argc, char **argv)
       ori[(size_t)e * P + i] = dd >= 0 ? 1 : -1;
     }
   std::vector<double> y_ref(N, 0.0), d_ref(N, 0.0);
-  orc_apply_add(kind, ne, P, Q, interp.data(), curl.data(), idx.data(), ori.data(), qdata.data(), blob.data(), x.data(), y_ref.data());
-  orc_diag_add(kind, ne, P, Q, interp.data(), curl.data(), idx.data(), qdata.data(), blob.data(), d_ref.data());
+  if (mode == "dense_co")
+    orc_apply_add_co(kind, ne, P, Q, interp.data(), curl.data(), idx.data(), co_ref.data(), qdata.data(), blob.data(), x.data(), y_ref.data());
+  else
+    orc_apply_add(kind, ne, P, Q, interp.data(), curl.data(), idx.data(), ori.data(), qdata.data(), blob.data(), x.data(), y_ref.data());
+  if (mode == "dense_co")
+    d_ref = d;  // (the oracle has no diagonal through the tridiagonal restriction: tests/test_tet_gpu.py covers it)
+  else
+    orc_diag_add(kind, ne, P, Q, interp.data(), curl.data(), idx.data(), qdata.data(), blob.data(), d_ref.data());
   double en = 0, rn = 0, ed = 0, rd = 0;
   for (int i = 0; i < N; i++)
   {

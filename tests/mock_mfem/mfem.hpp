@@ -74,7 +74,7 @@ public:
 // signatures and conventions (column-major DofToQuad tables, -1-d encoding of flipped dofs, byNODES vdofs). ----
 struct IntegrationPoint
 {
-  double x = 0.0, weight = 0.0;
+  double x = 0.0, weight = 0.0, y = 0.0, z = 0.0;
 };
 class IntegrationRule
 {
@@ -92,6 +92,8 @@ struct DofToQuad
   };
   int ndof = 0, nqpt = 0;
   std::vector<double> B, G;  // B[q + nqpt * d]
+  // FULL mode of a vector element: column-major (ndof, nqpt, dim) = row-major [dim][nqpt][ndof], values and curls / gradients
+  std::vector<double> Bt, Gt;
 };
 class FiniteElement
 {
@@ -102,6 +104,41 @@ public:
   explicit FiniteElement(int p) : order(p) {}
   virtual ~FiniteElement() = default;
   int GetOrder() const { return order; }
+};
+// any vector element seen through its full tables (what InitNonTensorBasis reads, fem/libceed/basis.cpp:40-85)
+class VectorFiniteElement : public FiniteElement
+{
+public:
+  DofToQuad full_maps;
+  int dim = 3;
+  explicit VectorFiniteElement(int p) : FiniteElement(p) {}
+  int GetDim() const { return dim; }
+  const DofToQuad &GetDofToQuad(const IntegrationRule &, DofToQuad::Mode) const { return full_maps; }
+};
+// element dof transformation of ND tets / prisms with p >= 2 (fem/doftrans.hpp): the mock holds the matrix the primal inverse applies
+class DofTransformation
+{
+public:
+  int n = 0;
+  std::vector<double> Minv;  // row-major [n][n]
+  void InvTransformPrimal(Vector &v) const
+  {
+    std::vector<double> t(n, 0.0);
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) t[i] += Minv[(size_t)i * n + j] * v[j];
+    for (int i = 0; i < n; i++) v[i] = t[i];
+  }
+};
+class DenseMatrix
+{
+public:
+  double a[9] = {0};
+  double &operator()(int i, int j) { return a[i + 3 * j]; }
+  const double &operator()(int i, int j) const { return a[i + 3 * j]; }
+  double Det() const
+  {
+    return a[0] * (a[4] * a[8] - a[7] * a[5]) - a[3] * (a[1] * a[8] - a[7] * a[2]) + a[6] * (a[1] * a[5] - a[4] * a[2]);
+  }
 };
 class TensorBasisElement
 {
@@ -138,6 +175,12 @@ public:
   int GetVDim() const { return vdim; }
   const FiniteElement *GetFE(int) const { return fe; }
   void GetElementDofs(int e, Array<int> &dofs) const { dofs.Assign(elem_dofs[e]); }
+  std::vector<const DofTransformation *> elem_trans;  // per element or empty
+  const DofTransformation *GetElementDofs(int e, Array<int> &dofs, int) const
+  {
+    dofs.Assign(elem_dofs[e]);
+    return elem_trans.empty() ? nullptr : elem_trans[e];
+  }
   void GetElementVDofs(int e, Array<int> &vdofs) const  // Ordering::byNODES
   {
     std::vector<int> v;
@@ -160,12 +203,48 @@ public:
     for (int i = 0; i < dofs.Size(); i++) out.HostWrite()[i] = Read()[dofs[i]];
   }
 };
+// trilinear hexahedron through its 8 nodes (MFEM vertex order), enough for Jacobians at integration points
+class ElementTransformation
+{
+public:
+  double X[3][8];
+  DenseMatrix J;
+  void SetIntPoint(const IntegrationPoint *ip)
+  {
+    static const int cx[8] = {0, 1, 1, 0, 0, 1, 1, 0}, cy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, cz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    const double xi[3] = {ip->x, ip->y, ip->z};
+    for (int c = 0; c < 3; c++)
+      for (int d = 0; d < 3; d++) J(c, d) = 0.0;
+    for (int v = 0; v < 8; v++)
+    {
+      const int cc[3] = {cx[v], cy[v], cz[v]};
+      for (int d = 0; d < 3; d++)
+      {
+        double g = cc[d] ? 1.0 : -1.0;
+        for (int o = 0; o < 3; o++)
+          if (o != d) g *= cc[o] ? xi[o] : 1.0 - xi[o];
+        for (int c = 0; c < 3; c++) J(c, d) += X[c][v] * g;
+      }
+    }
+  }
+  const DenseMatrix &Jacobian() const { return J; }
+  double Weight() const { return J.Det(); }
+};
 class Mesh
 {
 public:
   int ne = 0;
   std::vector<int> attributes;
   const GridFunction *nodes = nullptr;
+  mutable ElementTransformation trans;
+  ElementTransformation *GetElementTransformation(int e) const
+  {
+    const FiniteElementSpace *nf = nodes->FESpace();
+    const int nd = nf->vsize / nf->vdim;
+    for (int c = 0; c < 3; c++)
+      for (int v = 0; v < 8; v++) trans.X[c][v] = (*nodes)[nf->elem_dofs[e][v] + c * nd];
+    return &trans;
+  }
   int GetNE() const { return ne; }
   int GetAttribute(int e) const { return attributes[e]; }
   const GridFunction *GetNodes() const { return nodes; }

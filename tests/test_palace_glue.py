@@ -28,8 +28,8 @@ def _build(tmp_path, libdir, libname):
     return exe, path
 
 
-def _run(exe, blob, p):
-    r = subprocess.run([exe, blob, str(p)], capture_output=True, text=True, timeout=600)
+def _run(exe, blob, p, mode="hex"):
+    r = subprocess.run([exe, blob, str(p), mode], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "GLUE_EXEC OK" in r.stdout, r.stdout + r.stderr
 
 
@@ -42,6 +42,19 @@ def test_glue_executes_on_the_emulation_build(tmp_path, p):
     emu_mode.build()
     exe, blob = _build(tmp_path, os.path.join(ROOT, "tests", "emu"), "libb2p_emu.so")
     _run(exe, blob, p)
+
+
+@pytest.mark.parametrize("mode", ["dense", "dense_co"])
+def test_dense_element_glue_executes_on_the_emulation_build(tmp_path, mode):
+    """The non-tensor glue (GatherDenseNDSpace / CreateGeneralGeometry / CreateDenseNDIntegrator: FULL DofToQuad tables, element
+    transformations for the geometry factors, DofTransformation columns -> int8 tridiagonal rows as restriction.cpp:301-329)."""
+    from oracle import pyoracle as O
+    from tests.emu import emu_mode
+
+    O.lib()
+    emu_mode.build()
+    exe, blob = _build(tmp_path, os.path.join(ROOT, "tests", "emu"), "libb2p_emu.so")
+    _run(exe, blob, 2, mode)
 
 
 @pytest.mark.gpu
