@@ -266,6 +266,9 @@ def run_experiments(args):
         "cylinder_cavity_p4_vs_reference_eig_csv": (["tools/cylinder_bench.py", "--order", "4", "--refine", "0", "--nev", "4"], {}),
         "tet_dense_p3_1M_dofs": (["tools/tet_bench.py", "--order", "3", "--n", "21", "--steps", "20", "--terms"], {}),
         "tet_dense_p6_1M_dofs": (["tools/tet_bench.py", "--order", "6", "--n", "11", "--steps", "10"], {}),
+        # BASELINE config 3's workflow in miniature on one GPU: frequency sweep on order-3 tets, operators re-coefficiented in
+        # place, SetOperators of the p-multigrid per frequency, complex FGMRES + real V-cycle (PCMatReal)
+        "driven_sweep_tets_p3": (["tools/driven_sweep_bench.py", "--order", "3", "--n", "12", "--freqs", "4"], {}),
         # BASELINE config 2 at size: cylinder cavity, ND order 4, p-multigrid {1, 2, 4}, Chebyshev order 8 + Hiptmair, 7.94M dofs
         "cylinder_cavity_p4_7p9M_dofs": (["tools/cylinder_bench.py", "--order", "4", "--refine", "3", "--nev", "2", "--tol", "1e-8",
                                           "--coarse-tol", "1e-4"], {"B2P_COARSE_ASSEMBLED": "1"}),

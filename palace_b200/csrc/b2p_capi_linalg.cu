@@ -397,6 +397,8 @@ int b2p_solver_mult(b2p_solver *s, const double *x, double *y)
 {
   if (!s || !s->s) return B2P_ERR_ARG;
   B2P_CHECK(s->s->ctx, s->s->Height() > 0, B2P_ERR_ARG, "solver applied before SetOperator (a preconditioner needs its own set_operator call, as in Palace's KspSolver::SetOperators)");
+  if (auto *k = dynamic_cast<IterativeSolver *>(s->s.get()))
+    B2P_CHECK(k->ctx, k->type != KspType::FGMRES || k->B, B2P_ERR_ARG, "Operator and preconditioner must be set for FgmresSolver::Mult!");  // iterative.cpp:738
   B2P_TRY(s->s->ctx, s->s->Mult(x, y));
   return B2P_SUCCESS;
 }

@@ -1041,7 +1041,7 @@ private:
     else
       initial_res = res;
     eps = std::max(rel_tol * initial_res, abs_tol);
-    converged = (res < eps);
+    converged = (res < eps) || res == 0.0;  // a zero residual (zero right-hand side: the imaginary part under PCMatReal) is converged, not 0 / 0
     int it = 0;
     for (; it < max_it && !converged; it++)
     {
@@ -1471,6 +1471,9 @@ int b2p_csolver_set_initial_guess(b2p_csolver *s, int flag)
 int b2p_csolver_mult(b2p_csolver *s, const double *br, const double *bi, double *xr, double *xi)
 {
   if (!s || !s->s) return B2P_ERR_ARG;
+  if (auto *k = dynamic_cast<ComplexIterativeSolver *>(s->s.get()))
+    B2P_CHECK(k->ctx, k->A && (k->type != KspType::FGMRES || k->B), B2P_ERR_ARG,
+              "Operator and preconditioner must be set for FgmresSolver::Mult (operator for the others)!");  // iterative.cpp:738
   B2P_CTRY(s->s->ctx, s->s->Mult(CCPtr{br, bi}, CPtr{xr, xi}));
   return B2P_SUCCESS;
 }

@@ -733,7 +733,7 @@ void IterativeSolver::MultCG(const double *b, double *x) const
   else
     initial_res = res;
   eps = std::max(rel_tol * initial_res, abs_tol);
-  converged = (res < eps);
+  converged = (res < eps) || res == 0.0;  // a zero residual (zero right-hand side: the imaginary part under PCMatReal) is converged, not 0 / 0
   int it = 0;
   for (; it < max_it && !converged; it++)
   {
@@ -810,7 +810,7 @@ void IterativeSolver::MultCGDeviceScalars(const double *b, double *x) const
   else
     initial_res = res;
   const double eps = std::max(rel_tol * initial_res, abs_tol);
-  converged = (res < eps);
+  converged = (res < eps) || res == 0.0;  // a zero residual (zero right-hand side: the imaginary part under PCMatReal) is converged, not 0 / 0
   int it = 0;
   for (; it < max_it && !converged; it++)
   {
