@@ -1144,7 +1144,7 @@ private:
         eps = std::max(rel_tol * initial_res, abs_tol);
       }
       beta = true_beta;
-      if (beta < eps)
+      if (beta < eps || beta == 0.0)  // (a zero residual is converged: 1 / beta below)
       {
         converged = true;
         break;

@@ -911,7 +911,7 @@ void IterativeSolver::MultGMRES(const double *b, double *x, bool flexible) const
       eps = std::max(rel_tol * initial_res, abs_tol);
     }
     beta = true_beta;
-    if (beta < eps)
+    if (beta < eps || beta == 0.0)  // (a zero residual is converged: 1 / beta below)
     {
       converged = true;
       break;

@@ -74,3 +74,19 @@ def test_fgmres_without_a_preconditioner_is_an_error(b2p_ctx, system):
     k.set_operator(A)
     with pytest.raises(capi.B2PError):
         k.mult(_dev(np.ones(n)), torch.zeros(n, dtype=torch.float64, device="cuda"))
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+def test_gmres_with_a_zero_right_hand_side_converges_to_zero(b2p_ctx, system, kind):
+    from palace_b200 import capi
+
+    prob, A = system
+    n = prob.nd.ndofs
+    pc = capi.Solver.jacobi(b2p_ctx)
+    pc.set_operator(A)
+    k = capi.Solver.krylov(b2p_ctx, kind, rel_tol=1e-6, max_it=20)
+    k.set_operator(A)
+    k.set_preconditioner(pc)
+    x = torch.full((n,), 3.0, dtype=torch.float64, device="cuda")
+    k.mult(_dev(np.zeros(n)), x)
+    assert k.stats()["converged"] and float(x.abs().max()) == 0.0
