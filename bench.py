@@ -242,7 +242,9 @@ def run_experiments(args):
     """Side measurements of the same run, each taken by a child process (a failure or hang of one of them cannot touch the
     headline numbers) and printed as ITS OWN short JSON line -- {"experiment": name, ...} -- before the headline line, so that
     none of them can fall off a log tail. The headline line stays the last line of the output."""
-    t_start, budget_s = time.time(), float(os.environ.get("B2P_BENCH_EXPERIMENT_BUDGET_S", "330"))
+    # no experiment STARTS after budget_s; each is cut off at 150 s, so the side measurements end within ~7 minutes in the worst case
+    # (they took 1.5 minutes on B200 with the round-2 list of 13, profiles/r02_bench_n1_with_experiments.jsonl)
+    t_start, budget_s = time.time(), float(os.environ.get("B2P_BENCH_EXPERIMENT_BUDGET_S", "270"))
     common = ["--steps", str(args.steps), "--warmup", str(args.warmup), "--order", str(args.order), "--n", str(args.n),
               "--no-cpu-baseline", "--no-experiments"]
     # (1) the same bench on other kernels / coefficients: value, kernel time and roofline fraction of each
