@@ -72,6 +72,27 @@ def tet_quadrature(degree: int):
     return pts, W.ravel()
 
 
+def tet_quadrature_symmetric6():
+    """The 24-point, degree-6 symmetric rule on the reference tetrahedron (Keast 1986; orbits 4 + 4 + 4 + 12, positive weights):
+    the rule MFEM's IntRules returns for a tetrahedron at order 6, i.e. what the reference integrates order-3 forms with
+    (q_order = 2 p, /root/reference/palace/fem/integrator.cpp:14-22). Exact to 3e-17 on every monomial of degree <= 6
+    (tests/test_tet_cpu.py); with curved elements the integrand is not a polynomial and the choice of rule shows at the 1e-8 level,
+    which is why the pin against the reference's stored capacitances uses this rule (tests/test_spheres_golden.py)."""
+    import itertools
+
+    pts, w = [], []
+    for a, wt in ((0.21460287125915202, 0.0066537917096945820), (0.040673958534611353, 0.0016795351758867738),
+                  (0.32233789014227551, 0.0092261969239424536)):
+        b = 1.0 - 3.0 * a
+        pts += [(a, a, a), (a, a, b), (a, b, a), (b, a, a)]
+        w += [wt] * 4
+    a, b = 0.063661001875017525, 0.26967233145831580
+    orbit = sorted(set(itertools.permutations((a, a, b, 1.0 - 2.0 * a - b))))
+    pts += [q[:3] for q in orbit]
+    w += [0.0080357142857142857] * len(orbit)
+    return np.array(pts), np.array(w)
+
+
 # ------------------------------------------------------------------------------------------------
 # Reference element: dof functionals and shape functions
 # ------------------------------------------------------------------------------------------------

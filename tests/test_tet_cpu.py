@@ -46,6 +46,21 @@ def test_quadrature_is_exact_to_its_degree():
                 assert abs((w * pts[:, 0] ** a * pts[:, 1] ** b * pts[:, 2] ** c).sum() - exact) < 1e-15
 
 
+def test_symmetric_24_point_rule_is_exact_to_degree_6():
+    """The rule MFEM returns for tetrahedra at order 6 (what the reference integrates order-3 forms with)."""
+    from math import factorial
+
+    pts, w = ts.tet_quadrature_symmetric6()
+    assert len(w) == 24 and (w > 0).all() and (pts > 0).all() and (pts.sum(axis=1) < 1).all()
+    for deg in range(7):
+        for a in range(deg + 1):
+            for b in range(deg + 1 - a):
+                c = deg - a - b
+                exact = factorial(a) * factorial(b) * factorial(c) / factorial(a + b + c + 3)
+                assert abs((w * pts[:, 0] ** a * pts[:, 1] ** b * pts[:, 2] ** c).sum() - exact) < 1e-16
+    assert abs((w * pts[:, 0] ** 7).sum() - factorial(7) / factorial(10)) > 1e-7  # and no further
+
+
 def test_qdata_layout_matches_the_hex_oracle_convention():
     """Same J -> {w detJ, adj(J)^T/detJ column-major} packing as orc_geom_hex_qdata (geom_33_qf.h:9-34):
     an affine map applied to a hex and to a tet must give the same per-point factors."""
