@@ -97,3 +97,29 @@ def test_dense_complex_sum_runs_as_two_dense_operators(b2p_ctx):
     A.set_coefficients(coefs2)
     A.mult(_dev(x.real), _dev(x.imag), yr, yi)
     assert _rel(yr.cpu().numpy() + 1j * yi.cpu().numpy(), ref(coefs2)) < RTOL
+
+
+def test_fused_dense_sum_assembles_into_the_coarse_matrix(b2p_ctx):
+    """The multigrid's assembled coarse level (MfemWrapperSolver analogue) on a ParOperator whose terms were fused into one dense
+    operator: the device CSR matrix is the eliminated sum, and the Jacobi-PCG on it solves the system."""
+    import scipy.sparse.linalg as spla
+
+    from palace_b200 import capi
+
+    prob = common.make_problem(n=(3, 2, 2), p=1, n_attr=2)
+    bk = common.coefficient(O.CURLCURL, 2, "matrix", a_curl=0.7)
+    bm = common.coefficient(O.ND_MASS, 2, "matrix", a_mass=1.3)
+    (K, M), sp = _terms(b2p_ctx, prob, [(O.CURLCURL, bk), (O.ND_MASS, bm)])
+    A = capi.Operator.par(b2p_ctx, sp.ndofs, sp.ndofs, [K, M], [1.0, 2.0], sp.ess_dofs, diag_policy=1)
+    assert A.is_fused()
+    Ao = S.eliminate((common.oracle_matrix(prob, O.CURLCURL, bk, eliminate=False)
+                      + 2.0 * common.oracle_matrix(prob, O.ND_MASS, bm, eliminate=False)).tocsr(), sp.ess_dofs)
+    cg = capi.Solver.krylov(b2p_ctx, capi.CG, rel_tol=1e-12, max_it=500)
+    solver = capi.Solver.assembled(b2p_ctx, cg, capi.Solver.jacobi(b2p_ctx))
+    solver.set_operator(A)
+    assert solver.assembled_nnz() >= Ao.nnz
+    b = np.random.default_rng(9).random(sp.ndofs)
+    b[sp.ess_dofs] = 0.0
+    x = torch.zeros(sp.ndofs, dtype=torch.float64, device="cuda")
+    solver.mult(_dev(b), x)
+    assert _rel(x.cpu().numpy(), spla.spsolve(Ao.tocsc(), b)) < 1e-9
