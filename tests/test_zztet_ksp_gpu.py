@@ -1,0 +1,75 @@
+"""GPU: the BaseKspSolver composer (b2p_ksp_*) on tetrahedra -- the reference's default configuration (FGMRES, p-multigrid, Chebyshev
++ Hiptmair smoothing, linalg/ksp.cpp:131-239, utils/iodata.cpp:500-545) over dense-basis operators with curl-oriented restrictions,
+system matrix a0 K + a2 M given as TWO terms (fused into one dense operator), coarse level either Jacobi-smoothed or the Jacobi-PCG
+on the device-assembled matrix. The solution must solve the oracle's assembled system."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle import pyoracle as O
+from palace_b200.host import coeff as cf
+from palace_b200.host import tetspace as ts
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("coarse_type", [0, 1])
+def test_ksp_composer_on_tetrahedra(b2p_ctx, coarse_type):
+    from palace_b200 import capi
+
+    capi.set_stream(b2p_ctx)
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=4)
+    orders = [1, 2]
+    spaces = [ts.build_nd_tet_space(mesh, p) for p in orders]
+    h1s = [ts.build_h1_tet_space(mesh, s_, s_.p) for s_ in spaces]
+    _, _, qpts, qw = ts.nd_tet_tables(orders[-1])
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    geom = capi.Geom.general(b2p_ctx, qd)
+    one = cf.coeff_ctx(a=1.0)
+    a0, a2 = 1.0, 2.5
+    pars, auxs, grads, keep = [], [], [], []
+    for s_, h1 in zip(spaces, h1s):
+        interp, curl = ts.nd_tet_element(s_.p).tabulate(qpts)
+        K = capi.Op.create_dense(b2p_ctx, geom, O.CURLCURL, s_.ndofs, s_.idx, None, None, curl, one, curl_orient=s_.curl_orient)
+        M = capi.Op.create_dense(b2p_ctx, geom, O.ND_MASS, s_.ndofs, s_.idx, None, interp, None, one, curl_orient=s_.curl_orient)
+        keep += [K, M]
+        A = capi.Operator.par(b2p_ctx, s_.ndofs, s_.ndofs, [K, M], [a0, a2], s_.ess_dofs, diag_policy=1)
+        assert A.is_fused()
+        pars.append(A)
+        _, grad = ts.h1_tet_element(h1.p).tabulate(qpts)
+        aop = capi.Op.create_dense(b2p_ctx, geom, O.H1_DIFFUSION, h1.ndofs, h1.idx, None, None, grad, cf.coeff_ctx(a=a2))
+        keep.append(aop)
+        auxs.append(capi.Operator.par(b2p_ctx, h1.ndofs, h1.ndofs, [aop], None, h1.ess_dofs, diag_policy=1))
+        git = capi.Interp.dense(b2p_ctx, ts.tet_discrete_gradient(s_.p), h1.idx, h1.ndofs, s_.idx, s_.ndofs, out_curl_orient=ts.dual_orient(s_))
+        grads.append(capi.Operator.interp(b2p_ctx, git))
+    it = capi.Interp.dense(b2p_ctx, ts.nd_tet_prolongation(1, 2), spaces[0].idx, spaces[0].ndofs, spaces[1].idx, spaces[1].ndofs,
+                           in_curl_orient=spaces[0].curl_orient, out_curl_orient=ts.dual_orient(spaces[1]))
+    prol = [capi.Operator.interp(b2p_ctx, it)]
+    ksp = capi.Ksp(b2p_ctx, 2, prol, grads, tol=1e-10, max_it=80, coarse_type=coarse_type, coarse_tol=1e-6, coarse_max_it=400)
+    ksp.set_operators(pars[-1], pars, auxs)
+    fine = spaces[-1]
+    b = np.random.default_rng(2).random(fine.ndofs)
+    b[fine.ess_dofs] = 0.0
+    x = torch.zeros(fine.ndofs, dtype=torch.float64, device="cuda")
+    ksp.mult(_dev(b), x)
+    st = ksp.stats()
+    assert st["converged"] and st["num_total_mult"] == 1 and st["num_total_mult_its"] == st["its"], st
+    interp, curl = ts.nd_tet_element(fine.p).tabulate(qpts)
+    blob = cf.coeff_ctx_pair(cf.coeff_ctx(a=a2), cf.coeff_ctx(a=a0))
+    Ae = O.element_matrices(O.CURLCURL_MASS, interp, curl, None, qd, blob, fine.P)
+    A = np.zeros((fine.ndofs, fine.ndofs))
+    for e in range(mesh.ne):
+        T = fine.dense_T(e)
+        A[np.ix_(fine.idx[e], fine.idx[e])] += T.T @ Ae[e] @ T
+    ess = fine.ess_dofs
+    A[ess, :] = 0
+    A[:, ess] = 0
+    A[ess, ess] = 1.0
+    xs = x.cpu().numpy()
+    assert np.linalg.norm(b - A @ xs) < 1e-8 * np.linalg.norm(b)
