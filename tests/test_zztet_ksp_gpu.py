@@ -73,3 +73,65 @@ def test_ksp_composer_on_tetrahedra(b2p_ctx, coarse_type):
     A[ess, ess] = 1.0
     xs = x.cpu().numpy()
     assert np.linalg.norm(b - A @ xs) < 1e-8 * np.linalg.norm(b)
+
+
+def test_complex_multigrid_on_tetrahedra(b2p_ctx):
+    """GeometricMultigridSolver<ComplexOperator> with Hiptmair smoothing (the reference's default for complex systems, PCMatReal =
+    false) over dense-basis tetrahedral level operators K + (1 + 0.3 i) M -- complex sums over dense terms, i.e. the two-coefficient-sum
+    path -- preconditioning complex FGMRES; the solution must solve the assembled complex system."""
+    from palace_b200 import capi
+
+    capi.set_stream(b2p_ctx)
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=6)
+    orders = [1, 2]
+    spaces = [ts.build_nd_tet_space(mesh, p) for p in orders]
+    h1s = [ts.build_h1_tet_space(mesh, s_, s_.p) for s_ in spaces]
+    _, _, qpts, qw = ts.nd_tet_tables(orders[-1])
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    geom = capi.Geom.general(b2p_ctx, qd)
+    one = cf.coeff_ctx(a=1.0)
+    cm = 1.0 + 0.3j
+    A, AG, G, keep = [], [], [], []
+    for s_, h1 in zip(spaces, h1s):
+        interp, curl = ts.nd_tet_element(s_.p).tabulate(qpts)
+        K = capi.Op.create_dense(b2p_ctx, geom, O.CURLCURL, s_.ndofs, s_.idx, None, None, curl, one, curl_orient=s_.curl_orient)
+        M = capi.Op.create_dense(b2p_ctx, geom, O.ND_MASS, s_.ndofs, s_.idx, None, interp, None, one, curl_orient=s_.curl_orient)
+        _, grad = ts.h1_tet_element(h1.p).tabulate(qpts)
+        D = capi.Op.create_dense(b2p_ctx, geom, O.H1_DIFFUSION, h1.ndofs, h1.idx, None, None, grad, one)
+        keep += [K, M, D]
+        A.append(capi.ComplexOperator.par(b2p_ctx, s_.ndofs, s_.ndofs, [K, M], [1.0, cm], s_.ess_dofs, 1))
+        AG.append(capi.ComplexOperator.par(b2p_ctx, h1.ndofs, h1.ndofs, [D], [cm], h1.ess_dofs, 1))
+        git = capi.Interp.dense(b2p_ctx, ts.tet_discrete_gradient(s_.p), h1.idx, h1.ndofs, s_.idx, s_.ndofs, out_curl_orient=ts.dual_orient(s_))
+        G.append(capi.Operator.interp(b2p_ctx, git))
+    it = capi.Interp.dense(b2p_ctx, ts.nd_tet_prolongation(1, 2), spaces[0].idx, spaces[0].ndofs, spaces[1].idx, spaces[1].ndofs,
+                           in_curl_orient=spaces[0].curl_orient, out_curl_orient=ts.dual_orient(spaces[1]))
+    P = [capi.Operator.interp(b2p_ctx, it)]
+    coarse = capi.ComplexSolver.krylov(b2p_ctx, 1, rel_tol=1e-12, max_it=300, max_dim=300)
+    mg = capi.ComplexSolver.gmg(b2p_ctx, coarse, P, G, cycle_it=1, smooth_it=1, cheby_order=4)
+    mg.gmg_set_operators(A, AG)
+    fine = spaces[-1]
+    n = fine.ndofs
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    b[fine.ess_dofs] = 0.0
+    k = capi.ComplexSolver.krylov(b2p_ctx, 2, rel_tol=1e-10, max_it=60, max_dim=60)
+    k.set_operator(A[-1])
+    k.set_preconditioner(mg)
+    zr, zi = torch.zeros(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+    k.mult(_dev(b.real), _dev(b.imag), zr, zi)
+    st = k.stats()
+    assert st["converged"] and st["its"] <= 30, st
+    assert A[-1].fused_applies() > 0
+    interp, curl = ts.nd_tet_element(fine.p).tabulate(qpts)
+    Ke = O.element_matrices(O.CURLCURL, interp, curl, None, qd, one, fine.P)
+    Me = O.element_matrices(O.ND_MASS, interp, curl, None, qd, one, fine.P)
+    Z = np.zeros((n, n), dtype=complex)
+    for e in range(mesh.ne):
+        T = fine.dense_T(e)
+        Z[np.ix_(fine.idx[e], fine.idx[e])] += T.T @ (Ke[e] + cm * Me[e]) @ T
+    ess = fine.ess_dofs
+    Z[ess, :] = 0
+    Z[:, ess] = 0
+    Z[ess, ess] = 1.0
+    z = zr.cpu().numpy() + 1j * zi.cpu().numpy()
+    assert np.linalg.norm(b - Z @ z) < 1e-8 * np.linalg.norm(b)
