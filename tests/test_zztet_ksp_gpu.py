@@ -135,3 +135,64 @@ def test_complex_multigrid_on_tetrahedra(b2p_ctx):
     Z[ess, ess] = 1.0
     z = zr.cpu().numpy() + 1j * zi.cpu().numpy()
     assert np.linalg.norm(b - Z @ z) < 1e-8 * np.linalg.norm(b)
+
+
+def test_divfree_projection_on_tetrahedra(b2p_ctx):
+    """DivFreeSolver (linalg/divfree.cpp:42-186) over dense tetrahedral operators: the result is discretely divergence-free,
+    G^T M (y + G psi) = 0 on the free H1 dofs, and equals the projection formed from the oracle's assembled matrices."""
+    from palace_b200 import capi
+
+    capi.set_stream(b2p_ctx)
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=8)
+    p = 2
+    nd = ts.build_nd_tet_space(mesh, p)
+    h1l = [ts.build_h1_tet_space(mesh, nd, q) for q in (1, 2)]
+    interp, curl, qpts, qw = ts.nd_tet_tables(p)
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    geom = capi.Geom.general(b2p_ctx, qd)
+    eps = cf.coeff_ctx(a=1.7)
+    Mop = capi.Op.create_dense(b2p_ctx, geom, O.ND_MASS, nd.ndofs, nd.idx, None, interp, None, eps, curl_orient=nd.curl_orient)
+    Mpar = capi.Operator.par(b2p_ctx, nd.ndofs, nd.ndofs, [Mop], None, None, diag_policy=1)   # no essential dofs (b2p.h)
+    git = capi.Interp.dense(b2p_ctx, ts.tet_discrete_gradient(p), h1l[1].idx, h1l[1].ndofs, nd.idx, nd.ndofs, out_curl_orient=ts.dual_orient(nd))
+    G = capi.Operator.interp(b2p_ctx, git)
+    h1_ops, keep = [], []
+    for h1 in h1l:
+        _, grad = ts.h1_tet_element(h1.p).tabulate(qpts)
+        D = capi.Op.create_dense(b2p_ctx, geom, O.H1_DIFFUSION, h1.ndofs, h1.idx, None, None, grad, eps)
+        keep.append(D)
+        h1_ops.append(capi.Operator.par(b2p_ctx, h1.ndofs, h1.ndofs, [D], None, h1.ess_dofs, diag_policy=1))
+    pit = capi.Interp.dense(b2p_ctx, ts.h1_tet_prolongation(1, 2), h1l[0].idx, h1l[0].ndofs, h1l[1].idx, h1l[1].ndofs)
+    h1_P = [capi.Operator.interp(b2p_ctx, pit)]
+    df = capi.DivFree(b2p_ctx, Mpar, G, h1_ops, h1_P, h1l[1].ess_dofs, 2, tol=1e-12, max_it=200, coarse_type=0)
+    y0 = np.random.default_rng(4).standard_normal(nd.ndofs)
+    y = _dev(y0)
+    df.mult(y)
+    assert df.stats()["converged"]
+    # oracle-side matrices
+    Me = O.element_matrices(O.ND_MASS, interp, curl, None, qd, eps, nd.P)
+    M = np.zeros((nd.ndofs, nd.ndofs))
+    for e in range(mesh.ne):
+        T = nd.dense_T(e)
+        M[np.ix_(nd.idx[e], nd.idx[e])] += T.T @ Me[e] @ T
+    dual = ts.dual_orient(nd)
+
+    def dualT(e):
+        P_ = nd.P
+        T = np.zeros((P_, P_))
+        for r in range(P_):
+            T[r, r] = dual[e, r, 1]
+            if r > 0:
+                T[r, r - 1] = dual[e, r, 0]
+            if r < P_ - 1:
+                T[r, r + 1] = dual[e, r, 2]
+        return T
+
+    Gm = np.asarray(ts.global_interp_matrix(ts.tet_discrete_gradient(p), h1l[1].idx, None, nd.idx, dualT, h1l[1].ndofs, nd.ndofs).todense())
+    free = np.setdiff1d(np.arange(h1l[1].ndofs), h1l[1].ess_dofs)
+    S_ = Gm.T @ M @ Gm
+    psi = np.zeros(h1l[1].ndofs)
+    psi[free] = np.linalg.solve(S_[np.ix_(free, free)], -(Gm.T @ (M @ y0))[free])
+    y_ref = y0 + Gm @ psi
+    ys = y.cpu().numpy()
+    assert np.linalg.norm(ys - y_ref) < 1e-9 * np.linalg.norm(y_ref)
+    assert np.abs((Gm.T @ (M @ ys))[free]).max() < 1e-9 * np.abs(Gm.T @ (M @ y0)).max()
