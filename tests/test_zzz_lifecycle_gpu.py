@@ -23,7 +23,23 @@ def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
 
 
-def test_every_handle_type_is_created_used_and_destroyed(b2p_ctx):
+def test_every_handle_type_is_created_used_and_destroyed():
+    """Runs in a child process: a crash in a destructor must be a failed test, not the end of the pytest run."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import os, sys; sys.path.insert(0, %r)\n"
+            "if os.environ.get('B2P_EMU_TESTS') == '1':\n"
+            "    from tests.emu import emu_mode; emu_mode.enable()\n"
+            "from palace_b200 import capi\n"
+            "from tests import test_zzz_lifecycle_gpu as t\n"
+            "ctx = capi.Ctx(0); t.lifecycle(ctx); ctx.close(); print('LIFECYCLE OK')\n") % common.__file__.rsplit("/tests/", 1)[0]
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ))
+    assert r.returncode == 0 and "LIFECYCLE OK" in r.stdout, (r.returncode, r.stdout[-400:], r.stderr[-1200:])
+
+
+def lifecycle(b2p_ctx):
     from palace_b200 import capi
 
     L = capi.lib()
