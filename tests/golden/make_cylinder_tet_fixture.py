@@ -38,10 +38,19 @@ def main():
         for line in f:
             rows.append([float(x) for x in line.split(",")])
     rows = np.array(rows)
+    # the same mesh, space and materials with a Floquet wave vector (examples/cylinder/floquet.json: "FloquetWaveVector": [0, 0, 0.4]):
+    # test/data/regression/ref/cylinder/floquet/eig.csv -- the end-to-end golden of the periodic (mixed curl) terms
+    frows = []
+    with open(os.path.join(REF, "test/data/regression/ref/cylinder/floquet/eig.csv")) as f:
+        next(f)
+        for line in f:
+            frows.append([float(x) for x in line.split(",")])
+    frows = np.array(frows)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cylinder_waveguide_tet.npz")
     np.savez_compressed(path, verts=m.verts, elems=m.elems, elems_periodic=ren[m.elems], attr=m.attr, xe=m.xe, geom_order=m.order,
                         ref_f_re_ghz=rows[:, 1], ref_f_im_ghz=rows[:, 2], ref_Q=rows[:, 3], order=4, eps_r=2.08, loss_tan=4.0e-4,
-                        L0=1.0e-2, target_ghz=2.0)
+                        L0=1.0e-2, target_ghz=2.0, floquet_wave_vector=np.array([0.0, 0.0, 0.4]), floquet_f_re_ghz=frows[:, 1],
+                        floquet_f_im_ghz=frows[:, 2], floquet_Q=frows[:, 3])
     print("wrote", path, os.path.getsize(path), "bytes;", m.ne, "tets,", rows.shape[0], "reference modes")
 
 
