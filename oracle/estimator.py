@@ -8,11 +8,13 @@ assembled matrices (no product code is used here; only tests import this module)
   element error integrand               /root/reference/palace/fem/qfunctions/33/hcurlhdiv_error_33_qf.h:46-76
   summation over the element            /root/reference/palace/fem/libceed/integrator.cpp:560-574 (all-ones basis)
 
-Parity: the pointwise arithmetic (mixed mass D, both element error integrands) is pinned to the reference's own QFunction headers
-compiled in place (oracle/_ref, oracle/ref_qf.cpp) through tests/golden/qf_mixed_golden.npz
-(tests/test_oracle_golden.py::test_estimator_oracle_matches_reference_golden, 1e-14). The reference stores no vectors for whole
-estimator runs (its regression suite compares error-indicator statistics of full solves), so the projection + summation around that
-arithmetic follows errorestimator.cpp term by term without a stored golden."""
+Parity: (1) the pointwise arithmetic (mixed mass D, both element error integrands) is pinned to the reference's own QFunction
+headers compiled in place (oracle/_ref, oracle/ref_qf.cpp) through tests/golden/qf_mixed_golden.npz
+(tests/test_oracle_golden.py::test_estimator_oracle_matches_reference_golden, 1e-14); (2) END TO END: the statistics of the element
+indicators the reference's regression suite stores for examples/cylinder/cavity_pec.json
+(test/data/regression/ref/cylinder/cavity_pec/error-indicators.csv: 15 modes, grad-flux + curl-flux estimators, energy normalisation)
+are reproduced by this module on the oracle-side discretisation -- the global norm to 1e-7, the reference's projection tolerance
+being 1e-6 (tests/test_cylinder_indicator_golden.py)."""
 import numpy as np
 import scipy.sparse as sp
 
