@@ -46,6 +46,23 @@ def problem_on_mesh(mesh, p=2, q1d=None, mesh_order=2) -> Problem:
     return Problem(mesh, topo, p, q1d, mesh_order, xe, nd, h1, hs.tables_1d(p, q1d), (nB, nG), qd)
 
 
+def eigsh_above(A, M, k, sigma, extra=6, vectors=False, tol=1e-13):
+    """The k eigenvalues of A x = lam M x just above sigma (shift-invert ARPACK, as Palace orders its modes), DETERMINISTICALLY: a
+    seeded start vector instead of ARPACK's random one, a few extra modes and a generous Krylov space, so that one copy of a
+    (nearly) multiple eigenvalue cannot be missed from one run to the next."""
+    import scipy.sparse.linalg as spla
+
+    n = A.shape[0]
+    v0 = np.random.default_rng(20260923).standard_normal(n)
+    kk = min(k + extra, n - 2)
+    r = spla.eigsh(A, k=kk, M=M, sigma=sigma, which="LA", tol=tol, v0=v0, ncv=min(n - 1, max(4 * kk, 60)), return_eigenvectors=vectors)
+    if vectors:
+        lam, V = r
+        o = np.argsort(lam)[:k]
+        return lam[o], V[:, o]
+    return np.sort(r)[:k]
+
+
 def coefficient(kind, n_attr, coeff_type="matrix", a_mass=1.0, a_curl=1.0):
     """Coefficient context blob for operator ``kind`` in the style of the reference unit tests."""
     if coeff_type == "const":

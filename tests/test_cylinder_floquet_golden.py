@@ -18,6 +18,7 @@ import scipy.sparse.linalg as spla
 
 from oracle import pyoracle as O
 from palace_b200.host import coeff as cf
+from tests import common
 from tests.test_cylinder_tet_golden import FIX, frequencies_ghz, sigma_target, space_and_tables
 
 
@@ -62,7 +63,7 @@ def test_floquet_eigenfrequencies_match_the_reference():
     Krf, Kif, Mf = Kr[free][:, free], Ki[free][:, free], M[free][:, free]
     A2 = sp.bmat([[Krf, -Kif], [Kif, Krf]], format="csc")
     M2 = sp.block_diag([Mf, Mf], format="csc")
-    lam2 = np.sort(spla.eigsh(A2, k=30, M=M2, sigma=sigma_target(), which="LA", tol=1e-13, return_eigenvectors=False))
+    lam2 = common.eigsh_above(A2, M2, 30, sigma_target(), extra=8)
     assert np.abs(lam2[0::2] - lam2[1::2]).max() < 1e-9 * lam2.max()
     lam = 0.5 * (lam2[0::2] + lam2[1::2])
     f = frequencies_ghz(lam)

@@ -17,6 +17,7 @@ from oracle import pyoracle as O
 from oracle import solvers as S
 from palace_b200.host import coeff as cf
 from palace_b200.host import hexspace as hs
+from tests import common
 from tests.test_cylinder_golden import FIX, cylinder_problem, target_lambda
 
 # test/data/regression/ref/cylinder/cavity_pec/error-indicators.csv: Norm, Minimum, Maximum, Mean
@@ -33,11 +34,10 @@ def cavity_modes(p, n_modes=15):
     K = S.assemble_sparse(O.element_matrices(O.CURLCURL, interp, curl, ori, qd, one, nd.P), idx.astype(np.int64), nd.ndofs).tocsr()
     M = S.assemble_sparse(O.element_matrices(O.ND_MASS, interp, curl, ori, qd, one, nd.P), idx.astype(np.int64), nd.ndofs).tocsr()
     free = np.setdiff1d(np.arange(nd.ndofs), nd.ess_dofs)
-    lam, V = spla.eigsh(K[free][:, free].tocsc(), k=n_modes, M=M[free][:, free].tocsc(), sigma=target_lambda(), which="LA", tol=1e-13)
-    o = np.argsort(lam)
+    lam, V = common.eigsh_above(K[free][:, free].tocsc(), M[free][:, free].tocsc(), n_modes, target_lambda(), vectors=True)
     modes = np.zeros((n_modes, nd.ndofs))
-    modes[:, free] = V[:, o].T
-    return dict(mesh=mesh, topo=topo, nd=nd, rt=rt, q1d=q1d, qd=qd, interp=interp, idx=idx, ori=ori, M=M, lam=lam[o], modes=modes,
+    modes[:, free] = V.T
+    return dict(mesh=mesh, topo=topo, nd=nd, rt=rt, q1d=q1d, qd=qd, interp=interp, idx=idx, ori=ori, M=M, lam=lam, modes=modes,
                 eps=float(FIX["eps_r"]))
 
 

@@ -108,7 +108,8 @@ def test_box_cavity_eigenfrequencies(b2p_ctx):
     # the same eigenproblem on the oracle's assembled matrices
     Ko = common.oracle_matrix(prob, O.CURLCURL, ident, space=nd[p], eliminate=False)[free][:, free]
     Mo = common.oracle_matrix(prob, O.ND_MASS, ident, space=nd[p], eliminate=False)[free][:, free]
-    lam_ref = np.sort(spla.eigsh(Ko.tocsc(), k=nev, M=Mo.tocsc(), sigma=sigma, which="LM", tol=1e-13, return_eigenvectors=False))
+    lam_ref = np.sort(spla.eigsh(Ko.tocsc(), k=nev, M=Mo.tocsc(), sigma=sigma, which="LM", tol=1e-13, return_eigenvectors=False,
+                                 v0=np.random.default_rng(1).standard_normal(nf)))
 
     rel_ref = np.abs(lam_gpu - lam_ref) / lam_ref
     rel_exact = np.abs(lam_gpu - lam_exact) / lam_exact
