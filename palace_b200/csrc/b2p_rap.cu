@@ -93,10 +93,12 @@ public:
     P->refcount++;
     if (n_ess > 0)
     {
-      upload(c, ess_tdofs, (size_t)n_ess, &d_ess);
+      ok = upload(c, ess_tdofs, (size_t)n_ess, &d_ess) == B2P_SUCCESS;
       tx.resize(c, P->cols);
     }
+    ok = ok && (P->rows == 0 || (lx.p && ly.p)) && (n_ess == 0 || P->cols == 0 || tx.p);
   }
+  bool ok = true;  // device allocations of the constructor succeeded
   ~RapOperator() override
   {
     cudaFree(d_ess);
@@ -264,7 +266,9 @@ int b2p_operator_rap(b2p_ctx *ctx, b2p_operator *A_local, b2p_spmat *P, const in
   for (int64_t i = 0; i < n_ess; i++)
     B2P_CHECK(ctx, ess_tdofs[i] >= 0 && ess_tdofs[i] < P->cols, B2P_ERR_ARG, "b2p_operator_rap: essential true dof %d outside [0, %lld)",
               ess_tdofs[i], (long long)P->cols);
-  *out = wrap_operator(std::make_unique<RapOperator>(ctx, A, P, ess_tdofs, n_ess, diag_policy));
+  auto op = std::make_unique<RapOperator>(ctx, A, P, ess_tdofs, n_ess, diag_policy);
+  B2P_CHECK(ctx, op->ok, B2P_ERR_CUDA, "b2p_operator_rap: device allocation failed");
+  *out = wrap_operator(std::move(op));
   return B2P_SUCCESS;
 }
 
