@@ -601,13 +601,11 @@ public:
   bool IsReal() const override { return Ai == nullptr; }
   const int32_t *EssentialTrueDofs() const override
   {
-    const auto *p = dynamic_cast<const ParOperator *>(Ar ? Ar : Ai);
-    return p ? p->EssentialTrueDofs() : nullptr;
+    return (Ar ? Ar : Ai)->EssentialTrueDofs();  // ParOperator and its general-prolongation form report theirs; others none
   }
   int64_t NumEssential() const override
   {
-    const auto *p = dynamic_cast<const ParOperator *>(Ar ? Ar : Ai);
-    return p ? p->NumEssential() : 0;
+    return (Ar ? Ar : Ai)->NumEssential();
   }
   void Mult(CCPtr x, CPtr y) const override { apply(x, y, false); }
   void MultHermitianTranspose(CCPtr x, CPtr y) const override { apply(x, y, true); }

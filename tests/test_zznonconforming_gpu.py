@@ -274,3 +274,43 @@ def test_hiptmair_multigrid_on_the_non_conforming_mesh(b2p_ctx):
     st = K.stats()
     assert st["converged"] and st["its"] <= 25, st
     assert _rel(xd.cpu().numpy(), spla.spsolve(At[2].tocsc(), b)) < 1e-8
+
+
+def test_complex_system_on_the_non_conforming_mesh(b2p_ctx):
+    """ComplexWrapperOperator over two general-prolongation operators (real part P^T (K - w^2 M) P, imaginary part P^T (w C) P with
+    DIAG_ZERO): complex GMRES with the complex Jacobi smoother solves the lossy constrained system to the SciPy solution; the wrapper
+    reports the essential true dofs of its parts (what the complex multigrid masks restricted residuals with)."""
+    from palace_b200 import capi
+
+    p = 2
+    hb = nc.hanging_box_mesh(nc=(1, 1, 1), nfx=2, h=1.0, scramble_seed=2, n_attr=1)
+    cs = nc.build_constrained_nd_space(hb, p)
+    prob = common.problem_on_mesh(hb.mesh, p)
+    geom = common.gpu_geom(b2p_ctx, prob)
+    bk, bm = common.coefficient(O.CURLCURL, 1, "const"), common.coefficient(O.ND_MASS, 1, "const")
+    nL = prob.nd.ndofs
+    w2, wc = 1.3, 0.4
+    ops = [common.gpu_op(b2p_ctx, geom, prob, k, b) for k, b in ((O.CURLCURL, bk), (O.ND_MASS, bm), (O.ND_MASS, bm))]
+    Ar_loc = capi.Operator.par(b2p_ctx, nL, nL, ops[:2], [1.0, w2], None, diag_policy=1)
+    Ai_loc = capi.Operator.par(b2p_ctx, nL, nL, ops[2:], [wc], None, diag_policy=1)
+    P = capi.SpMat(b2p_ctx, cs.P)
+    Ar = capi.operator_rap(b2p_ctx, Ar_loc, P, cs.ess_tdofs, diag_policy=1)
+    Ai = capi.operator_rap(b2p_ctx, Ai_loc, P, cs.ess_tdofs, diag_policy=0)
+    Z = capi.ComplexOperator.wrap(b2p_ctx, Ar, Ai)
+    Ko = common.oracle_matrix(prob, O.CURLCURL, bk, eliminate=False)
+    Mo = common.oracle_matrix(prob, O.ND_MASS, bm, eliminate=False)
+    Zo = (S.eliminate((cs.P.T @ (Ko + w2 * Mo) @ cs.P).tocsr(), cs.ess_tdofs)
+          + 1j * S.eliminate((cs.P.T @ (wc * Mo) @ cs.P).tocsr(), cs.ess_tdofs, diag_one=False)).tocsc()
+    n = cs.P.shape[1]
+    rng = np.random.default_rng(6)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    b[cs.ess_tdofs] = 0.0
+    zj = capi.ComplexSolver.jacobi(b2p_ctx)
+    zj.set_operator(Z)
+    k = capi.ComplexSolver.krylov(b2p_ctx, capi.GMRES, rel_tol=1e-11, max_it=400, max_dim=400)
+    k.set_operator(Z)
+    k.set_preconditioner(zj)
+    xr, xi = torch.zeros(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+    k.mult(_dev(b.real), _dev(b.imag), xr, xi)
+    assert k.stats()["converged"]
+    assert _rel(xr.cpu().numpy() + 1j * xi.cpu().numpy(), spla.spsolve(Zo, b)) < 1e-8
