@@ -943,6 +943,30 @@ int b2p_op_create_sum(b2p_ctx *ctx, int n_terms, b2p_op *const *ops, const doubl
       if (!tc && ops[t]->dense_row_c >= 0 && ops[t]->kind != B2P_ND_MASS) tc = ops[t];
     }
     const int Q = o0->geom->Q, Ppad = o0->dense_Ppad, blk = 3 * Q;
+    // every term must tabulate the SAME basis: compare each term's blocks with the ones taken over
+    {
+      std::vector<double> ref((size_t)blk * Ppad), cmp((size_t)blk * Ppad);
+      for (int which = 0; which < 2 && !rc; which++)
+      {
+        const b2p_op *src = which ? tc : tu;
+        if (!src) continue;
+        const int srow = which ? src->dense_row_c : src->dense_row_u;
+        if (cudaMemcpy(ref.data(), src->dense_T + (size_t)srow * Ppad, sizeof(double) * ref.size(), cudaMemcpyDeviceToHost) != cudaSuccess) rc = B2P_ERR_CUDA;
+        for (int t = 0; t < n_terms && !rc; t++)
+        {
+          const int trow = which ? ops[t]->dense_row_c : ops[t]->dense_row_u;
+          if (ops[t] == src || trow < 0) continue;
+          if (cudaMemcpy(cmp.data(), ops[t]->dense_T + (size_t)trow * Ppad, sizeof(double) * cmp.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = B2P_ERR_CUDA;
+          else if (cmp != ref)
+          {
+            set_error(ctx, "b2p_op_create_sum: term %d tabulates another basis (its %s table differs)", t, which ? "derivative" : "value");
+            b2p_op_destroy(op);
+            return B2P_ERR_UNSUPPORTED;
+          }
+        }
+      }
+    }
     op->dense = true;
     op->dense_Ppad = Ppad;
     op->dense_row_u = tu ? 0 : -1;

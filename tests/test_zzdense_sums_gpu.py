@@ -123,3 +123,24 @@ def test_fused_dense_sum_assembles_into_the_coarse_matrix(b2p_ctx):
     x = torch.zeros(sp.ndofs, dtype=torch.float64, device="cuda")
     solver.mult(_dev(b), x)
     assert _rel(x.cpu().numpy(), spla.spsolve(Ao.tocsc(), b)) < 1e-9
+
+
+def test_terms_with_different_tables_are_not_fused(b2p_ctx):
+    """Two dense operators on one geometry handle that tabulate different bases must stay two operators."""
+    from palace_b200 import capi
+
+    prob = common.make_problem(n=(3, 2, 2), p=1, n_attr=1)
+    geom = capi.Geom.general(b2p_ctx, prob.qdata_ref)
+    sp = prob.nd
+    interp, curl, _ = O.nd_hex_tables(sp.p, prob.q1d)
+    idx, ori = sp.native_restriction()
+    bm = common.coefficient(O.ND_MASS, 1, "const")
+    M1 = capi.Op.create_dense(b2p_ctx, geom, O.ND_MASS, sp.ndofs, idx, ori, interp, None, bm)
+    M2 = capi.Op.create_dense(b2p_ctx, geom, O.ND_MASS, sp.ndofs, idx, ori, 2.0 * interp, None, bm)
+    A = capi.Operator.par(b2p_ctx, sp.ndofs, sp.ndofs, [M1, M2], [1.0, 1.0], None, diag_policy=1)
+    assert not A.is_fused()
+    x = np.random.default_rng(1).random(sp.ndofs)
+    y = torch.empty(sp.ndofs, dtype=torch.float64, device="cuda")
+    A.mult(_dev(x), y)
+    Mo = common.oracle_matrix(prob, O.ND_MASS, bm, eliminate=False)
+    assert _rel(y.cpu().numpy(), 5.0 * (Mo @ x)) < RTOL
