@@ -706,3 +706,56 @@ def global_interp_matrix(I_loc, in_idx, in_T, out_idx, out_Tdual, n_in, n_out):
         np.add.at(mult, out_idx[e], 1.0)
     A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_out, n_in))
     return sp.diags(1.0 / mult) @ A
+
+
+# ------------------------------------------------------------------------------------------------
+# Lowest-order Raviart-Thomas space and the discrete curl of the order-1 Nedelec space (the flux spaces of the error
+# estimators on simplices, /root/reference/palace/linalg/errorestimator.cpp: B = curl E lives in RT, D = eps E is projected to it)
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclasses.dataclass
+class RT0TetSpace:
+    ndofs: int
+    idx: np.ndarray      # [ne][4] face number of the local face opposite vertex f
+    orient: np.ndarray   # [ne][4] +1 / -1: outward normal against the global one (vertices sorted by global id, right-hand rule)
+
+
+def rt0_tet_tables(pts):
+    """interp[3][Q][4]: phi_f(x) = 2 (x - v_f), unit outward flux through the face opposite reference vertex f, zero through the others."""
+    pts = np.asarray(pts, dtype=np.float64)
+    interp = np.zeros((3, len(pts), 4))
+    for f in range(4):
+        interp[:, :, f] = 2.0 * (pts - _REF_VERTS[f][None]).T
+    return interp
+
+
+def build_rt0_tet_space(mesh: TetMesh, nd: TetSpace) -> RT0TetSpace:
+    ne = mesh.ne
+    idx = np.zeros((ne, 4), dtype=np.int32)
+    ori = np.zeros((ne, 4), dtype=np.int8)
+    X = mesh.verts
+    for e in range(ne):
+        v = mesh.elems[e]
+        for f in range(4):
+            g = sorted(int(v[t]) for t in range(4) if t != f)
+            idx[e, f] = nd.faces[tuple(g)]
+            n_glob = np.cross(X[g[1]] - X[g[0]], X[g[2]] - X[g[0]])
+            outward = X[g[0]] - X[int(v[f])]          # from the opposite vertex towards the face
+            ori[e, f] = 1 if n_glob @ outward > 0 else -1
+    return RT0TetSpace(nd.n_faces, idx, ori)
+
+
+def discrete_curl_p1(nd: TetSpace, rt: RT0TetSpace):
+    """Sparse [n_faces x n_edges]: the flux of curl u through a face is the circulation of u around it (order-1 ND dofs are edge
+    circulations from the lower to the higher vertex id; a face's loop runs g0 -> g1 -> g2 -> g0 over its sorted vertices)."""
+    import scipy.sparse as sp
+
+    assert nd.p == 1
+    rows, cols, vals = [], [], []
+    for g, F in nd.faces.items():
+        for (a, b, s) in ((g[0], g[1], 1.0), (g[1], g[2], 1.0), (g[0], g[2], -1.0)):
+            rows.append(F)
+            cols.append(nd.edges[(a, b)])
+            vals.append(s)
+    return sp.csr_matrix((vals, (rows, cols)), shape=(rt.ndofs, nd.ndofs))

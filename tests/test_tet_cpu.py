@@ -258,3 +258,37 @@ def test_transfer_operators_on_tets(p):
         Mc = _assemble_dense(O.ND_MASS, mesh, ic, cc, ndc.idx, ndc.dense_T, ndc.ndofs, ndc.P, qd)
         assert np.abs(Pg.T @ K @ Pg - Kc).max() < 1e-12 * np.abs(Kc).max()
         assert np.abs(Pg.T @ M @ Pg - Mc).max() < 1e-12 * np.abs(Mc).max()
+
+
+def test_lowest_order_raviart_thomas_space_and_discrete_curl():
+    """RT_0 on scrambled tets: unit outward reference fluxes, normal continuity through the orientation signs (a constant field has
+    one flux per face whichever neighbour computes it), and curl of the order-1 ND interpolant = RT_0 interpolant of the curl."""
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.25, scramble_seed=5)
+    nd = ts.build_nd_tet_space(mesh, 1)
+    rt = ts.build_rt0_tet_space(mesh, nd)
+    # reference fluxes: int over face g of phi_f . n = delta_fg
+    V = ts._REF_VERTS
+    for g in range(4):
+        oth = [t for t in range(4) if t != g]
+        c = V[oth].mean(axis=0)
+        nvec = np.cross(V[oth[1]] - V[oth[0]], V[oth[2]] - V[oth[0]]) / 2.0          # area-weighted normal
+        if nvec @ (c - V[g]) < 0:
+            nvec = -nvec
+        flux = ts.rt0_tet_tables(c[None])[:, 0, :].T @ nvec                          # the normal component is constant on a face
+        assert np.abs(flux - np.eye(4)[g]).max() < 1e-14
+    # a field with constant curl: E = 0.5 w x r + a  ->  curl E = w; ND dofs = edge circulations, RT dofs = face fluxes of w
+    w, a = np.array([0.3, -0.7, 0.5]), np.array([0.2, 0.1, -0.4])
+    x = ts.interpolate(mesh, nd, lambda X: 0.5 * np.cross(w, X) + a)
+    X = mesh.verts
+    flux = np.zeros(rt.ndofs)
+    for g, F in nd.faces.items():
+        flux[F] = 0.5 * np.cross(X[g[1]] - X[g[0]], X[g[2]] - X[g[0]]) @ w
+    C = ts.discrete_curl_p1(nd, rt)
+    assert np.abs(C @ x - flux).max() < 1e-13
+    # element view: the physical field J phi^ / detJ assembled with the signs reproduces the constant w in every element
+    interp = ts.rt0_tet_tables(np.array([[0.25, 0.25, 0.25]]))
+    for e in range(mesh.ne):
+        Xe = X[mesh.elems[e]]
+        J = np.stack([Xe[1] - Xe[0], Xe[2] - Xe[0], Xe[3] - Xe[0]], axis=1)
+        u = J @ (interp[:, 0, :] @ (rt.orient[e] * flux[rt.idx[e]])) / np.linalg.det(J)
+        assert np.abs(u - w).max() < 1e-12

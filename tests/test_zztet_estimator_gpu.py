@@ -1,0 +1,93 @@
+"""GPU: the flux error estimators on TETRAHEDRA at lowest order (the element type of BASELINE configs 3 and 4): order-1 Nedelec
+and RT_0 spaces of the host layer (tetspace.build_rt0_tet_space, discrete_curl_p1), curl-flux configuration
+(CurlFluxErrorEstimator, /root/reference/palace/linalg/errorestimator.cpp:400-513: mu^-1 B projected onto ND, element integrals) and
+grad-flux configuration (:272-398: eps E projected onto RT_0 with the table-described RT mass) through the C ABI against
+oracle/estimator.py; a field whose flux lies in the smooth space has no error."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from oracle import estimator as E
+from oracle import pyoracle as O
+from palace_b200.host import coeff as cf
+from palace_b200.host import tetspace as ts
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_flux_estimators_on_lowest_order_tetrahedra(b2p_ctx):
+    from palace_b200 import capi
+
+    mesh = ts.box_tet_mesh((2, 2, 2), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=9, n_attr=2)
+    nd = ts.build_nd_tet_space(mesh, 1)
+    rt = ts.build_rt0_tet_space(mesh, nd)
+    C = ts.discrete_curl_p1(nd, rt)
+    nd_interp, _, qpts, qw = ts.nd_tet_tables(1, 4)
+    rt_interp = ts.rt0_tet_tables(qpts)
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    ne = mesh.ne
+    geom = capi.Geom.general(b2p_ctx, qd)
+    nd_sign = nd.orient_signs()
+    sp_nd = dict(P=nd.P, map_type=capi.MAP_HCURL, interp=nd_interp, idx=nd.idx, orient=nd_sign, lsize=nd.ndofs)
+    sp_rt = dict(P=4, map_type=capi.MAP_HDIV, interp=rt_interp, idx=rt.idx, orient=rt.orient, lsize=rt.ndofs)
+    mop = capi.Op.create_dense(b2p_ctx, geom, O.ND_MASS, nd.ndofs, nd.idx, nd_sign, nd_interp, None, cf.coeff_ctx(a=1.0))
+    Mnd = capi.Operator.par(b2p_ctx, nd.ndofs, nd.ndofs, [mop], None, None, diag_policy=1)
+    # two materials: mu^-1 = diag-dominant SPD matrices per attribute
+    muinv = np.array([[[2.0, 0.1, 0.0], [0.1, 1.5, 0.2], [0.0, 0.2, 1.0]], [[1.0, 0.0, 0.3], [0.0, 3.0, 0.0], [0.3, 0.0, 2.0]]])
+    c_flux = np.stack([m.ravel(order="F") for m in muinv])
+    c_disc = np.stack([E.spd_power(m, 0.5).ravel(order="F") for m in muinv])
+    c_smooth = np.stack([E.spd_power(m, -0.5).ravel(order="F") for m in muinv])
+    est = capi.FluxEstimator(b2p_ctx, geom, sp_rt, sp_nd, c_flux, c_disc, c_smooth, Mnd, tol=1e-13, max_it=5000)
+    attr = mesh.attr - 1
+    celem = lambda tab: [E._mat33(tab[a]) for a in attr]
+    idx_n, ori_n = nd.idx.astype(np.int64), nd_sign.astype(float)
+    idx_r, ori_r = rt.idx.astype(np.int64), rt.orient.astype(float)
+    F = E.mixed_mass_matrix(qd, rt_interp, E.HDIV, idx_r, ori_r, rt.ndofs, nd_interp, E.HCURL, idx_n, ori_n, nd.ndofs, celem(c_flux))
+    Mo = E.mixed_mass_matrix(qd, nd_interp, E.HCURL, idx_n, ori_n, nd.ndofs, nd_interp, E.HCURL, idx_n, ori_n, nd.ndofs, [np.eye(3)] * ne)
+    rng = np.random.default_rng(5)
+    B = C @ rng.standard_normal(nd.ndofs)                       # a discrete curl: the estimator's input in the reference
+    H_ref = spla.spsolve(Mo.tocsc(), F @ B)
+    eta2 = E.element_errors(qd, rt_interp, E.HDIV, idx_r, ori_r, B, celem(c_disc), nd_interp, E.HCURL, idx_n, ori_n, H_ref, celem(c_smooth))
+    Hd = torch.zeros(nd.ndofs, dtype=torch.float64, device="cuda")
+    est.project(_dev(B), Hd)
+    assert est.stats()["converged"] and _rel(Hd.cpu().numpy(), H_ref) < 1e-9
+    ed = torch.zeros(ne, dtype=torch.float64, device="cuda")
+    est.integrate(_dev(B), Hd, ed)
+    assert _rel(ed.cpu().numpy(), eta2) < 1e-9
+    # one material, constant B: mu^-1 B is a constant field, which the order-1 ND space holds exactly -> no error
+    I9 = np.eye(3).ravel()[None].repeat(2, axis=0)
+    est1 = capi.FluxEstimator(b2p_ctx, geom, sp_rt, sp_nd, I9, I9, I9, Mnd, tol=1e-14, max_it=5000)
+    w = np.array([0.3, -0.7, 0.5])
+    X = mesh.verts
+    Bc = np.zeros(rt.ndofs)
+    for g, Fi in nd.faces.items():
+        Bc[Fi] = 0.5 * np.cross(X[g[1]] - X[g[0]], X[g[2]] - X[g[0]]) @ w
+    est1.indicator(_dev(Bc), None, 0.0, ed)
+    assert float(ed.abs().max()) < 1e-10 * np.linalg.norm(w)
+    # grad-flux roles: eps E (E in ND) projected onto RT_0 with the table-described RT mass
+    Mrt = capi.vecfe_mass_operator(b2p_ctx, geom, sp_rt)
+    Mrt_o = E.mixed_mass_matrix(qd, rt_interp, E.HDIV, idx_r, ori_r, rt.ndofs, rt_interp, E.HDIV, idx_r, ori_r, rt.ndofs, [np.eye(3)] * ne)
+    xr = rng.standard_normal(rt.ndofs)
+    yr = torch.empty(rt.ndofs, dtype=torch.float64, device="cuda")
+    Mrt.mult(_dev(xr), yr)
+    assert _rel(yr.cpu().numpy(), Mrt_o @ xr) < 1e-12
+    gest = capi.FluxEstimator(b2p_ctx, geom, sp_nd, sp_rt, c_flux, c_disc, c_smooth, Mrt, tol=1e-13, max_it=5000)
+    Ev = rng.standard_normal(nd.ndofs)
+    Fg = E.mixed_mass_matrix(qd, nd_interp, E.HCURL, idx_n, ori_n, nd.ndofs, rt_interp, E.HDIV, idx_r, ori_r, rt.ndofs, celem(c_flux))
+    D_ref = spla.spsolve(Mrt_o.tocsc(), Fg @ Ev)
+    eg = E.element_errors(qd, nd_interp, E.HCURL, idx_n, ori_n, Ev, celem(c_disc), rt_interp, E.HDIV, idx_r, ori_r, D_ref, celem(c_smooth))
+    Dd = torch.zeros(rt.ndofs, dtype=torch.float64, device="cuda")
+    gest.project(_dev(Ev), Dd)
+    assert gest.stats()["converged"] and _rel(Dd.cpu().numpy(), D_ref) < 1e-9
+    ed.zero_()
+    gest.integrate(_dev(Ev), Dd, ed)
+    assert _rel(ed.cpu().numpy(), eg) < 1e-8
