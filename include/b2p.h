@@ -540,6 +540,9 @@ typedef struct
   const int32_t *idx;   /* [ne][P] */
   const int8_t *orient; /* [ne][P] or NULL */
   int64_t lsize;
+  /* [ne][P][3] row-major tridiagonal element transformations of ND tetrahedra / prisms of order >= 2 (restriction.cpp:301-329, as
+   * b2p_dense_op_desc.curl_orient) or NULL; when given it carries the signs and `orient` is ignored */
+  const int8_t *curl_orient;
 } b2p_vecfe_space_desc;
 typedef struct b2p_flux_estimator b2p_flux_estimator;
 /* VectorFEMassIntegrator on ONE table-described space: y = sum_e E^T B^T (w detJ P^T C P) B E x with the space's map P; coef

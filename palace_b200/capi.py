@@ -949,7 +949,7 @@ class DivFree:
 class VecFESpaceDesc(C.Structure):
     """b2p_vecfe_space_desc (include/b2p.h): a vector finite element space as libCEED sees a non-tensor basis."""
     _fields_ = [("P", C.c_int), ("map_type", C.c_int), ("interp", C.c_void_p), ("idx", C.c_void_p), ("orient", C.c_void_p),
-                ("lsize", C.c_int64)]
+                ("lsize", C.c_int64), ("curl_orient", C.c_void_p)]
 
 
 MAP_HCURL, MAP_HDIV = 1, 2
@@ -959,9 +959,10 @@ def _vecfe_desc(sp, keep):
     interp = np.ascontiguousarray(sp["interp"], dtype=np.float64)
     idx = np.ascontiguousarray(sp["idx"], dtype=np.int32)
     ori = None if sp.get("orient") is None else np.ascontiguousarray(sp["orient"], dtype=np.int8)
-    keep.extend([interp, idx, ori])
+    co = None if sp.get("curl_orient") is None else np.ascontiguousarray(sp["curl_orient"], dtype=np.int8)
+    keep.extend([interp, idx, ori, co])
     return VecFESpaceDesc(int(sp["P"]), int(sp["map_type"]), interp.ctypes.data, idx.ctypes.data, None if ori is None else ori.ctypes.data,
-                          int(sp["lsize"]))
+                          int(sp["lsize"]), None if co is None else co.ctypes.data)
 
 
 def vecfe_mass_operator(ctx, geom, space, coef=None):

@@ -44,6 +44,9 @@ struct VecFESpace
   int64_t lsize = 0;
   double *interp = nullptr;  // device [3][Q][P]
   int32_t *sidx = nullptr;   // device [ne][P], sign folded in: >= 0 -> +x[i], < 0 -> -x[-1 - i]
+  // device [ne][P][3] row-major tridiagonal element transformation (ND tetrahedra / prisms of order >= 2, restriction.cpp:301-329)
+  // or null; with it sidx holds plain indices and x_e = T_e x[idx_e]
+  int8_t *co = nullptr;
 };
 
 __device__ __forceinline__ double gather_signed(const double *x, int32_t gi) { return gi >= 0 ? x[gi] : -x[-1 - gi]; }
@@ -58,6 +61,48 @@ __device__ __forceinline__ void piola_matrix(int map, const double A[9], double 
   }
   else
     cofactor33(A, M);
+}
+
+// x_e of element e in shared memory (all threads of the block; ends with a barrier): signs folded into the index, or the tridiagonal
+// transformation applied to the raw values (tmp: P doubles of scratch, used only then)
+__device__ void load_element_vector(const VecFESpace &sp, int e, const double *__restrict__ x, double *xe, double *tmp)
+{
+  if (!sp.co)
+  {
+    for (int j = threadIdx.x; j < sp.P; j += blockDim.x) xe[j] = gather_signed(x, sp.sidx[(size_t)e * sp.P + j]);
+    __syncthreads();
+    return;
+  }
+  for (int j = threadIdx.x; j < sp.P; j += blockDim.x) tmp[j] = x[sp.sidx[(size_t)e * sp.P + j]];
+  __syncthreads();
+  const int8_t *co = sp.co + (size_t)e * sp.P * 3;
+  for (int i = threadIdx.x; i < sp.P; i += blockDim.x)
+  {
+    double v = (double)co[3 * i + 1] * tmp[i];
+    if (i > 0) v += (double)co[3 * i] * tmp[i - 1];
+    if (i < sp.P - 1) v += (double)co[3 * i + 2] * tmp[i + 1];
+    xe[i] = v;
+  }
+  __syncthreads();
+}
+// entry j of T_e^T s (s in shared memory)
+__device__ __forceinline__ double transposed_entry(const VecFESpace &sp, int e, const double *s, int j)
+{
+  const int8_t *co = sp.co + (size_t)e * sp.P * 3;
+  double v = (double)co[3 * j + 1] * s[j];
+  if (j > 0) v += (double)co[3 * (j - 1) + 2] * s[j - 1];
+  if (j < sp.P - 1) v += (double)co[3 * (j + 1)] * s[j + 1];
+  return v;
+}
+// value of table row `row` for the j-th GLOBAL-side shape function of element e: column j, or the combination T_e(., j) of columns
+__device__ __forceinline__ double transformed_column(const VecFESpace &sp, int e, const double *row, int j)
+{
+  if (!sp.co) return row[j];
+  const int8_t *co = sp.co + (size_t)e * sp.P * 3;
+  double v = (double)co[3 * j + 1] * row[j];
+  if (j > 0) v += (double)co[3 * (j - 1) + 2] * row[j - 1];
+  if (j < sp.P - 1) v += (double)co[3 * (j + 1)] * row[j + 1];
+  return v;
 }
 
 // values of space `sp` at the quadrature points of element e: u[c * Q + q] = sum_j interp[c][q][j] xe[j]
@@ -77,11 +122,11 @@ __global__ void mixed_mass_kernel(int ne, int Q, int q1d, VecFESpace trial, VecF
                                   const double *__restrict__ coef, const double *__restrict__ x, double *y)
 {
   B2P_DYN_SMEM(double, sm);
-  double *xe = sm, *u = sm + max(trial.P, test.P);
+  const int PM = max(trial.P, test.P);
+  double *xe = sm, *u = sm + PM, *tmp = u + 3 * Q;  // tmp [PM]: raw values / element result of transformed restrictions
   const int e = blockIdx.x;
   if (e >= ne) return;
-  for (int j = threadIdx.x; j < trial.P; j += blockDim.x) xe[j] = gather_signed(x, trial.sidx[(size_t)e * trial.P + j]);
-  __syncthreads();
+  load_element_vector(trial, e, x, xe, tmp);
   eval_at_points(Q, trial.P, trial.interp, xe, u);
   __syncthreads();
   const double *C = coef + (size_t)e * 9;
@@ -112,8 +157,18 @@ __global__ void mixed_mass_kernel(int ne, int Q, int q1d, VecFESpace trial, VecF
   {
     double s = 0.0;
     for (int w = 0; w < 3 * Q; w++) s += test.interp[(size_t)w * test.P + i] * u[w];
-    const int32_t gi = test.sidx[(size_t)e * test.P + i];
-    atomicAdd(y + (gi >= 0 ? gi : -1 - gi), gi >= 0 ? s : -s);
+    if (test.co)
+      tmp[i] = s;
+    else
+    {
+      const int32_t gi = test.sidx[(size_t)e * test.P + i];
+      atomicAdd(y + (gi >= 0 ? gi : -1 - gi), gi >= 0 ? s : -s);
+    }
+  }
+  if (test.co)
+  {
+    __syncthreads();
+    for (int j = threadIdx.x; j < test.P; j += blockDim.x) atomicAdd(y + test.sidx[(size_t)e * test.P + j], transposed_entry(test, e, tmp, j));
   }
 }
 
@@ -123,12 +178,11 @@ __global__ void flux_error_kernel(int ne, int Q, int q1d, VecFESpace s1, VecFESp
                                   const double *__restrict__ x2, double *est)
 {
   B2P_DYN_SMEM(double, sm);
-  double *xe1 = sm, *xe2 = xe1 + s1.P, *u1 = xe2 + s2.P, *u2 = u1 + 3 * Q, *red = u2 + 3 * Q;
+  double *xe1 = sm, *xe2 = xe1 + s1.P, *u1 = xe2 + s2.P, *u2 = u1 + 3 * Q, *red = u2 + 3 * Q, *tmp = red + FLUX_NT;  // tmp [max P]
   const int e = blockIdx.x;
   if (e >= ne) return;
-  for (int j = threadIdx.x; j < s1.P; j += blockDim.x) xe1[j] = gather_signed(x1, s1.sidx[(size_t)e * s1.P + j]);
-  for (int j = threadIdx.x; j < s2.P; j += blockDim.x) xe2[j] = gather_signed(x2, s2.sidx[(size_t)e * s2.P + j]);
-  __syncthreads();
+  load_element_vector(s1, e, x1, xe1, tmp);
+  load_element_vector(s2, e, x2, xe2, tmp);
   eval_at_points(Q, s1.P, s1.interp, xe1, u1);
   eval_at_points(Q, s2.P, s2.interp, xe2, u2);
   __syncthreads();
@@ -183,7 +237,7 @@ public:
   void Mult(const double *x, double *y) const override
   {
     vec::set(ctx, y, height, 0.0);
-    const size_t shmem = (size_t)(std::max(trial.P, test.P) + 3 * geom->Q) * sizeof(double);
+    const size_t shmem = (size_t)(2 * std::max(trial.P, test.P) + 3 * geom->Q) * sizeof(double);
     if (shmem > 48 * 1024) cudaFuncSetAttribute(mixed_mass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
     B2P_LAUNCH(mixed_mass_kernel, geom->ne, FLUX_NT, shmem, ctx->stream, geom->ne, geom->Q, geom->q1d, trial, test,
                (const double *)geom->qd, d_coef, x, y);
@@ -215,8 +269,9 @@ __global__ void vecfe_mass_diag_kernel(int ne, int Q, int q1d, VecFESpace sp, co
         Cm[k] = C[k];
       }
       piola_matrix(sp.map, A, M);
-      const double u[3] = {sp.interp[(size_t)(0 * Q + q) * sp.P + i], sp.interp[(size_t)(1 * Q + q) * sp.P + i],
-                           sp.interp[(size_t)(2 * Q + q) * sp.P + i]};
+      const double u[3] = {transformed_column(sp, e, sp.interp + (size_t)(0 * Q + q) * sp.P, i),
+                           transformed_column(sp, e, sp.interp + (size_t)(1 * Q + q) * sp.P, i),
+                           transformed_column(sp, e, sp.interp + (size_t)(2 * Q + q) * sp.P, i)};
       double t[3], z[3];
       Ax33(M, u, t);
       Ax33(Cm, t, z);
@@ -241,6 +296,7 @@ public:
   {
     cudaFree(trial.interp);
     cudaFree(trial.sidx);
+    cudaFree(trial.co);
     cudaFree(owned_coef);
     b2p_geom_destroy(owned_geom);
   }
@@ -288,10 +344,11 @@ int upload_space(b2p_ctx *ctx, const b2p_vecfe_space_desc *d, int ne, int Q, Vec
     const int32_t g = d->idx[i];
     B2P_CHECK(ctx, g >= 0 && g < d->lsize, B2P_ERR_ARG, "b2p_flux_estimator_create: restriction index %d outside [0, %lld)", (int)g,
               (long long)d->lsize);
-    s[i] = (d->orient && d->orient[i] < 0) ? -1 - g : g;
+    s[i] = (!d->curl_orient && d->orient && d->orient[i] < 0) ? -1 - g : g;  // (the tridiagonal rows carry the signs themselves)
   }
   int rc = upload(ctx, s.data(), s.size(), &out->sidx);
   if (rc) return rc;
+  if (d->curl_orient && (rc = upload(ctx, d->curl_orient, (size_t)ne * d->P * 3, &out->co))) return rc;
   return upload(ctx, d->interp, (size_t)3 * Q * d->P, &out->interp);
 }
 
@@ -316,8 +373,10 @@ struct b2p_flux_estimator
   {
     cudaFree(flux.interp);
     cudaFree(flux.sidx);
+    cudaFree(flux.co);
     cudaFree(smooth.interp);
     cudaFree(smooth.sidx);
+    cudaFree(smooth.co);
     cudaFree(d_coef_flux);
     cudaFree(d_coef_disc);
     cudaFree(d_coef_smooth);
@@ -419,7 +478,7 @@ int b2p_flux_estimator_integrate(b2p_flux_estimator *e, const double *flux_dofs,
   if (!e || !flux_dofs || !smooth_dofs || !estimates) return B2P_ERR_ARG;
   b2p_ctx *ctx = e->ctx;
   const b2p_geom *g = e->geom;
-  const size_t shmem = (size_t)(e->flux.P + e->smooth.P + 6 * g->Q + FLUX_NT) * sizeof(double);
+  const size_t shmem = (size_t)(e->flux.P + e->smooth.P + 6 * g->Q + FLUX_NT + std::max(e->flux.P, e->smooth.P)) * sizeof(double);
   if (shmem > 48 * 1024) cudaFuncSetAttribute(flux_error_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
   B2P_LAUNCH(flux_error_kernel, g->ne, FLUX_NT, shmem, ctx->stream, g->ne, g->Q, g->q1d, e->flux, e->smooth, (const double *)g->qd,
              (const double *)e->d_coef_disc, (const double *)e->d_coef_smooth, flux_dofs, smooth_dofs, estimates);
