@@ -45,5 +45,5 @@ def test_element_kernels_under_emulation(order):
 def test_solver_layer_under_emulation():
     """Vector kernels, smoothers, interpolators, V-cycle and Krylov solvers: the whole device-resident loop of
     tests/test_solvers_gpu.py the divergence-free projection of tests/test_divfree_gpu.py and the flux error estimator of
-    tests/test_flux_estimator_gpu.py on the emulated machine (reductions use two blocks per emulated SM)."""
-    assert _run(["tests/test_solvers_gpu.py", "tests/test_divfree_gpu.py", "tests/test_flux_estimator_gpu.py"], "fwd") >= 34
+    tests/test_zzflux_estimator_gpu.py on the emulated machine (reductions use two blocks per emulated SM)."""
+    assert _run(["tests/test_solvers_gpu.py", "tests/test_divfree_gpu.py", "tests/test_zzflux_estimator_gpu.py"], "fwd") >= 34
