@@ -759,3 +759,165 @@ def discrete_curl_p1(nd: TetSpace, rt: RT0TetSpace):
             cols.append(nd.edges[(a, b)])
             vals.append(s)
     return sp.csr_matrix((vals, (rows, cols)), shape=(rt.ndofs, nd.ndofs))
+
+
+# ------------------------------------------------------------------------------------------------
+# Raviart-Thomas tetrahedra RT_k (k = p - 1: the flux space of order-p Nedelec fields) and the element-local discrete curl
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclasses.dataclass
+class RTTetElement:
+    k: int
+    P: int
+    nodes: np.ndarray     # [P][3] reference points of the dof functionals
+    dirs: np.ndarray      # [P][3] functional d(u) = u(node) . dir: twice the outward area vector on faces, unit vectors inside
+    coef: np.ndarray      # [P][M] shape function d = sum_m coef[d][m] phi_m
+    face_off: int = 0     # faces first ((k+1)(k+2)/2 each, TET_FACES order), then the interior
+    int_off: int = 0
+    cond: float = 0.0
+
+    def tabulate(self, pts):
+        """interp[3][n][P]: reference shape functions at pts (contravariant Piola: u = J u^ / detJ)."""
+        Phi = _rt_modal_basis(self.k, np.asarray(pts, dtype=np.float64))
+        return np.ascontiguousarray(np.einsum("dm,mnc->cnd", self.coef, Phi))
+
+
+def rt_tet_ndof(k: int) -> int:
+    return (k + 1) * (k + 2) * (k + 4) // 2
+
+
+def _rt_modal_basis(k, pts):
+    """A basis of RT_k = P_k^3 + (x - c) P~_k at pts: Phi[M][n][3] (products of shifted Legendre polynomials; the last block uses the
+    products of total degree exactly k, whose leading parts span the homogeneous polynomials)."""
+    n = pts.shape[0]
+    Lx, _ = _leg01(k, pts[:, 0])
+    Ly, _ = _leg01(k, pts[:, 1])
+    Lz, _ = _leg01(k, pts[:, 2])
+    Phi = []
+    for l in range(k + 1):
+        for j in range(k + 1 - l):
+            for i in range(k + 1 - l - j):
+                s = Lx[:, i] * Ly[:, j] * Lz[:, l]
+                for d in range(3):
+                    v = np.zeros((n, 3))
+                    v[:, d] = s
+                    Phi.append(v)
+    xc = pts - 0.25
+    for l in range(k + 1):
+        for j in range(k + 1 - l):
+            i = k - l - j
+            Phi.append((Lx[:, i] * Ly[:, j] * Lz[:, l])[:, None] * xc)
+    return np.array(Phi)
+
+
+def rt_face_index(k):
+    """(i1, i2) -> running index of the (k + 1)(k + 2) / 2 points of a face's lattice (i1 + i2 <= k; weights of the second and third
+    vertex of the face in its canonical, sorted-by-global-id order)."""
+    out, o = {}, 0
+    for j in range(k + 1):
+        for i in range(k + 1 - j):
+            out[(i, j)] = o
+            o += 1
+    return out
+
+
+def _rt_functionals(k):
+    V = _REF_VERTS
+    nodes, dirs = [], []
+    for (a, b, c) in TET_FACES:
+        nf = np.cross(V[b] - V[a], V[c] - V[a])             # twice the outward area vector
+        for j in range(k + 1):
+            for i in range(k + 1 - j):
+                w = np.array([k - i - j + 1.0, i + 1.0, j + 1.0]) / (k + 3.0)    # open lattice: strictly inside the face
+                nodes.append(w[0] * V[a] + w[1] * V[b] + w[2] * V[c])
+                dirs.append(nf)
+    int_off = len(nodes)
+    for l in range(k):
+        for j in range(k - l):
+            for i in range(k - l - j):
+                x = np.array([i + 1.0, j + 1.0, l + 1.0]) / (k + 3.0)
+                for d in range(3):
+                    nodes.append(x)
+                    dirs.append(np.eye(3)[d])
+    return np.array(nodes), np.array(dirs), int_off
+
+
+_RT_ELEMENTS = {}
+
+
+def rt_tet_element(k: int) -> RTTetElement:
+    if k in _RT_ELEMENTS:
+        return _RT_ELEMENTS[k]
+    nodes, dirs, int_off = _rt_functionals(k)
+    P = rt_tet_ndof(k)
+    assert nodes.shape[0] == P, (nodes.shape, P)
+    Phi = _rt_modal_basis(k, nodes)
+    assert Phi.shape[0] == P
+    T = np.einsum("mdc,dc->md", Phi, dirs)
+    el = RTTetElement(k, P, nodes, dirs, np.linalg.inv(T), 0, int_off, float(np.linalg.cond(T)))
+    _RT_ELEMENTS[k] = el
+    return el
+
+
+@dataclasses.dataclass
+class RTTetSpace:
+    k: int
+    P: int
+    ndofs: int
+    idx: np.ndarray      # [ne][P]
+    orient: np.ndarray   # [ne][P] +1 / -1 (face dofs: local outward normal against the global one; interior: +1)
+
+
+def _perm_parity(seq):
+    s, seq = 1, list(seq)
+    for i in range(len(seq)):
+        for j in range(i + 1, len(seq)):
+            if seq[i] > seq[j]:
+                s = -s
+    return s
+
+
+def build_rt_tet_space(mesh: TetMesh, nd: TetSpace, k: int) -> RTTetSpace:
+    """Global RT_k space on the faces numbered by `nd` (any order of nd): a face's dofs sit on its lattice in the canonical order of its
+    vertices sorted by global id, with the normal of that order (right-hand rule); a tetrahedron sees them through the permutation
+    of its own vertex order and the sign of that permutation."""
+    el = rt_tet_element(k)
+    nfd = (k + 1) * (k + 2) // 2
+    nid = el.P - 4 * nfd
+    fidx = rt_face_index(k)
+    ne = mesh.ne
+    int_base = nfd * nd.n_faces
+    idx = np.zeros((ne, el.P), dtype=np.int32)
+    ori = np.ones((ne, el.P), dtype=np.int8)
+    for e in range(ne):
+        v = mesh.elems[e]
+        o = 0
+        for f in TET_FACES:
+            g = [int(v[t]) for t in f]
+            key = tuple(sorted(g))
+            rank = [key.index(t) for t in g]
+            sgn = _perm_parity(rank)
+            base = nfd * nd.faces[key]
+            for j in range(k + 1):
+                for i in range(k + 1 - j):
+                    trip = (k - i - j, i, j)          # lattice weights on the local vertices a, b, c
+                    gtrip = [0, 0, 0]
+                    for t in range(3):
+                        gtrip[rank[t]] = trip[t]
+                    idx[e, o], ori[e, o] = base + fidx[(gtrip[1], gtrip[2])], sgn
+                    o += 1
+        for t in range(nid):
+            idx[e, o] = int_base + nid * e + t
+            o += 1
+        assert o == el.P
+    return RTTetSpace(k, el.P, int_base + nid * ne, idx, ori)
+
+
+def tet_discrete_curl(p: int) -> np.ndarray:
+    """[P_rt x P_nd] element matrix of the discrete curl ND_p -> RT_{p-1} in reference coordinates: entry (i, j) is the i-th RT dof
+    functional of curl phi_j (the curl of a covariantly mapped field is the contravariantly mapped reference curl, so one matrix
+    serves every element)."""
+    nd, rt = nd_tet_element(p), rt_tet_element(p - 1)
+    _, curl = nd.tabulate(rt.nodes)                       # [3][P_rt][P_nd]
+    return np.einsum("cij,ic->ij", curl, rt.dirs)

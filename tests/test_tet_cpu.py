@@ -292,3 +292,64 @@ def test_lowest_order_raviart_thomas_space_and_discrete_curl():
         J = np.stack([Xe[1] - Xe[0], Xe[2] - Xe[0], Xe[3] - Xe[0]], axis=1)
         u = J @ (interp[:, 0, :] @ (rt.orient[e] * flux[rt.idx[e]])) / np.linalg.det(J)
         assert np.abs(u - w).max() < 1e-12
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_raviart_thomas_tetrahedra_and_the_discrete_curl(p):
+    """RT_{p-1} on scrambled, jittered tets: unisolvent reference element, normal continuity of the assembled space (a polynomial
+    field of the space has ONE set of global dofs whichever tetrahedron evaluates them), and the commuting property
+    curl(ND interpolant) = RT interpolant of the curl for fields of the ND space."""
+    k = p - 1
+    el = ts.rt_tet_element(k)
+    assert el.P == ts.rt_tet_ndof(k) and el.cond < 1e6
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.25, scramble_seed=5)
+    nd = ts.build_nd_tet_space(mesh, p)
+    rt = ts.build_rt_tet_space(mesh, nd, k)
+    # a field of P_{p-1}^3 (inside RT_k): u = polynomial; global dofs from every element must agree
+    rng = np.random.default_rng(p)
+    A = rng.standard_normal((3, 3))
+    c0 = rng.standard_normal(3)
+
+    def curl_field(X):   # curl of E below when p >= 2: constant; for p = 1 take a constant field
+        return np.array([A[2, 1] - A[1, 2], A[0, 2] - A[2, 0], A[1, 0] - A[0, 1]]) if p >= 2 else np.zeros(3)
+
+    def E_field(X):
+        return (A @ X + c0) if p >= 2 else c0
+
+    u = (lambda X: A @ X + c0) if k >= 1 else (lambda X: c0)
+    vals = np.full(rt.ndofs, np.nan)
+    for e in range(mesh.ne):
+        Xe = mesh.verts[mesh.elems[e]]
+        J = np.stack([Xe[1] - Xe[0], Xe[2] - Xe[0], Xe[3] - Xe[0]], axis=1)
+        detJ = np.linalg.det(J)
+        for i in range(el.P):
+            x = Xe[0] + J @ el.nodes[i]
+            uhat = detJ * np.linalg.solve(J, u(x))            # u = J u^ / detJ
+            d = rt.orient[e, i] * (uhat @ el.dirs[i])
+            g = rt.idx[e, i]
+            if np.isnan(vals[g]):
+                vals[g] = d
+            else:
+                assert abs(vals[g] - d) < 1e-11 * (1 + abs(d))
+    assert not np.isnan(vals).any()
+    # reconstruction inside an element reproduces the field
+    pts = np.array([[0.2, 0.3, 0.1], [0.25, 0.25, 0.25]])
+    tab = el.tabulate(pts)
+    for e in (0, mesh.ne - 1):
+        Xe = mesh.verts[mesh.elems[e]]
+        J = np.stack([Xe[1] - Xe[0], Xe[2] - Xe[0], Xe[3] - Xe[0]], axis=1)
+        for q in range(2):
+            uq = J @ (tab[:, q, :] @ (rt.orient[e] * vals[rt.idx[e]])) / np.linalg.det(J)
+            assert np.abs(uq - u(Xe[0] + J @ pts[q])).max() < 1e-10
+    # commuting diagram on the ND interpolant of E
+    x_nd = ts.interpolate(mesh, nd, E_field)
+    C = ts.tet_discrete_curl(p)
+    for e in range(mesh.ne):
+        Xe = mesh.verts[mesh.elems[e]]
+        J = np.stack([Xe[1] - Xe[0], Xe[2] - Xe[0], Xe[3] - Xe[0]], axis=1)
+        detJ = np.linalg.det(J)
+        b_loc = C @ (nd.dense_T(e) @ x_nd[nd.idx[e]])
+        for i in range(el.P):
+            x = Xe[0] + J @ el.nodes[i]
+            want = (detJ * np.linalg.solve(J, curl_field(x))) @ el.dirs[i]
+            assert abs(b_loc[i] - want) < 1e-10 * (1 + abs(want))

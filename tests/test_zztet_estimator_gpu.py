@@ -91,3 +91,56 @@ def test_flux_estimators_on_lowest_order_tetrahedra(b2p_ctx):
     ed.zero_()
     gest.integrate(_dev(Ev), Dd, ed)
     assert _rel(ed.cpu().numpy(), eg) < 1e-8
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_curl_flux_estimator_on_higher_order_tetrahedra(b2p_ctx, p):
+    """Order-p Nedelec tetrahedra with their REAL tridiagonal element transformations (scrambled vertex orders) as the smooth space,
+    RT_{p-1} as the flux space, B a discrete curl: projection and element errors against the oracle on transformed element vectors;
+    a field whose curl flux is a polynomial the ND space holds has no error."""
+    from palace_b200 import capi
+    from tests.test_zzflux_curl_oriented_gpu import assembled, dense_T
+
+    mesh = ts.box_tet_mesh((2, 1, 1), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=11)
+    nd = ts.build_nd_tet_space(mesh, p)
+    rt = ts.build_rt_tet_space(mesh, nd, p - 1)
+    nd_i, _, qpts, qw = ts.nd_tet_tables(p, 2 * p + 1)
+    rt_i = ts.rt_tet_element(p - 1).tabulate(qpts)
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    ne = mesh.ne
+    geom = capi.Geom.general(b2p_ctx, qd)
+    sp_nd = dict(P=nd.P, map_type=capi.MAP_HCURL, interp=nd_i, idx=nd.idx, orient=None, lsize=nd.ndofs, curl_orient=nd.curl_orient)
+    sp_rt = dict(P=rt.P, map_type=capi.MAP_HDIV, interp=rt_i, idx=rt.idx, orient=rt.orient, lsize=rt.ndofs)
+    Mnd = capi.vecfe_mass_operator(b2p_ctx, geom, sp_nd)
+    I9 = np.eye(3).ravel()[None]
+    est = capi.FluxEstimator(b2p_ctx, geom, sp_rt, sp_nd, I9, I9, I9, Mnd, tol=1e-13, max_it=8000)
+    co_r = np.zeros((ne, rt.P, 3), dtype=np.int8)
+    co_r[:, :, 1] = rt.orient
+    I3 = [np.eye(3)] * ne
+    F = assembled(qd, rt_i, E.HDIV, rt.idx, co_r, rt.ndofs, nd_i, E.HCURL, nd.idx, nd.curl_orient, nd.ndofs, I3)
+    Mo = assembled(qd, nd_i, E.HCURL, nd.idx, nd.curl_orient, nd.ndofs, nd_i, E.HCURL, nd.idx, nd.curl_orient, nd.ndofs, I3)
+    C = ts.tet_discrete_curl(p)
+    rng = np.random.default_rng(p)
+    x = rng.standard_normal(nd.ndofs)
+    B = np.zeros(rt.ndofs)
+    for e in range(ne):                                      # global RT dofs of curl x (the same from every element: conformity)
+        B[rt.idx[e]] = rt.orient[e] * (C @ (nd.dense_T(e) @ x[nd.idx[e]]))
+    H_ref = spla.spsolve(Mo.tocsc(), F @ B)
+    Hd = torch.zeros(nd.ndofs, dtype=torch.float64, device="cuda")
+    est.project(_dev(B), Hd)
+    assert est.stats()["converged"] and _rel(Hd.cpu().numpy(), H_ref) < 1e-8
+    Be = np.concatenate([rt.orient[e] * B[rt.idx[e]] for e in range(ne)])
+    He = np.concatenate([dense_T(nd.curl_orient[e]) @ H_ref[nd.idx[e]] for e in range(ne)])
+    dr, dn = np.arange(ne * rt.P).reshape(ne, rt.P), np.arange(ne * nd.P).reshape(ne, nd.P)
+    eta2 = E.element_errors(qd, rt_i, E.HDIV, dr, np.ones((ne, rt.P)), Be, I3, nd_i, E.HCURL, dn, np.ones((ne, nd.P)), He, I3)
+    ed = torch.zeros(ne, dtype=torch.float64, device="cuda")
+    est.integrate(_dev(B), Hd, ed)
+    assert _rel(ed.cpu().numpy(), eta2) < 1e-7
+    # E = 0.5 w x r: B = w (constant), held exactly by ND_p -> no error
+    w = np.array([0.3, -0.7, 0.5])
+    xw = ts.interpolate(mesh, nd, lambda X: 0.5 * np.cross(w, X))
+    Bw = np.zeros(rt.ndofs)
+    for e in range(ne):
+        Bw[rt.idx[e]] = rt.orient[e] * (C @ (nd.dense_T(e) @ xw[nd.idx[e]]))
+    est.indicator(_dev(Bw), None, 0.0, ed)
+    assert float(ed.abs().max()) < 1e-8 * np.linalg.norm(w)
