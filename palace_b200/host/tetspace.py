@@ -93,6 +93,34 @@ def tet_quadrature_symmetric6():
     return np.array(pts), np.array(w)
 
 
+def tet_quadrature_symmetric8():
+    """A 43-point, degree-8 symmetric rule on the reference tetrahedron (orbits 4 + 4 + 12 + 6 + 12 + 4 + centroid, the centroid
+    weight negative: the structure of Keast's degree-8 rule). The constants solve the moment equations up to degree 8 for this orbit
+    structure (residual 3e-17; exactness is tested in tests/test_tet_cpu.py). Kept as a second degree-8 rule beside the conical
+    tet_quadrature(8): error-type quantities on CURVED elements move at the 1e-4 ... 1e-3 level between rules of one degree
+    (tests/test_cylinder_tet_indicator_golden.py measures exactly that against the reference's stored indicators), eigenvalues at 1e-8.
+    Whether MFEM's order-8 tetrahedron rule is this one cannot be checked here (MFEM is not in /root/reference)."""
+    import itertools
+
+    pts, w = [], []
+
+    def add(orbit, wt):
+        pts.extend(orbit)
+        w.extend([wt] * len(orbit))
+
+    o4 = lambda a: [(a, a, a), (a, a, 1 - 3 * a), (a, 1 - 3 * a, a), (1 - 3 * a, a, a)]
+    o6 = lambda a: [q[:3] for q in sorted(set(itertools.permutations((a, a, 0.5 - a, 0.5 - a))))]
+    o12 = lambda a, b: [q[:3] for q in sorted(set(itertools.permutations((a, a, b, 1 - 2 * a - b))))]
+    add(o4(0.005781950502546093), 0.00016983410907009535)
+    add(o4(0.08210358830838656), 0.001967033313071645)
+    add(o12(0.03660774955326096, 0.1904860419344086), 0.002140519141167885)
+    add(o6(0.050532740018802424), 0.0045796838244578746)
+    add(o12(0.22906653611675284, 0.0356395827889085), 0.005704485808728209)
+    add(o4(0.2068299316088912), 0.014250305821778431)
+    add([(0.25, 0.25, 0.25)], -0.020500188654514428)
+    return np.array(pts), np.array(w)
+
+
 # ------------------------------------------------------------------------------------------------
 # Reference element: dof functionals and shape functions
 # ------------------------------------------------------------------------------------------------

@@ -61,6 +61,21 @@ def test_symmetric_24_point_rule_is_exact_to_degree_6():
     assert abs((w * pts[:, 0] ** 7).sum() - factorial(7) / factorial(10)) > 1e-7  # and no further
 
 
+def test_symmetric_43_point_rule_is_exact_to_degree_8():
+    """A second degree-8 rule (Keast's orbit structure, one negative weight) beside the conical one."""
+    from math import factorial
+
+    pts, w = ts.tet_quadrature_symmetric8()
+    assert len(w) == 43 and (w < 0).sum() == 1 and (pts > 0).all() and (pts.sum(axis=1) < 1).all()
+    for deg in range(9):
+        for a in range(deg + 1):
+            for b in range(deg + 1 - a):
+                c = deg - a - b
+                exact = factorial(a) * factorial(b) * factorial(c) / factorial(a + b + c + 3)
+                assert abs((w * pts[:, 0] ** a * pts[:, 1] ** b * pts[:, 2] ** c).sum() - exact) < 1e-16
+    assert abs((w * pts[:, 0] ** 9).sum() - factorial(9) / factorial(12)) > 1e-9
+
+
 def test_qdata_layout_matches_the_hex_oracle_convention():
     """Same J -> {w detJ, adj(J)^T/detJ column-major} packing as orc_geom_hex_qdata (geom_33_qf.h:9-34):
     an affine map applied to a hex and to a tet must give the same per-point factors."""
