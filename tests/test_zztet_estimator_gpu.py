@@ -144,3 +144,35 @@ def test_curl_flux_estimator_on_higher_order_tetrahedra(b2p_ctx, p):
         Bw[rt.idx[e]] = rt.orient[e] * (C @ (nd.dense_T(e) @ xw[nd.idx[e]]))
     est.indicator(_dev(Bw), None, 0.0, ed)
     assert float(ed.abs().max()) < 1e-8 * np.linalg.norm(w)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_discrete_curl_operator_on_tetrahedra(b2p_ctx, p):
+    """The reference's Curl operator (SpaceOperator::GetCurlMatrix: a DiscreteLinearOperator ND -> RT, assembled like the gradient and
+    the prolongations as an element-dense interpolator, fem/bilinearform.cpp:203-282) through b2p_interp_create_dense: ND side with
+    the curl-oriented restriction, RT side with its signs; against the host layer's global curl and the transposed product."""
+    from palace_b200 import capi
+
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=13)
+    nd = ts.build_nd_tet_space(mesh, p)
+    rt = ts.build_rt_tet_space(mesh, nd, p - 1)
+    C = ts.tet_discrete_curl(p)
+    it = capi.Interp.dense(b2p_ctx, C, nd.idx, nd.ndofs, rt.idx, rt.ndofs, in_curl_orient=nd.curl_orient, out_orient=rt.orient)
+    Cop = capi.Operator.interp(b2p_ctx, it)
+    rng = np.random.default_rng(p)
+    x = rng.standard_normal(nd.ndofs)
+    B_ref = np.zeros(rt.ndofs)
+    for e in range(mesh.ne):
+        B_ref[rt.idx[e]] = rt.orient[e] * (C @ (nd.dense_T(e) @ x[nd.idx[e]]))   # the same value from every element sharing a face
+    y = torch.empty(rt.ndofs, dtype=torch.float64, device="cuda")
+    Cop.mult(_dev(x), y)
+    assert _rel(y.cpu().numpy(), B_ref) < 1e-12
+    # curl of a gradient vanishes: compose with the discrete gradient
+    h1 = ts.build_h1_tet_space(mesh, nd, p)
+    git = capi.Interp.dense(b2p_ctx, ts.tet_discrete_gradient(p), h1.idx, h1.ndofs, nd.idx, nd.ndofs, out_curl_orient=ts.dual_orient(nd))
+    G = capi.Operator.interp(b2p_ctx, git)
+    phi = rng.standard_normal(h1.ndofs)
+    g = torch.empty(nd.ndofs, dtype=torch.float64, device="cuda")
+    G.mult(_dev(phi), g)
+    Cop.mult(g, y)
+    assert float(y.abs().max()) < 1e-11 * float(g.abs().max())
