@@ -176,3 +176,41 @@ def test_discrete_curl_operator_on_tetrahedra(b2p_ctx, p):
     G.mult(_dev(phi), g)
     Cop.mult(g, y)
     assert float(y.abs().max()) < 1e-11 * float(g.abs().max())
+
+
+@pytest.mark.parametrize("p", [1, 2])
+def test_floquet_correction_solver_is_a_flux_projection(b2p_ctx, p):
+    """FloquetCorrSolver (/root/reference/palace/linalg/floquetcorrection.cpp:18-84: y = M_rt^-1 Cross x with Cross the mixed
+    ND -> RT mass of the cross-product matrix [k x], PCG + Jacobi) is the flux projection with the ND space as flux space, RT as
+    smooth space and [k x] as the flux coefficient: b2p_flux_estimator_project. For a constant field E = a the result is the RT
+    interpolant of k x a exactly (constants lie in RT_{p-1} on straight-sided tets)."""
+    from palace_b200 import capi
+
+    mesh = ts.box_tet_mesh((2, 2, 1), (1.0, 0.8, 0.9), jitter=0.2, scramble_seed=17)
+    nd = ts.build_nd_tet_space(mesh, p)
+    rt = ts.build_rt_tet_space(mesh, nd, p - 1)
+    nd_i, _, qpts, qw = ts.nd_tet_tables(p, 2 * p)
+    rt_el = ts.rt_tet_element(p - 1)
+    rt_i = rt_el.tabulate(qpts)
+    qd = ts.geom_qdata(mesh.node_coords(1), mesh.attr, 1, qpts, qw)
+    geom = capi.Geom.general(b2p_ctx, qd)
+    sp_nd = dict(P=nd.P, map_type=capi.MAP_HCURL, interp=nd_i, idx=nd.idx, orient=None, lsize=nd.ndofs, curl_orient=nd.curl_orient)
+    sp_rt = dict(P=rt.P, map_type=capi.MAP_HDIV, interp=rt_i, idx=rt.idx, orient=rt.orient, lsize=rt.ndofs)
+    k = np.array([0.0, 0.3, 0.4])
+    kx = np.array([[0.0, -k[2], k[1]], [k[2], 0.0, -k[0]], [-k[1], k[0], 0.0]])
+    Mrt = capi.vecfe_mass_operator(b2p_ctx, geom, sp_rt)
+    I9 = np.eye(3).ravel()[None]
+    corr = capi.FluxEstimator(b2p_ctx, geom, sp_nd, sp_rt, kx.ravel(order="F")[None], I9, I9, Mrt, tol=1e-13, max_it=5000)
+    a = np.array([0.7, -1.1, 0.4])
+    x = ts.interpolate(mesh, nd, lambda X: a)
+    y = torch.zeros(rt.ndofs, dtype=torch.float64, device="cuda")
+    corr.project(_dev(x), y)
+    assert corr.stats()["converged"]
+    want = np.zeros(rt.ndofs)
+    u = np.cross(k, a)
+    for e in range(mesh.ne):
+        Xe = mesh.verts[mesh.elems[e]]
+        J = np.stack([Xe[1] - Xe[0], Xe[2] - Xe[0], Xe[3] - Xe[0]], axis=1)
+        uhat = np.linalg.det(J) * np.linalg.solve(J, u)
+        want[rt.idx[e]] = rt.orient[e] * (rt_el.dirs @ uhat)
+    assert _rel(y.cpu().numpy(), want) < 1e-9
