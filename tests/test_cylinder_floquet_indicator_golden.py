@@ -1,0 +1,92 @@
+"""End-to-end comparison of the COMPLEX post-processing chain of a Floquet run with the reference's own output (CPU, oracle side;
+slow: B2P_SLOW_TESTS=1, output kept in profiles/r02_floquet_indicator_vs_reference.log): error-indicators.csv of
+examples/cylinder/floquet.json. For each of the 15 complex modes of the Hermitian pencil of test_cylinder_floquet_golden.py:
+    B = -1/(i w) curl E + (1/w) M_rt^-1 ([k x] E, v)      (drivers/eigensolver.cpp:470-482, linalg/floquetcorrection.cpp)
+    eta_K^2 = (grad-flux + curl-flux element errors of the real and of the imaginary parts) * 0.5 / (E_elec + E_mag)
+on ND_4 with its curl-oriented transformations, RT_3, the element-local discrete curl, quadratic tetrahedra. The wave vector lifts
+the degeneracies of the k = 0 problem, so the element distribution itself is comparable: minimum and maximum agree with the stored
+values to 2e-6 and 2e-5, the norm and the mean to 3e-4 (the first two modes form a pair split by 4e-10, inside which the
+reference's eigenvectors are some basis; its projections stop at 1e-6). With the other sign of the correction term the electric and
+magnetic energies of a mode differ at the 1e-3 level instead of agreeing to 2e-7 ... 2e-6."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle import estimator as E
+from palace_b200.host import tetspace as ts
+from tests import common
+from tests.test_cylinder_floquet_golden import cross_matrix, floquet_matrices
+from tests.test_cylinder_tet_golden import FIX, sigma_target, space_and_tables
+from tests.test_zzflux_curl_oriented_gpu import assembled, dense_T
+
+# test/data/regression/ref/cylinder/floquet/error-indicators.csv: Norm, Minimum, Maximum, Mean
+REF = (3.835530770915e-03, 7.714216953117e-05, 3.962052334382e-04, 2.056120601911e-04)
+
+
+@pytest.mark.skipif(os.environ.get("B2P_SLOW_TESTS") != "1", reason="about three minutes of NumPy loops: B2P_SLOW_TESTS=1")
+def test_floquet_error_indicators_against_the_reference():
+    p = int(FIX["order"])
+    mesh, nd, interp, curl, qd = space_and_tables(p)
+    _, _, qpts, _ = ts.nd_tet_tables(p, 2 * p + 2)
+    rt = ts.build_rt_tet_space(mesh, nd, p - 1)
+    rt_i = ts.rt_tet_element(p - 1).tabulate(qpts)
+    ne, eps = mesh.ne, float(FIX["eps_r"])
+    k = FIX["floquet_wave_vector"]
+    Kr, Ki, M = floquet_matrices(nd, interp, curl, qd, k)
+    free = np.setdiff1d(np.arange(nd.ndofs), nd.ess_dofs)
+    nf = free.size
+    Krf, Kif, Mf = Kr[free][:, free], Ki[free][:, free], M[free][:, free]
+    lam2, V2 = common.eigsh_above(sp.bmat([[Krf, -Kif], [Kif, Krf]], format="csc"), sp.block_diag([Mf, Mf], format="csc"), 30,
+                                  sigma_target(), extra=8, vectors=True)
+    I3 = [np.eye(3)] * ne
+    co_r = np.zeros((ne, rt.P, 3), dtype=np.int8)
+    co_r[:, :, 1] = rt.orient
+    rt_args = (rt_i, E.HDIV, rt.idx, co_r, rt.ndofs)
+    nd_args = (interp, E.HCURL, nd.idx, nd.curl_orient, nd.ndofs)
+    Mrt = assembled(qd, *rt_args, *rt_args, I3)
+    F = assembled(qd, *nd_args, *rt_args, I3)                               # ND -> RT mass
+    Fk = assembled(qd, *nd_args, *rt_args, [cross_matrix(k)] * ne)          # ND -> RT mass of [k x] (FloquetCorrSolver's Cross)
+    lu_rt, lu_nd = spla.splu(Mrt.tocsc()), spla.splu(M.tocsc())
+    C = ts.tet_discrete_curl(p)
+    Tn = [dense_T(nd.curl_orient[e]) for e in range(ne)]
+    dr, dn = np.arange(ne * rt.P).reshape(ne, rt.P), np.arange(ne * nd.P).reshape(ne, nd.P)
+    onr, onn = np.ones((ne, rt.P)), np.ones((ne, nd.P))
+    se, ise = [np.sqrt(eps) * np.eye(3)] * ne, [np.eye(3) / np.sqrt(eps)] * ne
+
+    def curl_dofs(v):
+        B = np.zeros(rt.ndofs)
+        for e in range(ne):
+            B[rt.idx[e]] = rt.orient[e] * (C @ (Tn[e] @ v[nd.idx[e]]))
+        return B
+
+    def element_errors(v, D, Bv, H):
+        ve = np.concatenate([Tn[e] @ v[nd.idx[e]] for e in range(ne)])
+        He = np.concatenate([Tn[e] @ H[nd.idx[e]] for e in range(ne)])
+        Be = np.concatenate([rt.orient[e] * Bv[rt.idx[e]] for e in range(ne)])
+        De = np.concatenate([rt.orient[e] * D[rt.idx[e]] for e in range(ne)])
+        return (E.element_errors(qd, interp, E.HCURL, dn, onn, ve, se, rt_i, E.HDIV, dr, onr, De, ise)
+                + E.element_errors(qd, rt_i, E.HDIV, dr, onr, Be, I3, interp, E.HCURL, dn, onn, He, I3))
+
+    acc = np.zeros(ne)
+    order = np.argsort(lam2)
+    for j in range(15):
+        v2 = V2[:, order[2 * j]]
+        z = np.zeros(nd.ndofs, dtype=complex)
+        z[free] = v2[:nf] + 1j * v2[nf:]
+        w = np.sqrt(lam2[order[2 * j]] / eps)
+        B = (1j / w) * (curl_dofs(z.real) + 1j * curl_dofs(z.imag)) + (1.0 / w) * (lu_rt.solve(Fk @ z.real) + 1j * lu_rt.solve(Fk @ z.imag))
+        Eel, Emag = 0.5 * eps * np.real(np.conj(z) @ (M @ z)), 0.5 * np.real(np.conj(B) @ (Mrt @ B))
+        assert abs(Eel / Emag - 1) < 1e-5                                   # (the RT projection of k x E loses up to 2e-6 at this order)
+        tot = np.zeros(ne)
+        for part in (np.real, np.imag):
+            v, Bv = np.ascontiguousarray(part(z)), np.ascontiguousarray(part(B))
+            tot += element_errors(v, lu_rt.solve(eps * (F @ v)), Bv, lu_nd.solve(F.T @ Bv))
+        acc += 0.5 / (Eel + Emag) * tot
+    e_ = np.sqrt(acc / 15)
+    got = (np.linalg.norm(e_), e_.min(), e_.max(), e_.mean())
+    print("Norm, Min, Max, Mean:", *got, " reference:", *REF)
+    assert abs(got[0] / REF[0] - 1) < 1e-3 and abs(got[3] / REF[3] - 1) < 1e-3
+    assert abs(got[1] / REF[1] - 1) < 1e-4 and abs(got[2] / REF[2] - 1) < 1e-4
