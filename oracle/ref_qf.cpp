@@ -3,6 +3,7 @@
 //   palace/fem/qfunctions/33/{geom,hdiv,hcurl,hdivmass,hdiv_build,hcurl_build,hdivmass_build}_33_qf.h
 //   palace/fem/qfunctions/apply/apply_33_qf.h
 //   palace/fem/qfunctions/32/{geom,hcurl}_32_qf.h   (boundary integrators)
+//   palace/fem/qfunctions/31/{geom,hcurl}_31_qf.h   (line elements in 3-D: boundaries of the wave ports' 2-D submeshes)
 //   palace/fem/qfunctions/33/{hcurlhdiv,hcurlhdiv_error}_33_qf.h   (mixed curl / weak curl integrators, flux error estimators)
 // behind the minimal libCEED macro shim below. Used only to pin oracle.cpp's restatement of the
 // pointwise arithmetic (tests/test_oracle_ref.py). The libCEED operator/basis/restriction layer and
@@ -24,6 +25,9 @@ typedef int CeedInt;
 // boundary (2-D elements embedded in 3-D) geometry factors and the H(curl) mass QFunction
 #include "fem/qfunctions/32/geom_32_qf.h"
 #include "fem/qfunctions/32/hcurl_32_qf.h"
+// 1-D elements embedded in 3-D
+#include "fem/qfunctions/31/geom_31_qf.h"
+#include "fem/qfunctions/31/hcurl_31_qf.h"
 // scalar curl of a 2-D element (boundary curl-curl: integ/curlcurl.cpp:54-60, case 32 -> f_apply_l2_1)
 #include "fem/qfunctions/1/l2_1_qf.h"
 // mixed H(curl) / H(div) mass (MixedVectorCurl / MixedVectorWeakCurl integrators, FluxProjector) and the element error integrands
@@ -70,6 +74,19 @@ int ref_apply_hcurl_32(void *ctx, int Q, const double *qdata, const double *u, d
   const double *in[2] = {qdata, u};
   double *out[1] = {v};
   return f_apply_hcurl_32(ctx, Q, in, out);
+}
+// in = {attr[Q], qw[Q], J[3][Q]} (geom_31_qf.h:12): qdata[5][Q] = {attr, w |J|, (adj(J)^T / |J|)[3]}
+int ref_build_geom_factor_31(int Q, const double *attr, const double *qw, const double *J, double *qdata)
+{
+  const double *in[3] = {attr, qw, J};
+  double *out[1] = {qdata};
+  return f_build_geom_factor_31(nullptr, Q, in, out);
+}
+int ref_apply_hcurl_31(void *ctx, int Q, const double *qdata, const double *u, double *v)
+{
+  const double *in[2] = {qdata, u};
+  double *out[1] = {v};
+  return f_apply_hcurl_31(ctx, Q, in, out);
 }
 int ref_build_hcurl_33(void *ctx, int Q, const double *qdata, double *qd)
 {

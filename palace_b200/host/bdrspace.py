@@ -31,6 +31,24 @@ def geom32_qdata(attr, qw, J):
     return np.concatenate([np.asarray(attr, dtype=np.float64)[None], (qw * d)[None], adj / d], axis=0)
 
 
+def geom31_qdata(attr, qw, J):
+    """Restatement of f_build_geom_factor_31 (geom_31_qf.h:9-30 with AdjJt31, utils_31_qf.h:20-31): the tangent J[3][Q] of a line
+    element in 3-D -> qdata[5][Q] = {attr, w |J|, adj(J)^T / |J| = J / |J|^2}, |J| the length element."""
+    J = np.asarray(J, dtype=np.float64)
+    d = np.sqrt(J[0] ** 2 + J[1] ** 2 + J[2] ** 2)
+    return np.concatenate([np.asarray(attr, dtype=np.float64)[None], (qw * d)[None], J / d / d], axis=0)
+
+
+def pad31_to_33(qd5):
+    """qdata[..., 5, Q] of a line element -> the [..., 11, Q] layout of the 3-D operators: second and third columns zero. With the
+    1-component field padded to (u, 0, 0) the 3-D H(curl) mass map is f_apply_hcurl_31 (hcurl_31_qf.h:12-31), so an edge block
+    enters the dense-basis operator like a boundary-face block does."""
+    qd5 = np.asarray(qd5)
+    out = np.zeros(qd5.shape[:-2] + (11, qd5.shape[-1]))
+    out[..., :5, :] = qd5
+    return out
+
+
 def pad32_to_33(qd8):
     """qdata[..., 8, Q] of a boundary element -> the [..., 11, Q] layout of the 3-D operators: third column zero."""
     qd8 = np.asarray(qd8)

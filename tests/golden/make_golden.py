@@ -89,6 +89,31 @@ def main32():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main31():
+    """tests/golden/qf31_golden.npz: the reference's line-element (dim 1 in space_dim 3) geometry-factor and H(curl) mass QFunctions
+    (qfunctions/31/geom_31_qf.h, hcurl_31_qf.h) on seeded inputs."""
+    ref = O.ref()
+    assert ref is not None, "oracle/_ref not built (needs /root/reference)"
+    rng = np.random.default_rng(20260927)
+    Q = 48
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    J = np.ascontiguousarray(rng.random((3, Q)) - 0.5) + np.array([0.9, 0.0, 0.0])[:, None]
+    n_attr = 4
+    attr = (1 + rng.integers(0, n_attr, size=Q)).astype(np.float64)
+    qw = 0.1 + rng.random(Q)
+    qd = np.empty((5, Q))
+    assert ref.ref_build_geom_factor_31(Q, p(attr), p(qw), p(J), p(qd)) == 0
+    am, mc = cf.test_suite_coefficient(n_attr, "matrix")
+    mc = mc + 0.05 * rng.random(mc.shape)
+    ctx = cf.coeff_ctx(am, mc, a=0.7)
+    u = np.ascontiguousarray(rng.random((1, Q)) - 0.5)
+    v = np.empty((1, Q))
+    assert ref.ref_apply_hcurl_31(p(ctx), Q, p(qd), p(u), p(v)) == 0
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "qf31_golden.npz")
+    np.savez_compressed(path, J=J, attr=attr, qw=qw, qdata=qd, ctx=ctx, u=u, v=v)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main_mixed():
     """tests/golden/qf_mixed_golden.npz: the reference's mixed H(curl) / H(div) QFunctions (qfunctions/33/hcurlhdiv_33_qf.h:
     MixedVectorWeakCurl / MixedVectorCurl integrators and the FluxProjector's mixed mass) and the element error integrands of
@@ -148,6 +173,8 @@ def main32curl():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "32":
         main32()
+    elif len(sys.argv) > 1 and sys.argv[1] == "31":
+        main31()
     elif len(sys.argv) > 1 and sys.argv[1] == "32curl":
         main32curl()
     elif len(sys.argv) > 1 and sys.argv[1] == "mixed":

@@ -34,6 +34,34 @@ def test_padded_3d_mass_map_is_the_reference_hcurl_32():
     assert _rel(v[:2], G["v"]) < 2e-15 * 10 and np.abs(v[2]).max() == 0.0
 
 
+G31 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qf31_golden.npz"))
+
+
+def test_line_elements_in_3d_are_the_padded_3d_map_too():
+    """qfunctions/31 (1-D elements in 3-D space: the boundary edges of the wave ports' 2-D submeshes, integ/vecfemass.cpp case 31):
+    the restated geometry factor against the reference's golden q-data, and f_apply_hcurl_31 = the 3-D H(curl) mass map on
+    [A | 0 | 0] and (u, 0, 0) (tests/golden/qf31_golden.npz, generator tests/golden/make_golden.py 31). On a straight edge with a
+    constant field the quadratic form is the line integral of (E . t)^2 t^T C t."""
+    assert _rel(bs.geom31_qdata(G31["attr"], G31["qw"], G31["J"]), G31["qdata"]) < 1e-13
+    Q = G31["u"].shape[1]
+    u3 = np.concatenate([G31["u"], np.zeros((2, Q))], axis=0)
+    v, _ = O.apply_D(O.ND_MASS, np.ascontiguousarray(G31["ctx"]), np.ascontiguousarray(bs.pad31_to_33(G31["qdata"])),
+                     np.ascontiguousarray(u3), None)
+    assert _rel(v[:1], G31["v"]) < 2e-14 and np.abs(v[1:]).max() == 0.0
+    a, b = np.array([0.2, -0.1, 0.4]), np.array([1.1, 0.7, -0.3])
+    Cm = np.array([[2.0, 0.3, 0.1], [0.3, 1.5, -0.2], [0.1, -0.2, 1.0]])
+    Ev = np.array([0.5, -1.2, 0.8])
+    x, w = np.polynomial.legendre.leggauss(3)
+    t = np.repeat((b - a)[:, None], 3, axis=1)
+    qd = bs.pad31_to_33(bs.geom31_qdata(np.ones(3), 0.5 * w, t))
+    ut = np.zeros((3, 3))
+    ut[0] = Ev @ (b - a)                                        # covariant component of the constant field
+    ctx = cf.coeff_ctx(np.zeros(1, dtype=int), Cm[None], a=1.0)
+    v, _ = O.apply_D(O.ND_MASS, ctx, np.ascontiguousarray(qd), ut, None)
+    th = (b - a) / np.linalg.norm(b - a)
+    assert abs((ut * v).sum() - np.linalg.norm(b - a) * (Ev @ th) ** 2 * (th @ Cm @ th)) < 1e-13
+
+
 @pytest.mark.skipif(O.ref() is None, reason="oracle/_ref not built (no /root/reference on this box)")
 def test_against_compiled_reference_32_headers():
     import ctypes as C
