@@ -12,7 +12,7 @@
 //
 // PARITY PINNING: the pointwise D and geometry-factor arithmetic is pinned against the
 // reference's own QFunction headers compiled from /root/reference (oracle/_ref, see ref_qf.cpp and
-// tests/test_oracle_ref.py). The element tables (MFEM ND_HexahedronElement, un-vendored, pinned
+// tests/test_oracle_golden.py, tests/test_bdr_cpu.py). The element tables (MFEM ND_HexahedronElement, un-vendored, pinned
 // tag d9d6526c) are a restatement from the published element definition: "parity unpinned" at
 // the MFEM boundary; pinned only through operator identities and analytic cavity eigenvalues.
 #include <cstdint>

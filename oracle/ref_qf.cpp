@@ -6,7 +6,7 @@
 //   palace/fem/qfunctions/31/{geom,hcurl}_31_qf.h   (line elements in 3-D: boundaries of the wave ports' 2-D submeshes)
 //   palace/fem/qfunctions/33/{hcurlhdiv,hcurlhdiv_error}_33_qf.h   (mixed curl / weak curl integrators, flux error estimators)
 // behind the minimal libCEED macro shim below. Used only to pin oracle.cpp's restatement of the
-// pointwise arithmetic (tests/test_oracle_ref.py). The libCEED operator/basis/restriction layer and
+// pointwise arithmetic (tests/test_oracle_golden.py, tests/test_bdr_cpu.py). The libCEED operator/basis/restriction layer and
 // MFEM are un-vendored, so this is the only part of the reference path that compiles here.
 #define CEED_QFUNCTION(name) static inline int name
 #define CEED_QFUNCTION_HELPER static inline
