@@ -142,3 +142,36 @@ def test_error_indicators_of_the_spheres_example(spheres):
     rel = [g / r - 1 for g, r in zip(got, IND_REF)]
     print("error indicators (norm, min, max, mean):", got, "rel. to the reference's error-indicators.csv:", rel)
     assert abs(rel[0]) < 1e-6 and abs(rel[3]) < 1e-6 and abs(rel[1]) < 5e-4 and abs(rel[2]) < 1e-4
+
+
+@pytest.mark.skipif(not os.path.exists(MESH), reason="needs the reference's example mesh")
+def test_probe_field_of_the_spheres_example(spheres):
+    """probe-E.csv: E = -grad V at (-1.49, 0, 0) cm, "just above the surface of the smaller sphere", for both terminals. The point is
+    located in its curved cubic tetrahedron by Newton's method on the order-3 geometry map, E = -J^-T grad_ref V there; volts per metre
+    are sqrt(Z0) / L0 times the value in mesh units (utils/units.hpp:27-34,115-117: E_c = H_c Z0 with H_c^2 Z0 L_c^2 = 1 W, and one
+    nondimensional length is L_c). The large component agrees to 8e-8, the vector to 5e-7 of its length."""
+    m, h1, p = spheres["m"], spheres["h1"], spheres["p"]
+    ref = np.array([[+2.337300901858e+03, +1.334018133064e+01, -1.974701031155e+01],
+                    [-1.587529647745e+03, -1.151288542522e+01, +1.802818191385e+01]])
+    x0, order = np.array([-1.49, 0.0, 0.0]), m.order
+    expo = [(a, b, c) for c in range(order + 1) for b in range(order + 1 - c) for a in range(order + 1 - b - c)]
+    vand = lambda X: np.stack([X[:, 0] ** a * X[:, 1] ** b * X[:, 2] ** c for (a, b, c) in expo], axis=1)
+    Vinv = np.linalg.inv(vand(ts.tet_lattice(order)))                # nodal basis of the geometry: N(xi) = mono(xi) Vinv
+    found = None
+    for e in np.argsort(np.linalg.norm(m.xe.mean(axis=2) - x0, axis=1))[:40]:
+        xi = np.full(3, 0.25)
+        for _ in range(30):
+            J = m.xe[e] @ ts._lagrange_tet_grad(order, xi[None])[:, 0, :]
+            xi = xi - np.linalg.solve(J, m.xe[e] @ (vand(xi[None]) @ Vinv)[0] - x0)
+        if np.linalg.norm(m.xe[e] @ (vand(xi[None]) @ Vinv)[0] - x0) < 1e-12 and xi.min() > -1e-10 and xi.sum() < 1 + 1e-10:
+            found = (e, xi)
+            break
+    assert found is not None
+    e, xi = found
+    J = m.xe[e] @ ts._lagrange_tet_grad(order, xi[None])[:, 0, :]
+    _, grad = ts.h1_tet_element(p).tabulate(xi[None])
+    mu0, c0, L0 = 1.25663706127e-6, 299792458.0, 1.0e-2
+    for k, x in enumerate(spheres["V"]):
+        Ev = -np.linalg.solve(J.T, grad[:, 0, :] @ x[h1.idx[e]]) * np.sqrt(mu0 * c0) / L0
+        print("probe E (V/m), terminal", k + 1, Ev, "reference", ref[k])
+        assert abs(Ev[0] / ref[k, 0] - 1) < 5e-7 and np.linalg.norm(Ev - ref[k]) < 2e-6 * np.linalg.norm(ref[k])
