@@ -175,3 +175,49 @@ def test_probe_field_of_the_spheres_example(spheres):
         Ev = -np.linalg.solve(J.T, grad[:, 0, :] @ x[h1.idx[e]]) * np.sqrt(mu0 * c0) / L0
         print("probe E (V/m), terminal", k + 1, Ev, "reference", ref[k])
         assert abs(Ev[0] / ref[k, 0] - 1) < 5e-7 and np.linalg.norm(Ev - ref[k]) < 2e-6 * np.linalg.norm(ref[k])
+
+
+@pytest.mark.skipif(not os.path.exists(MESH), reason="needs the reference's example mesh")
+def test_surface_charges_of_the_spheres_example(spheres):
+    """surface-F.csv: the electric flux through each sphere for each terminal's field, Q = int eps E . n dS with n pointing into the
+    domain, integrated on the CURVED boundary triangles -- each as a face of its parent cubic tetrahedron: points on the reference
+    face, n dS = (J e_s x J e_t) w, E = -J^-T grad_ref V of the parent (the construction of host/tetbdr.py with the cubic geometry
+    map). Coulombs are eps0 sqrt(Z0) L0 times the mesh-unit value (utils/units.hpp:115-121). All four entries agree to 4e-7 (they
+    are 1.7 % away from C V, which is why the reference prefers the energy formula; the comparison is of the same discrete field)."""
+    from palace_b200.host import tetbdr as tb
+
+    m, h1, p = spheres["m"], spheres["h1"], spheres["p"]
+    ref = np.array([[+2.361114386696e-11, -9.140234297242e-12], [-9.102953898712e-12, +4.734636562291e-11]])
+    pts2, w2 = tb.tri_quadrature(10)
+    face_of = {}
+    for e in range(m.ne):
+        v = m.elems[e][:4]
+        for fc in range(4):
+            face_of[tuple(sorted(int(v[t]) for t in range(4) if t != fc))] = (e, fc)
+    h1el = ts.h1_tet_element(p)
+    out = np.zeros((2, 2))
+    for s_i, attr in enumerate((3, 4)):
+        byf = {fc: [] for fc in range(4)}
+        for tri in m.bdr_verts[m.bdr_attr == attr]:
+            e, fc = face_of[tuple(sorted(int(x) for x in tri))]
+            byf[fc].append(e)
+        for fc, els in byf.items():
+            if not els:
+                continue
+            els = np.array(els)
+            others = [t for t in range(4) if t != fc]
+            es, et = tb.REF_VERTS[others[1]] - tb.REF_VERTS[others[0]], tb.REF_VERTS[others[2]] - tb.REF_VERTS[others[0]]
+            rpts = tb.REF_VERTS[others[0]][None] + pts2[:, :1] * es[None] + pts2[:, 1:] * et[None]
+            J = np.einsum("ecn,nqd->eqcd", m.xe[els], ts._lagrange_tet_grad(m.order, rpts))
+            nv = np.cross(J @ es, J @ et)
+            X = m.verts[m.elems[els][:, :4]]
+            nv *= -np.sign(np.einsum("eqc,ec->eq", nv, X[:, others].mean(axis=1) - X[:, fc]))[..., None]   # towards the parent: into the domain
+            _, grad = h1el.tabulate(rpts)
+            for k, x in enumerate(spheres["V"]):
+                g = np.einsum("dqi,ei->eqd", grad, x[h1.idx[els]])
+                Eph = -np.einsum("eqdc,eqd->eqc", np.linalg.inv(J), g)
+                out[k, s_i] += np.einsum("eqc,eqc,q->", Eph, nv, w2)
+    mu0, c0, L0 = 1.25663706127e-6, 299792458.0, 1.0e-2
+    Qs = out * np.sqrt(mu0 * c0) * L0 / (mu0 * c0 * c0)
+    print("surface charges (C):", Qs, "rel. to the reference's surface-F.csv:", Qs / ref - 1)
+    assert np.abs(Qs / ref - 1).max() < 2e-6
