@@ -39,6 +39,13 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
 
 
+def test_reference_arm_runs_on_rank_zero_only():
+    """Under torchrun (N > 1) rank 0 alone times the CPU implementation; the other ranks exit 0 without work or output."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--n", "4"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
 def test_experiment_lines_precede_the_headline_line():
     """Every side measurement is its own short JSON line {"experiment": ...} and the headline is the LAST line, so that no
     experiment can fall off a log tail and no headline key can be pushed out by them (VERDICT r01, weak #9)."""
