@@ -8,8 +8,8 @@ the degeneracies of the k = 0 problem, so the element distribution itself is com
 values to 2e-6 and 2e-5, the norm and the mean to 3e-4 (the first two modes form a pair split by 4e-10, inside which the
 reference's eigenvectors are some basis; its projections stop at 1e-6). The magnetic energy of a mode falls short of the electric one
 by what the RT projection of k x E loses, 1e-9 ... 4e-6 depending on the mode: those 15 numbers agree with the reference's stored
-domain-E.csv mode by mode (1e-9 + 2e-3 relative; -4.003e-6 against -3.999e-6 for mode 10), once the 8.0006e-8 that all of its eigenmode
-outputs carry is taken off. With the other sign of the correction term the two energies differ at the 1e-3 level."""
+domain-E.csv mode by mode (1e-9 + 2e-3 relative; -4.003e-6 against -3.999e-6 for mode 10), once the tan^2(delta) / 2 = 8.0e-8 of its lossy
+material is taken off (this test computes with the real permittivity). With the other sign of the correction term the two energies differ at the 1e-3 level."""
 import os
 
 import numpy as np
@@ -28,11 +28,12 @@ from tests.test_zzflux_curl_oriented_gpu import assembled, dense_T
 REF = (3.835530770915e-03, 7.714216953117e-05, 3.962052334382e-04, 2.056120601911e-04)
 
 
-# test/data/regression/ref/cylinder/floquet/domain-E.csv: E_mag / E_elec - 1 of the 15 modes, minus the 8.0006e-8 that every mode of
-# every eigenmode example of the reference shows (cavity_pec, waveguide: 7.97e-8 ... 8.02e-8, a property of its unit constants)
+# test/data/regression/ref/cylinder/floquet/domain-E.csv: E_mag / E_elec - 1 of the 15 modes, minus the 8.0e-8 that every mode of every
+# eigenmode example on this material shows (cavity_pec, waveguide: 7.97e-8 ... 8.02e-8): the loss tangent 4e-4 makes omega^2 complex,
+# |omega|^2 = omega_0^2 / sqrt(1 + tan^2 d), and E_elec is taken with the real permittivity: E_mag / E_elec = 1 + tan^2 d / 2 = 1 + 8.0e-8
 REF_DEFECT = np.array([7.86062391e-08, 7.89969541e-08, 7.76243640e-08, -7.73664002e-07, -1.56867990e-06, -1.21528882e-06, 4.94451859e-08,
                        4.93033863e-08, -7.34464278e-07, -3.91892443e-06, -4.12801084e-08, -4.11979391e-08, -3.62957853e-08,
-                       -1.18609713e-07, -6.64410111e-08]) - 8.0006e-8
+                       -1.18609713e-07, -6.64410111e-08]) - 0.5 * 0.0004 ** 2
 
 
 @pytest.mark.skipif(os.environ.get("B2P_SLOW_TESTS") != "1", reason="about three minutes of NumPy loops: B2P_SLOW_TESTS=1")
